@@ -1,0 +1,211 @@
+"""ctypes binding of libbfx.so (the C-ABI declared in include/bfx.h).
+
+There is NO CPU fallback: importing this module fails loudly when the shared
+library is missing, and every compute call fails with ``BfxError`` when no CUDA
+device is present.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbfx.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build the CUDA extension first (python -m dolfinx_b200.build). "
+        "dolfinx_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+OK = 0
+ERR_NOT_IN_SPARSITY = 3
+ERR_NO_DEVICE = 6
+
+# kernel ids (include/bfx.h)
+K_LAPLACE_P1_TRI_A = 0
+K_SOURCE_P1_TRI_L = 1
+K_MASS_COEFF_P1_TRI_A = 2
+K_LOAD_COEFF_P1_TRI_L = 3
+K_FACET_MASS_P1_TRI_A = 4
+K_FACET_CONST_P1_TRI_L = 5
+K_POISSON_P1_TET_A = 6
+K_LOAD_P1_TET_L = 7
+K_POISSON_P2_TET_A = 8
+K_LOAD_P2_TET_L = 9
+K_ELASTICITY_Q1_HEX_A = 10
+K_LOAD_Q1_HEX_L = 11
+K_FACET_LOAD_P1_TET_L = 12
+K_FACET_MASS_P1_TET_A = 13
+
+ASM_ATOMIC, ASM_GATHER = 0, 1
+VALUES_ADD, VALUES_OVERWRITE = 0, 1
+SPMV_FULL, SPMV_DIAG, SPMV_OFFDIAG = 0, 1, 2
+
+
+class BfxError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nx", "nd", "bs", "rank", "w_size", "c_size", "facet")]
+
+
+class CoeffSrc(C.Structure):
+    _fields_ = [("values_dev", C.c_void_p), ("dofmap_dev", C.c_void_p), ("nd", C.c_int), ("bs", C.c_int), ("offset", C.c_int)]
+
+
+class Coeffs(C.Structure):
+    _fields_ = [("packed_dev", C.c_void_p), ("cstride", C.c_int), ("n_fused", C.c_int), ("fused", CoeffSrc * 4)]
+
+
+vp, i32, i64, f64, ci = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_int
+pvp = C.POINTER(C.c_void_p)
+
+_SIGS = {
+    "bfx_version": ([], ci),
+    "bfx_device_count": ([C.POINTER(ci)], ci),
+    "bfx_set_device": ([ci], ci),
+    "bfx_malloc": ([pvp, C.c_size_t], ci),
+    "bfx_free": ([vp], ci),
+    "bfx_memcpy": ([vp, vp, C.c_size_t, vp], ci),
+    "bfx_memset": ([vp, ci, C.c_size_t, vp], ci),
+    "bfx_stream_sync": ([vp], ci),
+    "bfx_host_alloc": ([pvp, C.c_size_t], ci),
+    "bfx_host_free": ([vp], ci),
+    "bfx_kernel_info": ([ci, C.POINTER(KernelInfo)], ci),
+    "bfx_csr_create": ([pvp, i32, i32, vp, vp, vp, ci, ci], ci),
+    "bfx_csr_destroy": ([vp], ci),
+    "bfx_csr_nnz": ([vp], i64),
+    "bfx_csr_get_structure": ([vp, vp, vp, vp], ci),
+    "bfx_csr_device_ptrs": ([vp, pvp, pvp, pvp], ci),
+    "bfx_sparsity_build": ([pvp, i32, i32, i32, vp, ci, vp, ci, vp, i64, vp, vp, i64, ci, ci, vp], ci),
+    "bfx_sparsity_ghost_rows": ([i32, i32, vp, ci, vp, ci, vp, i64, vp, vp, vp], ci),
+    "bfx_csr_insert": ([vp, vp, ci, ci, ci, vp, vp, ci, vp, ci, ci, vp], ci),
+    "bfx_csr_set_diagonal": ([vp, vp, vp, i64, f64, vp], ci),
+    "bfx_csr_squared_norm": ([vp, vp, C.POINTER(f64), vp], ci),
+    "bfx_spmv": ([vp, vp, vp, vp, ci, vp], ci),
+    "bfx_spmvT": ([vp, vp, vp, vp, ci, vp], ci),
+    "bfx_asm_create": ([pvp, vp, vp, ci, vp, ci, vp, ci, i64, vp, i64, i32, ci, vp], ci),
+    "bfx_asm_destroy": ([vp], ci),
+    "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
+    "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),
+    "bfx_lift_bc_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp, vp, vp, f64, vp], ci),
+    "bfx_assemble_matrix_facets": ([vp, ci, vp, vp, i64, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),
+    "bfx_assemble_vector_facets": ([vp, ci, vp, vp, i64, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),
+    "bfx_pack_coefficient": ([vp, ci, ci, vp, vp, ci, ci, vp, vp, i64, vp], ci),
+    "bfx_assemble_matrix_cells_host": ([vp, ci, vp, i64, vp, vp, i64, vp, i64, ci, C.POINTER(f64), ci, vp, ci, vp], ci),
+    "bfx_bc_mark": ([vp, vp, i64, vp], ci),
+    "bfx_bc_set": ([vp, i32, vp, vp, i64, vp, ci, ci, vp, f64, vp], ci),
+    "bfx_dot": ([i64, vp, vp, C.POINTER(f64), vp], ci),
+    "bfx_norm": ([i64, vp, ci, C.POINTER(f64), vp], ci),
+    "bfx_axpy": ([i64, f64, vp, vp, vp], ci),
+    "bfx_comm_unique_id": ([C.c_char_p], ci),
+    "bfx_comm_create": ([pvp, C.c_char_p, ci, ci], ci),
+    "bfx_comm_destroy": ([vp], ci),
+    "bfx_comm_rank": ([vp, C.POINTER(ci), C.POINTER(ci)], ci),
+    "bfx_comm_allreduce": ([vp, vp, i64, ci, vp], ci),
+    "bfx_scatter_create": ([pvp, vp, vp, i64, vp, i64, vp, vp, vp, ci, vp, vp, vp, ci], ci),
+    "bfx_scatter_destroy": ([vp], ci),
+    "bfx_scatter_fwd_begin": ([vp, vp, vp], ci),
+    "bfx_scatter_fwd_end": ([vp, vp, i64, vp], ci),
+    "bfx_scatter_rev_begin": ([vp, vp, i64, vp], ci),
+    "bfx_scatter_rev_end": ([vp, vp, ci, vp], ci),
+    "bfx_csr_scatter_create": ([pvp, vp, vp, vp, i32, vp, vp, ci, vp, vp, ci, vp], ci),
+    "bfx_csr_scatter_destroy": ([vp], ci),
+    "bfx_csr_scatter_rev_begin": ([vp, vp, vp], ci),
+    "bfx_csr_scatter_rev_end": ([vp, vp, vp], ci),
+    "bfx_host_first_touch_i32": ([vp, i64, i32, vp], ci),
+    "bfx_host_first_touch_i64": ([vp, i64, i64, vp], ci),
+}
+
+EXPORTS = sorted(_SIGS) + ["bfx_last_error", "bfx_status_string"]
+
+for _name, (_args, _res) in _SIGS.items():
+    _f = getattr(lib, _name)
+    _f.argtypes = _args
+    _f.restype = _res
+lib.bfx_last_error.restype = C.c_char_p
+lib.bfx_status_string.restype = C.c_char_p
+lib.bfx_status_string.argtypes = [ci]
+
+
+def check(status: int):
+    if status != OK:
+        msg = lib.bfx_last_error().decode(errors="replace")
+        raise BfxError(status, msg or lib.bfx_status_string(status).decode())
+
+
+def np_ptr(a: np.ndarray):
+    """Host pointer of a contiguous numpy array (kept alive by the caller)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def dptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return np_ptr(t)
+    assert t.is_contiguous()
+    return t.data_ptr()
+
+
+def current_stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else None
+
+
+def host_first_touch(flat: np.ndarray, ndofs: int) -> np.ndarray:
+    flat = np.ascontiguousarray(flat)
+    if flat.dtype == np.int32:
+        out = np.empty(ndofs, dtype=np.int32)
+        check(lib.bfx_host_first_touch_i32(flat.ctypes.data, flat.size, ndofs, out.ctypes.data))
+    else:
+        flat = flat.astype(np.int64, copy=False)
+        out = np.empty(ndofs, dtype=np.int64)
+        check(lib.bfx_host_first_touch_i64(flat.ctypes.data, flat.size, ndofs, out.ctypes.data))
+    return out
+
+
+def kernel_info(kernel_id: int) -> KernelInfo:
+    ki = KernelInfo()
+    check(lib.bfx_kernel_info(kernel_id, C.byref(ki)))
+    return ki
+
+
+def make_coeffs(packed=None, cstride=0, fused=None, offset=0):
+    """Build a bfx_coeffs_t. ``fused`` = (values tensor, dofmap tensor, nd, bs)."""
+    c = Coeffs()
+    if packed is not None:
+        c.packed_dev = dptr(packed)
+        c.cstride = cstride
+        c.n_fused = 1
+        c.fused[0].offset = offset
+    elif fused is not None:
+        v, dm, nd, bs = fused
+        c.n_fused = 1
+        c.fused[0].values_dev = dptr(v)
+        c.fused[0].dofmap_dev = dptr(dm)
+        c.fused[0].nd = nd
+        c.fused[0].bs = bs
+        c.fused[0].offset = offset
+    return c
+
+
+def constants_array(constants):
+    if constants is None or len(constants) == 0:
+        return None, 0
+    arr = (f64 * len(constants))(*[float(v) for v in constants])
+    return arr, len(constants)

@@ -1,0 +1,967 @@
+// Cell / exterior-facet assembly on device: fem::impl::assemble_cells_matrix<LiftingMode>
+// (fem/assemble_matrix_impl.h:92-200), assemble_entities (:264-379), assemble_cells (vector,
+// fem/assemble_vector_impl.h:72-116), assemble_entities (:157-215), lift_bc (:361-414),
+// pack_coefficient_entity (fem/pack.h:121-176) and DirichletBC::mark_dofs/set
+// (fem/DirichletBC.h:495-601).
+#include "assemble.cuh"
+#include "elements.cuh"
+#include <vector>
+
+using namespace bfx;
+
+namespace
+{
+// ---------------------------------------------------------------------------------------------
+// shared device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ cols, int64_t b, int64_t e, int32_t c)
+{
+  int64_t lo = b, hi = e;
+  while (lo < hi)
+  {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cols[mid] < c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (lo < e && cols[lo] == c) ? lo : -1;
+}
+
+template <int N>
+__device__ __forceinline__ void load_ints(const int32_t* __restrict__ p, int32_t (&out)[N])
+{
+  if constexpr (N % 4 == 0)
+  {
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k)
+    {
+      const int4 v = ldg_stream(reinterpret_cast<const int4*>(p) + k);
+      out[4 * k] = v.x, out[4 * k + 1] = v.y, out[4 * k + 2] = v.z, out[4 * k + 3] = v.w;
+    }
+  }
+  else if constexpr (N % 2 == 0)
+  {
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k)
+    {
+      const int2 v = __ldg(reinterpret_cast<const int2*>(p) + k);
+      out[2 * k] = v.x, out[2 * k + 1] = v.y;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      out[k] = __ldg(p + k);
+  }
+}
+
+// coordinate_dofs gather: x is (N,3) row-major (assemble_matrix_impl.h:146-148)
+template <int NX>
+__device__ __forceinline__ void gather_coords(const double* __restrict__ x, const int32_t (&xd)[NX],
+                                              double (&xc)[NX][3])
+{
+#pragma unroll
+  for (int i = 0; i < NX; ++i)
+  {
+    const double* p = x + 3 * (int64_t)xd[i];
+    xc[i][0] = __ldg(p);
+    xc[i][1] = __ldg(p + 1);
+    xc[i][2] = __ldg(p + 2);
+  }
+}
+
+// Coefficients: packed reference layout, or the fused gather of ONE coefficient whose layout the
+// element fixes at compile time (pack_impl, fem/pack.h:77-103)
+template <class E>
+__device__ __forceinline__ void load_w(const AsmArgs& a, int64_t e, int32_t cell, double* w)
+{
+  if constexpr (E::WSIZE > 0)
+  {
+    if (a.coef.packed)
+    {
+#pragma unroll
+      for (int k = 0; k < E::WSIZE; ++k)
+        w[k] = __ldg(a.coef.packed + e * a.coef.cstride + a.coef.f[0].off + k);
+    }
+    else
+    {
+      const int32_t* dm = a.coef.f[0].dm + (int64_t)cell * E::WND;
+      const double* v = a.coef.f[0].v;
+#pragma unroll
+      for (int i = 0; i < E::WND; ++i)
+      {
+        const int64_t d = __ldg(dm + i);
+#pragma unroll
+        for (int k = 0; k < E::WBS; ++k)
+          w[E::WBS * i + k] = __ldg(v + E::WBS * d + k);
+      }
+    }
+  }
+}
+
+template <typename PosT, int COUNT>
+struct PosRegs
+{
+  static constexpr int BYTES = COUNT * (int)sizeof(PosT);
+  static constexpr int STRIDE = (BYTES + 15) / 16 * 16;
+  uint32_t wds[STRIDE / 4];
+  __device__ __forceinline__ void load(const void* base, int64_t e)
+  {
+    const uint4* p = reinterpret_cast<const uint4*>(static_cast<const char*>(base) + e * STRIDE);
+#pragma unroll
+    for (int k = 0; k < STRIDE / 16; ++k)
+    {
+      const int4 v = ldg_stream(reinterpret_cast<const int4*>(p + k));
+      wds[4 * k] = v.x, wds[4 * k + 1] = v.y, wds[4 * k + 2] = v.z, wds[4 * k + 3] = v.w;
+    }
+  }
+  __device__ __forceinline__ uint32_t get(int t) const
+  {
+    if constexpr (sizeof(PosT) == 1)
+      return (wds[t >> 2] >> ((t & 3) * 8)) & 0xffu;
+    else
+      return (wds[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// generic thread-per-cell matrix kernel.  MODE 0: assemble with bc row/col zeroing into CSR
+// (fp64 RED); MODE 1: lifting (b -= alpha Ae (g - x0) on marked columns).
+// ---------------------------------------------------------------------------------------------
+template <class E, typename PosT, int MODE>
+__global__ void __launch_bounds__(128) k_matrix_cells(const AsmArgs a)
+{
+  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    int32_t cell;
+    int lf = 0;
+    if (a.entities)
+    {
+      cell = a.entities[2 * e];
+      lf = a.entities[2 * e + 1];
+    }
+    else
+      cell = a.cells ? a.cells[e] : (int32_t)e;
+
+    int32_t d0[ND], d1[ND];
+    load_ints<ND>(a.dofmap0 + (int64_t)cell * ND, d0);
+    load_ints<ND>(a.dofmap1 + (int64_t)cell * ND, d1);
+
+    uint32_t m0 = 0, m1 = 0; // bc marker bit per scalar row / column of Ae
+    if (a.bc1)
+    {
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        m1 |= (a.bc1[(int64_t)BS * d1[j / BS] + j % BS] ? 1u : 0u) << j;
+    }
+    if (MODE == 1 && m1 == 0)
+      continue; // has_bc (assemble_matrix_impl.h:27-34,139-143)
+    if (MODE == 0 && a.bc0)
+    {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        m0 |= (a.bc0[(int64_t)BS * d0[i / BS] + i % BS] ? 1u : 0u) << i;
+    }
+
+    int32_t xd[NX];
+    load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
+    double xc[NX][3];
+    gather_coords<NX>(a.x, xd, xc);
+    double w[E::WSIZE > 0 ? E::WSIZE : 1];
+    load_w<E>(a, e, cell, w);
+    typename E::Geo g;
+    E::prepare(g, xc, w, a.constants, lf);
+
+    if constexpr (MODE == 0)
+    {
+      PosRegs<PosT, ND * ND> pos;
+      if (a.pos)
+        pos.load(a.pos, e);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+      {
+        if ((m0 >> i) & 1u)
+          continue;
+        double row[N];
+        E::row(g, i, row);
+        const int32_t r = d0[i / BS];
+        const int64_t rb = a.row_ptr[r];
+        const int64_t re = a.pos ? 0 : a.row_ptr[r + 1];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+        {
+          if ((m1 >> j) & 1u)
+            continue;
+          int64_t p;
+          if (a.pos)
+            p = rb + pos.get((i / BS) * ND + j / BS);
+          else
+          {
+            p = find_col(a.cols, rb, re, d1[j / BS]);
+            if (p < 0)
+            {
+              *a.err = 1;
+              continue;
+            }
+          }
+          red_add(a.values + p * (BS * BS) + (i % BS) * BS + (j % BS), row[j]);
+        }
+      }
+    }
+    else
+    {
+      double dv[N]; // alpha * (g - x0) on marked columns (assemble_vector_impl.h:377-402)
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+      {
+        const int64_t jj = (int64_t)BS * d1[j / BS] + j % BS;
+        dv[j] = ((m1 >> j) & 1u) ? a.alpha * (a.bc_values1[jj] - (a.x0 ? a.x0[jj] : 0.0)) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+      {
+        double row[N];
+        E::row(g, i, row);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          acc = fma(row[j], dv[j], acc);
+        if (acc != 0.0)
+          red_add(a.b + (int64_t)BS * d0[i / BS] + i % BS, -acc);
+      }
+    }
+  }
+}
+
+// generic thread-per-cell vector kernel
+template <class E>
+__global__ void __launch_bounds__(128) k_vector_cells(const AsmArgs a)
+{
+  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    int32_t cell;
+    int lf = 0;
+    if (a.entities)
+    {
+      cell = a.entities[2 * e];
+      lf = a.entities[2 * e + 1];
+    }
+    else
+      cell = a.cells ? a.cells[e] : (int32_t)e;
+    int32_t d0[ND], xd[NX];
+    load_ints<ND>(a.dofmap0 + (int64_t)cell * ND, d0);
+    load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
+    double xc[NX][3];
+    gather_coords<NX>(a.x, xd, xc);
+    double w[E::WSIZE > 0 ? E::WSIZE : 1];
+    load_w<E>(a, e, cell, w);
+    typename E::Geo g;
+    E::prepare(g, xc, w, a.constants, lf);
+    double out[N];
+    E::vec(g, out);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (!E::FACET || out[i] != 0.0)
+        red_add(a.b + (int64_t)BS * d0[i / BS] + i % BS, out[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q1 hexahedron linear elasticity (bs = 3): 64 threads per cell, one per (i, j) node pair.
+// Phase 1: 8 threads per cell evaluate K = J^{-1}, |det J| and the 8 physical gradients at the
+// 2x2x2 Gauss points into shared memory.  Phase 2: thread (i, j) accumulates
+// D[a][b] = sum_q w_q g_i[a] g_j[b] and forms the 3x3 block
+//   A[(i,k),(j,l)] = mu (delta_kl tr D + D[l][k]) + lambda D[k][l]
+// (python/demo/demo_elasticity.py:131-150), then 9 REDs into the bs=3 CSR block.
+// ---------------------------------------------------------------------------------------------
+constexpr int Q1_CELLS = 4;
+
+template <typename PosT, int MODE>
+__global__ void __launch_bounds__(64 * Q1_CELLS) k_elasticity_q1(const AsmArgs a)
+{
+  __shared__ double s_xc[Q1_CELLS][8][3];
+  __shared__ double s_g[Q1_CELLS][8][8][3];
+  __shared__ double s_w[Q1_CELLS][8];
+  __shared__ int32_t s_d0[Q1_CELLS][8], s_d1[Q1_CELLS][8];
+  __shared__ int s_skip[Q1_CELLS];
+
+  const int cl = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const double mu = a.constants[0], lmbda = a.constants[1];
+  for (int64_t e0 = (int64_t)blockIdx.x * Q1_CELLS; e0 < a.n; e0 += (int64_t)gridDim.x * Q1_CELLS)
+  {
+    const int64_t e = e0 + cl;
+    const bool active = e < a.n;
+    int32_t cell = 0;
+    if (active)
+      cell = a.cells ? a.cells[e] : (int32_t)e;
+    if (active && t < 24)
+    {
+      const int node = t / 3, m = t % 3;
+      s_xc[cl][node][m] = a.x[3 * (int64_t)a.x_dofmap[(int64_t)cell * 8 + node] + m];
+    }
+    if (active && t >= 32 && t < 40)
+      s_d0[cl][t - 32] = a.dofmap0[(int64_t)cell * 8 + (t - 32)];
+    if (active && t >= 40 && t < 48)
+      s_d1[cl][t - 40] = a.dofmap1[(int64_t)cell * 8 + (t - 40)];
+    __syncthreads();
+    if (t == 0)
+    {
+      int skip = !active;
+      if (MODE == 1 && active)
+      {
+        int any = 0;
+        for (int j = 0; j < 8; ++j)
+          for (int k = 0; k < 3; ++k)
+            any |= a.bc1[3 * (int64_t)s_d1[cl][j] + k];
+        skip = !any;
+      }
+      s_skip[cl] = skip;
+    }
+    if (active && t < 8)
+    {
+      double xc[8][3];
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          xc[n][m] = s_xc[cl][n][m];
+      const double g0 = 0.5 - 0.28867513459481287, g1 = 0.5 + 0.28867513459481287;
+      const double X[3] = {(t & 1) ? g1 : g0, (t & 2) ? g1 : g0, (t & 4) ? g1 : g0};
+      double K[3][3];
+      const double det = el::HexQ1::jacobian_inverse(xc, X, K);
+      s_w[cl][t] = 0.125 * fabs(det);
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+      {
+        double d[3], phi;
+        el::HexQ1::dphi(n, X, d, phi);
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          s_g[cl][t][n][m] = d[0] * K[0][m] + d[1] * K[1][m] + d[2] * K[2][m];
+      }
+    }
+    __syncthreads();
+    if (!s_skip[cl])
+    {
+      const int i = t >> 3, j = t & 7;
+      double D[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+      {
+        const double wq = s_w[cl][q];
+        const double gi[3] = {s_g[cl][q][i][0], s_g[cl][q][i][1], s_g[cl][q][i][2]};
+        const double gj[3] = {s_g[cl][q][j][0], s_g[cl][q][j][1], s_g[cl][q][j][2]};
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+        {
+          const double wg = wq * gi[p];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            D[p][r] = fma(wg, gj[r], D[p][r]);
+        }
+      }
+      const double tr = D[0][0] + D[1][1] + D[2][2];
+      double A[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+          A[k][l] = mu * ((k == l ? tr : 0.0) + D[l][k]) + lmbda * D[k][l];
+      const int32_t r = s_d0[cl][i], c = s_d1[cl][j];
+      if constexpr (MODE == 0)
+      {
+        int64_t p;
+        const int64_t rb = a.row_ptr[r];
+        if (a.pos)
+          p = rb + static_cast<const PosT*>(a.pos)[e * 64 + t];
+        else
+          p = find_col(a.cols, rb, a.row_ptr[r + 1], c);
+        if (p < 0)
+          *a.err = 1;
+        else
+        {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+          {
+            if (a.bc0 && a.bc0[3 * (int64_t)r + k])
+              continue;
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+            {
+              if (a.bc1 && a.bc1[3 * (int64_t)c + l])
+                continue;
+              red_add(a.values + p * 9 + k * 3 + l, A[k][l]);
+            }
+          }
+        }
+      }
+      else
+      {
+        double dv[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+        {
+          const int64_t jj = 3 * (int64_t)c + l;
+          dv[l] = a.bc1[jj] ? a.alpha * (a.bc_values1[jj] - (a.x0 ? a.x0[jj] : 0.0)) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+          const double acc = A[k][0] * dv[0] + A[k][1] * dv[1] + A[k][2] * dv[2];
+          if (acc != 0.0)
+            red_add(a.b + 3 * (int64_t)r + k, -acc);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan construction: cell -> CSR position map (replaces std::lower_bound of insert_csr)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_max_row_len(int32_t n, const int64_t* __restrict__ row_ptr, int* __restrict__ out)
+{
+  int m = 0;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = max(m, (int)(row_ptr[i + 1] - row_ptr[i]));
+  for (int o = 16; o > 0; o >>= 1)
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(out, m);
+}
+
+template <typename PosT>
+__global__ void k_build_pos(int64_t ncells, const int32_t* __restrict__ cells, const int32_t* __restrict__ dofmap0,
+                            int nd0, const int32_t* __restrict__ dofmap1, int nd1,
+                            const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols, int32_t n_rows,
+                            char* __restrict__ pos, int stride, int* __restrict__ err)
+{
+  const int64_t total = ncells * nd0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t e = t / nd0;
+    const int i = (int)(t - e * nd0);
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    const int32_t r = dofmap0[(int64_t)cell * nd0 + i];
+    PosT* out = reinterpret_cast<PosT*>(pos + e * stride) + (int64_t)i * nd1;
+    if (r < 0 || r >= n_rows)
+    {
+      *err = 2;
+      continue;
+    }
+    const int64_t rb = row_ptr[r], re = row_ptr[r + 1];
+    for (int j = 0; j < nd1; ++j)
+    {
+      const int64_t p = find_col(cols, rb, re, dofmap1[(int64_t)cell * nd1 + j]);
+      if (p < 0)
+      {
+        *err = 1;
+        out[j] = 0;
+      }
+      else
+        out[j] = (PosT)(p - rb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack / bc kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack(double* __restrict__ coeffs, int cstride, int offset, const double* __restrict__ v,
+                       const int32_t* __restrict__ dofmap, int nd, int bs, const int32_t* __restrict__ cells,
+                       const int32_t* __restrict__ entities, int64_t n)
+{
+  const int64_t total = n * nd * bs;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t e = t / (nd * bs);
+    const int rem = (int)(t - e * nd * bs);
+    const int i = rem / bs, k = rem - i * bs;
+    const int32_t cell = entities ? entities[2 * e] : (cells ? cells[e] : (int32_t)e);
+    if (cell < 0)
+      continue;
+    coeffs[e * cstride + offset + bs * i + k] = v[(int64_t)bs * dofmap[(int64_t)cell * nd + i] + k];
+  }
+}
+
+__global__ void k_bc_mark(int8_t* __restrict__ markers, const int32_t* __restrict__ dofs, int64_t n)
+{
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    markers[dofs[t]] = 1;
+}
+
+__global__ void k_bc_set(double* __restrict__ x, int32_t x_size, const int32_t* __restrict__ dofs0,
+                         const int32_t* __restrict__ dofs_g, int64_t n, const double* __restrict__ g, int g_kind,
+                         int bs, const double* __restrict__ x0, double alpha)
+{
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t dof = dofs0[t];
+    if (dof >= x_size)
+      continue; // DirichletBC.h:506-511
+    double v = 0.0;
+    if (alpha != 0.0)
+    {
+      const double gv = g_kind == 0 ? g[dofs_g ? dofs_g[t] : dof] : g[dof % bs];
+      v = x0 ? alpha * (gv - x0[dof]) : alpha * gv;
+    }
+    x[dof] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+template <class E, int MODE>
+int launch_matrix(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
+{
+  if (a.n == 0)
+    return BFX_OK;
+  const unsigned grid = grid_for(a.n, 128, 0);
+  if (P->pos_bytes == 2 && a.pos)
+    k_matrix_cells<E, uint16_t, MODE><<<grid, 128, 0, st>>>(a);
+  else
+    k_matrix_cells<E, uint8_t, MODE><<<grid, 128, 0, st>>>(a);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+template <int MODE>
+int launch_q1(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
+{
+  if (a.n == 0)
+    return BFX_OK;
+  const unsigned grid = grid_for((a.n + Q1_CELLS - 1) / Q1_CELLS, 1, 0);
+  if (P->pos_bytes == 2 && a.pos)
+    k_elasticity_q1<uint16_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
+  else
+    k_elasticity_q1<uint8_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+template <class E>
+int launch_vector(const AsmArgs& a, cudaStream_t st)
+{
+  if (a.n == 0)
+    return BFX_OK;
+  k_vector_cells<E><<<grid_for(a.n, 128, 0), 128, 0, st>>>(a);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+template <int MODE>
+int dispatch_matrix(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st)
+{
+  switch (kernel_id)
+  {
+  case BFX_K_LAPLACE_P1_TRI_A: return launch_matrix<el::LaplaceP1Tri, MODE>(P, a, st);
+  case BFX_K_MASS_COEFF_P1_TRI_A: return launch_matrix<el::MassCoeffP1Tri, MODE>(P, a, st);
+  case BFX_K_FACET_MASS_P1_TRI_A: return launch_matrix<el::FacetMassP1Tri, MODE>(P, a, st);
+  case BFX_K_POISSON_P1_TET_A: return launch_matrix<el::PoissonP1Tet, MODE>(P, a, st);
+  case BFX_K_POISSON_P2_TET_A: return launch_matrix<el::PoissonP2Tet, MODE>(P, a, st);
+  case BFX_K_FACET_MASS_P1_TET_A: return launch_matrix<el::FacetMassP1Tet, MODE>(P, a, st);
+  case BFX_K_ELASTICITY_Q1_HEX_A: return launch_q1<MODE>(P, a, st);
+  default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a bilinear-form kernel", kernel_id);
+  }
+}
+
+int dispatch_vector(int kernel_id, const AsmArgs& a, cudaStream_t st)
+{
+  switch (kernel_id)
+  {
+  case BFX_K_SOURCE_P1_TRI_L: return launch_vector<el::SourceP1Tri>(a, st);
+  case BFX_K_LOAD_COEFF_P1_TRI_L: return launch_vector<el::LoadCoeffP1Tri>(a, st);
+  case BFX_K_FACET_CONST_P1_TRI_L: return launch_vector<el::FacetConstP1Tri>(a, st);
+  case BFX_K_LOAD_P1_TET_L: return launch_vector<el::LoadP1Tet>(a, st);
+  case BFX_K_LOAD_P2_TET_L: return launch_vector<el::LoadP2Tet>(a, st);
+  case BFX_K_LOAD_Q1_HEX_L: return launch_vector<el::LoadQ1Hex>(a, st);
+  case BFX_K_FACET_LOAD_P1_TET_L: return launch_vector<el::FacetLoadP1Tet>(a, st);
+  default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a linear-form kernel", kernel_id);
+  }
+}
+
+const bfx_kernel_info_t KINFO[BFX_K_COUNT] = {
+    /* nx nd bs rank w c facet */
+    {3, 3, 1, 2, 0, 0, 0},  {3, 3, 1, 1, 0, 0, 0},  {3, 3, 1, 2, 3, 0, 0},  {3, 3, 1, 1, 3, 0, 0},
+    {3, 3, 1, 2, 0, 0, 1},  {3, 3, 1, 1, 0, 1, 1},  {4, 4, 1, 2, 0, 1, 0},  {4, 4, 1, 1, 4, 0, 0},
+    {4, 10, 1, 2, 0, 1, 0}, {4, 10, 1, 1, 10, 0, 0}, {8, 8, 3, 2, 0, 2, 0}, {8, 8, 3, 1, 24, 0, 0},
+    {4, 4, 1, 1, 4, 0, 1},  {4, 4, 1, 2, 0, 0, 1}};
+
+int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, const bfx_coeffs_t* coeffs,
+                const double* constants, int n_constants, AsmArgs& a, bool need_csr = true)
+{
+  BFX_REQUIRE(P && x, "assemble: null plan or geometry");
+  BFX_REQUIRE(kernel_id >= 0 && kernel_id < BFX_K_COUNT, "assemble: bad kernel id %d", kernel_id);
+  const bfx_kernel_info_t& ki = KINFO[kernel_id];
+  BFX_REQUIRE(ki.rank == rank, "kernel id %d has rank %d, expected %d", kernel_id, ki.rank, rank);
+  BFX_REQUIRE(ki.nx == P->nx && ki.nd == P->nd0, "kernel id %d expects nx=%d nd=%d, plan has nx=%d nd=%d", kernel_id,
+              ki.nx, ki.nd, P->nx, P->nd0);
+  if (rank == 2)
+  {
+    BFX_REQUIRE(P->nd1 == ki.nd, "bilinear kernel %d needs a plan with a trial dofmap of %d dofs per cell", kernel_id,
+                ki.nd);
+    if (need_csr)
+      BFX_REQUIRE(P->csr && P->csr->bs0 == ki.bs && P->csr->bs1 == ki.bs,
+                  "bilinear kernel %d needs a plan with a matching MatrixCSR (bs=%d)", kernel_id, ki.bs);
+  }
+  BFX_REQUIRE(n_constants >= ki.c_size && n_constants <= 8, "kernel id %d needs %d constants (max 8), got %d",
+              kernel_id, ki.c_size, n_constants);
+  memset(&a, 0, sizeof(a));
+  a.x_dofmap = P->x_dofmap;
+  a.dofmap0 = P->dofmap0;
+  a.dofmap1 = P->dofmap1 ? P->dofmap1 : P->dofmap0;
+  a.x = x;
+  for (int k = 0; k < n_constants; ++k)
+    a.constants[k] = constants[k];
+  if (ki.w_size > 0)
+  {
+    BFX_REQUIRE(coeffs, "kernel id %d needs coefficients", kernel_id);
+    if (coeffs->packed_dev)
+    {
+      BFX_REQUIRE(coeffs->cstride >= ki.w_size, "packed coefficient stride %d < %d", coeffs->cstride, ki.w_size);
+      a.coef.packed = coeffs->packed_dev;
+      a.coef.cstride = coeffs->cstride;
+      a.coef.f[0].off = coeffs->n_fused > 0 ? coeffs->fused[0].offset : 0;
+    }
+    else
+    {
+      BFX_REQUIRE(coeffs->n_fused == 1 && coeffs->fused[0].values_dev && coeffs->fused[0].dofmap_dev,
+                  "fused coefficient gather supports exactly one coefficient");
+      BFX_REQUIRE(coeffs->fused[0].nd * coeffs->fused[0].bs == ki.w_size,
+                  "coefficient layout nd*bs=%d does not match kernel w size %d", coeffs->fused[0].nd * coeffs->fused[0].bs,
+                  ki.w_size);
+      a.coef.f[0].v = coeffs->fused[0].values_dev;
+      a.coef.f[0].dm = coeffs->fused[0].dofmap_dev;
+    }
+  }
+  if (P->csr)
+  {
+    a.row_ptr = P->csr->row_ptr;
+    a.cols = P->csr->cols;
+    a.err = P->csr->err_flag;
+  }
+  return BFX_OK;
+}
+
+int check_err(const bfx_asm* P, cudaStream_t st, const char* what)
+{
+  int h = 0;
+  BFX_CUDA(cudaMemcpyAsync(&h, P->csr->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BFX_CUDA(cudaStreamSynchronize(st));
+  if (h)
+  {
+    BFX_CUDA(cudaMemsetAsync(P->csr->err_flag, 0, sizeof(int), st));
+    return fail(h == 1 ? BFX_ERR_NOT_IN_SPARSITY : BFX_ERR_INVALID,
+                h == 1 ? "%s: Entry not in sparsity" : "%s: dof index out of range", what);
+  }
+  return BFX_OK;
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C"
+{
+int bfx_kernel_info(int kernel_id, bfx_kernel_info_t* info)
+{
+  BFX_REQUIRE(kernel_id >= 0 && kernel_id < BFX_K_COUNT && info, "bfx_kernel_info: bad kernel id %d", kernel_id);
+  *info = KINFO[kernel_id];
+  return BFX_OK;
+}
+
+int bfx_asm_create(bfx_asm_t** out, const bfx_csr_t* csr, const int32_t* x_dofmap, int nx, const int32_t* dofmap0,
+                   int nd0, const int32_t* dofmap1, int nd1, int64_t ncells_all, const int32_t* cells, int64_t ncells,
+                   int32_t n_rows_all, int borrow, bfx_stream_t stream)
+{
+  BFX_REQUIRE(out && x_dofmap && dofmap0 && nx > 0 && nd0 > 0 && ncells_all >= 0 && ncells >= 0,
+              "bfx_asm_create: bad arguments");
+  cudaStream_t st = S(stream);
+  bfx_asm* P = new bfx_asm();
+  P->csr = csr;
+  P->nx = nx;
+  P->nd0 = nd0;
+  P->nd1 = dofmap1 ? nd1 : (csr ? nd0 : 0);
+  P->ncells_all = ncells_all;
+  P->ncells = ncells;
+  P->n_rows_all = n_rows_all;
+  P->owns = !borrow;
+  int e = BFX_OK;
+  if (borrow)
+  {
+    P->x_dofmap = const_cast<int32_t*>(x_dofmap);
+    P->dofmap0 = const_cast<int32_t*>(dofmap0);
+    P->dofmap1 = dofmap1 && dofmap1 != dofmap0 ? const_cast<int32_t*>(dofmap1) : nullptr;
+    P->cells = const_cast<int32_t*>(cells);
+  }
+  else
+  {
+    if ((e = upload(&P->x_dofmap, x_dofmap, (size_t)ncells_all * nx, st))
+        || (e = upload(&P->dofmap0, dofmap0, (size_t)ncells_all * nd0, st)))
+      return e;
+    if (dofmap1 && dofmap1 != dofmap0)
+    {
+      if ((e = upload(&P->dofmap1, dofmap1, (size_t)ncells_all * nd1, st)))
+        return e;
+    }
+    if (cells)
+    {
+      if ((e = upload(&P->cells, cells, (size_t)ncells, st)))
+        return e;
+    }
+  }
+  if (csr && ncells > 0)
+  {
+    BFX_REQUIRE(n_rows_all == csr->n_rows_all, "bfx_asm_create: plan rows %d != matrix rows %d", n_rows_all,
+                csr->n_rows_all);
+    int* d_max = nullptr;
+    BFX_CUDA(cudaMalloc(&d_max, sizeof(int)));
+    BFX_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+    k_max_row_len<<<grid_for(csr->n_rows_all, 256, 8), 256, 0, st>>>(csr->n_rows_all, csr->row_ptr, d_max);
+    int h_max = 0;
+    BFX_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    BFX_CUDA(cudaFree(d_max));
+    if (h_max > 65536)
+      return fail(BFX_ERR_UNSUPPORTED, "rows with more than 65536 block entries are not supported (%d)", h_max);
+    P->pos_bytes = h_max <= 256 ? 1 : 2;
+    const int count = P->nd0 * P->nd1;
+    P->pos_stride = (count * P->pos_bytes + 15) / 16 * 16;
+    if (P->nd0 == 8 && P->nd1 == 8 && csr->bs0 == 3)
+      P->pos_stride = 64 * P->pos_bytes; // Q1 elasticity kernel reads one entry per thread
+    if ((e = dev_alloc(&P->pos, (size_t)ncells * P->pos_stride)))
+      return e;
+    const int32_t* dm1 = P->dofmap1 ? P->dofmap1 : P->dofmap0;
+    const unsigned grid = grid_for(ncells * nd0, 256, 0);
+    if (P->pos_bytes == 1)
+      k_build_pos<uint8_t><<<grid, 256, 0, st>>>(ncells, P->cells, P->dofmap0, P->nd0, dm1, P->nd1, csr->row_ptr,
+                                                 csr->cols, csr->n_rows_all, P->pos, P->pos_stride, csr->err_flag);
+    else
+      k_build_pos<uint16_t><<<grid, 256, 0, st>>>(ncells, P->cells, P->dofmap0, P->nd0, dm1, P->nd1, csr->row_ptr,
+                                                  csr->cols, csr->n_rows_all, P->pos, P->pos_stride, csr->err_flag);
+    BFX_CHECK_LAUNCH();
+    if ((e = check_err(P, st, "bfx_asm_create")))
+    {
+      bfx_asm_destroy(P);
+      return e;
+    }
+  }
+  BFX_CUDA(cudaStreamSynchronize(st));
+  *out = P;
+  return BFX_OK;
+}
+
+int bfx_asm_destroy(bfx_asm_t* P)
+{
+  if (!P)
+    return BFX_OK;
+  if (P->owns)
+  {
+    cudaFree(P->x_dofmap);
+    cudaFree(P->dofmap0);
+    cudaFree(P->dofmap1);
+    cudaFree(P->cells);
+  }
+  cudaFree(P->pos);
+  cudaFree(P->h_x);
+  cudaFree(P->h_coeff);
+  cudaFree(P->h_bc0);
+  cudaFree(P->h_bc1);
+  cudaFree(P->h_values);
+  delete P;
+  return BFX_OK;
+}
+
+int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x, const int8_t* bc0,
+                              const int8_t* bc1, const bfx_coeffs_t* coeffs, const double* constants, int n_constants,
+                              double* values, int strategy, int values_mode, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 2, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(values, "bfx_assemble_matrix_cells: null values");
+  BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
+  (void)values_mode;
+  if (strategy != BFX_ASM_ATOMIC)
+    return fail(BFX_ERR_UNSUPPORTED, "assembly strategy %d not available", strategy);
+  a.cells = P->cells;
+  a.n = P->ncells;
+  a.bc0 = bc0;
+  a.bc1 = bc1;
+  a.values = values;
+  a.pos = P->pos;
+  return dispatch_matrix<0>(P, kernel_id, a, S(stream));
+}
+
+int bfx_assemble_matrix_facets(const bfx_asm_t* P, int kernel_id, const double* x, const int32_t* entities,
+                               int64_t n_entities, const int8_t* bc0, const int8_t* bc1, const bfx_coeffs_t* coeffs,
+                               const double* constants, int n_constants, double* values, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 2, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(values && (entities || n_entities == 0), "bfx_assemble_matrix_facets: null argument");
+  BFX_REQUIRE(KINFO[kernel_id].facet, "kernel id %d is not a facet kernel", kernel_id);
+  a.entities = entities;
+  a.n = n_entities;
+  a.bc0 = bc0;
+  a.bc1 = bc1;
+  a.values = values;
+  a.pos = nullptr; // few entities: locate entries by binary search like insert_csr
+  if ((e = dispatch_matrix<0>(P, kernel_id, a, S(stream))))
+    return e;
+  return check_err(P, S(stream), "assemble exterior facets");
+}
+
+int bfx_lift_bc_cells(const bfx_asm_t* P, int kernel_id, const double* x, const bfx_coeffs_t* coeffs,
+                      const double* constants, int n_constants, double* b, const double* bc_values1,
+                      const int8_t* bc_markers1, const double* x0, double alpha, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 2, x, coeffs, constants, n_constants, a, false);
+  if (e)
+    return e;
+  BFX_REQUIRE(b && bc_values1 && bc_markers1, "bfx_lift_bc_cells: null argument");
+  a.cells = P->cells;
+  a.n = P->ncells;
+  a.bc1 = bc_markers1;
+  a.b = b;
+  a.bc_values1 = bc_values1;
+  a.x0 = x0;
+  a.alpha = alpha;
+  return dispatch_matrix<1>(P, kernel_id, a, S(stream));
+}
+
+int bfx_assemble_vector_cells(const bfx_asm_t* P, int kernel_id, const double* x, const bfx_coeffs_t* coeffs,
+                              const double* constants, int n_constants, double* b, int strategy, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 1, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(b, "bfx_assemble_vector_cells: null b");
+  BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
+  if (strategy != BFX_ASM_ATOMIC)
+    return fail(BFX_ERR_UNSUPPORTED, "assembly strategy %d not available", strategy);
+  a.cells = P->cells;
+  a.n = P->ncells;
+  a.b = b;
+  return dispatch_vector(kernel_id, a, S(stream));
+}
+
+int bfx_assemble_vector_facets(const bfx_asm_t* P, int kernel_id, const double* x, const int32_t* entities,
+                               int64_t n_entities, const bfx_coeffs_t* coeffs, const double* constants,
+                               int n_constants, double* b, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 1, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(b && (entities || n_entities == 0), "bfx_assemble_vector_facets: null argument");
+  BFX_REQUIRE(KINFO[kernel_id].facet, "kernel id %d is not a facet kernel", kernel_id);
+  a.entities = entities;
+  a.n = n_entities;
+  a.b = b;
+  return dispatch_vector(kernel_id, a, S(stream));
+}
+
+int bfx_pack_coefficient(double* coeffs, int cstride, int offset, const double* values, const int32_t* dofmap, int nd,
+                         int bs, const int32_t* cells, const int32_t* entities, int64_t n, bfx_stream_t stream)
+{
+  BFX_REQUIRE(coeffs && values && dofmap && nd > 0 && bs > 0, "bfx_pack_coefficient: bad arguments");
+  if (n == 0)
+    return BFX_OK;
+  k_pack<<<grid_for(n * nd * bs, 256, 16), 256, 0, S(stream)>>>(coeffs, cstride, offset, values, dofmap, nd, bs, cells,
+                                                                 entities, n);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+int bfx_bc_mark(int8_t* markers, const int32_t* dofs0, int64_t n, bfx_stream_t stream)
+{
+  if (n == 0)
+    return BFX_OK;
+  BFX_REQUIRE(markers && dofs0, "bfx_bc_mark: null argument");
+  k_bc_mark<<<grid_for(n, 256, 8), 256, 0, S(stream)>>>(markers, dofs0, n);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+int bfx_bc_set(double* x, int32_t x_size, const int32_t* dofs0, const int32_t* dofs_g, int64_t n, const double* g,
+               int g_kind, int bs, const double* x0, double alpha, bfx_stream_t stream)
+{
+  if (n == 0)
+    return BFX_OK;
+  BFX_REQUIRE(x && dofs0 && g && bs > 0, "bfx_bc_set: bad arguments");
+  k_bc_set<<<grid_for(n, 256, 8), 256, 0, S(stream)>>>(x, x_size, dofs0, dofs_g, n, g, g_kind, bs, x0, alpha);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+int bfx_assemble_matrix_cells_host(bfx_asm_t* P, int kernel_id, const double* x_host, int64_t n_x_nodes,
+                                   const int8_t* bc0_host, const int8_t* bc1_host, int64_t n_bc,
+                                   const double* coeff_values_host, int64_t n_coeff_values, int coeff_bs,
+                                   const double* constants, int n_constants, double* values_host, int strategy,
+                                   bfx_stream_t stream)
+{
+  BFX_REQUIRE(P && P->csr && x_host && values_host, "bfx_assemble_matrix_cells_host: null argument");
+  cudaStream_t st = S(stream);
+  const size_t nval = (size_t)P->csr->nnz * P->csr->bs0 * P->csr->bs1;
+  // device scratch is allocated on first use and kept by the plan
+  if (!P->h_x || P->h_x_n < n_x_nodes)
+  {
+    cudaFree(P->h_x);
+    BFX_CUDA(cudaMalloc(&P->h_x, sizeof(double) * 3 * (size_t)n_x_nodes));
+    P->h_x_n = n_x_nodes;
+  }
+  if (!P->h_values)
+    BFX_CUDA(cudaMalloc(&P->h_values, sizeof(double) * nval));
+  if (n_bc > 0 && (!P->h_bc0 || P->h_bc_n < n_bc))
+  {
+    cudaFree(P->h_bc0);
+    cudaFree(P->h_bc1);
+    BFX_CUDA(cudaMalloc(&P->h_bc0, (size_t)n_bc));
+    BFX_CUDA(cudaMalloc(&P->h_bc1, (size_t)n_bc));
+    P->h_bc_n = n_bc;
+  }
+  if (n_coeff_values > 0 && (!P->h_coeff || P->h_coeff_n < n_coeff_values))
+  {
+    cudaFree(P->h_coeff);
+    BFX_CUDA(cudaMalloc(&P->h_coeff, sizeof(double) * (size_t)n_coeff_values));
+    P->h_coeff_n = n_coeff_values;
+  }
+  BFX_CUDA(cudaMemcpyAsync(P->h_x, x_host, sizeof(double) * 3 * (size_t)n_x_nodes, cudaMemcpyHostToDevice, st));
+  if (bc0_host)
+    BFX_CUDA(cudaMemcpyAsync(P->h_bc0, bc0_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
+  if (bc1_host)
+    BFX_CUDA(cudaMemcpyAsync(P->h_bc1, bc1_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
+  bfx_coeffs_t cf;
+  memset(&cf, 0, sizeof(cf));
+  if (coeff_values_host && n_coeff_values > 0)
+  {
+    BFX_CUDA(cudaMemcpyAsync(P->h_coeff, coeff_values_host, sizeof(double) * (size_t)n_coeff_values,
+                             cudaMemcpyHostToDevice, st));
+    cf.n_fused = 1;
+    cf.fused[0].values_dev = P->h_coeff;
+    cf.fused[0].dofmap_dev = P->dofmap0;
+    cf.fused[0].nd = P->nd0;
+    cf.fused[0].bs = coeff_bs;
+  }
+  BFX_CUDA(cudaMemsetAsync(P->h_values, 0, sizeof(double) * nval, st));
+  int e = bfx_assemble_matrix_cells(P, kernel_id, P->h_x, bc0_host ? P->h_bc0 : nullptr, bc1_host ? P->h_bc1 : nullptr,
+                                    &cf, constants, n_constants, P->h_values, strategy, BFX_VALUES_OVERWRITE, stream);
+  if (e)
+    return e;
+  BFX_CUDA(cudaMemcpyAsync(values_host, P->h_values, sizeof(double) * nval, cudaMemcpyDeviceToHost, st));
+  BFX_CUDA(cudaStreamSynchronize(st));
+  return BFX_OK;
+}
+}

@@ -1,0 +1,670 @@
+// la::MatrixCSR on device: structure, SpMV / SpMV^T, insertion, set_diagonal, reductions.
+#include "csr.cuh"
+#include <algorithm>
+#include <vector>
+
+using namespace bfx;
+
+// ---------------------------------------------------------------------------------------------
+// reductions (la/Vector.h:434-514, la/MatrixCSR.h:473-486)
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int RED_THREADS = 256;
+
+struct RedWorkspace
+{
+  double* partial = nullptr; // [max_blocks + 1]
+  int max_blocks = 0;
+};
+
+RedWorkspace& red_ws()
+{
+  static thread_local RedWorkspace ws;
+  return ws;
+}
+
+int ensure_red_ws()
+{
+  RedWorkspace& ws = red_ws();
+  if (!ws.partial)
+  {
+    ws.max_blocks = sm_count() * 8;
+    BFX_CUDA(cudaMalloc(&ws.partial, sizeof(double) * (ws.max_blocks + 1)));
+  }
+  return BFX_OK;
+}
+
+// op: 0 = sum x*y, 1 = sum |x|, 2 = max |x|
+template <int OP>
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_stage1(int64_t n, const double* __restrict__ x,
+                                                               const double* __restrict__ y, double* __restrict__ out)
+{
+  double acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  {
+    if (OP == 0)
+      acc = fma(x[i], y[i], acc);
+    else if (OP == 1)
+      acc += fabs(x[i]);
+    else
+      acc = fmax(acc, fabs(x[i]));
+  }
+  __shared__ double sm[RED_THREADS / 32];
+  if (OP == 2)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  }
+  else
+    acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0)
+    sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32)
+  {
+    double v = threadIdx.x < RED_THREADS / 32 ? sm[threadIdx.x] : 0.0;
+    if (OP == 2)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    else
+      v = warp_sum(v);
+    if (threadIdx.x == 0)
+      out[blockIdx.x] = v;
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_stage2(int nb, const double* __restrict__ partial,
+                                                               double* __restrict__ out)
+{
+  // deterministic fixed-order final sum
+  double acc = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    acc = OP == 2 ? fmax(acc, partial[i]) : acc + partial[i];
+  __shared__ double sm[RED_THREADS];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = RED_THREADS / 2; s > 0; s >>= 1)
+  {
+    if (threadIdx.x < s)
+      sm[threadIdx.x] = OP == 2 ? fmax(sm[threadIdx.x], sm[threadIdx.x + s]) : sm[threadIdx.x] + sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *out = sm[0];
+}
+
+template <int OP>
+int reduce(int64_t n, const double* x, const double* y, double* result_host, cudaStream_t st)
+{
+  int e = ensure_red_ws();
+  if (e)
+    return e;
+  RedWorkspace& ws = red_ws();
+  int nb = (int)std::min<int64_t>(ws.max_blocks, std::max<int64_t>(1, (n + RED_THREADS - 1) / RED_THREADS));
+  k_reduce_stage1<OP><<<nb, RED_THREADS, 0, st>>>(n, x, y, ws.partial);
+  k_reduce_stage2<OP><<<1, RED_THREADS, 0, st>>>(nb, ws.partial, ws.partial + ws.max_blocks);
+  BFX_CHECK_LAUNCH();
+  BFX_CUDA(cudaMemcpyAsync(result_host, ws.partial + ws.max_blocks, sizeof(double), cudaMemcpyDeviceToHost, st));
+  BFX_CUDA(cudaStreamSynchronize(st));
+  return BFX_OK;
+}
+
+__global__ void k_axpy(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fma(alpha, x[i], y[i]);
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// SpMV (la/matrix_csr_impl.h:259-286; split of la/MatrixCSR.h:877-946)
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_CHUNK = 4096; // products staged per pass (32 KB of shared memory)
+
+// bs = 1.  One CTA owns R = SPMV_THREADS / LPR consecutive rows; their nonzeros are one contiguous
+// range of values/cols, streamed with coalesced 128-bit loads (4 entries per thread per step),
+// multiplied by the gathered x and staged in shared memory; LPR lanes then reduce each row.
+// part: FULL sums [row_ptr[i], row_ptr[i+1]); DIAG sums [row_ptr[i], off_diag[i]) (products of the
+// ghost columns are staged but never read).
+template <int LPR>
+__global__ void __launch_bounds__(SPMV_THREADS)
+    k_spmv_stream(int32_t n_rows, const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ row_end_sel,
+                  const int32_t* __restrict__ cols, const double* __restrict__ values, const double* __restrict__ x,
+                  double* __restrict__ y)
+{
+  constexpr int R = SPMV_THREADS / LPR;
+  __shared__ __align__(16) double prod[SPMV_CHUNK];
+  const int32_t r0 = blockIdx.x * R;
+  const int32_t r1 = min(r0 + R, n_rows);
+  const int64_t start = row_ptr[r0];
+  const int64_t end = row_ptr[r1];
+
+  const int my_row = r0 + threadIdx.x / LPR;
+  const int sub = threadIdx.x % LPR;
+  int64_t rb = 0, re = 0;
+  if (my_row < r1)
+  {
+    rb = row_ptr[my_row];
+    re = row_end_sel[my_row];
+  }
+  double sum = 0.0;
+
+  const int64_t astart = start & ~int64_t(3); // 16 B aligned for cols, 32 B for values
+  for (int64_t base = astart; base < end; base += SPMV_CHUNK)
+  {
+    // ---- stage products
+#pragma unroll
+    for (int it = 0; it < SPMV_CHUNK / (4 * SPMV_THREADS); ++it)
+    {
+      const int off = (it * SPMV_THREADS + threadIdx.x) * 4;
+      const int64_t k = base + off;
+      if (k + 3 < end && k >= start)
+      {
+        const int4 c = ldg_stream(reinterpret_cast<const int4*>(cols + k));
+        const double2 v0 = ldg_stream(reinterpret_cast<const double2*>(values + k));
+        const double2 v1 = ldg_stream(reinterpret_cast<const double2*>(values + k + 2));
+        double2 p0, p1;
+        p0.x = v0.x * __ldg(x + c.x);
+        p0.y = v0.y * __ldg(x + c.y);
+        p1.x = v1.x * __ldg(x + c.z);
+        p1.y = v1.y * __ldg(x + c.w);
+        *reinterpret_cast<double2*>(prod + off) = p0;
+        *reinterpret_cast<double2*>(prod + off + 2) = p1;
+      }
+      else if (k < end)
+      {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (k + m < end && k + m >= start)
+            prod[off + m] = values[k + m] * __ldg(x + cols[k + m]);
+      }
+    }
+    __syncthreads();
+    // ---- reduce the part of my row that lies in this chunk
+    const int64_t lo = max(rb, base), hi = min(re, base + SPMV_CHUNK);
+    for (int64_t k = lo + sub; k < hi; k += LPR)
+      sum += prod[k - base];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (my_row < r1 && sub == 0)
+    y[my_row] += sum;
+}
+
+// Blocked rows, compile-time block sizes: one warp per block row, lanes stream the row's
+// nnz*BS0*BS1 contiguous scalars (coalesced), BS0 accumulators per lane, shuffle reduction.
+template <int BS0, int BS1>
+__global__ void __launch_bounds__(256)
+    k_spmv_blocked(int32_t n_rows, const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
+                   const int32_t* __restrict__ cols, const double* __restrict__ values, const double* __restrict__ x,
+                   double* __restrict__ y, const int32_t* __restrict__ row_list)
+{
+  constexpr int BS2 = BS0 * BS1;
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n_rows; w += nw)
+  {
+    const int32_t row = row_list ? row_list[w] : (int32_t)w;
+    const int64_t b = row_begin[row], e = row_end[row];
+    double acc[BS0];
+#pragma unroll
+    for (int k = 0; k < BS0; ++k)
+      acc[k] = 0.0;
+    const int64_t s0 = b * BS2, s1 = e * BS2;
+    for (int64_t s = s0 + lane; s < s1; s += 32)
+    {
+      const int64_t j = s / BS2;
+      const int rem = (int)(s - j * BS2);
+      const int k0 = rem / BS1, k1 = rem - k0 * BS1;
+      const double p = values[s] * __ldg(x + (int64_t)cols[j] * BS1 + k1);
+#pragma unroll
+      for (int k = 0; k < BS0; ++k)
+        acc[k] += (k == k0) ? p : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < BS0; ++k)
+      acc[k] = warp_sum(acc[k]);
+    if (lane == 0)
+    {
+#pragma unroll
+      for (int k = 0; k < BS0; ++k)
+        y[(int64_t)row * BS0 + k] += acc[k];
+    }
+  }
+}
+
+// Runtime block sizes (fallback; k0 outermost like the reference loop)
+__global__ void __launch_bounds__(256)
+    k_spmv_generic(int32_t n_rows, const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
+                   const int32_t* __restrict__ cols, const double* __restrict__ values, const double* __restrict__ x,
+                   double* __restrict__ y, int bs0, int bs1, const int32_t* __restrict__ row_list)
+{
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int bs2 = bs0 * bs1;
+  for (; w < n_rows; w += nw)
+  {
+    const int32_t row = row_list ? row_list[w] : (int32_t)w;
+    const int64_t b = row_begin[row], e = row_end[row];
+    for (int k0 = 0; k0 < bs0; ++k0)
+    {
+      double acc = 0.0;
+      const int64_t n = (e - b) * bs1;
+      for (int64_t t = lane; t < n; t += 32)
+      {
+        const int64_t j = b + t / bs1;
+        const int k1 = (int)(t % bs1);
+        acc += values[j * bs2 + k0 * bs1 + k1] * x[(int64_t)cols[j] * bs1 + k1];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0)
+        y[(int64_t)row * bs0 + k0] += acc;
+    }
+  }
+}
+
+// y[cols[j]*bs1+k1] += values[...] * x[i*bs0+k0]  (la/matrix_csr_impl.h:319-343), scalar-parallel with REDs
+__global__ void __launch_bounds__(256)
+    k_spmvT(int32_t n_rows, const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
+            const int32_t* __restrict__ cols, const double* __restrict__ values, const double* __restrict__ x,
+            double* __restrict__ y, int bs0, int bs1)
+{
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int bs2 = bs0 * bs1;
+  for (; w < n_rows; w += nw)
+  {
+    const int64_t b = row_begin[w], e = row_end[w];
+    for (int64_t s = b * bs2 + lane; s < e * bs2; s += 32)
+    {
+      const int64_t j = s / bs2;
+      const int rem = (int)(s - j * bs2);
+      const int k0 = rem / bs1, k1 = rem - k0 * bs1;
+      red_add(y + (int64_t)cols[j] * bs1 + k1, values[s] * x[w * bs0 + k0]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// insertion (la/matrix_csr_impl.h:67-232) and set_diagonal (fem/assembler.h:644-686)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ cols, int64_t b, int64_t e, int32_t c)
+{
+  // std::lower_bound over the sorted columns of one row; -1 when absent
+  int64_t lo = b, hi = e;
+  while (lo < hi)
+  {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cols[mid] < c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (lo < e && cols[lo] == c) ? lo : -1;
+}
+
+// kind 0: insert_csr<dbs0,dbs1> (matrix bs == data bs); 1: insert_blocked_csr (matrix bs = 1);
+// 2: insert_nonblocked_csr (data bs = 1, matrix bs = mbs0 x mbs1).  One thread per scalar of x.
+__global__ void k_insert(int kind, int dbs0, int dbs1, int mbs0, int mbs1, const int64_t* __restrict__ row_ptr,
+                         const int32_t* __restrict__ cols, double* __restrict__ data, const double* __restrict__ x,
+                         const int32_t* __restrict__ xrows, int nr, const int32_t* __restrict__ xcols, int nc, int op,
+                         int* __restrict__ err)
+{
+  const int64_t total = (int64_t)nr * dbs0 * nc * dbs1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t ncs = (int64_t)nc * dbs1;
+    const int64_t R = t / ncs, Cc = t - R * ncs; // scalar row / col within x
+    const int r = (int)(R / dbs0), i = (int)(R - (int64_t)r * dbs0);
+    const int c = (int)(Cc / dbs1), j = (int)(Cc - (int64_t)c * dbs1);
+    const double v = x[t];
+    int64_t pos;
+    if (kind == 0)
+    {
+      const int32_t row = xrows[r];
+      const int64_t d = find_col(cols, row_ptr[row], row_ptr[row + 1], xcols[c]);
+      pos = d < 0 ? -1 : d * dbs0 * dbs1 + i * dbs1 + j;
+    }
+    else if (kind == 1)
+    {
+      const int32_t row = xrows[r] * dbs0 + i;
+      const int64_t d = find_col(cols, row_ptr[row], row_ptr[row + 1], xcols[c] * dbs1);
+      // the reference locates the first column of the block and writes dbs1 consecutive entries
+      pos = d < 0 ? -1 : d + j;
+    }
+    else
+    {
+      const int32_t rq = xrows[r] / mbs0, rr = xrows[r] - rq * mbs0;
+      const int32_t cq = xcols[c] / mbs1, cr = xcols[c] - cq * mbs1;
+      const int64_t d = find_col(cols, row_ptr[rq], row_ptr[rq + 1], cq);
+      pos = d < 0 ? -1 : d * mbs0 * mbs1 + rr * mbs1 + cr;
+    }
+    if (pos < 0)
+    {
+      *err = 1;
+      continue;
+    }
+    if (op)
+      red_add(data + pos, v);
+    else
+      data[pos] = v;
+  }
+}
+
+__global__ void k_set_diagonal(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                               double* __restrict__ data, const int32_t* __restrict__ rows, int64_t n, int bs0, int bs1,
+                               double diag, int* __restrict__ err)
+{
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t dof = rows[t];
+    const int32_t rq = dof / bs0, rr = dof - rq * bs0;
+    const int32_t cq = dof / bs1, cr = dof - cq * bs1;
+    const int64_t d = find_col(cols, row_ptr[rq], row_ptr[rq + 1], cq);
+    if (d < 0)
+      *err = 1;
+    else
+      data[d * bs0 * bs1 + rr * bs1 + cr] = diag;
+  }
+}
+
+__global__ void k_list_offdiag_rows(int32_t n, const int64_t* __restrict__ off_diag,
+                                    const int64_t* __restrict__ row_ptr, int32_t* __restrict__ list,
+                                    int32_t* __restrict__ count)
+{
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (off_diag[i] < row_ptr[i + 1])
+      list[atomicAdd(count, 1)] = i;
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+namespace bfx
+{
+int csr_finish_create(bfx_csr* A)
+{
+  // nnz, nnz of owned rows, and the list of owned rows that have off-diagonal (ghost-column) entries
+  BFX_CUDA(cudaMemcpy(&A->nnz, A->row_ptr + A->n_rows_all, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  BFX_CUDA(cudaMemcpy(&A->nnz_owned, A->row_ptr + A->n_rows_owned, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  A->n_offdiag_rows = 0;
+  A->offdiag_rows = nullptr;
+  if (A->n_rows_owned > 0)
+  {
+    int32_t *list = nullptr, *count = nullptr;
+    BFX_CUDA(cudaMalloc(&list, sizeof(int32_t) * A->n_rows_owned));
+    BFX_CUDA(cudaMalloc(&count, sizeof(int32_t)));
+    BFX_CUDA(cudaMemset(count, 0, sizeof(int32_t)));
+    k_list_offdiag_rows<<<grid_for(A->n_rows_owned, 256, 8), 256>>>(A->n_rows_owned, A->off_diag, A->row_ptr, list,
+                                                                    count);
+    BFX_CHECK_LAUNCH();
+    BFX_CUDA(cudaMemcpy(&A->n_offdiag_rows, count, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    BFX_CUDA(cudaFree(count));
+    if (A->n_offdiag_rows > 0)
+    {
+      // sort for determinism / locality
+      std::vector<int32_t> h(A->n_offdiag_rows);
+      BFX_CUDA(cudaMemcpy(h.data(), list, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost));
+      std::sort(h.begin(), h.end());
+      BFX_CUDA(cudaMalloc(&A->offdiag_rows, sizeof(int32_t) * h.size()));
+      BFX_CUDA(cudaMemcpy(A->offdiag_rows, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice));
+    }
+    BFX_CUDA(cudaFree(list));
+  }
+  BFX_CUDA(cudaMalloc(&A->err_flag, sizeof(int)));
+  BFX_CUDA(cudaMemset(A->err_flag, 0, sizeof(int)));
+  return BFX_OK;
+}
+} // namespace bfx
+
+extern "C"
+{
+int bfx_csr_create(bfx_csr_t** out, int32_t n_rows_all, int32_t n_rows_owned, const int64_t* row_ptr,
+                   const int32_t* cols, const int64_t* off_diag, int bs0, int bs1)
+{
+  BFX_REQUIRE(out && row_ptr && n_rows_all >= 0 && n_rows_owned >= 0 && n_rows_owned <= n_rows_all && bs0 > 0
+                  && bs1 > 0,
+              "bfx_csr_create: bad arguments");
+  bfx_csr* A = new bfx_csr();
+  A->n_rows_all = n_rows_all;
+  A->n_rows_owned = n_rows_owned;
+  A->bs0 = bs0;
+  A->bs1 = bs1;
+  int e = upload(&A->row_ptr, row_ptr, (size_t)n_rows_all + 1);
+  if (e)
+    return e;
+  int64_t nnz = 0;
+  BFX_CUDA(cudaMemcpy(&nnz, A->row_ptr + n_rows_all, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if ((e = upload(&A->cols, cols, (size_t)nnz)))
+    return e;
+  if (off_diag)
+  {
+    if ((e = upload(&A->off_diag, off_diag, (size_t)n_rows_all)))
+      return e;
+  }
+  else
+  {
+    // no ghost columns: off_diag = row end
+    if ((e = dev_alloc(&A->off_diag, (size_t)n_rows_all)))
+      return e;
+    BFX_CUDA(cudaMemcpy(A->off_diag, A->row_ptr + 1, sizeof(int64_t) * n_rows_all, cudaMemcpyDeviceToDevice));
+  }
+  if ((e = csr_finish_create(A)))
+    return e;
+  *out = A;
+  return BFX_OK;
+}
+
+int bfx_csr_destroy(bfx_csr_t* A)
+{
+  if (!A)
+    return BFX_OK;
+  cudaFree(A->row_ptr);
+  cudaFree(A->cols);
+  cudaFree(A->off_diag);
+  cudaFree(A->offdiag_rows);
+  cudaFree(A->err_flag);
+  delete A;
+  return BFX_OK;
+}
+
+int64_t bfx_csr_nnz(const bfx_csr_t* A) { return A ? A->nnz : -1; }
+
+int bfx_csr_get_structure(const bfx_csr_t* A, int64_t* row_ptr, int32_t* cols, int64_t* off_diag)
+{
+  BFX_REQUIRE(A, "null csr");
+  if (row_ptr)
+    BFX_CUDA(cudaMemcpy(row_ptr, A->row_ptr, sizeof(int64_t) * ((size_t)A->n_rows_all + 1), cudaMemcpyDefault));
+  if (cols && A->nnz)
+    BFX_CUDA(cudaMemcpy(cols, A->cols, sizeof(int32_t) * (size_t)A->nnz, cudaMemcpyDefault));
+  if (off_diag && A->n_rows_all)
+    BFX_CUDA(cudaMemcpy(off_diag, A->off_diag, sizeof(int64_t) * (size_t)A->n_rows_all, cudaMemcpyDefault));
+  return BFX_OK;
+}
+
+int bfx_csr_device_ptrs(const bfx_csr_t* A, const int64_t** row_ptr, const int32_t** cols, const int64_t** off_diag)
+{
+  BFX_REQUIRE(A, "null csr");
+  if (row_ptr)
+    *row_ptr = A->row_ptr;
+  if (cols)
+    *cols = A->cols;
+  if (off_diag)
+    *off_diag = A->off_diag;
+  return BFX_OK;
+}
+
+int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* y, int part, bfx_stream_t stream)
+{
+  BFX_REQUIRE(A && values && x && y, "bfx_spmv: null argument");
+  const int32_t n = A->n_rows_owned;
+  if (n == 0)
+    return BFX_OK;
+  cudaStream_t st = S(stream);
+  const int64_t* rb = A->row_ptr;
+  const int64_t* re = A->row_ptr + 1;
+  const int32_t* row_list = nullptr;
+  int32_t n_launch = n;
+  if (part == BFX_SPMV_DIAG)
+    re = A->off_diag;
+  else if (part == BFX_SPMV_OFFDIAG)
+  {
+    rb = A->off_diag;
+    row_list = A->offdiag_rows; // only rows that have ghost columns
+    n_launch = A->n_offdiag_rows;
+    if (n_launch == 0)
+      return BFX_OK;
+  }
+  else if (part != BFX_SPMV_FULL)
+    return fail(BFX_ERR_INVALID, "bfx_spmv: bad part %d", part);
+
+  if (A->bs0 == 1 && A->bs1 == 1 && part != BFX_SPMV_OFFDIAG)
+  {
+    const double avg = (double)A->nnz_owned / (double)n;
+    // rows per CTA chosen so that one pass of SPMV_CHUNK products usually covers the CTA's rows
+    if (avg <= 14.0 * 1.15)
+      k_spmv_stream<1><<<(n + 255) / 256, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
+    else if (avg <= 30.0 * 1.05)
+      k_spmv_stream<2><<<(n + 127) / 128, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
+    else if (avg <= 62.0)
+      k_spmv_stream<4><<<(n + 63) / 64, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
+    else
+      k_spmv_stream<8><<<(n + 31) / 32, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
+  }
+  else
+  {
+    const unsigned grid = grid_for((int64_t)n_launch * 32, 256, 32);
+#define BLK(a, b)                                                                                                    \
+  if (A->bs0 == a && A->bs1 == b)                                                                                    \
+    k_spmv_blocked<a, b><<<grid, 256, 0, st>>>(n_launch, rb, re, A->cols, values, x, y, row_list);                   \
+  else
+    BLK(1, 1) BLK(2, 2) BLK(3, 3) BLK(1, 2) BLK(2, 1) BLK(2, 3) BLK(3, 2)
+#undef BLK
+    k_spmv_generic<<<grid, 256, 0, st>>>(n_launch, rb, re, A->cols, values, x, y, A->bs0, A->bs1, row_list);
+  }
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+int bfx_spmvT(const bfx_csr_t* A, const double* values, const double* x, double* y, int part, bfx_stream_t stream)
+{
+  BFX_REQUIRE(A && values && x && y, "bfx_spmvT: null argument");
+  const int32_t n = A->n_rows_owned;
+  if (n == 0)
+    return BFX_OK;
+  const int64_t* rb = A->row_ptr;
+  const int64_t* re = A->row_ptr + 1;
+  if (part == BFX_SPMV_DIAG)
+    re = A->off_diag;
+  else if (part == BFX_SPMV_OFFDIAG)
+    rb = A->off_diag;
+  k_spmvT<<<grid_for((int64_t)n * 32, 256, 32), 256, 0, S(stream)>>>(n, rb, re, A->cols, values, x, y, A->bs0,
+                                                                      A->bs1);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+static int check_err_flag(const bfx_csr_t* A, cudaStream_t st, const char* what)
+{
+  int h = 0;
+  BFX_CUDA(cudaMemcpyAsync(&h, A->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BFX_CUDA(cudaStreamSynchronize(st));
+  if (h)
+  {
+    BFX_CUDA(cudaMemsetAsync(A->err_flag, 0, sizeof(int), st));
+    return fail(BFX_ERR_NOT_IN_SPARSITY, "%s: Entry not in sparsity", what);
+  }
+  return BFX_OK;
+}
+
+int bfx_csr_insert(const bfx_csr_t* A, double* values, int kind, int dbs0, int dbs1, const double* x,
+                   const int32_t* xrows, int nr, const int32_t* xcols, int nc, int op, bfx_stream_t stream)
+{
+  BFX_REQUIRE(A && values && x && xrows && xcols && nr >= 0 && nc >= 0, "bfx_csr_insert: bad arguments");
+  if (kind == 0)
+    BFX_REQUIRE(dbs0 == A->bs0 && dbs1 == A->bs1, "insert_csr: data block size must equal matrix block size");
+  else if (kind == 1)
+    BFX_REQUIRE(A->bs0 == 1 && A->bs1 == 1, "insert_blocked_csr: matrix block size must be 1");
+  else if (kind == 2)
+    BFX_REQUIRE(dbs0 == 1 && dbs1 == 1, "insert_nonblocked_csr: data block size must be 1");
+  else
+    return fail(BFX_ERR_INVALID, "bfx_csr_insert: bad kind %d", kind);
+  if (nr == 0 || nc == 0)
+    return BFX_OK;
+  cudaStream_t st = S(stream);
+  const size_t nx = (size_t)nr * dbs0 * nc * dbs1;
+  // not a hot path (explicit MatrixCSR::add/set calls): stage the operands on the device
+  double* dx = nullptr;
+  int32_t *dr = nullptr, *dc = nullptr;
+  int e;
+  if ((e = upload(&dx, x, nx, st)) || (e = upload(&dr, xrows, (size_t)nr, st)) || (e = upload(&dc, xcols, (size_t)nc, st)))
+    return e;
+  k_insert<<<grid_for((int64_t)nx, 256, 8), 256, 0, st>>>(kind, dbs0, dbs1, A->bs0, A->bs1, A->row_ptr, A->cols,
+                                                          values, dx, dr, nr, dc, nc, op, A->err_flag);
+  BFX_CHECK_LAUNCH();
+  e = check_err_flag(A, st, "MatrixCSR insert");
+  cudaFree(dx);
+  cudaFree(dr);
+  cudaFree(dc);
+  return e;
+}
+
+int bfx_csr_set_diagonal(const bfx_csr_t* A, double* values, const int32_t* rows, int64_t n, double diag,
+                         bfx_stream_t stream)
+{
+  BFX_REQUIRE(A && values, "bfx_csr_set_diagonal: null argument");
+  if (n == 0)
+    return BFX_OK;
+  cudaStream_t st = S(stream);
+  k_set_diagonal<<<grid_for(n, 256, 8), 256, 0, st>>>(A->row_ptr, A->cols, values, rows, n, A->bs0, A->bs1, diag,
+                                                      A->err_flag);
+  BFX_CHECK_LAUNCH();
+  return check_err_flag(A, st, "set_diagonal");
+}
+
+int bfx_csr_squared_norm(const bfx_csr_t* A, const double* values, double* result_host, bfx_stream_t stream)
+{
+  BFX_REQUIRE(A && values && result_host, "bfx_csr_squared_norm: null argument");
+  return reduce<0>(A->nnz_owned * A->bs0 * A->bs1, values, values, result_host, S(stream));
+}
+
+int bfx_dot(int64_t n, const double* x, const double* y, double* result_host, bfx_stream_t stream)
+{
+  return reduce<0>(n, x, y, result_host, S(stream));
+}
+
+int bfx_norm(int64_t n, const double* x, int type, double* result_host, bfx_stream_t stream)
+{
+  if (type == 0)
+    return reduce<1>(n, x, x, result_host, S(stream));
+  if (type == 1)
+    return reduce<0>(n, x, x, result_host, S(stream));
+  if (type == 2)
+    return reduce<2>(n, x, x, result_host, S(stream));
+  return fail(BFX_ERR_INVALID, "bfx_norm: bad type %d", type);
+}
+
+int bfx_axpy(int64_t n, double alpha, const double* x, double* y, bfx_stream_t stream)
+{
+  if (n <= 0)
+    return BFX_OK;
+  k_axpy<<<grid_for(n, 256, 16), 256, 0, S(stream)>>>(n, alpha, x, y);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+}

@@ -1,0 +1,530 @@
+"""Host mirror of dolfinx::fem for the assembly hot path, over the libbfx C-ABI.
+
+Reference: cpp/dolfinx/fem/{assembler.h,assemble_matrix_impl.h,assemble_vector_impl.h,pack.h,
+DirichletBC.h,Form.h,DofMap.h,FunctionSpace.h,utils.h} and the Python surface
+python/dolfinx/fem/{assemble.py,bcs.py,forms.py}.  Function names, argument meaning and error
+behaviour follow the reference; the cell loops run as CUDA kernels.  ``Mesh``, ``DofMap``,
+``FunctionSpace`` only carry the arrays the path reads (their builders are out of scope).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import la
+from .common import Comm, IndexMap
+
+
+class IntegralType(enum.IntEnum):
+    cell = 0
+    exterior_facet = 1
+    interior_facet = 2
+    vertex = 3
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _to_dev(a, dtype=None):
+    torch = _torch()
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and a.dtype != dtype:
+        a = a.to(dtype)
+    return a.to(la._device()).contiguous()
+
+
+class Mesh:
+    """The part of mesh::Mesh the assembler reads: geometry x (N,3), geometry dofmap (C,nx)
+    (mesh/Geometry.h:131,155) and the number of owned cells (default cell domain, fem/utils.h:579-588)."""
+
+    def __init__(self, comm: Comm, x, x_dofmap, cell_type: str, num_cells_local=None):
+        self.comm = comm
+        self.cell_type = cell_type
+        self._x_host = np.ascontiguousarray(x, dtype=np.float64) if isinstance(x, np.ndarray) else None
+        self._xd_host = np.ascontiguousarray(x_dofmap, dtype=np.int32) if isinstance(x_dofmap, np.ndarray) else None
+        self._x_dev = None if isinstance(x, np.ndarray) else x
+        self._xd_dev = None if isinstance(x_dofmap, np.ndarray) else x_dofmap
+        shape = x_dofmap.shape
+        self.num_cells = int(shape[0])
+        self.num_cells_local = self.num_cells if num_cells_local is None else int(num_cells_local)
+        self.nx = int(shape[1])
+
+    @property
+    def x(self):
+        """Device coordinates (N,3) float64."""
+        if self._x_dev is None:
+            self._x_dev = _to_dev(self._x_host)
+        return self._x_dev
+
+    @property
+    def x_dofmap(self):
+        if self._xd_dev is None:
+            self._xd_dev = _to_dev(self._xd_host, _torch().int32)
+        return self._xd_dev
+
+    @property
+    def x_host(self):
+        if self._x_host is None:
+            self._x_host = self._x_dev.cpu().numpy()
+        return self._x_host
+
+    @property
+    def x_dofmap_host(self):
+        if self._xd_host is None:
+            self._xd_host = self._xd_dev.cpu().numpy()
+        return self._xd_host
+
+
+class DofMap:
+    """fem::DofMap accessor subset (fem/DofMap.h:127-167): ``map`` (C,nd) int32, ``bs``, ``index_map``."""
+
+    def __init__(self, dofmap, bs: int, index_map: IndexMap, index_map_bs=None):
+        self._host = np.ascontiguousarray(dofmap, dtype=np.int32) if isinstance(dofmap, np.ndarray) else None
+        self._dev = None if isinstance(dofmap, np.ndarray) else dofmap
+        self.shape = tuple(dofmap.shape)
+        self.bs = int(bs)
+        self.index_map = index_map
+        self.index_map_bs = int(bs if index_map_bs is None else index_map_bs)
+
+    def map(self):
+        if self._host is None:
+            self._host = self._dev.cpu().numpy()
+        return self._host
+
+    def cell_dofs(self, c):
+        return self.map()[c]
+
+    @property
+    def dev(self):
+        if self._dev is None:
+            self._dev = _to_dev(self._host, _torch().int32)
+        return self._dev
+
+
+class FunctionSpace:
+    """fem::FunctionSpace: mesh + element label + dofmap (fem/FunctionSpace.h)."""
+
+    def __init__(self, mesh: Mesh, element: str, dofmap: DofMap):
+        self.mesh, self.element, self.dofmap = mesh, element, dofmap
+
+    def contains(self, V) -> bool:
+        """fem/FunctionSpace.h:153 — no sub-spaces on this path: identity."""
+        return V is self
+
+    @property
+    def space_dimension(self):
+        return self.dofmap.shape[1] * self.dofmap.bs
+
+
+class Function:
+    """fem::Function: a FunctionSpace + la::Vector of dof values (block size = dofmap.bs)."""
+
+    def __init__(self, V: FunctionSpace):
+        self.function_space = V
+        self.x = la.Vector(V.dofmap.index_map, V.dofmap.bs)
+
+
+class Constant:
+    """fem::Constant (fem/Constant.h): flattened value array."""
+
+    def __init__(self, value):
+        self.value = np.atleast_1d(np.asarray(value, dtype=np.float64)).reshape(-1)
+
+
+@dataclass
+class IntegralData:
+    """fem::integral_data (fem/Form.h:52-87): kernel, entities, active coefficient indices.
+
+    ``kernel`` is a libbfx kernel id (the device replacement of the FFCx function pointer).
+    ``entities``: cells (n,) for cell integrals, (n,2) (cell, local_facet) pairs for exterior facets;
+    None = all owned cells (fem/utils.h:579-588)."""
+
+    kernel: int
+    entities: object = None
+    coeffs: list = field(default_factory=list)
+
+
+class Form:
+    """fem::Form (fem/Form.h:116-668), hand-built like cpp/demo/custom_kernel/main.cpp:77-81 and
+    python/test/unit/fem/test_custom_jit_kernels.py:91-104."""
+
+    def __init__(self, function_spaces, integrals: dict, coefficients=(), constants=(), mesh: Mesh = None):
+        self.function_spaces = list(function_spaces)
+        self.rank = len(self.function_spaces)
+        self._integrals = {}
+        for key, lst in integrals.items():
+            itype = key if isinstance(key, IntegralType) else IntegralType(key)
+            for idx, entry in enumerate(lst):
+                if not isinstance(entry, IntegralData):
+                    ident, kernel, entities, active = entry
+                    entry = IntegralData(kernel, entities, list(active))
+                else:
+                    ident = idx
+                self._integrals[(itype, ident)] = entry
+        self.coefficients = list(coefficients)
+        self.constants = list(constants)
+        self.mesh = mesh if mesh is not None else self.function_spaces[0].mesh
+        self._plans = {}
+
+    def integral_ids(self, itype):
+        return sorted(i for (t, i) in self._integrals if t == itype)
+
+    def integral(self, itype, ident) -> IntegralData:
+        return self._integrals[(itype, ident)]
+
+    def coefficient_offsets(self):
+        """fem/Form.h:593-604"""
+        n = [0]
+        for c in self.coefficients:
+            n.append(n[-1] + c.function_space.space_dimension)
+        return n
+
+
+def pack_constants(form: Form) -> np.ndarray:
+    """fem::pack_constants (fem/pack.h:578-619)."""
+    if not form.constants:
+        return np.zeros(0)
+    return np.concatenate([c.value for c in form.constants])
+
+
+def _entities_dev(form: Form, integ: IntegralData, itype):
+    torch = _torch()
+    key = ("ent", id(integ))
+    if key not in form._plans:
+        ent = integ.entities
+        if ent is None:
+            form._plans[key] = (None, form.mesh.num_cells_local)
+        else:
+            t = _to_dev(np.ascontiguousarray(ent, dtype=np.int32) if isinstance(ent, np.ndarray) else ent, torch.int32)
+            n = t.shape[0]
+            form._plans[key] = (t.reshape(-1), n)
+    return form._plans[key]
+
+
+def pack_coefficients(form: Form):
+    """fem::pack_coefficients (fem/pack.h:265-…): {(type, id): (coeffs (n, cstride) device tensor, cstride)}.
+
+    Materialises the reference's packed layout on the device.  The assemblers below do not need it
+    (they gather coefficients inside the element kernel) but accept it for parity with callers that
+    pre-pack (python/test/unit/fem/test_assembler.py:1111-1205)."""
+    from . import _lib
+
+    torch = _torch()
+    offsets = form.coefficient_offsets()
+    cstride = offsets[-1]
+    out = {}
+    for (itype, ident), integ in form._integrals.items():
+        ent, n = _entities_dev(form, integ, itype)
+        c = torch.zeros((n, cstride), dtype=torch.float64, device=la._device())
+        for k in integ.coeffs:
+            u = form.coefficients[k]
+            dm = u.function_space.dofmap
+            is_facet = itype == IntegralType.exterior_facet
+            _lib.check(_lib.lib.bfx_pack_coefficient(
+                c.data_ptr(), cstride, offsets[k], u.x.array.data_ptr(), dm.dev.data_ptr(), dm.shape[1], dm.bs,
+                None if (ent is None or is_facet) else ent.data_ptr(), ent.data_ptr() if is_facet else None, n,
+                _lib.current_stream()))
+        out[(itype, ident)] = (c, cstride)
+    return out
+
+
+def create_sparsity_pattern(a: Form) -> la.SparsityPattern:
+    """fem::create_sparsity_pattern (fem/utils.h:197-218) → sparsitybuild::cells over every cell /
+    exterior-facet integral domain (fem/utils.h:225-314)."""
+    assert a.rank == 2
+    V0, V1 = a.function_spaces
+    dm0, dm1 = V0.dofmap, V1.dofmap
+    sp = la.SparsityPattern(a.mesh.comm, [dm0.index_map, dm1.index_map], [dm0.index_map_bs, dm1.index_map_bs])
+    on_device = _torch().cuda.is_available()
+    all_cells = False
+    for (itype, ident), integ in a._integrals.items():
+        if itype == IntegralType.cell and integ.entities is None:
+            all_cells = True
+    if all_cells or not a._integrals:
+        n = a.mesh.num_cells_local
+        if on_device:
+            cells = None if n == dm0.shape[0] else _torch().arange(n, dtype=_torch().int32, device=la._device())
+            sp.insert_cells(cells, dm0.dev, dm1.dev)
+        else:
+            sp.insert_cells(np.arange(n), dm0.map(), dm1.map())
+    for (itype, ident), integ in a._integrals.items():
+        if integ.entities is None:
+            continue
+        ent = np.asarray(integ.entities if isinstance(integ.entities, np.ndarray) else integ.entities.cpu().numpy())
+        cells = ent if itype == IntegralType.cell else ent.reshape(-1, 2)[:, 0]
+        if all_cells:
+            continue  # already covered
+        sp.insert_cells(np.unique(cells), dm0.map(), dm1.map())
+    return sp
+
+
+# ---------------------------------------------------------------------------------------------
+# Dirichlet boundary conditions
+# ---------------------------------------------------------------------------------------------
+class DirichletBC:
+    """fem::DirichletBC (fem/DirichletBC.h:262-601): sorted dof list (block indices unrolled by the
+    block size, :357-361), value g (Function or Constant), number of owned dofs (:262-271)."""
+
+    def __init__(self, g, dofs, V: FunctionSpace = None):
+        torch = _torch()
+        if isinstance(g, Function):
+            V = g.function_space if V is None else V
+        if V is None:
+            raise RuntimeError("DirichletBC with a Constant needs the function space")
+        self.function_space = V
+        self.g = g
+        bs = V.dofmap.bs
+        dofs = np.asarray(dofs, dtype=np.int32)
+        if isinstance(g, Constant) and g.value.size != bs:
+            raise RuntimeError(
+                "Creating a DirichletBC using a Constant is not supported when the Constant size is not equal to the "
+                "block size of the constrained (sub-)space. Use a fem::Function to create the fem::DirichletBC.")
+        if bs > 1:
+            dofs = (bs * dofs[:, None] + np.arange(bs, dtype=np.int32)[None, :]).reshape(-1)
+        self._dofs0 = np.ascontiguousarray(dofs, dtype=np.int32)
+        owned_size = V.dofmap.index_map_bs * V.dofmap.index_map.size_local
+        self._owned_indices0 = int(np.searchsorted(self._dofs0, owned_size))
+        self._dofs0_dev = None
+        self._g_dev = None
+
+    def dof_indices(self):
+        """(unrolled dofs, number of owned) — fem/DirichletBC.h:465-468"""
+        return self._dofs0, self._owned_indices0
+
+    @property
+    def dofs_dev(self):
+        if self._dofs0_dev is None:
+            self._dofs0_dev = _to_dev(self._dofs0, _torch().int32)
+        return self._dofs0_dev
+
+    def mark_dofs(self, markers):
+        """DirichletBC::mark_dofs (fem/DirichletBC.h:589-601); markers: int8 device tensor."""
+        from . import _lib
+
+        if self._dofs0.size and int(self._dofs0.max()) >= markers.numel():
+            raise RuntimeError("Marker array is too short for the boundary condition dofs.")
+        _lib.check(_lib.lib.bfx_bc_mark(markers.data_ptr(), self.dofs_dev.data_ptr(), self._dofs0.size, _lib.current_stream()))
+
+    def set(self, x, x0=None, alpha: float = 1.0):
+        """DirichletBC::set (fem/DirichletBC.h:495-578): x[dof] = alpha (g[dof] - x0[dof])."""
+        from . import _lib
+
+        if isinstance(self.g, Function):
+            g_dev, kind = self.g.x.array, 0
+        else:
+            if self._g_dev is None:
+                self._g_dev = _to_dev(self.g.value)
+            g_dev, kind = self._g_dev, 1
+        if x0 is not None:
+            assert x.numel() <= x0.numel()
+        _lib.check(_lib.lib.bfx_bc_set(x.data_ptr(), x.numel(), self.dofs_dev.data_ptr(), None, self._dofs0.size,
+                                       g_dev.data_ptr(), kind, self.function_space.dofmap.bs,
+                                       None if x0 is None else x0.data_ptr(), float(alpha), _lib.current_stream()))
+
+
+def dirichletbc(value, dofs, V=None) -> DirichletBC:
+    return DirichletBC(value, dofs, V)
+
+
+def set_bc(b, bcs, x0=None, alpha: float = 1.0):
+    """python/dolfinx/fem/bcs.py set_bc → DirichletBC::set for every bc."""
+    arr = b.array if isinstance(b, la.Vector) else b
+    for bc in bcs:
+        bc.set(arr, x0, alpha)
+
+
+# ---------------------------------------------------------------------------------------------
+# assembly
+# ---------------------------------------------------------------------------------------------
+def _bc_markers(V: FunctionSpace, bcs):
+    """dof markers of length bs*(owned+ghost) (fem/assembler.h:558-577); None when no bc applies."""
+    torch = _torch()
+    mk = None
+    for bc in bcs:
+        if V.contains(bc.function_space):
+            if mk is None:
+                im = V.dofmap.index_map
+                mk = torch.zeros(V.dofmap.index_map_bs * (im.size_local + im.num_ghosts), dtype=torch.int8, device=la._device())
+            bc.mark_dofs(mk)
+    return mk
+
+
+def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None):
+    """bfx_asm_t for one integral of a form (cached on the form)."""
+    from . import _lib
+
+    key = ("plan", id(integ), id(A) if A is not None else None)
+    if key in form._plans:
+        return form._plans[key][0]
+    mesh = form.mesh
+    V0 = form.function_spaces[0]
+    dm0 = V0.dofmap
+    dm1 = form.function_spaces[1].dofmap if form.rank == 2 else None
+    if itype == IntegralType.cell:
+        ent, n = _entities_dev(form, integ, itype)
+    else:
+        ent, n = None, 0  # facet integrals pass their entities at call time
+    im0 = dm0.index_map
+    h = C.c_void_p()
+    _lib.check(
+        _lib.lib.bfx_asm_create(
+            C.byref(h), A._csr if A is not None else None, mesh.x_dofmap.data_ptr(), mesh.nx, dm0.dev.data_ptr(),
+            dm0.shape[1], dm1.dev.data_ptr() if dm1 is not None else None, dm1.shape[1] if dm1 is not None else 0,
+            mesh.num_cells, None if ent is None else ent.data_ptr(), n, im0.size_local + im0.num_ghosts, 1,
+            _lib.current_stream(),
+        )
+    )
+    form._plans[key] = (h, ent)
+    return h
+
+
+def _coeffs_for(form: Form, integ: IntegralData, packed):
+    from . import _lib
+
+    if packed is not None:
+        c, cstride = packed
+        off = form.coefficient_offsets()[integ.coeffs[0]] if integ.coeffs else 0
+        return _lib.make_coeffs(packed=c, cstride=cstride, offset=off)
+    if integ.coeffs:
+        if len(integ.coeffs) != 1:
+            raise NotImplementedError("fused coefficient gather supports one active coefficient; pass pack_coefficients(form)")
+        u = form.coefficients[integ.coeffs[0]]
+        dm = u.function_space.dofmap
+        return _lib.make_coeffs(fused=(u.x.array, dm.dev, dm.shape[1], dm.bs))
+    return _lib.make_coeffs()
+
+
+def _translate(e):
+    from . import _lib
+
+    if isinstance(e, _lib.BfxError) and e.status == _lib.ERR_NOT_IN_SPARSITY:
+        return RuntimeError("Entry not in sparsity")
+    return e
+
+
+def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=None, strategy=None):
+    """fem::assemble_matrix(A.mat_add_values(), a, bcs) — fem/assembler.h:513-630.
+
+    Does not zero A and does not finalise it (assembler.h:497-498): call ``A.scatter_reverse()``
+    afterwards.  bc rows/columns are zeroed in the element tensors (assemble_matrix_impl.h:161-196);
+    use ``set_diagonal`` for the diagonal."""
+    from . import _lib
+
+    assert a.rank == 2
+    V0, V1 = a.function_spaces
+    bc0 = _bc_markers(V0, bcs)
+    bc1 = _bc_markers(V1, bcs)
+    consts = pack_constants(a) if constants is None else np.asarray(constants, dtype=np.float64)
+    carr, nc = _lib.constants_array(consts)
+    strat = _lib.ASM_ATOMIC if strategy is None else strategy
+    try:
+        for (itype, ident), integ in a._integrals.items():
+            plan = _asm_plan(a, integ, itype, A)
+            cf = _coeffs_for(a, integ, None if coeffs is None else coeffs[(itype, ident)])
+            if itype == IntegralType.cell:
+                mode = _lib.VALUES_OVERWRITE if A._is_zero else _lib.VALUES_ADD
+                _lib.check(_lib.lib.bfx_assemble_matrix_cells(
+                    plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
+                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(), strat, mode,
+                    _lib.current_stream()))
+            elif itype == IntegralType.exterior_facet:
+                ent, n = _entities_dev(a, integ, itype)
+                _lib.check(_lib.lib.bfx_assemble_matrix_facets(
+                    plan, integ.kernel, a.mesh.x.data_ptr(), ent.data_ptr(), n, None if bc0 is None else bc0.data_ptr(),
+                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(),
+                    _lib.current_stream()))
+            else:
+                raise NotImplementedError(f"integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
+            A._is_zero = False
+    except _lib.BfxError as e:
+        raise _translate(e) from e
+    return A
+
+
+def assemble_vector(b, L: Form, constants=None, coeffs=None):
+    """fem::assemble_vector(b, L) — fem/assembler.h:230-257: accumulates into b (not zeroed, ghosts not
+    scattered: call ``b.scatter_reverse(InsertMode.add)``)."""
+    from . import _lib
+
+    assert L.rank == 1
+    arr = b.array if isinstance(b, la.Vector) else b
+    consts = pack_constants(L) if constants is None else np.asarray(constants, dtype=np.float64)
+    carr, nc = _lib.constants_array(consts)
+    for (itype, ident), integ in L._integrals.items():
+        plan = _asm_plan(L, integ, itype, None)
+        cf = _coeffs_for(L, integ, None if coeffs is None else coeffs[(itype, ident)])
+        if itype == IntegralType.cell:
+            _lib.check(_lib.lib.bfx_assemble_vector_cells(plan, integ.kernel, L.mesh.x.data_ptr(), C.byref(cf), carr, nc,
+                                                          arr.data_ptr(), _lib.ASM_ATOMIC, _lib.current_stream()))
+        elif itype == IntegralType.exterior_facet:
+            ent, n = _entities_dev(L, integ, itype)
+            _lib.check(_lib.lib.bfx_assemble_vector_facets(plan, integ.kernel, L.mesh.x.data_ptr(), ent.data_ptr(), n,
+                                                           C.byref(cf), carr, nc, arr.data_ptr(), _lib.current_stream()))
+        else:
+            raise NotImplementedError(f"integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
+    return b
+
+
+def apply_lifting(b, a, bcs, x0=None, alpha: float = 1.0, constants=None, coeffs=None):
+    """fem::apply_lifting — fem/assembler.h:336-493: b <- b - alpha A_j (g_j - x0_j) for every block j.
+
+    ``a``: list of bilinear forms (or None), ``bcs``: list (per form) of lists of DirichletBC,
+    ``x0``: optional list of device tensors."""
+    from . import _lib
+
+    torch = _torch()
+    arr = b.array if isinstance(b, la.Vector) else b
+    if all(ai is None for ai in a):
+        return
+    if x0 is not None and len(x0) != len(a):
+        raise RuntimeError("Mismatch in size between x0 and bilinear form in assembler.")
+    if len(a) != len(bcs):
+        raise RuntimeError("Mismatch in size between a and bcs in assembler.")
+    for j, aj in enumerate(a):
+        if aj is None or not bcs[j]:
+            continue
+        V1 = aj.function_spaces[1]
+        im1 = V1.dofmap.index_map
+        crange = V1.dofmap.index_map_bs * (im1.size_local + im1.num_ghosts)
+        markers = torch.zeros(crange, dtype=torch.int8, device=la._device())
+        values = torch.zeros(crange, dtype=torch.float64, device=la._device())
+        for bc in bcs[j]:
+            bc.mark_dofs(markers)
+            bc.set(values, None, 1.0)
+        consts = pack_constants(aj) if constants is None else np.asarray(constants[j], dtype=np.float64)
+        carr, nc = _lib.constants_array(consts)
+        for (itype, ident), integ in aj._integrals.items():
+            if itype != IntegralType.cell:
+                raise NotImplementedError("lifting of facet integrals")
+            plan = _asm_plan(aj, integ, itype, None)
+            cf = _coeffs_for(aj, integ, None if coeffs is None else coeffs[j][(itype, ident)])
+            _lib.check(_lib.lib.bfx_lift_bc_cells(
+                plan, integ.kernel, aj.mesh.x.data_ptr(), C.byref(cf), carr, nc, arr.data_ptr(), values.data_ptr(),
+                markers.data_ptr(), None if x0 is None else x0[j].data_ptr(), float(alpha), _lib.current_stream()))
+
+
+def set_diagonal(A: la.MatrixCSR, V: FunctionSpace, bcs, diagonal: float = 1.0):
+    """fem::set_diagonal — fem/assembler.h:644-686: A[dof,dof] = diagonal (SET) on OWNED bc rows."""
+    from . import _lib
+
+    for bc in bcs:
+        if V.contains(bc.function_space):
+            dofs, n_owned = bc.dof_indices()
+            if n_owned == 0:
+                continue
+            try:
+                _lib.check(_lib.lib.bfx_csr_set_diagonal(A._csr, A.data.data_ptr(), bc.dofs_dev.data_ptr(), n_owned,
+                                                         float(diagonal), _lib.current_stream()))
+            except _lib.BfxError as e:
+                raise _translate(e) from e
+            A._is_zero = False

@@ -1,0 +1,669 @@
+"""Host mirror of dolfinx::la — SparsityPattern, MatrixCSR, Vector — over the libbfx C-ABI.
+
+Reference: cpp/dolfinx/la/{SparsityPattern.h,SparsityPattern.cpp,MatrixCSR.h,matrix_csr_impl.h,Vector.h}
+and the Python surface python/dolfinx/la/__init__.py (same method names: ``insert``, ``finalize``,
+``add``, ``set``, ``scatter_reverse``, ``squared_norm``, ``mult``, ``to_dense``, ``to_scipy``,
+``scatter_forward`` …).  Values live in HBM as torch tensors (torch is the allocator); every
+arithmetic call goes to a CUDA kernel of libbfx.so — there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+
+from .common import Comm, IndexMap, Scatterer, cached_scatterer
+
+
+class InsertMode(enum.IntEnum):
+    add = 0
+    insert = 1
+
+
+class Norm(enum.IntEnum):
+    l1 = 0
+    l2 = 1
+    linf = 2
+    frobenius = 3
+
+
+class BlockMode(enum.IntEnum):
+    compact = 0
+    expanded = 1
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _device():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        from ._lib import BfxError, ERR_NO_DEVICE
+
+        raise BfxError(ERR_NO_DEVICE, "no CUDA device: dolfinx_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------
+# SparsityPattern
+# ---------------------------------------------------------------------------------------------
+class SparsityPattern:
+    """la::SparsityPattern (la/SparsityPattern.h:25-180).
+
+    ``insert`` / ``insert_diagonal`` append to a COO cache like the reference
+    (SparsityPattern.cpp:194-240).  ``insert_cells`` is the bulk entry used by
+    ``fem.create_sparsity_pattern`` (fem::sparsitybuild::cells, fem/sparsitybuild.h:36-50): with
+    device dofmaps the pattern is built on the GPU without ever materialising the COO cache.
+    ``finalize`` follows SparsityPattern.cpp:264-491 bit for bit: ghost-row entries go to the row
+    owners as (global row, global col, col owner) triplets, unknown columns are appended to the
+    column IndexMap in arrival order, rows are de-duplicated and sorted by local column index.
+    """
+
+    def __init__(self, comm: Comm, maps, bs):
+        self.comm = comm
+        self._index_maps = [maps[0], maps[1]]
+        self._bs = (int(bs[0]), int(bs[1]))
+        self._segments = []  # ("coo", rows, cols) | ("cells", cells, dofmap0, dofmap1)
+        self._finalized = False
+        self._edges = self._offsets = self._off_diag = None
+        self._csr = None  # device structure (bfx_csr_t*) when built natively
+        self._col_ghosts = self._col_ghost_owners = None
+
+    # -- insertion -------------------------------------------------------------------------------
+    def _check_open(self):
+        if self._finalized:
+            raise RuntimeError("Cannot insert into sparsity pattern. It has already been finalized")
+
+    def insert(self, rows, cols):
+        """SparsityPattern::insert(rows, cols): dense block rows x cols (SparsityPattern.cpp:207-227)."""
+        self._check_open()
+        rows = np.atleast_1d(np.asarray(rows, dtype=np.int32))
+        cols = np.atleast_1d(np.asarray(cols, dtype=np.int32))
+        self._segments.append(("coo", np.repeat(rows, cols.size), np.tile(cols, rows.size)))
+
+    def insert_diagonal(self, rows):
+        """SparsityPattern.cpp:229-240"""
+        self._check_open()
+        rows = np.atleast_1d(np.asarray(rows, dtype=np.int32))
+        self._segments.append(("coo", rows.copy(), rows.copy()))
+
+    def insert_cells(self, cells, dofmap0, dofmap1):
+        """fem::sparsitybuild::cells: for every cell insert(dofmap0[cell], dofmap1[cell]).
+
+        ``cells`` None means all rows of the dofmaps.  numpy inputs are expanded on the host
+        (reference behaviour); torch CUDA inputs are kept for the native device build.
+        """
+        self._check_open()
+        if isinstance(dofmap0, np.ndarray):
+            d0 = dofmap0 if cells is None else dofmap0[np.asarray(cells)]
+            d1 = dofmap1 if cells is None else dofmap1[np.asarray(cells)]
+            nd0, nd1 = d0.shape[1], d1.shape[1]
+            rows = np.repeat(d0[:, :, None], nd1, axis=2).reshape(-1).astype(np.int32)
+            cols = np.repeat(d1[:, None, :], nd0, axis=1).reshape(-1).astype(np.int32)
+            self._segments.append(("coo", rows, cols))
+        else:
+            self._segments.append(("cells", cells, dofmap0, dofmap1))
+
+    # -- finalize --------------------------------------------------------------------------------
+    def _ghost_row_lists(self, local_size0, num_rows0):
+        """Per ghost row: columns in insertion order, first occurrences only."""
+        n_ghost = num_rows0 - local_size0
+        lists = [[] for _ in range(n_ghost)]
+        seen = [set() for _ in range(n_ghost)]
+        for seg in self._segments:
+            if seg[0] == "coo":
+                _, rows, cols = seg
+                sel = np.flatnonzero(rows >= local_size0)
+                for r, c in zip(rows[sel] - local_size0, cols[sel]):
+                    c = int(c)
+                    if c not in seen[r]:
+                        seen[r].add(c)
+                        lists[r].append(c)
+            else:
+                from . import _lib
+
+                _, cells, dm0, dm1 = seg
+                ncells = dm0.shape[0] if cells is None else cells.numel()
+                counts = np.zeros(n_ghost, dtype=np.int64)
+                args = (num_rows0, local_size0, _lib.dptr(dm0), dm0.shape[1], _lib.dptr(dm1), dm1.shape[1],
+                        _lib.dptr(cells), ncells)
+                _lib.check(_lib.lib.bfx_sparsity_ghost_rows(*args, counts.ctypes.data, None, _lib.current_stream()))
+                packed = np.zeros(int(counts.sum()), dtype=np.int32)
+                _lib.check(_lib.lib.bfx_sparsity_ghost_rows(*args, counts.ctypes.data, packed.ctypes.data, _lib.current_stream()))
+                off = np.concatenate([[0], np.cumsum(counts)])
+                for g in range(n_ghost):
+                    for c in packed[off[g]:off[g + 1]]:
+                        c = int(c)
+                        if c not in seen[g]:
+                            seen[g].add(c)
+                            lists[g].append(c)
+        return lists
+
+    def finalize(self):
+        if self._finalized:
+            raise RuntimeError("Sparsity pattern has already been finalised.")
+        m0, m1 = self._index_maps
+        local_size0, local_size1 = m0.size_local, m1.size_local
+        num_rows0 = local_size0 + m0.num_ghosts
+        col_ghosts = list(m1.ghosts)
+        col_ghost_owners = list(m1.owners)
+        recv_rows = np.zeros(0, dtype=np.int32)
+        recv_cols = np.zeros(0, dtype=np.int32)
+
+        if self.comm.size > 1:
+            # (global row, global col, col owner) triplets of ghost rows -> owners (:291-383)
+            lists = self._ghost_row_lists(local_size0, num_rows0)
+            neighbour_rank = np.searchsorted(m0.src, m0.owners)
+            bufs = [[] for _ in m0.src]
+            for i, cols_i in enumerate(lists):
+                if not cols_i:
+                    continue
+                cl = np.asarray(cols_i, dtype=np.int64)
+                owned = cl < local_size1
+                gcol = np.where(owned, cl + m1.local_range[0], 0)
+                gown = np.full(cl.size, self.comm.rank, dtype=np.int64)
+                if np.any(~owned):
+                    gi = cl[~owned] - local_size1
+                    gcol[~owned] = m1.ghosts[gi]
+                    gown[~owned] = m1.owners[gi]
+                trip = np.stack([np.full(cl.size, m0.ghosts[i], dtype=np.int64), gcol, gown], axis=1).reshape(-1)
+                bufs[neighbour_rank[i]].append(trip)
+            send = [np.concatenate(b) if b else np.zeros(0, dtype=np.int64) for b in bufs]
+            recv = self.comm.neighbor_alltoallv(m0.src, m0.dest, send, dtype=np.int64)
+            data_in = np.concatenate(recv) if recv else np.zeros(0, dtype=np.int64)
+            # new ghost columns in arrival order (:389-423)
+            g2l = {int(g): local_size1 + i for i, g in enumerate(col_ghosts)}
+            rr, rc = [], []
+            local_i = local_size1 + len(col_ghosts)
+            for i in range(0, data_in.size, 3):
+                row_local = int(data_in[i]) - m0.local_range[0]
+                col, owner = int(data_in[i + 1]), int(data_in[i + 2])
+                rr.append(row_local)
+                if m1.local_range[0] <= col < m1.local_range[1]:
+                    rc.append(col - m1.local_range[0])
+                else:
+                    j = g2l.get(col)
+                    if j is None:
+                        j = g2l[col] = local_i
+                        col_ghosts.append(col)
+                        col_ghost_owners.append(owner)
+                        local_i += 1
+                    rc.append(j)
+            recv_rows = np.asarray(rr, dtype=np.int32)
+            recv_cols = np.asarray(rc, dtype=np.int32)
+
+        cell_segs = [s for s in self._segments if s[0] == "cells"]
+        coo_rows = [s[1] for s in self._segments if s[0] == "coo"] + [recv_rows]
+        coo_cols = [s[2] for s in self._segments if s[0] == "coo"] + [recv_cols]
+        coo_rows = np.concatenate(coo_rows).astype(np.int32)
+        coo_cols = np.concatenate(coo_cols).astype(np.int32)
+        if len(cell_segs) == 1:
+            # native device build: per-row dedup + sort (:438-478)
+            from . import _lib
+
+            _, cells, dm0, dm1 = cell_segs[0]
+            ncells = dm0.shape[0] if cells is None else cells.numel()
+            h = C.c_void_p()
+            _lib.check(
+                _lib.lib.bfx_sparsity_build(
+                    C.byref(h), num_rows0, local_size0, local_size1, _lib.dptr(dm0), dm0.shape[1], _lib.dptr(dm1),
+                    dm1.shape[1], _lib.dptr(cells), ncells, coo_rows.ctypes.data if coo_rows.size else None,
+                    coo_cols.ctypes.data if coo_cols.size else None, coo_rows.size, self._bs[0], self._bs[1],
+                    _lib.current_stream(),
+                )
+            )
+            self._csr = h
+        elif len(cell_segs) > 1:
+            raise NotImplementedError("at most one device cell list per SparsityPattern")
+        else:
+            if coo_rows.size and (coo_rows.min() < 0 or coo_rows.max() >= num_rows0):
+                raise RuntimeError("SparsityPattern: row index out of range")
+            ncols = local_size1 + len(col_ghosts)
+            keys = np.unique(coo_rows.astype(np.int64) * ncols + coo_cols)
+            rows_u = keys // ncols
+            self._edges = (keys % ncols).astype(np.int32)
+            offsets = np.zeros(num_rows0 + 1, dtype=np.int64)
+            np.add.at(offsets, rows_u + 1, 1)
+            self._offsets = np.cumsum(offsets)
+            diag = np.zeros(num_rows0, dtype=np.int64)
+            np.add.at(diag, rows_u[self._edges < local_size1], 1)
+            self._off_diag = diag.astype(np.int32)
+
+        self._segments = []
+        self._col_ghosts = np.asarray(col_ghosts, dtype=np.int64)
+        self._col_ghost_owners = np.asarray(col_ghost_owners, dtype=np.int32)
+        # new column IndexMap (:488-490)
+        if self.comm.size > 1 or len(col_ghosts) != m1.num_ghosts:
+            self._index_maps[1] = IndexMap(self.comm, m1.size_local, self._col_ghosts, self._col_ghost_owners)
+        self._finalized = True
+
+    # -- accessors -------------------------------------------------------------------------------
+    def _need_final(self):
+        if not self._finalized:
+            raise RuntimeError("Sparsity pattern has not been finalised.")
+
+    def _download(self):
+        if self._edges is None:
+            from . import _lib
+
+            n = self._index_maps[0].size_local + self._index_maps[0].num_ghosts
+            nnz = int(_lib.lib.bfx_csr_nnz(self._csr))
+            self._offsets = np.empty(n + 1, dtype=np.int64)
+            self._edges = np.empty(nnz, dtype=np.int32)
+            od = np.empty(n, dtype=np.int64)
+            _lib.check(_lib.lib.bfx_csr_get_structure(self._csr, self._offsets.ctypes.data, self._edges.ctypes.data, od.ctypes.data))
+            self._off_diag = (od - self._offsets[:-1]).astype(np.int32)
+
+    def index_map(self, dim):
+        return self._index_maps[dim]
+
+    def block_size(self, dim):
+        return self._bs[dim]
+
+    @property
+    def num_nonzeros(self):
+        self._need_final()
+        if self._edges is None:
+            from . import _lib
+
+            return int(_lib.lib.bfx_csr_nnz(self._csr))
+        return int(self._edges.size)
+
+    @property
+    def graph(self):
+        """(edges int32, offsets int64) — SparsityPattern::graph (SparsityPattern.cpp:514-520)."""
+        self._need_final()
+        self._download()
+        return self._edges, self._offsets
+
+    @property
+    def off_diagonal_offsets(self):
+        self._need_final()
+        self._download()
+        return self._off_diag
+
+    def nnz_diag(self, row):
+        return int(self.off_diagonal_offsets[row])
+
+    def nnz_off_diag(self, row):
+        e, o = self.graph
+        return int(o[row + 1] - o[row] - self._off_diag[row])
+
+    def column_indices(self):
+        """SparsityPattern.cpp:247-259"""
+        self._need_final()
+        m1 = self._index_maps[1]
+        return np.concatenate([np.arange(m1.local_range[0], m1.local_range[1], dtype=np.int64), self._col_ghosts])
+
+
+# ---------------------------------------------------------------------------------------------
+# Vector
+# ---------------------------------------------------------------------------------------------
+class Vector:
+    """la::Vector<double> with device storage (la/Vector.h:47-422).
+
+    ``array`` is a torch CUDA tensor [owned*bs | ghosts*bs]; scatter_forward / scatter_reverse run the
+    pack kernel, the NCCL exchange and the unpack kernel of libbfx (Vector.h:219-379).
+    """
+
+    def __init__(self, index_map: IndexMap, bs: int = 1, array=None):
+        torch = _torch()
+        self.index_map, self.bs = index_map, int(bs)
+        n = self.bs * (index_map.size_local + index_map.num_ghosts)
+        self.array = torch.zeros(n, dtype=torch.float64, device=_device()) if array is None else array
+        assert self.array.numel() == n
+        self._scatterer = cached_scatterer(index_map, self.bs)
+
+    @property
+    def block_size(self):
+        return self.bs
+
+    @property
+    def scatterer(self) -> Scatterer:
+        return self._scatterer
+
+    def set(self, v: float):
+        self.array.fill_(v)
+
+    def _n_owned(self):
+        return self.bs * self.index_map.size_local
+
+    def scatter_fwd_begin(self):
+        from . import _lib
+
+        if self.index_map.comm.size > 1:
+            _lib.check(_lib.lib.bfx_scatter_fwd_begin(self._scatterer.device_plan(), self.array.data_ptr(), _lib.current_stream()))
+
+    def scatter_fwd_end(self):
+        from . import _lib
+
+        if self.index_map.comm.size > 1:
+            _lib.check(_lib.lib.bfx_scatter_fwd_end(self._scatterer.device_plan(), self.array.data_ptr(), self._n_owned(), _lib.current_stream()))
+
+    def scatter_forward(self):
+        """Vector::scatter_fwd — owner values to ghosts."""
+        self.scatter_fwd_begin()
+        self.scatter_fwd_end()
+
+    def scatter_rev_begin(self):
+        from . import _lib
+
+        if self.index_map.comm.size > 1:
+            _lib.check(_lib.lib.bfx_scatter_rev_begin(self._scatterer.device_plan(), self.array.data_ptr(), self._n_owned(), _lib.current_stream()))
+
+    def scatter_rev_end(self, mode: InsertMode = InsertMode.add):
+        from . import _lib
+
+        if self.index_map.comm.size > 1:
+            op = 1 if mode == InsertMode.add else 0
+            _lib.check(_lib.lib.bfx_scatter_rev_end(self._scatterer.device_plan(), self.array.data_ptr(), op, _lib.current_stream()))
+
+    def scatter_reverse(self, mode: InsertMode = InsertMode.add):
+        """Vector::scatter_rev(op) — ghost values to owners (add or insert)."""
+        self.scatter_rev_begin()
+        self.scatter_rev_end(mode)
+
+
+def inner_product(a: Vector, b: Vector) -> float:
+    """la::inner_product (la/Vector.h:434-460): owned entries, summed over ranks."""
+    from . import _lib
+
+    n = a.bs * a.index_map.size_local
+    if n != b.bs * b.index_map.size_local:
+        raise RuntimeError("Incompatible vector sizes")
+    out = C.c_double(0.0)
+    _lib.check(_lib.lib.bfx_dot(n, a.array.data_ptr(), b.array.data_ptr(), C.byref(out), _lib.current_stream()))
+    return a.index_map.comm.allreduce_sum(out.value)
+
+
+def squared_norm(a: Vector) -> float:
+    return inner_product(a, a)
+
+
+def norm(x: Vector, type: Norm = Norm.l2) -> float:
+    """la::norm (la/Vector.h:479-514)."""
+    from . import _lib
+
+    n = x.bs * x.index_map.size_local
+    out = C.c_double(0.0)
+    if type == Norm.l2:
+        return float(np.sqrt(squared_norm(x)))
+    if type == Norm.l1:
+        _lib.check(_lib.lib.bfx_norm(n, x.array.data_ptr(), 0, C.byref(out), _lib.current_stream()))
+        return x.index_map.comm.allreduce_sum(out.value)
+    if type == Norm.linf:
+        _lib.check(_lib.lib.bfx_norm(n, x.array.data_ptr(), 2, C.byref(out), _lib.current_stream()))
+        return x.index_map.comm.allreduce_max(out.value)
+    raise RuntimeError("Norm type not supported")
+
+
+# ---------------------------------------------------------------------------------------------
+# MatrixCSR
+# ---------------------------------------------------------------------------------------------
+class MatrixCSR:
+    """la::MatrixCSR<double> with device storage (la/MatrixCSR.h:67-624).
+
+    ``data`` (torch CUDA, nnz*bs0*bs1), ``indices`` int32, ``indptr`` int64 keep the reference's
+    names and widths (python/dolfinx/la/__init__.py).  The constructor builds the ghost-row
+    exchange plan of la/MatrixCSR.h:705-849.
+    """
+
+    def __init__(self, pattern: SparsityPattern, block_mode: BlockMode = BlockMode.compact):
+        from . import _lib
+
+        if block_mode != BlockMode.compact:
+            raise NotImplementedError("BlockMode.expanded: expand the pattern with bs=1 maps before constructing")
+        pattern._need_final()
+        torch = _torch()
+        self._pattern = pattern
+        self._index_maps = [pattern.index_map(0), pattern.index_map(1)]
+        self._bs = (pattern.block_size(0), pattern.block_size(1))
+        m0 = self._index_maps[0]
+        n_all = m0.size_local + m0.num_ghosts
+        if pattern._csr is None:
+            edges, offsets = pattern.graph
+            off_diag = (pattern.off_diagonal_offsets.astype(np.int64) + offsets[:-1])  # :695-703
+            h = C.c_void_p()
+            _lib.check(_lib.lib.bfx_csr_create(C.byref(h), n_all, m0.size_local, offsets.ctypes.data,
+                                               np.ascontiguousarray(edges).ctypes.data, off_diag.ctypes.data,
+                                               self._bs[0], self._bs[1]))
+            self._csr = h
+        else:
+            self._csr = pattern._csr
+        self._nnz = int(_lib.lib.bfx_csr_nnz(self._csr))
+        self.data = torch.zeros(self._nnz * self._bs[0] * self._bs[1], dtype=torch.float64, device=_device())
+        self._is_zero = True
+        self._scatter_plan = None
+        self._asm_plans = {}
+        self._build_ghost_plan()
+
+    # -- ghost-row plan (la/MatrixCSR.h:705-849) -------------------------------------------------
+    def _build_ghost_plan(self):
+        m0, m1 = self._index_maps
+        comm = m0.comm
+        self._plan_arrays = None
+        if comm.size == 1:
+            return
+        from . import _lib
+
+        bs2 = self._bs[0] * self._bs[1]
+        indices, indptr = self.indices, self.indptr
+        ls0, ls1 = m0.size_local, m1.size_local
+        ghost_row_to_rank = np.searchsorted(m0.src, m0.owners).astype(np.int32)
+        row_len = np.diff(indptr[ls0:])
+        data_per_proc = np.zeros(len(m0.src), dtype=np.int64)
+        np.add.at(data_per_proc, ghost_row_to_rank, row_len)
+        val_send_disp = np.concatenate([[0], np.cumsum(data_per_proc)]).astype(np.int64)
+        # (global row, global col) of every ghost-row entry, grouped by owner in ghost-row order
+        grows = np.repeat(np.arange(m0.num_ghosts), row_len)
+        gcols_local = indices[indptr[ls0]:]
+        gcol = m1.local_to_global(gcols_local)
+        grow = m0.ghosts[grows]
+        order = np.argsort(ghost_row_to_rank[grows], kind="stable")
+        pairs = np.stack([grow[order], gcol[order]], axis=1).reshape(-1)
+        send = [pairs[2 * val_send_disp[i]:2 * val_send_disp[i + 1]] for i in range(len(m0.src))]
+        recv = comm.neighbor_alltoallv(m0.src, m0.dest, send, dtype=np.int64)
+        recv_disp = np.concatenate([[0], np.cumsum([len(a) for a in recv])]).astype(np.int64)
+        arr = np.concatenate(recv) if recv else np.zeros(0, dtype=np.int64)
+        # positions in the owner's CSR (:820-846)
+        lrow = (arr[0::2] - m0.local_range[0]).astype(np.int64)
+        gc = arr[1::2]
+        lcol = gc - m1.local_range[0]
+        ghost_mask = (lcol < 0) | (lcol >= ls1)
+        if np.any(ghost_mask):
+            order1 = np.argsort(m1.ghosts, kind="stable")
+            pos = np.searchsorted(m1.ghosts[order1], gc[ghost_mask])
+            lcol[ghost_mask] = ls1 + order1[pos]
+        unpack = np.empty(lrow.size, dtype=np.int64)
+        for k in range(lrow.size):
+            c0, c1 = indptr[lrow[k]], indptr[lrow[k] + 1]
+            d = c0 + np.searchsorted(indices[c0:c1], lcol[k])
+            if d >= c1 or indices[d] != lcol[k]:
+                raise RuntimeError("MatrixCSR: received ghost-row entry not in sparsity")
+            unpack[k] = d
+        self._plan_arrays = dict(
+            ghost_row_to_rank=ghost_row_to_rank, val_send_disp=val_send_disp * bs2, val_recv_disp=bs2 * recv_disp // 2,
+            unpack_pos=unpack, src=m0.src.copy(), dest=m0.dest.copy(),
+        )
+
+    def _device_scatter_plan(self):
+        if self._scatter_plan is None and self._plan_arrays is not None:
+            from . import _lib
+
+            p = self._plan_arrays
+            m0 = self._index_maps[0]
+            h = C.c_void_p()
+            _lib.check(
+                _lib.lib.bfx_csr_scatter_create(
+                    C.byref(h), self._csr, m0.comm.nccl, p["ghost_row_to_rank"].ctypes.data, m0.num_ghosts,
+                    np.ascontiguousarray(p["val_send_disp"]).ctypes.data, np.ascontiguousarray(p["src"]).ctypes.data,
+                    len(p["src"]), np.ascontiguousarray(p["val_recv_disp"]).ctypes.data,
+                    np.ascontiguousarray(p["dest"]).ctypes.data, len(p["dest"]), p["unpack_pos"].ctypes.data,
+                )
+            )
+            self._scatter_plan = h
+        return self._scatter_plan
+
+    # -- accessors -------------------------------------------------------------------------------
+    def index_map(self, i):
+        return self._index_maps[i]
+
+    @property
+    def block_size(self):
+        return list(self._bs)
+
+    @property
+    def bs(self):
+        return self._bs
+
+    @property
+    def indices(self):
+        return self._pattern.graph[0]
+
+    @property
+    def indptr(self):
+        return self._pattern.graph[1]
+
+    @property
+    def off_diag_offset(self):
+        return self._pattern.off_diagonal_offsets.astype(np.int64) + self.indptr[:-1]
+
+    def num_owned_rows(self):
+        return self._index_maps[0].size_local
+
+    def num_all_rows(self):
+        return self._index_maps[0].size_local + self._index_maps[0].num_ghosts
+
+    # -- value manipulation ------------------------------------------------------------------------
+    def set_value(self, x: float):
+        """MatrixCSR::set(value) (la/MatrixCSR.h:239-241)."""
+        self.data.fill_(x)
+        self._is_zero = x == 0.0
+
+    def _insert(self, x, rows, cols, bs, op):
+        from . import _lib
+
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        # dispatch of MatrixCSR::add / set (la/MatrixCSR.h:265-335)
+        if bs == self._bs[0] and bs == self._bs[1]:
+            kind, d0, d1 = 0, self._bs[0], self._bs[1]
+        elif self._bs[0] == 1 and self._bs[1] == 1:
+            kind, d0, d1 = 1, bs, bs
+        elif bs == 1:
+            kind, d0, d1 = 2, 1, 1
+        else:
+            raise RuntimeError("Unsupported block size in MatrixCSR insertion")
+        assert x.size == rows.size * cols.size * d0 * d1
+        try:
+            _lib.check(_lib.lib.bfx_csr_insert(self._csr, self.data.data_ptr(), kind, d0, d1, x.ctypes.data,
+                                               rows.ctypes.data, rows.size, cols.ctypes.data, cols.size, op,
+                                               _lib.current_stream()))
+        except _lib.BfxError as e:
+            if e.status == _lib.ERR_NOT_IN_SPARSITY:
+                raise RuntimeError("Entry not in sparsity") from e
+            raise
+        self._is_zero = False
+
+    def add(self, x, rows, cols, bs=1):
+        """MatrixCSR::add (la/MatrixCSR.h:310-335)."""
+        self._insert(x, rows, cols, bs, 1)
+
+    def set(self, x, rows, cols, bs=1):
+        """MatrixCSR::set (la/MatrixCSR.h:265-292)."""
+        self._insert(x, rows, cols, bs, 0)
+
+    def scatter_rev_begin(self):
+        from . import _lib
+
+        p = self._device_scatter_plan()
+        if p is not None:
+            _lib.check(_lib.lib.bfx_csr_scatter_rev_begin(p, self.data.data_ptr(), _lib.current_stream()))
+
+    def scatter_rev_end(self):
+        from . import _lib
+
+        p = self._device_scatter_plan()
+        if p is not None:
+            _lib.check(_lib.lib.bfx_csr_scatter_rev_end(p, self.data.data_ptr(), _lib.current_stream()))
+
+    def scatter_reverse(self):
+        """MatrixCSR::scatter_rev (la/MatrixCSR.h:384-468)."""
+        self.scatter_rev_begin()
+        self.scatter_rev_end()
+
+    def squared_norm(self) -> float:
+        """MatrixCSR::squared_norm (la/MatrixCSR.h:473-486)."""
+        from . import _lib
+
+        out = C.c_double(0.0)
+        _lib.check(_lib.lib.bfx_csr_squared_norm(self._csr, self.data.data_ptr(), C.byref(out), _lib.current_stream()))
+        return self._index_maps[0].comm.allreduce_sum(out.value)
+
+    def mult(self, x: Vector, y: Vector, transpose: bool = False):
+        """MatrixCSR::mult / multT (la/MatrixCSR.h:877-1016): y += A x (or A^T x).
+
+        x must live on the matrix's column map ``index_map(1)``.
+        """
+        from . import _lib
+
+        st = _lib.current_stream()
+        L = _lib.lib
+        multi = self._index_maps[0].comm.size > 1
+        if not transpose:
+            if not multi:
+                _lib.check(L.bfx_spmv(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_FULL, st))
+                return
+            x.scatter_fwd_begin()
+            _lib.check(L.bfx_spmv(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
+            x.scatter_fwd_end()
+            _lib.check(L.bfx_spmv(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
+        else:
+            ncl = self._bs[1] * self._index_maps[1].size_local
+            y.array[ncl:].zero_()
+            _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
+            y.scatter_reverse(InsertMode.add)
+            _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
+
+    def to_dense(self):
+        """MatrixCSR::to_dense (la/MatrixCSR.h:343-370), host numpy."""
+        bs0, bs1 = self._bs
+        nrows = self.num_all_rows()
+        ncols = self._index_maps[1].size_local + self._index_maps[1].num_ghosts
+        A = np.zeros((nrows * bs0, ncols * bs1))
+        data = self.data.cpu().numpy().reshape(-1, bs0, bs1)
+        indptr, indices = self.indptr, self.indices
+        for r in range(nrows):
+            for j in range(indptr[r], indptr[r + 1]):
+                c = indices[j]
+                A[r * bs0:(r + 1) * bs0, c * bs1:(c + 1) * bs1] = data[j]
+        return A
+
+    def to_scipy(self, ghosted=False):
+        """python/dolfinx/la/__init__.py:279-319 — the storage *is* SciPy CSR/BSR."""
+        import scipy.sparse as sp
+
+        bs0, bs1 = self._bs
+        ncols = self._index_maps[1].size_local + self._index_maps[1].num_ghosts
+        nrows = self.num_all_rows() if ghosted else self.num_owned_rows()
+        nnzlocal = self.indptr[nrows]
+        data = self.data.cpu().numpy()
+        indptr, indices = self.indptr[: nrows + 1], self.indices[:nnzlocal]
+        if bs0 == 1 and bs1 == 1:
+            return sp.csr_matrix((data[:nnzlocal], indices, indptr), shape=(nrows, ncols))
+        return sp.bsr_matrix((data[: nnzlocal * bs0 * bs1].reshape(-1, bs0, bs1), indices, indptr),
+                             shape=(bs0 * nrows, bs1 * ncols))
+
+
+def matrix_csr(pattern: SparsityPattern, block_mode: BlockMode = BlockMode.compact) -> MatrixCSR:
+    return MatrixCSR(pattern, block_mode)
+
+
+def vector(index_map: IndexMap, bs: int = 1) -> Vector:
+    return Vector(index_map, bs)

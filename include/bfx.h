@@ -1,0 +1,290 @@
+/*
+ * bfx.h — C-ABI of the B200-native DOLFINx hot path (libbfx.so).
+ *
+ * One CUDA context per process / rank / GPU.  Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary.  Every function returns an int status (0 = BFX_OK); the text of
+ * the last error on the calling thread is available from bfx_last_error().  Nothing throws.
+ * "dev" pointers are device pointers of the current device; "any" pointers may be host or
+ * device (copied with cudaMemcpyDefault at plan-build time).  Hot calls take a stream
+ * (cudaStream_t passed as void*; NULL = legacy default stream) and never allocate.
+ *
+ * Each entry point cites the reference interface it replaces; paths are relative to
+ * /root/reference/cpp/dolfinx (DOLFINx 0.12.0.dev0).
+ */
+#ifndef BFX_H
+#define BFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define BFX_VERSION 100
+
+  /* ---- status ---------------------------------------------------------------------------- */
+  enum
+  {
+    BFX_OK = 0,
+    BFX_ERR_CUDA = 1,            /* a CUDA runtime call failed (text in bfx_last_error) */
+    BFX_ERR_INVALID = 2,         /* invalid argument */
+    BFX_ERR_NOT_IN_SPARSITY = 3, /* "Entry not in sparsity" — la/matrix_csr_impl.h:93-94,161-162,223-224 */
+    BFX_ERR_UNSUPPORTED = 4,     /* kernel id / block size / row length not supported */
+    BFX_ERR_NCCL = 5,            /* NCCL unavailable or a NCCL call failed */
+    BFX_ERR_NO_DEVICE = 6        /* no CUDA device: the product has no CPU fallback */
+  };
+
+  typedef void* bfx_stream_t;
+  typedef struct bfx_csr bfx_csr_t;         /* la::MatrixCSR structure on device (la/MatrixCSR.h:67-70) */
+  typedef struct bfx_asm bfx_asm_t;         /* per-(form integral) assembly plan */
+  typedef struct bfx_scatter bfx_scatter_t; /* common::Scatterer plan on device (common/Scatterer.h:46-538) */
+  typedef struct bfx_comm bfx_comm_t;       /* NCCL communicator (replaces MPI_Comm on the data path) */
+
+  const char* bfx_last_error(void);
+  const char* bfx_status_string(int status);
+  int bfx_version(void);
+  int bfx_device_count(int* count);
+  int bfx_set_device(int device);
+
+  /* ---- memory plumbing for non-torch hosts (C++ API mirror) ------------------------------ */
+  int bfx_malloc(void** dev_ptr, size_t bytes);
+  int bfx_free(void* dev_ptr);
+  int bfx_memcpy(void* dst_any, const void* src_any, size_t bytes, bfx_stream_t stream); /* cudaMemcpyDefault, async */
+  int bfx_memset(void* dev_ptr, int value, size_t bytes, bfx_stream_t stream);
+  int bfx_stream_sync(bfx_stream_t stream);
+  int bfx_host_alloc(void** host_ptr, size_t bytes); /* pinned */
+  int bfx_host_free(void* host_ptr);
+
+  /* ---- element kernels: the FFCx tabulate_tensor plug point -------------------------------
+   * Replaces the std::function<tabulate_tensor> stored in fem::integral_data::kernel
+   * (fem/Form.h:52-87, fem/kernel.h:18-20, fem/traits.h:28-30).  A kernel id selects a
+   * hand-written sm_100a device function with the UFCx argument meaning
+   * (A, w, c, coordinate_dofs, entity_local_index).                                          */
+  enum
+  {
+    BFX_K_LAPLACE_P1_TRI_A = 0,     /* python/test/unit/fem/test_custom_jit_kernels.py:29-46 */
+    BFX_K_SOURCE_P1_TRI_L = 1,      /* test_custom_jit_kernels.py:49-62 */
+    BFX_K_MASS_COEFF_P1_TRI_A = 2,  /* inner(f*u, v)*dx, f P1 coefficient (test_ghost_mesh_assembly.py:50) */
+    BFX_K_LOAD_COEFF_P1_TRI_L = 3,  /* inner(f, v)*dx */
+    BFX_K_FACET_MASS_P1_TRI_A = 4,  /* inner(u, v)*ds */
+    BFX_K_FACET_CONST_P1_TRI_L = 5, /* inner(c0, v)*ds */
+    BFX_K_POISSON_P1_TET_A = 6,     /* kappa*inner(grad u, grad v)*dx (cpp/demo/poisson/poisson.py, 3-D) */
+    BFX_K_LOAD_P1_TET_L = 7,        /* inner(f, v)*dx, f P1 */
+    BFX_K_POISSON_P2_TET_A = 8,     /* cpp/test/poisson.py:16-27 */
+    BFX_K_LOAD_P2_TET_L = 9,        /* inner(f, v)*dx, f P2 */
+    BFX_K_ELASTICITY_Q1_HEX_A = 10, /* inner(sigma(u), grad(v))*dx, python/demo/demo_elasticity.py:131-150; c={mu,lambda} */
+    BFX_K_LOAD_Q1_HEX_L = 11,       /* inner(f, v)*dx, f Q1 vector (bs=3) */
+    BFX_K_FACET_LOAD_P1_TET_L = 12, /* inner(g, v)*ds, g P1 */
+    BFX_K_FACET_MASS_P1_TET_A = 13, /* inner(u, v)*ds */
+    BFX_K_COUNT = 14
+  };
+
+  /* Static description of a kernel id: geometry nodes per cell, dofs per cell of test/trial space,
+   * block size, rank (1 = vector, 2 = matrix), length of w and c it reads, 1 if facet kernel. */
+  typedef struct
+  {
+    int nx, nd, bs, rank, w_size, c_size, facet;
+  } bfx_kernel_info_t;
+  int bfx_kernel_info(int kernel_id, bfx_kernel_info_t* info);
+
+  /* ---- la::MatrixCSR structure ------------------------------------------------------------ */
+  /* MatrixCSR(const SparsityPattern&) — la/MatrixCSR.h:628-703: copies graph, off_diag = row_ptr + nnz_diag.
+   * row_ptr: int64[n_rows_all+1], cols: int32[nnz] (sorted per row), off_diag: int64[n_rows_all]. */
+  int bfx_csr_create(bfx_csr_t** out, int32_t n_rows_all, int32_t n_rows_owned, const int64_t* row_ptr_any,
+                     const int32_t* cols_any, const int64_t* off_diag_any, int bs0, int bs1);
+  int bfx_csr_destroy(bfx_csr_t* csr);
+  int64_t bfx_csr_nnz(const bfx_csr_t* csr);
+  /* copy structure out (any of the destinations may be NULL) */
+  int bfx_csr_get_structure(const bfx_csr_t* csr, int64_t* row_ptr_any, int32_t* cols_any, int64_t* off_diag_any);
+  /* device pointers of the structure (valid for the life of csr) */
+  int bfx_csr_device_ptrs(const bfx_csr_t* csr, const int64_t** row_ptr, const int32_t** cols,
+                          const int64_t** off_diag);
+
+  /* fem::create_sparsity_pattern + SparsityPattern::finalize, local part, on device.
+   * fem/sparsitybuild.h:36-50 (cells) + la/SparsityPattern.cpp:438-478 (per-row dedup + sort,
+   * off_diagonal_offsets = #cols < n_cols_owned).  Rows/cols are local block indices; extra
+   * (row, col) pairs (entries received from other ranks, :394-423, or insert_diagonal) are merged in.
+   * cells_any == NULL means cells [0, ncells). */
+  int bfx_sparsity_build(bfx_csr_t** out, int32_t n_rows_all, int32_t n_rows_owned, int32_t n_cols_owned,
+                         const int32_t* dofmap0_dev, int nd0, const int32_t* dofmap1_dev, int nd1,
+                         const int32_t* cells_dev, int64_t ncells, const int32_t* extra_rows_any,
+                         const int32_t* extra_cols_any, int64_t n_extra, int bs0, int bs1, bfx_stream_t stream);
+  /* For ghost rows (rows >= n_rows_owned): de-duplicated column lists in INSERTION order (cell order,
+   * then cell-local dof order) — what finalize() sends to the owners (SparsityPattern.cpp:326-351);
+   * duplicates dropped (first occurrence kept), which leaves the owner-side result unchanged.
+   * Two-phase: counts_host[n_ghost_rows] first (cols_host == NULL), then the packed columns. */
+  int bfx_sparsity_ghost_rows(int32_t n_rows_all, int32_t n_rows_owned, const int32_t* dofmap0_dev, int nd0,
+                              const int32_t* dofmap1_dev, int nd1, const int32_t* cells_dev, int64_t ncells,
+                              int64_t* counts_host, int32_t* cols_host, bfx_stream_t stream);
+
+  /* MatrixCSR::add / set with explicit blocks — la/MatrixCSR.h:265-335 → impl::insert_csr (kind 0),
+   * insert_blocked_csr (kind 1), insert_nonblocked_csr (kind 2), la/matrix_csr_impl.h:67-232.
+   * x: row-major (nr*dbs0 x nc*dbs1) values; op 0 = set, 1 = add. dbs = block size of the DATA. */
+  int bfx_csr_insert(const bfx_csr_t* csr, double* values_dev, int kind, int dbs0, int dbs1, const double* x_any,
+                     const int32_t* xrows_any, int nr, const int32_t* xcols_any, int nc, int op, bfx_stream_t stream);
+  /* fem::set_diagonal — fem/assembler.h:644-686: values[row,row] = diag (SET) for unrolled dof rows. */
+  int bfx_csr_set_diagonal(const bfx_csr_t* csr, double* values_dev, const int32_t* rows_unrolled_dev, int64_t n,
+                           double diag, bfx_stream_t stream);
+  /* MatrixCSR::squared_norm — la/MatrixCSR.h:473-486 (owned rows; caller reduces over ranks). */
+  int bfx_csr_squared_norm(const bfx_csr_t* csr, const double* values_dev, double* result_host, bfx_stream_t stream);
+
+  /* MatrixCSR::mult — la/MatrixCSR.h:877-946 → impl::spmv la/matrix_csr_impl.h:259-286.  y[0:n_owned*bs0] += A x.
+   * part: 0 = whole rows, 1 = diagonal block [row_ptr, off_diag), 2 = off-diagonal block [off_diag, row_end). */
+  enum
+  {
+    BFX_SPMV_FULL = 0,
+    BFX_SPMV_DIAG = 1,
+    BFX_SPMV_OFFDIAG = 2
+  };
+  int bfx_spmv(const bfx_csr_t* csr, const double* values_dev, const double* x_dev, double* y_dev, int part,
+               bfx_stream_t stream);
+  /* MatrixCSR::multT local kernels — la/MatrixCSR.h:950-1016 → impl::spmvT la/matrix_csr_impl.h:319-343 */
+  int bfx_spmvT(const bfx_csr_t* csr, const double* values_dev, const double* x_dev, double* y_dev, int part,
+                bfx_stream_t stream);
+
+  /* ---- assembly ---------------------------------------------------------------------------- */
+  /* Coefficient sources.  Either the reference's packed array (fem/pack.h:265-…: ncells x cstride,
+   * row e belongs to the e-th entity of the integral) or a fused gather from the coefficient dof
+   * vectors (pack_impl, fem/pack.h:77-103, done inside the element kernel): w[offset + bs*i + k] =
+   * values[bs*dofmap[cell, i] + k]. */
+  typedef struct
+  {
+    const double* values_dev;
+    const int32_t* dofmap_dev;
+    int nd, bs, offset;
+  } bfx_coeff_src_t;
+  typedef struct
+  {
+    const double* packed_dev; /* or NULL */
+    int cstride;
+    int n_fused; /* used when packed_dev == NULL */
+    bfx_coeff_src_t fused[4];
+  } bfx_coeffs_t;
+
+  enum
+  {
+    BFX_ASM_ATOMIC = 0, /* cell-parallel, fp64 RED atomics into CSR through the cell->nnz map */
+    BFX_ASM_GATHER = 1  /* row-parallel, each CSR value written once, CPU summation order */
+  };
+  enum
+  {
+    BFX_VALUES_ADD = 0,      /* reference semantics: values += contributions (assembler.h:497-498) */
+    BFX_VALUES_OVERWRITE = 1 /* caller guarantees values are zero: fuses the zero-fill (gather mode) */
+  };
+
+  /* Plan for impl::assemble_cells_matrix / assemble_cells over one cell list
+   * (fem/assemble_matrix_impl.h:92-200, fem/assemble_vector_impl.h:72-116): uploads / borrows
+   * x_dofmap, dofmap0, dofmap1 and cells, and precomputes the cell -> CSR-position map
+   * (replaces the per-entry std::lower_bound of insert_csr, la/matrix_csr_impl.h:92).
+   * csr may be NULL for a linear form (then dofmap1 is ignored).  Returns BFX_ERR_NOT_IN_SPARSITY
+   * where the reference would throw "Entry not in sparsity".
+   * borrow != 0: the dofmap / cells pointers are device pointers that outlive the plan (no copy). */
+  int bfx_asm_create(bfx_asm_t** out, const bfx_csr_t* csr, const int32_t* x_dofmap_any, int nx,
+                     const int32_t* dofmap0_any, int nd0, const int32_t* dofmap1_any, int nd1,
+                     int64_t ncells_all, const int32_t* cells_any, int64_t ncells, int32_t n_rows_all, int borrow,
+                     bfx_stream_t stream);
+  int bfx_asm_destroy(bfx_asm_t* plan);
+
+  /* impl::assemble_cells_matrix<false> — fem/assemble_matrix_impl.h:92-200 (+ bc row/col zeroing :161-196).
+   * bc0/bc1: int8 markers of length bs*(owned+ghost) or NULL.  constants: host array. */
+  int bfx_assemble_matrix_cells(const bfx_asm_t* plan, int kernel_id, const double* x_dev, const int8_t* bc0_dev,
+                                const int8_t* bc1_dev, const bfx_coeffs_t* coeffs, const double* constants_host,
+                                int n_constants, double* values_dev, int strategy, int values_mode,
+                                bfx_stream_t stream);
+  /* impl::assemble_cells — fem/assemble_vector_impl.h:72-116: b[bs*dof+k] += be[bs*i+k]. */
+  int bfx_assemble_vector_cells(const bfx_asm_t* plan, int kernel_id, const double* x_dev,
+                                const bfx_coeffs_t* coeffs, const double* constants_host, int n_constants,
+                                double* b_dev, int strategy, bfx_stream_t stream);
+  /* impl::lift_bc — fem/assemble_vector_impl.h:361-414 through assemble_cells_matrix<true>
+   * (cell skip has_bc, assemble_matrix_impl.h:27-34,139-143): b -= alpha * Ae (bc_values1 - x0) on marked columns. */
+  int bfx_lift_bc_cells(const bfx_asm_t* plan, int kernel_id, const double* x_dev, const bfx_coeffs_t* coeffs,
+                        const double* constants_host, int n_constants, double* b_dev, const double* bc_values1_dev,
+                        const int8_t* bc_markers1_dev, const double* x0_dev, double alpha, bfx_stream_t stream);
+  /* impl::assemble_entities (exterior facets) — fem/assemble_matrix_impl.h:264-379,
+   * fem/assemble_vector_impl.h:157-215.  entities: flat (cell, local_facet) int32 pairs on device;
+   * packed coefficient rows (if any) are per entity.  values_dev / b_dev as above. */
+  int bfx_assemble_matrix_facets(const bfx_asm_t* plan, int kernel_id, const double* x_dev,
+                                 const int32_t* entities_dev, int64_t n_entities, const int8_t* bc0_dev,
+                                 const int8_t* bc1_dev, const bfx_coeffs_t* coeffs, const double* constants_host,
+                                 int n_constants, double* values_dev, bfx_stream_t stream);
+  int bfx_assemble_vector_facets(const bfx_asm_t* plan, int kernel_id, const double* x_dev,
+                                 const int32_t* entities_dev, int64_t n_entities, const bfx_coeffs_t* coeffs,
+                                 const double* constants_host, int n_constants, double* b_dev, bfx_stream_t stream);
+  /* pack_coefficient_entity — fem/pack.h:121-176: materialise the reference's packed layout on device
+   * (parity with callers that pass packed coefficients). */
+  int bfx_pack_coefficient(double* coeffs_dev, int cstride, int offset, const double* values_dev,
+                           const int32_t* dofmap_dev, int nd, int bs, const int32_t* cells_dev,
+                           const int32_t* entities_dev, int64_t n, bfx_stream_t stream);
+
+  /* Host-buffer entry (drop-in call with the reference's host containers): copies x, the fused
+   * coefficient dof vectors and bc markers to the device, assembles, copies the CSR values back.
+   * All *_host arrays are host memory (pinned for full speed).  Scratch is owned by the plan. */
+  int bfx_assemble_matrix_cells_host(bfx_asm_t* plan, int kernel_id, const double* x_host, int64_t n_x_nodes,
+                                     const int8_t* bc0_host, const int8_t* bc1_host, int64_t n_bc,
+                                     const double* coeff_values_host, int64_t n_coeff_values, int coeff_bs,
+                                     const double* constants_host, int n_constants, double* values_host,
+                                     int strategy, bfx_stream_t stream);
+
+  /* ---- Dirichlet conditions ----------------------------------------------------------------- */
+  /* DirichletBC::mark_dofs — fem/DirichletBC.h:589-601 */
+  int bfx_bc_mark(int8_t* markers_dev, const int32_t* dofs0_dev, int64_t n, bfx_stream_t stream);
+  /* DirichletBC::set — fem/DirichletBC.h:495-578.  g_kind 0: Function, x[dofs0[i]] = alpha*(g[dofs_g[i]] - x0[dofs0[i]]);
+   * g_kind 1: Constant, g[dofs0[i] % bs].  dofs_g NULL = dofs0; x0 NULL = no x0; dofs >= x_size skipped. */
+  int bfx_bc_set(double* x_dev, int32_t x_size, const int32_t* dofs0_dev, const int32_t* dofs_g_dev, int64_t n,
+                 const double* g_dev, int g_kind, int bs, const double* x0_dev, double alpha, bfx_stream_t stream);
+
+  /* ---- la::Vector reductions — la/Vector.h:434-514 (local part; caller all-reduces) -------- */
+  int bfx_dot(int64_t n, const double* x_dev, const double* y_dev, double* result_host, bfx_stream_t stream);
+  int bfx_norm(int64_t n, const double* x_dev, int type /*0 l1, 1 l2^2, 2 linf*/, double* result_host,
+               bfx_stream_t stream);
+  int bfx_axpy(int64_t n, double alpha, const double* x_dev, double* y_dev, bfx_stream_t stream);
+
+  /* ---- communicator (NCCL over NVLink; replaces MPI on the data path) ------------------------ */
+  int bfx_comm_unique_id(char id_out[128]);
+  int bfx_comm_create(bfx_comm_t** out, const char id[128], int rank, int size);
+  int bfx_comm_destroy(bfx_comm_t* comm);
+  int bfx_comm_rank(const bfx_comm_t* comm, int* rank, int* size);
+  int bfx_comm_allreduce(bfx_comm_t* comm, double* buf_dev, int64_t n, int op /*0 sum, 1 max*/, bfx_stream_t stream);
+
+  /* ---- common::Scatterer / la::Vector ghost exchange -------------------------------------------
+   * Plan arrays are exactly the Scatterer members (common/Scatterer.h:65-198): local_inds / remote_inds
+   * (already expanded by the block size), sizes/displs per neighbour (x bs), dest = ranks that ghost my
+   * owned indices, src = ranks that own my ghosts.  comm may be NULL when n_dest = n_src = 0. */
+  int bfx_scatter_create(bfx_scatter_t** out, bfx_comm_t* comm, const int32_t* local_inds_any, int64_t n_local,
+                         const int32_t* remote_inds_any, int64_t n_remote, const int32_t* sizes_local,
+                         const int32_t* displs_local, const int32_t* dest, int n_dest, const int32_t* sizes_remote,
+                         const int32_t* displs_remote, const int32_t* src, int n_src);
+  int bfx_scatter_destroy(bfx_scatter_t* sc);
+  /* Vector::scatter_fwd_begin/end — la/Vector.h:219-281 → Scatterer::scatter_fwd_begin common/Scatterer.h:251-308:
+   * pack owned values (kernel) → grouped ncclSend/ncclRecv on the plan's comm stream → unpack into the ghost tail.
+   * x_dev holds [owned | ghosts]; n_owned = bs*size_local.  begin() returns immediately; work queued after
+   * `stream` in program order; end() makes `stream` wait for the exchange and runs the unpack on it. */
+  int bfx_scatter_fwd_begin(bfx_scatter_t* sc, const double* x_dev, bfx_stream_t stream);
+  int bfx_scatter_fwd_end(bfx_scatter_t* sc, double* x_dev, int64_t n_owned, bfx_stream_t stream);
+  /* Vector::scatter_rev_begin/end — la/Vector.h:314-379 → common/Scatterer.h:336-396; op 0 = set, 1 = add */
+  int bfx_scatter_rev_begin(bfx_scatter_t* sc, const double* x_dev, int64_t n_owned, bfx_stream_t stream);
+  int bfx_scatter_rev_end(bfx_scatter_t* sc, double* x_dev, int op, bfx_stream_t stream);
+
+  /* MatrixCSR::scatter_rev_begin/end — la/MatrixCSR.h:399-468 with the plan built by the constructor
+   * (:705-849): ghost_row_to_rank[n_ghost_rows] (index into src), val_send_disp[n_src+1], val_recv_disp[n_dest+1]
+   * (both already x bs0*bs1), unpack_pos[val_recv_disp[n_dest]/bs2] (block positions in the owner's CSR). */
+  typedef struct bfx_csr_scatter bfx_csr_scatter_t;
+  int bfx_csr_scatter_create(bfx_csr_scatter_t** out, const bfx_csr_t* csr, bfx_comm_t* comm,
+                             const int32_t* ghost_row_to_rank, int32_t n_ghost_rows, const int64_t* val_send_disp,
+                             const int32_t* src, int n_src, const int64_t* val_recv_disp, const int32_t* dest,
+                             int n_dest, const int64_t* unpack_pos_any);
+  int bfx_csr_scatter_destroy(bfx_csr_scatter_t* plan);
+  int bfx_csr_scatter_rev_begin(bfx_csr_scatter_t* plan, const double* values_dev, bfx_stream_t stream);
+  int bfx_csr_scatter_rev_end(bfx_csr_scatter_t* plan, double* values_dev, bfx_stream_t stream);
+
+  /* ---- host helpers for the synthetic fixtures (not on the timed path) ----------------------- */
+  /* first-touch dof numbering, fem/dofmapbuilder.cpp:446-459: new_index[old] for old in [0, ndofs) */
+  int bfx_host_first_touch_i32(const int32_t* dofmap, int64_t n, int32_t ndofs, int32_t* new_index);
+  int bfx_host_first_touch_i64(const int64_t* dofmap, int64_t n, int64_t ndofs, int64_t* new_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFX_H */

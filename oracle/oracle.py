@@ -1,0 +1,597 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product.
+
+Python/numpy half of the CPU oracle: (i) ctypes bindings of ``oracle.c`` (the
+arithmetic loops) and (ii) a line-by-line restatement of the reference's
+index-plan construction (IndexMap, Scatterer, SparsityPattern::finalize,
+MatrixCSR ghost-row plan, Vector/MatrixCSR ghost exchange) executed for N
+*simulated* ranks inside one process: every MPI neighbourhood collective of the
+reference is replaced by :func:`neighbor_alltoallv`, which routes the per-rank
+send buffers exactly as ``MPI_Neighbor_alltoallv`` on a
+``MPI_Dist_graph_create_adjacent`` communicator would.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  Citations are relative to
+/root/reference/cpp/dolfinx.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# Kernel ids (shared with include/bfx.h BFX_K_*)
+K_LAPLACE_P1_TRI_A = 0
+K_SOURCE_P1_TRI_L = 1
+K_MASS_COEFF_P1_TRI_A = 2
+K_LOAD_COEFF_P1_TRI_L = 3
+K_FACET_MASS_P1_TRI_A = 4
+K_FACET_CONST_P1_TRI_L = 5
+K_POISSON_P1_TET_A = 6
+K_LOAD_P1_TET_L = 7
+K_POISSON_P2_TET_A = 8
+K_LOAD_P2_TET_L = 9
+K_ELASTICITY_Q1_HEX_A = 10
+K_LOAD_Q1_HEX_L = 11
+K_FACET_LOAD_P1_TET_L = 12
+K_FACET_MASS_P1_TET_A = 13
+
+
+def build(fast: bool = False) -> str:
+    """Compile oracle.c if the shared library is missing; returns its path."""
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    path = os.path.join(_HERE, name)
+    src = os.path.join(_HERE, "oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        import subprocess
+
+        subprocess.check_call(["make", "-C", _HERE, name])
+    return path
+
+
+_libs = {}
+
+
+def lib(fast: bool = False):
+    if fast not in _libs:
+        _libs[fast] = C.CDLL(build(fast))
+    return _libs[fast]
+
+
+def _p(a, ct):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int8)
+
+
+def tabulate(kernel_id, nA, xc, w=None, c=None, local_entity=0):
+    A = np.zeros(nA)
+    w, c, xc = _f64(w), _f64(c), _f64(xc)
+    err = lib().orc_tabulate(
+        C.c_int(kernel_id), _p(A, C.c_double), C.c_int(nA), _p(w, C.c_double), _p(c, C.c_double), _p(xc, C.c_double),
+        C.c_int(local_entity),
+    )
+    assert err == 0
+    return A
+
+
+def insert_csr(kind, data, cols, row_ptr, x, xrows, xcols, bs0, bs1, op):
+    """kind: 'csr' | 'blocked' | 'nonblocked'; op: 'set' | 'add'. Raises RuntimeError like the reference."""
+    fn = {"csr": lib().orc_insert_csr, "blocked": lib().orc_insert_blocked_csr, "nonblocked": lib().orc_insert_nonblocked_csr}[kind]
+    cols, xrows, xcols, x = _i32(cols), _i32(xrows), _i32(xcols), _f64(x)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    err = fn(
+        _p(data, C.c_double), _p(cols, C.c_int32), _p(row_ptr, C.c_int64), _p(x, C.c_double), _p(xrows, C.c_int32),
+        C.c_int(len(xrows)), _p(xcols, C.c_int32), C.c_int(len(xcols)), C.c_int(bs0), C.c_int(bs1),
+        C.c_int(1 if op == "add" else 0),
+    )
+    if err:
+        raise RuntimeError("Entry not in sparsity")
+
+
+def spmv(values, row_begin, row_end, indices, x, y, bs0, bs1, transpose=False, fast=False):
+    fn = lib(fast).orc_spmvT if transpose else lib(fast).orc_spmv
+    fn.restype = None
+    values, x, indices = _f64(values), _f64(x), _i32(indices)
+    rb = np.ascontiguousarray(row_begin, dtype=np.int64)
+    re = np.ascontiguousarray(row_end, dtype=np.int64)
+    fn(_p(values, C.c_double), _p(rb, C.c_int64), _p(re, C.c_int64), _p(indices, C.c_int32), _p(x, C.c_double),
+       _p(y, C.c_double), C.c_int(bs0), C.c_int(bs1), C.c_int64(len(rb)))
+
+
+def assemble_matrix(kernel_id, x_dofmap, x, cells, dmap0, bs0, dmap1, bs1, data, cols, row_ptr, bc0=None, bc1=None,
+                    coeffs=None, constants=None, entities=None, fast=False):
+    """fem::assemble_matrix of one integral into CSR ``data`` (in place, +=)."""
+    x_dofmap, dmap0, dmap1 = _i32(x_dofmap), _i32(dmap0), _i32(dmap1)
+    cells, entities = _i32(cells), _i32(entities)
+    n = len(entities) if entities is not None else len(cells)
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    bc0, bc1 = _i8(bc0), _i8(bc1)
+    cols = _i32(cols)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    cstride = 0 if coeffs is None else coeffs.shape[1]
+    err = lib(fast).orc_assemble_matrix(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(cells, C.c_int32), _p(entities, C.c_int32), C.c_int64(n), _p(dmap0, C.c_int32), C.c_int(dmap0.shape[1]),
+        C.c_int(bs0), _p(dmap1, C.c_int32), C.c_int(dmap1.shape[1]), C.c_int(bs1), _p(bc0, C.c_int8),
+        _p(bc1, C.c_int8), _p(coeffs, C.c_double), C.c_int(cstride), _p(constants, C.c_double), _p(data, C.c_double),
+        _p(cols, C.c_int32), _p(row_ptr, C.c_int64),
+    )
+    if err == -1:
+        raise RuntimeError("Entry not in sparsity")
+    assert err == 0
+
+
+def lift_bc(kernel_id, x_dofmap, x, cells, dmap0, bs0, dmap1, bs1, b, bc_values1, bc_markers1, x0=None, alpha=1.0,
+            coeffs=None, constants=None, entities=None):
+    x_dofmap, dmap0, dmap1 = _i32(x_dofmap), _i32(dmap0), _i32(dmap1)
+    cells, entities = _i32(cells), _i32(entities)
+    n = len(entities) if entities is not None else len(cells)
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    bc_values1, x0, bc_markers1 = _f64(bc_values1), _f64(x0), _i8(bc_markers1)
+    cstride = 0 if coeffs is None else coeffs.shape[1]
+    err = lib().orc_lift_bc(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(cells, C.c_int32), _p(entities, C.c_int32), C.c_int64(n), _p(dmap0, C.c_int32), C.c_int(dmap0.shape[1]),
+        C.c_int(bs0), _p(dmap1, C.c_int32), C.c_int(dmap1.shape[1]), C.c_int(bs1), _p(coeffs, C.c_double),
+        C.c_int(cstride), _p(constants, C.c_double), _p(b, C.c_double), _p(bc_values1, C.c_double),
+        _p(bc_markers1, C.c_int8), _p(x0, C.c_double), C.c_double(alpha),
+    )
+    assert err == 0
+
+
+def assemble_vector(kernel_id, x_dofmap, x, cells, dmap, bs, b, coeffs=None, constants=None, entities=None, fast=False):
+    x_dofmap, dmap = _i32(x_dofmap), _i32(dmap)
+    cells, entities = _i32(cells), _i32(entities)
+    n = len(entities) if entities is not None else len(cells)
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    cstride = 0 if coeffs is None else coeffs.shape[1]
+    err = lib(fast).orc_assemble_vector(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(cells, C.c_int32), _p(entities, C.c_int32), C.c_int64(n), _p(dmap, C.c_int32), C.c_int(dmap.shape[1]),
+        C.c_int(bs), _p(coeffs, C.c_double), C.c_int(cstride), _p(constants, C.c_double), _p(b, C.c_double),
+    )
+    assert err == 0
+
+
+def pack_coefficient(coeffs, offset, v, dofmap, bs, cells=None, entities=None):
+    dofmap, cells, entities, v = _i32(dofmap), _i32(cells), _i32(entities), _f64(v)
+    n = len(entities) if entities is not None else len(cells)
+    f = lib().orc_pack_coefficient
+    f.restype = None
+    f(_p(coeffs, C.c_double), C.c_int(coeffs.shape[1]), C.c_int(offset), _p(v, C.c_double), _p(dofmap, C.c_int32),
+      C.c_int(dofmap.shape[1]), C.c_int(bs), _p(cells, C.c_int32), _p(entities, C.c_int32), C.c_int64(n))
+
+
+def bc_mark(markers, dofs0):
+    dofs0 = _i32(dofs0)
+    f = lib().orc_bc_mark
+    f.restype = None
+    f(_p(markers, C.c_int8), _p(dofs0, C.c_int32), C.c_int64(len(dofs0)))
+
+
+def bc_set(x, dofs0, g, g_kind, bs, x0=None, alpha=1.0, dofs_g=None):
+    dofs0, dofs_g, g, x0 = _i32(dofs0), _i32(dofs_g), _f64(g), _f64(x0)
+    f = lib().orc_bc_set
+    f.restype = None
+    f(_p(x, C.c_double), C.c_int32(len(x)), _p(dofs0, C.c_int32), _p(dofs_g, C.c_int32), C.c_int64(len(dofs0)),
+      _p(g, C.c_double), C.c_int(g_kind), C.c_int(bs), _p(x0, C.c_double), C.c_double(alpha))
+
+
+def set_diagonal(data, cols, row_ptr, bs0, bs1, rows, diagonal=1.0):
+    rows, cols = _i32(rows), _i32(cols)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    err = lib().orc_set_diagonal(_p(data, C.c_double), _p(cols, C.c_int32), _p(row_ptr, C.c_int64), C.c_int(bs0),
+                                 C.c_int(bs1), _p(rows, C.c_int32), C.c_int64(len(rows)), C.c_double(diagonal))
+    if err:
+        raise RuntimeError("Entry not in sparsity")
+
+
+def unroll_dofs(dofs, bs):
+    """DirichletBC::unroll_dofs (fem/DirichletBC.h:273-281)."""
+    dofs = np.asarray(dofs, dtype=np.int32)
+    return (bs * dofs[:, None] + np.arange(bs, dtype=np.int32)[None, :]).reshape(-1)
+
+
+# ---------------------------------------------------------------------------
+# Simulated MPI world
+# ---------------------------------------------------------------------------
+
+
+def neighbor_alltoallv(out_edges, in_edges, send):
+    """MPI_Neighbor_alltoallv on a dist-graph communicator.
+
+    out_edges[r] / in_edges[r]: destination / source rank lists of rank r.
+    send[r][i]: array rank r sends to out_edges[r][i].
+    Returns recv[r][j] = array received from in_edges[r][j].
+    """
+    size = len(out_edges)
+    recv = []
+    for r in range(size):
+        rr = []
+        for s in in_edges[r]:
+            i = list(out_edges[s]).index(r)
+            rr.append(np.array(send[s][i], copy=True))
+        recv.append(rr)
+    return recv
+
+
+@dataclass
+class OIndexMap:
+    """common::IndexMap accessor subset (common/IndexMap.h:178-257)."""
+
+    rank: int
+    size: int
+    local_range: tuple
+    ghosts: np.ndarray
+    owners: np.ndarray
+    src: np.ndarray
+    dest: np.ndarray
+    size_global: int
+
+    @property
+    def size_local(self):
+        return self.local_range[1] - self.local_range[0]
+
+    @property
+    def num_ghosts(self):
+        return len(self.ghosts)
+
+    def local_to_global(self, local):
+        """common/IndexMap.cpp:957-974"""
+        local = np.asarray(local)
+        out = np.empty(local.shape, dtype=np.int64)
+        m = local < self.size_local
+        out[m] = self.local_range[0] + local[m]
+        out[~m] = self.ghosts[local[~m] - self.size_local]
+        return out
+
+
+def make_index_maps(size_locals, ghosts, owners):
+    """IndexMap(comm, local_size, ghosts, owners) on every rank (common/IndexMap.cpp:888-932).
+
+    offset = MPI_Exscan, size_global = MPI_Allreduce; src = sorted unique owners;
+    dest = ranks that ghost my indices (build_src_dest -> NBX), sorted.
+    """
+    size = len(size_locals)
+    offs = np.concatenate([[0], np.cumsum(size_locals)]).astype(np.int64)
+    srcs = [np.unique(np.asarray(owners[r], dtype=np.int32)) for r in range(size)]
+    dests = [np.array(sorted(s for s in range(size) if r in srcs[s]), dtype=np.int32) for r in range(size)]
+    return [
+        OIndexMap(r, size, (int(offs[r]), int(offs[r + 1])), np.asarray(ghosts[r], dtype=np.int64),
+                  np.asarray(owners[r], dtype=np.int32), srcs[r], dests[r], int(offs[-1]))
+        for r in range(size)
+    ]
+
+
+@dataclass
+class OScatterer:
+    """common::Scatterer plan (common/Scatterer.h:65-198)."""
+
+    src: np.ndarray
+    dest: np.ndarray
+    local_inds: np.ndarray
+    remote_inds: np.ndarray
+    sizes_local: np.ndarray
+    displs_local: np.ndarray
+    sizes_remote: np.ndarray
+    displs_remote: np.ndarray
+
+
+def make_scatterers(maps, bs):
+    size = len(maps)
+    if size == 1:  # Scatterer.h:71-72
+        m = maps[0]
+        z = np.zeros(0, dtype=np.int32)
+        return [OScatterer(m.src, m.dest, z, z, z, np.zeros(1, np.int32), z, np.zeros(1, np.int32))]
+    perms, ghosts_sorted, sizes_remote, displs_remote = [], [], [], []
+    for m in maps:
+        # stable sort of ghost positions by owner (radix sort, Scatterer.h:98-101)
+        perm = np.argsort(m.owners, kind="stable").astype(np.int32)
+        owners_sorted = m.owners[perm]
+        gs = m.ghosts[perm]
+        sr = np.array([np.count_nonzero(owners_sorted == s) for s in m.src], dtype=np.int32)
+        dr = np.concatenate([[0], np.cumsum(sr)]).astype(np.int32)
+        perms.append(perm)
+        ghosts_sorted.append(gs)
+        sizes_remote.append(sr)
+        displs_remote.append(dr)
+    # comm1: ghost -> owner. out-edges = src, in-edges = dest (Scatterer.h:89-95)
+    send = [[ghosts_sorted[r][displs_remote[r][i]:displs_remote[r][i + 1]] for i in range(len(maps[r].src))] for r in range(size)]
+    recv = neighbor_alltoallv([m.src for m in maps], [m.dest for m in maps], send)
+    out = []
+    for r, m in enumerate(maps):
+        sl = np.array([len(a) for a in recv[r]], dtype=np.int32)
+        dl = np.concatenate([[0], np.cumsum(sl)]).astype(np.int32)
+        recv_buffer = np.concatenate(recv[r]) if recv[r] else np.zeros(0, dtype=np.int64)
+        assert np.all((recv_buffer >= m.local_range[0]) & (recv_buffer < m.local_range[1]))
+        k = np.arange(bs, dtype=np.int64)
+        local_inds = ((recv_buffer[:, None] * bs + k[None, :]) - m.local_range[0] * bs).reshape(-1).astype(np.int32)
+        remote_inds = (perms[r].astype(np.int64)[:, None] * bs + k[None, :]).reshape(-1).astype(np.int32)
+        out.append(OScatterer(m.src, m.dest, local_inds, remote_inds, sl * bs, dl * bs, sizes_remote[r] * bs,
+                              displs_remote[r] * bs))
+    return out
+
+
+def vector_scatter_fwd(maps, scs, bs, xs):
+    """la::Vector::scatter_fwd (la/Vector.h:219-281): owner -> ghost, in place on xs[r]."""
+    size = len(maps)
+    if size == 1:
+        return
+    # pack: buf_local[i] = x[local_inds[i]]; comm0 out-edges = dest, in-edges = src
+    send = []
+    for r in range(size):
+        buf = xs[r][scs[r].local_inds]
+        send.append([buf[scs[r].displs_local[i]:scs[r].displs_local[i + 1]] for i in range(len(scs[r].dest))])
+    recv = neighbor_alltoallv([s.dest for s in scs], [s.src for s in scs], send)
+    for r in range(size):
+        buf_remote = np.concatenate(recv[r]) if recv[r] else np.zeros(0)
+        n0 = bs * maps[r].size_local
+        xs[r][n0 + scs[r].remote_inds] = buf_remote  # unpack (Vector.h:75-88)
+
+
+def vector_scatter_rev(maps, scs, bs, xs, op="add"):
+    """la::Vector::scatter_rev(op) (la/Vector.h:314-379): ghost -> owner."""
+    size = len(maps)
+    if size == 1:
+        return
+    send = []
+    for r in range(size):
+        n0 = bs * maps[r].size_local
+        buf = xs[r][n0 + scs[r].remote_inds]
+        send.append([buf[scs[r].displs_remote[i]:scs[r].displs_remote[i + 1]] for i in range(len(scs[r].src))])
+    recv = neighbor_alltoallv([s.src for s in scs], [s.dest for s in scs], send)
+    for r in range(size):
+        buf_local = np.concatenate(recv[r]) if recv[r] else np.zeros(0)
+        # serial unpack with op; one slot may be hit several times (Vector.h:96-114)
+        for i, idx in enumerate(scs[r].local_inds):
+            if op == "add":
+                xs[r][idx] = xs[r][idx] + buf_local[i]
+            else:
+                xs[r][idx] = buf_local[i]
+
+
+# ---------------------------------------------------------------------------
+# la::SparsityPattern
+# ---------------------------------------------------------------------------
+
+
+@dataclass
+class OPattern:
+    """Finalised la::SparsityPattern of one rank (la/SparsityPattern.h:25-180)."""
+
+    index_maps: list
+    bs: tuple
+    edges: np.ndarray  # int32 local column indices, sorted per row
+    offsets: np.ndarray  # int64
+    off_diagonal_offsets: np.ndarray  # int32, per row
+
+
+def sparsity_insert_cells(cells, dofmap0, dofmap1):
+    """fem::sparsitybuild::cells (fem/sparsitybuild.h:36-50) -> COO cache (rows, cols) in insertion order.
+
+    SparsityPattern::insert(rows, cols) appends, for each row, all cols (SparsityPattern.cpp:207-227).
+    """
+    d0 = np.asarray(dofmap0)[cells]
+    d1 = np.asarray(dofmap1)[cells]
+    nd0, nd1 = d0.shape[1], d1.shape[1]
+    rows = np.repeat(d0[:, :, None], nd1, axis=2).reshape(-1)
+    cols = np.repeat(d1[:, None, :], nd0, axis=1).reshape(-1)
+    return rows.astype(np.int32), cols.astype(np.int32)
+
+
+def _bucket_by_row(rows, cols, num_rows):
+    """bucket_by_row (la/SparsityPattern.cpp:28-44): stable counting sort by row."""
+    order = np.argsort(rows, kind="stable")
+    offsets = np.zeros(num_rows + 1, dtype=np.int64)
+    np.add.at(offsets, np.asarray(rows, dtype=np.int64) + 1, 1)
+    return np.cumsum(offsets), np.asarray(cols)[order]
+
+
+def sparsity_finalize(maps0, maps1, bs, cache_rows, cache_cols):
+    """SparsityPattern::finalize on every simulated rank (la/SparsityPattern.cpp:264-491)."""
+    size = len(maps0)
+    buckets, send, nbr = [], [], []
+    for r in range(size):
+        m0, m1 = maps0[r], maps1[r]
+        local_size0, local_size1 = m0.size_local, m1.size_local
+        num_rows0 = local_size0 + m0.num_ghosts
+        off, cc = _bucket_by_row(cache_rows[r], cache_cols[r], num_rows0)
+        buckets.append((off, cc))
+        neighbour_rank = np.searchsorted(m0.src, m0.owners)  # :291-299
+        bufs = [[] for _ in m0.src]
+        for i in range(m0.num_ghosts):  # :326-351 — (global row, global col, col owner) triplets
+            for k in range(off[local_size0 + i], off[local_size0 + i + 1]):
+                col_local = int(cc[k])
+                if col_local < local_size1:
+                    trip = (int(m0.ghosts[i]), col_local + m1.local_range[0], r)
+                else:
+                    trip = (int(m0.ghosts[i]), int(m1.ghosts[col_local - local_size1]), int(m1.owners[col_local - local_size1]))
+                bufs[neighbour_rank[i]].extend(trip)
+        send.append([np.array(b, dtype=np.int64) for b in bufs])
+        nbr.append(neighbour_rank)
+    # :354-383 — dist graph (sources = dest0, destinations = src0): send to src0, receive from dest0
+    recv = neighbor_alltoallv([m.src for m in maps0], [m.dest for m in maps0], send)
+    out = []
+    for r in range(size):
+        m0, m1 = maps0[r], maps1[r]
+        local_size0, local_size1 = m0.size_local, m1.size_local
+        num_rows0 = local_size0 + m0.num_ghosts
+        off, cc = buckets[r]
+        col_ghosts = list(m1.ghosts)
+        col_ghost_owners = list(m1.owners)
+        g2l = {int(g): local_size1 + i for i, g in enumerate(col_ghosts)}
+        ghost_data_in = np.concatenate(recv[r]) if recv[r] else np.zeros(0, dtype=np.int64)
+        recv_rows, recv_cols = [], []
+        local_i = local_size1 + len(col_ghosts)
+        for i in range(0, len(ghost_data_in), 3):  # :394-423
+            row_local = int(ghost_data_in[i]) - m0.local_range[0]
+            col = int(ghost_data_in[i + 1])
+            owner = int(ghost_data_in[i + 2])
+            recv_rows.append(row_local)
+            if m1.local_range[0] <= col < m1.local_range[1]:
+                recv_cols.append(col - m1.local_range[0])
+            else:
+                if col not in g2l:
+                    g2l[col] = local_i
+                    col_ghosts.append(col)
+                    col_ghost_owners.append(owner)
+                    local_i += 1
+                recv_cols.append(g2l[col])
+        roff, rcc = _bucket_by_row(np.array(recv_rows, dtype=np.int64), np.array(recv_cols, dtype=np.int32), local_size0)
+        # :438-478 — dedup + sort per row; vectorised (the result, sorted unique columns, is order independent)
+        row_of_cache = np.repeat(np.arange(num_rows0, dtype=np.int64), np.diff(off))
+        row_of_recv = np.repeat(np.arange(local_size0, dtype=np.int64), np.diff(roff))
+        ncols = local_size1 + len(col_ghosts)
+        keys = np.concatenate([row_of_cache * ncols + cc, row_of_recv * ncols + rcc])
+        keys = np.unique(keys)
+        rows_u = keys // ncols
+        edges = (keys % ncols).astype(np.int32)
+        offsets = np.zeros(num_rows0 + 1, dtype=np.int64)
+        np.add.at(offsets, rows_u + 1, 1)
+        offsets = np.cumsum(offsets)
+        diag = np.zeros(num_rows0, dtype=np.int64)
+        np.add.at(diag, rows_u[edges < local_size1], 1)
+        new_m1 = OIndexMap(r, size, m1.local_range, np.array(col_ghosts, dtype=np.int64),
+                           np.array(col_ghost_owners, dtype=np.int32), None, None, m1.size_global)
+        out.append((edges, offsets, diag.astype(np.int32), new_m1))
+    # :488-490 — new column IndexMap (src/dest recomputed from the extended ghost owners)
+    new_maps1 = make_index_maps([m.size_local for m in maps1], [o[3].ghosts for o in out], [o[3].owners for o in out])
+    return [OPattern([maps0[r], new_maps1[r]], tuple(bs), out[r][0], out[r][1], out[r][2]) for r in range(size)]
+
+
+# ---------------------------------------------------------------------------
+# la::MatrixCSR
+# ---------------------------------------------------------------------------
+
+
+@dataclass
+class OMatrix:
+    """la::MatrixCSR (compact block mode) of one rank: structure + ghost-row plan (la/MatrixCSR.h:628-850)."""
+
+    index_maps: list
+    bs: tuple
+    data: np.ndarray
+    cols: np.ndarray
+    row_ptr: np.ndarray
+    off_diag_offset: np.ndarray
+    ghost_row_to_rank: np.ndarray = None
+    val_send_disp: np.ndarray = None
+    val_recv_disp: np.ndarray = None
+    unpack_pos: np.ndarray = None
+
+
+def make_matrices(patterns):
+    size = len(patterns)
+    mats, send = [], []
+    for r, p in enumerate(patterns):
+        m0, m1 = p.index_maps
+        bs2 = p.bs[0] * p.bs[1]
+        A = OMatrix(p.index_maps, p.bs, np.zeros(len(p.edges) * bs2), p.edges.copy(), p.offsets.copy(),
+                    (p.off_diagonal_offsets.astype(np.int64) + p.offsets[:-1]))  # :695-703
+        local_size = (m0.size_local, m1.size_local)
+        A.ghost_row_to_rank = np.searchsorted(m0.src, m0.owners).astype(np.int32)  # :725-733
+        data_per_proc = np.zeros(len(m0.src), dtype=np.int64)
+        for i, g in enumerate(A.ghost_row_to_rank):  # :735-742
+            pos = local_size[0] + i
+            data_per_proc[g] += A.row_ptr[pos + 1] - A.row_ptr[pos]
+        val_send_disp = np.concatenate([[0], np.cumsum(data_per_proc)]).astype(np.int64)
+        bufs = [[] for _ in m0.src]
+        for i, g in enumerate(A.ghost_row_to_rank):  # :750-775 — (global row, global col) pairs
+            row_id = local_size[0] + i
+            for j in range(A.row_ptr[row_id], A.row_ptr[row_id + 1]):
+                col_local = int(A.cols[j])
+                gc = col_local + m1.local_range[0] if col_local < local_size[1] else int(m1.ghosts[col_local - local_size[1]])
+                bufs[g].extend((int(m0.ghosts[i]), gc))
+        send.append([np.array(b, dtype=np.int64) for b in bufs])
+        A.val_send_disp = (val_send_disp * bs2).astype(np.int64)  # :806-811
+        mats.append(A)
+    # comm: sources = dest_ranks, destinations = src_ranks (:715-721)
+    recv = neighbor_alltoallv([p.index_maps[0].src for p in patterns], [p.index_maps[0].dest for p in patterns], send)
+    for r, A in enumerate(mats):
+        m0, m1 = A.index_maps
+        bs2 = A.bs[0] * A.bs[1]
+        recv_disp = np.concatenate([[0], np.cumsum([len(a) for a in recv[r]])]).astype(np.int64)
+        A.val_recv_disp = bs2 * recv_disp // 2
+        arr = np.concatenate(recv[r]) if recv[r] else np.zeros(0, dtype=np.int64)
+        g2l = {int(g): m1.size_local + i for i, g in enumerate(m1.ghosts)}
+        unpack = []
+        for i in range(0, len(arr), 2):  # :820-846
+            local_row = int(arr[i]) - m0.local_range[0]
+            assert 0 <= local_row < m0.size_local
+            local_col = int(arr[i + 1]) - m1.local_range[0]
+            if local_col < 0 or local_col >= m1.size_local:
+                local_col = g2l[int(arr[i + 1])]
+            c0, c1 = A.row_ptr[local_row], A.row_ptr[local_row + 1]
+            d = c0 + int(np.searchsorted(A.cols[c0:c1], local_col))
+            assert d < c1 and A.cols[d] == local_col
+            unpack.append(d)
+        A.unpack_pos = np.array(unpack, dtype=np.int64)
+    return mats
+
+
+def matrix_scatter_rev(mats):
+    """MatrixCSR::scatter_rev (la/MatrixCSR.h:399-468): ghost-row values -> owners (+=), zero ghost rows."""
+    size = len(mats)
+    send = []
+    for A in mats:
+        m0 = A.index_maps[0]
+        bs2 = A.bs[0] * A.bs[1]
+        bufs = [[] for _ in m0.src]
+        for i, g in enumerate(A.ghost_row_to_rank):  # :406-420 pack per neighbour in ghost-row order
+            r0, r1 = A.row_ptr[m0.size_local + i] * bs2, A.row_ptr[m0.size_local + i + 1] * bs2
+            bufs[g].append(A.data[r0:r1])
+        send.append([np.concatenate(b) if b else np.zeros(0) for b in bufs])
+    recv = neighbor_alltoallv([A.index_maps[0].src for A in mats], [A.index_maps[0].dest for A in mats], send)
+    for r, A in enumerate(mats):
+        bs2 = A.bs[0] * A.bs[1]
+        vin = np.concatenate(recv[r]) if recv[r] else np.zeros(0)
+        assert len(vin) == len(A.unpack_pos) * bs2
+        for i, p in enumerate(A.unpack_pos):  # :457-459 serial +=
+            A.data[p * bs2:(p + 1) * bs2] += vin[i * bs2:(i + 1) * bs2]
+        A.data[A.row_ptr[A.index_maps[0].size_local] * bs2:] = 0  # :465-467
+
+
+def matrix_squared_norm(mats):
+    """MatrixCSR::squared_norm (la/MatrixCSR.h:473-486): owned rows only, summed over ranks."""
+    tot = 0.0
+    for A in mats:
+        bs2 = A.bs[0] * A.bs[1]
+        n = A.row_ptr[A.index_maps[0].size_local] * bs2
+        tot += float(np.sum(A.data[:n] ** 2))
+    return tot
+
+
+def matrix_mult(mats, scs_col, xs, ys):
+    """MatrixCSR::mult (la/MatrixCSR.h:877-946): y += A x with the diag / off-diag split around the ghost update."""
+    maps1 = [A.index_maps[1] for A in mats]
+    bs1 = mats[0].bs[1]
+    # x.scatter_fwd_begin(); diagonal block; x.scatter_fwd_end(); off-diagonal block
+    for A, x, y in zip(mats, xs, ys):
+        n = A.index_maps[0].size_local
+        spmv(A.data, A.row_ptr[:n], A.off_diag_offset[:n], A.cols, x, y, A.bs[0], A.bs[1])
+    vector_scatter_fwd(maps1, scs_col, bs1, xs)
+    for A, x, y in zip(mats, xs, ys):
+        n = A.index_maps[0].size_local
+        spmv(A.data, A.off_diag_offset[:n], A.row_ptr[1:n + 1], A.cols, x, y, A.bs[0], A.bs[1])
+
+
+def inner_product(maps, bs, xs, ys):
+    """la::inner_product (la/Vector.h:434-460): owned entries, MPI_SUM."""
+    return float(sum(np.dot(x[: bs * m.size_local], y[: bs * m.size_local]) for m, x, y in zip(maps, xs, ys)))

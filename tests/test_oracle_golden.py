@@ -1,0 +1,268 @@
+"""Pin the CPU oracle: reference golden scalars, known answers, and the reference's own
+la/matrix_csr_impl.h (compiled from /root/reference when present, oracle/_ref)."""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import problems as P
+
+REF_SO = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libref_csr.so")
+
+
+def test_golden_p1_laplace_unit_square_13(oracle):
+    """python/test/unit/fem/test_custom_jit_kernels.py:115-116 (and :290-294, frozen FFCx C)."""
+    O = oracle
+    p = P.tri_p1(13, 13)
+    pat, data = P.oracle_assemble_matrix(O, p, O.K_LAPLACE_P1_TRI_A)
+    b = P.oracle_assemble_vector(O, p, O.K_SOURCE_P1_TRI_L)
+    assert np.isclose(np.sqrt(np.sum(data**2)), 56.124860801609124, rtol=1e-14, atol=0)
+    assert np.isclose(np.linalg.norm(b), 0.0739710713711999, rtol=1e-14, atol=0)
+
+
+def test_golden_ghost_mesh_assembly(oracle):
+    """python/test/unit/fem/test_ghost_mesh_assembly.py:43-66: a = f u v dx + u v ds, L = f v dx + 2 v ds."""
+    O = oracle
+    from dolfinx_b200 import mesh as M
+
+    p = P.tri_p1(12, 12)
+    f = np.full(p.ndofs, 10.0)
+    pat, data = P.oracle_assemble_matrix(O, p, O.K_MASS_COEFF_P1_TRI_A, coeff=(f, p.dofmap, 1))
+    ents = M.exterior_facets(p.x_dofmap, M.TRI_FACETS)
+    assert len(ents) == 48
+    O.assemble_matrix(O.K_FACET_MASS_P1_TRI_A, p.x_dofmap, p.x, None, p.dofmap, 1, p.dofmap, 1, data, pat.edges,
+                      pat.offsets, entities=ents)
+    b = P.oracle_assemble_vector(O, p, O.K_LOAD_COEFF_P1_TRI_L, coeff=(f, p.dofmap, 1))
+    O.assemble_vector(O.K_FACET_CONST_P1_TRI_L, p.x_dofmap, p.x, None, p.dofmap, 1, b, constants=np.array([2.0]),
+                      entities=ents)
+    assert np.sqrt(np.sum(data**2)) == pytest.approx(0.6713621455570528, rel=1e-12)
+    assert np.linalg.norm(b) == pytest.approx(1.582294032953906, rel=1e-12)
+
+
+def test_boundary_measure(oracle):
+    """python/test/unit/fem/test_assembler.py:83-89 flavour: sum of int 1*v ds over the unit cube = 6."""
+    O = oracle
+    from dolfinx_b200 import mesh as M
+
+    p = P.tet_p1(3)
+    ents = M.exterior_facets(p.x_dofmap, M.TET_FACETS)
+    assert len(ents) == 12 * 9
+    b = np.zeros(p.ndofs)
+    coeffs = np.ones((len(ents), 4))
+    O.assemble_vector(O.K_FACET_LOAD_P1_TET_L, p.x_dofmap, p.x, None, p.dofmap, 1, b, coeffs=coeffs, entities=ents)
+    assert b.sum() == pytest.approx(6.0, rel=1e-13)
+
+
+def test_p2_poisson_box12_known_answers(oracle):
+    """cpp/test/matrix.cpp:31-120: P2 Poisson kappa=2 on create_box 12^3 tets, A.1 = 0 to 1e-13;
+    sizes from SURVEY.md Appendix A."""
+    O = oracle
+    p = P.tet_p2(12)
+    assert p.ndofs == 15625
+    pat, data = P.oracle_assemble_matrix(O, p, O.K_POISSON_P2_TET_A, constants=np.array([2.0]))
+    assert len(pat.edges) == 417601
+    y = np.zeros(p.ndofs)
+    O.spmv(data, pat.offsets[:-1], pat.offsets[1:], pat.edges, np.ones(p.ndofs), y, 1, 1)
+    assert np.max(np.abs(y)) < 1e-13
+    A = sp.csr_matrix((data, pat.edges, pat.offsets))
+    assert abs(A - A.T).max() < 1e-13
+
+
+def test_p1_sizes_and_row_sums(oracle):
+    O = oracle
+    p = P.tet_p1(12, numbering="first_touch")
+    pat, data = P.oracle_assemble_matrix(O, p, O.K_POISSON_P1_TET_A, constants=np.array([2.0]))
+    assert p.ndofs == 2197 and len(pat.edges) == 29053
+    A = sp.csr_matrix((data, pat.edges, pat.offsets))
+    assert np.max(np.abs(A @ np.ones(p.ndofs))) < 1e-13
+    # exact energy of u = x0: kappa * |grad u|^2 * volume = 2
+    u = p.dof_coords[:, 0]
+    assert u @ (A @ u) == pytest.approx(2.0, rel=1e-13)
+
+
+def test_p1_load_integrates_exactly(oracle):
+    O = oracle
+    p = P.tet_p1(4, numbering="random", seed=3)
+    f = 1.0 + 2.0 * p.dof_coords[:, 0] - p.dof_coords[:, 2]  # linear -> exact
+    b = P.oracle_assemble_vector(O, p, O.K_LOAD_P1_TET_L, coeff=(f, p.dofmap, 1))
+    assert b.sum() == pytest.approx(1.0 + 1.0 - 0.5, rel=1e-13)
+    p2 = P.tet_p2(3)
+    f2 = p2.dof_coords[:, 0] ** 2 + p2.dof_coords[:, 1]  # quadratic, in P2
+    b2 = P.oracle_assemble_vector(O, p2, O.K_LOAD_P2_TET_L, coeff=(f2, p2.dofmap, 1))
+    assert b2.sum() == pytest.approx(1.0 / 3.0 + 0.5, rel=1e-13)
+
+
+def test_elasticity_rigid_body_modes(oracle):
+    """Rigid-body null space (cf. python/test/unit/la/test_nullspace.py:86-127) + symmetry."""
+    O = oracle
+    p = P.hex_q1(3, skew=True)
+    E, nu = 1.0e9, 0.3
+    mu, lmbda = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    pat, data = P.oracle_assemble_matrix(O, p, O.K_ELASTICITY_Q1_HEX_A, constants=np.array([mu, lmbda]))
+    A = sp.bsr_matrix((data.reshape(-1, 3, 3), pat.edges, pat.offsets)).tocsr()
+    X = p.dof_coords
+    modes = []
+    for k in range(3):
+        t = np.zeros_like(X)
+        t[:, k] = 1
+        modes.append(t.reshape(-1))
+    for a, b in [(0, 1), (1, 2), (0, 2)]:
+        r = np.zeros_like(X)
+        r[:, a], r[:, b] = -X[:, b], X[:, a]
+        modes.append(r.reshape(-1))
+    scale = abs(A).max()
+    for m in modes:
+        assert np.max(np.abs(A @ m)) < 1e-12 * scale * np.max(np.abs(m))
+    assert abs(A - A.T).max() < 1e-12 * scale
+
+
+def test_reassembly_doubles(oracle):
+    """python/test/unit/fem/test_assembler.py:145-165: assembling twice without zeroing doubles A and b."""
+    O = oracle
+    p = P.tet_p1(3)
+    pat, data = P.oracle_assemble_matrix(O, p, O.K_POISSON_P1_TET_A, constants=np.array([1.0]))
+    n1 = np.sum(data**2)
+    P.oracle_assemble_matrix(O, p, O.K_POISSON_P1_TET_A, pat=pat, constants=np.array([1.0]), data=data)
+    assert np.sum(data**2) == pytest.approx(4 * n1, rel=1e-14)
+
+
+def test_lifting_identity(oracle):
+    """python/test/unit/fem/test_assembler.py:276-294: b - A g (then set_bc) == assemble + apply_lifting + set_bc."""
+    O = oracle
+    p = P.tet_p1(4, numbering="random", seed=1)
+    bdofs = np.flatnonzero(np.isclose(p.dof_coords[:, 0], 0.0) | np.isclose(p.dof_coords[:, 0], 1.0)).astype(np.int32)
+    g = 1.0 + p.dof_coords[:, 1] * 3.0
+    f = P.source_f(p.dof_coords)
+    kappa = np.array([2.0])
+    # unconstrained A, then b - A g
+    pat, A0 = P.oracle_assemble_matrix(O, p, O.K_POISSON_P1_TET_A, constants=kappa)
+    b0 = P.oracle_assemble_vector(O, p, O.K_LOAD_P1_TET_L, coeff=(f, p.dofmap, 1))
+    gvec = np.zeros(p.ndofs)
+    gvec[bdofs] = g[bdofs]
+    ref = b0 - sp.csr_matrix((A0, pat.edges, pat.offsets)) @ gvec
+    ref[bdofs] = g[bdofs]
+    # lifting path
+    b = P.oracle_assemble_vector(O, p, O.K_LOAD_P1_TET_L, coeff=(f, p.dofmap, 1))
+    markers = np.zeros(p.ndofs, dtype=np.int8)
+    values = np.zeros(p.ndofs)
+    O.bc_mark(markers, bdofs)
+    O.bc_set(values, bdofs, g, 0, 1)
+    O.lift_bc(O.K_POISSON_P1_TET_A, p.x_dofmap, p.x, np.arange(len(p.dofmap)), p.dofmap, 1, p.dofmap, 1, b, values,
+              markers, constants=kappa)
+    O.bc_set(b, bdofs, g, 0, 1)
+    assert np.allclose(b, ref, rtol=1e-12, atol=1e-14)
+    # bc rows/cols zeroed + unit diagonal gives the same solution on the boundary rows
+    pat, A1 = P.oracle_assemble_matrix(O, p, O.K_POISSON_P1_TET_A, constants=kappa, bc=markers)
+    O.set_diagonal(A1, pat.edges, pat.offsets, 1, 1, bdofs, 1.0)
+    A1m = sp.csr_matrix((A1, pat.edges, pat.offsets))
+    assert np.allclose((A1m @ gvec)[bdofs], g[bdofs])
+    assert abs(A1m - A1m.T).max() < 1e-14
+
+
+@pytest.mark.parametrize("bs", [(1, 1), (2, 2), (1, 2), (2, 1), (2, 3), (3, 3)])
+def test_spmv_vs_scipy(oracle, bs):
+    """python/test/unit/la/test_matrix_vector.py:47-106 with the fixture data of la/conftest.py:44-65."""
+    O = oracle
+    p = P.tri_p1(5, 4)
+    maps = O.make_index_maps([p.ndofs], [[]], [[]])
+    rows = np.repeat(np.arange(p.ndofs, dtype=np.int32), p.ndofs)
+    cols = np.tile(np.arange(p.ndofs, dtype=np.int32), p.ndofs)
+    pat = O.sparsity_finalize(maps, maps, bs, [rows], [cols])[0]
+    rng = np.random.default_rng(12345)
+    data = rng.random(len(pat.edges) * bs[0] * bs[1])
+    A = sp.bsr_matrix((data.reshape(-1, bs[0], bs[1]), pat.edges, pat.offsets))
+    x = np.arange(p.ndofs * bs[1], dtype=np.float64)
+    y = np.zeros(p.ndofs * bs[0])
+    O.spmv(data, pat.offsets[:-1], pat.offsets[1:], pat.edges, x, y, bs[0], bs[1])
+    assert np.allclose(y, A @ x)
+    xt = np.arange(p.ndofs * bs[0], dtype=np.float64)
+    yt = np.zeros(p.ndofs * bs[1])
+    O.spmv(data, pat.offsets[:-1], pat.offsets[1:], pat.edges, xt, yt, bs[0], bs[1], transpose=True)
+    assert np.allclose(yt, A.T @ xt)
+
+
+def test_insert_paths(oracle):
+    """python/test/unit/la/test_matrix_csr.py:36-107, 253-269."""
+    O = oracle
+    n = 12
+    maps = O.make_index_maps([n], [[]], [[]])
+    rows = np.array([0, 1, 2, 3, 4, 5], dtype=np.int32)
+    r = np.repeat(rows, 6)
+    c = np.tile(rows, 6)
+    p1 = O.sparsity_finalize(maps, maps, (1, 1), [r], [c])[0]
+    data = np.zeros(len(p1.edges))
+    O.insert_csr("csr", data, p1.edges, p1.offsets, np.arange(4.0), [0, 1], [2, 3], 1, 1, "add")
+    O.insert_csr("blocked", data, p1.edges, p1.offsets, np.arange(16.0), [0], [2], 2, 2, "add")  # bs=2 data into bs=1
+    with pytest.raises(RuntimeError, match="Entry not in sparsity"):
+        O.insert_csr("csr", data, p1.edges, p1.offsets, [1.0], [0], [7], 1, 1, "add")
+    maps2 = O.make_index_maps([6], [[]], [[]])
+    p2 = O.sparsity_finalize(maps2, maps2, (2, 2), [np.repeat(np.arange(3, dtype=np.int32), 3)], [np.tile(np.arange(3, dtype=np.int32), 3)])[0]
+    d2 = np.zeros(len(p2.edges) * 4)
+    O.insert_csr("nonblocked", d2, p2.edges, p2.offsets, np.arange(16.0), [0, 1, 2, 3], [0, 1, 2, 3], 2, 2, "set")
+    dense = sp.bsr_matrix((d2.reshape(-1, 2, 2), p2.edges, p2.offsets), shape=(12, 12)).toarray()
+    assert np.array_equal(dense[:4, :4], np.arange(16.0).reshape(4, 4))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="reference shim only exists in the build container")
+@pytest.mark.parametrize("bs", [(1, 1), (2, 2), (3, 3), (2, 3)])
+def test_restatement_vs_reference_matrix_csr_impl(oracle, bs):
+    """Differential test against the REFERENCE's la/matrix_csr_impl.h compiled in place (oracle/_ref)."""
+    O = oracle
+    ref = C.CDLL(REF_SO)
+    rng = np.random.default_rng(7)
+    nrow, ncol = 40, 50
+    dense = rng.random((nrow, ncol)) < 0.3
+    dense[np.arange(nrow), np.arange(nrow)] = True
+    row_ptr = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.int64)
+    cols = np.concatenate([np.flatnonzero(dense[i]) for i in range(nrow)]).astype(np.int32)
+    bs2 = bs[0] * bs[1]
+    for trial in range(20):
+        i = int(rng.integers(nrow))
+        avail = np.flatnonzero(dense[i])
+        xr = np.array([i], dtype=np.int32)
+        xc = rng.choice(avail, size=min(3, len(avail)), replace=False).astype(np.int32)
+        x = rng.random(len(xr) * len(xc) * bs2)
+        for op in (0, 1):
+            d_a = rng.random(len(cols) * bs2)
+            d_b = d_a.copy()
+            O.insert_csr("csr", d_a, cols, row_ptr, x, xr, xc, bs[0], bs[1], "add" if op else "set")
+            err = ref.ref_insert(0, bs[0], bs[1], d_b.ctypes.data_as(C.c_void_p), C.c_size_t(len(d_b)),
+                                 cols.ctypes.data_as(C.c_void_p), C.c_size_t(len(cols)), row_ptr.ctypes.data_as(C.c_void_p),
+                                 C.c_size_t(len(row_ptr)), x.ctypes.data_as(C.c_void_p), xr.ctypes.data_as(C.c_void_p),
+                                 len(xr), xc.ctypes.data_as(C.c_void_p), len(xc), op)
+            assert err == 0
+            assert np.array_equal(d_a, d_b)
+    # spmv / spmvT bit-exact
+    vals = rng.random(len(cols) * bs2)
+    x = rng.random(ncol * bs[1])
+    y_a = rng.random(nrow * bs[0])
+    y_b = y_a.copy()
+    O.spmv(vals, row_ptr[:-1], row_ptr[1:], cols, x, y_a, bs[0], bs[1])
+    ref.ref_spmv.restype = None
+    rb, re = np.ascontiguousarray(row_ptr[:-1]), np.ascontiguousarray(row_ptr[1:])
+    ref.ref_spmv(0, vals.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)), rb.ctypes.data_as(C.c_void_p),
+                 re.ctypes.data_as(C.c_void_p), C.c_size_t(nrow), cols.ctypes.data_as(C.c_void_p), C.c_size_t(len(cols)),
+                 x.ctypes.data_as(C.c_void_p), C.c_size_t(len(x)), y_b.ctypes.data_as(C.c_void_p), C.c_size_t(len(y_b)),
+                 bs[0], bs[1])
+    assert np.array_equal(y_a, y_b)
+    xt = rng.random(nrow * bs[0])
+    yt_a = np.zeros(ncol * bs[1])
+    yt_b = yt_a.copy()
+    O.spmv(vals, row_ptr[:-1], row_ptr[1:], cols, xt, yt_a, bs[0], bs[1], transpose=True)
+    ref.ref_spmv(1, vals.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)), rb.ctypes.data_as(C.c_void_p),
+                 re.ctypes.data_as(C.c_void_p), C.c_size_t(nrow), cols.ctypes.data_as(C.c_void_p), C.c_size_t(len(cols)),
+                 xt.ctypes.data_as(C.c_void_p), C.c_size_t(len(xt)), yt_b.ctypes.data_as(C.c_void_p),
+                 C.c_size_t(len(yt_b)), bs[0], bs[1])
+    assert np.array_equal(yt_a, yt_b)
+    # out-of-pattern entry raises in both
+    d = np.zeros(len(cols) * bs2)
+    missing = int(np.flatnonzero(~dense[0])[0])
+    with pytest.raises(RuntimeError):
+        O.insert_csr("csr", d, cols, row_ptr, np.zeros(bs2), [0], [missing], bs[0], bs[1], "add")
+    xr, xc, x = np.array([0], dtype=np.int32), np.array([missing], dtype=np.int32), np.zeros(bs2)
+    assert ref.ref_insert(0, bs[0], bs[1], d.ctypes.data_as(C.c_void_p), C.c_size_t(len(d)), cols.ctypes.data_as(C.c_void_p),
+                          C.c_size_t(len(cols)), row_ptr.ctypes.data_as(C.c_void_p), C.c_size_t(len(row_ptr)),
+                          x.ctypes.data_as(C.c_void_p), xr.ctypes.data_as(C.c_void_p), 1, xc.ctypes.data_as(C.c_void_p), 1, 1) == -1
