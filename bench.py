@@ -1,0 +1,511 @@
+#!/usr/bin/env python
+"""Benchmark of the DOLFINx assembly hot path on B200 (contract: task statement, section 4).
+
+    python bench.py --gpus N --steps K --warmup W           # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+A *step* is one full matrix assembly call sequence on one batch of synthetic input
+(SURVEY.md §8d): ``assemble_matrix`` with Dirichlet markers + ``set_diagonal`` +
+``MatrixCSR.scatter_reverse``; the ``values <- 0`` fill is excluded (values accumulate
+across steps).  ``value`` = global DOFs / step time, inputs resident in HBM.  ``e2e`` is the same
+metric through the host-buffer C-ABI entry (bfx_assemble_matrix_cells_host): geometry and bc
+markers copied host->device and the CSR values copied device->host inside the timed region.
+SpMV (MatrixCSR::mult) is timed in a second loop and reported under ``spmv``.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "assembled_dofs_per_s_fp64_matrix"
+UNIT = "DOF/s"
+
+CONFIGS = {
+    # name: (cell, element, default n, kernel ids (A, L), block size)
+    "p1": ("tet", "P1", 256),
+    "p2": ("tet", "P2", 128),
+    "q1": ("hex", "Q1", 192),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# problem construction (inputs of the path; not timed)
+# ---------------------------------------------------------------------------------------------
+def build_problem(cfg, n, comm, device):
+    """Returns dict with mesh, V, forms, bc, counts.  Single rank: whole box; N ranks: brick partition."""
+    import torch
+
+    from dolfinx_b200 import _lib as K
+    from dolfinx_b200 import common, fem, mesh as M
+
+    cell, elem, _ = CONFIGS[cfg]
+    if comm.size == 1:
+        n3 = (n, n, n)
+        x = M.box_vertices_torch(n3, device)
+        if cell == "tet":
+            cells = M.box_tets_torch(n3, device)
+        else:
+            cells = M.box_hexes_torch(n3, device)
+        nv = x.shape[0]
+        if elem in ("P1", "Q1"):
+            new = M.first_touch_numbering_torch(cells, nv)
+            dofmap = new[cells.long()].contiguous()
+            ndofs = nv
+            dof_x = torch.empty_like(x)
+            dof_x[new.long()] = x
+            del new
+        else:  # P2: vertices + edges, numbered on the host helper then first-touch
+            cells_h = cells.cpu().numpy()
+            dm_h, ndofs = M.p2_tet_dofmap(cells_h, nv)
+            dofmap = torch.from_numpy(dm_h).to(device)
+            dof_x = None
+        im = common.IndexMap(comm, ndofs)
+        n_cells_local = cells.shape[0]
+        msh = fem.Mesh(comm, x, cells, cell, n_cells_local)
+        ghosts = None
+    else:
+        pg = M.pgrid_for(comm.size)
+        nglob = tuple(n * pg[d] for d in range(3))
+        part = M.BoxPartition(comm.rank, pg, nglob)
+        xh = part.coordinates()
+        if cell == "tet":
+            xd, dm, n_owned, ghosts, owners = part.tets()
+        else:
+            xd, dm, n_owned, ghosts, owners = part.hexes()
+        if elem == "P2":
+            raise SystemExit("multi-GPU bench is defined for P1 / Q1 (BASELINE configs[4])")
+        im = common.IndexMap(comm, n_owned, ghosts, owners)
+        x = torch.from_numpy(xh).to(device)
+        cells = torch.from_numpy(xd).to(device)
+        dofmap = torch.from_numpy(dm).to(device)
+        ndofs = n_owned + len(ghosts)
+        local, _, _, _ = part.vertex_numbering()
+        dof_x = torch.empty((ndofs, 3), dtype=torch.float64, device=device)
+        dof_x[torch.from_numpy(local.reshape(-1)).to(device)] = x
+        msh = fem.Mesh(comm, x, cells, cell, cells.shape[0])
+    bs = 3 if elem == "Q1" else 1
+    V = fem.FunctionSpace(msh, elem, fem.DofMap(dofmap, bs, im))
+    if elem == "P1":
+        kA, kL, consts = K.K_POISSON_P1_TET_A, K.K_LOAD_P1_TET_L, [2.0]
+    elif elem == "P2":
+        kA, kL, consts = K.K_POISSON_P2_TET_A, K.K_LOAD_P2_TET_L, [2.0]
+    else:
+        E, nu = 1.0e9, 0.3
+        kA, kL = K.K_ELASTICITY_Q1_HEX_A, K.K_LOAD_Q1_HEX_L
+        consts = [[E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))]]
+    a = fem.Form([V, V], {fem.IntegralType.cell: [(0, kA, None, [])]}, constants=[fem.Constant(c) for c in consts])
+    f = fem.Function(V)
+    if dof_x is not None:
+        if bs == 1:
+            f.x.array.copy_(10.0 * torch.exp(-((dof_x[:, 0] - 0.5) ** 2 + (dof_x[:, 1] - 0.5) ** 2) / 0.02))
+        else:
+            fv = f.x.array.view(-1, 3)
+            fv[:, 0] = 10 * 300.0**2 * dof_x[:, 0]
+            fv[:, 1] = 10 * 300.0**2 * dof_x[:, 1]
+    else:
+        f.x.array.fill_(1.0)
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, kL, None, [0])]}, coefficients=[f])
+    # Dirichlet dofs: x0 in {0, 1} (cpp/demo/poisson/main.cpp:159-175); elasticity: x0 = 0 or x1 = 1
+    if dof_x is not None:
+        if elem == "Q1":
+            mask = (dof_x[:, 0] < 1e-12) | (dof_x[:, 1] > 1 - 1e-12)
+        else:
+            mask = (dof_x[:, 0] < 1e-12) | (dof_x[:, 0] > 1 - 1e-12)
+        bdofs = torch.nonzero(mask).reshape(-1).to(torch.int32).cpu().numpy()
+    else:
+        bdofs = np.zeros(0, dtype=np.int32)
+    bc = fem.DirichletBC(fem.Constant(np.zeros(bs)), bdofs, V)
+    return dict(mesh=msh, V=V, a=a, L=L, bc=bc, ndofs_local=im.size_local, ndofs_global=im.size_global,
+                n_cells=int(cells.shape[0]), n_x=int(x.shape[0]), bs=bs, nx=int(cells.shape[1]), nd=int(dofmap.shape[1]))
+
+
+def alg_bytes_asm(pb, nnz, n_rows):
+    """B_asm of SURVEY.md §8d."""
+    bs = pb["bs"]
+    return (4 * pb["n_cells"] * (pb["nx"] + pb["nd"]) + 24 * pb["n_x"] + 8 * bs * bs * nnz + 4 * nnz
+            + 8 * (n_rows + 1) + bs * n_rows)
+
+
+def alg_bytes_spmv(pb, nnz, n_rows, n_cols):
+    bs = pb["bs"]
+    return (8 * bs * bs + 4) * nnz + 8 * (n_rows + 1) + 8 * bs * n_cols + 16 * bs * n_rows
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port on the host cores)
+# ---------------------------------------------------------------------------------------------
+def cpu_assembly_rate(cfg, n_sample, repeats, threads):
+    """DOFs/s of the oracle port: `threads` workers, each assembling its own n_sample^3 box
+    (MPI-rank-like decomposition without the halo), `repeats` times."""
+    from oracle import oracle as O
+    from tests import problems as P
+
+    O.build(fast=True)
+    if cfg == "p1":
+        p = P.tet_p1(n_sample, numbering="first_touch", shuffle_geometry=False)
+        kid, consts = O.K_POISSON_P1_TET_A, np.array([2.0])
+    elif cfg == "p2":
+        p = P.tet_p2(n_sample)
+        kid, consts = O.K_POISSON_P2_TET_A, np.array([2.0])
+    else:
+        p = P.hex_q1(n_sample)
+        kid, consts = O.K_ELASTICITY_Q1_HEX_A, np.array([1.0e9 / 2.6, 1.0e9 * 0.3 / (1.3 * 0.4)])
+    pat = P.oracle_pattern(O, p)
+    cells = np.arange(len(p.dofmap), dtype=np.int32)
+    bdofs = np.flatnonzero((p.dof_coords[:, 0] < 1e-12) | (p.dof_coords[:, 0] > 1 - 1e-12)).astype(np.int32)
+    markers = np.zeros(p.ndofs * p.bs, dtype=np.int8)
+    O.bc_mark(markers, O.unroll_dofs(bdofs, p.bs))
+    datas = [np.zeros(len(pat.edges) * p.bs * p.bs) for _ in range(threads)]
+
+    def work(t):
+        for _ in range(repeats):
+            O.assemble_matrix(kid, p.x_dofmap, p.x, cells, p.dofmap, p.bs, p.dofmap, p.bs, datas[t], pat.edges,
+                              pat.offsets, bc0=markers, bc1=markers, constants=consts, fast=True)
+            O.set_diagonal(datas[t], pat.edges, pat.offsets, p.bs, p.bs, O.unroll_dofs(bdofs, p.bs), 1.0)
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    dofs = p.ndofs * p.bs * threads * repeats
+    return dofs / dt, dt, p.ndofs * p.bs, len(cells)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    n_sample = {"p1": 48, "p2": 20, "q1": 24}[args.config]
+    # size each step so that the whole run stays within a few minutes
+    rate, dt, dofs, ncells = cpu_assembly_rate(args.config, n_sample, 1, cores)
+    target_s = 4.0
+    repeats = max(1, int(target_s / max(dt, 1e-3)))
+    for _ in range(args.warmup):
+        cpu_assembly_rate(args.config, n_sample, 1, cores)
+    times, rates = [], []
+    for _ in range(args.steps):
+        r, dts, _, _ = cpu_assembly_rate(args.config, n_sample, repeats, cores)
+        times.append(dts)
+        rates.append(r)
+    value = float(np.mean(rates))
+    sample = (f"{cores} threads x {repeats} x oracle assemble_matrix+set_diagonal on a {n_sample}^3 box "
+              f"({ncells} cells, {dofs} DOFs each), liboracle_fast.so")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    cell, elem, n_def = CONFIGS[args.config]
+    n = args.n or n_def
+    names = {"p1": "Poisson P1 tets", "p2": "Poisson P2 tets", "q1": "Linear elasticity Q1 hexes (bs=3)"}
+    pg = (1, 1, 1)
+    if world > 1:
+        from dolfinx_b200 import mesh as M
+
+        pg = M.pgrid_for(world)
+    return {"workload": f"{names[args.config]} on a {n * pg[0]}x{n * pg[1]}x{n * pg[2]} box: assemble_matrix(bcs) + "
+                        "set_diagonal + scatter_reverse into MatrixCSR",
+            "cells_per_gpu": n, "bricks": list(pg), "l2": "inputs larger than L2 (no flush needed)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="bfx", choices=["bfx", "reference"])
+    ap.add_argument("--config", default="p1", choices=list(CONFIGS))
+    ap.add_argument("--n", type=int, default=0, help="cells per box edge (per GPU); 0 = BASELINE size")
+    ap.add_argument("--strategy", default="atomic", choices=["atomic", "gather"])
+    ap.add_argument("--spmv-reps", type=int, default=100)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "bfx" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from dolfinx_b200 import _lib as K
+    from dolfinx_b200 import common, fem, la
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    comm = common.Comm()
+    cell, elem, n_def = CONFIGS[args.config]
+    n = args.n or n_def
+
+    t0 = time.perf_counter()
+    pb = build_problem(args.config, n, comm, device)
+    torch.cuda.synchronize()
+    t_mesh = time.perf_counter() - t0
+    a, L, V, bc = pb["a"], pb["L"], pb["V"], pb["bc"]
+
+    t0 = time.perf_counter()
+    sp = fem.create_sparsity_pattern(a)
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    torch.cuda.synchronize()
+    t_pattern = time.perf_counter() - t0
+    strat = K.ASM_ATOMIC if args.strategy == "atomic" else K.ASM_GATHER
+    t0 = time.perf_counter()
+    fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)  # builds the assembly plan
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter() - t0
+
+    nnz = A._nnz
+    n_rows = A.num_all_rows()
+    n_cols = A.index_map(1).size_local + A.index_map(1).num_ghosts
+    b_asm = alg_bytes_asm(pb, nnz, n_rows)
+    b_spmv = alg_bytes_spmv(pb, nnz, A.num_owned_rows(), n_cols)
+    hbm_peak, peak_src = peaks()
+
+    def step():
+        fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)
+        fem.set_diagonal(A, V, [bc], 1.0)
+        A.scatter_reverse()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # kernel-only timing of the dominant kernel (assembly) with events on the launching stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    plan = fem._asm_plan(a, a.integral(fem.IntegralType.cell, 0), fem.IntegralType.cell, A)
+    bc0 = fem._bc_markers(V, [bc])
+    carr, ncst = K.constants_array(fem.pack_constants(a))
+    cf = K.make_coeffs()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for i in range(args.steps):
+        step()
+    e_stop.record()
+    barrier()
+    ms_total = e_start.elapsed_time(e_stop)
+    clocks = sampler.stop() if rank == 0 else None
+    # dominant-kernel launches alone, same stream
+    for i in range(args.steps):
+        ev[i][0].record()
+        K.check(K.lib.bfx_assemble_matrix_cells(plan, a.integral(fem.IntegralType.cell, 0).kernel, a.mesh.x.data_ptr(),
+                                                bc0.data_ptr(), bc0.data_ptr(), C.byref(cf), carr, ncst, A.data.data_ptr(),
+                                                strat, K.VALUES_ADD, K.current_stream()))
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms_kernel = float(np.mean([s.elapsed_time(e) for s, e in ev]))
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = pb["ndofs_global"] * pb["bs"] / (ms_step * 1e-3)
+
+    # ---- vector assembly + SpMV (second timed loops) -------------------------------------------
+    b = la.Vector(V.dofmap.index_map, pb["bs"])
+    fem.assemble_vector(b, L)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(5):
+        fem.assemble_vector(b, L)
+        b.scatter_reverse(la.InsertMode.add)
+    e1.record()
+    barrier()
+    ms_vec = e0.elapsed_time(e1) / 5
+    A.set_value(0.0)
+    fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)
+    fem.set_diagonal(A, V, [bc], 1.0)
+    A.scatter_reverse()
+    x = la.Vector(A.index_map(1), pb["bs"])
+    y = la.Vector(A.index_map(0), pb["bs"])
+    g = torch.Generator(device=device)
+    g.manual_seed(12345)
+    x.array.copy_(torch.rand(x.array.numel(), generator=g, device=device, dtype=torch.float64))
+    for _ in range(10):
+        A.mult(x, y)
+    barrier()
+    e0.record()
+    for _ in range(args.spmv_reps):
+        A.mult(x, y)
+    e1.record()
+    barrier()
+    ms_spmv = e0.elapsed_time(e1) / args.spmv_reps
+    tt = torch.tensor([ms_spmv, ms_vec], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_spmv, ms_vec = float(tt[0]), float(tt[1])
+
+    # ---- end-to-end through the host-buffer C-ABI entry ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nval = A.data.numel()
+        x_host = torch.empty((pb["n_x"], 3), dtype=torch.float64, pin_memory=True)
+        x_host.copy_(a.mesh.x)
+        mk_host = torch.empty(bc0.numel(), dtype=torch.int8, pin_memory=True)
+        mk_host.copy_(bc0)
+        out_host = torch.empty(nval, dtype=torch.float64, pin_memory=True)
+        reps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            K.check(K.lib.bfx_assemble_matrix_cells_host(
+                plan, a.integral(fem.IntegralType.cell, 0).kernel, x_host.data_ptr(), pb["n_x"], mk_host.data_ptr(),
+                mk_host.data_ptr(), mk_host.numel(), None, 0, 1, carr, ncst, out_host.data_ptr(), strat, K.current_stream()))
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        td = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        e2e = {"value": pb["ndofs_global"] * pb["bs"] / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 8 + 2 * mk_host.numel()), "d2h_bytes_per_step": int(nval * 8),
+               "ms_per_step": dt * 1e3, "call": "bfx_assemble_matrix_cells_host (pinned host buffers)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        n_sample = {"p1": 48, "p2": 20, "q1": 24}[args.config]
+        r1, dt1, dofs, ncells = cpu_assembly_rate(args.config, n_sample, 1, cores)
+        reps = max(1, int(8.0 / max(dt1, 1e-3)))
+        rate, dtc, _, _ = cpu_assembly_rate(args.config, n_sample, reps, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} threads x {reps} x oracle assemble_matrix+set_diagonal on a {n_sample}^3 box "
+                         f"({ncells} cells, {dofs} DOFs each; {dtc:.1f} s), liboracle_fast.so"}
+
+    if rank == 0:
+        ach = b_asm / (ms_kernel * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "roofline": {"bound": "hbm", "kernel": f"assemble_cells_matrix[{args.config},{args.strategy}]",
+                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "alg_bytes_per_launch": b_asm, "kernel_ms": ms_kernel},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": 3 * args.steps,
+            "clocks": clocks,
+            "spmv": {"ms": ms_spmv, "gbs": b_spmv / (ms_spmv * 1e-3) / 1e9, "frac": b_spmv / (ms_spmv * 1e-3) / 1e9 / hbm_peak,
+                     "gflops": 2 * pb["bs"] ** 2 * nnz / (ms_spmv * 1e-3) / 1e9, "alg_bytes": b_spmv, "reps": args.spmv_reps},
+            "vector_assembly_ms": ms_vec,
+            "sizes": {"dofs_global": pb["ndofs_global"] * pb["bs"], "cells_per_gpu": pb["n_cells"], "nnz_per_gpu": nnz},
+            "setup_s": {"mesh": t_mesh, "sparsity+matrix": t_pattern, "assembly_plan+first_call": t_plan},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -405,6 +405,54 @@ def norm(x: Vector, type: Norm = Norm.l2) -> float:
 # ---------------------------------------------------------------------------------------------
 # MatrixCSR
 # ---------------------------------------------------------------------------------------------
+def matrix_ghost_plan(index_maps, bs, indptr, indices):
+    """Ghost-row exchange plan built by the MatrixCSR constructor (la/MatrixCSR.h:705-849), host side.
+
+    Returns the reference's members: ``ghost_row_to_rank`` (index into src), ``val_send_disp`` /
+    ``val_recv_disp`` (already x bs0*bs1), ``unpack_pos`` (block positions in the owner's CSR)."""
+    m0, m1 = index_maps
+    comm = m0.comm
+    bs2 = bs[0] * bs[1]
+    ls0, ls1 = m0.size_local, m1.size_local
+    ghost_row_to_rank = np.searchsorted(m0.src, m0.owners).astype(np.int32)  # :725-733
+    row_len = np.diff(indptr[ls0:])
+    data_per_proc = np.zeros(len(m0.src), dtype=np.int64)
+    np.add.at(data_per_proc, ghost_row_to_rank, row_len)  # :735-742
+    val_send_disp = np.concatenate([[0], np.cumsum(data_per_proc)]).astype(np.int64)
+    # (global row, global col) of every ghost-row entry, grouped by owner in ghost-row order (:750-775)
+    grows = np.repeat(np.arange(m0.num_ghosts), row_len)
+    gcols_local = indices[indptr[ls0]:]
+    gcol = m1.local_to_global(gcols_local)
+    grow = m0.ghosts[grows]
+    order = np.argsort(ghost_row_to_rank[grows], kind="stable")
+    pairs = np.stack([grow[order], gcol[order]], axis=1).reshape(-1)
+    send = [pairs[2 * val_send_disp[i]:2 * val_send_disp[i + 1]] for i in range(len(m0.src))]
+    recv = comm.neighbor_alltoallv(m0.src, m0.dest, send, dtype=np.int64)  # :777-800
+    recv_disp = np.concatenate([[0], np.cumsum([len(a) for a in recv])]).astype(np.int64)
+    arr = np.concatenate(recv) if recv else np.zeros(0, dtype=np.int64)
+    # positions in the owner's CSR (:813-846)
+    lrow = (arr[0::2] - m0.local_range[0]).astype(np.int64)
+    if lrow.size and (lrow.min() < 0 or lrow.max() >= ls0):
+        raise RuntimeError("MatrixCSR: received a ghost row this rank does not own")
+    gc = arr[1::2]
+    lcol = gc - m1.local_range[0]
+    ghost_mask = (lcol < 0) | (lcol >= ls1)
+    if np.any(ghost_mask):
+        order1 = np.argsort(m1.ghosts, kind="stable")
+        pos = np.searchsorted(m1.ghosts[order1], gc[ghost_mask])
+        lcol[ghost_mask] = ls1 + order1[pos]
+    unpack = np.empty(lrow.size, dtype=np.int64)
+    for k in range(lrow.size):
+        c0, c1 = indptr[lrow[k]], indptr[lrow[k] + 1]
+        d = c0 + np.searchsorted(indices[c0:c1], lcol[k])
+        if d >= c1 or indices[d] != lcol[k]:
+            raise RuntimeError("MatrixCSR: received ghost-row entry not in sparsity")
+        unpack[k] = d
+    return dict(ghost_row_to_rank=ghost_row_to_rank, val_send_disp=val_send_disp * bs2,
+                val_recv_disp=bs2 * recv_disp // 2, unpack_pos=unpack, src=m0.src.copy(), dest=m0.dest.copy())
+
+
+
 class MatrixCSR:
     """la::MatrixCSR<double> with device storage (la/MatrixCSR.h:67-624).
 
@@ -444,52 +492,9 @@ class MatrixCSR:
 
     # -- ghost-row plan (la/MatrixCSR.h:705-849) -------------------------------------------------
     def _build_ghost_plan(self):
-        m0, m1 = self._index_maps
-        comm = m0.comm
         self._plan_arrays = None
-        if comm.size == 1:
-            return
-        from . import _lib
-
-        bs2 = self._bs[0] * self._bs[1]
-        indices, indptr = self.indices, self.indptr
-        ls0, ls1 = m0.size_local, m1.size_local
-        ghost_row_to_rank = np.searchsorted(m0.src, m0.owners).astype(np.int32)
-        row_len = np.diff(indptr[ls0:])
-        data_per_proc = np.zeros(len(m0.src), dtype=np.int64)
-        np.add.at(data_per_proc, ghost_row_to_rank, row_len)
-        val_send_disp = np.concatenate([[0], np.cumsum(data_per_proc)]).astype(np.int64)
-        # (global row, global col) of every ghost-row entry, grouped by owner in ghost-row order
-        grows = np.repeat(np.arange(m0.num_ghosts), row_len)
-        gcols_local = indices[indptr[ls0]:]
-        gcol = m1.local_to_global(gcols_local)
-        grow = m0.ghosts[grows]
-        order = np.argsort(ghost_row_to_rank[grows], kind="stable")
-        pairs = np.stack([grow[order], gcol[order]], axis=1).reshape(-1)
-        send = [pairs[2 * val_send_disp[i]:2 * val_send_disp[i + 1]] for i in range(len(m0.src))]
-        recv = comm.neighbor_alltoallv(m0.src, m0.dest, send, dtype=np.int64)
-        recv_disp = np.concatenate([[0], np.cumsum([len(a) for a in recv])]).astype(np.int64)
-        arr = np.concatenate(recv) if recv else np.zeros(0, dtype=np.int64)
-        # positions in the owner's CSR (:820-846)
-        lrow = (arr[0::2] - m0.local_range[0]).astype(np.int64)
-        gc = arr[1::2]
-        lcol = gc - m1.local_range[0]
-        ghost_mask = (lcol < 0) | (lcol >= ls1)
-        if np.any(ghost_mask):
-            order1 = np.argsort(m1.ghosts, kind="stable")
-            pos = np.searchsorted(m1.ghosts[order1], gc[ghost_mask])
-            lcol[ghost_mask] = ls1 + order1[pos]
-        unpack = np.empty(lrow.size, dtype=np.int64)
-        for k in range(lrow.size):
-            c0, c1 = indptr[lrow[k]], indptr[lrow[k] + 1]
-            d = c0 + np.searchsorted(indices[c0:c1], lcol[k])
-            if d >= c1 or indices[d] != lcol[k]:
-                raise RuntimeError("MatrixCSR: received ghost-row entry not in sparsity")
-            unpack[k] = d
-        self._plan_arrays = dict(
-            ghost_row_to_rank=ghost_row_to_rank, val_send_disp=val_send_disp * bs2, val_recv_disp=bs2 * recv_disp // 2,
-            unpack_pos=unpack, src=m0.src.copy(), dest=m0.dest.copy(),
-        )
+        if self._index_maps[0].comm.size > 1:
+            self._plan_arrays = matrix_ghost_plan(self._index_maps, self._bs, self.indptr, self.indices)
 
     def _device_scatter_plan(self):
         if self._scatter_plan is None and self._plan_arrays is not None:

@@ -313,3 +313,69 @@ def pgrid_for(nranks: int):
     if nranks in table:
         return table[nranks]
     return (nranks, 1, 1)
+
+
+# ---------------------------------------------------------------------------
+# Device-side generators (torch) for the large benchmark meshes
+# ---------------------------------------------------------------------------
+def box_tets_torch(n, device, origin_stride=None):
+    """Same cells as :func:`box_tets` built on ``device`` (int32, (6*ncubes, 4))."""
+    import torch
+
+    nx, ny, nz = n
+    iz, iy, ix = torch.meshgrid(
+        torch.arange(nz, device=device, dtype=torch.int64),
+        torch.arange(ny, device=device, dtype=torch.int64),
+        torch.arange(nx, device=device, dtype=torch.int64),
+        indexing="ij",
+    )
+    v0 = ((iz * (ny + 1) + iy) * (nx + 1) + ix).reshape(-1)
+    stride = np.array([1, nx + 1, (nx + 1) * (ny + 1)], dtype=np.int64)
+    offs = torch.from_numpy((_CORNER @ stride)[_TET_TABLE].astype(np.int32)).to(device)  # (6,4)
+    return (v0.to(torch.int32)[:, None, None] + offs[None]).reshape(-1, 4).contiguous()
+
+
+def box_hexes_torch(n, device):
+    import torch
+
+    nx, ny, nz = n
+    iz, iy, ix = torch.meshgrid(
+        torch.arange(nz, device=device, dtype=torch.int64),
+        torch.arange(ny, device=device, dtype=torch.int64),
+        torch.arange(nx, device=device, dtype=torch.int64),
+        indexing="ij",
+    )
+    v0 = ((iz * (ny + 1) + iy) * (nx + 1) + ix).reshape(-1)
+    stride = np.array([1, nx + 1, (nx + 1) * (ny + 1)], dtype=np.int64)
+    corner = torch.from_numpy((_CORNER @ stride).astype(np.int32)).to(device)
+    return (v0.to(torch.int32)[:, None] + corner[None]).contiguous()
+
+
+def box_vertices_torch(n, device, p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0), origin=(0, 0, 0), ntot=None):
+    import torch
+
+    nx, ny, nz = n
+    ntot = n if ntot is None else ntot
+    ext = [(p1[i] - p0[i]) / float(ntot[i]) for i in range(3)]
+    ax = [torch.arange(m + 1, device=device, dtype=torch.float64) + origin[d] for d, m in enumerate((nx, ny, nz))]
+    x = torch.empty((nz + 1, ny + 1, nx + 1, 3), device=device, dtype=torch.float64)
+    x[..., 0] = (p0[0] + ax[0] * ext[0])[None, None, :]
+    x[..., 1] = (p0[1] + ax[1] * ext[1])[None, :, None]
+    x[..., 2] = (p0[2] + ax[2] * ext[2])[:, None, None]
+    return x.reshape(-1, 3)
+
+
+def first_touch_numbering_torch(dofmap, ndofs):
+    """Device version of :func:`first_touch_numbering` (scatter-min of first positions + sort)."""
+    import torch
+
+    flat = dofmap.reshape(-1).to(torch.int64)
+    big = flat.numel()
+    first = torch.full((ndofs,), big, device=flat.device, dtype=torch.int64)
+    pos = torch.arange(big, device=flat.device, dtype=torch.int64)
+    first.scatter_reduce_(0, flat, pos, reduce="amin", include_self=True)
+    del pos
+    order = torch.argsort(first, stable=True)
+    new = torch.empty(ndofs, device=flat.device, dtype=torch.int32)
+    new[order] = torch.arange(ndofs, device=flat.device, dtype=torch.int32)
+    return new

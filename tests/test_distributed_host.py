@@ -1,0 +1,190 @@
+"""N>1 path on CPU: (1) the oracle's simulated-rank restatement reproduces serial results;
+(2) the product's host plan construction (IndexMap, Scatterer, SparsityPattern.finalize,
+MatrixCSR ghost plan), run as two gloo processes, is bit-identical to the oracle's plans."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from dolfinx_b200 import mesh as M  # noqa: E402
+from tests import problems as P  # noqa: E402
+
+
+def brick_inputs(nranks, nglob, cell="tet"):
+    pg = M.pgrid_for(nranks)
+    parts = [M.BoxPartition(r, pg, nglob) for r in range(nranks)]
+    out = []
+    for part in parts:
+        x = part.coordinates()
+        xd, dm, n_owned, ghosts, owners = part.tets() if cell == "tet" else part.hexes()
+        out.append(dict(x=x, x_dofmap=xd, dofmap=dm, n_owned=n_owned, ghosts=ghosts, owners=owners, part=part))
+    return out
+
+
+def oracle_world(O, inputs, bs=1):
+    maps = O.make_index_maps([i["n_owned"] for i in inputs], [i["ghosts"] for i in inputs], [i["owners"] for i in inputs])
+    rows, cols = [], []
+    for i in inputs:
+        r, c = O.sparsity_insert_cells(np.arange(len(i["dofmap"])), i["dofmap"], i["dofmap"])
+        rows.append(r)
+        cols.append(c)
+    pats = O.sparsity_finalize(maps, maps, (bs, bs), rows, cols)
+    mats = O.make_matrices(pats)
+    return maps, pats, mats
+
+
+@pytest.mark.parametrize("nranks,nglob", [(2, (4, 3, 3)), (3, (6, 2, 3)), (4, (4, 4, 2)), (8, (4, 4, 4))])
+def test_oracle_distributed_assembly_equals_serial(oracle, nranks, nglob):
+    """Assemble per rank + scatter_rev, gather by global index: identical structure, values to 1e-12,
+    of the serial assembly (cf. cpp/test/matrix.cpp:59-64, serial vs parallel norm)."""
+    O = oracle
+    inputs = brick_inputs(nranks, nglob)
+    maps, pats, mats = oracle_world(O, inputs)
+    kappa = np.array([2.0])
+    for i, A in zip(inputs, mats):
+        O.assemble_matrix(O.K_POISSON_P1_TET_A, i["x_dofmap"], i["x"], np.arange(len(i["dofmap"])), i["dofmap"], 1,
+                          i["dofmap"], 1, A.data, A.cols, A.row_ptr, constants=kappa)
+    total_before = sum(A.data.sum() for A in mats)
+    O.matrix_scatter_rev(mats)
+    # python/test/unit/la/test_matrix_csr.py:111-147: sum preserved, ghost rows zeroed
+    assert sum(A.data.sum() for A in mats) == pytest.approx(total_before, abs=1e-10)
+    for A in mats:
+        assert np.all(A.data[A.row_ptr[A.index_maps[0].size_local]:] == 0)
+    # gather the owned rows in global numbering
+    N = maps[0].size_global
+    G = sp.lil_matrix((N, N))
+    pattern = set()
+    for A in mats:
+        m0, m1 = A.index_maps
+        for r in range(m0.size_local):
+            gr = m0.local_range[0] + r
+            gc = m1.local_to_global(A.cols[A.row_ptr[r]:A.row_ptr[r + 1]])
+            G[gr, gc] = A.data[A.row_ptr[r]:A.row_ptr[r + 1]]
+            pattern.update((gr, int(c)) for c in gc)
+    # serial reference in the same global numbering
+    x = M.box_vertices(nglob)
+    cells = M.box_tets(nglob)
+    # global index of each lattice vertex: owner's offset + owned lexicographic index
+    gid = np.empty(len(x), dtype=np.int64)
+    for i, m in zip(inputs, maps):
+        part = i["part"]
+        local, n_owned, ghosts, owners = part.vertex_numbering()
+        ox, oy, oz = part.origin
+        nz, ny, nx = local.shape
+        izz, iyy, ixx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        lat = ((izz + oz) * (nglob[1] + 1) + (iyy + oy)) * (nglob[0] + 1) + (ixx + ox)
+        lf = local.reshape(-1)
+        own = lf < n_owned
+        gid[lat.reshape(-1)[own]] = m.local_range[0] + lf[own]
+    dm = gid[cells].astype(np.int32)
+    ps = P.Problem(x, cells, dm, len(x), 1, "tetrahedron")
+    pat, ref = P.oracle_assemble_matrix(O, ps, O.K_POISSON_P1_TET_A, constants=kappa)
+    S = sp.csr_matrix((ref, pat.edges, pat.offsets), shape=(N, N))
+    ref_pattern = set(zip(np.repeat(np.arange(N), np.diff(pat.offsets)).tolist(), pat.edges.tolist()))
+    assert pattern == ref_pattern
+    assert abs(G.tocsr() - S).max() <= 1e-12 * abs(S).max()
+    assert O.matrix_squared_norm(mats) == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
+    # distributed mult == serial mult; x on the matrix column map
+    maps1 = [A.index_maps[1] for A in mats]
+    scs = O.make_scatterers(maps1, 1)
+    xg = np.random.default_rng(0).random(N)
+    xs = [np.concatenate([xg[m.local_range[0]:m.local_range[1]], np.zeros(m.num_ghosts)]) for m in maps1]
+    ys = [np.zeros(A.index_maps[0].size_local + A.index_maps[0].num_ghosts) for A in mats]
+    O.matrix_mult(mats, scs, xs, ys)
+    yg = np.concatenate([y[: m.size_local] for y, m in zip(ys, maps)])
+    assert np.max(np.abs(yg - S @ xg)) <= 1e-12 * np.max(np.abs(S @ xg))
+
+
+def test_oracle_scatter_semantics(oracle):
+    """python/test/unit/la/test_vector_scatter.py:26-113, common/test_scatterer.py:11-55:
+    forward => ghosts == owner rank; reverse(add) => owners accumulate every ghost copy."""
+    O = oracle
+    inputs = brick_inputs(4, (4, 4, 2))
+    maps = O.make_index_maps([i["n_owned"] for i in inputs], [i["ghosts"] for i in inputs], [i["owners"] for i in inputs])
+    for bs in (1, 3):
+        scs = O.make_scatterers(maps, bs)
+        xs = [np.concatenate([np.full(bs * m.size_local, float(m.rank)), np.full(bs * m.num_ghosts, -1.0)]) for m in maps]
+        O.vector_scatter_fwd(maps, scs, bs, xs)
+        for m, x in zip(maps, xs):
+            assert np.array_equal(x[bs * m.size_local:], np.repeat(m.owners.astype(float), bs))
+        # reverse add: every ghost holds 1 -> owners gain the number of ranks ghosting each dof
+        xs = [np.concatenate([np.zeros(bs * m.size_local), np.ones(bs * m.num_ghosts)]) for m in maps]
+        O.vector_scatter_rev(maps, scs, bs, xs, "add")
+        assert sum(x[: bs * m.size_local].sum() for m, x in zip(maps, xs)) == bs * sum(m.num_ghosts for m in maps)
+        # plan invariants (common/Scatterer.h:98-101,154-187)
+        for m, s in zip(maps, scs):
+            assert np.all(np.diff(m.owners[s.remote_inds[::bs] // bs]) >= 0)
+            assert s.displs_remote[-1] == bs * m.num_ghosts and len(s.local_inds) == s.displs_local[-1]
+
+
+# ---------------------------------------------------------------------------------------------
+# product host logic under gloo, world_size 2
+# ---------------------------------------------------------------------------------------------
+def _worker(rank, world, port, nglob, tmpdir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        from dolfinx_b200 import common, la
+        from oracle import oracle as O
+
+        inputs = brick_inputs(world, nglob)
+        me = inputs[rank]
+        comm = common.Comm()
+        assert (comm.rank, comm.size) == (rank, world)
+        omaps, opats, omats = oracle_world(O, inputs)
+        # IndexMap
+        im = common.IndexMap(comm, me["n_owned"], me["ghosts"], me["owners"])
+        om = omaps[rank]
+        assert im.local_range == om.local_range and im.size_global == om.size_global
+        assert np.array_equal(im.src, om.src) and np.array_equal(im.dest, om.dest)
+        # Scatterer, bs 1 and 3
+        for bs in (1, 3):
+            sc = common.Scatterer(im, bs)
+            osc = O.make_scatterers(omaps, bs)[rank]
+            for name in ("local_inds", "remote_inds", "sizes_local", "displs_local", "sizes_remote", "displs_remote"):
+                assert np.array_equal(getattr(sc, name), getattr(osc, name)), (name, bs)
+        # SparsityPattern (host COO path) — bit-exact graph, off-diagonal offsets and extended column map
+        pat = la.SparsityPattern(comm, [im, im], [1, 1])
+        pat.insert_cells(np.arange(len(me["dofmap"])), me["dofmap"], me["dofmap"])
+        pat.finalize()
+        op = opats[rank]
+        edges, offsets = pat.graph
+        assert np.array_equal(offsets, op.offsets) and np.array_equal(edges, op.edges)
+        assert np.array_equal(pat.off_diagonal_offsets, op.off_diagonal_offsets)
+        m1, om1 = pat.index_map(1), op.index_maps[1]
+        assert np.array_equal(m1.ghosts, om1.ghosts) and np.array_equal(m1.owners, om1.owners)
+        assert np.array_equal(m1.src, om1.src) and np.array_equal(m1.dest, om1.dest)
+        # MatrixCSR ghost-row plan
+        plan = la.matrix_ghost_plan([pat.index_map(0), pat.index_map(1)], (1, 1), offsets, edges)
+        oA = omats[rank]
+        assert np.array_equal(plan["ghost_row_to_rank"], oA.ghost_row_to_rank)
+        assert np.array_equal(plan["val_send_disp"], oA.val_send_disp)
+        assert np.array_equal(plan["val_recv_disp"], oA.val_recv_disp)
+        assert np.array_equal(plan["unpack_pos"], oA.unpack_pos)
+        # collectives used by la::norm / inner_product
+        assert comm.allreduce_sum(float(rank + 1)) == sum(range(1, world + 1))
+        assert comm.allreduce_max(float(rank)) == world - 1
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nglob", [(2, (4, 3, 2)), (3, (6, 2, 2))])
+def test_product_host_plans_gloo(tmp_path, world, nglob):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(world, port, nglob, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))

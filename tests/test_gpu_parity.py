@@ -1,0 +1,418 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same inputs.
+
+Tolerance (BASELINE.json north_star: 1e-12 relative, fp64, summation order differs under atomics),
+read as SURVEY.md §8c prescribes: |a_ij - ref_ij| <= 1e-12 * max_k |ref_ik| (row-scaled) and
+||A - Aref||_F <= 1e-12 ||Aref||_F.  Structure (row_ptr, cols, off-diagonal offsets) is bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from tests import problems as P
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def bfx():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dolfinx_b200 import _lib, common, fem, la
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.lib, ns.common, ns.fem, ns.la, ns.torch = _lib, common, fem, la, torch
+    return ns
+
+
+def make_space(bfx, p):
+    comm = bfx.common.COMM_SELF
+    msh = bfx.fem.Mesh(comm, p.x, p.x_dofmap, p.cell)
+    im = bfx.common.IndexMap(comm, p.ndofs)
+    V = bfx.fem.FunctionSpace(msh, "Lagrange", bfx.fem.DofMap(p.dofmap, p.bs, im))
+    return msh, V
+
+
+def assemble_A(bfx, V, kernel, constants=(), coefficients=(), active=(), bcs=()):
+    fem, la = bfx.fem, bfx.la
+    a = fem.Form([V, V], {fem.IntegralType.cell: [(0, kernel, None, list(active))]},
+                 coefficients=coefficients, constants=[fem.Constant(c) for c in constants])
+    sp = fem.create_sparsity_pattern(a)
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    fem.assemble_matrix(A, a, bcs=bcs)
+    return a, sp, A
+
+
+def check_matrix(A, pat, ref_data, bs2=1):
+    edges, offsets = A.indices, A.indptr
+    assert np.array_equal(offsets, pat.offsets), "row_ptr must be bit-exact"
+    assert np.array_equal(edges, pat.edges), "column indices must be bit-exact"
+    data = A.data.cpu().numpy()
+    assert P.row_scaled_error(data, ref_data, pat.offsets, bs2) <= TOL
+    assert np.linalg.norm(data - ref_data) <= TOL * np.linalg.norm(ref_data)
+
+
+@pytest.mark.parametrize("numbering", ["lex", "first_touch", "random"])
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_poisson_p1_matrix(bfx, oracle, n, numbering):
+    p = P.tet_p1(n, numbering=numbering, seed=n)
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, bfx.lib.K_POISSON_P1_TET_A, constants=[2.0])
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([2.0]))
+    check_matrix(A, pat, ref)
+    assert np.array_equal(sp.off_diagonal_offsets, pat.off_diagonal_offsets)
+    assert A.squared_norm() == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
+
+
+def test_poisson_p1_32_config1(bfx, oracle):
+    """BASELINE configs[0]: P1 Laplacian on create_box 32^3 tets — matrix + vector into MatrixCSR."""
+    fem, la = bfx.fem, bfx.la
+    p = P.tet_p1(32, numbering="first_touch")
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, bfx.lib.K_POISSON_P1_TET_A, constants=[2.0])
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([2.0]))
+    assert len(pat.edges) == 513313 and p.ndofs == 35937
+    check_matrix(A, pat, ref)
+    f = fem.Function(V)
+    fh = P.source_f(p.dof_coords)
+    f.x.array.copy_(bfx.torch.from_numpy(fh))
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, bfx.lib.K_LOAD_P1_TET_L, None, [0])]}, coefficients=[f])
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    bref = P.oracle_assemble_vector(oracle, p, oracle.K_LOAD_P1_TET_L, coeff=(fh, p.dofmap, 1))
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
+    assert la.norm(b) == pytest.approx(np.linalg.norm(bref), rel=1e-12)
+
+
+def test_golden_scalars_on_gpu(bfx):
+    """The reference's golden numbers reproduced by the CUDA path itself
+    (test_custom_jit_kernels.py:115-116, test_ghost_mesh_assembly.py:64-66)."""
+    fem, la, K = bfx.fem, bfx.la, bfx.lib
+    from dolfinx_b200 import mesh as M
+
+    p = P.tri_p1(13, 13)
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, K.K_LAPLACE_P1_TRI_A)
+    A.scatter_reverse()
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_SOURCE_P1_TRI_L, None, [])]})
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    b.scatter_reverse(la.InsertMode.add)
+    assert np.isclose(np.sqrt(A.squared_norm()), 56.124860801609124, rtol=1e-13)
+    assert np.isclose(la.norm(b), 0.0739710713711999, rtol=1e-13)
+
+    p = P.tri_p1(12, 12)
+    msh, V = make_space(bfx, p)
+    f = fem.Function(V)
+    f.x.array.fill_(10.0)
+    ents = M.exterior_facets(p.x_dofmap, M.TRI_FACETS)
+    a = fem.Form([V, V], {fem.IntegralType.cell: [(0, K.K_MASS_COEFF_P1_TRI_A, None, [0])],
+                          fem.IntegralType.exterior_facet: [(0, K.K_FACET_MASS_P1_TRI_A, ents, [])]}, coefficients=[f])
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_LOAD_COEFF_P1_TRI_L, None, [0])],
+                       fem.IntegralType.exterior_facet: [(0, K.K_FACET_CONST_P1_TRI_L, ents, [])]},
+                 coefficients=[f], constants=[fem.Constant(2.0)])
+    sp = fem.create_sparsity_pattern(a)
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    fem.assemble_matrix(A, a)
+    A.scatter_reverse()
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    b.scatter_reverse(la.InsertMode.add)
+    assert np.sqrt(A.squared_norm()) == pytest.approx(0.6713621455570528, rel=1e-12)
+    assert la.norm(b) == pytest.approx(1.582294032953906, rel=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 6])
+def test_poisson_p2_matrix_and_vector(bfx, oracle, n):
+    fem, la = bfx.fem, bfx.la
+    p = P.tet_p2(n)
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, bfx.lib.K_POISSON_P2_TET_A, constants=[2.0])
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P2_TET_A, constants=np.array([2.0]))
+    check_matrix(A, pat, ref)
+    # cpp/test/matrix.cpp:66-120: A.1 = 0
+    x = la.Vector(A.index_map(1), 1)
+    y = la.Vector(A.index_map(0), 1)
+    x.set(1.0)
+    A.mult(x, y)
+    assert float(y.array.abs().max()) < 1e-13 * float(np.max(np.abs(ref))) * 10
+    f = fem.Function(V)
+    fh = P.source_f(p.dof_coords)
+    f.x.array.copy_(bfx.torch.from_numpy(fh))
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, bfx.lib.K_LOAD_P2_TET_L, None, [0])]}, coefficients=[f])
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    bref = P.oracle_assemble_vector(oracle, p, oracle.K_LOAD_P2_TET_L, coeff=(fh, p.dofmap, 1))
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
+
+
+@pytest.mark.parametrize("skew", [False, True])
+def test_elasticity_q1_matrix_and_vector(bfx, oracle, skew):
+    fem, la = bfx.fem, bfx.la
+    p = P.hex_q1(4, numbering="random", seed=5, skew=skew)
+    msh, V = make_space(bfx, p)
+    E, nu = 1.0e9, 0.3
+    mu, lmbda = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    a, sp, A = assemble_A(bfx, V, bfx.lib.K_ELASTICITY_Q1_HEX_A, constants=[[mu, lmbda]])
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_ELASTICITY_Q1_HEX_A, constants=np.array([mu, lmbda]))
+    check_matrix(A, pat, ref, bs2=9)
+    # f = rho omega^2 (x0, x1, 0), python/demo/demo_elasticity.py:123-125
+    fh = np.zeros((p.ndofs, 3))
+    fh[:, 0], fh[:, 1] = 10 * 300**2 * p.dof_coords[:, 0], 10 * 300**2 * p.dof_coords[:, 1]
+    f = fem.Function(V)
+    f.x.array.copy_(bfx.torch.from_numpy(fh.reshape(-1)))
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, bfx.lib.K_LOAD_Q1_HEX_L, None, [0])]}, coefficients=[f])
+    b = la.Vector(V.dofmap.index_map, 3)
+    fem.assemble_vector(b, L)
+    bref = P.oracle_assemble_vector(oracle, p, oracle.K_LOAD_Q1_HEX_L, coeff=(fh.reshape(-1), p.dofmap, 3))
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
+
+
+@pytest.mark.parametrize("case", ["p1", "q1"])
+def test_bcs_lifting_set_diagonal(bfx, oracle, case):
+    """bc row/col zeroing, set_diagonal, apply_lifting, set_bc against the oracle
+    (fem/assemble_matrix_impl.h:161-196, assembler.h:336-493,644-686, DirichletBC.h:495-578)."""
+    fem, la, O = bfx.fem, bfx.la, oracle
+    torch = bfx.torch
+    if case == "p1":
+        p = P.tet_p1(5, numbering="random", seed=2)
+        kA, consts = bfx.lib.K_POISSON_P1_TET_A, [2.0]
+        okA = O.K_POISSON_P1_TET_A
+    else:
+        p = P.hex_q1(4, numbering="first_touch")
+        kA, consts = bfx.lib.K_ELASTICITY_Q1_HEX_A, [[1.0, 1.5]]
+        okA = O.K_ELASTICITY_Q1_HEX_A
+    bs = p.bs
+    msh, V = make_space(bfx, p)
+    bnodes = np.flatnonzero(np.isclose(p.dof_coords[:, 0], 0.0) | np.isclose(p.dof_coords[:, 1], 1.0)).astype(np.int32)
+    g = fem.Function(V)
+    gh = np.random.default_rng(0).random(p.ndofs * bs)
+    g.x.array.copy_(torch.from_numpy(gh))
+    bc = fem.DirichletBC(g, bnodes)
+    dofs_unrolled, n_owned = bc.dof_indices()
+    assert np.array_equal(dofs_unrolled, O.unroll_dofs(bnodes, bs)) and n_owned == len(dofs_unrolled)
+    a, sp, A = assemble_A(bfx, V, kA, constants=consts, bcs=[bc])
+    fem.set_diagonal(A, V, [bc], 1.0)
+    markers = np.zeros(p.ndofs * bs, dtype=np.int8)
+    O.bc_mark(markers, dofs_unrolled)
+    cc = np.asarray(consts, dtype=np.float64).reshape(-1)
+    pat, ref = P.oracle_assemble_matrix(O, p, okA, constants=cc, bc=markers)
+    O.set_diagonal(ref, pat.edges, pat.offsets, bs, bs, dofs_unrolled, 1.0)
+    check_matrix(A, pat, ref, bs2=bs * bs)
+    # lifting with x0 and alpha
+    x0h = np.random.default_rng(1).random(p.ndofs * bs)
+    x0 = torch.from_numpy(x0h).cuda()
+    b = la.Vector(V.dofmap.index_map, bs)
+    b.array.copy_(torch.from_numpy(np.arange(p.ndofs * bs, dtype=np.float64)))
+    fem.apply_lifting(b, [a], [[bc]], x0=[x0], alpha=0.5)
+    bref = np.arange(p.ndofs * bs, dtype=np.float64)
+    values = np.zeros(p.ndofs * bs)
+    O.bc_set(values, dofs_unrolled, gh, 0, bs)
+    O.lift_bc(okA, p.x_dofmap, p.x, np.arange(len(p.dofmap)), p.dofmap, bs, p.dofmap, bs, bref, values, markers,
+              x0=x0h, alpha=0.5, constants=cc)
+    scale = np.max(np.abs(bref - np.arange(p.ndofs * bs)))
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * max(scale, 1.0)
+    fem.set_bc(b, [bc], x0=x0, alpha=0.5)
+    O.bc_set(bref, dofs_unrolled, gh, 0, bs, x0=x0h, alpha=0.5)
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * max(scale, 1.0)
+    # Constant-valued bc: value[dof % bs]
+    cval = np.arange(1, bs + 1, dtype=np.float64) * 1e-3
+    bcc = fem.DirichletBC(fem.Constant(cval), bnodes, V)
+    xx = torch.zeros(p.ndofs * bs, dtype=torch.float64, device="cuda")
+    bcc.set(xx, None, 2.0)
+    xr = np.zeros(p.ndofs * bs)
+    O.bc_set(xr, dofs_unrolled, cval, 1, bs, alpha=2.0)
+    assert np.array_equal(xx.cpu().numpy(), xr)
+
+
+def test_reassembly_and_packed_coefficients(bfx, oracle):
+    """'does not zero' contract (test_assembler.py:145-165) and pre-packed coefficients (:1111-1205)."""
+    fem, la = bfx.fem, bfx.la
+    p = P.tet_p1(4)
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, bfx.lib.K_POISSON_P1_TET_A, constants=[1.0])
+    n1 = A.squared_norm()
+    fem.assemble_matrix(A, a)
+    assert A.squared_norm() == pytest.approx(4 * n1, rel=1e-13)
+    f = fem.Function(V)
+    fh = P.source_f(p.dof_coords)
+    f.x.array.copy_(bfx.torch.from_numpy(fh))
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, bfx.lib.K_LOAD_P1_TET_L, None, [0])]}, coefficients=[f])
+    b1 = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b1, L)
+    packed = fem.pack_coefficients(L)
+    c, cstride = packed[(fem.IntegralType.cell, 0)]
+    ref = np.zeros((len(p.dofmap), 4))
+    oracle.pack_coefficient(ref, 0, fh, p.dofmap, 1, cells=np.arange(len(p.dofmap)))
+    assert np.array_equal(c.cpu().numpy(), ref)
+    b2 = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b2, L, coeffs=packed)
+    fem.assemble_vector(b2, L, coeffs=packed)
+    assert np.allclose(b2.array.cpu().numpy(), 2 * b1.array.cpu().numpy(), rtol=1e-13, atol=0)
+
+
+def test_exterior_facets_tet(bfx, oracle):
+    fem, la, K, O = bfx.fem, bfx.la, bfx.lib, oracle
+    from dolfinx_b200 import mesh as M
+
+    p = P.tet_p1(4, numbering="random", seed=4)
+    msh, V = make_space(bfx, p)
+    ents = M.exterior_facets(p.x_dofmap, M.TET_FACETS)
+    g = fem.Function(V)
+    gh = np.sin(5 * p.dof_coords[:, 0])
+    g.x.array.copy_(bfx.torch.from_numpy(gh))
+    L = fem.Form([V], {fem.IntegralType.exterior_facet: [(0, K.K_FACET_LOAD_P1_TET_L, ents, [0])]}, coefficients=[g])
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    coeffs = np.zeros((len(ents), 4))
+    O.pack_coefficient(coeffs, 0, gh, p.dofmap, 1, entities=ents)
+    bref = np.zeros(p.ndofs)
+    O.assemble_vector(O.K_FACET_LOAD_P1_TET_L, p.x_dofmap, p.x, None, p.dofmap, 1, bref, coeffs=coeffs, entities=ents)
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
+    a = fem.Form([V, V], {fem.IntegralType.cell: [(0, K.K_POISSON_P1_TET_A, None, [])],
+                          fem.IntegralType.exterior_facet: [(0, K.K_FACET_MASS_P1_TET_A, ents, [])]},
+                 constants=[fem.Constant(1.0)])
+    sp = fem.create_sparsity_pattern(a)
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    fem.assemble_matrix(A, a)
+    pat, ref = P.oracle_assemble_matrix(O, p, O.K_POISSON_P1_TET_A, constants=np.array([1.0]))
+    O.assemble_matrix(O.K_FACET_MASS_P1_TET_A, p.x_dofmap, p.x, None, p.dofmap, 1, p.dofmap, 1, ref, pat.edges,
+                      pat.offsets, entities=ents)
+    check_matrix(A, pat, ref)
+
+
+@pytest.mark.parametrize("bs", [(1, 1), (2, 2), (1, 2), (2, 1), (2, 3), (3, 3)])
+def test_spmv_all_block_sizes(bfx, oracle, bs):
+    """python/test/unit/la/test_matrix_vector.py:47-106 (float64) against scipy and the oracle."""
+    import scipy.sparse as sps
+
+    la, common, torch = bfx.la, bfx.common, bfx.torch
+    n = 30
+    im = common.IndexMap(common.COMM_SELF, n)
+    sp = la.SparsityPattern(common.COMM_SELF, [im, im], bs)
+    sp.insert(np.arange(n), np.arange(n))
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    rng = np.random.default_rng(12345)
+    A.data.copy_(torch.from_numpy(rng.random(A.data.numel())))
+    As = A.to_scipy()
+    b = la.Vector(im, bs[1])
+    u = la.Vector(im, bs[0])
+    b.array.copy_(torch.arange(b.array.numel(), dtype=torch.float64))
+    A.mult(b, u)
+    assert np.allclose(u.array.cpu().numpy(), As @ b.array.cpu().numpy(), rtol=1e-13)
+    bt = la.Vector(im, bs[0])
+    ut = la.Vector(im, bs[1])
+    bt.array.copy_(torch.arange(bt.array.numel(), dtype=torch.float64))
+    A.mult(bt, ut, transpose=True)
+    assert np.allclose(ut.array.cpu().numpy(), As.T @ bt.array.cpu().numpy(), rtol=1e-13)
+    assert np.allclose(A.to_dense(), As.toarray())
+
+
+@pytest.mark.parametrize("kind", ["p1", "p2", "q1"])
+def test_spmv_assembled(bfx, oracle, kind):
+    la, fem, torch = bfx.la, bfx.fem, bfx.torch
+    if kind == "p1":
+        p, k, c = P.tet_p1(12, numbering="random", seed=9), bfx.lib.K_POISSON_P1_TET_A, [2.0]
+    elif kind == "p2":
+        p, k, c = P.tet_p2(6), bfx.lib.K_POISSON_P2_TET_A, [2.0]
+    else:
+        p, k, c = P.hex_q1(6), bfx.lib.K_ELASTICITY_Q1_HEX_A, [[1.0, 2.0]]
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, k, constants=c)
+    x = la.Vector(A.index_map(1), p.bs)
+    y = la.Vector(A.index_map(0), p.bs)
+    xh = np.random.default_rng(12345).random(x.array.numel())
+    x.array.copy_(torch.from_numpy(xh))
+    y0 = np.random.default_rng(1).random(y.array.numel())
+    y.array.copy_(torch.from_numpy(y0))
+    A.mult(x, y)  # y += A x
+    data = A.data.cpu().numpy()
+    yref = y0.copy()
+    oracle.spmv(data, A.indptr[:-1], A.indptr[1:], A.indices, xh, yref, p.bs, p.bs)
+    assert np.max(np.abs(y.array.cpu().numpy() - yref)) <= TOL * np.max(np.abs(yref))
+
+
+def test_insert_set_add_and_errors(bfx, oracle):
+    """python/test/unit/la/test_matrix_csr.py:36-107, 253-269."""
+    la, common = bfx.la, bfx.common
+    im = common.IndexMap(common.COMM_SELF, 8)
+    for bs in (1, 2):
+        sp = la.SparsityPattern(common.COMM_SELF, [im, im], [bs, bs])
+        sp.insert(np.arange(4), np.arange(4))
+        sp.finalize()
+        A = la.MatrixCSR(sp)
+        ref = np.zeros(A.data.numel())
+        edges, offsets = sp.graph
+        for dbs, kind in ((bs, "csr"), (1 if bs == 2 else 2, "nonblocked" if bs == 2 else "blocked")):
+            nr, nc = 2, 2
+            x = np.random.default_rng(dbs).random(nr * nc * dbs * dbs)
+            if kind == "nonblocked":
+                rows, cols = [0, 3], [1, 2]
+            else:
+                rows, cols = [0, 1], [1, 0]
+            A.add(x, rows, cols, dbs)
+            oracle.insert_csr(kind, ref, edges, offsets, x, rows, cols, dbs if kind != "nonblocked" else bs,
+                              dbs if kind != "nonblocked" else bs, "add")
+            A.set(x, rows, cols, dbs)
+            oracle.insert_csr(kind, ref, edges, offsets, x, rows, cols, dbs if kind != "nonblocked" else bs,
+                              dbs if kind != "nonblocked" else bs, "set")
+        assert np.allclose(A.data.cpu().numpy(), ref, rtol=1e-15)
+        with pytest.raises(RuntimeError, match="Entry not in sparsity"):
+            A.add(np.ones(bs * bs), [0], [6], bs)
+
+
+def test_not_in_sparsity_at_plan_build(bfx):
+    """Assembling a form whose dofmap touches entries outside the pattern raises like insert_csr."""
+    fem, la, common = bfx.fem, bfx.la, bfx.common
+    p = P.tet_p1(2)
+    msh, V = make_space(bfx, p)
+    a = fem.Form([V, V], {fem.IntegralType.cell: [(0, bfx.lib.K_POISSON_P1_TET_A, None, [])]}, constants=[fem.Constant(1.0)])
+    im = V.dofmap.index_map
+    sp = la.SparsityPattern(common.COMM_SELF, [im, im], [1, 1])
+    sp.insert_diagonal(np.arange(p.ndofs))
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    with pytest.raises(RuntimeError, match="Entry not in sparsity"):
+        fem.assemble_matrix(A, a)
+
+
+def test_vector_reductions(bfx):
+    """cpp/test/vector.cpp:22-55 flavour on one rank: norms and inner product."""
+    la, common, torch = bfx.la, bfx.common, bfx.torch
+    im = common.IndexMap(common.COMM_SELF, 100003)
+    v = la.Vector(im, 1)
+    h = np.random.default_rng(3).standard_normal(100003)
+    v.array.copy_(torch.from_numpy(h))
+    assert la.norm(v, la.Norm.l2) == pytest.approx(np.linalg.norm(h), rel=1e-13)
+    assert la.norm(v, la.Norm.l1) == pytest.approx(np.abs(h).sum(), rel=1e-13)
+    assert la.norm(v, la.Norm.linf) == np.abs(h).max()
+    w = la.Vector(im, 1)
+    w.set(2.0)
+    assert la.inner_product(v, w) == pytest.approx(2 * h.sum(), rel=1e-11, abs=1e-9)
+
+
+def test_host_buffer_entry(bfx, oracle):
+    """bfx_assemble_matrix_cells_host: the drop-in call with the reference's host containers."""
+    import ctypes as C
+
+    fem, la, lib = bfx.fem, bfx.la, bfx.lib
+    p = P.tet_p1(6, numbering="first_touch")
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, lib.K_POISSON_P1_TET_A, constants=[2.0])
+    plan = fem._asm_plan(a, a.integral(fem.IntegralType.cell, 0), fem.IntegralType.cell, A)
+    out = np.zeros(A.data.numel())
+    carr, nc = lib.constants_array([2.0])
+    lib.check(lib.lib.bfx_assemble_matrix_cells_host(plan, lib.K_POISSON_P1_TET_A, p.x.ctypes.data, len(p.x), None, None, 0,
+                                                     None, 0, 1, carr, nc, out.ctypes.data, lib.ASM_ATOMIC,
+                                                     lib.current_stream()))
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([2.0]))
+    assert P.row_scaled_error(out, ref, pat.offsets) <= TOL
