@@ -281,13 +281,18 @@ __global__ void __launch_bounds__(128) k_vector_cells(const AsmArgs a)
 constexpr int Q1_CELLS = 4;
 
 template <typename PosT, int MODE>
-__global__ void __launch_bounds__(64 * Q1_CELLS) k_elasticity_q1(const AsmArgs a)
+__global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArgs a)
 {
   __shared__ double s_xc[Q1_CELLS][8][3];
   __shared__ double s_g[Q1_CELLS][8][8][3];
   __shared__ double s_w[Q1_CELLS][8];
   __shared__ int32_t s_d0[Q1_CELLS][8], s_d1[Q1_CELLS][8];
   __shared__ int s_skip[Q1_CELLS];
+  // staging of the 64 3x3 blocks of a cell: the 576 scalars are then issued as REDs in address
+  // order (9 consecutive doubles per block), so that the lanes of one RED instruction share 32 B
+  // sectors (each fp64 RED costs a full sector on the L1->L2 crossbar)
+  __shared__ double s_blk[MODE == 0 ? Q1_CELLS : 1][64 * 9];
+  __shared__ long long s_p[MODE == 0 ? Q1_CELLS : 1][64];
 
   const int cl = threadIdx.x >> 6, t = threadIdx.x & 63;
   const double mu = a.constants[0], lmbda = a.constants[1];
@@ -345,7 +350,8 @@ __global__ void __launch_bounds__(64 * Q1_CELLS) k_elasticity_q1(const AsmArgs a
       }
     }
     __syncthreads();
-    if (!s_skip[cl])
+    const bool work = !s_skip[cl];
+    if (work)
     {
       const int i = t >> 3, j = t & 7;
       double D[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -365,12 +371,6 @@ __global__ void __launch_bounds__(64 * Q1_CELLS) k_elasticity_q1(const AsmArgs a
         }
       }
       const double tr = D[0][0] + D[1][1] + D[2][2];
-      double A[3][3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int l = 0; l < 3; ++l)
-          A[k][l] = mu * ((k == l ? tr : 0.0) + D[l][k]) + lmbda * D[k][l];
       const int32_t r = s_d0[cl][i], c = s_d1[cl][j];
       if constexpr (MODE == 0)
       {
@@ -382,22 +382,28 @@ __global__ void __launch_bounds__(64 * Q1_CELLS) k_elasticity_q1(const AsmArgs a
           p = find_col(a.cols, rb, a.row_ptr[r + 1], c);
         if (p < 0)
           *a.err = 1;
-        else
+        s_p[cl][t] = p < 0 ? -1 : p * 9;
+        bool zr[3] = {false, false, false}, zc[3] = {false, false, false};
+        if (a.bc0)
         {
 #pragma unroll
           for (int k = 0; k < 3; ++k)
-          {
-            if (a.bc0 && a.bc0[3 * (int64_t)r + k])
-              continue;
-#pragma unroll
-            for (int l = 0; l < 3; ++l)
-            {
-              if (a.bc1 && a.bc1[3 * (int64_t)c + l])
-                continue;
-              red_add(a.values + p * 9 + k * 3 + l, A[k][l]);
-            }
-          }
+            zr[k] = a.bc0[3 * (int64_t)r + k];
         }
+        if (a.bc1)
+        {
+#pragma unroll
+          for (int l = 0; l < 3; ++l)
+            zc[l] = a.bc1[3 * (int64_t)c + l];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int l = 0; l < 3; ++l)
+          {
+            const double v = mu * ((k == l ? tr : 0.0) + D[l][k]) + lmbda * D[k][l];
+            s_blk[cl][t * 9 + k * 3 + l] = (zr[k] || zc[l]) ? 0.0 : v;
+          }
       }
       else
       {
@@ -411,9 +417,29 @@ __global__ void __launch_bounds__(64 * Q1_CELLS) k_elasticity_q1(const AsmArgs a
 #pragma unroll
         for (int k = 0; k < 3; ++k)
         {
-          const double acc = A[k][0] * dv[0] + A[k][1] * dv[1] + A[k][2] * dv[2];
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < 3; ++l)
+            acc = fma(mu * ((k == l ? tr : 0.0) + D[l][k]) + lmbda * D[k][l], dv[l], acc);
           if (acc != 0.0)
             red_add(a.b + 3 * (int64_t)r + k, -acc);
+        }
+      }
+    }
+    if constexpr (MODE == 0)
+    {
+      __syncthreads();
+      if (work)
+      {
+#pragma unroll
+        for (int it = 0; it < 9; ++it)
+        {
+          const int s = it * 64 + t;
+          const int b = s / 9;
+          const long long p = s_p[cl][b];
+          const double v = s_blk[cl][s];
+          if (p >= 0 && v != 0.0)
+            red_add(a.values + p + (s - 9 * b), v);
         }
       }
     }
