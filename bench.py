@@ -137,21 +137,14 @@ def build_problem(cfg, n, comm, device):
         pg = M.pgrid_for(comm.size)
         nglob = tuple(n * pg[d] for d in range(3))
         part = M.BoxPartition(comm.rank, pg, nglob)
-        xh = part.coordinates()
-        if cell == "tet":
-            xd, dm, n_owned, ghosts, owners = part.tets()
-        else:
-            xd, dm, n_owned, ghosts, owners = part.hexes()
         if elem == "P2":
             raise SystemExit("multi-GPU bench is defined for P1 / Q1 (BASELINE configs[4])")
+        x, cells, dofmap, local, n_owned, ghosts, owners = M.partition_cells_torch(part, cell, device)
         im = common.IndexMap(comm, n_owned, ghosts, owners)
-        x = torch.from_numpy(xh).to(device)
-        cells = torch.from_numpy(xd).to(device)
-        dofmap = torch.from_numpy(dm).to(device)
         ndofs = n_owned + len(ghosts)
-        local, _, _, _ = part.vertex_numbering()
         dof_x = torch.empty((ndofs, 3), dtype=torch.float64, device=device)
-        dof_x[torch.from_numpy(local.reshape(-1)).to(device)] = x
+        dof_x[local.reshape(-1).long()] = x
+        del local
         msh = fem.Mesh(comm, x, cells, cell, cells.shape[0])
     bs = 3 if elem == "Q1" else 1
     V = fem.FunctionSpace(msh, elem, fem.DofMap(dofmap, bs, im))
@@ -359,9 +352,14 @@ def main():
     hbm_peak, peak_src = peaks()
 
     def step():
-        fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)
-        fem.set_diagonal(A, V, [bc], 1.0)
-        A.scatter_reverse()
+        if world > 1:
+            # boundary cells -> ghost-row exchange on the comm stream -> interior cells -> add received rows
+            fem.assemble_matrix_overlapped(A, a, bcs=[bc], strategy=strat)
+            fem.set_diagonal(A, V, [bc], 1.0)
+        else:
+            fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)
+            fem.set_diagonal(A, V, [bc], 1.0)
+            A.scatter_reverse()
 
     def barrier():
         if world > 1:

@@ -288,6 +288,8 @@ __global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArg
   __shared__ double s_w[Q1_CELLS][8];
   __shared__ int32_t s_d0[Q1_CELLS][8], s_d1[Q1_CELLS][8];
   __shared__ int s_skip[Q1_CELLS];
+  __shared__ int s_affine[Q1_CELLS];
+  __shared__ double s_K[Q1_CELLS][10]; // affine cells: K = J^{-1} (9) and |det J|
   // staging of the 64 3x3 blocks of a cell: the 576 scalars are then issued as REDs in address
   // order (9 consecutive doubles per block), so that the lanes of one RED instruction share 32 B
   // sectors (each fp64 RED costs a full sector on the L1->L2 crossbar)
@@ -334,19 +336,54 @@ __global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArg
 #pragma unroll
         for (int m = 0; m < 3; ++m)
           xc[n][m] = s_xc[cl][n][m];
-      const double g0 = 0.5 - 0.28867513459481287, g1 = 0.5 + 0.28867513459481287;
-      const double X[3] = {(t & 1) ? g1 : g0, (t & 2) ? g1 : g0, (t & 4) ? g1 : g0};
-      double K[3][3];
-      const double det = el::HexQ1::jacobian_inverse(xc, X, K);
-      s_w[cl][t] = 0.125 * fabs(det);
+      // Parallelepiped test: x3 = x1+x2-x0, x5 = x1+x4-x0, x6 = x2+x4-x0, x7 = x1+x2+x4-2x0.
+      // On such (affine) cells the integrals are pre-integrated exactly from the 1-D reference
+      // integrals; general trilinear cells use 2x2x2 Gauss points.
+      double dev2 = 0.0, h2 = 0.0;
 #pragma unroll
-      for (int n = 0; n < 8; ++n)
+      for (int m = 0; m < 3; ++m)
       {
-        double d[3], phi;
-        el::HexQ1::dphi(n, X, d, phi);
+        const double e1 = xc[1][m] - xc[0][m], e2 = xc[2][m] - xc[0][m], e3 = xc[4][m] - xc[0][m];
+        const double d3 = xc[3][m] - xc[0][m] - e1 - e2, d5 = xc[5][m] - xc[0][m] - e1 - e3;
+        const double d6 = xc[6][m] - xc[0][m] - e2 - e3, d7 = xc[7][m] - xc[0][m] - e1 - e2 - e3;
+        dev2 += d3 * d3 + d5 * d5 + d6 * d6 + d7 * d7;
+        h2 += e1 * e1 + e2 * e2 + e3 * e3;
+      }
+      const bool affine = dev2 <= 1e-26 * h2;
+      if (affine)
+      {
+        if (t == 0)
+        {
+          const double X[3] = {0.5, 0.5, 0.5};
+          double K[3][3];
+          const double det = el::HexQ1::jacobian_inverse(xc, X, K);
 #pragma unroll
-        for (int m = 0; m < 3; ++m)
-          s_g[cl][t][n][m] = d[0] * K[0][m] + d[1] * K[1][m] + d[2] * K[2][m];
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+              s_K[cl][3 * c + m] = K[c][m];
+          s_K[cl][9] = fabs(det);
+          s_affine[cl] = 1;
+        }
+      }
+      else
+      {
+        if (t == 0)
+          s_affine[cl] = 0;
+        const double g0 = 0.5 - 0.28867513459481287, g1 = 0.5 + 0.28867513459481287;
+        const double X[3] = {(t & 1) ? g1 : g0, (t & 2) ? g1 : g0, (t & 4) ? g1 : g0};
+        double K[3][3];
+        const double det = el::HexQ1::jacobian_inverse(xc, X, K);
+        s_w[cl][t] = 0.125 * fabs(det);
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+        {
+          double d[3], phi;
+          el::HexQ1::dphi(n, X, d, phi);
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+            s_g[cl][t][n][m] = d[0] * K[0][m] + d[1] * K[1][m] + d[2] * K[2][m];
+        }
       }
     }
     __syncthreads();
@@ -355,19 +392,64 @@ __global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArg
     {
       const int i = t >> 3, j = t & 7;
       double D[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
+      if (s_affine[cl])
       {
-        const double wq = s_w[cl][q];
-        const double gi[3] = {s_g[cl][q][i][0], s_g[cl][q][i][1], s_g[cl][q][i][2]};
-        const double gj[3] = {s_g[cl][q][j][0], s_g[cl][q][j][1], s_g[cl][q][j][2]};
+        // reference tensor That[c][d] = int d_c phi_i d_d phi_j over the unit cube, from the 1-D
+        // integrals of N0 = 1 - s, N1 = s: mass 1/3 | 1/6, stiffness +1 | -1, mixed +-1/2
+        double Mm[3], Ss[3], Cij[3], Cji[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+        {
+          const int bi = (i >> m) & 1, bj = (j >> m) & 1;
+          Mm[m] = bi == bj ? (1.0 / 3.0) : (1.0 / 6.0);
+          Ss[m] = bi == bj ? 1.0 : -1.0;
+          Cij[m] = bi ? 0.5 : -0.5; // int N'_i N_j
+          Cji[m] = bj ? 0.5 : -0.5; // int N_i N'_j
+        }
+        double That[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+          {
+            const int o = 3 - c - d; // the third direction when c != d
+            That[c][d] = c == d ? Ss[c] * Mm[(c + 1) % 3] * Mm[(c + 2) % 3] : Cij[c] * Cji[d] * Mm[o];
+          }
+        double K[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+            K[c][m] = s_K[cl][3 * c + m];
+        const double adet = s_K[cl][9];
+        double M1[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            M1[c][b] = That[c][0] * K[0][b] + That[c][1] * K[1][b] + That[c][2] * K[2][b];
 #pragma unroll
         for (int p = 0; p < 3; ++p)
-        {
-          const double wg = wq * gi[p];
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
-            D[p][r] = fma(wg, gj[r], D[p][r]);
+          for (int b = 0; b < 3; ++b)
+            D[p][b] = adet * (K[0][p] * M1[0][b] + K[1][p] * M1[1][b] + K[2][p] * M1[2][b]);
+      }
+      else
+      {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+          const double wq = s_w[cl][q];
+          const double gi[3] = {s_g[cl][q][i][0], s_g[cl][q][i][1], s_g[cl][q][i][2]};
+          const double gj[3] = {s_g[cl][q][j][0], s_g[cl][q][j][1], s_g[cl][q][j][2]};
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+          {
+            const double wg = wq * gi[p];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              D[p][r] = fma(wg, gj[r], D[p][r]);
+          }
         }
       }
       const double tr = D[0][0] + D[1][1] + D[2][2];

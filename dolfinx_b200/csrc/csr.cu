@@ -131,8 +131,11 @@ constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_CHUNK = 4096; // products staged per pass (32 KB of shared memory)
 
 // bs = 1.  One CTA owns R = SPMV_THREADS / LPR consecutive rows; their nonzeros are one contiguous
-// range of values/cols, streamed with coalesced 128-bit loads (4 entries per thread per step),
-// multiplied by the gathered x and staged in shared memory; LPR lanes then reduce each row.
+// range of values/cols.  Consecutive lanes take consecutive entries (coalesced 4 B / 8 B streaming
+// loads), so one warp instruction gathers x for ~2 adjacent rows, whose column sets share cache
+// lines: the x gather — the L1-wavefront limiter of this kernel (ncu, profiles/r01_prof_spmv_p1_128.csv)
+// — touches ~2x fewer lines than with a 4-entries-per-lane (128-bit) mapping.  Products are staged
+// in shared memory and LPR lanes reduce each row.
 // part: FULL sums [row_ptr[i], row_ptr[i+1]); DIAG sums [row_ptr[i], off_diag[i]) (products of the
 // ghost columns are staged but never read).
 template <int LPR>
@@ -142,7 +145,8 @@ __global__ void __launch_bounds__(SPMV_THREADS)
                   double* __restrict__ y)
 {
   constexpr int R = SPMV_THREADS / LPR;
-  __shared__ __align__(16) double prod[SPMV_CHUNK];
+  constexpr int UNROLL = 8;
+  __shared__ double prod[SPMV_CHUNK];
   const int32_t r0 = blockIdx.x * R;
   const int32_t r1 = min(r0 + R, n_rows);
   const int64_t start = row_ptr[r0];
@@ -158,35 +162,25 @@ __global__ void __launch_bounds__(SPMV_THREADS)
   }
   double sum = 0.0;
 
-  const int64_t astart = start & ~int64_t(3); // 16 B aligned for cols, 32 B for values
-  for (int64_t base = astart; base < end; base += SPMV_CHUNK)
+  for (int64_t base = start; base < end; base += SPMV_CHUNK)
   {
-    // ---- stage products
+    // ---- stage products: SPMV_CHUNK / SPMV_THREADS entries per thread, UNROLL loads in flight
 #pragma unroll
-    for (int it = 0; it < SPMV_CHUNK / (4 * SPMV_THREADS); ++it)
+    for (int it0 = 0; it0 < SPMV_CHUNK / SPMV_THREADS; it0 += UNROLL)
     {
-      const int off = (it * SPMV_THREADS + threadIdx.x) * 4;
-      const int64_t k = base + off;
-      if (k + 3 < end && k >= start)
-      {
-        const int4 c = ldg_stream(reinterpret_cast<const int4*>(cols + k));
-        const double2 v0 = ldg_stream(reinterpret_cast<const double2*>(values + k));
-        const double2 v1 = ldg_stream(reinterpret_cast<const double2*>(values + k + 2));
-        double2 p0, p1;
-        p0.x = v0.x * __ldg(x + c.x);
-        p0.y = v0.y * __ldg(x + c.y);
-        p1.x = v1.x * __ldg(x + c.z);
-        p1.y = v1.y * __ldg(x + c.w);
-        *reinterpret_cast<double2*>(prod + off) = p0;
-        *reinterpret_cast<double2*>(prod + off + 2) = p1;
-      }
-      else if (k < end)
-      {
+      int32_t c[UNROLL];
+      double v[UNROLL];
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
-          if (k + m < end && k + m >= start)
-            prod[off + m] = values[k + m] * __ldg(x + cols[k + m]);
+      for (int u = 0; u < UNROLL; ++u)
+      {
+        const int64_t k = base + (it0 + u) * SPMV_THREADS + threadIdx.x;
+        c[u] = k < end ? __ldg(cols + k) : -1;
+        v[u] = k < end ? __ldg(values + k) : 0.0;
       }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (c[u] >= 0)
+          prod[(it0 + u) * SPMV_THREADS + threadIdx.x] = v[u] * __ldg(x + c[u]);
     }
     __syncthreads();
     // ---- reduce the part of my row that lies in this chunk
@@ -202,8 +196,10 @@ __global__ void __launch_bounds__(SPMV_THREADS)
     y[my_row] += sum;
 }
 
-// Blocked rows, compile-time block sizes: one warp per block row, lanes stream the row's
-// nnz*BS0*BS1 contiguous scalars (coalesced), BS0 accumulators per lane, shuffle reduction.
+// Blocked rows, compile-time block sizes: one warp per block row.  The row's nnz*BS0*BS1 contiguous
+// scalars are copied to a per-warp shared buffer with coalesced loads (32 blocks per pass), then
+// each lane owns one block: BS0*BS1 conflict-free LDS (odd stride), BS1 gathered x values, BS0
+// accumulators, shuffle reduction at the end of the row.
 template <int BS0, int BS1>
 __global__ void __launch_bounds__(256)
     k_spmv_blocked(int32_t n_rows, const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
@@ -211,7 +207,10 @@ __global__ void __launch_bounds__(256)
                    double* __restrict__ y, const int32_t* __restrict__ row_list)
 {
   constexpr int BS2 = BS0 * BS1;
-  const int lane = threadIdx.x & 31;
+  constexpr int STRIDE = (BS2 % 2 == 0) ? BS2 + 1 : BS2; // odd stride -> conflict-free per-lane blocks
+  __shared__ double stage[8][32 * STRIDE];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* buf = stage[wib];
   int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (; w < n_rows; w += nw)
@@ -222,16 +221,36 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < BS0; ++k)
       acc[k] = 0.0;
-    const int64_t s0 = b * BS2, s1 = e * BS2;
-    for (int64_t s = s0 + lane; s < s1; s += 32)
+    for (int64_t j0 = b; j0 < e; j0 += 32)
     {
-      const int64_t j = s / BS2;
-      const int rem = (int)(s - j * BS2);
-      const int k0 = rem / BS1, k1 = rem - k0 * BS1;
-      const double p = values[s] * __ldg(x + (int64_t)cols[j] * BS1 + k1);
+      const int nb = (int)min((int64_t)32, e - j0);
+      const double* src = values + j0 * BS2;
+      // coalesced copy of nb*BS2 scalars; scalar s of block q goes to buf[q*STRIDE + s]
 #pragma unroll
-      for (int k = 0; k < BS0; ++k)
-        acc[k] += (k == k0) ? p : 0.0;
+      for (int it = 0; it < BS2; ++it)
+      {
+        const int t = it * 32 + lane;
+        if (t < nb * BS2)
+        {
+          const int q = t / BS2;
+          buf[q * STRIDE + (t - q * BS2)] = __ldg(src + t);
+        }
+      }
+      __syncwarp();
+      if (lane < nb)
+      {
+        const int64_t c = cols[j0 + lane];
+        double xv[BS1];
+#pragma unroll
+        for (int k1 = 0; k1 < BS1; ++k1)
+          xv[k1] = __ldg(x + c * BS1 + k1);
+#pragma unroll
+        for (int k0 = 0; k0 < BS0; ++k0)
+#pragma unroll
+          for (int k1 = 0; k1 < BS1; ++k1)
+            acc[k0] = fma(buf[lane * STRIDE + k0 * BS1 + k1], xv[k1], acc[k0]);
+      }
+      __syncwarp();
     }
 #pragma unroll
     for (int k = 0; k < BS0; ++k)

@@ -359,18 +359,23 @@ def _bc_markers(V: FunctionSpace, bcs):
     return mk
 
 
-def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None):
-    """bfx_asm_t for one integral of a form (cached on the form)."""
+def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, subset=None):
+    """bfx_asm_t for one integral of a form (cached on the form).
+
+    ``subset`` = (tag, cells int32 device tensor) restricts a cell integral to part of its domain
+    (used to overlap boundary-cell assembly with the ghost-row exchange)."""
     from . import _lib
 
-    key = ("plan", id(integ), id(A) if A is not None else None)
+    key = ("plan", id(integ), id(A) if A is not None else None, subset[0] if subset else None)
     if key in form._plans:
         return form._plans[key][0]
     mesh = form.mesh
     V0 = form.function_spaces[0]
     dm0 = V0.dofmap
     dm1 = form.function_spaces[1].dofmap if form.rank == 2 else None
-    if itype == IntegralType.cell:
+    if subset is not None:
+        ent, n = subset[1], int(subset[1].numel())
+    elif itype == IntegralType.cell:
         ent, n = _entities_dev(form, integ, itype)
     else:
         ent, n = None, 0  # facet integrals pass their entities at call time
@@ -386,6 +391,22 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None):
     )
     form._plans[key] = (h, ent)
     return h
+
+
+def _boundary_interior_cells(form: Form, integ: IntegralData):
+    """Split a cell domain into cells that touch a ghost row (their contributions must travel to the
+    owner, la/MatrixCSR.h:399-468) and interior cells (SURVEY.md §8e overlap plan)."""
+    torch = _torch()
+    key = ("split", id(integ))
+    if key not in form._plans:
+        dm0 = form.function_spaces[0].dofmap
+        n_owned = dm0.index_map.size_local
+        ent, n = _entities_dev(form, integ, IntegralType.cell)
+        dmap = dm0.dev if ent is None else dm0.dev[ent.long()]
+        touches = (dmap[:n] >= n_owned).any(dim=1)
+        ids = torch.arange(n, dtype=torch.int32, device=dmap.device) if ent is None else ent
+        form._plans[key] = (ids[touches].contiguous(), ids[~touches].contiguous())
+    return form._plans[key]
 
 
 def _coeffs_for(form: Form, integ: IntegralData, packed):
@@ -448,6 +469,50 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
             A._is_zero = False
     except _lib.BfxError as e:
         raise _translate(e) from e
+    return A
+
+
+def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None, strategy=None):
+    """``assemble_matrix`` + ``A.scatter_reverse()`` with the ghost-row exchange hidden behind the
+    interior cells: boundary cells are assembled first, the NCCL exchange of the ghost rows starts on
+    the communication stream, interior cells are assembled meanwhile, then the received values are
+    added (north_star: "overlapped with interior-cell assembly").  Same result as the two separate
+    reference calls (fem/assembler.h:589-602 then la/MatrixCSR.h:384-468) up to summation order."""
+    from . import _lib
+
+    if a.mesh.comm.size == 1:
+        assemble_matrix(A, a, bcs, constants=constants, strategy=strategy)
+        A.scatter_reverse()
+        return A
+    V0, V1 = a.function_spaces
+    bc0, bc1 = _bc_markers(V0, bcs), _bc_markers(V1, bcs)
+    consts = pack_constants(a) if constants is None else np.asarray(constants, dtype=np.float64)
+    carr, nc = _lib.constants_array(consts)
+    strat = _lib.ASM_ATOMIC if strategy is None else strategy
+    items = list(a._integrals.items())
+    if any(itype != IntegralType.cell for (itype, _), _ in items):
+        raise NotImplementedError("overlapped assembly handles cell integrals")
+
+    def run(tag_index):
+        for (itype, ident), integ in items:
+            cells = _boundary_interior_cells(a, integ)[tag_index]
+            if cells.numel() == 0:
+                continue
+            plan = _asm_plan(a, integ, itype, A, subset=(("bnd", "int")[tag_index], cells))
+            cf = _coeffs_for(a, integ, None)
+            _lib.check(_lib.lib.bfx_assemble_matrix_cells(
+                plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
+                None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(), strat,
+                _lib.VALUES_ADD, _lib.current_stream()))
+
+    try:
+        run(0)
+        A.scatter_rev_begin()
+        run(1)
+        A.scatter_rev_end()
+    except _lib.BfxError as e:
+        raise _translate(e) from e
+    A._is_zero = False
     return A
 
 

@@ -307,6 +307,60 @@ class BoxPartition:
         return lat.astype(np.int32), np.ascontiguousarray(dm.astype(np.int32)), n_owned, ghosts, owners
 
 
+def _partition_numbering_torch(part: "BoxPartition", device):
+    """Device version of :meth:`BoxPartition.vertex_numbering`: (local int32 (nz+1,ny+1,nx+1), n_owned,
+    ghosts int64 numpy, owners int32 numpy)."""
+    import torch
+
+    nx, ny, nz = part.nloc
+    lx, ly, lz = part.lo
+    iz, iy, ix = torch.meshgrid(
+        torch.arange(nz + 1, device=device, dtype=torch.int32),
+        torch.arange(ny + 1, device=device, dtype=torch.int32),
+        torch.arange(nx + 1, device=device, dtype=torch.int32),
+        indexing="ij",
+    )
+    owned = (ix >= lx) & (iy >= ly) & (iz >= lz)
+    ox, oy, oz = part.owned_shape()
+    n_owned = ox * oy * oz
+    local = (((iz - lz) * oy + (iy - ly)) * ox + (ix - lx)).to(torch.int32)
+    gmask = ~owned
+    gidx = torch.nonzero(gmask.reshape(-1)).reshape(-1)  # lexicographic order of the ghosts
+    n_ghost = int(gidx.numel())
+    local.reshape(-1)[gidx] = n_owned + torch.arange(n_ghost, device=device, dtype=torch.int32)
+    gx = ix.reshape(-1)[gidx].to(torch.int64)
+    gy = iy.reshape(-1)[gidx].to(torch.int64)
+    gz = iz.reshape(-1)[gidx].to(torch.int64)
+    mvx = (gx == 0) & (lx == 1)
+    mvy = (gy == 0) & (ly == 1)
+    mvz = (gz == 0) & (lz == 1)
+    orx = part.rc[0] - mvx.to(torch.int64)
+    ory = part.rc[1] - mvy.to(torch.int64)
+    orz = part.rc[2] - mvz.to(torch.int64)
+    owners = orx + part.pgrid[0] * (ory + part.pgrid[1] * orz)
+    ghosts = torch.empty(n_ghost, device=device, dtype=torch.int64)
+    for o in torch.unique(owners).tolist():
+        sel = owners == o
+        rc = (o % part.pgrid[0], (o // part.pgrid[0]) % part.pgrid[1], o // (part.pgrid[0] * part.pgrid[1]))
+        on = tuple(part._split(part.nglob[d], part.pgrid[d], rc[d])[1] for d in range(3))
+        olo = tuple(1 if rc[d] > 0 else 0 for d in range(3))
+        osh = part.owned_shape(rc)
+        px_ = torch.where(mvx[sel], torch.full_like(gx[sel], on[0]), gx[sel])
+        py_ = torch.where(mvy[sel], torch.full_like(gy[sel], on[1]), gy[sel])
+        pz_ = torch.where(mvz[sel], torch.full_like(gz[sel], on[2]), gz[sel])
+        ghosts[sel] = part.offset(o) + ((pz_ - olo[2]) * osh[1] + (py_ - olo[1])) * osh[0] + (px_ - olo[0])
+    return local, n_owned, ghosts.cpu().numpy(), owners.to(torch.int32).cpu().numpy()
+
+
+def partition_cells_torch(part: "BoxPartition", cell: str, device):
+    """(x (N,3) f64, x_dofmap int32, dofmap int32, local numbering, n_owned, ghosts, owners) on ``device``."""
+    local, n_owned, ghosts, owners = _partition_numbering_torch(part, device)
+    lat = box_tets_torch(part.nloc, device) if cell == "tet" else box_hexes_torch(part.nloc, device)
+    dm = local.reshape(-1)[lat.long()].contiguous()
+    x = box_vertices_torch(part.nloc, device, origin=part.origin, ntot=part.nglob)
+    return x, lat, dm, local, n_owned, ghosts, owners
+
+
 def pgrid_for(nranks: int):
     """Brick grid used by the benchmarks: 1, 2x1x1, 2x2x1, 2x2x2."""
     table = {1: (1, 1, 1), 2: (2, 1, 1), 3: (3, 1, 1), 4: (2, 2, 1), 6: (3, 2, 1), 8: (2, 2, 2)}

@@ -539,23 +539,24 @@ static double q1_hex_geometry(const double* xc, const double* X, double phi[8], 
   return fabs(det);
 }
 
-static const double GL3[3] = {0.1127016653792583, 0.5, 0.8872983346207417};
-static const double GW3[3] = {0.2777777777777778, 0.4444444444444444, 0.2777777777777778};
-
 /* a = inner(sigma(u), grad(v)) dx, sigma = 2 mu sym(grad u) + lambda tr(sym grad u) I
  * (python/demo/demo_elasticity.py:131-150); constants c = {mu, lambda}; Q1 vector, bs = 3,
  * element dof index = 3*node + component (assemble_matrix_impl.h:168-173). */
-static void k_elasticity_q1_hex_A(double* A, const double* w, const double* c, const double* xc, const int* e,
-                                  const uint8_t* q, void* d)
+static const double GL3[3] = {0.1127016653792583, 0.5, 0.8872983346207417};
+static const double GW3[3] = {0.2777777777777778, 0.4444444444444444, 0.2777777777777778};
+static const double GL2[2] = {0.21132486540518713, 0.7886751345948129};
+static const double GW2[2] = {0.5, 0.5};
+
+static void elasticity_q1_hex(double* A, const double* c, const double* xc, int npts, const double* gl,
+                              const double* gw)
 {
-  (void)w; (void)e; (void)q; (void)d;
   const double mu = c[0], lmbda = c[1];
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b)
-      for (int cc = 0; cc < 3; ++cc)
+  for (int a = 0; a < npts; ++a)
+    for (int b = 0; b < npts; ++b)
+      for (int cc = 0; cc < npts; ++cc)
       {
-        double X[3] = {GL3[a], GL3[b], GL3[cc]}, phi[8], g[8][3];
-        double wt = GW3[a] * GW3[b] * GW3[cc] * q1_hex_geometry(xc, X, phi, g);
+        double X[3] = {gl[a], gl[b], gl[cc]}, phi[8], g[8][3];
+        double wt = gw[a] * gw[b] * gw[cc] * q1_hex_geometry(xc, X, phi, g);
         for (int i = 0; i < 8; ++i)
           for (int k = 0; k < 3; ++k)
             for (int j = 0; j < 8; ++j)
@@ -568,6 +569,22 @@ static void k_elasticity_q1_hex_A(double* A, const double* w, const double* c, c
                 A[(3 * i + k) * 24 + (3 * j + l)] += wt * v;
               }
       }
+}
+
+static void k_elasticity_q1_hex_A(double* A, const double* w, const double* c, const double* xc, const int* e,
+                                  const uint8_t* q, void* d)
+{
+  (void)w; (void)e; (void)q; (void)d;
+  elasticity_q1_hex(A, c, xc, 3, GL3, GW3);
+}
+
+/* same form with the 2x2x2 Gauss rule (exact on parallelepipeds; the rule the CUDA kernel uses on
+ * general trilinear cells) */
+static void k_elasticity_q1_hex_A_g2(double* A, const double* w, const double* c, const double* xc, const int* e,
+                                     const uint8_t* q, void* d)
+{
+  (void)w; (void)e; (void)q; (void)d;
+  elasticity_q1_hex(A, c, xc, 2, GL2, GW2);
 }
 
 /* L = f . v dx, f a Q1 vector coefficient (w[3*node + comp]) */
@@ -609,6 +626,7 @@ enum
   K_LOAD_Q1_HEX_L = 11,
   K_FACET_LOAD_P1_TET_L = 12,
   K_FACET_MASS_P1_TET_A = 13,
+  K_ELASTICITY_Q1_HEX_A_G2 = 14, /* oracle-only variant: 2x2x2 Gauss */
   K_COUNT
 };
 
@@ -630,6 +648,7 @@ static orc_kernel_t kernel_table(int id)
   case K_LOAD_Q1_HEX_L: return k_load_q1_hex_L;
   case K_FACET_LOAD_P1_TET_L: return k_facet_load_p1_tet_L;
   case K_FACET_MASS_P1_TET_A: return k_facet_mass_p1_tet_A;
+  case K_ELASTICITY_Q1_HEX_A_G2: return k_elasticity_q1_hex_A_g2;
   default: return 0;
   }
 }

@@ -39,6 +39,7 @@ K_ELASTICITY_Q1_HEX_A = 10
 K_LOAD_Q1_HEX_L = 11
 K_FACET_LOAD_P1_TET_L = 12
 K_FACET_MASS_P1_TET_A = 13
+K_ELASTICITY_Q1_HEX_A_G2 = 14  # oracle-only: 2x2x2 Gauss variant
 
 
 def build(fast: bool = False) -> str:

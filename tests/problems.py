@@ -66,12 +66,14 @@ def tet_p2(n, seed=0):
     return Problem(x, cells.copy(), dofmap, ndofs, 1, "tetrahedron", dc)
 
 
-def hex_q1(n, bs=3, numbering="first_touch", seed=0, skew=False):
+def hex_q1(n, bs=3, numbering="first_touch", seed=0, skew=False, perturb=0.0):
     n3 = (n, n, n) if np.isscalar(n) else tuple(n)
     x = M.box_vertices(n3)
     if skew:  # affine map: still parallelepipeds
         T = np.array([[1.0, 0.2, 0.1], [0.0, 0.9, 0.3], [0.05, 0.0, 1.1]])
         x = x @ T.T
+    if perturb:  # general trilinear (non-affine) cells
+        x = x + perturb / max(n3) * (np.random.default_rng(seed + 17).random(x.shape) - 0.5)
     cells = M.box_hexes(n3)
     nv = len(x)
     if numbering == "lex":

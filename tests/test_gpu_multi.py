@@ -71,6 +71,12 @@ def _worker(rank, world, port, nglob, cell, tmpdir):
         assert np.max(np.abs(post - oA.data)) <= 1e-12 * scale
         assert np.all(post[A.indptr[im.size_local] * bs * bs:] == 0)
         assert A.squared_norm() == pytest.approx(O.matrix_squared_norm(omats), rel=1e-12)
+        # overlapped variant: boundary cells -> start ghost-row exchange -> interior cells -> add
+        A2 = la.MatrixCSR(sp)
+        fem.assemble_matrix_overlapped(A2, a)
+        assert np.max(np.abs(A2.data.cpu().numpy() - oA.data)) <= 1e-12 * scale
+        bnd, interior = fem._boundary_interior_cells(a, a.integral(fem.IntegralType.cell, 0))
+        assert bnd.numel() > 0 and interior.numel() > 0 and bnd.numel() + interior.numel() == len(me["dofmap"])
 
         # vector assembly + reverse scatter (la/Vector.h:371-379)
         f = fem.Function(V)

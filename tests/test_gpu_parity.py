@@ -175,6 +175,24 @@ def test_elasticity_q1_matrix_and_vector(bfx, oracle, skew):
     assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
 
 
+def test_elasticity_q1_nonaffine_cells(bfx, oracle):
+    """General trilinear hexahedra take the 2x2x2 Gauss path of the CUDA kernel: compare with the oracle's
+    2x2x2 variant to 1e-12 and with its 3x3x3 rule to quadrature accuracy; a mesh mixing affine and
+    perturbed cells exercises the per-cell switch."""
+    fem, la = bfx.fem, bfx.la
+    p = P.hex_q1(4, numbering="random", seed=6, perturb=0.3)
+    half = p.x[:, 2] < 0.4  # keep the lower layers affine
+    p.x[half] = P.hex_q1(4, numbering="random", seed=6).x[half]
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, bfx.lib.K_ELASTICITY_Q1_HEX_A, constants=[[1.0, 1.5]])
+    pat, ref2 = P.oracle_assemble_matrix(oracle, p, oracle.K_ELASTICITY_Q1_HEX_A_G2, constants=np.array([1.0, 1.5]))
+    check_matrix(A, pat, ref2, bs2=9)
+    pat, ref3 = P.oracle_assemble_matrix(oracle, p, oracle.K_ELASTICITY_Q1_HEX_A, constants=np.array([1.0, 1.5]))
+    data = A.data.cpu().numpy()
+    assert np.linalg.norm(data - ref3) <= 2e-2 * np.linalg.norm(ref3)
+    assert np.linalg.norm(data - ref3) > 1e-9 * np.linalg.norm(ref3)  # the mesh really is non-affine
+
+
 @pytest.mark.parametrize("case", ["p1", "q1"])
 def test_bcs_lifting_set_diagonal(bfx, oracle, case):
     """bc row/col zeroing, set_diagonal, apply_lifting, set_bc against the oracle
