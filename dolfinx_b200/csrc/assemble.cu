@@ -530,6 +530,238 @@ __global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArg
 }
 
 // ---------------------------------------------------------------------------------------------
+// Q1 elasticity, second generation (assembly mode only).  8 cells per CTA, 36 threads per cell: one
+// thread per UNIQUE node pair i <= j (the form is symmetric, block(j,i) = block(i,j)^T), so the
+// fp64 work per cell drops from 64 to 36 block evaluations.  Parallelepiped cells use the
+// pre-integrated reference tensor (no quadrature loop, no per-point gradients); general trilinear
+// cells fall back to 2x2x2 Gauss points staged in shared memory.  All 64 blocks of a cell are
+// staged in shared memory with the bc rows/columns zeroed, then the CTA issues the 8 x 576 scalars
+// as REDs in address order (sector-sharing lanes, see k_elasticity_q1).
+// ---------------------------------------------------------------------------------------------
+constexpr int Q2_CELLS = 8;
+constexpr int Q2_THREADS = 36 * Q2_CELLS;
+
+struct Q2Smem
+{
+  double blk[Q2_CELLS][64 * 9];
+  double g[Q2_CELLS][8][8][3];
+  double w[Q2_CELLS][8];
+  double xc[Q2_CELLS][8][3];
+  double K[Q2_CELLS][10];
+  long long p[Q2_CELLS][64];
+  int32_t d0[Q2_CELLS][8], d1[Q2_CELLS][8];
+  int affine[Q2_CELLS];
+  unsigned char z0[Q2_CELLS][24], z1[Q2_CELLS][24];
+  unsigned char pi[36], pj[36];
+};
+
+template <typename PosT>
+__global__ void __launch_bounds__(Q2_THREADS, 2) k_elasticity_q1_sym(const AsmArgs a)
+{
+  extern __shared__ __align__(16) unsigned char q2_raw[];
+  Q2Smem& S = *reinterpret_cast<Q2Smem*>(q2_raw);
+  const int cl = threadIdx.x / 36, u = threadIdx.x % 36;
+  const double mu = a.constants[0], lmbda = a.constants[1];
+  if (threadIdx.x < 36)
+  {
+    // u -> (i, j), i <= j, row-major over the upper triangle
+    int i = 0, rem = threadIdx.x;
+    while (rem >= 8 - i)
+    {
+      rem -= 8 - i;
+      ++i;
+    }
+    S.pi[threadIdx.x] = (unsigned char)i;
+    S.pj[threadIdx.x] = (unsigned char)(i + rem);
+  }
+  for (int64_t e0 = (int64_t)blockIdx.x * Q2_CELLS; e0 < a.n; e0 += (int64_t)gridDim.x * Q2_CELLS)
+  {
+    const int64_t e = e0 + cl;
+    const bool active = e < a.n;
+    int32_t cell = 0;
+    if (active)
+      cell = a.cells ? a.cells[e] : (int32_t)e;
+    if (active && u < 24)
+    {
+      const int node = u / 3, m = u % 3;
+      S.xc[cl][node][m] = a.x[3 * (int64_t)a.x_dofmap[(int64_t)cell * 8 + node] + m];
+      const int32_t r = a.dofmap0[(int64_t)cell * 8 + node], c = a.dofmap1[(int64_t)cell * 8 + node];
+      S.z0[cl][u] = a.bc0 ? (unsigned char)a.bc0[3 * (int64_t)r + m] : 0;
+      S.z1[cl][u] = a.bc1 ? (unsigned char)a.bc1[3 * (int64_t)c + m] : 0;
+      if (m == 0)
+      {
+        S.d0[cl][node] = r;
+        S.d1[cl][node] = c;
+      }
+    }
+    __syncthreads();
+    if (active && u < 8)
+    {
+      double xc[8][3];
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          xc[n][m] = S.xc[cl][n][m];
+      double dev2 = 0.0, h2 = 0.0;
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+      {
+        const double e1 = xc[1][m] - xc[0][m], e2 = xc[2][m] - xc[0][m], e3 = xc[4][m] - xc[0][m];
+        const double d3 = xc[3][m] - xc[0][m] - e1 - e2, d5 = xc[5][m] - xc[0][m] - e1 - e3;
+        const double d6 = xc[6][m] - xc[0][m] - e2 - e3, d7 = xc[7][m] - xc[0][m] - e1 - e2 - e3;
+        dev2 += d3 * d3 + d5 * d5 + d6 * d6 + d7 * d7;
+        h2 += e1 * e1 + e2 * e2 + e3 * e3;
+      }
+      const bool affine = dev2 <= 1e-26 * h2;
+      if (affine)
+      {
+        if (u == 0)
+        {
+          const double X[3] = {0.5, 0.5, 0.5};
+          double K[3][3];
+          const double det = el::HexQ1::jacobian_inverse(xc, X, K);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+              S.K[cl][3 * c + m] = K[c][m];
+          S.K[cl][9] = fabs(det);
+          S.affine[cl] = 1;
+        }
+      }
+      else
+      {
+        if (u == 0)
+          S.affine[cl] = 0;
+        const double g0 = 0.5 - 0.28867513459481287, g1 = 0.5 + 0.28867513459481287;
+        const double X[3] = {(u & 1) ? g1 : g0, (u & 2) ? g1 : g0, (u & 4) ? g1 : g0};
+        double K[3][3];
+        const double det = el::HexQ1::jacobian_inverse(xc, X, K);
+        S.w[cl][u] = 0.125 * fabs(det);
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+        {
+          double d[3], phi;
+          el::HexQ1::dphi(n, X, d, phi);
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+            S.g[cl][u][n][m] = d[0] * K[0][m] + d[1] * K[1][m] + d[2] * K[2][m];
+        }
+      }
+    }
+    __syncthreads();
+    if (active)
+    {
+      const int i = S.pi[u], j = S.pj[u];
+      double D[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      if (S.affine[cl])
+      {
+        double Mm[3], Ss[3], Cij[3], Cji[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+        {
+          const int bi = (i >> m) & 1, bj = (j >> m) & 1;
+          Mm[m] = bi == bj ? (1.0 / 3.0) : (1.0 / 6.0);
+          Ss[m] = bi == bj ? 1.0 : -1.0;
+          Cij[m] = bi ? 0.5 : -0.5;
+          Cji[m] = bj ? 0.5 : -0.5;
+        }
+        double K[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+            K[c][m] = S.K[cl][3 * c + m];
+        const double adet = S.K[cl][9];
+        double M1[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+          double T[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            T[d] = c == d ? Ss[c] * Mm[(c + 1) % 3] * Mm[(c + 2) % 3] : Cij[c] * Cji[d] * Mm[3 - c - d];
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            M1[c][b] = T[0] * K[0][b] + T[1] * K[1][b] + T[2] * K[2][b];
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            D[p][b] = adet * (K[0][p] * M1[0][b] + K[1][p] * M1[1][b] + K[2][p] * M1[2][b]);
+      }
+      else
+      {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+          const double wq = S.w[cl][q];
+          const double gi[3] = {S.g[cl][q][i][0], S.g[cl][q][i][1], S.g[cl][q][i][2]};
+          const double gj[3] = {S.g[cl][q][j][0], S.g[cl][q][j][1], S.g[cl][q][j][2]};
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+          {
+            const double wg = wq * gi[p];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              D[p][r] = fma(wg, gj[r], D[p][r]);
+          }
+        }
+      }
+      const double tr = D[0][0] + D[1][1] + D[2][2];
+      // positions of block (i,j) and of its transpose (j,i)
+      const int32_t ri = S.d0[cl][i], rj = S.d0[cl][j], ci = S.d1[cl][i], cj = S.d1[cl][j];
+      int64_t pij, pji;
+      if (a.pos)
+      {
+        const PosT* pp = static_cast<const PosT*>(a.pos) + e * 64;
+        pij = a.row_ptr[ri] + pp[i * 8 + j];
+        pji = a.row_ptr[rj] + pp[j * 8 + i];
+      }
+      else
+      {
+        pij = find_col(a.cols, a.row_ptr[ri], a.row_ptr[ri + 1], cj);
+        pji = find_col(a.cols, a.row_ptr[rj], a.row_ptr[rj + 1], ci);
+      }
+      if (pij < 0 || pji < 0)
+        *a.err = 1;
+      S.p[cl][i * 8 + j] = pij < 0 ? -1 : pij * 9;
+      S.p[cl][j * 8 + i] = pji < 0 ? -1 : pji * 9;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+        {
+          // A[(i,k),(j,l)] = mu (delta_kl tr D + D[l][k]) + lambda D[k][l]  =  A[(j,l),(i,k)]
+          const double v = mu * ((k == l ? tr : 0.0) + D[l][k]) + lmbda * D[k][l];
+          S.blk[cl][(i * 8 + j) * 9 + k * 3 + l] = (S.z0[cl][3 * i + k] || S.z1[cl][3 * j + l]) ? 0.0 : v;
+          if (i != j)
+            S.blk[cl][(j * 8 + i) * 9 + l * 3 + k] = (S.z0[cl][3 * j + l] || S.z1[cl][3 * i + k]) ? 0.0 : v;
+        }
+    }
+    __syncthreads();
+    const int ncell = (int)min((int64_t)Q2_CELLS, a.n - e0);
+#pragma unroll 4
+    for (int it = 0; it < (Q2_CELLS * 576) / Q2_THREADS; ++it)
+    {
+      const int s = it * Q2_THREADS + threadIdx.x;
+      const int c2 = s / 576;
+      if (c2 >= ncell)
+        break;
+      const int loc = s - c2 * 576;
+      const int b = loc / 9;
+      const long long p = S.p[c2][b];
+      const double v = S.blk[c2][loc];
+      if (p >= 0 && v != 0.0)
+        red_add(a.values + p + (loc - 9 * b), v);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // plan construction: cell -> CSR position map (replaces std::lower_bound of insert_csr)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_max_row_len(int32_t n, const int64_t* __restrict__ row_ptr, int* __restrict__ out)
@@ -644,11 +876,31 @@ int launch_q1(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
 {
   if (a.n == 0)
     return BFX_OK;
-  const unsigned grid = grid_for((a.n + Q1_CELLS - 1) / Q1_CELLS, 1, 0);
-  if (P->pos_bytes == 2 && a.pos)
-    k_elasticity_q1<uint16_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
+  if constexpr (MODE == 0)
+  {
+    static bool configured = false;
+    if (!configured)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_elasticity_q1_sym<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(Q2Smem)));
+      BFX_CUDA(cudaFuncSetAttribute(k_elasticity_q1_sym<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(Q2Smem)));
+      configured = true;
+    }
+    const unsigned grid = grid_for((a.n + Q2_CELLS - 1) / Q2_CELLS, 1, 0);
+    if (P->pos_bytes == 2 && a.pos)
+      k_elasticity_q1_sym<uint16_t><<<grid, Q2_THREADS, sizeof(Q2Smem), st>>>(a);
+    else
+      k_elasticity_q1_sym<uint8_t><<<grid, Q2_THREADS, sizeof(Q2Smem), st>>>(a);
+  }
   else
-    k_elasticity_q1<uint8_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
+  {
+    const unsigned grid = grid_for((a.n + Q1_CELLS - 1) / Q1_CELLS, 1, 0);
+    if (P->pos_bytes == 2 && a.pos)
+      k_elasticity_q1<uint16_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
+    else
+      k_elasticity_q1<uint8_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
+  }
   BFX_CHECK_LAUNCH();
   return BFX_OK;
 }

@@ -196,6 +196,69 @@ __global__ void __launch_bounds__(SPMV_THREADS)
     y[my_row] += sum;
 }
 
+// bs = 1, row-per-thread variant.  The CTA's contiguous (cols, values) range is staged raw in shared
+// memory with coalesced 128-bit loads; thread t then walks row r0+t out of shared memory (odd row
+// strides are bank-conflict free) and gathers x itself, accumulating in a register.  One warp
+// instruction gathers the k-th entries of 32 CONSECUTIVE ROWS: on locality-ordered matrices these
+// are neighbouring x entries (2-3 cache lines), which is what the entry-consecutive mapping of
+// k_spmv_stream cannot achieve.  Which of the two kernels is faster depends on the numbering, so
+// bfx_spmv times both once per matrix (plan-time autotuning) and keeps the winner.
+constexpr int SPMV_ROWS_CAP = 3840; // staged entries per pass: 45 KB of shared memory
+
+template <int R>
+__global__ void __launch_bounds__(R)
+    k_spmv_rows(int32_t n_rows, const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ row_end_sel,
+                const int32_t* __restrict__ cols, const double* __restrict__ values, const double* __restrict__ x,
+                double* __restrict__ y)
+{
+  __shared__ __align__(16) double s_val[SPMV_ROWS_CAP];
+  __shared__ __align__(16) int32_t s_col[SPMV_ROWS_CAP];
+  const int32_t r0 = blockIdx.x * R;
+  const int32_t r1 = min(r0 + R, n_rows);
+  const int64_t start = row_ptr[r0];
+  const int64_t end = row_ptr[r1];
+  const int my_row = r0 + threadIdx.x;
+  int64_t rb = 0, re = 0;
+  if (my_row < r1)
+  {
+    rb = row_ptr[my_row];
+    re = row_end_sel[my_row];
+  }
+  double sum = 0.0;
+  const int64_t astart = start & ~int64_t(3);
+  for (int64_t base = astart; base < end; base += SPMV_ROWS_CAP)
+  {
+    const int64_t lim = min(end, base + SPMV_ROWS_CAP);
+    // ---- coalesced 128-bit staging of cols and values (4 entries per thread per step)
+    for (int64_t k = base + 4 * (int64_t)threadIdx.x; k < lim; k += 4 * R)
+    {
+      const int o = (int)(k - base);
+      if (k + 3 < lim)
+      {
+        *reinterpret_cast<int4*>(s_col + o) = ldg_stream(reinterpret_cast<const int4*>(cols + k));
+        *reinterpret_cast<double2*>(s_val + o) = ldg_stream(reinterpret_cast<const double2*>(values + k));
+        *reinterpret_cast<double2*>(s_val + o + 2) = ldg_stream(reinterpret_cast<const double2*>(values + k + 2));
+      }
+      else
+      {
+        for (int m = 0; m < 4 && k + m < lim; ++m)
+        {
+          s_col[o + m] = cols[k + m];
+          s_val[o + m] = values[k + m];
+        }
+      }
+    }
+    __syncthreads();
+    const int64_t lo = max(rb, base), hi = min(re, lim);
+#pragma unroll 4
+    for (int64_t k = lo; k < hi; ++k)
+      sum = fma(s_val[k - base], __ldg(x + s_col[k - base]), sum);
+    __syncthreads();
+  }
+  if (my_row < r1)
+    y[my_row] += sum;
+}
+
 // Blocked rows, compile-time block sizes: one warp per block row.  The row's nnz*BS0*BS1 contiguous
 // scalars are copied to a per-warp shared buffer with coalesced loads (32 blocks per pass), then
 // each lane owns one block: BS0*BS1 conflict-free LDS (odd stride), BS1 gathered x values, BS0
@@ -555,15 +618,68 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
   if (A->bs0 == 1 && A->bs1 == 1 && part != BFX_SPMV_OFFDIAG)
   {
     const double avg = (double)A->nnz_owned / (double)n;
-    // rows per CTA chosen so that one pass of SPMV_CHUNK products usually covers the CTA's rows
-    if (avg <= 14.0 * 1.15)
-      k_spmv_stream<1><<<(n + 255) / 256, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
-    else if (avg <= 30.0 * 1.05)
-      k_spmv_stream<2><<<(n + 127) / 128, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
-    else if (avg <= 62.0)
-      k_spmv_stream<4><<<(n + 63) / 64, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
-    else
-      k_spmv_stream<8><<<(n + 31) / 32, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, y);
+    auto launch = [&](int variant, double* yy)
+    {
+      if (variant == 1)
+      {
+        // row-per-thread out of staged (cols, values); rows per CTA so that one pass covers them
+        if (avg <= 15.0)
+          k_spmv_rows<256><<<(n + 255) / 256, 256, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+        else if (avg <= 30.0)
+          k_spmv_rows<128><<<(n + 127) / 128, 128, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+        else
+          k_spmv_rows<64><<<(n + 63) / 64, 64, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+        return;
+      }
+      // entry-consecutive stream; rows per CTA chosen so that one pass of SPMV_CHUNK products covers them
+      if (avg <= 14.0 * 1.15)
+        k_spmv_stream<1><<<(n + 255) / 256, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+      else if (avg <= 30.0 * 1.05)
+        k_spmv_stream<2><<<(n + 127) / 128, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+      else if (avg <= 62.0)
+        k_spmv_stream<4><<<(n + 63) / 64, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+      else
+        k_spmv_stream<8><<<(n + 31) / 32, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
+    };
+    if (A->spmv_variant < 0)
+    {
+      // plan-time autotuning (once per matrix): time both kernels into a scratch y, keep the faster
+      double* scratch = nullptr;
+      cudaEvent_t e0, e1;
+      if (cudaMalloc(&scratch, sizeof(double) * (size_t)n) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess
+          && cudaEventCreate(&e1) == cudaSuccess)
+      {
+        float best = 1e30f;
+        int best_v = 0;
+        for (int v = 0; v < 2; ++v)
+        {
+          float ms = 1e30f;
+          for (int rep = 0; rep < 3; ++rep)
+          {
+            cudaEventRecord(e0, st);
+            launch(v, scratch);
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float t = 0;
+            cudaEventElapsedTime(&t, e0, e1);
+            ms = t < ms ? t : ms;
+          }
+          if (ms < best)
+          {
+            best = ms;
+            best_v = v;
+          }
+        }
+        const_cast<bfx_csr*>(A)->spmv_variant = best_v;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+      }
+      else
+        const_cast<bfx_csr*>(A)->spmv_variant = 0;
+      cudaFree(scratch);
+      BFX_CHECK_LAUNCH();
+    }
+    launch(A->spmv_variant, y);
   }
   else
   {
