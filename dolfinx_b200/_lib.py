@@ -43,7 +43,12 @@ K_LOAD_Q1_HEX_L = 11
 K_FACET_LOAD_P1_TET_L = 12
 K_FACET_MASS_P1_TET_A = 13
 
-ASM_ATOMIC, ASM_GATHER = 0, 1
+ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED = 0, 1, 2
+ERR_UNSUPPORTED = 4
+# bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
+# where it beats the fp64-RED kernel on B200; P2 (id 8) has the variant too but its 100-entry element
+# matrices leave room for only 64 cells per chunk, too few to aggregate (measured slower), so it stays on REDs
+CHUNKED_KERNELS = frozenset({0, 2, 6})
 VALUES_ADD, VALUES_OVERWRITE = 0, 1
 SPMV_FULL, SPMV_DIAG, SPMV_OFFDIAG = 0, 1, 2
 
@@ -95,6 +100,8 @@ _SIGS = {
     "bfx_spmvT": ([vp, vp, vp, vp, ci, vp], ci),
     "bfx_asm_create": ([pvp, vp, vp, ci, vp, ci, vp, ci, i64, vp, i64, i32, ci, vp], ci),
     "bfx_asm_destroy": ([vp], ci),
+    "bfx_asm_build_chunks": ([vp, vp, vp], ci),
+    "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),
     "bfx_lift_bc_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp, vp, vp, f64, vp], ci),

@@ -41,6 +41,38 @@ struct AsmArgs
 };
 } // namespace bfx
 
+// Chunk-aggregated assembly plan (strategy BFX_ASM_CHUNKED, chunked.cu).  The cell list is cut into
+// chunks of `cb` cells; the element matrices of a chunk are staged in shared memory and summed per
+// DISTINCT CSR destination before anything leaves the SM.
+struct ChunkHdr
+{
+  int64_t src_base32; // first 32-entry group of the chunk's source lists
+  int64_t dest_base;  // first destination of the chunk (multiple of 32)
+  int32_t n_dest;     // distinct destinations of the chunk
+  int32_t n_complete; // the first n_complete receive every contribution from this chunk (plain update)
+  int32_t n_src32;    // 32-entry groups of source-list entries
+  int32_t pad;
+};
+
+struct bfx_chunks
+{
+  int cb = 0, n2 = 0;
+  int64_t nchunks = 0, n_dest_pad = 0, n_src32 = 0;
+  ChunkHdr* hdr = nullptr;
+  uint32_t* winfo = nullptr;  // per group of 32 destinations: (offset of its source lists / 32) << 8 | list length
+  void* dest_addr = nullptr;  // scalar index into values per destination
+  int addr_bytes = 4;
+  uint16_t* src = nullptr;    // source lists: indices into the staged element matrices, 32-way interleaved
+  int32_t* perm = nullptr;    // locality ordering of the plan's cell list (or NULL)
+  // geometry dofmap / dofmaps in chunk order (one row per cell slot), so that phase 1 streams them
+  // instead of chasing perm -> cells -> dofmap; NULL = the plan's own arrays are already in order
+  int32_t *xdm = nullptr, *dm0 = nullptr, *dm1 = nullptr;
+  // Dirichlet markers of the current call packed to one bit per dof (rebuilt by every call: 1/8 of the
+  // marker bytes, so the per-cell lookups of phase 1 stay in L1/L2)
+  uint32_t *bits0 = nullptr, *bits1 = nullptr;
+  int64_t n_dofs0 = 0, n_dofs1 = 0; // scalar dofs indexed through dofmap0 / dofmap1
+};
+
 struct bfx_asm
 {
   const bfx_csr* csr = nullptr;
@@ -56,4 +88,13 @@ struct bfx_asm
   double *h_x = nullptr, *h_coeff = nullptr, *h_values = nullptr;
   int8_t *h_bc0 = nullptr, *h_bc1 = nullptr;
   int64_t h_x_n = 0, h_coeff_n = 0, h_bc_n = 0;
+  bfx_chunks* chunks = nullptr;
 };
+
+namespace bfx
+{
+// chunked.cu
+int chunked_supported(int kernel_id);
+int launch_chunked(const bfx_asm* P, int kernel_id, const AsmArgs& a, int values_mode, cudaStream_t st);
+void free_chunks(bfx_chunks* c);
+} // namespace bfx

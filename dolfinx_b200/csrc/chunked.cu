@@ -1,0 +1,986 @@
+// Chunk-aggregated matrix assembly (strategy BFX_ASM_CHUNKED) for
+// fem::impl::assemble_cells_matrix (fem/assemble_matrix_impl.h:92-200) + MatrixCSR::add
+// (la/MatrixCSR.h:310-335, la/matrix_csr_impl.h:67-109).
+//
+// Why: a fp64 RED costs 1.2-1.9 SM-cycles per lane even when it hits L2
+// (profiles/r01_microbench_red_bulk_lds.txt), a shared-memory load 0.07-0.2.  A P1 mesh sends 16
+// contributions per cell to ~2.5 distinct CSR entries per cell, so the sums are formed on the SM:
+//   phase 1  one thread per cell of a chunk of CB cells: gather geometry, element matrix in
+//            registers, bc rows/columns zeroed, entries stored to shared memory (entry-major, so the
+//            stores of a warp are conflict free);
+//   phase 2  one thread per DISTINCT destination of the chunk: sums its contributions from shared
+//            memory through a precomputed source list; destinations that receive all their
+//            contributions from this chunk are updated with a plain load/add/store (or a plain store
+//            when the caller guarantees zeroed values), the others (chunk boundary) with one RED.
+// The plan (bfx_asm_build_chunks) orders the cells along a Morton curve of their centroids when
+// the geometry is given, so a chunk is a compact patch and most destinations are complete.
+// Destinations are sorted by (complete, list length, address): the 32 lanes of a warp walk lists of
+// equal length, the lists are stored 32-way interleaved (one coalesced 64-byte load per step).
+#include "asm_device.cuh"
+#include "elements.cuh"
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+using namespace bfx;
+
+namespace
+{
+constexpr int PLAN_THREADS = 1024;
+constexpr int MAX_LIST = 255;
+
+// cells per chunk for an element matrix of n2 scalars: staging fits 64-100 KB of shared memory and
+// the plan kernel's 1024 x ITEMS keys
+constexpr int chunk_cb(int n2) { return n2 <= 16 ? 512 : (n2 <= 36 ? 256 : (n2 <= 100 ? 64 : 0)); }
+// threads per chunk: one per cell for small element matrices, 4 per cell (rows dealt round-robin) for P2
+constexpr int chunk_threads(int n2) { return n2 <= 16 ? 512 : 256; }
+
+// ---------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------
+struct ChunkBuildArgs
+{
+  int64_t n; // entities of the plan
+  int cb, nd0, nd1, bs0, bs1, n2;
+  const int32_t *perm, *cells, *dofmap0;
+  const int64_t* row_ptr;
+  const char* pos;
+  int pos_stride, pos_bytes;
+  const int32_t* total; // contributions per block entry over the whole cell list
+  int addr_bits;
+  int64_t *o_ndw, *o_nsrc32;                // pass A: per chunk
+  const int64_t *dest_base32, *src_base32;  // pass B: exclusive scans of the above
+  ChunkHdr* hdr;
+  uint32_t* winfo;
+  void* dest_addr;
+  int addr_bytes;
+  uint16_t* src;
+  int* err;
+};
+
+__device__ __forceinline__ uint32_t pos_at(const char* pos, int pos_stride, int pos_bytes, int64_t e, int t)
+{
+  const char* row = pos + e * pos_stride;
+  return pos_bytes == 1 ? (uint32_t) reinterpret_cast<const uint8_t*>(row)[t]
+                        : (uint32_t) reinterpret_cast<const uint16_t*>(row)[t];
+}
+
+// scalar index into values of staged entry idx = k * cb + c of chunk q (k = I * N1 + J), or -1
+__device__ __forceinline__ int64_t contrib_addr(const ChunkBuildArgs& p, int64_t q, int idx, int64_t& blk)
+{
+  const int N1 = p.nd1 * p.bs1;
+  const int c = idx % p.cb, k = idx / p.cb;
+  const int I = k / N1, J = k - I * N1;
+  const int i = I / p.bs0, a = I - i * p.bs0, j = J / p.bs1, b = J - j * p.bs1;
+  const int64_t slot = q * p.cb + c;
+  if (slot >= p.n)
+    return -1;
+  const int64_t e = p.perm ? p.perm[slot] : slot;
+  const int32_t cell = p.cells ? p.cells[e] : (int32_t)e;
+  const int32_t r = p.dofmap0[(int64_t)cell * p.nd0 + i];
+  blk = p.row_ptr[r] + pos_at(p.pos, p.pos_stride, p.pos_bytes, e, i * p.nd1 + j);
+  return blk * (p.bs0 * p.bs1) + a * p.bs1 + b;
+}
+
+// contributions per block entry (how many (cell, i, j) land on it)
+__global__ void k_count_contrib(int64_t n, const int32_t* __restrict__ cells, const int32_t* __restrict__ dofmap0,
+                                int nd0, int nd1, const int64_t* __restrict__ row_ptr, const char* __restrict__ pos,
+                                int pos_stride, int pos_bytes, int32_t* __restrict__ total)
+{
+  const int64_t work = n * nd0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t e = t / nd0;
+    const int i = (int)(t - e * nd0);
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    const int64_t rb = row_ptr[dofmap0[(int64_t)cell * nd0 + i]];
+    for (int j = 0; j < nd1; ++j)
+      atomicAdd(total + rb + pos_at(pos, pos_stride, pos_bytes, e, i * nd1 + j), 1);
+  }
+}
+
+template <int ITEMS, bool WRITE>
+__global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArgs p)
+{
+  using Sort1 = cub::BlockRadixSort<uint64_t, PLAN_THREADS, ITEMS>;
+  using Sort2 = cub::BlockRadixSort<uint32_t, PLAN_THREADS, ITEMS, uint16_t>;
+  using Scan = cub::BlockScan<int, PLAN_THREADS>;
+  constexpr int NK = PLAN_THREADS * ITEMS;
+  union Temp
+  {
+    typename Sort1::TempStorage s1;
+    typename Sort2::TempStorage s2;
+    typename Scan::TempStorage sc;
+  };
+  extern __shared__ __align__(16) unsigned char raw[];
+  Temp& temp = *reinterpret_cast<Temp*>(raw);
+  uint64_t* lastkey = reinterpret_cast<uint64_t*>(raw + ((sizeof(Temp) + 15) / 16) * 16);
+  uint32_t* mw = reinterpret_cast<uint32_t*>(lastkey + PLAN_THREADS);
+  uint32_t* woff = mw + PLAN_THREADS;
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(woff + PLAN_THREADS);
+  uint16_t* dstart = sidx + NK;
+
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ncontrib = p.n2 * p.cb;
+  const uint16_t ZERO = (uint16_t)ncontrib;
+
+  // ---- 1. keys (address << 16 | staged index), sorted by address
+  uint64_t keys[ITEMS];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it)
+  {
+    const int idx = tid * ITEMS + it;
+    int64_t blk, addr = -1;
+    if (idx < ncontrib)
+      addr = contrib_addr(p, q, idx, blk);
+    keys[it] = addr >= 0 ? ((uint64_t)addr << 16) | (uint64_t)idx : ~0ull;
+  }
+  Sort1(temp.s1).Sort(keys, 16, 16 + p.addr_bits);
+  __syncthreads();
+
+  // ---- 2. distinct destinations: heads of equal-address runs
+  lastkey[tid] = keys[ITEMS - 1];
+  mw[tid] = 0;
+  __syncthreads();
+  int nheads = 0, nvalid = 0;
+  bool head[ITEMS];
+  {
+    uint64_t prev = tid ? lastkey[tid - 1] : ~0ull;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+    {
+      const bool valid = keys[it] != ~0ull;
+      head[it] = valid && ((tid == 0 && it == 0) || (keys[it] >> 16) != (prev >> 16));
+      nheads += head[it];
+      nvalid += valid;
+      prev = keys[it];
+    }
+  }
+  int dbase, n_dest, vbase, n_valid;
+  Scan(temp.sc).ExclusiveSum(nheads, dbase, n_dest);
+  __syncthreads();
+  Scan(temp.sc).ExclusiveSum(nvalid, vbase, n_valid);
+  __syncthreads();
+  {
+    int d = dbase;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+    {
+      const int at = tid * ITEMS + it;
+      if (keys[it] != ~0ull)
+        sidx[at] = (uint16_t)(keys[it] & 0xffffu);
+      if (head[it])
+        dstart[d++] = (uint16_t)at;
+    }
+    if (tid == 0)
+      dstart[n_dest] = (uint16_t)n_valid; // NK <= 65535 is checked on the host
+  }
+  __syncthreads();
+
+  // ---- 3. order destinations by (incomplete, list length descending); radix sort is stable, so
+  //         the address order survives inside each class
+  uint32_t k2[ITEMS];
+  uint16_t v2[ITEMS];
+  int ncomp = 0;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it)
+  {
+    const int d = tid * ITEMS + it;
+    k2[it] = 0x3ffu;
+    v2[it] = 0xffffu;
+    if (d < n_dest)
+    {
+      const int st = dstart[d];
+      int cnt = (int)dstart[d + 1] - st;
+      if (cnt > MAX_LIST)
+      {
+        *p.err = 3;
+        cnt = MAX_LIST;
+      }
+      int64_t blk;
+      contrib_addr(p, q, sidx[st], blk);
+      const bool complete = p.total[blk] == cnt;
+      ncomp += complete;
+      k2[it] = ((complete ? 0u : 1u) << 8) | (uint32_t)(MAX_LIST - cnt);
+      v2[it] = (uint16_t)d;
+    }
+  }
+  Sort2(temp.s2).Sort(k2, v2, 0, 10);
+  __syncthreads();
+  int cb_, n_complete;
+  Scan(temp.sc).ExclusiveSum(ncomp, cb_, n_complete);
+  __syncthreads();
+
+  // ---- 4. list length of every group of 32 destinations and the offsets of their lists
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it)
+  {
+    const int r = tid * ITEMS + it;
+    if (r < n_dest)
+      atomicMax(&mw[r >> 5], (uint32_t)(MAX_LIST - (int)(k2[it] & 0xffu)));
+  }
+  __syncthreads();
+  const int n_dw = (n_dest + 31) >> 5;
+  int my_m = tid < n_dw ? (int)mw[tid] : 0, my_off, n_src32;
+  if (n_dw > PLAN_THREADS) // cannot happen: NK / 32 <= 1024 for ITEMS <= 32
+    *p.err = 4;
+  Scan(temp.sc).ExclusiveSum(my_m, my_off, n_src32);
+  woff[tid] = (uint32_t)my_off;
+  __syncthreads();
+
+  if constexpr (!WRITE)
+  {
+    if (tid == 0)
+    {
+      p.o_ndw[q] = n_dw;
+      p.o_nsrc32[q] = n_src32;
+    }
+    return;
+  }
+  else
+  {
+    const int64_t dest_base = p.dest_base32[q] << 5;
+    const int64_t src_base32 = p.src_base32[q];
+    if (tid == 0)
+    {
+      ChunkHdr h;
+      h.src_base32 = src_base32;
+      h.dest_base = dest_base;
+      h.n_dest = n_dest;
+      h.n_complete = n_complete;
+      h.n_src32 = n_src32;
+      h.pad = 0;
+      p.hdr[q] = h;
+    }
+    if (tid < n_dw)
+      p.winfo[(dest_base >> 5) + tid] = (woff[tid] << 8) | mw[tid];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+    {
+      const int r = tid * ITEMS + it;
+      if (r >= n_dw * 32)
+        continue;
+      const int w = r >> 5, lane = r & 31, m = (int)mw[w];
+      uint16_t* out = p.src + ((src_base32 + woff[w]) << 5) + lane;
+      int st = 0, cnt = 0;
+      if (r < n_dest)
+      {
+        const int d = v2[it];
+        st = dstart[d];
+        cnt = min((int)dstart[d + 1] - st, MAX_LIST);
+        int64_t blk;
+        const int64_t addr = contrib_addr(p, q, sidx[st], blk);
+        if (p.addr_bytes == 4)
+          static_cast<uint32_t*>(p.dest_addr)[dest_base + r] = (uint32_t)addr;
+        else
+          static_cast<uint64_t*>(p.dest_addr)[dest_base + r] = (uint64_t)addr;
+      }
+      else if (p.addr_bytes == 4)
+        static_cast<uint32_t*>(p.dest_addr)[dest_base + r] = 0;
+      else
+        static_cast<uint64_t*>(p.dest_addr)[dest_base + r] = 0;
+      for (int j = 0; j < m; ++j)
+        out[j << 5] = j < cnt ? sidx[st + j] : ZERO;
+    }
+  }
+}
+
+template <int ITEMS>
+size_t plan_smem()
+{
+  using Sort1 = cub::BlockRadixSort<uint64_t, PLAN_THREADS, ITEMS>;
+  using Sort2 = cub::BlockRadixSort<uint32_t, PLAN_THREADS, ITEMS, uint16_t>;
+  using Scan = cub::BlockScan<int, PLAN_THREADS>;
+  size_t t = sizeof(typename Sort1::TempStorage);
+  t = t > sizeof(typename Sort2::TempStorage) ? t : sizeof(typename Sort2::TempStorage);
+  t = t > sizeof(typename Scan::TempStorage) ? t : sizeof(typename Scan::TempStorage);
+  t = (t + 15) / 16 * 16;
+  return t + PLAN_THREADS * 8 + PLAN_THREADS * 4 * 2 + (size_t)(2 * PLAN_THREADS * ITEMS + 2) * 2 + 16;
+}
+
+template <int ITEMS>
+int run_plan_pass(bool write, const ChunkBuildArgs& p, int64_t nchunks, cudaStream_t st)
+{
+  const size_t smem = plan_smem<ITEMS>();
+  if (write)
+  {
+    BFX_CUDA(cudaFuncSetAttribute(k_chunk_plan<ITEMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chunk_plan<ITEMS, true><<<(unsigned)nchunks, PLAN_THREADS, smem, st>>>(p);
+  }
+  else
+  {
+    BFX_CUDA(cudaFuncSetAttribute(k_chunk_plan<ITEMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chunk_plan<ITEMS, false><<<(unsigned)nchunks, PLAN_THREADS, smem, st>>>(p);
+  }
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+int run_plan_pass_items(int items, bool write, const ChunkBuildArgs& p, int64_t nchunks, cudaStream_t st)
+{
+  switch (items)
+  {
+  case 5: return run_plan_pass<5>(write, p, nchunks, st);
+  case 7: return run_plan_pass<7>(write, p, nchunks, st);
+  case 8: return run_plan_pass<8>(write, p, nchunks, st);
+  case 9: return run_plan_pass<9>(write, p, nchunks, st);
+  default: return fail(BFX_ERR_UNSUPPORTED, "chunk plan: %d keys per thread not instantiated", items);
+  }
+}
+
+// ---- Morton ordering of the cell list ------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long u)
+{
+  u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+  return __longlong_as_double((long long)u);
+}
+
+__device__ __forceinline__ void centroid(const double* __restrict__ x, const int32_t* __restrict__ xd, int nx,
+                                         double (&c)[3])
+{
+  c[0] = c[1] = c[2] = 0.0;
+  for (int k = 0; k < nx; ++k)
+  {
+    const double* pt = x + 3 * (int64_t)xd[k];
+    c[0] += pt[0], c[1] += pt[1], c[2] += pt[2];
+  }
+  const double s = 1.0 / nx;
+  c[0] *= s, c[1] *= s, c[2] *= s;
+}
+
+// bb[0..2] = min keys, bb[3..5] = max keys
+__global__ void k_centroid_bbox(int64_t n, const int32_t* __restrict__ cells, const int32_t* __restrict__ x_dofmap,
+                                int nx, const double* __restrict__ x, unsigned long long* __restrict__ bb)
+{
+  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    double c[3];
+    centroid(x, x_dofmap + (int64_t)cell * nx, nx, c);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+    {
+      const unsigned long long k = dkey(c[m]);
+      lo[m] = k < lo[m] ? k : lo[m];
+      hi[m] = k > hi[m] ? k : hi[m];
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+  {
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[m], o), b = __shfl_xor_sync(0xffffffffu, hi[m], o);
+      lo[m] = a < lo[m] ? a : lo[m];
+      hi[m] = b > hi[m] ? b : hi[m];
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicMin(bb + m, lo[m]);
+      atomicMax(bb + 3 + m, hi[m]);
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint64_t v)
+{
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void k_morton_keys(int64_t n, const int32_t* __restrict__ cells, const int32_t* __restrict__ x_dofmap,
+                              int nx, const double* __restrict__ x, const unsigned long long* __restrict__ bb,
+                              uint64_t* __restrict__ keys, int32_t* __restrict__ ids)
+{
+  double lo[3], inv[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+  {
+    lo[m] = dkey_inv(bb[m]);
+    const double ext = dkey_inv(bb[3 + m]) - lo[m];
+    inv[m] = ext > 0.0 ? 2097151.0 / ext : 0.0;
+  }
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    double c[3];
+    centroid(x, x_dofmap + (int64_t)cell * nx, nx, c);
+    uint64_t key = 0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+    {
+      double t = (c[m] - lo[m]) * inv[m];
+      t = t < 0.0 ? 0.0 : (t > 2097151.0 ? 2097151.0 : t);
+      key |= spread21((uint64_t)t) << m;
+    }
+    keys[e] = key;
+    ids[e] = (int32_t)e;
+  }
+}
+
+__global__ void k_max_dof(int64_t n, const int32_t* __restrict__ cells, const int32_t* __restrict__ dofmap, int nd,
+                          int32_t* __restrict__ out)
+{
+  int32_t m = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    for (int k = 0; k < nd; ++k)
+      m = max(m, dofmap[(int64_t)cell * nd + k]);
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(out, m);
+}
+
+__global__ void k_permute_rows(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ cells,
+                               const int32_t* __restrict__ map, int width, int32_t* __restrict__ out)
+{
+  const int64_t total = n * width;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t slot = t / width;
+    const int k = (int)(t - slot * width);
+    const int64_t e = perm ? perm[slot] : slot;
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    out[t] = map[(int64_t)cell * width + k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// assembly kernel
+// ---------------------------------------------------------------------------------------------
+struct ChunkArgs
+{
+  const ChunkHdr* hdr;
+  const uint32_t* winfo;
+  const void* dest_addr;
+  const uint16_t* src;
+  const int32_t* perm;
+  const int32_t *xdm, *dm0, *dm1; // chunk-ordered copies or NULL
+  const uint32_t *bits0, *bits1;  // bit-packed Dirichlet markers or NULL
+  int same_bc;                    // rows and columns share dofmap and markers
+  int overwrite;
+};
+
+// ---- TMA bulk copy + mbarrier (one chunk's lists are contiguous: two bulk copies per CTA) -----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra DONE_%=;\n"
+               "bra WAIT_%=;\n"
+               "DONE_%=:\n"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+
+// shared-memory budget of the lists of one chunk (chunks over budget read their lists from global)
+template <int N2, int CB>
+struct ChunkSmem
+{
+  static constexpr int SRC_GROUPS = (N2 * CB / 32) * 3 / 2; // 32-entry groups of source entries
+  static constexpr int DEST_BYTES = (N2 * CB / 2) * 4;      // destination addresses
+  static constexpr int WINFO = N2 * CB / 32;                // groups of 32 destinations
+  static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)N2 * (CB + 1) + 2) + 127) / 128 * 128;
+  static constexpr size_t SRC_OFF = E_BYTES;
+  static constexpr size_t DEST_OFF = SRC_OFF + (size_t)SRC_GROUPS * 64;
+  static constexpr size_t WINFO_OFF = DEST_OFF + DEST_BYTES;
+  static constexpr size_t BAR_OFF = WINFO_OFF + (size_t)WINFO * 4;
+  static constexpr size_t TOTAL = BAR_OFF + 16;
+};
+
+template <class E, int CB, int THREADS, typename AddrT>
+__global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
+{
+  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, N2 = N * N, TPC = THREADS / CB;
+  static_assert(THREADS % CB == 0 && CB % 32 == 0, "a warp must work on one row residue");
+  using L = ChunkSmem<N2, CB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Es = reinterpret_cast<double*>(smem_raw);
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(smem_raw + L::SRC_OFF);
+  AddrT* s_dest = reinterpret_cast<AddrT*>(smem_raw + L::DEST_OFF);
+  uint32_t* s_winfo = reinterpret_cast<uint32_t*>(smem_raw + L::WINFO_OFF);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+
+  const int c = threadIdx.x % CB, sub = threadIdx.x / CB;
+  const int64_t q = blockIdx.x;
+  const int64_t slot = q * CB + c;
+
+  // ---- prefetch of the chunk's lists: TMA bulk copies land while phase 1 computes
+  const ChunkHdr h = ch.hdr[q];
+  const int n_dw = (h.n_dest + 31) >> 5;
+  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 32u * (uint32_t)sizeof(AddrT);
+  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
+  const uint16_t* g_src = ch.src + (h.src_base32 << 5);
+  const AddrT* g_dest = static_cast<const AddrT*>(ch.dest_addr) + h.dest_base;
+  const uint32_t* g_winfo = ch.winfo + (h.dest_base >> 5);
+  if (threadIdx.x == 0)
+  {
+    mbar_init(bar, 1);
+    Es[N2 * (CB + 1)] = 0.0; // the slot padded list entries point at
+  }
+  __syncthreads();
+  if (fits)
+  {
+    if (threadIdx.x == 0 && n_dw > 0)
+    {
+      mbar_expect_tx(bar, src_bytes + dest_bytes);
+      bulk_g2s(s_src, g_src, src_bytes, bar);
+      bulk_g2s(s_dest, g_dest, dest_bytes, bar);
+    }
+    for (int w = threadIdx.x; w < n_dw; w += THREADS)
+      s_winfo[w] = g_winfo[w];
+  }
+
+  // ---- phase 1: element matrices of the chunk -> shared memory (entry-major)
+  if (slot < a.n)
+  {
+    int64_t e = slot;
+    int32_t cell = (int32_t)slot;
+    if (E::WSIZE > 0 || !ch.xdm)
+    {
+      e = ch.perm ? ch.perm[slot] : slot;
+      cell = a.cells ? a.cells[e] : (int32_t)e;
+    }
+    uint32_t m0 = 0, m1 = 0; // bc marker bit per scalar row / column of Ae
+    if (ch.bits0 || ch.bits1)
+    {
+      int32_t d0[ND];
+      load_ints<ND>(ch.dm0 ? ch.dm0 + slot * ND : a.dofmap0 + (int64_t)cell * ND, d0);
+      if (ch.bits0)
+      {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+        {
+          const int64_t d = (int64_t)BS * d0[i / BS] + i % BS;
+          m0 |= ((__ldg(ch.bits0 + (d >> 5)) >> (d & 31)) & 1u) << i;
+        }
+      }
+      if (ch.same_bc)
+        m1 = m0;
+      else if (ch.bits1)
+      {
+        int32_t d1[ND];
+        load_ints<ND>(ch.dm1 ? ch.dm1 + slot * ND : a.dofmap1 + (int64_t)cell * ND, d1);
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+        {
+          const int64_t d = (int64_t)BS * d1[j / BS] + j % BS;
+          m1 |= ((__ldg(ch.bits1 + (d >> 5)) >> (d & 31)) & 1u) << j;
+        }
+      }
+    }
+    int32_t xd[NX];
+    load_ints<NX>(ch.xdm ? ch.xdm + slot * NX : a.x_dofmap + (int64_t)cell * NX, xd);
+    double xc[NX][3];
+    gather_coords<NX>(a.x, xd, xc);
+    double w[E::WSIZE > 0 ? E::WSIZE : 1];
+    load_w<E>(a, e, cell, w);
+    typename E::Geo g;
+    E::prepare(g, xc, w, a.constants, 0);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+    {
+      if (TPC > 1 && i % TPC != sub) // warp-uniform: the TPC threads of a cell share its rows
+        continue;
+      double row[N];
+      E::row(g, i, row);
+      const bool zr = (m0 >> i) & 1u;
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        Es[(i * N + j) * (CB + 1) + c] = (zr || ((m1 >> j) & 1u)) ? 0.0 : row[j];
+    }
+  }
+  __syncthreads();
+  if (fits && n_dw > 0)
+    mbar_wait(bar, 0);
+
+  // ---- phase 2: one thread per distinct destination
+  const int lane = threadIdx.x & 31;
+  const uint16_t* srcp = fits ? s_src : g_src;
+  const AddrT* destp = fits ? s_dest : g_dest;
+  const uint32_t* winfop = fits ? s_winfo : g_winfo;
+  for (int dw = threadIdx.x >> 5; dw < n_dw; dw += THREADS / 32)
+  {
+    const uint32_t info = winfop[dw];
+    const int m = (int)(info & 0xffu);
+    const uint16_t* p = srcp + ((size_t)(info >> 8) << 5) + lane;
+    const int t = (dw << 5) + lane;
+    double* dst = a.values + (int64_t)destp[t];
+    double old = 0.0;
+    const bool plain = t < h.n_complete;
+    if (plain && !ch.overwrite)
+      old = *dst; // issued before the list walk: its latency hides behind the shared-memory sums
+    double s0 = 0.0, s1 = 0.0;
+    int j = 0;
+    // staged entry idx = k * CB + c lives at k * (CB + 1) + c: the entries of one cell fall into
+    // different banks (neighbouring destinations draw on the same few cells)
+    for (; j + 4 <= m; j += 4)
+    {
+      const uint32_t i0 = p[(j + 0) << 5], i1 = p[(j + 1) << 5], i2 = p[(j + 2) << 5], i3 = p[(j + 3) << 5];
+      s0 += Es[i0 + i0 / CB];
+      s1 += Es[i1 + i1 / CB];
+      s0 += Es[i2 + i2 / CB];
+      s1 += Es[i3 + i3 / CB];
+    }
+    for (; j < m; ++j)
+    {
+      const uint32_t i0 = p[j << 5];
+      s0 += Es[i0 + i0 / CB];
+    }
+    const double sum = s0 + s1;
+    if (t < h.n_dest)
+    {
+      if (plain)
+        *dst = old + sum;
+      else
+        red_add(dst, sum);
+    }
+  }
+}
+
+// int8 markers -> one bit per dof (32 dofs per word, one warp ballot per word)
+__global__ void k_pack_marker_bits(int64_t n, const int8_t* __restrict__ markers, uint32_t* __restrict__ bits)
+{
+  const int64_t nw = (n + 31) / 32 * 32;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nw; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const unsigned b = __ballot_sync(0xffffffffu, t < n && markers[t] != 0);
+    if ((t & 31) == 0)
+      bits[t >> 5] = b;
+  }
+}
+
+template <class E>
+int launch_chunked_e(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
+{
+  constexpr int N2 = E::ND * E::BS * E::ND * E::BS;
+  constexpr int CB = chunk_cb(N2), THREADS = chunk_threads(N2);
+  static_assert(CB > 0, "element too large for the chunked path");
+  const bfx_chunks* c = P->chunks;
+  if (c->cb != CB || c->n2 != N2)
+    return fail(BFX_ERR_INVALID, "chunk plan (cb=%d, n2=%d) does not match the kernel (cb=%d, n2=%d)", c->cb, c->n2, CB,
+                N2);
+  if (a.n == 0)
+    return BFX_OK;
+  ChunkArgs ch;
+  ch.hdr = c->hdr;
+  ch.winfo = c->winfo;
+  ch.dest_addr = c->dest_addr;
+  ch.src = c->src;
+  ch.perm = c->perm;
+  ch.xdm = c->xdm;
+  ch.dm0 = c->dm0;
+  ch.dm1 = c->dm1 ? c->dm1 : c->dm0;
+  ch.overwrite = values_mode == BFX_VALUES_OVERWRITE;
+  ch.bits0 = ch.bits1 = nullptr;
+  ch.same_bc = a.bc0 && a.bc0 == a.bc1 && a.dofmap0 == a.dofmap1;
+  if (a.bc0)
+  {
+    k_pack_marker_bits<<<grid_for(c->n_dofs0, 256, 8), 256, 0, st>>>(c->n_dofs0, a.bc0, c->bits0);
+    ch.bits0 = c->bits0;
+  }
+  if (a.bc1 && !ch.same_bc)
+  {
+    k_pack_marker_bits<<<grid_for(c->n_dofs1, 256, 8), 256, 0, st>>>(c->n_dofs1, a.bc1, c->bits1);
+    ch.bits1 = c->bits1;
+  }
+  const size_t smem = ChunkSmem<N2, CB>::TOTAL;
+  if (c->addr_bytes == 4)
+  {
+    BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, CB, THREADS, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    k_matrix_chunked<E, CB, THREADS, uint32_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+  }
+  else
+  {
+    BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, CB, THREADS, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    k_matrix_chunked<E, CB, THREADS, uint64_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+  }
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+} // namespace
+
+namespace bfx
+{
+int chunked_supported(int kernel_id)
+{
+  switch (kernel_id)
+  {
+  case BFX_K_LAPLACE_P1_TRI_A:
+  case BFX_K_MASS_COEFF_P1_TRI_A:
+  case BFX_K_POISSON_P1_TET_A:
+  case BFX_K_POISSON_P2_TET_A: return 1;
+  default: return 0;
+  }
+}
+
+int launch_chunked(const bfx_asm* P, int kernel_id, const AsmArgs& a, int values_mode, cudaStream_t st)
+{
+  if (!P->chunks)
+    return fail(BFX_ERR_INVALID, "BFX_ASM_CHUNKED needs bfx_asm_build_chunks() on the plan first");
+  switch (kernel_id)
+  {
+  case BFX_K_LAPLACE_P1_TRI_A: return launch_chunked_e<el::LaplaceP1Tri>(P, a, values_mode, st);
+  case BFX_K_MASS_COEFF_P1_TRI_A: return launch_chunked_e<el::MassCoeffP1Tri>(P, a, values_mode, st);
+  case BFX_K_POISSON_P1_TET_A: return launch_chunked_e<el::PoissonP1Tet>(P, a, values_mode, st);
+  case BFX_K_POISSON_P2_TET_A: return launch_chunked_e<el::PoissonP2Tet>(P, a, values_mode, st);
+  default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d has no chunk-aggregated variant", kernel_id);
+  }
+}
+
+void free_chunks(bfx_chunks* c)
+{
+  if (!c)
+    return;
+  cudaFree(c->hdr);
+  cudaFree(c->winfo);
+  cudaFree(c->dest_addr);
+  cudaFree(c->src);
+  cudaFree(c->perm);
+  cudaFree(c->xdm);
+  cudaFree(c->dm0);
+  cudaFree(c->dm1);
+  cudaFree(c->bits0);
+  cudaFree(c->bits1);
+  delete c;
+}
+} // namespace bfx
+
+extern "C"
+{
+int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)
+{
+  BFX_REQUIRE(P && P->csr && P->pos, "bfx_asm_build_chunks: plan has no matrix / position map");
+  cudaStream_t st = S(stream);
+  const bfx_csr* csr = P->csr;
+  const int n2 = P->nd0 * csr->bs0 * P->nd1 * csr->bs1;
+  const int cb = chunk_cb(n2);
+  if (cb == 0 || P->ncells == 0)
+    return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d scalars are not supported", n2);
+  const int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
+  free_chunks(P->chunks);
+  P->chunks = nullptr;
+  bfx_chunks* c = new bfx_chunks();
+  c->cb = cb;
+  c->n2 = n2;
+  c->nchunks = (P->ncells + cb - 1) / cb;
+  int e = BFX_OK;
+  auto bail = [&](int status)
+  {
+    free_chunks(c);
+    return status;
+  };
+
+  // ---- locality ordering of the cell list
+  if (x_dev)
+  {
+    unsigned long long* bb = nullptr;
+    uint64_t *k0 = nullptr, *k1 = nullptr;
+    int32_t* i0 = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int64_t n = P->ncells;
+    if ((e = dev_alloc(&bb, 6)) || (e = dev_alloc(&k0, (size_t)n)) || (e = dev_alloc(&k1, (size_t)n))
+        || (e = dev_alloc(&i0, (size_t)n)) || (e = dev_alloc(&c->perm, (size_t)n)))
+      return bail(e);
+    const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
+    BFX_CUDA(cudaMemcpyAsync(bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_centroid_bbox<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb);
+    k_morton_keys<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb, k0, i0);
+    BFX_CHECK_LAUNCH();
+    BFX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, c->perm, n, 0, 63, st));
+    BFX_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    BFX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, i0, c->perm, n, 0, 63, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    cudaFree(bb);
+    cudaFree(k0);
+    cudaFree(k1);
+    cudaFree(i0);
+  }
+
+  // ---- index arrays in chunk order (phase 1 streams them)
+  if (c->perm || P->cells)
+  {
+    const int64_t n = P->ncells;
+    if ((e = dev_alloc(&c->xdm, (size_t)n * P->nx)) || (e = dev_alloc(&c->dm0, (size_t)n * P->nd0)))
+      return bail(e);
+    k_permute_rows<<<grid_for(n * P->nx, 256, 16), 256, 0, st>>>(n, c->perm, P->cells, P->x_dofmap, P->nx, c->xdm);
+    k_permute_rows<<<grid_for(n * P->nd0, 256, 16), 256, 0, st>>>(n, c->perm, P->cells, P->dofmap0, P->nd0, c->dm0);
+    if (P->dofmap1 && P->dofmap1 != P->dofmap0)
+    {
+      if ((e = dev_alloc(&c->dm1, (size_t)n * P->nd1)))
+        return bail(e);
+      k_permute_rows<<<grid_for(n * P->nd1, 256, 16), 256, 0, st>>>(n, c->perm, P->cells, P->dofmap1, P->nd1, c->dm1);
+    }
+    BFX_CHECK_LAUNCH();
+  }
+
+  // ---- scratch of the bit-packed Dirichlet markers (sized by the largest dof the cells reference)
+  {
+    int32_t* d_max = nullptr;
+    int32_t h_max[2] = {0, 0};
+    if ((e = dev_alloc(&d_max, 2)))
+      return bail(e);
+    BFX_CUDA(cudaMemsetAsync(d_max, 0, 2 * sizeof(int32_t), st));
+    const int32_t* dm1p = P->dofmap1 ? P->dofmap1 : P->dofmap0;
+    k_max_dof<<<grid_for(P->ncells, 256, 8), 256, 0, st>>>(P->ncells, P->cells, P->dofmap0, P->nd0, d_max);
+    k_max_dof<<<grid_for(P->ncells, 256, 8), 256, 0, st>>>(P->ncells, P->cells, dm1p, P->nd1, d_max + 1);
+    BFX_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_max);
+    c->n_dofs0 = ((int64_t)h_max[0] + 1) * csr->bs0;
+    c->n_dofs1 = ((int64_t)h_max[1] + 1) * csr->bs1;
+    if ((e = dev_alloc(&c->bits0, (size_t)(c->n_dofs0 + 31) / 32 + 1))
+        || (e = dev_alloc(&c->bits1, (size_t)(c->n_dofs1 + 31) / 32 + 1)))
+      return bail(e);
+  }
+
+  // ---- contributions per block entry
+  int32_t* total = nullptr;
+  if ((e = dev_alloc(&total, (size_t)csr->nnz)))
+    return bail(e);
+  BFX_CUDA(cudaMemsetAsync(total, 0, sizeof(int32_t) * (size_t)csr->nnz, st));
+  k_count_contrib<<<grid_for(P->ncells * P->nd0, 256, 16), 256, 0, st>>>(P->ncells, P->cells, P->dofmap0, P->nd0, P->nd1,
+                                                                         csr->row_ptr, P->pos, P->pos_stride,
+                                                                         P->pos_bytes, total);
+  BFX_CHECK_LAUNCH();
+
+  // ---- pass A: sizes; scans; pass B: write
+  const uint64_t nvals = (uint64_t)csr->nnz * csr->bs0 * csr->bs1;
+  int addr_bits = 1;
+  while (addr_bits < 47 && ((1ull << addr_bits) - 1) < nvals)
+    ++addr_bits;
+  c->addr_bytes = nvals < 0xffffffffull ? 4 : 8;
+  int64_t *ndw = nullptr, *nsrc = nullptr;
+  if ((e = dev_alloc(&ndw, (size_t)c->nchunks + 1)) || (e = dev_alloc(&nsrc, (size_t)c->nchunks + 1)))
+    return bail(e);
+  BFX_CUDA(cudaMemsetAsync(ndw, 0, sizeof(int64_t) * (size_t)(c->nchunks + 1), st));
+  BFX_CUDA(cudaMemsetAsync(nsrc, 0, sizeof(int64_t) * (size_t)(c->nchunks + 1), st));
+  ChunkBuildArgs p;
+  memset(&p, 0, sizeof(p));
+  p.n = P->ncells;
+  p.cb = cb;
+  p.nd0 = P->nd0, p.nd1 = P->nd1, p.bs0 = csr->bs0, p.bs1 = csr->bs1, p.n2 = n2;
+  p.perm = c->perm;
+  p.cells = P->cells;
+  p.dofmap0 = P->dofmap0;
+  p.row_ptr = csr->row_ptr;
+  p.pos = P->pos;
+  p.pos_stride = P->pos_stride;
+  p.pos_bytes = P->pos_bytes;
+  p.total = total;
+  p.addr_bits = addr_bits;
+  p.o_ndw = ndw;
+  p.o_nsrc32 = nsrc;
+  p.err = csr->err_flag;
+  if ((e = run_plan_pass_items(items, false, p, c->nchunks, st)))
+    return bail(e);
+  {
+    void* tmp = nullptr;
+    size_t bytes = 0;
+    BFX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, ndw, ndw, c->nchunks + 1, st));
+    BFX_CUDA(cudaMalloc(&tmp, bytes));
+    BFX_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, ndw, ndw, c->nchunks + 1, st));
+    BFX_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, nsrc, nsrc, c->nchunks + 1, st));
+    int64_t tot[2];
+    BFX_CUDA(cudaMemcpyAsync(&tot[0], ndw + c->nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaMemcpyAsync(&tot[1], nsrc + c->nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    int herr = 0;
+    BFX_CUDA(cudaMemcpyAsync(&herr, csr->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    if (herr)
+    {
+      BFX_CUDA(cudaMemsetAsync(csr->err_flag, 0, sizeof(int), st));
+      cudaFree(total);
+      cudaFree(ndw);
+      cudaFree(nsrc);
+      return bail(fail(BFX_ERR_UNSUPPORTED, "chunk plan: a CSR entry receives more than %d contributions from one chunk",
+                       MAX_LIST));
+    }
+    c->n_dest_pad = tot[0] * 32;
+    c->n_src32 = tot[1];
+  }
+  if ((e = dev_alloc(&c->hdr, (size_t)c->nchunks)) || (e = dev_alloc(&c->winfo, (size_t)(c->n_dest_pad / 32 + 1)))
+      || (e = dev_alloc(&c->src, (size_t)c->n_src32 * 32 + 32)))
+    return bail(e);
+  {
+    void* da = nullptr;
+    BFX_CUDA(cudaMalloc(&da, (size_t)(c->n_dest_pad + 32) * c->addr_bytes));
+    c->dest_addr = da;
+  }
+  p.dest_base32 = ndw;
+  p.src_base32 = nsrc;
+  p.hdr = c->hdr;
+  p.winfo = c->winfo;
+  p.dest_addr = c->dest_addr;
+  p.addr_bytes = c->addr_bytes;
+  p.src = c->src;
+  if ((e = run_plan_pass_items(items, true, p, c->nchunks, st)))
+    return bail(e);
+  BFX_CUDA(cudaStreamSynchronize(st));
+  cudaFree(total);
+  cudaFree(ndw);
+  cudaFree(nsrc);
+  P->chunks = c;
+  return BFX_OK;
+}
+
+int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
+                        int64_t* plan_bytes)
+{
+  BFX_REQUIRE(P && P->chunks, "bfx_asm_chunk_stats: no chunk plan");
+  const bfx_chunks* c = P->chunks;
+  if (nchunks)
+    *nchunks = c->nchunks;
+  if (n_dest)
+    *n_dest = c->n_dest_pad;
+  if (n_src_entries)
+    *n_src_entries = c->n_src32 * 32;
+  if (plan_bytes)
+    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4 + c->n_dest_pad * c->addr_bytes
+                  + c->n_src32 * 64 + (c->perm ? P->ncells * 4 : 0)
+                  + (c->xdm ? P->ncells * 4 * (int64_t)(P->nx + P->nd0 + (c->dm1 ? P->nd1 : 0)) : 0);
+  return BFX_OK;
+}
+}

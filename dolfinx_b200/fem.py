@@ -393,6 +393,41 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
     return h
 
 
+def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
+    """Assembly strategy of a cell integral: the caller's choice, else the chunk-aggregated kernel when
+    the element has one (the plan's chunk lists are built once, on first use), else fp64 REDs."""
+    from . import _lib
+
+    if strategy is not None and strategy != _lib.ASM_CHUNKED:
+        return strategy
+    key = ("chunks", plan.value)
+    if key not in form._plans:
+        ok = False
+        if integ.kernel in _lib.CHUNKED_KERNELS:
+            st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), _lib.current_stream())
+            if st == _lib.OK:
+                ok = True
+            elif st != _lib.ERR_UNSUPPORTED:
+                _lib.check(st)
+        form._plans[key] = ok
+    if form._plans[key]:
+        return _lib.ASM_CHUNKED
+    if strategy == _lib.ASM_CHUNKED:
+        raise NotImplementedError("no chunk-aggregated variant for this kernel / mesh")
+    return _lib.ASM_ATOMIC
+
+
+def chunk_stats(form: Form, A: la.MatrixCSR, itype=None, ident=0):
+    """(chunks, destinations, source-list entries, plan bytes) of the chunk plan of a cell integral."""
+    from . import _lib
+
+    integ = form.integral(IntegralType.cell if itype is None else itype, ident)
+    plan = _asm_plan(form, integ, IntegralType.cell, A)
+    out = [C.c_int64() for _ in range(4)]
+    _lib.check(_lib.lib.bfx_asm_chunk_stats(plan, *[C.byref(o) for o in out]))
+    return tuple(int(o.value) for o in out)
+
+
 def _boundary_interior_cells(form: Form, integ: IntegralData):
     """Split a cell domain into cells that touch a ghost row (their contributions must travel to the
     owner, la/MatrixCSR.h:399-468) and interior cells (SURVEY.md §8e overlap plan)."""
@@ -444,15 +479,15 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
     assert a.rank == 2
     V0, V1 = a.function_spaces
     bc0 = _bc_markers(V0, bcs)
-    bc1 = _bc_markers(V1, bcs)
+    bc1 = bc0 if V1 is V0 else _bc_markers(V1, bcs)  # same space: one marker array (assembler.h:558-577)
     consts = pack_constants(a) if constants is None else np.asarray(constants, dtype=np.float64)
     carr, nc = _lib.constants_array(consts)
-    strat = _lib.ASM_ATOMIC if strategy is None else strategy
     try:
         for (itype, ident), integ in a._integrals.items():
             plan = _asm_plan(a, integ, itype, A)
             cf = _coeffs_for(a, integ, None if coeffs is None else coeffs[(itype, ident)])
             if itype == IntegralType.cell:
+                strat = _matrix_strategy(a, integ, plan, strategy)
                 mode = _lib.VALUES_OVERWRITE if A._is_zero else _lib.VALUES_ADD
                 _lib.check(_lib.lib.bfx_assemble_matrix_cells(
                     plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
@@ -485,10 +520,10 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
         A.scatter_reverse()
         return A
     V0, V1 = a.function_spaces
-    bc0, bc1 = _bc_markers(V0, bcs), _bc_markers(V1, bcs)
+    bc0 = _bc_markers(V0, bcs)
+    bc1 = bc0 if V1 is V0 else _bc_markers(V1, bcs)
     consts = pack_constants(a) if constants is None else np.asarray(constants, dtype=np.float64)
     carr, nc = _lib.constants_array(consts)
-    strat = _lib.ASM_ATOMIC if strategy is None else strategy
     items = list(a._integrals.items())
     if any(itype != IntegralType.cell for (itype, _), _ in items):
         raise NotImplementedError("overlapped assembly handles cell integrals")
@@ -499,6 +534,7 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
             if cells.numel() == 0:
                 continue
             plan = _asm_plan(a, integ, itype, A, subset=(("bnd", "int")[tag_index], cells))
+            strat = _matrix_strategy(a, integ, plan, strategy)
             cf = _coeffs_for(a, integ, None)
             _lib.check(_lib.lib.bfx_assemble_matrix_cells(
                 plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),

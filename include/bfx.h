@@ -166,7 +166,9 @@ extern "C"
   enum
   {
     BFX_ASM_ATOMIC = 0, /* cell-parallel, fp64 RED atomics into CSR through the cell->nnz map */
-    BFX_ASM_GATHER = 1  /* row-parallel, each CSR value written once, CPU summation order */
+    BFX_ASM_GATHER = 1, /* reserved (row-parallel gather); returns BFX_ERR_UNSUPPORTED */
+    BFX_ASM_CHUNKED = 2 /* chunk-aggregated: element matrices staged in shared memory, one update per distinct
+                           CSR entry and chunk; needs bfx_asm_build_chunks() */
   };
   enum
   {
@@ -186,6 +188,15 @@ extern "C"
                      int64_t ncells_all, const int32_t* cells_any, int64_t ncells, int32_t n_rows_all, int borrow,
                      bfx_stream_t stream);
   int bfx_asm_destroy(bfx_asm_t* plan);
+  /* Plan of the chunk-aggregated strategy (BFX_ASM_CHUNKED) for the plan's cell list and MatrixCSR: cuts the
+   * cell list into chunks, and for every chunk precomputes the distinct CSR destinations and the source
+   * lists that sum the staged element matrices into them (the device-side replacement of the per-entry
+   * lower_bound + "+=" of insert_csr, la/matrix_csr_impl.h:67-109).  x_dev (optional geometry, (N,3)) orders
+   * the cells along a Morton curve of their centroids so that a chunk is a compact patch; NULL keeps the
+   * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
+  int bfx_asm_build_chunks(bfx_asm_t* plan, const double* x_dev, bfx_stream_t stream);
+  int bfx_asm_chunk_stats(const bfx_asm_t* plan, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
+                          int64_t* plan_bytes);
 
   /* impl::assemble_cells_matrix<false> — fem/assemble_matrix_impl.h:92-200 (+ bc row/col zeroing :161-196).
    * bc0/bc1: int8 markers of length bs*(owned+ghost) or NULL.  constants: host array. */

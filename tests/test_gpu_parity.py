@@ -38,14 +38,14 @@ def make_space(bfx, p):
     return msh, V
 
 
-def assemble_A(bfx, V, kernel, constants=(), coefficients=(), active=(), bcs=()):
+def assemble_A(bfx, V, kernel, constants=(), coefficients=(), active=(), bcs=(), strategy=None):
     fem, la = bfx.fem, bfx.la
     a = fem.Form([V, V], {fem.IntegralType.cell: [(0, kernel, None, list(active))]},
                  coefficients=coefficients, constants=[fem.Constant(c) for c in constants])
     sp = fem.create_sparsity_pattern(a)
     sp.finalize()
     A = la.MatrixCSR(sp)
-    fem.assemble_matrix(A, a, bcs=bcs)
+    fem.assemble_matrix(A, a, bcs=bcs, strategy=strategy)
     return a, sp, A
 
 
@@ -68,6 +68,39 @@ def test_poisson_p1_matrix(bfx, oracle, n, numbering):
     check_matrix(A, pat, ref)
     assert np.array_equal(sp.off_diagonal_offsets, pat.off_diagonal_offsets)
     assert A.squared_norm() == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
+
+
+@pytest.mark.parametrize("case", ["p1_lex", "p1_random", "p2", "tri"])
+def test_chunked_and_atomic_strategies(bfx, oracle, case):
+    """Both scatter-add strategies against the oracle on meshes spanning many chunks: the
+    chunk-aggregated kernel (default; complete destinations by plain update, chunk-boundary ones by
+    RED) and the plain fp64-RED kernel; then re-assembly without zeroing (values += , the
+    "does not zero" contract of fem/assembler.h:497-498, test_assembler.py:157-165)."""
+    fem, K = bfx.fem, bfx.lib
+    if case.startswith("p1"):
+        p = P.tet_p1(13, numbering="lex" if case == "p1_lex" else "random", seed=5)
+        kern, okern, consts = K.K_POISSON_P1_TET_A, oracle.K_POISSON_P1_TET_A, [2.0]
+    elif case == "p2":
+        p = P.tet_p2(6)
+        kern, okern, consts = K.K_POISSON_P2_TET_A, oracle.K_POISSON_P2_TET_A, [2.0]
+    else:
+        p = P.tri_p1(40, 37)
+        kern, okern, consts = K.K_LAPLACE_P1_TRI_A, oracle.K_LAPLACE_P1_TRI_A, []
+    msh, V = make_space(bfx, p)
+    pat, ref = P.oracle_assemble_matrix(oracle, p, okern, constants=np.array(consts))
+    for strategy in (K.ASM_CHUNKED, K.ASM_ATOMIC):
+        a, sp, A = assemble_A(bfx, V, kern, constants=consts, strategy=strategy)
+        check_matrix(A, pat, ref)
+        fem.assemble_matrix(A, a, strategy=strategy)  # A is not zero any more: add mode
+        assert np.linalg.norm(A.data.cpu().numpy() - 2 * ref) <= TOL * np.linalg.norm(2 * ref)
+        if strategy == K.ASM_CHUNKED:
+            nchunks, ndest, nsrc, nbytes = fem.chunk_stats(a, A)
+            assert nchunks > 4 and ndest >= len(pat.edges) and nsrc >= ref.size
+    # default strategy = chunk-aggregated for the P1 kernels
+    a, sp, A = assemble_A(bfx, V, kern, constants=consts)
+    if kern in K.CHUNKED_KERNELS:
+        assert fem.chunk_stats(a, A)[0] > 4
+    check_matrix(A, pat, ref)
 
 
 def test_poisson_p1_32_config1(bfx, oracle):
