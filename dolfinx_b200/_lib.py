@@ -43,7 +43,8 @@ K_LOAD_Q1_HEX_L = 11
 K_FACET_LOAD_P1_TET_L = 12
 K_FACET_MASS_P1_TET_A = 13
 
-ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED = 0, 1, 2
+ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
+ROWGATHER_KERNELS = frozenset({10})
 ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
 # where it beats the fp64-RED kernel on B200; P2 (id 8) has the variant too but its 100-entry element
@@ -101,6 +102,7 @@ _SIGS = {
     "bfx_asm_create": ([pvp, vp, vp, ci, vp, ci, vp, ci, i64, vp, i64, i32, ci, vp], ci),
     "bfx_asm_destroy": ([vp], ci),
     "bfx_asm_build_chunks": ([vp, vp, vp], ci),
+    "bfx_asm_build_rowgather": ([vp, vp], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),

@@ -460,10 +460,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 2) k_elasticity_q1_sym(const AsmAr
     S.pi[threadIdx.x] = (unsigned char)i;
     S.pj[threadIdx.x] = (unsigned char)(i + rem);
   }
-  for (int64_t e0 = (int64_t)blockIdx.x * Q2_CELLS; e0 < a.n; e0 += (int64_t)gridDim.x * Q2_CELLS)
+  const int64_t n_ent = a.n_dev ? min(a.n, (int64_t)*a.n_dev) : a.n;
+  for (int64_t e0 = (int64_t)blockIdx.x * Q2_CELLS; e0 < n_ent; e0 += (int64_t)gridDim.x * Q2_CELLS)
   {
     const int64_t e = e0 + cl;
-    const bool active = e < a.n;
+    const bool active = e < n_ent;
     int32_t cell = 0;
     if (active)
       cell = a.cells ? a.cells[e] : (int32_t)e;
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 2) k_elasticity_q1_sym(const AsmAr
         }
     }
     __syncthreads();
-    const int ncell = (int)min((int64_t)Q2_CELLS, a.n - e0);
+    const int ncell = (int)min((int64_t)Q2_CELLS, n_ent - e0);
 #pragma unroll 4
     for (int it = 0; it < (Q2_CELLS * 576) / Q2_THREADS; ++it)
     {
@@ -773,7 +774,8 @@ int launch_q1(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
                                     (int)sizeof(Q2Smem)));
       configured = true;
     }
-    const unsigned grid = grid_for((a.n + Q2_CELLS - 1) / Q2_CELLS, 1, 0);
+    // a device-side count means "few cells" (the non-affine remainder of the row-gather path): small grid
+    const unsigned grid = grid_for((a.n + Q2_CELLS - 1) / Q2_CELLS, 1, a.n_dev ? 2 : 0);
     if (P->pos_bytes == 2 && a.pos)
       k_elasticity_q1_sym<uint16_t><<<grid, Q2_THREADS, sizeof(Q2Smem), st>>>(a);
     else
@@ -895,6 +897,15 @@ int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, cons
   return BFX_OK;
 }
 
+} // namespace
+
+namespace bfx
+{
+int launch_q1_red(const bfx_asm* P, const AsmArgs& a, cudaStream_t st) { return launch_q1<0>(P, a, st); }
+} // namespace bfx
+
+namespace
+{
 int check_err(const bfx_asm* P, cudaStream_t st, const char* what)
 {
   int h = 0;
@@ -1016,6 +1027,7 @@ int bfx_asm_destroy(bfx_asm_t* P)
   }
   cudaFree(P->pos);
   free_chunks(P->chunks);
+  free_rowgather(P->rowgather);
   cudaFree(P->h_x);
   cudaFree(P->h_coeff);
   cudaFree(P->h_bc0);
@@ -1035,7 +1047,7 @@ int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x
     return e;
   BFX_REQUIRE(values, "bfx_assemble_matrix_cells: null values");
   BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
-  if (strategy != BFX_ASM_ATOMIC && strategy != BFX_ASM_CHUNKED)
+  if (strategy != BFX_ASM_ATOMIC && strategy != BFX_ASM_CHUNKED && strategy != BFX_ASM_ROWGATHER)
     return fail(BFX_ERR_UNSUPPORTED, "assembly strategy %d not available", strategy);
   a.cells = P->cells;
   a.n = P->ncells;
@@ -1045,6 +1057,12 @@ int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x
   a.pos = P->pos;
   if (strategy == BFX_ASM_CHUNKED)
     return launch_chunked(P, kernel_id, a, values_mode, S(stream));
+  if (strategy == BFX_ASM_ROWGATHER)
+  {
+    if (kernel_id != BFX_K_ELASTICITY_Q1_HEX_A)
+      return fail(BFX_ERR_UNSUPPORTED, "kernel id %d has no row-gather variant", kernel_id);
+    return launch_rowgather_q1(P, a, values_mode, S(stream));
+  }
   return dispatch_matrix<0>(P, kernel_id, a, S(stream));
 }
 

@@ -23,6 +23,7 @@ struct AsmArgs
   const int32_t* cells;    // cell list or NULL (= identity)
   const int32_t* entities; // (cell, local_facet) pairs or NULL
   int64_t n;               // number of cells / entities
+  const unsigned long long* n_dev; // optional device-side count (<= n) produced by an earlier kernel
   const double* x;         // geometry, (N,3) row-major
   const int8_t *bc0, *bc1; // Dirichlet markers or NULL
   CoefArgs coef;
@@ -73,6 +74,16 @@ struct bfx_chunks
   int64_t n_dofs0 = 0, n_dofs1 = 0; // scalar dofs indexed through dofmap0 / dofmap1
 };
 
+// Row-gather plan of the Q1 elasticity kernel (rowgather.cu)
+struct bfx_rowgather
+{
+  int64_t* tptr = nullptr;   // transposed dofmap: row -> incident (entity, local node) entries
+  uint32_t* tent = nullptr;  // (entity << 3) | local node
+  double* rec = nullptr;     // per-call cell records (K, |det J|)
+  int32_t* na_cells = nullptr;           // per-call list of cells that are not parallelepipeds
+  unsigned long long* na_count = nullptr;
+};
+
 struct bfx_asm
 {
   const bfx_csr* csr = nullptr;
@@ -89,6 +100,7 @@ struct bfx_asm
   int8_t *h_bc0 = nullptr, *h_bc1 = nullptr;
   int64_t h_x_n = 0, h_coeff_n = 0, h_bc_n = 0;
   bfx_chunks* chunks = nullptr;
+  bfx_rowgather* rowgather = nullptr;
 };
 
 namespace bfx
@@ -97,4 +109,9 @@ namespace bfx
 int chunked_supported(int kernel_id);
 int launch_chunked(const bfx_asm* P, int kernel_id, const AsmArgs& a, int values_mode, cudaStream_t st);
 void free_chunks(bfx_chunks* c);
+// rowgather.cu
+int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st);
+void free_rowgather(bfx_rowgather* g);
+// assemble.cu: the cell-parallel fp64-RED Q1 elasticity kernel (used for non-affine cells by the row-gather path)
+int launch_q1_red(const bfx_asm* P, const AsmArgs& a, cudaStream_t st);
 } // namespace bfx

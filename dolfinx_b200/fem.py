@@ -394,26 +394,32 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
 
 
 def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
-    """Assembly strategy of a cell integral: the caller's choice, else the chunk-aggregated kernel when
-    the element has one (the plan's chunk lists are built once, on first use), else fp64 REDs."""
+    """Assembly strategy of a cell integral: the caller's choice, else the aggregated kernel of the
+    element where it has one (chunk-aggregated for the P1 kernels, row-gather for Q1 elasticity; the
+    plan's lists are built once, on first use), else fp64 REDs."""
     from . import _lib
 
-    if strategy is not None and strategy != _lib.ASM_CHUNKED:
+    if strategy == _lib.ASM_ATOMIC:
         return strategy
-    key = ("chunks", plan.value)
+    want = strategy
+    if want is None:
+        want = (_lib.ASM_CHUNKED if integ.kernel in _lib.CHUNKED_KERNELS
+                else _lib.ASM_ROWGATHER if integ.kernel in _lib.ROWGATHER_KERNELS else _lib.ASM_ATOMIC)
+    if want == _lib.ASM_ATOMIC:
+        return want
+    key = ("aggplan", plan.value, want)
     if key not in form._plans:
-        ok = False
-        if integ.kernel in _lib.CHUNKED_KERNELS:
+        if want == _lib.ASM_CHUNKED:
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), _lib.current_stream())
-            if st == _lib.OK:
-                ok = True
-            elif st != _lib.ERR_UNSUPPORTED:
-                _lib.check(st)
-        form._plans[key] = ok
+        else:
+            st = _lib.lib.bfx_asm_build_rowgather(plan, _lib.current_stream())
+        if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):
+            _lib.check(st)
+        form._plans[key] = st == _lib.OK
     if form._plans[key]:
-        return _lib.ASM_CHUNKED
-    if strategy == _lib.ASM_CHUNKED:
-        raise NotImplementedError("no chunk-aggregated variant for this kernel / mesh")
+        return want
+    if strategy is not None:
+        raise NotImplementedError("the requested assembly strategy is not available for this kernel / mesh")
     return _lib.ASM_ATOMIC
 
 
@@ -489,9 +495,11 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
             if itype == IntegralType.cell:
                 strat = _matrix_strategy(a, integ, plan, strategy)
                 mode = _lib.VALUES_OVERWRITE if A._is_zero else _lib.VALUES_ADD
+                # a kernel that writes every value once absorbs a pending A.set_value(0)
+                vals = A._take_zero_fill() if (A._is_zero and strat == _lib.ASM_ROWGATHER) else A.data
                 _lib.check(_lib.lib.bfx_assemble_matrix_cells(
                     plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
-                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(), strat, mode,
+                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, vals.data_ptr(), strat, mode,
                     _lib.current_stream()))
             elif itype == IntegralType.exterior_facet:
                 ent, n = _entities_dev(a, integ, itype)

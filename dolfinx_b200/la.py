@@ -484,8 +484,9 @@ class MatrixCSR:
         else:
             self._csr = pattern._csr
         self._nnz = int(_lib.lib.bfx_csr_nnz(self._csr))
-        self.data = torch.zeros(self._nnz * self._bs[0] * self._bs[1], dtype=torch.float64, device=_device())
+        self._data = torch.zeros(self._nnz * self._bs[0] * self._bs[1], dtype=torch.float64, device=_device())
         self._is_zero = True
+        self._zero_pending = False  # set_value(0) not yet written to memory (see set_value)
         self._scatter_plan = None
         self._asm_plans = {}
         self._build_ghost_plan()
@@ -545,10 +546,32 @@ class MatrixCSR:
         return self._index_maps[0].size_local + self._index_maps[0].num_ghosts
 
     # -- value manipulation ------------------------------------------------------------------------
+    @property
+    def data(self):
+        """The value array (python/dolfinx/la/__init__.py ``MatrixCSR.data``)."""
+        if self._zero_pending:
+            self._data.zero_()
+            self._zero_pending = False
+        return self._data
+
     def set_value(self, x: float):
-        """MatrixCSR::set(value) (la/MatrixCSR.h:239-241)."""
-        self.data.fill_(x)
+        """MatrixCSR::set(value) (la/MatrixCSR.h:239-241).
+
+        ``set_value(0)`` is recorded and written to memory by the first reader of ``data`` - unless an
+        assembly kernel that writes every value exactly once (BFX_ASM_ROWGATHER with
+        BFX_VALUES_OVERWRITE) gets there first and fuses the zero-fill (``_take_zero_fill``)."""
+        if x == 0.0:
+            self._zero_pending = True
+        else:
+            self._zero_pending = False
+            self._data.fill_(x)
         self._is_zero = x == 0.0
+
+    def _take_zero_fill(self):
+        """For a kernel that overwrites EVERY value: returns the raw array and drops the pending zero-fill."""
+        assert self._is_zero
+        self._zero_pending = False
+        return self._data
 
     def _insert(self, x, rows, cols, bs, op):
         from . import _lib

@@ -167,8 +167,11 @@ extern "C"
   {
     BFX_ASM_ATOMIC = 0, /* cell-parallel, fp64 RED atomics into CSR through the cell->nnz map */
     BFX_ASM_GATHER = 1, /* reserved (row-parallel gather); returns BFX_ERR_UNSUPPORTED */
-    BFX_ASM_CHUNKED = 2 /* chunk-aggregated: element matrices staged in shared memory, one update per distinct
-                           CSR entry and chunk; needs bfx_asm_build_chunks() */
+    BFX_ASM_CHUNKED = 2, /* chunk-aggregated: element matrices staged in shared memory, one update per distinct
+                            CSR entry and chunk; needs bfx_asm_build_chunks() */
+    BFX_ASM_ROWGATHER = 3 /* row-parallel gather with per-(row, cell) recomputation, every CSR value written once by
+                             plain stores, no atomics, bitwise reproducible; BFX_K_ELASTICITY_Q1_HEX_A only;
+                             needs bfx_asm_build_rowgather() */
   };
   enum
   {
@@ -195,6 +198,10 @@ extern "C"
    * the cells along a Morton curve of their centroids so that a chunk is a compact patch; NULL keeps the
    * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
   int bfx_asm_build_chunks(bfx_asm_t* plan, const double* x_dev, bfx_stream_t stream);
+  /* Plan of the row-gather strategy (BFX_ASM_ROWGATHER): the transposed dofmap (row -> incident (cell, local
+   * node) pairs in ascending cell order, cf. fem::transpose_dofmap, fem/DofMap.h:62-64) and the per-call scratch of
+   * the cell records.  BFX_ERR_UNSUPPORTED unless the plan is Q1 hexahedra x block size 3 with one dofmap. */
+  int bfx_asm_build_rowgather(bfx_asm_t* plan, bfx_stream_t stream);
   int bfx_asm_chunk_stats(const bfx_asm_t* plan, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
                           int64_t* plan_bytes);
 

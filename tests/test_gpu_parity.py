@@ -208,6 +208,32 @@ def test_elasticity_q1_matrix_and_vector(bfx, oracle, skew):
     assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
 
 
+@pytest.mark.parametrize("n,skew,perturb", [(7, False, 0.0), (6, True, 0.0), (5, False, 0.3)])
+def test_q1_rowgather_and_atomic_strategies(bfx, oracle, n, skew, perturb):
+    """The row-gather elasticity kernel (default for Q1: every CSR value written once, no atomics) and
+    the cell-parallel fp64-RED kernel against the oracle: affine, skewed (parallelepiped) and partly
+    non-affine meshes (the non-affine remainder goes through the RED kernel), several 32-row tiles;
+    re-assembly adds; the row-gather result is bitwise reproducible."""
+    fem, K = bfx.fem, bfx.lib
+    p = P.hex_q1(n, numbering="random", seed=n, skew=skew, perturb=perturb)
+    if perturb:
+        keep = p.x[:, 2] < 0.5
+        p.x[keep] = P.hex_q1(n, numbering="random", seed=n).x[keep]
+    msh, V = make_space(bfx, p)
+    consts = [[1.0, 1.5]]
+    okern = oracle.K_ELASTICITY_Q1_HEX_A_G2 if perturb else oracle.K_ELASTICITY_Q1_HEX_A
+    pat, ref = P.oracle_assemble_matrix(oracle, p, okern, constants=np.array([1.0, 1.5]))
+    runs = []
+    for strategy in (K.ASM_ROWGATHER, K.ASM_ROWGATHER, K.ASM_ATOMIC):
+        a, sp, A = assemble_A(bfx, V, K.K_ELASTICITY_Q1_HEX_A, constants=consts, strategy=strategy)
+        check_matrix(A, pat, ref, bs2=9)
+        runs.append(A.data.cpu().numpy().copy())
+        fem.assemble_matrix(A, a, strategy=strategy)  # add mode
+        assert np.linalg.norm(A.data.cpu().numpy() - 2 * ref) <= TOL * np.linalg.norm(2 * ref)
+    if not perturb:
+        assert np.array_equal(runs[0], runs[1]), "row-gather assembly must be bitwise reproducible"
+
+
 def test_elasticity_q1_nonaffine_cells(bfx, oracle):
     """General trilinear hexahedra take the 2x2x2 Gauss path of the CUDA kernel: compare with the oracle's
     2x2x2 variant to 1e-12 and with its 3x3x3 rule to quadrature accuracy; a mesh mixing affine and
