@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--strategy", default="auto", choices=["auto", "atomic", "chunked", "rowgather"],
                     help="scatter-add strategy of the matrix kernel; auto = the aggregated kernel of the element")
     ap.add_argument("--spmv-reps", type=int, default=100)
+    ap.add_argument("--spmv-variant", type=int, default=-1, help="bs=1 SpMV kernel (0 stream, 1 rows, 2 TMA rows); -1 = timed selection")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -432,6 +433,8 @@ def main():
     fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)
     fem.set_diagonal(A, V, [bc], 1.0)
     A.scatter_reverse()
+    if args.spmv_variant >= 0:
+        K.check(K.lib.bfx_csr_set_spmv_variant(A._csr, args.spmv_variant))
     x = la.Vector(A.index_map(1), pb["bs"])
     y = la.Vector(A.index_map(0), pb["bs"])
     g = torch.Generator(device=device)

@@ -98,6 +98,7 @@ _SIGS = {
     "bfx_csr_set_diagonal": ([vp, vp, vp, i64, f64, vp], ci),
     "bfx_csr_squared_norm": ([vp, vp, C.POINTER(f64), vp], ci),
     "bfx_spmv": ([vp, vp, vp, vp, ci, vp], ci),
+    "bfx_csr_set_spmv_variant": ([vp, ci], ci),
     "bfx_spmvT": ([vp, vp, vp, vp, ci, vp], ci),
     "bfx_asm_create": ([pvp, vp, vp, ci, vp, ci, vp, ci, i64, vp, i64, i32, ci, vp], ci),
     "bfx_asm_destroy": ([vp], ci),

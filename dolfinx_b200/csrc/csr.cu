@@ -259,6 +259,210 @@ __global__ void __launch_bounds__(R)
     y[my_row] += sum;
 }
 
+// bs = 1, TMA-pipelined row-per-thread variant.  Same arithmetic as k_spmv_rows, but the contiguous
+// (cols, values) range of a tile of R rows reaches shared memory through TMA bulk copies
+// (cp.async.bulk + mbarrier, SASS UBLKCP) issued by one thread, two stages deep: while the CTA walks
+// the rows of one tile the next tile is already in flight, no registers or LSU slots are spent on the
+// streaming part, and persistent CTAs (grid = resident CTAs) keep the pipeline full across tiles.
+constexpr int SPMV_TMA_CAP = 3840; // entries per stage (multiple of 4: 16-byte granules of cols)
+
+__device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   sp_smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(sp_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra DONE_%=;\n"
+               "bra WAIT_%=;\n"
+               "DONE_%=:\n"
+               "}" ::"r"(sp_smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+
+// position in the CTA's sequence of chunks: tile (R rows) and the entry range of the chunk inside it
+struct SpmvChunkIt
+{
+  int64_t tile, base, end;
+};
+
+template <int R>
+__global__ void __launch_bounds__(R)
+    k_spmv_tma(int32_t n_rows, int64_t nnz_total, const int64_t* __restrict__ row_ptr,
+               const int64_t* __restrict__ row_end_sel, const int32_t* __restrict__ cols,
+               const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y)
+{
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  double* s_val = reinterpret_cast<double*>(sp_raw);                                          // [2][CAP]
+  int32_t* s_col = reinterpret_cast<int32_t*>(sp_raw + 2 * SPMV_TMA_CAP * sizeof(double));     // [2][CAP]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sp_raw + 2 * SPMV_TMA_CAP * (sizeof(double) + sizeof(int32_t)));
+  const int64_t ntiles = ((int64_t)n_rows + R - 1) / R;
+  if (threadIdx.x == 0)
+  {
+    sp_mbar_init(&bar[0], 1);
+    sp_mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto load_tile = [&](SpmvChunkIt& it)
+  {
+    if (it.tile < ntiles)
+    {
+      const int64_t start = row_ptr[it.tile * R];
+      it.end = row_ptr[min((it.tile + 1) * R, (int64_t)n_rows)];
+      it.base = start & ~int64_t(3);
+    }
+  };
+  auto advance = [&](SpmvChunkIt& it)
+  {
+    it.base += SPMV_TMA_CAP;
+    if (it.base >= it.end)
+    {
+      it.tile += gridDim.x;
+      load_tile(it);
+    }
+  };
+  // bytes the TMA brings for a chunk: whole 16-byte granules that lie inside the arrays
+  auto tma_entries = [&](const SpmvChunkIt& it) -> int64_t
+  {
+    const int64_t lim = min(it.end, it.base + SPMV_TMA_CAP);
+    const int64_t want = (lim - it.base + 3) & ~int64_t(3);
+    const int64_t avail = (nnz_total - it.base) & ~int64_t(3);
+    return max((int64_t)0, min(want, avail));
+  };
+  auto issue = [&](const SpmvChunkIt& it, int stage)
+  {
+    const uint32_t n = (uint32_t)tma_entries(it);
+    sp_mbar_expect_tx(&bar[stage], n * 12u);
+    if (n)
+    {
+      sp_bulk_g2s(s_col + stage * SPMV_TMA_CAP, cols + it.base, n * 4u, &bar[stage]);
+      sp_bulk_g2s(s_val + stage * SPMV_TMA_CAP, values + it.base, n * 8u, &bar[stage]);
+    }
+  };
+
+  SpmvChunkIt cons, prod;
+  cons.tile = blockIdx.x, cons.base = 0, cons.end = 0;
+  load_tile(cons);
+  prod = cons;
+  // prologue: two chunks in flight
+  if (threadIdx.x == 0)
+  {
+    if (prod.tile < ntiles)
+      issue(prod, 0);
+  }
+  if (prod.tile < ntiles)
+    advance(prod);
+  if (threadIdx.x == 0)
+  {
+    if (prod.tile < ntiles)
+      issue(prod, 1);
+  }
+  if (prod.tile < ntiles)
+    advance(prod);
+
+  // row bounds and y of the CURRENT tile are fetched one chunk ahead (their latency would otherwise
+  // sit between the barrier and the first product)
+  double sum = 0.0, y_old = 0.0;
+  int64_t rb = 0, re = 0;
+  {
+    const int64_t my_row = cons.tile * R + threadIdx.x;
+    if (cons.tile < ntiles && my_row < n_rows)
+    {
+      rb = row_ptr[my_row];
+      re = row_end_sel[my_row];
+      y_old = y[my_row];
+    }
+  }
+  for (uint32_t c = 0; cons.tile < ntiles; ++c)
+  {
+    const int stage = c & 1;
+    const int64_t my_row = cons.tile * R + threadIdx.x;
+    const int64_t lim = min(cons.end, cons.base + SPMV_TMA_CAP);
+    const bool last = cons.base + SPMV_TMA_CAP >= cons.end;
+    // prefetch for the next tile of this CTA
+    SpmvChunkIt nxt = cons;
+    advance(nxt);
+    int64_t rb_n = 0, re_n = 0;
+    double y_n = 0.0;
+    if (last && nxt.tile < ntiles)
+    {
+      const int64_t row_n = nxt.tile * R + threadIdx.x;
+      if (row_n < n_rows)
+      {
+        rb_n = row_ptr[row_n];
+        re_n = row_end_sel[row_n];
+        y_n = y[row_n];
+      }
+    }
+    sp_mbar_wait(&bar[stage], (c >> 1) & 1);
+    double* sv = s_val + stage * SPMV_TMA_CAP;
+    int32_t* sc = s_col + stage * SPMV_TMA_CAP;
+    const int64_t got = cons.base + tma_entries(cons);
+    if (got < lim)
+    {
+      // the last < 4 entries of the arrays: not a whole 16-byte granule, loaded by hand
+      for (int64_t k = got + threadIdx.x; k < lim; k += R)
+      {
+        sv[k - cons.base] = values[k];
+        sc[k - cons.base] = cols[k];
+      }
+      __syncthreads();
+    }
+    const int lo = (int)(max(rb, cons.base) - cons.base), hi = (int)(min(re, lim) - cons.base);
+    // 8 gathers of x in flight per thread, two accumulators
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = lo; k < hi; k += 8)
+    {
+      double xv[8], av[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+      {
+        const bool in = k + u < hi;
+        av[u] = in ? sv[k + u] : 0.0;
+        xv[u] = in ? __ldg(x + sc[k + u]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u += 2)
+      {
+        s0 = fma(av[u], xv[u], s0);
+        s1 = fma(av[u + 1], xv[u + 1], s1);
+      }
+    }
+    sum += s0 + s1;
+    if (last && my_row < n_rows)
+      y[my_row] = y_old + sum;
+    __syncthreads(); // every thread is done with this stage: it can be refilled
+    if (threadIdx.x == 0 && prod.tile < ntiles)
+      issue(prod, stage);
+    if (prod.tile < ntiles)
+      advance(prod);
+    if (last)
+    {
+      rb = rb_n, re = re_n, y_old = y_n;
+      sum = 0.0;
+    }
+    cons = nxt;
+  }
+}
+
 // Blocked rows, compile-time block sizes: one warp per block row.  The row's nnz*BS0*BS1 contiguous
 // scalars are copied to a per-warp shared buffer with coalesced loads (32 blocks per pass), then
 // each lane owns one block: BS0*BS1 conflict-free LDS (odd stride), BS1 gathered x values, BS0
@@ -591,6 +795,13 @@ int bfx_csr_device_ptrs(const bfx_csr_t* A, const int64_t** row_ptr, const int32
   return BFX_OK;
 }
 
+int bfx_csr_set_spmv_variant(bfx_csr_t* A, int variant)
+{
+  BFX_REQUIRE(A && variant >= -1 && variant <= 2, "bfx_csr_set_spmv_variant: variant must be -1 (select by timing) .. 2");
+  A->spmv_variant = variant;
+  return BFX_OK;
+}
+
 int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* y, int part, bfx_stream_t stream)
 {
   BFX_REQUIRE(A && values && x && y, "bfx_spmv: null argument");
@@ -620,6 +831,31 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
     const double avg = (double)A->nnz_owned / (double)n;
     auto launch = [&](int variant, double* yy)
     {
+      if (variant == 2)
+      {
+        // TMA-pipelined persistent CTAs: rows per tile so that one stage usually covers a tile
+        const size_t smem = 2 * SPMV_TMA_CAP * 12 + 64;
+        const int per_sm = 2;
+        if (avg <= 15.0)
+        {
+          cudaFuncSetAttribute(k_spmv_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + 255) / 256, (int64_t)sm_count() * per_sm);
+          k_spmv_tma<256><<<grid, 256, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);
+        }
+        else if (avg <= 30.0)
+        {
+          cudaFuncSetAttribute(k_spmv_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + 127) / 128, (int64_t)sm_count() * per_sm);
+          k_spmv_tma<128><<<grid, 128, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);
+        }
+        else
+        {
+          cudaFuncSetAttribute(k_spmv_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + 63) / 64, (int64_t)sm_count() * per_sm);
+          k_spmv_tma<64><<<grid, 64, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);
+        }
+        return;
+      }
       if (variant == 1)
       {
         // row-per-thread out of staged (cols, values); rows per CTA so that one pass covers them
@@ -651,7 +887,7 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
       {
         float best = 1e30f;
         int best_v = 0;
-        for (int v = 0; v < 2; ++v)
+        for (int v = 0; v < 3; ++v)
         {
           float ms = 1e30f;
           for (int rep = 0; rep < 3; ++rep)

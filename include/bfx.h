@@ -140,6 +140,10 @@ extern "C"
   };
   int bfx_spmv(const bfx_csr_t* csr, const double* values_dev, const double* x_dev, double* y_dev, int part,
                bfx_stream_t stream);
+  /* bs = 1 SpMV kernel of this matrix: 0 = entry-consecutive stream, 1 = row per thread out of staged (cols, values),
+   * 2 = row per thread fed by a two-stage TMA pipeline (persistent CTAs); -1 (default) = time the three on the first
+   * bfx_spmv call and keep the fastest (which one wins depends on the numbering of the matrix). */
+  int bfx_csr_set_spmv_variant(bfx_csr_t* csr, int variant);
   /* MatrixCSR::multT local kernels — la/MatrixCSR.h:950-1016 → impl::spmvT la/matrix_csr_impl.h:319-343 */
   int bfx_spmvT(const bfx_csr_t* csr, const double* values_dev, const double* x_dev, double* y_dev, int part,
                 bfx_stream_t stream);

@@ -416,6 +416,13 @@ def test_spmv_assembled(bfx, oracle, kind):
     yref = y0.copy()
     oracle.spmv(data, A.indptr[:-1], A.indptr[1:], A.indices, xh, yref, p.bs, p.bs)
     assert np.max(np.abs(y.array.cpu().numpy() - yref)) <= TOL * np.max(np.abs(yref))
+    if p.bs == 1:
+        # every bs = 1 kernel variant (stream, rows, TMA-pipelined rows), not only the one the timing picked
+        for variant in (0, 1, 2):
+            bfx.lib.check(bfx.lib.lib.bfx_csr_set_spmv_variant(A._csr, variant))
+            y.array.copy_(torch.from_numpy(y0))
+            A.mult(x, y)
+            assert np.max(np.abs(y.array.cpu().numpy() - yref)) <= TOL * np.max(np.abs(yref)), variant
 
 
 def test_insert_set_add_and_errors(bfx, oracle):
