@@ -47,9 +47,9 @@ ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
 ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
-# where it beats the fp64-RED kernel on B200; P2 (id 8) has the variant too but its 100-entry element
-# matrices leave room for only 64 cells per chunk, too few to aggregate (measured slower), so it stays on REDs
-CHUNKED_KERNELS = frozenset({0, 2, 6})
+# and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
+CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
+CHUNKS_SYMMETRIC = 1  # every chunked kernel (ids 0, 2, 6, 8) has a symmetric element matrix
 VALUES_ADD, VALUES_OVERWRITE = 0, 1
 SPMV_FULL, SPMV_DIAG, SPMV_OFFDIAG = 0, 1, 2
 
@@ -102,7 +102,7 @@ _SIGS = {
     "bfx_spmvT": ([vp, vp, vp, vp, ci, vp], ci),
     "bfx_asm_create": ([pvp, vp, vp, ci, vp, ci, vp, ci, i64, vp, i64, i32, ci, vp], ci),
     "bfx_asm_destroy": ([vp], ci),
-    "bfx_asm_build_chunks": ([vp, vp, vp], ci),
+    "bfx_asm_build_chunks": ([vp, vp, ci, vp], ci),
     "bfx_asm_build_rowgather": ([vp, vp], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),

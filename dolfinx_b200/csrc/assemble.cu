@@ -1056,7 +1056,14 @@ int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x
   a.values = values;
   a.pos = P->pos;
   if (strategy == BFX_ASM_CHUNKED)
-    return launch_chunked(P, kernel_id, a, values_mode, S(stream));
+  {
+    // a symmetric chunk plan refuses calls whose rows and columns differ in dofmap or markers: those (rare)
+    // calls take the RED kernel, which has no such requirement
+    const int st = launch_chunked(P, kernel_id, a, values_mode, S(stream));
+    if (st != BFX_ERR_UNSUPPORTED || !P->chunks)
+      return st;
+    return dispatch_matrix<0>(P, kernel_id, a, S(stream));
+  }
   if (strategy == BFX_ASM_ROWGATHER)
   {
     if (kernel_id != BFX_K_ELASTICITY_Q1_HEX_A)
@@ -1207,7 +1214,8 @@ int bfx_assemble_matrix_cells_host(bfx_asm_t* P, int kernel_id, const double* x_
   BFX_CUDA(cudaMemcpyAsync(P->h_x, x_host, sizeof(double) * 3 * (size_t)n_x_nodes, cudaMemcpyHostToDevice, st));
   if (bc0_host)
     BFX_CUDA(cudaMemcpyAsync(P->h_bc0, bc0_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
-  if (bc1_host)
+  const bool one_marker_array = bc1_host && bc1_host == bc0_host; // same space: rows and columns share the markers
+  if (bc1_host && !one_marker_array)
     BFX_CUDA(cudaMemcpyAsync(P->h_bc1, bc1_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
   bfx_coeffs_t cf;
   memset(&cf, 0, sizeof(cf));
@@ -1222,7 +1230,8 @@ int bfx_assemble_matrix_cells_host(bfx_asm_t* P, int kernel_id, const double* x_
     cf.fused[0].bs = coeff_bs;
   }
   BFX_CUDA(cudaMemsetAsync(P->h_values, 0, sizeof(double) * nval, st));
-  int e = bfx_assemble_matrix_cells(P, kernel_id, P->h_x, bc0_host ? P->h_bc0 : nullptr, bc1_host ? P->h_bc1 : nullptr,
+  int e = bfx_assemble_matrix_cells(P, kernel_id, P->h_x, bc0_host ? P->h_bc0 : nullptr,
+                                    bc1_host ? (one_marker_array ? P->h_bc0 : P->h_bc1) : nullptr,
                                     &cf, constants, n_constants, P->h_values, strategy, BFX_VALUES_OVERWRITE, stream);
   if (e)
     return e;

@@ -57,7 +57,8 @@ struct ChunkHdr
 
 struct bfx_chunks
 {
-  int cb = 0, n2 = 0;
+  int cb = 0, n2 = 0; // cells per chunk, staged scalars per cell
+  bool sym = false;   // symmetric form: destinations are (row i col j, row j col i) pairs
   int64_t nchunks = 0, n_dest_pad = 0, n_src32 = 0;
   ChunkHdr* hdr = nullptr;
   uint32_t* winfo = nullptr;  // per group of 32 destinations: (offset of its source lists / 32) << 8 | list length
@@ -68,6 +69,13 @@ struct bfx_chunks
   // geometry dofmap / dofmaps in chunk order (one row per cell slot), so that phase 1 streams them
   // instead of chasing perm -> cells -> dofmap; NULL = the plan's own arrays are already in order
   int32_t *xdm = nullptr, *dm0 = nullptr, *dm1 = nullptr;
+  // Warp tables: the distinct geometry nodes (wv_*) / dofs (wd_*) of each group of 32 consecutive cell slots
+  // and, per cell, the positions of its nodes in that table.  When a group has <= 32 distinct nodes (the rule
+  // on locality-ordered meshes) one lane loads one node and the cells pick theirs up with warp shuffles:
+  // 3 coordinate loads per WARP instead of 3 NX per cell.  cnt == 0: the group gathers directly.
+  int32_t *wv_ids = nullptr, *wd_ids = nullptr;
+  uint8_t *wv_cnt = nullptr, *wd_cnt = nullptr;
+  uint8_t *wv_loc = nullptr, *wd_loc = nullptr; // 4 * ceil(width / 4) bytes per slot
   // Dirichlet markers of the current call packed to one bit per dof (rebuilt by every call: 1/8 of the
   // marker bytes, so the per-cell lookups of phase 1 stay in L1/L2)
   uint32_t *bits0 = nullptr, *bits1 = nullptr;

@@ -30,11 +30,12 @@ namespace
 constexpr int PLAN_THREADS = 1024;
 constexpr int MAX_LIST = 255;
 
-// cells per chunk for an element matrix of n2 scalars: staging fits 64-100 KB of shared memory and
-// the plan kernel's 1024 x ITEMS keys
-constexpr int chunk_cb(int n2) { return n2 <= 16 ? 512 : (n2 <= 36 ? 256 : (n2 <= 100 ? 64 : 0)); }
-// threads per chunk: one per cell for small element matrices, 4 per cell (rows dealt round-robin) for P2
-constexpr int chunk_threads(int n2) { return n2 <= 16 ? 512 : 256; }
+// cells per chunk for ns staged scalars per cell (N^2, or N(N+1)/2 for a symmetric form): the staging
+// area fits 40-60 KB of shared memory and the plan kernel's 1024 x ITEMS keys
+constexpr int chunk_cb(int ns) { return ns <= 16 ? 512 : (ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0))); }
+// threads per chunk: one per cell for small element matrices, several per cell (rows dealt round-robin) else
+constexpr int chunk_threads(int ns) { return ns <= 16 ? 512 : 256; }
+constexpr int staged_per_cell(int n, bool sym) { return sym ? n * (n + 1) / 2 : n * n; }
 
 // ---------------------------------------------------------------------------------------------
 // plan construction
@@ -42,7 +43,8 @@ constexpr int chunk_threads(int n2) { return n2 <= 16 ? 512 : 256; }
 struct ChunkBuildArgs
 {
   int64_t n; // entities of the plan
-  int cb, nd0, nd1, bs0, bs1, n2;
+  int cb, nd0, nd1, bs0, bs1, ns; // ns: staged scalars per cell
+  int sym;                        // symmetric form: one staged entry and one destination PAIR per {i, j}
   const int32_t *perm, *cells, *dofmap0;
   const int64_t* row_ptr;
   const char* pos;
@@ -66,21 +68,39 @@ __device__ __forceinline__ uint32_t pos_at(const char* pos, int pos_stride, int 
                         : (uint32_t) reinterpret_cast<const uint16_t*>(row)[t];
 }
 
-// scalar index into values of staged entry idx = k * cb + c of chunk q (k = I * N1 + J), or -1
-__device__ __forceinline__ int64_t contrib_addr(const ChunkBuildArgs& p, int64_t q, int idx, int64_t& blk)
+// scalar index into values of staged entry idx = k * cb + c of chunk q, or -1.  General form: k = I * N1 + J.
+// Symmetric form (bs = 1, one dofmap): k ranks the pair i <= j; the key is the smaller of the addresses of
+// (row i, col j) and (row j, col i), `other` the larger (== key on the diagonal): both receive the same sum.
+__device__ __forceinline__ int64_t contrib_addr(const ChunkBuildArgs& p, int64_t q, int idx, int64_t& blk, int64_t& other)
 {
-  const int N1 = p.nd1 * p.bs1;
   const int c = idx % p.cb, k = idx / p.cb;
-  const int I = k / N1, J = k - I * N1;
-  const int i = I / p.bs0, a = I - i * p.bs0, j = J / p.bs1, b = J - j * p.bs1;
   const int64_t slot = q * p.cb + c;
   if (slot >= p.n)
     return -1;
   const int64_t e = p.perm ? p.perm[slot] : slot;
   const int32_t cell = p.cells ? p.cells[e] : (int32_t)e;
+  if (p.sym)
+  {
+    int i = 0, rem = k;
+    while (rem >= p.nd0 - i)
+    {
+      rem -= p.nd0 - i;
+      ++i;
+    }
+    const int j = i + rem;
+    const int64_t a1 = p.row_ptr[p.dofmap0[(int64_t)cell * p.nd0 + i]] + pos_at(p.pos, p.pos_stride, p.pos_bytes, e, i * p.nd1 + j);
+    const int64_t a2 = p.row_ptr[p.dofmap0[(int64_t)cell * p.nd0 + j]] + pos_at(p.pos, p.pos_stride, p.pos_bytes, e, j * p.nd1 + i);
+    blk = a1 < a2 ? a1 : a2;
+    other = a1 < a2 ? a2 : a1;
+    return blk;
+  }
+  const int N1 = p.nd1 * p.bs1;
+  const int I = k / N1, J = k - I * N1;
+  const int i = I / p.bs0, a = I - i * p.bs0, j = J / p.bs1, b = J - j * p.bs1;
   const int32_t r = p.dofmap0[(int64_t)cell * p.nd0 + i];
   blk = p.row_ptr[r] + pos_at(p.pos, p.pos_stride, p.pos_bytes, e, i * p.nd1 + j);
-  return blk * (p.bs0 * p.bs1) + a * p.bs1 + b;
+  other = blk * (p.bs0 * p.bs1) + a * p.bs1 + b;
+  return other;
 }
 
 // contributions per block entry (how many (cell, i, j) land on it)
@@ -123,7 +143,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
 
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int ncontrib = p.n2 * p.cb;
+  const int ncontrib = p.ns * p.cb;
   const uint16_t ZERO = (uint16_t)ncontrib;
 
   // ---- 1. keys (address << 16 | staged index), sorted by address
@@ -132,9 +152,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
   for (int it = 0; it < ITEMS; ++it)
   {
     const int idx = tid * ITEMS + it;
-    int64_t blk, addr = -1;
+    int64_t blk, other, addr = -1;
     if (idx < ncontrib)
-      addr = contrib_addr(p, q, idx, blk);
+      addr = contrib_addr(p, q, idx, blk, other);
     keys[it] = addr >= 0 ? ((uint64_t)addr << 16) | (uint64_t)idx : ~0ull;
   }
   Sort1(temp.s1).Sort(keys, 16, 16 + p.addr_bits);
@@ -199,8 +219,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
         *p.err = 3;
         cnt = MAX_LIST;
       }
-      int64_t blk;
-      contrib_addr(p, q, sidx[st], blk);
+      int64_t blk, other;
+      contrib_addr(p, q, sidx[st], blk, other);
       const bool complete = p.total[blk] == cnt;
       ncomp += complete;
       k2[it] = ((complete ? 0u : 1u) << 8) | (uint32_t)(MAX_LIST - cnt);
@@ -265,22 +285,28 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
       const int w = r >> 5, lane = r & 31, m = (int)mw[w];
       uint16_t* out = p.src + ((src_base32 + woff[w]) << 5) + lane;
       int st = 0, cnt = 0;
+      int64_t addr = 0, other = 0;
       if (r < n_dest)
       {
         const int d = v2[it];
         st = dstart[d];
         cnt = min((int)dstart[d + 1] - st, MAX_LIST);
         int64_t blk;
-        const int64_t addr = contrib_addr(p, q, sidx[st], blk);
-        if (p.addr_bytes == 4)
-          static_cast<uint32_t*>(p.dest_addr)[dest_base + r] = (uint32_t)addr;
-        else
-          static_cast<uint64_t*>(p.dest_addr)[dest_base + r] = (uint64_t)addr;
+        addr = contrib_addr(p, q, sidx[st], blk, other);
       }
-      else if (p.addr_bytes == 4)
-        static_cast<uint32_t*>(p.dest_addr)[dest_base + r] = 0;
+      const int64_t at = (dest_base + r) * (p.sym ? 2 : 1);
+      if (p.addr_bytes == 4)
+      {
+        static_cast<uint32_t*>(p.dest_addr)[at] = (uint32_t)addr;
+        if (p.sym)
+          static_cast<uint32_t*>(p.dest_addr)[at + 1] = (uint32_t)other;
+      }
       else
-        static_cast<uint64_t*>(p.dest_addr)[dest_base + r] = 0;
+      {
+        static_cast<uint64_t*>(p.dest_addr)[at] = (uint64_t)addr;
+        if (p.sym)
+          static_cast<uint64_t*>(p.dest_addr)[at + 1] = (uint64_t)other;
+      }
       for (int j = 0; j < m; ++j)
         out[j << 5] = j < cnt ? sidx[st + j] : ZERO;
     }
@@ -322,6 +348,7 @@ int run_plan_pass_items(int items, bool write, const ChunkBuildArgs& p, int64_t 
 {
   switch (items)
   {
+  case 3: return run_plan_pass<3>(write, p, nchunks, st);
   case 5: return run_plan_pass<5>(write, p, nchunks, st);
   case 7: return run_plan_pass<7>(write, p, nchunks, st);
   case 8: return run_plan_pass<8>(write, p, nchunks, st);
@@ -447,6 +474,76 @@ __global__ void k_max_dof(int64_t n, const int32_t* __restrict__ cells, const in
     atomicMax(out, m);
 }
 
+// distinct ids of every group of 32 consecutive slots + per-slot positions in that list (see bfx_chunks)
+template <int WMAX>
+__global__ void __launch_bounds__(128)
+    k_warp_tables(int64_t nslots_pad, int64_t n, int width, const int32_t* __restrict__ rows /* slot-ordered */,
+                  int32_t* __restrict__ ids_out, uint8_t* __restrict__ cnt_out, uint8_t* __restrict__ loc_out)
+{
+  __shared__ int32_t s_id[4][32 * WMAX];
+  __shared__ int32_t s_tab[4][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int locw = 4 * ((width + 3) / 4);
+  for (int64_t gw = (int64_t)blockIdx.x * 4 + wib; gw * 32 < nslots_pad; gw += (int64_t)gridDim.x * 4)
+  {
+    const int64_t slot = gw * 32 + lane;
+    int32_t* wid = s_id[wib];
+    for (int k = 0; k < width; ++k)
+      wid[lane * width + k] = slot < n ? rows[slot * width + k] : -1;
+    __syncwarp();
+    // first occurrences, numbered in index order
+    int nfirst = 0;
+    unsigned firstmask = 0;
+    for (int k = 0; k < width; ++k)
+    {
+      const int idx = lane * width + k;
+      const int32_t id = wid[idx];
+      bool first = id >= 0;
+      for (int m = 0; m < idx && first; ++m)
+        first = wid[m] != id;
+      if (first)
+      {
+        ++nfirst;
+        firstmask |= 1u << k;
+      }
+    }
+    int before = nfirst;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int v = __shfl_up_sync(0xffffffffu, before, o);
+      if (lane >= o)
+        before += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, before, 31);
+    before -= nfirst;
+    const bool ok = total >= 1 && total <= 32;
+    if (ok)
+    {
+      int num = before;
+      for (int k = 0; k < width; ++k)
+        if ((firstmask >> k) & 1u)
+          s_tab[wib][num++] = wid[lane * width + k];
+    }
+    __syncwarp();
+    if (lane == 0)
+      cnt_out[gw] = ok ? (uint8_t)total : 0;
+    ids_out[gw * 32 + lane] = ok ? s_tab[wib][lane < total ? lane : 0] : 0;
+    for (int k = 0; k < locw; ++k)
+    {
+      uint8_t l = 0;
+      if (ok && k < width)
+      {
+        const int32_t id = wid[lane * width + k];
+        for (int j = 0; j < total; ++j)
+          if (s_tab[wib][j] == id)
+            l = (uint8_t)j;
+      }
+      loc_out[slot * locw + k] = l;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void k_permute_rows(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ cells,
                                const int32_t* __restrict__ map, int width, int32_t* __restrict__ out)
 {
@@ -472,6 +569,8 @@ struct ChunkArgs
   const uint16_t* src;
   const int32_t* perm;
   const int32_t *xdm, *dm0, *dm1; // chunk-ordered copies or NULL
+  const int32_t *wv_ids, *wd_ids; // warp tables (see bfx_chunks) or NULL
+  const uint8_t *wv_cnt, *wd_cnt, *wv_loc, *wd_loc;
   const uint32_t *bits0, *bits1;  // bit-packed Dirichlet markers or NULL
   int same_bc;                    // rows and columns share dofmap and markers
   int overwrite;
@@ -510,13 +609,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // shared-memory budget of the lists of one chunk (chunks over budget read their lists from global)
-template <int N2, int CB>
+template <int NS, int CB, int DSTRIDE>
 struct ChunkSmem
 {
-  static constexpr int SRC_GROUPS = (N2 * CB / 32) * 3 / 2; // 32-entry groups of source entries
-  static constexpr int DEST_BYTES = (N2 * CB / 2) * 4;      // destination addresses
-  static constexpr int WINFO = N2 * CB / 32;                // groups of 32 destinations
-  static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)N2 * (CB + 1) + 2) + 127) / 128 * 128;
+  static constexpr int SRC_GROUPS = (NS * CB / 32) * 3 / 2;       // 32-entry groups of source entries
+  static constexpr int DEST_BYTES = (NS * CB / 2) * 4 * DSTRIDE;  // destination addresses
+  static constexpr int WINFO = NS * CB / 32;                      // groups of 32 destinations
+  static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)NS * (CB + 1) + 2) + 127) / 128 * 128;
   static constexpr size_t SRC_OFF = E_BYTES;
   static constexpr size_t DEST_OFF = SRC_OFF + (size_t)SRC_GROUPS * 64;
   static constexpr size_t WINFO_OFF = DEST_OFF + DEST_BYTES;
@@ -524,12 +623,14 @@ struct ChunkSmem
   static constexpr size_t TOTAL = BAR_OFF + 16;
 };
 
-template <class E, int CB, int THREADS, typename AddrT>
+template <class E, bool SYM, int CB, int THREADS, typename AddrT>
 __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
-  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, N2 = N * N, TPC = THREADS / CB;
+  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, NS = staged_per_cell(N, SYM), TPC = THREADS / CB;
+  constexpr int DS = SYM ? 2 : 1; // addresses per destination
   static_assert(THREADS % CB == 0 && CB % 32 == 0, "a warp must work on one row residue");
-  using L = ChunkSmem<N2, CB>;
+  static_assert(!SYM || BS == 1, "symmetric staging is implemented for block size 1");
+  using L = ChunkSmem<NS, CB, DS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Es = reinterpret_cast<double*>(smem_raw);
   uint16_t* s_src = reinterpret_cast<uint16_t*>(smem_raw + L::SRC_OFF);
@@ -541,18 +642,37 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
   const int64_t q = blockIdx.x;
   const int64_t slot = q * CB + c;
 
+  // ---- first-level loads of phase 1, all issued before anything waits (header, group tables, positions):
+  //      the dependent second level (marker words, coordinates) then costs one more latency, not three
+  constexpr int LOCWV = (NX + 3) / 4, LOCWD = (ND + 3) / 4;
+  const int lane1 = threadIdx.x & 31;
+  const int64_t gw = (q * CB + (c & ~31)) >> 5; // group of 32 consecutive cell slots this warp works on
+  const bool use_bits = ch.bits0 || ch.bits1;
+  const bool dof_tab = BS == 1 && use_bits && ch.wd_cnt && (ch.same_bc || !ch.bits1);
+  const int dcnt = dof_tab ? ch.wd_cnt[gw] : 0;
+  const int vcnt = ch.wv_cnt ? ch.wv_cnt[gw] : 0;
+  const int64_t dof_id = dof_tab ? ch.wd_ids[gw * 32 + lane1] : 0;
+  const int32_t vtx_id = ch.wv_cnt ? ch.wv_ids[gw * 32 + lane1] : 0;
+  uint32_t locd[LOCWD], locv[LOCWV];
+#pragma unroll
+  for (int k = 0; k < LOCWD; ++k)
+    locd[k] = dof_tab ? __ldg(reinterpret_cast<const uint32_t*>(ch.wd_loc) + slot * LOCWD + k) : 0u;
+#pragma unroll
+  for (int k = 0; k < LOCWV; ++k)
+    locv[k] = ch.wv_cnt ? __ldg(reinterpret_cast<const uint32_t*>(ch.wv_loc) + slot * LOCWV + k) : 0u;
+
   // ---- prefetch of the chunk's lists: TMA bulk copies land while phase 1 computes
   const ChunkHdr h = ch.hdr[q];
   const int n_dw = (h.n_dest + 31) >> 5;
-  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 32u * (uint32_t)sizeof(AddrT);
+  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 32u * DS * (uint32_t)sizeof(AddrT);
   const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
   const uint16_t* g_src = ch.src + (h.src_base32 << 5);
-  const AddrT* g_dest = static_cast<const AddrT*>(ch.dest_addr) + h.dest_base;
+  const AddrT* g_dest = static_cast<const AddrT*>(ch.dest_addr) + h.dest_base * DS;
   const uint32_t* g_winfo = ch.winfo + (h.dest_base >> 5);
   if (threadIdx.x == 0)
   {
     mbar_init(bar, 1);
-    Es[N2 * (CB + 1)] = 0.0; // the slot padded list entries point at
+    Es[NS * (CB + 1)] = 0.0; // the slot padded list entries point at
   }
   __syncthreads();
   if (fits)
@@ -568,17 +688,38 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
   }
 
   // ---- phase 1: element matrices of the chunk -> shared memory (entry-major)
-  if (slot < a.n)
+  const bool active = slot < a.n;
+  int64_t e = slot;
+  int32_t cell = (int32_t)slot;
+  if (active && (E::WSIZE > 0 || !ch.xdm))
   {
-    int64_t e = slot;
-    int32_t cell = (int32_t)slot;
-    if (E::WSIZE > 0 || !ch.xdm)
+    e = ch.perm ? ch.perm[slot] : slot;
+    cell = a.cells ? a.cells[e] : (int32_t)e;
+  }
+  // second level: the marker word of this lane's dof and the coordinates of this lane's node
+  uint32_t bword = 0;
+  double px = 0.0, py = 0.0, pz = 0.0;
+  if (dcnt && ch.bits0)
+    bword = __ldg(ch.bits0 + (dof_id >> 5));
+  if (vcnt)
+  {
+    const double* pp = a.x + 3 * (int64_t)vtx_id;
+    px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+  }
+  // -- Dirichlet marker bit per scalar row / column of Ae
+  uint32_t m0 = 0, m1 = 0;
+  if (use_bits)
+  {
+    if (dcnt) // warp-uniform: one lane fetched the bit of one distinct dof, the cells pick theirs with shuffles
     {
-      e = ch.perm ? ch.perm[slot] : slot;
-      cell = a.cells ? a.cells[e] : (int32_t)e;
+      const uint32_t b = (bword >> (dof_id & 31)) & 1u;
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        m0 |= __shfl_sync(0xffffffffu, b, (locd[i >> 2] >> (8 * (i & 3))) & 31u) << i;
+      if (ch.same_bc)
+        m1 = m0;
     }
-    uint32_t m0 = 0, m1 = 0; // bc marker bit per scalar row / column of Ae
-    if (ch.bits0 || ch.bits1)
+    else if (active)
     {
       int32_t d0[ND];
       load_ints<ND>(ch.dm0 ? ch.dm0 + slot * ND : a.dofmap0 + (int64_t)cell * ND, d0);
@@ -605,10 +746,28 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
         }
       }
     }
+  }
+  // -- coordinates
+  double xc[NX][3];
+  if (vcnt) // warp-uniform
+  {
+#pragma unroll
+    for (int v = 0; v < NX; ++v)
+    {
+      const int l = (int)((locv[v >> 2] >> (8 * (v & 3))) & 31u);
+      xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+      xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+      xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+    }
+  }
+  else if (active)
+  {
     int32_t xd[NX];
     load_ints<NX>(ch.xdm ? ch.xdm + slot * NX : a.x_dofmap + (int64_t)cell * NX, xd);
-    double xc[NX][3];
     gather_coords<NX>(a.x, xd, xc);
+  }
+  if (active)
+  {
     double w[E::WSIZE > 0 ? E::WSIZE : 1];
     load_w<E>(a, e, cell, w);
     typename E::Geo g;
@@ -622,8 +781,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
       E::row(g, i, row);
       const bool zr = (m0 >> i) & 1u;
 #pragma unroll
-      for (int j = 0; j < N; ++j)
-        Es[(i * N + j) * (CB + 1) + c] = (zr || ((m1 >> j) & 1u)) ? 0.0 : row[j];
+      for (int j = SYM ? i : 0; j < N; ++j)
+      {
+        // symmetric form: only j >= i is staged, at rank i N - i (i - 1) / 2 + (j - i)
+        const int k = SYM ? i * N - i * (i - 1) / 2 + (j - i) : i * N + j;
+        Es[k * (CB + 1) + c] = (zr || ((m1 >> j) & 1u)) ? 0.0 : row[j];
+      }
     }
   }
   __syncthreads();
@@ -641,11 +804,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
     const int m = (int)(info & 0xffu);
     const uint16_t* p = srcp + ((size_t)(info >> 8) << 5) + lane;
     const int t = (dw << 5) + lane;
-    double* dst = a.values + (int64_t)destp[t];
-    double old = 0.0;
+    double* dst = a.values + (int64_t)destp[t * DS];
+    double* dst2 = SYM ? a.values + (int64_t)destp[t * DS + (DS - 1)] : dst;
+    double old = 0.0, old2 = 0.0;
     const bool plain = t < h.n_complete;
     if (plain && !ch.overwrite)
+    {
       old = *dst; // issued before the list walk: its latency hides behind the shared-memory sums
+      if (SYM)
+        old2 = *dst2;
+    }
     double s0 = 0.0, s1 = 0.0;
     int j = 0;
     // staged entry idx = k * CB + c lives at k * (CB + 1) + c: the entries of one cell fall into
@@ -667,9 +835,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
     if (t < h.n_dest)
     {
       if (plain)
+      {
         *dst = old + sum;
+        if (SYM && dst2 != dst)
+          *dst2 = old2 + sum;
+      }
       else
+      {
         red_add(dst, sum);
+        if (SYM && dst2 != dst)
+          red_add(dst2, sum);
+      }
     }
   }
 }
@@ -686,16 +862,16 @@ __global__ void k_pack_marker_bits(int64_t n, const int8_t* __restrict__ markers
   }
 }
 
-template <class E>
-int launch_chunked_e(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
+template <class E, bool SYM>
+int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
 {
-  constexpr int N2 = E::ND * E::BS * E::ND * E::BS;
-  constexpr int CB = chunk_cb(N2), THREADS = chunk_threads(N2);
+  constexpr int N = E::ND * E::BS, NS = staged_per_cell(N, SYM);
+  constexpr int CB = chunk_cb(NS), THREADS = chunk_threads(NS);
   static_assert(CB > 0, "element too large for the chunked path");
   const bfx_chunks* c = P->chunks;
-  if (c->cb != CB || c->n2 != N2)
-    return fail(BFX_ERR_INVALID, "chunk plan (cb=%d, n2=%d) does not match the kernel (cb=%d, n2=%d)", c->cb, c->n2, CB,
-                N2);
+  if (c->cb != CB || c->n2 != NS)
+    return fail(BFX_ERR_INVALID, "chunk plan (cb=%d, staged=%d) does not match the kernel (cb=%d, staged=%d)", c->cb,
+                c->n2, CB, NS);
   if (a.n == 0)
     return BFX_OK;
   ChunkArgs ch;
@@ -707,6 +883,8 @@ int launch_chunked_e(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaSt
   ch.xdm = c->xdm;
   ch.dm0 = c->dm0;
   ch.dm1 = c->dm1 ? c->dm1 : c->dm0;
+  ch.wv_ids = c->wv_ids, ch.wv_cnt = c->wv_cnt, ch.wv_loc = c->wv_loc;
+  ch.wd_ids = c->wd_ids, ch.wd_cnt = c->wd_cnt, ch.wd_loc = c->wd_loc;
   ch.overwrite = values_mode == BFX_VALUES_OVERWRITE;
   ch.bits0 = ch.bits1 = nullptr;
   ch.same_bc = a.bc0 && a.bc0 == a.bc1 && a.dofmap0 == a.dofmap1;
@@ -720,21 +898,33 @@ int launch_chunked_e(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaSt
     k_pack_marker_bits<<<grid_for(c->n_dofs1, 256, 8), 256, 0, st>>>(c->n_dofs1, a.bc1, c->bits1);
     ch.bits1 = c->bits1;
   }
-  const size_t smem = ChunkSmem<N2, CB>::TOTAL;
+  const size_t smem = ChunkSmem<NS, CB, SYM ? 2 : 1>::TOTAL;
   if (c->addr_bytes == 4)
   {
-    BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, CB, THREADS, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    k_matrix_chunked<E, CB, THREADS, uint32_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+    BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_matrix_chunked<E, SYM, CB, THREADS, uint32_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
   }
   else
   {
-    BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, CB, THREADS, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    k_matrix_chunked<E, CB, THREADS, uint64_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+    BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint64_t>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_matrix_chunked<E, SYM, CB, THREADS, uint64_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
   }
   BFX_CHECK_LAUNCH();
   return BFX_OK;
+}
+
+// The symmetric plan needs a symmetric element matrix (all chunked kernels are) AND symmetric bc zeroing:
+// the same dofmap and the same markers for rows and columns.  BFX_ERR_UNSUPPORTED lets the caller fall back.
+template <class E>
+int launch_chunked_e(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
+{
+  if (!P->chunks->sym)
+    return launch_chunked_es<E, false>(P, a, values_mode, st);
+  if (a.dofmap0 != a.dofmap1 || a.bc0 != a.bc1)
+    return fail(BFX_ERR_UNSUPPORTED, "symmetric chunk plan needs one dofmap and one marker array for rows and columns");
+  return launch_chunked_es<E, true>(P, a, values_mode, st);
 }
 
 } // namespace
@@ -781,27 +971,37 @@ void free_chunks(bfx_chunks* c)
   cudaFree(c->dm1);
   cudaFree(c->bits0);
   cudaFree(c->bits1);
+  cudaFree(c->wv_ids);
+  cudaFree(c->wv_cnt);
+  cudaFree(c->wv_loc);
+  cudaFree(c->wd_ids);
+  cudaFree(c->wd_cnt);
+  cudaFree(c->wd_loc);
   delete c;
 }
 } // namespace bfx
 
 extern "C"
 {
-int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)
+int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_stream_t stream)
 {
   BFX_REQUIRE(P && P->csr && P->pos, "bfx_asm_build_chunks: plan has no matrix / position map");
   cudaStream_t st = S(stream);
   const bfx_csr* csr = P->csr;
-  const int n2 = P->nd0 * csr->bs0 * P->nd1 * csr->bs1;
+  const bool sym = (flags & BFX_CHUNKS_SYMMETRIC) != 0;
+  if (sym && !(csr->bs0 == 1 && csr->bs1 == 1 && P->nd0 == P->nd1 && (!P->dofmap1 || P->dofmap1 == P->dofmap0)))
+    return fail(BFX_ERR_UNSUPPORTED, "symmetric chunk plan needs block size 1 and one dofmap for rows and columns");
+  const int n2 = sym ? staged_per_cell(P->nd0, true) : P->nd0 * csr->bs0 * P->nd1 * csr->bs1; // staged per cell
   const int cb = chunk_cb(n2);
   if (cb == 0 || P->ncells == 0)
-    return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d scalars are not supported", n2);
+    return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d staged scalars are not supported", n2);
   const int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
   free_chunks(P->chunks);
   P->chunks = nullptr;
   bfx_chunks* c = new bfx_chunks();
   c->cb = cb;
   c->n2 = n2;
+  c->sym = sym;
   c->nchunks = (P->ncells + cb - 1) / cb;
   int e = BFX_OK;
   auto bail = [&](int status)
@@ -855,6 +1055,30 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)
     BFX_CHECK_LAUNCH();
   }
 
+  // ---- warp tables of geometry nodes and dofs (groups of 32 consecutive cell slots)
+  {
+    const int64_t nslots_pad = c->nchunks * cb, nw = nslots_pad / 32;
+    const int32_t* xrows = c->xdm ? c->xdm : P->x_dofmap;
+    const int32_t* drows = c->dm0 ? c->dm0 : P->dofmap0;
+    const int lv = 4 * ((P->nx + 3) / 4), ld = 4 * ((P->nd0 + 3) / 4);
+    const unsigned grid = grid_for(nw, 4, 16);
+    if (P->nx <= 8)
+    {
+      if ((e = dev_alloc(&c->wv_ids, (size_t)nw * 32)) || (e = dev_alloc(&c->wv_cnt, (size_t)nw))
+          || (e = dev_alloc(&c->wv_loc, (size_t)nslots_pad * lv)))
+        return bail(e);
+      k_warp_tables<8><<<grid, 128, 0, st>>>(nslots_pad, P->ncells, P->nx, xrows, c->wv_ids, c->wv_cnt, c->wv_loc);
+    }
+    if (P->nd0 <= 4 && csr->bs0 == 1) // more dofs per cell never fit 32 distinct per group
+    {
+      if ((e = dev_alloc(&c->wd_ids, (size_t)nw * 32)) || (e = dev_alloc(&c->wd_cnt, (size_t)nw))
+          || (e = dev_alloc(&c->wd_loc, (size_t)nslots_pad * ld)))
+        return bail(e);
+      k_warp_tables<8><<<grid, 128, 0, st>>>(nslots_pad, P->ncells, P->nd0, drows, c->wd_ids, c->wd_cnt, c->wd_loc);
+    }
+    BFX_CHECK_LAUNCH();
+  }
+
   // ---- scratch of the bit-packed Dirichlet markers (sized by the largest dof the cells reference)
   {
     int32_t* d_max = nullptr;
@@ -900,7 +1124,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)
   memset(&p, 0, sizeof(p));
   p.n = P->ncells;
   p.cb = cb;
-  p.nd0 = P->nd0, p.nd1 = P->nd1, p.bs0 = csr->bs0, p.bs1 = csr->bs1, p.n2 = n2;
+  p.nd0 = P->nd0, p.nd1 = P->nd1, p.bs0 = csr->bs0, p.bs1 = csr->bs1, p.ns = n2;
+  p.sym = sym;
   p.perm = c->perm;
   p.cells = P->cells;
   p.dofmap0 = P->dofmap0;
@@ -946,7 +1171,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)
     return bail(e);
   {
     void* da = nullptr;
-    BFX_CUDA(cudaMalloc(&da, (size_t)(c->n_dest_pad + 32) * c->addr_bytes));
+    BFX_CUDA(cudaMalloc(&da, (size_t)(c->n_dest_pad + 32) * c->addr_bytes * (sym ? 2 : 1)));
     c->dest_addr = da;
   }
   p.dest_base32 = ndw;
@@ -978,7 +1203,7 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
   if (n_src_entries)
     *n_src_entries = c->n_src32 * 32;
   if (plan_bytes)
-    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4 + c->n_dest_pad * c->addr_bytes
+    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4 + c->n_dest_pad * c->addr_bytes * (c->sym ? 2 : 1)
                   + c->n_src32 * 64 + (c->perm ? P->ncells * 4 : 0)
                   + (c->xdm ? P->ncells * 4 * (int64_t)(P->nx + P->nd0 + (c->dm1 ? P->nd1 : 0)) : 0);
   return BFX_OK;

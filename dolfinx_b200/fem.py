@@ -393,6 +393,11 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
     return h
 
 
+# chunk plans of forms on one scalar space use symmetric (i,j)/(j,i) destination pairs; tests switch this off
+# to exercise the general plan as well
+CHUNKS_SYMMETRIC = True
+
+
 def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
     """Assembly strategy of a cell integral: the caller's choice, else the aggregated kernel of the
     element where it has one (chunk-aggregated for the P1 kernels, row-gather for Q1 elasticity; the
@@ -410,7 +415,9 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
     key = ("aggplan", plan.value, want)
     if key not in form._plans:
         if want == _lib.ASM_CHUNKED:
-            st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), _lib.current_stream())
+            V0, V1 = form.function_spaces
+            flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
+            st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
         else:
             st = _lib.lib.bfx_asm_build_rowgather(plan, _lib.current_stream())
         if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):

@@ -201,7 +201,13 @@ extern "C"
    * lower_bound + "+=" of insert_csr, la/matrix_csr_impl.h:67-109).  x_dev (optional geometry, (N,3)) orders
    * the cells along a Morton curve of their centroids so that a chunk is a compact patch; NULL keeps the
    * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
-  int bfx_asm_build_chunks(bfx_asm_t* plan, const double* x_dev, bfx_stream_t stream);
+  enum
+  {
+    BFX_CHUNKS_SYMMETRIC = 1 /* symmetric bilinear form on one space (block size 1): stage the upper triangle of the
+                                element matrix only and update the (i,j)/(j,i) CSR entries from one sum; a call whose
+                                rows and columns do not share dofmap and bc markers is refused (BFX_ERR_UNSUPPORTED) */
+  };
+  int bfx_asm_build_chunks(bfx_asm_t* plan, const double* x_dev, int flags, bfx_stream_t stream);
   /* Plan of the row-gather strategy (BFX_ASM_ROWGATHER): the transposed dofmap (row -> incident (cell, local
    * node) pairs in ascending cell order, cf. fem::transpose_dofmap, fem/DofMap.h:62-64) and the per-call scratch of
    * the cell records.  BFX_ERR_UNSUPPORTED unless the plan is Q1 hexahedra x block size 3 with one dofmap. */

@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "chunked and p1_lex" > gpurun_out/sanitizer_chunked.log 2>&1; tail -4 gpurun_out/sanitizer_chunked.log
+for cfg in p1; do
+timeout 900 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_${cfg}_v14.json 2> gpurun_out/bench_${cfg}_v14.err; tail -c 300 gpurun_out/bench_${cfg}_v14.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_${cfg}_v14.json'))
+print('$cfg', d['roofline']['kernel'], 'step %.3f ms'%d['ms_per_step'], 'asm kernel %.3f ms frac %.3f'%(d['roofline']['kernel_ms'], d['roofline']['frac']), 'spmv %.3f ms frac %.3f'%(d['spmv']['ms'], d['spmv']['frac']), 'vec %.3f'%d['vector_assembly_ms'], d['setup_s'])
+PY
+done
+timeout 900 python bench.py --config p2 --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_p2_chunked_v14.json 2> gpurun_out/bench_p2_chunked_v14.err; tail -c 300 gpurun_out/bench_p2_chunked_v14.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_p2_chunked_v14.json'))
+print('p2 chunked', d['roofline']['kernel'], 'step %.3f ms'%d['ms_per_step'], 'asm kernel %.3f ms frac %.3f'%(d['roofline']['kernel_ms'], d['roofline']['frac']))
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_matrix_chunked" -s 3 -c 1 -o gpurun_out/prof_p1_128_chunked_sym2 python bench.py --n 128 --steps 1 --warmup 3 --no-cpu --no-e2e --spmv-reps 1 > gpurun_out/ncu_chunked.log 2>&1; tail -1 gpurun_out/ncu_chunked.log | cut -c1-100
