@@ -350,6 +350,11 @@ def main():
     strat_used = fem._matrix_strategy(a, integ0, fem._asm_plan(a, integ0, fem.IntegralType.cell, A), strat)
     strat_name = {K.ASM_ATOMIC: "atomic", K.ASM_CHUNKED: "chunked", K.ASM_ROWGATHER: "rowgather"}[strat_used]
 
+    plan_info = None
+    if strat_used == K.ASM_CHUNKED and world == 1:
+        nch, ndest, nsrc, pbytes = fem.chunk_stats(a, A)
+        plan_info = {"chunks": nch, "destinations": ndest, "list_entries": nsrc, "plan_bytes": pbytes,
+                     "bank_conflicts_left": fem.chunk_bank_conflicts(a, A)}
     nnz = A._nnz
     n_rows = A.num_all_rows()
     n_cols = A.index_map(1).size_local + A.index_map(1).num_ghosts
@@ -514,6 +519,7 @@ def main():
             "vector_assembly_ms": ms_vec,
             "sizes": {"dofs_global": pb["ndofs_global"] * pb["bs"], "cells_per_gpu": pb["n_cells"], "nnz_per_gpu": nnz},
             "setup_s": {"mesh": t_mesh, "sparsity+matrix": t_pattern, "assembly_plan+first_call": t_plan},
+            "chunk_plan": plan_info,
         }
         print(json.dumps(line))
     if world > 1:

@@ -104,6 +104,7 @@ _SIGS = {
     "bfx_asm_destroy": ([vp], ci),
     "bfx_asm_build_chunks": ([vp, vp, ci, vp], ci),
     "bfx_asm_build_rowgather": ([vp, vp], ci),
+    "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),

@@ -64,7 +64,11 @@ struct bfx_chunks
   uint32_t* winfo = nullptr;  // per group of 32 destinations: (offset of its source lists / 32) << 8 | list length
   void* dest_addr = nullptr;  // scalar index into values per destination
   int addr_bytes = 4;
-  uint16_t* src = nullptr;    // source lists: indices into the staged element matrices, 32-way interleaved
+  uint16_t* src = nullptr;    // source lists: shared-memory slots of the staged entries, 32-way interleaved
+  // bank-conflict-free staging (small element matrices): slot of entry k of cell c = (k * cb/16 + c/16) * 16 +
+  // colour[c][k]; the colours make the 16 lanes of every list step hit 16 different 8-byte banks
+  uint8_t* colour = nullptr;  // ns (padded to a multiple of 4) bytes per cell slot, or NULL (padded linear layout)
+  int64_t n_bank_conflicts = 0; // list reads the colouring could not make conflict free (diagnostic)
   int32_t* perm = nullptr;    // locality ordering of the plan's cell list (or NULL)
   // geometry dofmap / dofmaps in chunk order (one row per cell slot), so that phase 1 streams them
   // instead of chasing perm -> cells -> dofmap; NULL = the plan's own arrays are already in order

@@ -32,10 +32,13 @@ constexpr int MAX_LIST = 255;
 
 // cells per chunk for ns staged scalars per cell (N^2, or N(N+1)/2 for a symmetric form): the staging
 // area fits 40-60 KB of shared memory and the plan kernel's 1024 x ITEMS keys
-constexpr int chunk_cb(int ns) { return ns <= 16 ? 512 : (ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0))); }
+constexpr int chunk_cb(int ns) { return ns <= 16 ? 256 : (ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0))); }
 // threads per chunk: one per cell for small element matrices, several per cell (rows dealt round-robin) else
-constexpr int chunk_threads(int ns) { return ns <= 16 ? 512 : 256; }
+constexpr int chunk_threads(int ns) { return 256; }
 constexpr int staged_per_cell(int n, bool sym) { return sym ? n * (n + 1) / 2 : n * n; }
+// 32-entry groups of list entries a chunk may have to be staged in shared memory (lists are padded per group of
+// 32 destinations to the longest list of the group: ~1.4x the entries on tetrahedral meshes)
+constexpr int src_group_cap(int nst) { return nst <= 4096 ? (nst / 32) * 5 / 2 + 2 : (nst / 32) * 3 / 2 + 2; }
 
 // ---------------------------------------------------------------------------------------------
 // plan construction
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
   {
     if (tid == 0)
     {
-      p.o_ndw[q] = n_dw;
+      p.o_ndw[q] = (n_dw + 3) & ~3; // 16-byte aligned winfo / 128-destination aligned chunks (TMA)
       p.o_nsrc32[q] = n_src32;
     }
     return;
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
           static_cast<uint64_t*>(p.dest_addr)[at + 1] = (uint64_t)other;
       }
       for (int j = 0; j < m; ++j)
-        out[j << 5] = j < cnt ? sidx[st + j] : ZERO;
+        out[j << 5] = j < cnt ? (uint16_t)(sidx[st + j] + sidx[st + j] / p.cb) : (uint16_t)(p.ns * (p.cb + 1));
     }
   }
 }
@@ -348,7 +351,9 @@ int run_plan_pass_items(int items, bool write, const ChunkBuildArgs& p, int64_t 
 {
   switch (items)
   {
+  case 2: return run_plan_pass<2>(write, p, nchunks, st);
   case 3: return run_plan_pass<3>(write, p, nchunks, st);
+  case 4: return run_plan_pass<4>(write, p, nchunks, st);
   case 5: return run_plan_pass<5>(write, p, nchunks, st);
   case 7: return run_plan_pass<7>(write, p, nchunks, st);
   case 8: return run_plan_pass<8>(write, p, nchunks, st);
@@ -474,6 +479,124 @@ __global__ void k_max_dof(int64_t n, const int32_t* __restrict__ cells, const in
     atomicMax(out, m);
 }
 
+// Bank colouring of the staging area (one warp per chunk).  Every staged entry is written once (by the half
+// warp of 16 consecutive cells c, entry k: "write group") and read once (by a half warp at one step of the
+// list walk: "read group").  Giving the 16 entries of a write group the 16 slots of one aligned 128-byte
+// line in some order keeps the stores conflict free; the order is chosen so that the entries of a read group
+// land in different 8-byte banks too (a proper edge colouring of the bipartite write-group/read-group graph
+// exists by Koenig's theorem; this greedy pass finds most of it, what it cannot avoid is counted).
+template <int CB>
+__global__ void __launch_bounds__(256)
+    k_chunk_colour(int64_t nchunks, int ns, const ChunkHdr* __restrict__ hdr, uint16_t* __restrict__ src,
+                   uint8_t* __restrict__ colour, int colw, unsigned long long* __restrict__ n_conflicts,
+                   int* __restrict__ overflow)
+{
+  constexpr int WPB = 8;
+  extern __shared__ __align__(16) unsigned char craw[];
+  const int nst = ns * CB; // staged entries per chunk
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // per warp: pos_of[nst] (uint16: position of the reader in the list, 0xffff = none), used[] masks, col[nst]
+  const int max_rg = 2 * src_group_cap(nst);
+  const size_t per_warp = ((size_t)nst * 2 + (size_t)max_rg * 2 + (size_t)nst + 15) / 16 * 16;
+  uint16_t* pos_of = reinterpret_cast<uint16_t*>(craw + wib * per_warp);
+  uint16_t* used = pos_of + nst;
+  uint8_t* col = reinterpret_cast<uint8_t*>(used + max_rg);
+  const int zero_slot = ns * (CB + 1);
+  for (int64_t q = (int64_t)blockIdx.x * WPB + wib; q < nchunks; q += (int64_t)gridDim.x * WPB)
+  {
+    const ChunkHdr h = hdr[q];
+    uint16_t* list = src + (h.src_base32 << 5);
+    const int nent = h.n_src32 * 32;
+    if (2 * h.n_src32 > max_rg)
+    {
+      if (lane == 0)
+        *overflow = 1; // lists far longer than the entries: the host rebuilds the plan with the linear layout
+      continue;
+    }
+    for (int t = lane; t < nst; t += 32)
+      pos_of[t] = 0xffffu;
+    for (int t = lane; t < max_rg; t += 32)
+      used[t] = 0;
+    __syncwarp();
+    for (int p = lane; p < nent; p += 32)
+    {
+      const int a = list[p];
+      if (a != zero_slot)
+        pos_of[(a / (CB + 1)) * CB + a % (CB + 1)] = (uint16_t)p;
+    }
+    __syncwarp();
+    unsigned long long bad = 0;
+    for (int wg = 0; wg < nst / 16; ++wg)
+    {
+      const int k = wg / (CB / 16), c = (wg % (CB / 16)) * 16 + (lane & 15);
+      const int idx = k * CB + c;
+      const int pp = lane < 16 ? pos_of[idx] : 0xffff;
+      const int rg = pp == 0xffff ? -1 : (pp >> 4);
+      const unsigned forb = rg >= 0 ? used[rg] : 0u;
+      // sequential greedy over the 16 entries, most constrained (most forbidden banks) first
+      unsigned taken = 0, mine = 0;
+      unsigned done = 0; // lanes already served (warp-uniform)
+      for (int step = 0; step < 16; ++step)
+      {
+        // pick the unserved lane with the largest number of forbidden colours
+        const int score = (lane < 16 && !((done >> lane) & 1u)) ? (__popc((forb | taken) & 0xffffu) << 5) + (31 - lane) : -1;
+        int best = score;
+        for (int o = 16; o > 0; o >>= 1)
+          best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        const int who = 31 - (best & 31);
+        unsigned pick = 0;
+        if (lane == who)
+        {
+          unsigned freec = ~(forb | taken) & 0xffffu;
+          if (!freec)
+          {
+            freec = ~taken & 0xffffu; // unavoidable: two entries of one read group share a bank
+            if (rg >= 0)
+              ++bad;
+          }
+          pick = freec & (0u - freec);
+          mine = pick;
+        }
+        pick = __shfl_sync(0xffffffffu, pick, who);
+        taken |= pick;
+        done |= 1u << who;
+        // entries of the same read group inside this write group must see the new bank as forbidden at once
+        const int rg_who = __shfl_sync(0xffffffffu, rg, who);
+        if (lane == who && rg >= 0)
+          used[rg] |= (uint16_t)pick;
+        __syncwarp();
+        (void)rg_who;
+      }
+      if (lane < 16)
+        col[idx] = (uint8_t)(__ffs(mine) - 1);
+      __syncwarp();
+      // refresh forb for lanes whose read group was updated by an earlier lane of this write group is not needed:
+      // `taken` already excludes every colour used inside the write group
+    }
+    __syncwarp();
+    // rewrite the lists and emit the per-cell colours
+    for (int p = lane; p < nent; p += 32)
+    {
+      const int a = list[p];
+      if (a != zero_slot)
+      {
+        const int k = a / (CB + 1), c = a % (CB + 1);
+        list[p] = (uint16_t)((k * (CB / 16) + (c >> 4)) * 16 + col[k * CB + c]);
+      }
+      else
+        list[p] = (uint16_t)nst;
+    }
+    for (int t = lane; t < CB * colw; t += 32)
+    {
+      const int c = t / colw, k = t % colw;
+      colour[(q * CB + c) * colw + k] = k < ns ? col[k * CB + c] : 0;
+    }
+    if (lane == 0 && bad)
+      atomicAdd(n_conflicts, bad);
+    __syncwarp();
+  }
+}
+
 // distinct ids of every group of 32 consecutive slots + per-slot positions in that list (see bfx_chunks)
 template <int WMAX>
 __global__ void __launch_bounds__(128)
@@ -571,6 +694,7 @@ struct ChunkArgs
   const int32_t *xdm, *dm0, *dm1; // chunk-ordered copies or NULL
   const int32_t *wv_ids, *wd_ids; // warp tables (see bfx_chunks) or NULL
   const uint8_t *wv_cnt, *wd_cnt, *wv_loc, *wd_loc;
+  const uint8_t* colour;          // bank colours of the staged entries (per cell slot) or NULL
   const uint32_t *bits0, *bits1;  // bit-packed Dirichlet markers or NULL
   int same_bc;                    // rows and columns share dofmap and markers
   int overwrite;
@@ -612,19 +736,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 template <int NS, int CB, int DSTRIDE>
 struct ChunkSmem
 {
-  static constexpr int SRC_GROUPS = (NS * CB / 32) * 3 / 2;       // 32-entry groups of source entries
+  static constexpr int SRC_GROUPS = src_group_cap(NS * CB);        // 32-entry groups of source entries
   static constexpr int DEST_BYTES = (NS * CB / 2) * 4 * DSTRIDE;  // destination addresses
   static constexpr int WINFO = NS * CB / 32;                      // groups of 32 destinations
   static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)NS * (CB + 1) + 2) + 127) / 128 * 128;
   static constexpr size_t SRC_OFF = E_BYTES;
   static constexpr size_t DEST_OFF = SRC_OFF + (size_t)SRC_GROUPS * 64;
   static constexpr size_t WINFO_OFF = DEST_OFF + DEST_BYTES;
-  static constexpr size_t BAR_OFF = WINFO_OFF + (size_t)WINFO * 4;
+  static constexpr size_t BAR_OFF = WINFO_OFF + (((size_t)WINFO * 4 + 15) / 16) * 16 + 16;
   static constexpr size_t TOTAL = BAR_OFF + 16;
 };
 
 template <class E, bool SYM, int CB, int THREADS, typename AddrT>
-__global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2)) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
   constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, NS = staged_per_cell(N, SYM), TPC = THREADS / CB;
   constexpr int DS = SYM ? 2 : 1; // addresses per destination
@@ -653,6 +777,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
   const int vcnt = ch.wv_cnt ? ch.wv_cnt[gw] : 0;
   const int64_t dof_id = dof_tab ? ch.wd_ids[gw * 32 + lane1] : 0;
   const int32_t vtx_id = ch.wv_cnt ? ch.wv_ids[gw * 32 + lane1] : 0;
+  constexpr int COLW = (NS + 3) / 4;
+  uint32_t colw[NS <= 16 ? COLW : 1];
+  if constexpr (NS <= 16)
+  {
+#pragma unroll
+    for (int k = 0; k < COLW; ++k)
+      colw[k] = ch.colour ? __ldg(reinterpret_cast<const uint32_t*>(ch.colour) + slot * COLW + k) : 0u;
+  }
   uint32_t locd[LOCWD], locv[LOCWV];
 #pragma unroll
   for (int k = 0; k < LOCWD; ++k)
@@ -671,20 +803,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
   const uint32_t* g_winfo = ch.winfo + (h.dest_base >> 5);
   if (threadIdx.x == 0)
   {
+    // one thread arms the barrier and starts the copies; nobody else touches the header before phase 2
     mbar_init(bar, 1);
-    Es[NS * (CB + 1)] = 0.0; // the slot padded list entries point at
-  }
-  __syncthreads();
-  if (fits)
-  {
-    if (threadIdx.x == 0 && n_dw > 0)
+    Es[ch.colour ? NS * CB : NS * (CB + 1)] = 0.0; // the slot padded list entries point at
+    if (fits && n_dw > 0)
     {
-      mbar_expect_tx(bar, src_bytes + dest_bytes);
+      const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u; // chunks start on 4-group boundaries
+      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes);
       bulk_g2s(s_src, g_src, src_bytes, bar);
       bulk_g2s(s_dest, g_dest, dest_bytes, bar);
+      bulk_g2s(s_winfo, g_winfo, winfo_bytes, bar);
     }
-    for (int w = threadIdx.x; w < n_dw; w += THREADS)
-      s_winfo[w] = g_winfo[w];
   }
 
   // ---- phase 1: element matrices of the chunk -> shared memory (entry-major)
@@ -705,6 +834,32 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
   {
     const double* pp = a.x + 3 * (int64_t)vtx_id;
     px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+  }
+  // -- coordinates
+  double xc[NX][3];
+  if (vcnt) // warp-uniform
+  {
+#pragma unroll
+    for (int v = 0; v < NX; ++v)
+    {
+      const int l = (int)((locv[v >> 2] >> (8 * (v & 3))) & 31u);
+      xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+      xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+      xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+    }
+  }
+  else if (active)
+  {
+    int32_t xd[NX];
+    load_ints<NX>(ch.xdm ? ch.xdm + slot * NX : a.x_dofmap + (int64_t)cell * NX, xd);
+    gather_coords<NX>(a.x, xd, xc);
+  }
+  typename E::Geo g;
+  if (active)
+  {
+    double w[E::WSIZE > 0 ? E::WSIZE : 1];
+    load_w<E>(a, e, cell, w);
+    E::prepare(g, xc, w, a.constants, 0);
   }
   // -- Dirichlet marker bit per scalar row / column of Ae
   uint32_t m0 = 0, m1 = 0;
@@ -747,31 +902,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
       }
     }
   }
-  // -- coordinates
-  double xc[NX][3];
-  if (vcnt) // warp-uniform
-  {
-#pragma unroll
-    for (int v = 0; v < NX; ++v)
-    {
-      const int l = (int)((locv[v >> 2] >> (8 * (v & 3))) & 31u);
-      xc[v][0] = __shfl_sync(0xffffffffu, px, l);
-      xc[v][1] = __shfl_sync(0xffffffffu, py, l);
-      xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
-    }
-  }
-  else if (active)
-  {
-    int32_t xd[NX];
-    load_ints<NX>(ch.xdm ? ch.xdm + slot * NX : a.x_dofmap + (int64_t)cell * NX, xd);
-    gather_coords<NX>(a.x, xd, xc);
-  }
   if (active)
   {
-    double w[E::WSIZE > 0 ? E::WSIZE : 1];
-    load_w<E>(a, e, cell, w);
-    typename E::Geo g;
-    E::prepare(g, xc, w, a.constants, 0);
 #pragma unroll
     for (int i = 0; i < N; ++i)
     {
@@ -785,7 +917,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
       {
         // symmetric form: only j >= i is staged, at rank i N - i (i - 1) / 2 + (j - i)
         const int k = SYM ? i * N - i * (i - 1) / 2 + (j - i) : i * N + j;
-        Es[k * (CB + 1) + c] = (zr || ((m1 >> j) & 1u)) ? 0.0 : row[j];
+        int at = k * (CB + 1) + c;
+        if constexpr (NS <= 16)
+        {
+          if (ch.colour) // the 16 cells of a half warp permute the 16 slots of one 128-byte line
+            at = (k * (CB / 16) + (c >> 4)) * 16 + (int)((colw[k >> 2] >> (8 * (k & 3))) & 15u);
+        }
+        Es[at] = (zr || ((m1 >> j) & 1u)) ? 0.0 : row[j];
       }
     }
   }
@@ -816,20 +954,19 @@ __global__ void __launch_bounds__(THREADS, 2) k_matrix_chunked(const AsmArgs a, 
     }
     double s0 = 0.0, s1 = 0.0;
     int j = 0;
-    // staged entry idx = k * CB + c lives at k * (CB + 1) + c: the entries of one cell fall into
-    // different banks (neighbouring destinations draw on the same few cells)
+    // the lists hold shared-memory slots: k * (CB + 1) + c (padded linear layout) or the bank-coloured slot
     for (; j + 4 <= m; j += 4)
     {
       const uint32_t i0 = p[(j + 0) << 5], i1 = p[(j + 1) << 5], i2 = p[(j + 2) << 5], i3 = p[(j + 3) << 5];
-      s0 += Es[i0 + i0 / CB];
-      s1 += Es[i1 + i1 / CB];
-      s0 += Es[i2 + i2 / CB];
-      s1 += Es[i3 + i3 / CB];
+      s0 += Es[i0];
+      s1 += Es[i1];
+      s0 += Es[i2];
+      s1 += Es[i3];
     }
     for (; j < m; ++j)
     {
       const uint32_t i0 = p[j << 5];
-      s0 += Es[i0 + i0 / CB];
+      s0 += Es[i0];
     }
     const double sum = s0 + s1;
     if (t < h.n_dest)
@@ -885,6 +1022,7 @@ int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   ch.dm1 = c->dm1 ? c->dm1 : c->dm0;
   ch.wv_ids = c->wv_ids, ch.wv_cnt = c->wv_cnt, ch.wv_loc = c->wv_loc;
   ch.wd_ids = c->wd_ids, ch.wd_cnt = c->wd_cnt, ch.wd_loc = c->wd_loc;
+  ch.colour = c->colour;
   ch.overwrite = values_mode == BFX_VALUES_OVERWRITE;
   ch.bits0 = ch.bits1 = nullptr;
   ch.same_bc = a.bc0 && a.bc0 == a.bc1 && a.dofmap0 == a.dofmap1;
@@ -971,6 +1109,7 @@ void free_chunks(bfx_chunks* c)
   cudaFree(c->dm1);
   cudaFree(c->bits0);
   cudaFree(c->bits1);
+  cudaFree(c->colour);
   cudaFree(c->wv_ids);
   cudaFree(c->wv_cnt);
   cudaFree(c->wv_loc);
@@ -1166,7 +1305,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     c->n_dest_pad = tot[0] * 32;
     c->n_src32 = tot[1];
   }
-  if ((e = dev_alloc(&c->hdr, (size_t)c->nchunks)) || (e = dev_alloc(&c->winfo, (size_t)(c->n_dest_pad / 32 + 1)))
+  if ((e = dev_alloc(&c->hdr, (size_t)c->nchunks)) || (e = dev_alloc(&c->winfo, (size_t)(c->n_dest_pad / 32 + 8)))
       || (e = dev_alloc(&c->src, (size_t)c->n_src32 * 32 + 32)))
     return bail(e);
   {
@@ -1183,6 +1322,44 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   p.src = c->src;
   if ((e = run_plan_pass_items(items, true, p, c->nchunks, st)))
     return bail(e);
+  // ---- bank-conflict-free staging layout (element matrices of at most 16 staged entries)
+  if (n2 <= 16 && !(flags & BFX_CHUNKS_LINEAR_STAGING))
+  {
+    const int colw = 4 * ((n2 + 3) / 4);
+    unsigned long long* d_conf = nullptr;
+    int* d_over = nullptr;
+    if ((e = dev_alloc(&c->colour, (size_t)c->nchunks * cb * colw)) || (e = dev_alloc(&d_conf, 1))
+        || (e = dev_alloc(&d_over, 1)))
+      return bail(e);
+    BFX_CUDA(cudaMemsetAsync(d_conf, 0, sizeof(unsigned long long), st));
+    BFX_CUDA(cudaMemsetAsync(d_over, 0, sizeof(int), st));
+    const int nst = n2 * cb, max_rg = 2 * src_group_cap(nst);
+    const size_t per_warp = ((size_t)nst * 2 + (size_t)max_rg * 2 + (size_t)nst + 15) / 16 * 16;
+    const size_t smem = per_warp * 8;
+    const unsigned grid = grid_for((c->nchunks + 7) / 8, 1, 8);
+    static_assert(chunk_cb(16) == chunk_cb(1), "colouring assumes one chunk size for all small elements");
+    constexpr int CBS = chunk_cb(16);
+    BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<CBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chunk_colour<CBS><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
+    BFX_CHECK_LAUNCH();
+    unsigned long long h_conf = 0;
+    int h_over = 0;
+    BFX_CUDA(cudaMemcpyAsync(&h_conf, d_conf, sizeof(h_conf), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaMemcpyAsync(&h_over, d_over, sizeof(h_over), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_conf);
+    cudaFree(d_over);
+    c->n_bank_conflicts = (int64_t)h_conf;
+    if (h_over)
+    {
+      // some chunk's lists are far longer than its entries: keep the linear layout (rewrite the lists)
+      cudaFree(c->colour);
+      c->colour = nullptr;
+      c->n_bank_conflicts = -1;
+      if ((e = run_plan_pass_items(items, true, p, c->nchunks, st)))
+        return bail(e);
+    }
+  }
   BFX_CUDA(cudaStreamSynchronize(st));
   cudaFree(total);
   cudaFree(ndw);
@@ -1194,6 +1371,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
 int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
                         int64_t* plan_bytes)
 {
+  // (plan_bytes is followed by the diagnostic bfx_asm_chunk_bank_conflicts)
   BFX_REQUIRE(P && P->chunks, "bfx_asm_chunk_stats: no chunk plan");
   const bfx_chunks* c = P->chunks;
   if (nchunks)
@@ -1206,6 +1384,13 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
     *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4 + c->n_dest_pad * c->addr_bytes * (c->sym ? 2 : 1)
                   + c->n_src32 * 64 + (c->perm ? P->ncells * 4 : 0)
                   + (c->xdm ? P->ncells * 4 * (int64_t)(P->nx + P->nd0 + (c->dm1 ? P->nd1 : 0)) : 0);
+  return BFX_OK;
+}
+
+int bfx_asm_chunk_bank_conflicts(const bfx_asm_t* P, int64_t* n_conflicts)
+{
+  BFX_REQUIRE(P && P->chunks && n_conflicts, "bfx_asm_chunk_bank_conflicts: no chunk plan");
+  *n_conflicts = P->chunks->colour ? P->chunks->n_bank_conflicts : -1;
   return BFX_OK;
 }
 }

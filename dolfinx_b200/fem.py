@@ -441,6 +441,16 @@ def chunk_stats(form: Form, A: la.MatrixCSR, itype=None, ident=0):
     return tuple(int(o.value) for o in out)
 
 
+def chunk_bank_conflicts(form: Form, A: la.MatrixCSR, ident=0):
+    """Staged entries the plan's bank colouring could not make conflict free (-1: linear staging layout)."""
+    from . import _lib
+
+    plan = _asm_plan(form, form.integral(IntegralType.cell, ident), IntegralType.cell, A)
+    n = C.c_int64()
+    _lib.check(_lib.lib.bfx_asm_chunk_bank_conflicts(plan, C.byref(n)))
+    return int(n.value)
+
+
 def _boundary_interior_cells(form: Form, integ: IntegralData):
     """Split a cell domain into cells that touch a ghost row (their contributions must travel to the
     owner, la/MatrixCSR.h:399-468) and interior cells (SURVEY.md §8e overlap plan)."""

@@ -203,6 +203,7 @@ extern "C"
    * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
   enum
   {
+    BFX_CHUNKS_LINEAR_STAGING = 2, /* keep the padded linear staging layout (skip the bank colouring of the plan) */
     BFX_CHUNKS_SYMMETRIC = 1 /* symmetric bilinear form on one space (block size 1): stage the upper triangle of the
                                 element matrix only and update the (i,j)/(j,i) CSR entries from one sum; a call whose
                                 rows and columns do not share dofmap and bc markers is refused (BFX_ERR_UNSUPPORTED) */
@@ -214,6 +215,9 @@ extern "C"
   int bfx_asm_build_rowgather(bfx_asm_t* plan, bfx_stream_t stream);
   int bfx_asm_chunk_stats(const bfx_asm_t* plan, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
                           int64_t* plan_bytes);
+  /* Staged entries whose shared-memory bank still collides with another entry read in the same half-warp step
+   * after the plan's bank colouring (-1: linear staging layout in use). */
+  int bfx_asm_chunk_bank_conflicts(const bfx_asm_t* plan, int64_t* n_conflicts);
 
   /* impl::assemble_cells_matrix<false> — fem/assemble_matrix_impl.h:92-200 (+ bc row/col zeroing :161-196).
    * bc0/bc1: int8 markers of length bs*(owned+ghost) or NULL.  constants: host array. */

@@ -2,10 +2,10 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "chunked or p1 or golden or bcs" > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 for cfg in p1 p2; do
-timeout 900 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_${cfg}_v15.json 2> gpurun_out/bench_${cfg}_v15.err; tail -c 300 gpurun_out/bench_${cfg}_v15.err
+timeout 900 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_${cfg}_v19.json 2> gpurun_out/bench_${cfg}_v19.err; tail -c 300 gpurun_out/bench_${cfg}_v19.err
 python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_${cfg}_v15.json'))
-print('$cfg', d['roofline']['kernel'], 'step %.3f ms'%d['ms_per_step'], 'asm kernel %.3f ms frac %.3f'%(d['roofline']['kernel_ms'], d['roofline']['frac']), 'spmv %.3f ms frac %.3f'%(d['spmv']['ms'], d['spmv']['frac']), 'vec %.3f'%d['vector_assembly_ms'], d['setup_s'])
+d=json.load(open('gpurun_out/bench_${cfg}_v19.json'))
+print(d.get("chunk_plan")); print("$cfg", d["roofline"]["kernel"], 'step %.3f ms'%d['ms_per_step'], 'asm kernel %.3f ms frac %.3f'%(d['roofline']['kernel_ms'], d['roofline']['frac']), 'spmv %.3f ms frac %.3f'%(d['spmv']['ms'], d['spmv']['frac']), 'vec %.3f'%d['vector_assembly_ms'], d['setup_s'])
 PY
 done
