@@ -35,6 +35,9 @@ constexpr int MAX_LIST = 255;
 constexpr int chunk_cb(int ns) { return ns <= 16 ? 256 : (ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0))); }
 // threads per chunk: one per cell for small element matrices, several per cell (rows dealt round-robin) else
 constexpr int chunk_threads(int ns) { return 256; }
+// largest element (staged scalars per cell) that gets the bank-coloured staging layout: the colours of a cell
+// travel in registers
+constexpr int COLOUR_MAX_NS = 36; // (measured: P2 Poisson, 55 staged entries, is bound by its chunk-boundary REDs, not by bank conflicts)
 constexpr int staged_per_cell(int n, bool sym) { return sym ? n * (n + 1) / 2 : n * n; }
 // 32-entry groups of list entries a chunk may have to be staged in shared memory (lists are padded per group of
 // 32 destinations to the longest list of the group: ~1.4x the entries on tetrahedral meshes)
@@ -778,8 +781,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2)) k_matrix_ch
   const int64_t dof_id = dof_tab ? ch.wd_ids[gw * 32 + lane1] : 0;
   const int32_t vtx_id = ch.wv_cnt ? ch.wv_ids[gw * 32 + lane1] : 0;
   constexpr int COLW = (NS + 3) / 4;
-  uint32_t colw[NS <= 16 ? COLW : 1];
-  if constexpr (NS <= 16)
+  uint32_t colw[NS <= COLOUR_MAX_NS ? COLW : 1];
+  if constexpr (NS <= COLOUR_MAX_NS)
   {
 #pragma unroll
     for (int k = 0; k < COLW; ++k)
@@ -918,7 +921,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2)) k_matrix_ch
         // symmetric form: only j >= i is staged, at rank i N - i (i - 1) / 2 + (j - i)
         const int k = SYM ? i * N - i * (i - 1) / 2 + (j - i) : i * N + j;
         int at = k * (CB + 1) + c;
-        if constexpr (NS <= 16)
+        if constexpr (NS <= COLOUR_MAX_NS)
         {
           if (ch.colour) // the 16 cells of a half warp permute the 16 slots of one 128-byte line
             at = (k * (CB / 16) + (c >> 4)) * 16 + (int)((colw[k >> 2] >> (8 * (k & 3))) & 15u);
@@ -1323,7 +1326,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   if ((e = run_plan_pass_items(items, true, p, c->nchunks, st)))
     return bail(e);
   // ---- bank-conflict-free staging layout (element matrices of at most 16 staged entries)
-  if (n2 <= 16 && !(flags & BFX_CHUNKS_LINEAR_STAGING))
+  if (n2 <= COLOUR_MAX_NS && !(flags & BFX_CHUNKS_LINEAR_STAGING))
   {
     const int colw = 4 * ((n2 + 3) / 4);
     unsigned long long* d_conf = nullptr;
@@ -1337,10 +1340,18 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     const size_t per_warp = ((size_t)nst * 2 + (size_t)max_rg * 2 + (size_t)nst + 15) / 16 * 16;
     const size_t smem = per_warp * 8;
     const unsigned grid = grid_for((c->nchunks + 7) / 8, 1, 8);
-    static_assert(chunk_cb(16) == chunk_cb(1), "colouring assumes one chunk size for all small elements");
-    constexpr int CBS = chunk_cb(16);
-    BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<CBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_chunk_colour<CBS><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
+    if (cb == 256)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_chunk_colour<256><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
+    }
+    else if (cb == 128)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_chunk_colour<128><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
+    }
+    else
+      return bail(fail(BFX_ERR_INVALID, "chunk plan: no colouring kernel for %d cells per chunk", cb));
     BFX_CHECK_LAUNCH();
     unsigned long long h_conf = 0;
     int h_over = 0;

@@ -10,6 +10,7 @@ behaviour follow the reference; the cell loops run as CUDA kernels.  ``Mesh``, `
 from __future__ import annotations
 
 import ctypes as C
+import os
 import enum
 from dataclasses import dataclass, field
 
@@ -395,7 +396,7 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
 
 # chunk plans of forms on one scalar space use symmetric (i,j)/(j,i) destination pairs; tests switch this off
 # to exercise the general plan as well
-CHUNKS_SYMMETRIC = True
+CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 
 
 def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
