@@ -49,6 +49,7 @@ ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
 CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
+CHUNKS_SHARED_MATRIX = 4
 CHUNKS_SYMMETRIC = 1  # every chunked kernel (ids 0, 2, 6, 8) has a symmetric element matrix
 VALUES_ADD, VALUES_OVERWRITE = 0, 1
 SPMV_FULL, SPMV_DIAG, SPMV_OFFDIAG = 0, 1, 2

@@ -126,6 +126,28 @@ __global__ void k_count_contrib(int64_t n, const int32_t* __restrict__ cells, co
   }
 }
 
+// the same count over EVERY cell of the dofmap, entries located by binary search (cells outside the plan's list
+// have no position map): used when other launches add to the same matrix (BFX_CHUNKS_SHARED_MATRIX)
+__global__ void k_count_contrib_all(int64_t ncells_all, const int32_t* __restrict__ dofmap0, int nd0,
+                                    const int32_t* __restrict__ dofmap1, int nd1, const int64_t* __restrict__ row_ptr,
+                                    const int32_t* __restrict__ cols, int32_t* __restrict__ total)
+{
+  const int64_t work = ncells_all * nd0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t cell = t / nd0;
+    const int i = (int)(t - cell * nd0);
+    const int32_t r = dofmap0[cell * nd0 + i];
+    const int64_t rb = row_ptr[r], re = row_ptr[r + 1];
+    for (int j = 0; j < nd1; ++j)
+    {
+      const int64_t p = find_col(cols, rb, re, dofmap1[cell * nd1 + j]);
+      if (p >= 0)
+        atomicAdd(total + p, 1);
+    }
+  }
+}
+
 template <int ITEMS, bool WRITE>
 __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArgs p)
 {
@@ -1246,9 +1268,13 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   if ((e = dev_alloc(&total, (size_t)csr->nnz)))
     return bail(e);
   BFX_CUDA(cudaMemsetAsync(total, 0, sizeof(int32_t) * (size_t)csr->nnz, st));
-  k_count_contrib<<<grid_for(P->ncells * P->nd0, 256, 16), 256, 0, st>>>(P->ncells, P->cells, P->dofmap0, P->nd0, P->nd1,
-                                                                         csr->row_ptr, P->pos, P->pos_stride,
-                                                                         P->pos_bytes, total);
+  if (flags & BFX_CHUNKS_SHARED_MATRIX)
+    k_count_contrib_all<<<grid_for(P->ncells_all * P->nd0, 256, 16), 256, 0, st>>>(
+        P->ncells_all, P->dofmap0, P->nd0, P->dofmap1 ? P->dofmap1 : P->dofmap0, P->nd1, csr->row_ptr, csr->cols, total);
+  else
+    k_count_contrib<<<grid_for(P->ncells * P->nd0, 256, 16), 256, 0, st>>>(P->ncells, P->cells, P->dofmap0, P->nd0,
+                                                                           P->nd1, csr->row_ptr, P->pos, P->pos_stride,
+                                                                           P->pos_bytes, total);
   BFX_CHECK_LAUNCH();
 
   // ---- pass A: sizes; scans; pass B: write

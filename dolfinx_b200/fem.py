@@ -399,7 +399,7 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
 CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 
 
-def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
+def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=False):
     """Assembly strategy of a cell integral: the caller's choice, else the aggregated kernel of the
     element where it has one (chunk-aggregated for the P1 kernels, row-gather for Q1 elasticity; the
     plan's lists are built once, on first use), else fp64 REDs."""
@@ -418,6 +418,8 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy):
         if want == _lib.ASM_CHUNKED:
             V0, V1 = form.function_spaces
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
+            if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
+                flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
         else:
             st = _lib.lib.bfx_asm_build_rowgather(plan, _lib.current_stream())
@@ -554,18 +556,24 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
     if any(itype != IntegralType.cell for (itype, _), _ in items):
         raise NotImplementedError("overlapped assembly handles cell integrals")
 
+    was_zero = A._is_zero
+    vals = A.data  # (a pending set_value(0) is written here)
+
     def run(tag_index):
         for (itype, ident), integ in items:
             cells = _boundary_interior_cells(a, integ)[tag_index]
             if cells.numel() == 0:
                 continue
             plan = _asm_plan(a, integ, itype, A, subset=(("bnd", "int")[tag_index], cells))
-            strat = _matrix_strategy(a, integ, plan, strategy)
+            strat = _matrix_strategy(a, integ, plan, strategy, shared=True)
+            # on a zeroed matrix both launches may overwrite: their chunk plans treat an entry as complete only
+            # if no cell outside the chunk touches it (CHUNKS_SHARED_MATRIX); everything else is added
+            mode = _lib.VALUES_OVERWRITE if (was_zero and strat == _lib.ASM_CHUNKED and len(items) == 1) else _lib.VALUES_ADD
             cf = _coeffs_for(a, integ, None)
             _lib.check(_lib.lib.bfx_assemble_matrix_cells(
                 plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
-                None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(), strat,
-                _lib.VALUES_ADD, _lib.current_stream()))
+                None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, vals.data_ptr(), strat,
+                mode, _lib.current_stream()))
 
     try:
         run(0)

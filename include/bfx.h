@@ -203,6 +203,10 @@ extern "C"
    * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
   enum
   {
+    BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
+                                     zero-fill and this plan's launch (boundary/interior split): an entry counts as
+                                     complete only if EVERY cell of the dofmap that touches it lies in one chunk of this
+                                     plan, so BFX_VALUES_OVERWRITE never overwrites another launch's contribution */
     BFX_CHUNKS_LINEAR_STAGING = 2, /* keep the padded linear staging layout (skip the bank colouring of the plan) */
     BFX_CHUNKS_SYMMETRIC = 1 /* symmetric bilinear form on one space (block size 1): stage the upper triangle of the
                                 element matrix only and update the (i,j)/(j,i) CSR entries from one sum; a call whose
