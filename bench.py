@@ -40,6 +40,16 @@ CONFIGS = {
 }
 
 
+def measured_traffic(config, strategy, n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get(f"{config}:{strategy}:{n}")
+        return None if t is None else t["bytes"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -272,7 +282,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -292,7 +302,31 @@ def workload_config(args, world):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version) must not add lines to stdout: everything but the result line goes to
+    stderr; emit() writes the one JSON line to the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -508,7 +542,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "kernel": f"assemble_cells_matrix[{args.config},{strat_name}]",
-                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": measured_traffic(args.config, strat_name, n),
                          "peak_source": peak_src, "alg_bytes_per_launch": b_asm, "kernel_ms": ms_kernel},
             "cpu_baseline": cpu,
             "e2e": e2e,
@@ -521,7 +556,7 @@ def main():
             "setup_s": {"mesh": t_mesh, "sparsity+matrix": t_pattern, "assembly_plan+first_call": t_plan},
             "chunk_plan": plan_info,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -531,6 +531,158 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Blocked rows fed by TMA: persistent CTAs stream the contiguous (cols, values) range of a tile of TR block
+// rows into shared memory with cp.async.bulk (two stages, like k_spmv_tma); the blocks land in their
+// storage layout (BS2 consecutive scalars, odd stride for 3x3: lane-per-block reads are conflict free),
+// so the per-lane staging loads/stores of k_spmv_blocked disappear from the LSU pipe.  One warp per block
+// row of the tile, one lane per block, shuffle reduction per row.
+constexpr int SPMV_BTMA_CAP = 480; // blocks per stage (multiple of 4)
+constexpr int SPMV_BTMA_TR = 16;   // block rows per tile
+
+template <int BS0, int BS1>
+__global__ void __launch_bounds__(256)
+    k_spmv_blocked_tma(int32_t n_rows, int64_t nnz_total, const int64_t* __restrict__ row_ptr,
+                       const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
+                       const int32_t* __restrict__ cols, const double* __restrict__ values,
+                       const double* __restrict__ x, double* __restrict__ y)
+{
+  constexpr int BS2 = BS0 * BS1, TR = SPMV_BTMA_TR, CAP = SPMV_BTMA_CAP;
+  static_assert((BS2 * 8 * 2) % 16 == 0, "two blocks are a whole number of 16-byte granules");
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  double* s_val = reinterpret_cast<double*>(sp_raw);                                      // [2][CAP * BS2]
+  int32_t* s_col = reinterpret_cast<int32_t*>(sp_raw + 2 * (size_t)CAP * BS2 * sizeof(double)); // [2][CAP]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sp_raw + 2 * (size_t)CAP * (BS2 * sizeof(double) + sizeof(int32_t)));
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ntiles = ((int64_t)n_rows + TR - 1) / TR;
+  if (threadIdx.x == 0)
+  {
+    sp_mbar_init(&bar[0], 1);
+    sp_mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto load_tile = [&](SpmvChunkIt& it)
+  {
+    if (it.tile < ntiles)
+    {
+      const int64_t start = row_ptr[it.tile * TR];
+      it.end = row_ptr[min((it.tile + 1) * TR, (int64_t)n_rows)];
+      it.base = start & ~int64_t(3);
+    }
+  };
+  auto advance = [&](SpmvChunkIt& it)
+  {
+    it.base += CAP;
+    if (it.base >= it.end)
+    {
+      it.tile += gridDim.x;
+      load_tile(it);
+    }
+  };
+  auto tma_blocks = [&](const SpmvChunkIt& it) -> int64_t
+  {
+    const int64_t lim = min(it.end, it.base + CAP);
+    const int64_t want = (lim - it.base + 3) & ~int64_t(3);
+    const int64_t avail = (nnz_total - it.base) & ~int64_t(3);
+    return max((int64_t)0, min(want, avail));
+  };
+  auto issue = [&](const SpmvChunkIt& it, int stage)
+  {
+    const uint32_t n = (uint32_t)tma_blocks(it);
+    sp_mbar_expect_tx(&bar[stage], n * (uint32_t)(4 + BS2 * 8));
+    if (n)
+    {
+      sp_bulk_g2s(s_col + stage * CAP, cols + it.base, n * 4u, &bar[stage]);
+      sp_bulk_g2s(s_val + (size_t)stage * CAP * BS2, values + it.base * BS2, n * (uint32_t)(BS2 * 8), &bar[stage]);
+    }
+  };
+
+  SpmvChunkIt cons, prod;
+  cons.tile = blockIdx.x, cons.base = 0, cons.end = 0;
+  load_tile(cons);
+  prod = cons;
+  if (threadIdx.x == 0 && prod.tile < ntiles)
+    issue(prod, 0);
+  if (prod.tile < ntiles)
+    advance(prod);
+  if (threadIdx.x == 0 && prod.tile < ntiles)
+    issue(prod, 1);
+  if (prod.tile < ntiles)
+    advance(prod);
+
+  // each warp owns rows wib, wib + 8 of the tile; partial sums live across the chunks of a tile
+  double acc[TR / 8][BS0];
+#pragma unroll
+  for (int s = 0; s < TR / 8; ++s)
+#pragma unroll
+    for (int k = 0; k < BS0; ++k)
+      acc[s][k] = 0.0;
+  for (uint32_t c = 0; cons.tile < ntiles; ++c)
+  {
+    const int stage = c & 1;
+    const int64_t lim = min(cons.end, cons.base + CAP);
+    const bool last = cons.base + CAP >= cons.end;
+    sp_mbar_wait(&bar[stage], (c >> 1) & 1);
+    double* sv = s_val + (size_t)stage * CAP * BS2;
+    int32_t* sc = s_col + stage * CAP;
+    const int64_t got = cons.base + tma_blocks(cons);
+    if (got < lim)
+    {
+      for (int64_t k = got * BS2 + threadIdx.x; k < lim * BS2; k += blockDim.x)
+        sv[k - cons.base * BS2] = values[k];
+      for (int64_t k = got + threadIdx.x; k < lim; k += blockDim.x)
+        sc[k - cons.base] = cols[k];
+      __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < TR / 8; ++s)
+    {
+      const int64_t row = cons.tile * TR + wib + 8 * s;
+      if (row < n_rows)
+      {
+        const int64_t rb = row_begin[row], re = row_end[row];
+        const int64_t lo = max(rb, cons.base), hi = min(re, lim);
+        for (int64_t j0 = lo; j0 < hi; j0 += 32)
+        {
+          const int64_t j = j0 + lane;
+          if (j < hi)
+          {
+            const int o = (int)(j - cons.base);
+            const int64_t col = sc[o];
+            double xv[BS1];
+#pragma unroll
+            for (int k1 = 0; k1 < BS1; ++k1)
+              xv[k1] = __ldg(x + col * BS1 + k1);
+#pragma unroll
+            for (int k0 = 0; k0 < BS0; ++k0)
+#pragma unroll
+              for (int k1 = 0; k1 < BS1; ++k1)
+                acc[s][k0] = fma(sv[o * BS2 + k0 * BS1 + k1], xv[k1], acc[s][k0]);
+          }
+        }
+        if (last)
+        {
+#pragma unroll
+          for (int k = 0; k < BS0; ++k)
+          {
+            const double v = warp_sum(acc[s][k]);
+            if (lane == 0)
+              y[row * BS0 + k] += v;
+            acc[s][k] = 0.0;
+          }
+        }
+      }
+    }
+    __syncthreads(); // every warp is done with this stage: it can be refilled
+    if (threadIdx.x == 0 && prod.tile < ntiles)
+      issue(prod, stage);
+    if (prod.tile < ntiles)
+      advance(prod);
+    advance(cons);
+  }
+}
+
 // Runtime block sizes (fallback; k0 outermost like the reference loop)
 __global__ void __launch_bounds__(256)
     k_spmv_generic(int32_t n_rows, const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
@@ -919,6 +1071,60 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
   }
   else
   {
+    // bs = 3 (elasticity): two kernels, the faster one is kept per matrix (timed once, like the bs = 1 variants).
+    // The TMA variant reads whole rows (full / diagonal part), not the row-list form of the off-diagonal pass.
+    if (A->bs0 == 3 && A->bs1 == 3 && !row_list)
+    {
+      auto launch3 = [&](int variant, double* yy)
+      {
+        if (variant == 1)
+        {
+          const size_t smem = 2 * (size_t)SPMV_BTMA_CAP * (9 * 8 + 4) + 64;
+          cudaFuncSetAttribute(k_spmv_blocked_tma<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          const int64_t ntiles = ((int64_t)n_launch + SPMV_BTMA_TR - 1) / SPMV_BTMA_TR;
+          const unsigned g = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 3);
+          k_spmv_blocked_tma<3, 3><<<g, 256, smem, st>>>(n_launch, A->nnz, A->row_ptr, rb, re, A->cols, values, x, yy);
+        }
+        else
+          k_spmv_blocked<3, 3><<<grid_for((int64_t)n_launch * 32, 256, 32), 256, 0, st>>>(n_launch, rb, re, A->cols,
+                                                                                           values, x, yy, nullptr);
+      };
+      if (A->spmv_variant < 0)
+      {
+        double* scratch = nullptr;
+        cudaEvent_t e0, e1;
+        int best_v = 0;
+        if (cudaMalloc(&scratch, sizeof(double) * 3 * (size_t)n_launch) == cudaSuccess
+            && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+        {
+          float best = 1e30f;
+          for (int v = 0; v < 2; ++v)
+          {
+            float ms = 1e30f;
+            for (int rep = 0; rep < 3; ++rep)
+            {
+              cudaEventRecord(e0, st);
+              launch3(v, scratch);
+              cudaEventRecord(e1, st);
+              cudaEventSynchronize(e1);
+              float t = 0;
+              cudaEventElapsedTime(&t, e0, e1);
+              ms = t < ms ? t : ms;
+            }
+            if (ms < best)
+              best = ms, best_v = v;
+          }
+          cudaEventDestroy(e0);
+          cudaEventDestroy(e1);
+        }
+        cudaFree(scratch);
+        const_cast<bfx_csr*>(A)->spmv_variant = best_v;
+        BFX_CHECK_LAUNCH();
+      }
+      launch3(A->spmv_variant > 1 ? 1 : A->spmv_variant, y);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
     const unsigned grid = grid_for((int64_t)n_launch * 32, 256, 32);
 #define BLK(a, b)                                                                                                    \
   if (A->bs0 == a && A->bs1 == b)                                                                                    \

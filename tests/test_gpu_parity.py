@@ -419,9 +419,10 @@ def test_spmv_assembled(bfx, oracle, kind):
     yref = y0.copy()
     oracle.spmv(data, A.indptr[:-1], A.indptr[1:], A.indices, xh, yref, p.bs, p.bs)
     assert np.max(np.abs(y.array.cpu().numpy() - yref)) <= TOL * np.max(np.abs(yref))
-    if p.bs == 1:
-        # every bs = 1 kernel variant (stream, rows, TMA-pipelined rows), not only the one the timing picked
-        for variant in (0, 1, 2):
+    if p.bs in (1, 3):
+        # every kernel variant (bs = 1: stream, rows, TMA-pipelined rows; bs = 3: warp-staged, TMA-fed), not only
+        # the one the timing picked
+        for variant in ((0, 1, 2) if p.bs == 1 else (0, 1)):
             bfx.lib.check(bfx.lib.lib.bfx_csr_set_spmv_variant(A._csr, variant))
             y.array.copy_(torch.from_numpy(y0))
             A.mult(x, y)
