@@ -42,6 +42,9 @@ K_ELASTICITY_Q1_HEX_A = 10
 K_LOAD_Q1_HEX_L = 11
 K_FACET_LOAD_P1_TET_L = 12
 K_FACET_MASS_P1_TET_A = 13
+K_ACTION_POISSON_P1_TET_L = 15
+K_ACTION_POISSON_P2_TET_L = 16
+K_L2NORM2_P1_TET_M = 17
 
 ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
@@ -109,6 +112,7 @@ _SIGS = {
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),
+    "bfx_assemble_scalar_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, C.POINTER(f64), vp], ci),
     "bfx_lift_bc_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp, vp, vp, f64, vp], ci),
     "bfx_assemble_matrix_facets": ([vp, ci, vp, vp, i64, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),
     "bfx_assemble_vector_facets": ([vp, ci, vp, vp, i64, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),

@@ -156,6 +156,40 @@ __global__ void __launch_bounds__(128) k_vector_cells(const AsmArgs a)
   }
 }
 
+// functional (rank 0): per-thread cell values, block reduction, one fp64 atomic per block
+template <class E>
+__global__ void __launch_bounds__(256) k_scalar_cells(const AsmArgs a, double* __restrict__ result)
+{
+  constexpr int NX = E::NX;
+  double acc = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t cell = a.cells ? a.cells[e] : (int32_t)e;
+    int32_t xd[NX];
+    load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
+    double xc[NX][3];
+    gather_coords<NX>(a.x, xd, xc);
+    double w[E::WSIZE > 0 ? E::WSIZE : 1];
+    load_w<E>(a, e, cell, w);
+    typename E::Geo g;
+    E::prepare(g, xc, w, a.constants, 0);
+    acc += E::scalar(g);
+  }
+  __shared__ double part[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0)
+    part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8)
+  {
+    double v = part[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1)
+      v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0)
+      atomicAdd(result, v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Q1 hexahedron linear elasticity (bs = 3): 64 threads per cell, one per (i, j) node pair.
 // Phase 1: 8 threads per cell evaluate K = J^{-1}, |det J| and the 8 physical gradients at the
@@ -830,6 +864,8 @@ int dispatch_vector(int kernel_id, const AsmArgs& a, cudaStream_t st)
   case BFX_K_LOAD_P2_TET_L: return launch_vector<el::LoadP2Tet>(a, st);
   case BFX_K_LOAD_Q1_HEX_L: return launch_vector<el::LoadQ1Hex>(a, st);
   case BFX_K_FACET_LOAD_P1_TET_L: return launch_vector<el::FacetLoadP1Tet>(a, st);
+  case BFX_K_ACTION_POISSON_P1_TET_L: return launch_vector<el::ActionOf<el::PoissonP1Tet>>(a, st);
+  case BFX_K_ACTION_POISSON_P2_TET_L: return launch_vector<el::ActionOf<el::PoissonP2Tet>>(a, st);
   default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a linear-form kernel", kernel_id);
   }
 }
@@ -839,7 +875,8 @@ const bfx_kernel_info_t KINFO[BFX_K_COUNT] = {
     {3, 3, 1, 2, 0, 0, 0},  {3, 3, 1, 1, 0, 0, 0},  {3, 3, 1, 2, 3, 0, 0},  {3, 3, 1, 1, 3, 0, 0},
     {3, 3, 1, 2, 0, 0, 1},  {3, 3, 1, 1, 0, 1, 1},  {4, 4, 1, 2, 0, 1, 0},  {4, 4, 1, 1, 4, 0, 0},
     {4, 10, 1, 2, 0, 1, 0}, {4, 10, 1, 1, 10, 0, 0}, {8, 8, 3, 2, 0, 2, 0}, {8, 8, 3, 1, 24, 0, 0},
-    {4, 4, 1, 1, 4, 0, 1},  {4, 4, 1, 2, 0, 0, 1}};
+    {4, 4, 1, 1, 4, 0, 1},  {4, 4, 1, 2, 0, 0, 1},  {0, 0, 0, -1, 0, 0, 0}, {4, 4, 1, 1, 4, 1, 0},
+    {4, 10, 1, 1, 10, 1, 0}, {4, 4, 1, 0, 4, 0, 0}};
 
 int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, const bfx_coeffs_t* coeffs,
                 const double* constants, int n_constants, AsmArgs& a, bool need_csr = true)
@@ -1128,6 +1165,37 @@ int bfx_assemble_vector_cells(const bfx_asm_t* P, int kernel_id, const double* x
   a.n = P->ncells;
   a.b = b;
   return dispatch_vector(kernel_id, a, S(stream));
+}
+
+int bfx_assemble_scalar_cells(const bfx_asm_t* P, int kernel_id, const double* x, const bfx_coeffs_t* coeffs,
+                              const double* constants, int n_constants, double* result_host, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 0, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(result_host, "bfx_assemble_scalar_cells: null result");
+  cudaStream_t st = S(stream);
+  a.cells = P->cells;
+  a.n = P->ncells;
+  double* d_res = nullptr;
+  BFX_CUDA(cudaMalloc(&d_res, sizeof(double)));
+  BFX_CUDA(cudaMemsetAsync(d_res, 0, sizeof(double), st));
+  if (a.n > 0)
+  {
+    switch (kernel_id)
+    {
+    case BFX_K_L2NORM2_P1_TET_M:
+      k_scalar_cells<el::L2Norm2P1Tet><<<grid_for(a.n, 256, 8), 256, 0, st>>>(a, d_res);
+      break;
+    default: cudaFree(d_res); return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a functional kernel", kernel_id);
+    }
+  }
+  BFX_CUDA(cudaMemcpyAsync(result_host, d_res, sizeof(double), cudaMemcpyDeviceToHost, st));
+  BFX_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_res);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
 }
 
 int bfx_assemble_vector_facets(const bfx_asm_t* P, int kernel_id, const double* x, const int32_t* entities,

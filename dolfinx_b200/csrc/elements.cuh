@@ -433,6 +433,62 @@ struct FacetMassP1Tet : TetBase
   }
 };
 
+// action(a, ui): the element matrix of a bilinear kernel E applied to the coefficient dofs,
+// be_i = sum_j A_ij w_j (cpp/demo/poisson_matrix_free/poisson.py: M = action(a, ui)).  The matrix-free operator
+// of SURVEY.md §8f: one assemble_vector per operator application instead of assembling and reading the matrix.
+template <class E>
+struct ActionOf
+{
+  static constexpr int NX = E::NX, ND = E::ND, BS = E::BS, WSIZE = E::ND * E::BS, WND = E::ND, WBS = E::BS,
+                       CSIZE = E::CSIZE, RANK = 1;
+  static constexpr bool FACET = false;
+  struct Geo
+  {
+    typename E::Geo g;
+    double u[E::ND * E::BS];
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[NX][3], const double* w, const double* c, int lf)
+  {
+    E::prepare(g.g, xc, nullptr, c, lf);
+#pragma unroll
+    for (int j = 0; j < ND * BS; ++j)
+      g.u[j] = w[j];
+  }
+  static BFX_DI void vec(const Geo& g, double (&out)[E::ND * E::BS])
+  {
+#pragma unroll
+    for (int i = 0; i < ND * BS; ++i)
+    {
+      double row[E::ND * E::BS];
+      E::row(g.g, i, row);
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < ND * BS; ++j)
+        acc = fma(row[j], g.u[j], acc);
+      out[i] = acc;
+    }
+  }
+};
+
+// M = w^2 dx, w in P1 on tetrahedra (functional, RANK 0): |det| w^T Mhat w, Mhat = (1 + delta_ij) / 120
+struct L2Norm2P1Tet : TetBase
+{
+  static constexpr int ND = 4, BS = 1, WSIZE = 4, WND = 4, WBS = 1, CSIZE = 0, RANK = 0;
+  static constexpr bool FACET = false;
+  struct Geo
+  {
+    double v;
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[4][3], const double* w, const double*, int)
+  {
+    double n[4][3];
+    const double det = fabs(normals(xc, n));
+    const double s = w[0] + w[1] + w[2] + w[3];
+    g.v = det * (s * s + w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]) * (1.0 / 120.0);
+  }
+  static BFX_DI double scalar(const Geo& g) { return g.v; }
+};
+
 // ---- hexahedra (Q1, tensor node order, x fastest) ------------------------------------------------
 struct HexQ1
 {

@@ -371,7 +371,8 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
     if key in form._plans:
         return form._plans[key][0]
     mesh = form.mesh
-    V0 = form.function_spaces[0]
+    # a functional (rank 0) has no test space: its plan carries the dofmap of its (first) coefficient
+    V0 = form.function_spaces[0] if form.rank > 0 else form.coefficients[0].function_space
     dm0 = V0.dofmap
     dm1 = form.function_spaces[1].dofmap if form.rank == 2 else None
     if subset is not None:
@@ -584,6 +585,27 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
         raise _translate(e) from e
     A._is_zero = False
     return A
+
+
+def assemble_scalar(M: Form, constants=None, coeffs=None) -> float:
+    """fem::assemble_scalar(M) — fem/assembler.h:173-213: the functional summed over the owned cells of this
+    rank (the caller reduces over ranks, like the reference: cpp/demo/poisson_matrix_free/main.cpp:241-247)."""
+    from . import _lib
+
+    assert M.rank == 0
+    consts = pack_constants(M) if constants is None else np.asarray(constants, dtype=np.float64)
+    carr, nc = _lib.constants_array(consts)
+    total = 0.0
+    for (itype, ident), integ in M._integrals.items():
+        if itype != IntegralType.cell:
+            raise NotImplementedError(f"assemble_scalar: integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
+        plan = _asm_plan(M, integ, itype, None)
+        cf = _coeffs_for(M, integ, None if coeffs is None else coeffs[(itype, ident)])
+        out = C.c_double(0.0)
+        _lib.check(_lib.lib.bfx_assemble_scalar_cells(plan, integ.kernel, M.mesh.x.data_ptr(), C.byref(cf), carr, nc,
+                                                      C.byref(out), _lib.current_stream()))
+        total += out.value
+    return total
 
 
 def assemble_vector(b, L: Form, constants=None, coeffs=None):

@@ -402,6 +402,49 @@ def norm(x: Vector, type: Norm = Norm.l2) -> float:
     raise RuntimeError("Norm type not supported")
 
 
+def axpy(r: Vector, alpha: float, x: Vector, y: Vector):
+    """r = alpha x + y on the whole local array (cpp/demo/poisson_matrix_free/main.cpp:60-69)."""
+    from . import _lib
+
+    if r is y:
+        _lib.check(_lib.lib.bfx_axpy(r.array.numel(), float(alpha), x.array.data_ptr(), r.array.data_ptr(), _lib.current_stream()))
+    elif r is x:
+        r.array.mul_(float(alpha)).add_(y.array)
+    else:
+        r.array.copy_(y.array)
+        _lib.check(_lib.lib.bfx_axpy(r.array.numel(), float(alpha), x.array.data_ptr(), r.array.data_ptr(), _lib.current_stream()))
+
+
+def cg(x: Vector, b: Vector, action, kmax: int = 50, rtol: float = 1e-8) -> int:
+    """Conjugate gradients with an operator given by its action, everything on the device
+    (linalg::cg of cpp/demo/poisson_matrix_free/main.cpp:84-132, same update order).
+    ``action(p, y)`` computes y = A p; ghost values of x and b must be up to date.  Returns the iterations."""
+    torch = _torch()
+    r = Vector(b.index_map, b.bs, torch.empty_like(b.array))
+    y = Vector(b.index_map, b.bs, torch.empty_like(b.array))
+    action(x, y)
+    axpy(r, -1.0, y, b)
+    p = Vector(b.index_map, b.bs, r.array.clone())
+    rnorm0 = squared_norm(r)
+    rnorm = rnorm0
+    if rnorm0 == 0.0:
+        return 0
+    k = 0
+    while k < kmax:
+        k += 1
+        action(p, y)
+        alpha = rnorm / inner_product(p, y)
+        axpy(x, alpha, p, x)
+        axpy(r, -alpha, y, r)
+        rnorm_new = squared_norm(r)
+        beta = rnorm_new / rnorm
+        rnorm = rnorm_new
+        if rnorm / rnorm0 < rtol * rtol:
+            break
+        axpy(p, beta, p, r)
+    return k
+
+
 # ---------------------------------------------------------------------------------------------
 # MatrixCSR
 # ---------------------------------------------------------------------------------------------

@@ -78,7 +78,12 @@ extern "C"
     BFX_K_LOAD_Q1_HEX_L = 11,       /* inner(f, v)*dx, f Q1 vector (bs=3) */
     BFX_K_FACET_LOAD_P1_TET_L = 12, /* inner(g, v)*ds, g P1 */
     BFX_K_FACET_MASS_P1_TET_A = 13, /* inner(u, v)*ds */
-    BFX_K_COUNT = 14
+    /* 14 is reserved (the oracle's 2x2x2-Gauss elasticity variant has this number) */
+    BFX_K_ACTION_POISSON_P1_TET_L = 15, /* action(a, ui), a = kappa*inner(grad u, grad v)*dx, P1: the matrix-free operator
+                                           of cpp/demo/poisson_matrix_free (poisson.py: M = action(a, ui)); w = ui */
+    BFX_K_ACTION_POISSON_P2_TET_L = 16, /* same, P2 */
+    BFX_K_L2NORM2_P1_TET_M = 17,        /* functional inner(w, w)*dx, w P1 (the error functional E of that demo) */
+    BFX_K_COUNT = 18
   };
 
   /* Static description of a kernel id: geometry nodes per cell, dofs per cell of test/trial space,
@@ -233,6 +238,11 @@ extern "C"
   int bfx_assemble_vector_cells(const bfx_asm_t* plan, int kernel_id, const double* x_dev,
                                 const bfx_coeffs_t* coeffs, const double* constants_host, int n_constants,
                                 double* b_dev, int strategy, bfx_stream_t stream);
+  /* fem::assemble_scalar over cells — fem/assembler.h:173-213 -> impl::assemble_cells fem/assemble_scalar_impl.h:32-60:
+   * *result_host = sum over the plan's cells of the functional kernel (rank 0); the caller reduces over ranks. */
+  int bfx_assemble_scalar_cells(const bfx_asm_t* plan, int kernel_id, const double* x_dev, const bfx_coeffs_t* coeffs,
+                                const double* constants_host, int n_constants, double* result_host,
+                                bfx_stream_t stream);
   /* impl::lift_bc — fem/assemble_vector_impl.h:361-414 through assemble_cells_matrix<true>
    * (cell skip has_bc, assemble_matrix_impl.h:27-34,139-143): b -= alpha * Ae (bc_values1 - x0) on marked columns. */
   int bfx_lift_bc_cells(const bfx_asm_t* plan, int kernel_id, const double* x_dev, const bfx_coeffs_t* coeffs,

@@ -497,6 +497,46 @@ static void k_facet_mass_p1_tet_A(double* A, const double* w, const double* c, c
   }
 }
 
+/* action(a, ui) of the Poisson forms (cpp/demo/poisson_matrix_free/poisson.py: M = action(a, ui)): the element
+ * matrix of `a` applied to the coefficient dofs w, be_i = sum_j A_ij w_j */
+static void k_action_poisson_p1_tet_L(double* b, const double* w, const double* c, const double* xc, const int* e,
+                                      const uint8_t* q, void* d)
+{
+  double A[16] = {0};
+  k_poisson_p1_tet_A(A, 0, c, xc, e, q, d);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      b[i] += A[4 * i + j] * w[j];
+}
+
+static void k_action_poisson_p2_tet_L(double* b, const double* w, const double* c, const double* xc, const int* e,
+                                      const uint8_t* q, void* d)
+{
+  double A[100] = {0};
+  k_poisson_p2_tet_A(A, 0, c, xc, e, q, d);
+  for (int i = 0; i < 10; ++i)
+    for (int j = 0; j < 10; ++j)
+      b[i] += A[10 * i + j] * w[j];
+}
+
+/* M = w^2 dx, w in P1 (the error functional E = (usol - uexact)^2 dx of poisson_matrix_free/poisson.py with
+ * w = usol - uexact), by a degree-3 rule */
+static void k_l2norm2_p1_tet_M(double* m, const double* w, const double* c, const double* xc, const int* e,
+                               const uint8_t* q, void* d)
+{
+  (void)c; (void)e; (void)q; (void)d;
+  double K[3][3];
+  double det = fabs(tet_geometry(xc, K));
+  double pts[64][4];
+  int np = tet_rule(3, pts);
+  for (int p = 0; p < np; ++p)
+  {
+    const double X = pts[p][0], Y = pts[p][1], Z = pts[p][2];
+    const double v = w[0] * (1.0 - X - Y - Z) + w[1] * X + w[2] * Y + w[3] * Z;
+    m[0] += pts[p][3] * det * v * v;
+  }
+}
+
 /* --- hexahedra (Q1, tensor node order x fastest) --------------------------- */
 
 static void q1_hex_basis(const double* X, double phi[8], double dphi[8][3])
@@ -627,6 +667,9 @@ enum
   K_FACET_LOAD_P1_TET_L = 12,
   K_FACET_MASS_P1_TET_A = 13,
   K_ELASTICITY_Q1_HEX_A_G2 = 14, /* oracle-only variant: 2x2x2 Gauss */
+  K_ACTION_POISSON_P1_TET_L = 15,
+  K_ACTION_POISSON_P2_TET_L = 16,
+  K_L2NORM2_P1_TET_M = 17,
   K_COUNT
 };
 
@@ -649,6 +692,9 @@ static orc_kernel_t kernel_table(int id)
   case K_FACET_LOAD_P1_TET_L: return k_facet_load_p1_tet_L;
   case K_FACET_MASS_P1_TET_A: return k_facet_mass_p1_tet_A;
   case K_ELASTICITY_Q1_HEX_A_G2: return k_elasticity_q1_hex_A_g2;
+  case K_ACTION_POISSON_P1_TET_L: return k_action_poisson_p1_tet_L;
+  case K_ACTION_POISSON_P2_TET_L: return k_action_poisson_p2_tet_L;
+  case K_L2NORM2_P1_TET_M: return k_l2norm2_p1_tet_M;
   default: return 0;
   }
 }
@@ -840,6 +886,27 @@ int orc_assemble_vector(int kernel_id, const int32_t* x_dofmap, int nx, const do
   }
   free(be);
   free(cdofs);
+  return 0;
+}
+
+/* impl::assemble_cells of a functional (fem/assemble_scalar_impl.h:32-60): value += kernel(...) over the cells */
+int orc_assemble_scalar(int kernel_id, const int32_t* x_dofmap, int nx, const double* x, const int32_t* cells, int64_t n,
+                        const double* coeffs, int cstride, const double* constants, double* value)
+{
+  orc_kernel_t kernel = kernel_table(kernel_id);
+  if (!kernel)
+    return -2;
+  double* cdofs = (double*)malloc(sizeof(double) * 3 * nx);
+  double v = 0.0;
+  for (int64_t index = 0; index < n; ++index)
+  {
+    const int32_t* x_dofs = x_dofmap + (size_t)cells[index] * nx;
+    for (int i = 0; i < nx; ++i)
+      memcpy(cdofs + 3 * i, x + 3 * (size_t)x_dofs[i], 3 * sizeof(double));
+    kernel(&v, coeffs ? coeffs + (size_t)index * cstride : 0, constants, cdofs, 0, 0, 0);
+  }
+  free(cdofs);
+  *value = v;
   return 0;
 }
 

@@ -40,6 +40,9 @@ K_LOAD_Q1_HEX_L = 11
 K_FACET_LOAD_P1_TET_L = 12
 K_FACET_MASS_P1_TET_A = 13
 K_ELASTICITY_Q1_HEX_A_G2 = 14  # oracle-only: 2x2x2 Gauss variant
+K_ACTION_POISSON_P1_TET_L = 15
+K_ACTION_POISSON_P2_TET_L = 16
+K_L2NORM2_P1_TET_M = 17
 
 
 def build(fast: bool = False) -> str:
@@ -169,6 +172,20 @@ def assemble_vector(kernel_id, x_dofmap, x, cells, dmap, bs, b, coeffs=None, con
         C.c_int(bs), _p(coeffs, C.c_double), C.c_int(cstride), _p(constants, C.c_double), _p(b, C.c_double),
     )
     assert err == 0
+
+
+def assemble_scalar(kernel_id, x_dofmap, x, cells, coeffs=None, constants=None):
+    """fem::assemble_scalar over cells (fem/assemble_scalar_impl.h:32-60)."""
+    x_dofmap, cells = _i32(x_dofmap), _i32(cells)
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    cstride = 0 if coeffs is None else coeffs.shape[1]
+    out = C.c_double(0.0)
+    err = lib().orc_assemble_scalar(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(cells, C.c_int32), C.c_int64(len(cells)), _p(coeffs, C.c_double), C.c_int(cstride),
+        _p(constants, C.c_double), C.byref(out))
+    assert err == 0
+    return out.value
 
 
 def pack_coefficient(coeffs, offset, v, dofmap, bs, cells=None, entities=None):

@@ -504,3 +504,99 @@ def test_host_buffer_entry(bfx, oracle):
                                                      lib.current_stream()))
     pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([2.0]))
     assert P.row_scaled_error(out, ref, pat.offsets) <= TOL
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_matrix_free_action_and_cg(bfx, oracle, degree):
+    """SURVEY.md §8f rank 2, the flow of cpp/demo/poisson_matrix_free/main.cpp:150-247 on a tet box: the action
+    kernel M = action(a, ui) against the oracle and against the assembled matrix times u; the lifting by
+    assemble_vector(M) with ui = -g on the boundary; CG with the operator given by its action (all vectors on
+    the device) reproducing u = 1 + x^2 + 2 y^2 + 3 z^2 (exactly representable in P2; P1: against a direct solve
+    of the oracle-assembled system); the error functional through assemble_scalar."""
+    fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    if degree == 1:
+        p = P.tet_p1(6, numbering="random", seed=2)
+        kA, okA, kM, okM, kL, okL = (K.K_POISSON_P1_TET_A, oracle.K_POISSON_P1_TET_A, K.K_ACTION_POISSON_P1_TET_L,
+                                     oracle.K_ACTION_POISSON_P1_TET_L, K.K_LOAD_P1_TET_L, oracle.K_LOAD_P1_TET_L)
+    else:
+        p = P.tet_p2(4)
+        kA, okA, kM, okM, kL, okL = (K.K_POISSON_P2_TET_A, oracle.K_POISSON_P2_TET_A, K.K_ACTION_POISSON_P2_TET_L,
+                                     oracle.K_ACTION_POISSON_P2_TET_L, K.K_LOAD_P2_TET_L, oracle.K_LOAD_P2_TET_L)
+    msh, V = make_space(bfx, p)
+    dc = p.dof_coords
+    uex = 1.0 + dc[:, 0] ** 2 + 2 * dc[:, 1] ** 2 + 3 * dc[:, 2] ** 2
+    bdofs = np.flatnonzero(np.any((dc < 1e-12) | (dc > 1 - 1e-12), axis=1)).astype(np.int32)
+    u_D = fem.Function(V)
+    u_D.x.array.copy_(torch.from_numpy(uex))
+    bc = fem.DirichletBC(u_D, bdofs)
+    ui = fem.Function(V)
+    kappa = fem.Constant(1.0)
+    M = fem.Form([V], {fem.IntegralType.cell: [(0, kM, None, [0])]}, coefficients=[ui], constants=[kappa])
+    f = fem.Function(V)
+    f.x.array.fill_(-12.0)  # -laplace(u) = -12
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, kL, None, [0])]}, coefficients=[f])
+
+    # --- action kernel: oracle, and the assembled matrix applied to the same vector
+    w = np.random.default_rng(3).random(p.ndofs)
+    ui.x.array.copy_(torch.from_numpy(w))
+    y = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(y, M)
+    yref = P.oracle_assemble_vector(oracle, p, okM, coeff=(w, p.dofmap, 1), constants=np.array([1.0]))
+    assert np.max(np.abs(y.array.cpu().numpy() - yref)) <= TOL * np.max(np.abs(yref))
+    pat, Aref = P.oracle_assemble_matrix(oracle, p, okA, constants=np.array([1.0]))
+    Asp = sp.csr_matrix((Aref, pat.edges, pat.offsets), shape=(p.ndofs, p.ndofs))
+    assert np.max(np.abs(yref - Asp @ w)) <= 1e-11 * np.max(np.abs(yref))
+
+    # --- rhs with lifting through the action (main.cpp:185-200)
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    ui.x.array.zero_()
+    bc.set(ui.x.array, None, -1.0)
+    fem.assemble_vector(b, M)
+    b.scatter_reverse(la.InsertMode.add)
+    bc.set(b.array, None, 0.0)
+    b.scatter_forward()
+    bref = P.oracle_assemble_vector(oracle, p, okL, coeff=(np.full(p.ndofs, -12.0), p.dofmap, 1))
+    g = np.zeros(p.ndofs)
+    g[bdofs] = uex[bdofs]
+    bref = bref - Asp @ g
+    bref[bdofs] = 0.0
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= 1e-11 * np.max(np.abs(bref))
+
+    # --- operator action (main.cpp:207-226) and CG (:84-132), all on the device
+    def action(xv, yv):
+        yv.array.zero_()
+        ui.x.array.copy_(xv.array)
+        fem.assemble_vector(yv, M)
+        bc.set(yv.array, None, 0.0)
+        yv.scatter_reverse(la.InsertMode.add)
+        yv.scatter_forward()
+
+    u = fem.Function(V)
+    its = la.cg(u.x, b, action, kmax=400, rtol=1e-10)
+    assert 0 < its < 400
+    bc.set(u.x.array, None, 1.0)
+    uh = u.x.array.cpu().numpy()
+    # direct solve of the same system from the oracle-assembled matrix
+    free = np.setdiff1d(np.arange(p.ndofs), bdofs)
+    uref = g.copy()
+    uref[free] = spl.spsolve(Asp[free][:, free].tocsc(), bref[free])
+    assert np.max(np.abs(uh - uref)) <= 1e-7 * np.max(np.abs(uref))
+    if degree == 2:
+        assert np.max(np.abs(uh - uex)) <= 1e-7  # the quadratic is in the P2 space
+
+    # --- error functional E = (usol - uexact)^2 dx (main.cpp:232-247), P1 only (the functional kernel is P1)
+    if degree == 1:
+        d = fem.Function(V)
+        diff = uh - uex
+        d.x.array.copy_(torch.from_numpy(diff))
+        E = fem.Form([], {fem.IntegralType.cell: [(0, K.K_L2NORM2_P1_TET_M, None, [0])]}, coefficients=[d], mesh=msh)
+        err2 = fem.assemble_scalar(E)
+        cells = np.arange(len(p.dofmap), dtype=np.int32)
+        coeffs = np.zeros((len(cells), 4))
+        oracle.pack_coefficient(coeffs, 0, diff, p.dofmap, 1, cells=cells)
+        ref2 = oracle.assemble_scalar(oracle.K_L2NORM2_P1_TET_M, p.x_dofmap, p.x, cells, coeffs=coeffs)
+        assert err2 == pytest.approx(ref2, rel=1e-11) and err2 > 0

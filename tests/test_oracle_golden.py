@@ -266,3 +266,28 @@ def test_restatement_vs_reference_matrix_csr_impl(oracle, bs):
     assert ref.ref_insert(0, bs[0], bs[1], d.ctypes.data_as(C.c_void_p), C.c_size_t(len(d)), cols.ctypes.data_as(C.c_void_p),
                           C.c_size_t(len(cols)), row_ptr.ctypes.data_as(C.c_void_p), C.c_size_t(len(row_ptr)),
                           x.ctypes.data_as(C.c_void_p), xr.ctypes.data_as(C.c_void_p), 1, xc.ctypes.data_as(C.c_void_p), 1, 1) == -1
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_action_and_functional_kernels(oracle, degree):
+    """The matrix-free kernels of SURVEY.md §8f (cpp/demo/poisson_matrix_free/poisson.py): action(a, ui) equals the
+    assembled matrix times ui; it annihilates constants; the functional inner(w, w)*dx integrates the P1
+    interpolant of x0 over the unit cube to 1/3 (and a constant c to c^2)."""
+    O = oracle
+    p = P.tet_p1(4, numbering="random", seed=1) if degree == 1 else P.tet_p2(3)
+    kA, kM = ((O.K_POISSON_P1_TET_A, O.K_ACTION_POISSON_P1_TET_L) if degree == 1
+              else (O.K_POISSON_P2_TET_A, O.K_ACTION_POISSON_P2_TET_L))
+    pat, A = P.oracle_assemble_matrix(O, p, kA, constants=np.array([2.0]))
+    Asp = sp.csr_matrix((A, pat.edges, pat.offsets), shape=(p.ndofs, p.ndofs))
+    w = np.random.default_rng(0).random(p.ndofs)
+    y = P.oracle_assemble_vector(O, p, kM, coeff=(w, p.dofmap, 1), constants=np.array([2.0]))
+    assert np.max(np.abs(y - Asp @ w)) <= 1e-12 * np.max(np.abs(y))
+    y1 = P.oracle_assemble_vector(O, p, kM, coeff=(np.ones(p.ndofs), p.dofmap, 1), constants=np.array([2.0]))
+    assert np.max(np.abs(y1)) <= 1e-12 * np.max(np.abs(A))
+    if degree == 1:
+        cells = np.arange(len(p.dofmap), dtype=np.int32)
+        for vals, expect in ((p.dof_coords[:, 0], 1.0 / 3.0), (np.full(p.ndofs, 1.5), 2.25)):
+            coeffs = np.zeros((len(cells), 4))
+            O.pack_coefficient(coeffs, 0, vals, p.dofmap, 1, cells=cells)
+            m = O.assemble_scalar(O.K_L2NORM2_P1_TET_M, p.x_dofmap, p.x, cells, coeffs=coeffs)
+            assert m == pytest.approx(expect, rel=1e-13)
