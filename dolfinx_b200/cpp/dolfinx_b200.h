@@ -739,6 +739,41 @@ public:
     _plans[pk] = p;
     return p;
   }
+  /// scatter-add strategy of a cell integral of a bilinear form: the aggregated kernel of the element where it
+  /// has one (built once per plan: chunk lists for the P1/P2 Poisson kernels, the transposed dofmap for Q1
+  /// elasticity), else one fp64 RED per contribution
+  int matrix_strategy(std::pair<IntegralType, int> key, const bfx_csr_t* csr) const
+  {
+    auto pk = std::make_pair(key, (const void*)csr);
+    if (auto it = _strategies.find(pk); it != _strategies.end())
+      return it->second;
+    bfx_asm_t* p = plan(key, csr);
+    const int kernel = _integrals.at(key).kernel;
+    int strategy = BFX_ASM_ATOMIC;
+    if (key.first == IntegralType::cell and rank() == 2)
+    {
+      const bool one_space = _function_spaces[0] == _function_spaces[1] and _function_spaces[0]->dofmap()->bs() == 1;
+      const bool chunked = kernel == BFX_K_LAPLACE_P1_TRI_A or kernel == BFX_K_MASS_COEFF_P1_TRI_A
+                           or kernel == BFX_K_POISSON_P1_TET_A or kernel == BFX_K_POISSON_P2_TET_A;
+      int st = BFX_ERR_UNSUPPORTED;
+      if (chunked)
+      {
+        st = bfx_asm_build_chunks(p, mesh()->x.data(), one_space ? BFX_CHUNKS_SYMMETRIC : 0, nullptr);
+        if (st == BFX_OK)
+          strategy = BFX_ASM_CHUNKED;
+      }
+      else if (kernel == BFX_K_ELASTICITY_Q1_HEX_A)
+      {
+        st = bfx_asm_build_rowgather(p, nullptr);
+        if (st == BFX_OK)
+          strategy = BFX_ASM_ROWGATHER;
+      }
+      if (st != BFX_OK and st != BFX_ERR_UNSUPPORTED)
+        check(st);
+    }
+    _strategies[pk] = strategy;
+    return strategy;
+  }
 
 private:
   std::vector<std::shared_ptr<const FunctionSpace>> _function_spaces;
@@ -746,6 +781,7 @@ private:
   std::vector<std::shared_ptr<const Function<T>>> _coefficients;
   std::vector<std::shared_ptr<const Constant<T>>> _constants;
   mutable std::map<std::pair<std::pair<IntegralType, int>, const void*>, bfx_asm_t*> _plans;
+  mutable std::map<std::pair<std::pair<IntegralType, int>, const void*>, int> _strategies;
 };
 
 /// fem::pack_constants (fem/pack.h:578-619)
@@ -866,7 +902,10 @@ void assemble_matrix(la::MatrixCSR<T>& A, const Form<T>& a,
                      const std::vector<std::reference_wrapper<const DirichletBC<T>>>& bcs = {})
 {
   auto mk0 = impl::markers(*a.function_spaces()[0], bcs);
-  auto mk1 = impl::markers(*a.function_spaces()[1], bcs);
+  // one marker array when test and trial space coincide (what the symmetric chunk plan requires)
+  const bool one_space = a.function_spaces()[0] == a.function_spaces()[1];
+  auto mk1_own = one_space ? nullptr : impl::markers(*a.function_spaces()[1], bcs);
+  auto* mk1 = one_space ? mk0.get() : mk1_own.get();
   const std::vector<T> c = pack_constants(a);
   for (auto& [key, id] : a.integrals())
   {
@@ -875,7 +914,7 @@ void assemble_matrix(la::MatrixCSR<T>& A, const Form<T>& a,
     if (key.first == IntegralType::cell)
       check(bfx_assemble_matrix_cells(plan, id.kernel, a.mesh()->x.data(), mk0 ? mk0->data() : nullptr,
                                       mk1 ? mk1->data() : nullptr, &cf, c.data(), (int)c.size(), A.values().data(),
-                                      BFX_ASM_ATOMIC, BFX_VALUES_ADD, nullptr));
+                                      a.matrix_strategy(key, A.csr()), BFX_VALUES_ADD, nullptr));
     else if (key.first == IntegralType::exterior_facet)
     {
       DeviceArray<std::int32_t> ent{std::span<const std::int32_t>(id.entities)};
