@@ -48,6 +48,8 @@ K_L2NORM2_P1_TET_M = 17
 
 ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
+# linear-form kernels with the grouped (one RED per distinct dof of 32 cells) variant
+GROUPED_VECTOR_KERNELS = frozenset({1, 3, 7, 15})
 ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
@@ -108,6 +110,7 @@ _SIGS = {
     "bfx_asm_destroy": ([vp], ci),
     "bfx_asm_build_chunks": ([vp, vp, ci, vp], ci),
     "bfx_asm_build_rowgather": ([vp, vp], ci),
+    "bfx_asm_build_groups": ([vp, vp, vp], ci),
     "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),

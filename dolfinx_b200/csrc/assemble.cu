@@ -1159,11 +1159,13 @@ int bfx_assemble_vector_cells(const bfx_asm_t* P, int kernel_id, const double* x
     return e;
   BFX_REQUIRE(b, "bfx_assemble_vector_cells: null b");
   BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
-  if (strategy != BFX_ASM_ATOMIC)
+  if (strategy != BFX_ASM_ATOMIC && strategy != BFX_ASM_CHUNKED)
     return fail(BFX_ERR_UNSUPPORTED, "assembly strategy %d not available", strategy);
   a.cells = P->cells;
   a.n = P->ncells;
   a.b = b;
+  if (strategy == BFX_ASM_CHUNKED)
+    return launch_vector_grouped(P, kernel_id, a, S(stream));
   return dispatch_vector(kernel_id, a, S(stream));
 }
 

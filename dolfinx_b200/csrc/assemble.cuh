@@ -80,6 +80,10 @@ struct bfx_chunks
   int32_t *wv_ids = nullptr, *wd_ids = nullptr;
   uint8_t *wv_cnt = nullptr, *wd_cnt = nullptr;
   uint8_t *wv_loc = nullptr, *wd_loc = nullptr; // 4 * ceil(width / 4) bytes per slot
+  // Vector plans (bfx_asm_build_groups): for every group of 32 cell slots, the (cell, local dof) pairs that
+  // land on each distinct dof of the group: goff[g][l] .. goff[g][l+1] index glist[g][], entries = i * 32 + lane
+  uint8_t *glist = nullptr, *goff = nullptr;
+  int gstride = 0; // bytes of glist per group (32 * nd0)
   // Dirichlet markers of the current call packed to one bit per dof (rebuilt by every call: 1/8 of the
   // marker bytes, so the per-cell lookups of phase 1 stay in L1/L2)
   uint32_t *bits0 = nullptr, *bits1 = nullptr;
@@ -121,6 +125,8 @@ namespace bfx
 int chunked_supported(int kernel_id);
 int launch_chunked(const bfx_asm* P, int kernel_id, const AsmArgs& a, int values_mode, cudaStream_t st);
 void free_chunks(bfx_chunks* c);
+int grouped_vector_supported(int kernel_id);
+int launch_vector_grouped(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st);
 // rowgather.cu
 int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st);
 void free_rowgather(bfx_rowgather* g);

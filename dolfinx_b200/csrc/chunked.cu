@@ -1090,6 +1090,223 @@ int launch_chunked_e(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaSt
   return launch_chunked_es<E, true>(P, a, values_mode, st);
 }
 
+// Morton order of the centroids of the plan's cells: perm[slot] = entity
+int morton_perm(const bfx_asm* P, const double* x_dev, int32_t** perm_out, cudaStream_t st)
+{
+  unsigned long long* bb = nullptr;
+  uint64_t *k0 = nullptr, *k1 = nullptr;
+  int32_t* i0 = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  const int64_t n = P->ncells;
+  int e;
+  if ((e = dev_alloc(&bb, 6)) || (e = dev_alloc(&k0, (size_t)n)) || (e = dev_alloc(&k1, (size_t)n))
+      || (e = dev_alloc(&i0, (size_t)n)) || (e = dev_alloc(perm_out, (size_t)n)))
+    return e;
+  const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
+  BFX_CUDA(cudaMemcpyAsync(bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  k_centroid_bbox<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb);
+  k_morton_keys<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb, k0, i0);
+  BFX_CHECK_LAUNCH();
+  BFX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, *perm_out, n, 0, 63, st));
+  BFX_CUDA(cudaMalloc(&tmp, tmp_bytes));
+  BFX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, i0, *perm_out, n, 0, 63, st));
+  BFX_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  cudaFree(bb);
+  cudaFree(k0);
+  cudaFree(k1);
+  cudaFree(i0);
+  return BFX_OK;
+}
+
+// ---- vector plans: per group of 32 cell slots, which (cell, local dof) pairs land on each distinct dof ----
+__global__ void __launch_bounds__(128)
+    k_group_lists(int64_t ngroups, int nd, const uint8_t* __restrict__ wd_cnt, const uint8_t* __restrict__ wd_loc,
+                  int64_t n, uint8_t* __restrict__ glist, uint8_t* __restrict__ goff)
+{
+  __shared__ int s_cnt[4][32], s_off[4][33], s_cur[4][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int locw = 4 * ((nd + 3) / 4);
+  for (int64_t g = (int64_t)blockIdx.x * 4 + wib; g < ngroups; g += (int64_t)gridDim.x * 4)
+  {
+    const int64_t slot = g * 32 + lane;
+    const int dcnt = wd_cnt[g];
+    s_cnt[wib][lane] = 0;
+    s_cur[wib][lane] = 0;
+    __syncwarp();
+    if (dcnt && slot < n)
+      for (int i = 0; i < nd; ++i)
+        atomicAdd(&s_cnt[wib][wd_loc[slot * locw + i]], 1);
+    __syncwarp();
+    int incl = s_cnt[wib][lane];
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o)
+        incl += v;
+    }
+    s_off[wib][lane + 1] = incl;
+    if (lane == 0)
+      s_off[wib][0] = 0;
+    __syncwarp();
+    // cells in ascending lane order inside every dof: a fixed summation order
+    if (dcnt)
+      for (int c = 0; c < 32; ++c)
+      {
+        if (lane == c && slot < n)
+          for (int i = 0; i < nd; ++i)
+          {
+            const int l = wd_loc[slot * locw + i];
+            glist[g * 32 * nd + s_off[wib][l] + s_cur[wib][l]++] = (uint8_t)(i * 32 + lane);
+          }
+        __syncwarp();
+      }
+    goff[g * 36 + lane] = (uint8_t)s_off[wib][lane];
+    if (lane == 0)
+      goff[g * 36 + 32] = (uint8_t)min(s_off[wib][32], 255);
+    __syncwarp();
+  }
+}
+
+// Grouped vector assembly (fem::impl::assemble_cells, fem/assemble_vector_impl.h:72-116) for P1-sized elements:
+// one warp per group of 32 cells.  Coordinates and coefficient dofs come through the warp tables (one load per
+// distinct node / dof, shuffles), the element vectors are staged in shared memory, and one lane per DISTINCT dof
+// of the group sums its contributions and issues ONE RED (4 per cell in the cell-parallel kernel).
+template <class E>
+__global__ void __launch_bounds__(256) k_vector_grouped(const AsmArgs a, const ChunkArgs ch, const uint8_t* __restrict__ glist,
+                                                        const uint8_t* __restrict__ goff, int64_t ngroups)
+{
+  constexpr int NX = E::NX, ND = E::ND;
+  static_assert(E::BS == 1 && ND <= 4 && NX <= 4, "grouped vector kernel: P1-sized scalar elements");
+  constexpr int LOCWV = (NX + 3) / 4, LOCWD = (ND + 3) / 4;
+  __shared__ double s_be[8][ND][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int64_t g = (int64_t)blockIdx.x * 8 + wib; g < ngroups; g += (int64_t)gridDim.x * 8)
+  {
+    const int64_t slot = g * 32 + lane;
+    const bool active = slot < a.n;
+    const int vcnt = ch.wv_cnt[g], dcnt = ch.wd_cnt[g];
+    const int32_t vtx_id = ch.wv_ids[g * 32 + lane];
+    const int64_t dof_id = ch.wd_ids[g * 32 + lane];
+    uint32_t locv[LOCWV], locd[LOCWD];
+#pragma unroll
+    for (int k = 0; k < LOCWV; ++k)
+      locv[k] = __ldg(reinterpret_cast<const uint32_t*>(ch.wv_loc) + slot * LOCWV + k);
+#pragma unroll
+    for (int k = 0; k < LOCWD; ++k)
+      locd[k] = __ldg(reinterpret_cast<const uint32_t*>(ch.wd_loc) + slot * LOCWD + k);
+    const int my_lo = goff[g * 36 + lane], my_hi = goff[g * 36 + lane + 1];
+    // the group's list (32 * ND bytes) travels in registers: one word per lane, bytes fetched with shuffles
+    const uint32_t lword = lane < 8 * ND ? __ldg(reinterpret_cast<const uint32_t*>(glist + g * 32 * ND) + lane) : 0u;
+    int64_t e = slot;
+    int32_t cell = (int32_t)slot;
+    if (active && (!vcnt || !dcnt || E::WSIZE > 0))
+    {
+      e = ch.perm ? ch.perm[slot] : slot;
+      cell = a.cells ? a.cells[e] : (int32_t)e;
+    }
+    // coordinates
+    double xc[NX][3];
+    if (vcnt)
+    {
+      const double* pp = a.x + 3 * (int64_t)vtx_id;
+      const double px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+#pragma unroll
+      for (int v = 0; v < NX; ++v)
+      {
+        const int l = (int)((locv[v >> 2] >> (8 * (v & 3))) & 31u);
+        xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+        xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+        xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+      }
+    }
+    else if (active)
+    {
+      int32_t xd[NX];
+      load_ints<NX>(ch.xdm ? ch.xdm + slot * NX : a.x_dofmap + (int64_t)cell * NX, xd);
+      gather_coords<NX>(a.x, xd, xc);
+    }
+    // coefficient: through the dof table when it lives on the plan's dofmap, else the general gather
+    double w[E::WSIZE > 0 ? E::WSIZE : 1];
+    if constexpr (E::WSIZE > 0)
+    {
+      const bool same_map = !a.coef.packed && a.coef.f[0].dm == a.dofmap0 && E::WND == ND && E::WBS == 1;
+      if (dcnt && same_map)
+      {
+        const double fv = __ldg(a.coef.f[0].v + dof_id);
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+          w[i] = __shfl_sync(0xffffffffu, fv, (locd[i >> 2] >> (8 * (i & 3))) & 31u);
+      }
+      else if (active)
+        load_w<E>(a, e, cell, w);
+    }
+    double out[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      out[i] = 0.0;
+    if (active)
+    {
+      typename E::Geo geo;
+      E::prepare(geo, xc, w, a.constants, 0);
+      E::vec(geo, out);
+    }
+    if (dcnt)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        s_be[wib][i][lane] = out[i];
+      __syncwarp();
+      {
+        const double* be = &s_be[wib][0][0];
+        const int mine = lane < dcnt ? my_hi - my_lo : 0;
+        int longest = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
+        double sum = 0.0;
+        for (int k = 0; k < longest; ++k) // warp-uniform trip count: every lane takes part in the shuffles
+        {
+          const int t = k < mine ? my_lo + k : 0;
+          const uint32_t wv = __shfl_sync(0xffffffffu, lword, t >> 2);
+          if (k < mine)
+            sum += be[(wv >> (8 * (t & 3))) & 0xffu];
+        }
+        if (mine > 0)
+          red_add(a.b + dof_id, sum);
+      }
+      __syncwarp();
+    }
+    else if (active)
+    {
+      int32_t d0[ND];
+      load_ints<ND>(ch.dm0 ? ch.dm0 + slot * ND : a.dofmap0 + (int64_t)cell * ND, d0);
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        red_add(a.b + d0[i], out[i]);
+    }
+  }
+}
+
+template <class E>
+int launch_vector_grouped_e(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
+{
+  const bfx_chunks* c = P->chunks;
+  if (a.n == 0)
+    return BFX_OK;
+  ChunkArgs ch;
+  memset(&ch, 0, sizeof(ch));
+  ch.perm = c->perm;
+  ch.xdm = c->xdm;
+  ch.dm0 = c->dm0;
+  ch.wv_ids = c->wv_ids, ch.wv_cnt = c->wv_cnt, ch.wv_loc = c->wv_loc;
+  ch.wd_ids = c->wd_ids, ch.wd_cnt = c->wd_cnt, ch.wd_loc = c->wd_loc;
+  const int64_t ngroups = c->nchunks;
+  k_vector_grouped<E><<<grid_for(ngroups, 8, 0), 256, 0, st>>>(a, ch, c->glist, c->goff, ngroups);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
 } // namespace
 
 namespace bfx
@@ -1120,10 +1337,38 @@ int launch_chunked(const bfx_asm* P, int kernel_id, const AsmArgs& a, int values
   }
 }
 
+int grouped_vector_supported(int kernel_id)
+{
+  switch (kernel_id)
+  {
+  case BFX_K_SOURCE_P1_TRI_L:
+  case BFX_K_LOAD_COEFF_P1_TRI_L:
+  case BFX_K_LOAD_P1_TET_L:
+  case BFX_K_ACTION_POISSON_P1_TET_L: return 1;
+  default: return 0;
+  }
+}
+
+int launch_vector_grouped(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st)
+{
+  if (!P->chunks || !P->chunks->glist)
+    return fail(BFX_ERR_INVALID, "grouped vector assembly needs bfx_asm_build_groups() on the plan first");
+  switch (kernel_id)
+  {
+  case BFX_K_SOURCE_P1_TRI_L: return launch_vector_grouped_e<el::SourceP1Tri>(P, a, st);
+  case BFX_K_LOAD_COEFF_P1_TRI_L: return launch_vector_grouped_e<el::LoadCoeffP1Tri>(P, a, st);
+  case BFX_K_LOAD_P1_TET_L: return launch_vector_grouped_e<el::LoadP1Tet>(P, a, st);
+  case BFX_K_ACTION_POISSON_P1_TET_L: return launch_vector_grouped_e<el::ActionOf<el::PoissonP1Tet>>(P, a, st);
+  default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d has no grouped vector variant", kernel_id);
+  }
+}
+
 void free_chunks(bfx_chunks* c)
 {
   if (!c)
     return;
+  cudaFree(c->glist);
+  cudaFree(c->goff);
   cudaFree(c->hdr);
   cudaFree(c->winfo);
   cudaFree(c->dest_addr);
@@ -1175,32 +1420,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   };
 
   // ---- locality ordering of the cell list
-  if (x_dev)
-  {
-    unsigned long long* bb = nullptr;
-    uint64_t *k0 = nullptr, *k1 = nullptr;
-    int32_t* i0 = nullptr;
-    void* tmp = nullptr;
-    size_t tmp_bytes = 0;
-    const int64_t n = P->ncells;
-    if ((e = dev_alloc(&bb, 6)) || (e = dev_alloc(&k0, (size_t)n)) || (e = dev_alloc(&k1, (size_t)n))
-        || (e = dev_alloc(&i0, (size_t)n)) || (e = dev_alloc(&c->perm, (size_t)n)))
-      return bail(e);
-    const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
-    BFX_CUDA(cudaMemcpyAsync(bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    k_centroid_bbox<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb);
-    k_morton_keys<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb, k0, i0);
-    BFX_CHECK_LAUNCH();
-    BFX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, c->perm, n, 0, 63, st));
-    BFX_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    BFX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, i0, c->perm, n, 0, 63, st));
-    BFX_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-    cudaFree(bb);
-    cudaFree(k0);
-    cudaFree(k1);
-    cudaFree(i0);
-  }
+  if (x_dev && (e = morton_perm(P, x_dev, &c->perm, st)))
+    return bail(e);
 
   // ---- index arrays in chunk order (phase 1 streams them)
   if (c->perm || P->cells)
@@ -1401,6 +1622,52 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   cudaFree(total);
   cudaFree(ndw);
   cudaFree(nsrc);
+  P->chunks = c;
+  return BFX_OK;
+}
+
+int bfx_asm_build_groups(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)
+{
+  BFX_REQUIRE(P, "bfx_asm_build_groups: null plan");
+  if (P->nx > 4 || P->nd0 > 4 || P->ncells == 0)
+    return fail(BFX_ERR_UNSUPPORTED, "grouped vector plan: implemented for cells of at most 4 nodes / 4 dofs");
+  cudaStream_t st = S(stream);
+  free_chunks(P->chunks);
+  P->chunks = nullptr;
+  bfx_chunks* c = new bfx_chunks();
+  c->cb = 32;
+  c->nchunks = (P->ncells + 31) / 32;
+  int e = BFX_OK;
+  auto bail = [&](int status)
+  {
+    free_chunks(c);
+    return status;
+  };
+  if (x_dev && (e = morton_perm(P, x_dev, &c->perm, st)))
+    return bail(e);
+  const int64_t n = P->ncells, nslots_pad = c->nchunks * 32;
+  if (c->perm || P->cells)
+  {
+    if ((e = dev_alloc(&c->xdm, (size_t)n * P->nx)) || (e = dev_alloc(&c->dm0, (size_t)n * P->nd0)))
+      return bail(e);
+    k_permute_rows<<<grid_for(n * P->nx, 256, 16), 256, 0, st>>>(n, c->perm, P->cells, P->x_dofmap, P->nx, c->xdm);
+    k_permute_rows<<<grid_for(n * P->nd0, 256, 16), 256, 0, st>>>(n, c->perm, P->cells, P->dofmap0, P->nd0, c->dm0);
+  }
+  const int32_t* xrows = c->xdm ? c->xdm : P->x_dofmap;
+  const int32_t* drows = c->dm0 ? c->dm0 : P->dofmap0;
+  const int lv = 4 * ((P->nx + 3) / 4), ld = 4 * ((P->nd0 + 3) / 4);
+  c->gstride = 32 * P->nd0;
+  if ((e = dev_alloc(&c->wv_ids, (size_t)nslots_pad)) || (e = dev_alloc(&c->wv_cnt, (size_t)c->nchunks))
+      || (e = dev_alloc(&c->wv_loc, (size_t)nslots_pad * lv)) || (e = dev_alloc(&c->wd_ids, (size_t)nslots_pad))
+      || (e = dev_alloc(&c->wd_cnt, (size_t)c->nchunks)) || (e = dev_alloc(&c->wd_loc, (size_t)nslots_pad * ld))
+      || (e = dev_alloc(&c->glist, (size_t)c->nchunks * c->gstride)) || (e = dev_alloc(&c->goff, (size_t)c->nchunks * 36)))
+    return bail(e);
+  const unsigned grid = grid_for(c->nchunks, 4, 16);
+  k_warp_tables<8><<<grid, 128, 0, st>>>(nslots_pad, n, P->nx, xrows, c->wv_ids, c->wv_cnt, c->wv_loc);
+  k_warp_tables<8><<<grid, 128, 0, st>>>(nslots_pad, n, P->nd0, drows, c->wd_ids, c->wd_cnt, c->wd_loc);
+  k_group_lists<<<grid, 128, 0, st>>>(c->nchunks, P->nd0, c->wd_cnt, c->wd_loc, n, c->glist, c->goff);
+  BFX_CHECK_LAUNCH();
+  BFX_CUDA(cudaStreamSynchronize(st));
   P->chunks = c;
   return BFX_OK;
 }

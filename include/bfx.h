@@ -222,6 +222,11 @@ extern "C"
    * node) pairs in ascending cell order, cf. fem::transpose_dofmap, fem/DofMap.h:62-64) and the per-call scratch of
    * the cell records.  BFX_ERR_UNSUPPORTED unless the plan is Q1 hexahedra x block size 3 with one dofmap. */
   int bfx_asm_build_rowgather(bfx_asm_t* plan, bfx_stream_t stream);
+  /* Plan of the grouped vector strategy (bfx_assemble_vector_cells with BFX_ASM_CHUNKED) for linear-form plans of
+   * P1-sized scalar elements (<= 4 nodes, <= 4 dofs per cell): Morton order of the cells (x_dev, optional), the
+   * distinct nodes / dofs of every group of 32 cells and the list of (cell, local dof) pairs per distinct dof:
+   * one warp assembles 32 cells and issues one RED per distinct dof instead of one per (cell, local dof). */
+  int bfx_asm_build_groups(bfx_asm_t* plan, const double* x_dev, bfx_stream_t stream);
   int bfx_asm_chunk_stats(const bfx_asm_t* plan, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
                           int64_t* plan_bytes);
   /* Staged entries whose shared-memory bank still collides with another entry read in the same half-warp step

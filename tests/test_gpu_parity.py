@@ -600,3 +600,33 @@ def test_matrix_free_action_and_cg(bfx, oracle, degree):
         oracle.pack_coefficient(coeffs, 0, diff, p.dofmap, 1, cells=cells)
         ref2 = oracle.assemble_scalar(oracle.K_L2NORM2_P1_TET_M, p.x_dofmap, p.x, cells, coeffs=coeffs)
         assert err2 == pytest.approx(ref2, rel=1e-11) and err2 > 0
+
+
+@pytest.mark.parametrize("grouped", [True, False])
+def test_vector_assembly_grouped_and_atomic(bfx, oracle, grouped, monkeypatch):
+    """assemble_vector of the P1 load (fused coefficient gather) with the grouped kernel (one RED per distinct
+    dof of 32 Morton-ordered cells) and with the cell-parallel kernel, on a mesh of many groups with a random
+    numbering, a tail group, and a cell subset; accumulation into a non-zero vector."""
+    fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
+    monkeypatch.setattr(fem, "GROUPED_VECTORS", grouped)
+    p = P.tet_p1(9, numbering="random", seed=4)
+    msh, V = make_space(bfx, p)
+    fh = P.source_f(p.dof_coords) + 0.25
+    f = fem.Function(V)
+    f.x.array.copy_(torch.from_numpy(fh))
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_LOAD_P1_TET_L, None, [0])]}, coefficients=[f])
+    b = la.Vector(V.dofmap.index_map, 1)
+    b.array.fill_(0.5)
+    fem.assemble_vector(b, L)
+    bref = P.oracle_assemble_vector(oracle, p, oracle.K_LOAD_P1_TET_L, coeff=(fh, p.dofmap, 1), b=np.full(p.ndofs, 0.5))
+    assert np.max(np.abs(b.array.cpu().numpy() - bref)) <= TOL * np.max(np.abs(bref))
+    # a subset of the cells (every third cell)
+    sub = np.arange(0, len(p.dofmap), 3, dtype=np.int32)
+    Ls = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_LOAD_P1_TET_L, sub, [0])]}, coefficients=[f])
+    bs_ = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(bs_, Ls)
+    coeffs = np.zeros((len(sub), 4))
+    oracle.pack_coefficient(coeffs, 0, fh, p.dofmap, 1, cells=sub)
+    bsref = np.zeros(p.ndofs)
+    oracle.assemble_vector(oracle.K_LOAD_P1_TET_L, p.x_dofmap, p.x, sub, p.dofmap, 1, bsref, coeffs=coeffs)
+    assert np.max(np.abs(bs_.array.cpu().numpy() - bsref)) <= TOL * np.max(np.abs(bsref))
