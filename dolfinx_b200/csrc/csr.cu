@@ -539,8 +539,8 @@ __global__ void __launch_bounds__(256)
 constexpr int SPMV_BTMA_CAP = 480; // blocks per stage (multiple of 4)
 constexpr int SPMV_BTMA_TR = 16;   // block rows per tile
 
-template <int BS0, int BS1>
-__global__ void __launch_bounds__(256)
+template <int BS0, int BS1, int NW>
+__global__ void __launch_bounds__(32 * NW)
     k_spmv_blocked_tma(int32_t n_rows, int64_t nnz_total, const int64_t* __restrict__ row_ptr,
                        const int64_t* __restrict__ row_begin, const int64_t* __restrict__ row_end,
                        const int32_t* __restrict__ cols, const double* __restrict__ values,
@@ -598,88 +598,110 @@ __global__ void __launch_bounds__(256)
     }
   };
 
-  SpmvChunkIt cons, prod;
-  cons.tile = blockIdx.x, cons.base = 0, cons.end = 0;
-  load_tile(cons);
-  prod = cons;
-  if (threadIdx.x == 0 && prod.tile < ntiles)
-    issue(prod, 0);
-  if (prod.tile < ntiles)
-    advance(prod);
-  if (threadIdx.x == 0 && prod.tile < ntiles)
-    issue(prod, 1);
-  if (prod.tile < ntiles)
-    advance(prod);
+  // three iterators: it0 is consumed, it1 is in flight, it2 is the next to issue.  The row_ptr loads of a tile
+  // happen once (in advance(it2)), two iterations before the tile is consumed.
+  SpmvChunkIt it0, it1, it2;
+  it0.tile = blockIdx.x, it0.base = 0, it0.end = 0;
+  load_tile(it0);
+  if (threadIdx.x == 0 && it0.tile < ntiles)
+    issue(it0, 0);
+  it1 = it0;
+  if (it1.tile < ntiles)
+    advance(it1);
+  if (threadIdx.x == 0 && it1.tile < ntiles)
+    issue(it1, 1);
+  it2 = it1;
+  if (it2.tile < ntiles)
+    advance(it2);
 
-  // each warp owns rows wib, wib + 8 of the tile; partial sums live across the chunks of a tile
-  double acc[TR / 8][BS0];
+  // each warp owns rows wib, wib + NW, ... of the tile; partial sums live across the chunks of a tile
+  double acc[TR / NW][BS0];
 #pragma unroll
-  for (int s = 0; s < TR / 8; ++s)
+  for (int s = 0; s < TR / NW; ++s)
 #pragma unroll
     for (int k = 0; k < BS0; ++k)
       acc[s][k] = 0.0;
-  for (uint32_t c = 0; cons.tile < ntiles; ++c)
+  for (uint32_t c = 0; it0.tile < ntiles; ++c)
   {
     const int stage = c & 1;
-    const int64_t lim = min(cons.end, cons.base + CAP);
-    const bool last = cons.base + CAP >= cons.end;
+    const int64_t lim = min(it0.end, it0.base + CAP);
+    const bool last = it0.base + CAP >= it0.end;
+    // row bounds and the old y of my rows: issued before the wait, consumed after it
+    int64_t rbv[TR / NW], rev[TR / NW];
+    double yold[TR / NW][BS0];
+#pragma unroll
+    for (int s = 0; s < TR / NW; ++s)
+    {
+      const int64_t row = it0.tile * TR + wib + NW * s;
+      rbv[s] = rev[s] = 0;
+      if (row < n_rows)
+      {
+        rbv[s] = row_begin[row];
+        rev[s] = row_end[row];
+        if (last && lane < BS0)
+          yold[s][0] = y[row * BS0 + lane];
+      }
+    }
     sp_mbar_wait(&bar[stage], (c >> 1) & 1);
     double* sv = s_val + (size_t)stage * CAP * BS2;
     int32_t* sc = s_col + stage * CAP;
-    const int64_t got = cons.base + tma_blocks(cons);
+    const int64_t got = it0.base + tma_blocks(it0);
     if (got < lim)
     {
       for (int64_t k = got * BS2 + threadIdx.x; k < lim * BS2; k += blockDim.x)
-        sv[k - cons.base * BS2] = values[k];
+        sv[k - it0.base * BS2] = values[k];
       for (int64_t k = got + threadIdx.x; k < lim; k += blockDim.x)
-        sc[k - cons.base] = cols[k];
+        sc[k - it0.base] = cols[k];
       __syncthreads();
     }
 #pragma unroll
-    for (int s = 0; s < TR / 8; ++s)
+    for (int s = 0; s < TR / NW; ++s)
     {
-      const int64_t row = cons.tile * TR + wib + 8 * s;
-      if (row < n_rows)
+      const int64_t lo = max(rbv[s], it0.base), hi = min(rev[s], lim);
+      for (int64_t j0 = lo; j0 < hi; j0 += 32)
       {
-        const int64_t rb = row_begin[row], re = row_end[row];
-        const int64_t lo = max(rb, cons.base), hi = min(re, lim);
-        for (int64_t j0 = lo; j0 < hi; j0 += 32)
+        const int64_t j = j0 + lane;
+        if (j < hi)
         {
-          const int64_t j = j0 + lane;
-          if (j < hi)
-          {
-            const int o = (int)(j - cons.base);
-            const int64_t col = sc[o];
-            double xv[BS1];
+          const int o = (int)(j - it0.base);
+          const int64_t col = sc[o];
+          double xv[BS1];
+#pragma unroll
+          for (int k1 = 0; k1 < BS1; ++k1)
+            xv[k1] = __ldg(x + col * BS1 + k1);
+#pragma unroll
+          for (int k0 = 0; k0 < BS0; ++k0)
 #pragma unroll
             for (int k1 = 0; k1 < BS1; ++k1)
-              xv[k1] = __ldg(x + col * BS1 + k1);
-#pragma unroll
-            for (int k0 = 0; k0 < BS0; ++k0)
-#pragma unroll
-              for (int k1 = 0; k1 < BS1; ++k1)
-                acc[s][k0] = fma(sv[o * BS2 + k0 * BS1 + k1], xv[k1], acc[s][k0]);
-          }
-        }
-        if (last)
-        {
-#pragma unroll
-          for (int k = 0; k < BS0; ++k)
-          {
-            const double v = warp_sum(acc[s][k]);
-            if (lane == 0)
-              y[row * BS0 + k] += v;
-            acc[s][k] = 0.0;
-          }
+              acc[s][k0] = fma(sv[o * BS2 + k0 * BS1 + k1], xv[k1], acc[s][k0]);
         }
       }
     }
+    if (last)
+    {
+#pragma unroll
+      for (int s = 0; s < TR / NW; ++s)
+      {
+        const int64_t row = it0.tile * TR + wib + NW * s;
+        double mine = 0.0;
+#pragma unroll
+        for (int k = 0; k < BS0; ++k)
+        {
+          const double v = warp_sum(acc[s][k]);
+          mine = lane == k ? v : mine;
+          acc[s][k] = 0.0;
+        }
+        if (row < n_rows && lane < BS0)
+          y[row * BS0 + lane] = yold[s][0] + mine; // lanes 0..BS0-1 write the BS0 components
+      }
+    }
     __syncthreads(); // every warp is done with this stage: it can be refilled
-    if (threadIdx.x == 0 && prod.tile < ntiles)
-      issue(prod, stage);
-    if (prod.tile < ntiles)
-      advance(prod);
-    advance(cons);
+    if (threadIdx.x == 0 && it2.tile < ntiles)
+      issue(it2, stage);
+    it0 = it1;
+    it1 = it2;
+    if (it2.tile < ntiles)
+      advance(it2);
   }
 }
 
@@ -1080,10 +1102,10 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
         if (variant == 1)
         {
           const size_t smem = 2 * (size_t)SPMV_BTMA_CAP * (9 * 8 + 4) + 64;
-          cudaFuncSetAttribute(k_spmv_blocked_tma<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(k_spmv_blocked_tma<3, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           const int64_t ntiles = ((int64_t)n_launch + SPMV_BTMA_TR - 1) / SPMV_BTMA_TR;
           const unsigned g = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 3);
-          k_spmv_blocked_tma<3, 3><<<g, 256, smem, st>>>(n_launch, A->nnz, A->row_ptr, rb, re, A->cols, values, x, yy);
+          k_spmv_blocked_tma<3, 3, 16><<<g, 512, smem, st>>>(n_launch, A->nnz, A->row_ptr, rb, re, A->cols, values, x, yy);
         }
         else
           k_spmv_blocked<3, 3><<<grid_for((int64_t)n_launch * 32, 256, 32), 256, 0, st>>>(n_launch, rb, re, A->cols,
