@@ -302,8 +302,8 @@ struct SpmvChunkIt
   int64_t tile, base, end;
 };
 
-template <int R>
-__global__ void __launch_bounds__(R)
+template <int R, int LPR>
+__global__ void __launch_bounds__(R * LPR)
     k_spmv_tma(int32_t n_rows, int64_t nnz_total, const int64_t* __restrict__ row_ptr,
                const int64_t* __restrict__ row_end_sel, const int32_t* __restrict__ cols,
                const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y)
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(R)
   double sum = 0.0, y_old = 0.0;
   int64_t rb = 0, re = 0;
   {
-    const int64_t my_row = cons.tile * R + threadIdx.x;
+    const int64_t my_row = cons.tile * R + threadIdx.x / LPR;
     if (cons.tile < ntiles && my_row < n_rows)
     {
       rb = row_ptr[my_row];
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(R)
   for (uint32_t c = 0; cons.tile < ntiles; ++c)
   {
     const int stage = c & 1;
-    const int64_t my_row = cons.tile * R + threadIdx.x;
+    const int64_t my_row = cons.tile * R + threadIdx.x / LPR;
     const int64_t lim = min(cons.end, cons.base + SPMV_TMA_CAP);
     const bool last = cons.base + SPMV_TMA_CAP >= cons.end;
     // prefetch for the next tile of this CTA
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(R)
     double y_n = 0.0;
     if (last && nxt.tile < ntiles)
     {
-      const int64_t row_n = nxt.tile * R + threadIdx.x;
+      const int64_t row_n = nxt.tile * R + threadIdx.x / LPR;
       if (row_n < n_rows)
       {
         rb_n = row_ptr[row_n];
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(R)
     if (got < lim)
     {
       // the last < 4 entries of the arrays: not a whole 16-byte granule, loaded by hand
-      for (int64_t k = got + threadIdx.x; k < lim; k += R)
+      for (int64_t k = got + threadIdx.x; k < lim; k += R * LPR)
       {
         sv[k - cons.base] = values[k];
         sc[k - cons.base] = cols[k];
@@ -427,17 +427,17 @@ __global__ void __launch_bounds__(R)
       __syncthreads();
     }
     const int lo = (int)(max(rb, cons.base) - cons.base), hi = (int)(min(re, lim) - cons.base);
-    // 8 gathers of x in flight per thread, two accumulators
+    // 8 gathers of x in flight per thread, two accumulators; LPR lanes share a row (entries dealt round-robin)
     double s0 = 0.0, s1 = 0.0;
-    for (int k = lo; k < hi; k += 8)
+    for (int k = lo + (int)(threadIdx.x % LPR); k < hi; k += 8 * LPR)
     {
       double xv[8], av[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u)
       {
-        const bool in = k + u < hi;
-        av[u] = in ? sv[k + u] : 0.0;
-        xv[u] = in ? __ldg(x + sc[k + u]) : 0.0;
+        const bool in = k + u * LPR < hi;
+        av[u] = in ? sv[k + u * LPR] : 0.0;
+        xv[u] = in ? __ldg(x + sc[k + u * LPR]) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 8; u += 2)
@@ -447,8 +447,15 @@ __global__ void __launch_bounds__(R)
       }
     }
     sum += s0 + s1;
-    if (last && my_row < n_rows)
-      y[my_row] = y_old + sum;
+    if (last)
+    {
+      double tot = sum;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1)
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (my_row < n_rows && threadIdx.x % LPR == 0)
+        y[my_row] = y_old + tot;
+    }
     __syncthreads(); // every thread is done with this stage: it can be refilled
     if (threadIdx.x == 0 && prod.tile < ntiles)
       issue(prod, stage);
@@ -1007,27 +1014,23 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
     {
       if (variant == 2)
       {
-        // TMA-pipelined persistent CTAs: rows per tile so that one stage usually covers a tile
+        // TMA-pipelined persistent CTAs: rows per tile so that one stage usually covers a tile; longer rows get
+        // more lanes per row so that a CTA keeps 8-16 warps busy
         const size_t smem = 2 * SPMV_TMA_CAP * 12 + 64;
         const int per_sm = 2;
+#define BFX_TMA_LAUNCH(RR, LL)                                                                                        \
+  {                                                                                                                   \
+    cudaFuncSetAttribute(k_spmv_tma<RR, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + RR - 1) / RR, (int64_t)sm_count() * per_sm);     \
+    k_spmv_tma<RR, LL><<<grid, RR * LL, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);               \
+  }
         if (avg <= 15.0)
-        {
-          cudaFuncSetAttribute(k_spmv_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + 255) / 256, (int64_t)sm_count() * per_sm);
-          k_spmv_tma<256><<<grid, 256, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);
-        }
+          BFX_TMA_LAUNCH(256, 1)
         else if (avg <= 30.0)
-        {
-          cudaFuncSetAttribute(k_spmv_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + 127) / 128, (int64_t)sm_count() * per_sm);
-          k_spmv_tma<128><<<grid, 128, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);
-        }
+          BFX_TMA_LAUNCH(128, 4)
         else
-        {
-          cudaFuncSetAttribute(k_spmv_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)n + 63) / 64, (int64_t)sm_count() * per_sm);
-          k_spmv_tma<64><<<grid, 64, smem, st>>>(n, A->nnz, A->row_ptr, re, A->cols, values, x, yy);
-        }
+          BFX_TMA_LAUNCH(64, 8)
+#undef BFX_TMA_LAUNCH
         return;
       }
       if (variant == 1)
