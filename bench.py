@@ -468,6 +468,15 @@ def main():
     e1.record()
     barrier()
     ms_vec = e0.elapsed_time(e1) / 5
+    # apply_lifting (fem/assembler.h:336-493) for the same bc: b <- b - A g on the cells with a bc column
+    fem.apply_lifting(b, [a], [[bc]])
+    barrier()
+    e0.record()
+    for _ in range(5):
+        fem.apply_lifting(b, [a], [[bc]])
+    e1.record()
+    barrier()
+    ms_lift = e0.elapsed_time(e1) / 5
     A.set_value(0.0)
     fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)
     fem.set_diagonal(A, V, [bc], 1.0)
@@ -552,6 +561,7 @@ def main():
             "spmv": {"ms": ms_spmv, "gbs": b_spmv / (ms_spmv * 1e-3) / 1e9, "frac": b_spmv / (ms_spmv * 1e-3) / 1e9 / hbm_peak,
                      "gflops": 2 * pb["bs"] ** 2 * nnz / (ms_spmv * 1e-3) / 1e9, "alg_bytes": b_spmv, "reps": args.spmv_reps},
             "vector_assembly_ms": ms_vec,
+            "apply_lifting_ms": ms_lift,
             "sizes": {"dofs_global": pb["ndofs_global"] * pb["bs"], "cells_per_gpu": pb["n_cells"], "nnz_per_gpu": nnz},
             "setup_s": {"mesh": t_mesh, "sparsity+matrix": t_pattern, "assembly_plan+first_call": t_plan},
             "chunk_plan": plan_info,
