@@ -45,6 +45,7 @@ K_FACET_MASS_P1_TET_A = 13
 K_ACTION_POISSON_P1_TET_L = 15
 K_ACTION_POISSON_P2_TET_L = 16
 K_L2NORM2_P1_TET_M = 17
+K_AVG_MASS_P1_TRI_DS = 18
 
 ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})

@@ -848,6 +848,7 @@ int dispatch_matrix(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStrea
   case BFX_K_POISSON_P1_TET_A: return launch_matrix<el::PoissonP1Tet, MODE>(P, a, st);
   case BFX_K_POISSON_P2_TET_A: return launch_matrix<el::PoissonP2Tet, MODE>(P, a, st);
   case BFX_K_FACET_MASS_P1_TET_A: return launch_matrix<el::FacetMassP1Tet, MODE>(P, a, st);
+  case BFX_K_AVG_MASS_P1_TRI_DS: return launch_matrix<el::AvgMassP1TriDS, MODE>(P, a, st);
   case BFX_K_ELASTICITY_Q1_HEX_A: return launch_q1<MODE>(P, a, st);
   default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a bilinear-form kernel", kernel_id);
   }
@@ -876,7 +877,7 @@ const bfx_kernel_info_t KINFO[BFX_K_COUNT] = {
     {3, 3, 1, 2, 0, 0, 1},  {3, 3, 1, 1, 0, 1, 1},  {4, 4, 1, 2, 0, 1, 0},  {4, 4, 1, 1, 4, 0, 0},
     {4, 10, 1, 2, 0, 1, 0}, {4, 10, 1, 1, 10, 0, 0}, {8, 8, 3, 2, 0, 2, 0}, {8, 8, 3, 1, 24, 0, 0},
     {4, 4, 1, 1, 4, 0, 1},  {4, 4, 1, 2, 0, 0, 1},  {0, 0, 0, -1, 0, 0, 0}, {4, 4, 1, 1, 4, 1, 0},
-    {4, 10, 1, 1, 10, 1, 0}, {4, 4, 1, 0, 4, 0, 0}};
+    {4, 10, 1, 1, 10, 1, 0}, {4, 4, 1, 0, 4, 0, 0}, {6, 6, 1, 2, 0, 0, 1}};
 
 int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, const bfx_coeffs_t* coeffs,
                 const double* constants, int n_constants, AsmArgs& a, bool need_csr = true)

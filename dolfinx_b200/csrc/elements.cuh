@@ -182,6 +182,59 @@ struct FacetConstP1Tri : TriBase
   }
 };
 
+// inner(avg(u), avg(v))*dS, P1 triangles (python/test/unit/fem/test_ghost_mesh_assembly.py:104-122): macro element
+// of an interior facet.  coordinate_dofs = [cell0 (3 nodes), cell1 (3 nodes)]; A is 6 x 6 with the 2 x 2 block
+// layout of fem/assemble_matrix_impl.h:581-587; entity_local_index[0], [1] arrive packed as lf0 + 8 lf1.
+// avg(w) = (w+ + w-)/2, and on the edge only the two edge vertices of each cell contribute:
+// A[(s,a),(t,b)] = len (1 + delta_ab) / 24, vertices a, b matched between the cells through their coordinates.
+struct AvgMassP1TriDS
+{
+  static constexpr int NX = 6, ND = 6, BS = 1, WSIZE = 0, WND = 0, WBS = 1, CSIZE = 0, RANK = 2;
+  static constexpr bool FACET = true;
+  struct Geo
+  {
+    int v[2][2];
+    double len;
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[6][3], const double*, const double*, int lf)
+  {
+    const int lfs[2] = {lf & 7, lf >> 3};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+    {
+      double c3[3][3];
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          c3[n][m] = xc[3 * s + n][m];
+      double l;
+      TriBase::facet(c3, lfs[s], g.v[s][0], g.v[s][1], l);
+      g.len = l;
+    }
+    const double d = fabs(xc[g.v[0][0]][0] - xc[3 + g.v[1][0]][0]) + fabs(xc[g.v[0][0]][1] - xc[3 + g.v[1][0]][1])
+                     + fabs(xc[g.v[0][0]][2] - xc[3 + g.v[1][0]][2]);
+    if (d > 1e-12 * (1.0 + g.len))
+    {
+      const int t = g.v[1][0];
+      g.v[1][0] = g.v[1][1];
+      g.v[1][1] = t;
+    }
+  }
+  static BFX_DI void row(const Geo& g, int i, double (&out)[6])
+  {
+    const int s = i / 3, vi = i - 3 * s;
+    const int a = vi == g.v[s][0] ? 0 : (vi == g.v[s][1] ? 1 : -1);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+    {
+      const int t = j / 3, vj = j - 3 * t;
+      const int b = vj == g.v[t][0] ? 0 : (vj == g.v[t][1] ? 1 : -1);
+      out[j] = (a < 0 || b < 0) ? 0.0 : g.len * (a == b ? 2.0 : 1.0) * (1.0 / 24.0);
+    }
+  }
+};
+
 // ---- tetrahedra -------------------------------------------------------------------------------
 struct TetBase
 {

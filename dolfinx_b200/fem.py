@@ -262,6 +262,13 @@ def create_sparsity_pattern(a: Form) -> la.SparsityPattern:
         if integ.entities is None:
             continue
         ent = np.asarray(integ.entities if isinstance(integ.entities, np.ndarray) else integ.entities.cpu().numpy())
+        if itype == IntegralType.interior_facet:
+            # sparsitybuild::interior_facets (fem/sparsitybuild.h:52-85): joint dofs of the two cells of every facet
+            f = ent.reshape(-1, 2, 2)
+            d0, d1 = dm0.map(), dm1.map()
+            sp.insert_cells(None, np.concatenate([d0[f[:, 0, 0]], d0[f[:, 1, 0]]], axis=1),
+                            np.concatenate([d1[f[:, 0, 0]], d1[f[:, 1, 0]]], axis=1))
+            continue
         cells = ent if itype == IntegralType.cell else ent.reshape(-1, 2)[:, 0]
         if all_cells:
             continue  # already covered
@@ -458,6 +465,34 @@ def chunk_bank_conflicts(form: Form, A: la.MatrixCSR, ident=0):
     return int(n.value)
 
 
+def _interior_facet_plan(form: Form, integ: IntegralData, A: la.MatrixCSR):
+    """Plan of an interior-facet integral (fem/assemble_matrix_impl.h:442-667): every facet becomes a MACRO cell
+    whose geometry nodes and dofs are the joint arrays [cell0 | cell1]; the kernel receives the two local facet
+    indices packed as lf0 + 8 lf1.  Returns (plan, entities (facet, packed local facets) on device, n)."""
+    from . import _lib
+
+    torch = _torch()
+    key = ("dS", id(integ), id(A))
+    if key not in form._plans:
+        ent = integ.entities
+        f = torch.as_tensor(np.ascontiguousarray(np.asarray(ent).reshape(-1, 2, 2), dtype=np.int64)
+                            if not torch.is_tensor(ent) else ent.reshape(-1, 2, 2).long().cpu(), device=la._device())
+        n = int(f.shape[0])
+        mesh = form.mesh
+        dm0, dm1 = form.function_spaces[0].dofmap, form.function_spaces[1].dofmap
+        xdm = torch.cat([mesh.x_dofmap[f[:, 0, 0]], mesh.x_dofmap[f[:, 1, 0]]], dim=1).contiguous()
+        j0 = torch.cat([dm0.dev[f[:, 0, 0]], dm0.dev[f[:, 1, 0]]], dim=1).contiguous()
+        j1 = j0 if dm1 is dm0 else torch.cat([dm1.dev[f[:, 0, 0]], dm1.dev[f[:, 1, 0]]], dim=1).contiguous()
+        entities = torch.stack([torch.arange(n, device=f.device), f[:, 0, 1] + 8 * f[:, 1, 1]], dim=1).to(torch.int32).contiguous()
+        im0 = dm0.index_map
+        h = C.c_void_p()
+        _lib.check(_lib.lib.bfx_asm_create(
+            C.byref(h), A._csr, xdm.data_ptr(), xdm.shape[1], j0.data_ptr(), j0.shape[1], j1.data_ptr(), j1.shape[1],
+            n, None, 0, im0.size_local + im0.num_ghosts, 1, _lib.current_stream()))
+        form._plans[key] = (h, entities, n, (xdm, j0, j1))  # the joint arrays are borrowed by the plan: keep them
+    return form._plans[key][:3]
+
+
 def _boundary_interior_cells(form: Form, integ: IntegralData):
     """Split a cell domain into cells that touch a ghost row (their contributions must travel to the
     owner, la/MatrixCSR.h:399-468) and interior cells (SURVEY.md §8e overlap plan)."""
@@ -514,7 +549,7 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
     carr, nc = _lib.constants_array(consts)
     try:
         for (itype, ident), integ in a._integrals.items():
-            plan = _asm_plan(a, integ, itype, A)
+            plan = None if itype == IntegralType.interior_facet else _asm_plan(a, integ, itype, A)
             cf = _coeffs_for(a, integ, None if coeffs is None else coeffs[(itype, ident)])
             if itype == IntegralType.cell:
                 strat = _matrix_strategy(a, integ, plan, strategy)
@@ -527,6 +562,12 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
                     _lib.current_stream()))
             elif itype == IntegralType.exterior_facet:
                 ent, n = _entities_dev(a, integ, itype)
+                _lib.check(_lib.lib.bfx_assemble_matrix_facets(
+                    plan, integ.kernel, a.mesh.x.data_ptr(), ent.data_ptr(), n, None if bc0 is None else bc0.data_ptr(),
+                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(),
+                    _lib.current_stream()))
+            elif itype == IntegralType.interior_facet:
+                plan, ent, n = _interior_facet_plan(a, integ, A)
                 _lib.check(_lib.lib.bfx_assemble_matrix_facets(
                     plan, integ.kernel, a.mesh.x.data_ptr(), ent.data_ptr(), n, None if bc0 is None else bc0.data_ptr(),
                     None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(),

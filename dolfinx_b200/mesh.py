@@ -175,6 +175,21 @@ def exterior_facets(cells: np.ndarray, facet_table: np.ndarray):
     return np.ascontiguousarray(np.stack([ext // nf, ext % nf], 1).astype(np.int32))
 
 
+def interior_facets(cells: np.ndarray, facet_table: np.ndarray):
+    """(F, 2, 2) array [[cell0, local_facet0], [cell1, local_facet1]] of the facets shared by two cells, cell0 <
+    cell1 — the entity layout of interior-facet integrals (fem/Form.h:52-87, fem/utils.h get_cell_facet_pairs<2>)."""
+    C = cells.shape[0]
+    nf = facet_table.shape[0]
+    fv = np.sort(cells[:, facet_table].astype(np.int64), axis=2).reshape(C * nf, -1)
+    _, inv, counts = np.unique(fv, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1)
+    both = np.flatnonzero(counts[inv] == 2)
+    order = np.lexsort((both, inv[both]))  # group the two (cell, facet) slots of every shared facet, lower cell first
+    pairs = both[order].reshape(-1, 2)
+    out = np.stack([pairs // nf, pairs % nf], axis=2)
+    return np.ascontiguousarray(out[np.argsort(out[:, 0, 0] * nf + out[:, 0, 1], kind="stable")].astype(np.int32))
+
+
 # ---------------------------------------------------------------------------
 # Distributed box: brick partition with analytic, exchange-free numbering
 # ---------------------------------------------------------------------------

@@ -83,7 +83,12 @@ extern "C"
                                            of cpp/demo/poisson_matrix_free (poisson.py: M = action(a, ui)); w = ui */
     BFX_K_ACTION_POISSON_P2_TET_L = 16, /* same, P2 */
     BFX_K_L2NORM2_P1_TET_M = 17,        /* functional inner(w, w)*dx, w P1 (the error functional E of that demo) */
-    BFX_K_COUNT = 18
+    BFX_K_AVG_MASS_P1_TRI_DS = 18,      /* inner(avg(u), avg(v))*dS on interior facets, P1 triangles
+                                           (test_ghost_mesh_assembly.py:104-122).  Interior-facet kernels work on MACRO
+                                           cells: the plan is built on joint arrays [cell0 | cell1] of geometry nodes and
+                                           dofs per facet (fem/assemble_matrix_impl.h:442-667), and the entity list of
+                                           bfx_assemble_matrix_facets holds (facet, local_facet0 + 8 * local_facet1) */
+    BFX_K_COUNT = 19
   };
 
   /* Static description of a kernel id: geometry nodes per cell, dofs per cell of test/trial space,

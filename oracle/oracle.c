@@ -296,6 +296,40 @@ static void k_facet_const_p1_tri_L(double* b, const double* w, const double* c, 
   b[bb] += 0.5 * len * c[0];
 }
 
+/* a = inner(avg(u), avg(v)) dS, P1 triangles (python/test/unit/fem/test_ghost_mesh_assembly.py:104-122).
+ * Macro element of an interior facet: coordinate_dofs = [cell0 (3 x 3), cell1 (3 x 3)], A is (6 x 6) with the
+ * 2 x 2 block layout cell0cell0 | cell0cell1 / cell1cell0 | cell1cell1 (fem/assemble_matrix_impl.h:581-587),
+ * e[0], e[1] = local facet of the edge in cell0 / cell1.  avg(w) = (w+ + w-)/2; on the edge only the basis
+ * functions of the two edge vertices are non-zero, and the trace of a P1 basis function is the 1-D hat:
+ * int_edge phi_a phi_b = len (1 + delta_ab) / 6.  The shared vertices are matched through their coordinates. */
+static void k_avg_mass_p1_tri_dS(double* A, const double* w, const double* c, const double* xc, const int* e,
+                                 const uint8_t* q, void* d)
+{
+  (void)w; (void)c; (void)q; (void)d;
+  int v[2][2];
+  double len = 0.0;
+  for (int s = 0; s < 2; ++s)
+  {
+    double l;
+    tri_facet(xc + 9 * s, e[s], &v[s][0], &v[s][1], &l);
+    len = l;
+  }
+  /* orient cell1's edge like cell0's: v[1][k] must be the same point as v[0][k] */
+  const double* p0 = xc + 3 * v[0][0];
+  const double* q0 = xc + 9 + 3 * v[1][0];
+  if (fabs(p0[0] - q0[0]) + fabs(p0[1] - q0[1]) + fabs(p0[2] - q0[2]) > 1e-12 * (1.0 + len))
+  {
+    int t = v[1][0];
+    v[1][0] = v[1][1];
+    v[1][1] = t;
+  }
+  for (int s = 0; s < 2; ++s)
+    for (int t = 0; t < 2; ++t)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+          A[6 * (3 * s + v[s][a]) + 3 * t + v[t][b]] += 0.25 * len * (a == b ? 2.0 : 1.0) / 6.0;
+}
+
 /* --- tetrahedra ---------------------------------------------------------- */
 
 /* J = [x1-x0, x2-x0, x3-x0] (columns), as FFCx builds it (test_custom_jit_kernels.py:173-182) */
@@ -670,6 +704,7 @@ enum
   K_ACTION_POISSON_P1_TET_L = 15,
   K_ACTION_POISSON_P2_TET_L = 16,
   K_L2NORM2_P1_TET_M = 17,
+  K_AVG_MASS_P1_TRI_DS = 18,
   K_COUNT
 };
 
@@ -695,6 +730,7 @@ static orc_kernel_t kernel_table(int id)
   case K_ACTION_POISSON_P1_TET_L: return k_action_poisson_p1_tet_L;
   case K_ACTION_POISSON_P2_TET_L: return k_action_poisson_p2_tet_L;
   case K_L2NORM2_P1_TET_M: return k_l2norm2_p1_tet_M;
+  case K_AVG_MASS_P1_TRI_DS: return k_avg_mass_p1_tri_dS;
   default: return 0;
   }
 }
@@ -887,6 +923,58 @@ int orc_assemble_vector(int kernel_id, const int32_t* x_dofmap, int nx, const do
   free(be);
   free(cdofs);
   return 0;
+}
+
+/* impl::assemble_interior_facets (fem/assemble_matrix_impl.h:442-667), the common case of one mesh with a cell
+ * on both sides of every facet: facets = (F, 2, 2) [[cell0, local0], [cell1, local1]]; joint dofmaps
+ * [dofs(cell0), dofs(cell1)]; bc rows / columns zeroed (:613-645); mat_add of the whole joint block (:653-654). */
+int orc_assemble_matrix_interior_facets(int kernel_id, const int32_t* x_dofmap, int nx, const double* x,
+                                        const int32_t* facets, int64_t nf, const int32_t* dmap0, int nd0, int bs0,
+                                        const int32_t* dmap1, int nd1, int bs1, const int8_t* bc0, const int8_t* bc1,
+                                        const double* constants, double* data, const int32_t* cols,
+                                        const int64_t* row_ptr)
+{
+  orc_kernel_t kernel = kernel_table(kernel_id);
+  if (!kernel)
+    return -2;
+  const int nr = 2 * nd0 * bs0, nc = 2 * nd1 * bs1;
+  double* Ae = (double*)malloc(sizeof(double) * nr * nc);
+  double* cdofs = (double*)malloc(sizeof(double) * 3 * 2 * nx);
+  int32_t* j0 = (int32_t*)malloc(sizeof(int32_t) * 2 * nd0);
+  int32_t* j1 = (int32_t*)malloc(sizeof(int32_t) * 2 * nd1);
+  int err = 0;
+  for (int64_t f = 0; f < nf && !err; ++f)
+  {
+    const int32_t c[2] = {facets[4 * f], facets[4 * f + 2]};
+    const int lf[2] = {facets[4 * f + 1], facets[4 * f + 3]};
+    for (int s = 0; s < 2; ++s)
+    {
+      for (int i = 0; i < nx; ++i)
+        memcpy(cdofs + 3 * (s * nx + i), x + 3 * (size_t)x_dofmap[(size_t)c[s] * nx + i], 3 * sizeof(double));
+      memcpy(j0 + s * nd0, dmap0 + (size_t)c[s] * nd0, sizeof(int32_t) * nd0);
+      memcpy(j1 + s * nd1, dmap1 + (size_t)c[s] * nd1, sizeof(int32_t) * nd1);
+    }
+    memset(Ae, 0, sizeof(double) * nr * nc);
+    uint8_t perm[2] = {0, 0};
+    kernel(Ae, 0, constants, cdofs, lf, perm, 0);
+    if (bc0)
+      for (int i = 0; i < 2 * nd0; ++i)
+        for (int k = 0; k < bs0; ++k)
+          if (bc0[(size_t)bs0 * j0[i] + k])
+            memset(Ae + (size_t)nc * (bs0 * i + k), 0, sizeof(double) * nc);
+    if (bc1)
+      for (int j = 0; j < 2 * nd1; ++j)
+        for (int k = 0; k < bs1; ++k)
+          if (bc1[(size_t)bs1 * j1[j] + k])
+            for (int m = 0; m < nr; ++m)
+              Ae[(size_t)m * nc + bs1 * j + k] = 0;
+    err = orc_insert_csr(data, cols, row_ptr, Ae, j0, 2 * nd0, j1, 2 * nd1, bs0, bs1, 1);
+  }
+  free(Ae);
+  free(cdofs);
+  free(j0);
+  free(j1);
+  return err;
 }
 
 /* impl::assemble_cells of a functional (fem/assemble_scalar_impl.h:32-60): value += kernel(...) over the cells */

@@ -43,6 +43,7 @@ K_ELASTICITY_Q1_HEX_A_G2 = 14  # oracle-only: 2x2x2 Gauss variant
 K_ACTION_POISSON_P1_TET_L = 15
 K_ACTION_POISSON_P2_TET_L = 16
 K_L2NORM2_P1_TET_M = 17
+K_AVG_MASS_P1_TRI_DS = 18
 
 
 def build(fast: bool = False) -> str:
@@ -172,6 +173,36 @@ def assemble_vector(kernel_id, x_dofmap, x, cells, dmap, bs, b, coeffs=None, con
         C.c_int(bs), _p(coeffs, C.c_double), C.c_int(cstride), _p(constants, C.c_double), _p(b, C.c_double),
     )
     assert err == 0
+
+
+def sparsity_insert_interior_facets(facets, dofmap0, dofmap1):
+    """fem::sparsitybuild::interior_facets (fem/sparsitybuild.h:52-85): for every facet insert the joint dofs
+    [dofs(cell0), dofs(cell1)] x [dofs(cell0), dofs(cell1)]."""
+    f = np.asarray(facets).reshape(-1, 2, 2)
+    j0 = np.concatenate([np.asarray(dofmap0)[f[:, 0, 0]], np.asarray(dofmap0)[f[:, 1, 0]]], axis=1)
+    j1 = np.concatenate([np.asarray(dofmap1)[f[:, 0, 0]], np.asarray(dofmap1)[f[:, 1, 0]]], axis=1)
+    n0, n1 = j0.shape[1], j1.shape[1]
+    rows = np.repeat(j0[:, :, None], n1, axis=2).reshape(-1)
+    cols = np.repeat(j1[:, None, :], n0, axis=1).reshape(-1)
+    return rows.astype(np.int32), cols.astype(np.int32)
+
+
+def assemble_matrix_interior_facets(kernel_id, x_dofmap, x, facets, dmap0, bs0, dmap1, bs1, data, cols, row_ptr,
+                                    bc0=None, bc1=None, constants=None):
+    """impl::assemble_interior_facets (fem/assemble_matrix_impl.h:442-667), cells on both sides of every facet."""
+    x_dofmap, dmap0, dmap1 = _i32(x_dofmap), _i32(dmap0), _i32(dmap1)
+    facets = _i32(np.asarray(facets).reshape(-1, 4))
+    cols, constants, x = _i32(cols), _f64(constants), _f64(x)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    bc0 = None if bc0 is None else np.ascontiguousarray(bc0, dtype=np.int8)
+    bc1 = None if bc1 is None else np.ascontiguousarray(bc1, dtype=np.int8)
+    err = lib().orc_assemble_matrix_interior_facets(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(facets, C.c_int32), C.c_int64(len(facets)), _p(dmap0, C.c_int32), C.c_int(dmap0.shape[1]), C.c_int(bs0),
+        _p(dmap1, C.c_int32), C.c_int(dmap1.shape[1]), C.c_int(bs1), _p(bc0, C.c_int8), _p(bc1, C.c_int8),
+        _p(constants, C.c_double), _p(data, C.c_double), _p(cols, C.c_int32), _p(row_ptr, C.c_int64))
+    if err:
+        raise RuntimeError("Entry not in sparsity")
 
 
 def assemble_scalar(kernel_id, x_dofmap, x, cells, coeffs=None, constants=None):

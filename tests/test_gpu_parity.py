@@ -630,3 +630,40 @@ def test_vector_assembly_grouped_and_atomic(bfx, oracle, grouped, monkeypatch):
     bsref = np.zeros(p.ndofs)
     oracle.assemble_vector(oracle.K_LOAD_P1_TET_L, p.x_dofmap, p.x, sub, p.dofmap, 1, bsref, coeffs=coeffs)
     assert np.max(np.abs(bs_.array.cpu().numpy() - bsref)) <= TOL * np.max(np.abs(bsref))
+
+
+def test_interior_facets_dS(bfx, oracle):
+    """a = inner(avg(u), avg(v))*dS on the unit square 12 x 12, P1 — the reference's golden
+    norm 2.1834054713561906 (test_ghost_mesh_assembly.py:104-122) from the CUDA path, pattern and values against
+    the oracle, with and without Dirichlet rows/columns."""
+    fem, la, K = bfx.fem, bfx.la, bfx.lib
+    from dolfinx_b200 import mesh as M
+
+    p = P.tri_p1(12, 12)
+    msh, V = make_space(bfx, p)
+    facets = M.interior_facets(p.x_dofmap, M.TRI_FACETS)
+    a = fem.Form([V, V], {fem.IntegralType.interior_facet: [(0, K.K_AVG_MASS_P1_TRI_DS, facets, [])]})
+    sp = fem.create_sparsity_pattern(a)
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    fem.assemble_matrix(A, a)
+    A.scatter_reverse()
+    assert np.sqrt(A.squared_norm()) == pytest.approx(2.1834054713561906, rel=1e-12)
+    maps = oracle.make_index_maps([p.ndofs], [[]], [[]])
+    r, c = oracle.sparsity_insert_interior_facets(facets, p.dofmap, p.dofmap)
+    pat = oracle.sparsity_finalize(maps, maps, (1, 1), [r], [c])[0]
+    ref = np.zeros(len(pat.edges))
+    oracle.assemble_matrix_interior_facets(oracle.K_AVG_MASS_P1_TRI_DS, p.x_dofmap, p.x, facets, p.dofmap, 1, p.dofmap, 1,
+                                           ref, pat.edges, pat.offsets)
+    check_matrix(A, pat, ref)
+    # Dirichlet rows / columns zeroed in the macro element (fem/assemble_matrix_impl.h:613-645)
+    bdofs = np.flatnonzero((p.dof_coords[:, 0] < 1e-12) | (p.dof_coords[:, 1] > 1 - 1e-12)).astype(np.int32)
+    bc = fem.DirichletBC(fem.Constant(0.0), bdofs, V)
+    A2 = la.MatrixCSR(sp)
+    fem.assemble_matrix(A2, a, bcs=[bc])
+    mk = np.zeros(p.ndofs, dtype=np.int8)
+    mk[bdofs] = 1
+    ref2 = np.zeros(len(pat.edges))
+    oracle.assemble_matrix_interior_facets(oracle.K_AVG_MASS_P1_TRI_DS, p.x_dofmap, p.x, facets, p.dofmap, 1, p.dofmap, 1,
+                                           ref2, pat.edges, pat.offsets, bc0=mk, bc1=mk)
+    check_matrix(A2, pat, ref2)

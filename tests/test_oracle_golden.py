@@ -291,3 +291,25 @@ def test_action_and_functional_kernels(oracle, degree):
             O.pack_coefficient(coeffs, 0, vals, p.dofmap, 1, cells=cells)
             m = O.assemble_scalar(O.K_L2NORM2_P1_TET_M, p.x_dofmap, p.x, cells, coeffs=coeffs)
             assert m == pytest.approx(expect, rel=1e-13)
+
+
+def test_golden_interior_facets_dS(oracle):
+    """The reference's golden norm of a = inner(avg(u), avg(v))*dS on create_unit_square(12, 12), P1
+    (python/test/unit/fem/test_ghost_mesh_assembly.py:104-122): pins impl::assemble_interior_facets
+    (fem/assemble_matrix_impl.h:442-667), sparsitybuild::interior_facets and the macro-element kernel."""
+    from dolfinx_b200 import mesh as M
+
+    O = oracle
+    p = P.tri_p1(12, 12)
+    facets = M.interior_facets(p.x_dofmap, M.TRI_FACETS)
+    assert facets.shape == (3 * 12 * 12 - 2 * 12, 2, 2) and np.all(facets[:, 0, 0] < facets[:, 1, 0])
+    maps = O.make_index_maps([p.ndofs], [[]], [[]])
+    r, c = O.sparsity_insert_interior_facets(facets, p.dofmap, p.dofmap)
+    pat = O.sparsity_finalize(maps, maps, (1, 1), [r], [c])[0]
+    data = np.zeros(len(pat.edges))
+    O.assemble_matrix_interior_facets(O.K_AVG_MASS_P1_TRI_DS, p.x_dofmap, p.x, facets, p.dofmap, 1, p.dofmap, 1, data,
+                                      pat.edges, pat.offsets)
+    assert np.sqrt(np.sum(data**2)) == pytest.approx(2.1834054713561906, rel=1e-12)
+    # total of all entries = int_dS (avg 1)(avg 1) = total length of the interior edges
+    length = 2 * 11 * 1.0 + 144 * np.sqrt(2.0) / 12.0
+    assert np.sum(data) == pytest.approx(length, rel=1e-13)
