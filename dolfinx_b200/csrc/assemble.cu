@@ -218,10 +218,11 @@ __global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArg
 
   const int cl = threadIdx.x >> 6, t = threadIdx.x & 63;
   const double mu = a.constants[0], lmbda = a.constants[1];
-  for (int64_t e0 = (int64_t)blockIdx.x * Q1_CELLS; e0 < a.n; e0 += (int64_t)gridDim.x * Q1_CELLS)
+  const int64_t n_ent = a.n_dev ? min(a.n, (int64_t)*a.n_dev) : a.n;
+  for (int64_t e0 = (int64_t)blockIdx.x * Q1_CELLS; e0 < n_ent; e0 += (int64_t)gridDim.x * Q1_CELLS)
   {
     const int64_t e = e0 + cl;
-    const bool active = e < a.n;
+    const bool active = e < n_ent;
     int32_t cell = 0;
     if (active)
       cell = a.cells ? a.cells[e] : (int32_t)e;
@@ -682,6 +683,27 @@ __global__ void __launch_bounds__(Q2_THREADS, 2) k_elasticity_q1_sym(const AsmAr
   }
 }
 
+// has_bc (fem/assemble_matrix_impl.h:27-34) over the whole cell list: the cells with a marked column dof, compacted.
+// Lifting touches only those (a boundary layer); the per-cell kernels then run on the short list.
+__global__ void k_cells_with_bc(int64_t n, const int32_t* __restrict__ cells, const int32_t* __restrict__ dofmap1,
+                                int nd1, int bs1, const int8_t* __restrict__ bc1, int32_t* __restrict__ out,
+                                unsigned long long* __restrict__ count)
+{
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    int any = 0;
+    for (int j = 0; j < nd1; ++j)
+    {
+      const int64_t d = (int64_t)bs1 * dofmap1[(int64_t)cell * nd1 + j];
+      for (int k = 0; k < bs1; ++k)
+        any |= bc1[d + k];
+    }
+    if (any)
+      out[atomicAdd(count, 1ULL)] = cell;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // plan construction: cell -> CSR position map (replaces std::lower_bound of insert_csr)
 // ---------------------------------------------------------------------------------------------
@@ -817,7 +839,7 @@ int launch_q1(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
   }
   else
   {
-    const unsigned grid = grid_for((a.n + Q1_CELLS - 1) / Q1_CELLS, 1, 0);
+    const unsigned grid = grid_for((a.n + Q1_CELLS - 1) / Q1_CELLS, 1, a.n_dev ? 8 : 0);
     if (P->pos_bytes == 2 && a.pos)
       k_elasticity_q1<uint16_t, MODE><<<grid, 64 * Q1_CELLS, 0, st>>>(a);
     else
@@ -1064,6 +1086,8 @@ int bfx_asm_destroy(bfx_asm_t* P)
     cudaFree(P->cells);
   }
   cudaFree(P->pos);
+  cudaFree(P->lift_cells);
+  cudaFree(P->lift_count);
   free_chunks(P->chunks);
   free_rowgather(P->rowgather);
   cudaFree(P->h_x);
@@ -1148,6 +1172,23 @@ int bfx_lift_bc_cells(const bfx_asm_t* P, int kernel_id, const double* x, const 
   a.bc_values1 = bc_values1;
   a.x0 = x0;
   a.alpha = alpha;
+  if (kernel_id == BFX_K_ELASTICITY_Q1_HEX_A && P->ncells > 0)
+  {
+    // the 64-threads-per-cell elasticity kernel is too heavy to visit every cell for a test: compact first
+    bfx_asm* Pm = const_cast<bfx_asm*>(P);
+    if (!Pm->lift_cells)
+    {
+      BFX_CUDA(cudaMalloc(&Pm->lift_cells, sizeof(int32_t) * (size_t)P->ncells));
+      BFX_CUDA(cudaMalloc(&Pm->lift_count, sizeof(unsigned long long)));
+    }
+    cudaStream_t st = S(stream);
+    BFX_CUDA(cudaMemsetAsync(Pm->lift_count, 0, sizeof(unsigned long long), st));
+    k_cells_with_bc<<<grid_for(P->ncells, 256, 16), 256, 0, st>>>(P->ncells, P->cells, a.dofmap1, P->nd1,
+                                                                  KINFO[kernel_id].bs, bc_markers1, Pm->lift_cells,
+                                                                  Pm->lift_count);
+    a.cells = Pm->lift_cells;
+    a.n_dev = Pm->lift_count;
+  }
   return dispatch_matrix<1>(P, kernel_id, a, S(stream));
 }
 

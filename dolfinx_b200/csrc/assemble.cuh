@@ -117,6 +117,9 @@ struct bfx_asm
   int64_t h_x_n = 0, h_coeff_n = 0, h_bc_n = 0;
   bfx_chunks* chunks = nullptr;
   bfx_rowgather* rowgather = nullptr;
+  // lifting scratch: cells with a Dirichlet column dof (rebuilt by every call)
+  int32_t* lift_cells = nullptr;
+  unsigned long long* lift_count = nullptr;
 };
 
 namespace bfx

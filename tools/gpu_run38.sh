@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "bcs or q1 or elasticity" > gpurun_out/pytest_q1.log 2>&1; tail -3 gpurun_out/pytest_q1.log
+timeout 900 ncu --set full --clock-control none -k regex:"k_spmv_blocked_tma" -s 8 -c 1 -o gpurun_out/prof_spmv_q1_192_btma python bench.py --config q1 --steps 1 --warmup 3 --no-cpu --no-e2e --spmv-reps 2 --spmv-variant 1 > gpurun_out/ncu_3.log 2>&1; tail -1 gpurun_out/ncu_3.log | cut -c1-60
+timeout 900 ncu --set full --clock-control none -k regex:"k_spmv_tma" -s 8 -c 1 -o gpurun_out/prof_spmv_p1_256_tma_v2 python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --spmv-reps 2 --spmv-variant 2 > gpurun_out/ncu_4.log 2>&1; tail -1 gpurun_out/ncu_4.log | cut -c1-60
+timeout 900 python bench.py --config q1 --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_q1_final.json 2> gpurun_out/bench_q1_final.err; tail -c 200 gpurun_out/bench_q1_final.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_q1_final.json'))
+print("q1", d["roofline"]["kernel"], 'step %.3f ms'%d['ms_per_step'], 'asm kernel %.3f ms frac %.3f'%(d['roofline']['kernel_ms'], d['roofline']['frac']), 'spmv %.3f ms frac %.3f'%(d['spmv']['ms'], d['spmv']['frac']), 'vec %.3f lift %.3f'%(d['vector_assembly_ms'], d['apply_lifting_ms']))
+PY
