@@ -5,17 +5,22 @@
 // Why: a fp64 RED costs 1.2-1.9 SM-cycles per lane even when it hits L2
 // (profiles/r01_microbench_red_bulk_lds.txt), a shared-memory load 0.07-0.2.  A P1 mesh sends 16
 // contributions per cell to ~2.5 distinct CSR entries per cell, so the sums are formed on the SM:
-//   phase 1  one thread per cell of a chunk of CB cells: gather geometry, element matrix in
-//            registers, bc rows/columns zeroed, entries stored to shared memory (entry-major, so the
-//            stores of a warp are conflict free);
-//   phase 2  one thread per DISTINCT destination of the chunk: sums its contributions from shared
-//            memory through a precomputed source list; destinations that receive all their
-//            contributions from this chunk are updated with a plain load/add/store (or a plain store
-//            when the caller guarantees zeroed values), the others (chunk boundary) with one RED.
-// The plan (bfx_asm_build_chunks) orders the cells along a Morton curve of their centroids when
-// the geometry is given, so a chunk is a compact patch and most destinations are complete.
-// Destinations are sorted by (complete, list length, address): the 32 lanes of a warp walk lists of
-// equal length, the lists are stored 32-way interleaved (one coalesced 64-byte load per step).
+//   phase 1  one thread per cell of a chunk of CB cells (coordinates and marker bits through the warp
+//            tables: one load per distinct node of 32 cells + shuffles): element matrix in registers,
+//            bc rows/columns zeroed, entries stored to shared memory; symmetric forms stage the upper
+//            triangle only;
+//   phase 2  one thread per DISTINCT destination of the chunk (a pair of entries (i,j)/(j,i) for
+//            symmetric forms): sums its contributions from shared memory through a precomputed source
+//            list; destinations that receive all their contributions from this chunk are updated with a
+//            plain load/add/store (or a plain store when the caller guarantees zeroed values), the
+//            others (chunk boundary) with one RED.
+// The plan (bfx_asm_build_chunks) orders the cells along a Morton curve of their centroids when the
+// geometry is given, so a chunk is a compact patch and most destinations are complete.  Destinations
+// are sorted by (complete, list length, address): the 32 lanes of a warp walk lists of equal length,
+// the lists are stored 32-way interleaved and reach shared memory by TMA bulk copies while phase 1 runs.
+// The staging slots are bank-coloured by the plan (k_chunk_colour): stores and list reads are conflict
+// free.  DESIGN.md section 4.2 has the measured effect of every step.
+// The same file holds the grouped vector kernel (bfx_asm_build_groups) that reuses the warp tables.
 #include "asm_device.cuh"
 #include "elements.cuh"
 #include <cub/block/block_radix_sort.cuh>
@@ -32,7 +37,7 @@ constexpr int MAX_LIST = 255;
 
 // cells per chunk for ns staged scalars per cell (N^2, or N(N+1)/2 for a symmetric form): the staging
 // area fits 40-60 KB of shared memory and the plan kernel's 1024 x ITEMS keys
-constexpr int chunk_cb(int ns) { return ns <= 16 ? 256 : (ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0))); }
+constexpr int chunk_cb(int ns) { return ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0)); }
 // threads per chunk: one per cell for small element matrices, several per cell (rows dealt round-robin) else
 constexpr int chunk_threads(int ns) { return 256; }
 // largest element (staged scalars per cell) that gets the bank-coloured staging layout: the colours of a cell
