@@ -507,16 +507,42 @@ class MatrixCSR:
     def __init__(self, pattern: SparsityPattern, block_mode: BlockMode = BlockMode.compact):
         from . import _lib
 
-        if block_mode != BlockMode.compact:
-            raise NotImplementedError("BlockMode.expanded: expand the pattern with bs=1 maps before constructing")
         pattern._need_final()
         torch = _torch()
         self._pattern = pattern
+        self._block_mode = block_mode
         self._index_maps = [pattern.index_map(0), pattern.index_map(1)]
         self._bs = (pattern.block_size(0), pattern.block_size(1))
+        self._expanded = None
+        if block_mode == BlockMode.expanded and self._bs != (1, 1):
+            # la/MatrixCSR.h:638-694: index maps with every block index unrolled, every block row repeated bs0 times
+            # with its columns unrolled by bs1, block sizes 1
+            bs0, bs1 = self._bs
+            maps = []
+            for im, b in zip(self._index_maps, self._bs):
+                ghosts = (im.ghosts[:, None] * b + np.arange(b)[None, :]).reshape(-1)
+                maps.append(IndexMap(im.comm, im.size_local * b, ghosts, np.repeat(im.owners, b), (im.src, im.dest)))
+            edges, offsets = pattern.graph
+            lens = np.diff(offsets)
+            new_lens = np.repeat(lens * bs1, bs0)
+            new_ptr = np.concatenate([[0], np.cumsum(new_lens)]).astype(np.int64)
+            unrolled = (edges.astype(np.int64)[:, None] * bs1 + np.arange(bs1)[None, :]).reshape(-1)  # per block row
+            blk_ptr = offsets.astype(np.int64) * bs1
+            pieces = [unrolled[blk_ptr[i]:blk_ptr[i + 1]] for i in range(len(lens)) for _ in range(bs0)]
+            new_cols = (np.concatenate(pieces) if pieces else np.zeros(0)).astype(np.int32)
+            new_od = new_ptr[:-1] + np.repeat(pattern.off_diagonal_offsets.astype(np.int64) * bs1, bs0)
+            self._index_maps = maps
+            self._bs = (1, 1)
+            self._expanded = (new_cols, new_ptr, new_od)
         m0 = self._index_maps[0]
         n_all = m0.size_local + m0.num_ghosts
-        if pattern._csr is None:
+        if self._expanded is not None:
+            cols_e, ptr_e, od_e = self._expanded
+            h = C.c_void_p()
+            _lib.check(_lib.lib.bfx_csr_create(C.byref(h), n_all, m0.size_local, ptr_e.ctypes.data,
+                                               np.ascontiguousarray(cols_e).ctypes.data, od_e.ctypes.data, 1, 1))
+            self._csr = h
+        elif pattern._csr is None:
             edges, offsets = pattern.graph
             off_diag = (pattern.off_diagonal_offsets.astype(np.int64) + offsets[:-1])  # :695-703
             h = C.c_void_p()
@@ -572,14 +598,16 @@ class MatrixCSR:
 
     @property
     def indices(self):
-        return self._pattern.graph[0]
+        return self._expanded[0] if self._expanded is not None else self._pattern.graph[0]
 
     @property
     def indptr(self):
-        return self._pattern.graph[1]
+        return self._expanded[1] if self._expanded is not None else self._pattern.graph[1]
 
     @property
     def off_diag_offset(self):
+        if self._expanded is not None:
+            return self._expanded[2]
         return self._pattern.off_diagonal_offsets.astype(np.int64) + self.indptr[:-1]
 
     def num_owned_rows(self):

@@ -667,3 +667,58 @@ def test_interior_facets_dS(bfx, oracle):
     oracle.assemble_matrix_interior_facets(oracle.K_AVG_MASS_P1_TRI_DS, p.x_dofmap, p.x, facets, p.dofmap, 1, p.dofmap, 1,
                                            ref2, pat.edges, pat.offsets, bc0=mk, bc1=mk)
     check_matrix(A2, pat, ref2)
+
+
+def test_block_mode_expanded(bfx, oracle):
+    """MatrixCSR(pattern, BlockMode.expanded) (la/MatrixCSR.h:638-694; python/test/unit/la/test_matrix_csr.py:70-107):
+    the structure against a literal restatement of the reference loop, blocked data added to the compact and the
+    expanded matrix give the same dense matrix, and both multiply alike."""
+    la, common, torch = bfx.la, bfx.common, bfx.torch
+    n, bs0, bs1 = 9, 2, 3
+    im = common.IndexMap(common.COMM_SELF, n)
+    sp = la.SparsityPattern(common.COMM_SELF, [im, im], [bs0, bs1])
+    rng = np.random.default_rng(7)
+    for r in range(n):
+        sp.insert([r], np.unique(rng.integers(0, n, size=4)))
+    sp.insert_diagonal(np.arange(n))
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    B = la.MatrixCSR(sp, la.BlockMode.expanded)
+    assert B.bs == (1, 1) and B.index_map(0).size_local == n * bs0 and B.index_map(1).size_local == n * bs1
+    edges, offsets = sp.graph
+    cols_ref, ptr_ref = [], [0]
+    for i in range(n):  # the reference loop, :671-687
+        for q0 in range(bs0):
+            for j in range(offsets[i], offsets[i + 1]):
+                for q1 in range(bs1):
+                    cols_ref.append(edges[j] * bs1 + q1)
+            ptr_ref.append(len(cols_ref))
+    assert np.array_equal(B.indices, np.array(cols_ref, dtype=np.int32)) and np.array_equal(B.indptr, np.array(ptr_ref))
+    assert np.array_equal(B.off_diag_offset, np.array(ptr_ref[1:]))  # one rank: every column is owned
+    # the same dense matrix stored in both: block values into the compact matrix, scalars into the expanded one
+    dense = rng.random((n * bs0, n * bs1))
+    mask = np.zeros_like(dense, dtype=bool)
+    for r in range(n):
+        for c in edges[offsets[r]:offsets[r + 1]]:
+            mask[r * bs0:(r + 1) * bs0, c * bs1:(c + 1) * bs1] = True
+    dense[~mask] = 0.0
+    A.set_value(0.0)
+    vals = np.zeros(A.data.numel())
+    for r in range(n):
+        for k, c in enumerate(edges[offsets[r]:offsets[r + 1]]):
+            vals[(offsets[r] + k) * bs0 * bs1:(offsets[r] + k + 1) * bs0 * bs1] = dense[r * bs0:(r + 1) * bs0, c * bs1:(c + 1) * bs1].reshape(-1)
+    A.data.copy_(torch.from_numpy(vals))
+    for R in range(n * bs0):  # scalar entries into the expanded matrix (insert_csr with bs = 1)
+        cols = B.indices[B.indptr[R]:B.indptr[R + 1]]
+        B.add(dense[R, cols], [R], cols, 1)
+    assert np.array_equal(A.to_dense(), dense) and np.array_equal(B.to_dense(), dense)
+    x = la.Vector(A.index_map(1), bs1)
+    xe = la.Vector(B.index_map(1), 1)
+    xh = rng.random(n * bs1)
+    x.array.copy_(torch.from_numpy(xh))
+    xe.array.copy_(torch.from_numpy(xh))
+    y = la.Vector(A.index_map(0), bs0)
+    ye = la.Vector(B.index_map(0), 1)
+    A.mult(x, y)
+    B.mult(xe, ye)
+    assert np.allclose(y.array.cpu().numpy(), dense @ xh, rtol=1e-14) and np.allclose(ye.array.cpu().numpy(), dense @ xh, rtol=1e-14)
