@@ -122,6 +122,8 @@ _SIGS = {
     "bfx_assemble_vector_facets": ([vp, ci, vp, vp, i64, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),
     "bfx_pack_coefficient": ([vp, ci, ci, vp, vp, ci, ci, vp, vp, i64, vp], ci),
     "bfx_assemble_matrix_cells_host": ([vp, ci, vp, i64, vp, vp, i64, vp, i64, ci, C.POINTER(f64), ci, vp, ci, vp], ci),
+    "bfx_assemble_matrix_cells_host_begin": ([vp, ci, vp, i64, vp, vp, i64, vp, i64, ci, C.POINTER(f64), ci, vp, ci], ci),
+    "bfx_assemble_matrix_cells_host_end": ([vp], ci),
     "bfx_bc_mark": ([vp, vp, i64, vp], ci),
     "bfx_bc_set": ([vp, i32, vp, vp, i64, vp, ci, ci, vp, f64, vp], ci),
     "bfx_dot": ([i64, vp, vp, C.POINTER(f64), vp], ci),

@@ -1090,11 +1090,20 @@ int bfx_asm_destroy(bfx_asm_t* P)
   cudaFree(P->lift_count);
   free_chunks(P->chunks);
   free_rowgather(P->rowgather);
-  cudaFree(P->h_x);
-  cudaFree(P->h_coeff);
-  cudaFree(P->h_bc0);
-  cudaFree(P->h_bc1);
-  cudaFree(P->h_values);
+  for (auto& h : P->hs)
+  {
+    cudaFree(h.x);
+    cudaFree(h.coeff);
+    cudaFree(h.bc0);
+    cudaFree(h.bc1);
+    cudaFree(h.values);
+    if (h.st)
+      cudaStreamDestroy(h.st);
+    if (h.done)
+      cudaEventDestroy(h.done);
+    if (h.computed)
+      cudaEventDestroy(h.computed);
+  }
   delete P;
   return BFX_OK;
 }
@@ -1291,64 +1300,111 @@ int bfx_bc_set(double* x, int32_t x_size, const int32_t* dofs0, const int32_t* d
   return BFX_OK;
 }
 
+int bfx_assemble_matrix_cells_host_begin(bfx_asm_t* P, int kernel_id, const double* x_host, int64_t n_x_nodes,
+                                         const int8_t* bc0_host, const int8_t* bc1_host, int64_t n_bc,
+                                         const double* coeff_values_host, int64_t n_coeff_values, int coeff_bs,
+                                         const double* constants, int n_constants, double* values_host, int strategy)
+{
+  BFX_REQUIRE(P && P->csr && x_host && values_host, "bfx_assemble_matrix_cells_host: null argument");
+  bfx_asm::HostSlot& h = P->hs[P->hs_next];
+  if (h.busy)
+    return fail(BFX_ERR_INVALID, "bfx_assemble_matrix_cells_host_begin: two calls are already in flight (call _end)");
+  if (!h.st)
+  {
+    BFX_CUDA(cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking));
+    BFX_CUDA(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+    BFX_CUDA(cudaEventCreateWithFlags(&h.computed, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h.st;
+  const size_t nval = (size_t)P->csr->nnz * P->csr->bs0 * P->csr->bs1;
+  // device scratch is allocated on first use and kept by the plan
+  if (!h.x || h.x_n < n_x_nodes)
+  {
+    cudaFree(h.x);
+    BFX_CUDA(cudaMalloc(&h.x, sizeof(double) * 3 * (size_t)n_x_nodes));
+    h.x_n = n_x_nodes;
+  }
+  if (!h.values)
+    BFX_CUDA(cudaMalloc(&h.values, sizeof(double) * nval));
+  if (n_bc > 0 && (!h.bc0 || h.bc_n < n_bc))
+  {
+    cudaFree(h.bc0);
+    cudaFree(h.bc1);
+    BFX_CUDA(cudaMalloc(&h.bc0, (size_t)n_bc));
+    BFX_CUDA(cudaMalloc(&h.bc1, (size_t)n_bc));
+    h.bc_n = n_bc;
+  }
+  if (n_coeff_values > 0 && (!h.coeff || h.coeff_n < n_coeff_values))
+  {
+    cudaFree(h.coeff);
+    BFX_CUDA(cudaMalloc(&h.coeff, sizeof(double) * (size_t)n_coeff_values));
+    h.coeff_n = n_coeff_values;
+  }
+  BFX_CUDA(cudaMemcpyAsync(h.x, x_host, sizeof(double) * 3 * (size_t)n_x_nodes, cudaMemcpyHostToDevice, st));
+  if (bc0_host)
+    BFX_CUDA(cudaMemcpyAsync(h.bc0, bc0_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
+  const bool one_marker_array = bc1_host && bc1_host == bc0_host; // same space: rows and columns share the markers
+  if (bc1_host && !one_marker_array)
+    BFX_CUDA(cudaMemcpyAsync(h.bc1, bc1_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
+  bfx_coeffs_t cf;
+  memset(&cf, 0, sizeof(cf));
+  if (coeff_values_host && n_coeff_values > 0)
+  {
+    BFX_CUDA(cudaMemcpyAsync(h.coeff, coeff_values_host, sizeof(double) * (size_t)n_coeff_values,
+                             cudaMemcpyHostToDevice, st));
+    cf.n_fused = 1;
+    cf.fused[0].values_dev = h.coeff;
+    cf.fused[0].dofmap_dev = P->dofmap0;
+    cf.fused[0].nd = P->nd0;
+    cf.fused[0].bs = coeff_bs;
+  }
+  BFX_CUDA(cudaMemsetAsync(h.values, 0, sizeof(double) * nval, st));
+  // the assembly kernels of the two slots share the plan's per-call scratch (packed marker bits, row-gather cell
+  // records): they run one after the other; only the copies of one slot overlap the kernels of the other
+  const bfx_asm::HostSlot& other = P->hs[P->hs_next ^ 1];
+  if (other.computed && other.used)
+    BFX_CUDA(cudaStreamWaitEvent(st, other.computed, 0));
+  int e = bfx_assemble_matrix_cells(P, kernel_id, h.x, bc0_host ? h.bc0 : nullptr,
+                                    bc1_host ? (one_marker_array ? h.bc0 : h.bc1) : nullptr, &cf, constants,
+                                    n_constants, h.values, strategy, BFX_VALUES_OVERWRITE,
+                                    reinterpret_cast<bfx_stream_t>(st));
+  if (e)
+    return e;
+  BFX_CUDA(cudaEventRecord(h.computed, st));
+  h.used = true;
+  BFX_CUDA(cudaMemcpyAsync(values_host, h.values, sizeof(double) * nval, cudaMemcpyDeviceToHost, st));
+  BFX_CUDA(cudaEventRecord(h.done, st));
+  h.busy = true;
+  P->hs_next ^= 1;
+  return BFX_OK;
+}
+
+int bfx_assemble_matrix_cells_host_end(bfx_asm_t* P)
+{
+  BFX_REQUIRE(P, "bfx_assemble_matrix_cells_host_end: null plan");
+  // the oldest call in flight: the slot begin() would use next if it is busy, else the other one
+  int s = P->hs[P->hs_next].busy ? P->hs_next : (P->hs_next ^ 1);
+  bfx_asm::HostSlot& h = P->hs[s];
+  if (!h.busy)
+    return fail(BFX_ERR_INVALID, "bfx_assemble_matrix_cells_host_end: no call in flight");
+  BFX_CUDA(cudaEventSynchronize(h.done));
+  h.busy = false;
+  return BFX_OK;
+}
+
 int bfx_assemble_matrix_cells_host(bfx_asm_t* P, int kernel_id, const double* x_host, int64_t n_x_nodes,
                                    const int8_t* bc0_host, const int8_t* bc1_host, int64_t n_bc,
                                    const double* coeff_values_host, int64_t n_coeff_values, int coeff_bs,
                                    const double* constants, int n_constants, double* values_host, int strategy,
                                    bfx_stream_t stream)
 {
-  BFX_REQUIRE(P && P->csr && x_host && values_host, "bfx_assemble_matrix_cells_host: null argument");
-  cudaStream_t st = S(stream);
-  const size_t nval = (size_t)P->csr->nnz * P->csr->bs0 * P->csr->bs1;
-  // device scratch is allocated on first use and kept by the plan
-  if (!P->h_x || P->h_x_n < n_x_nodes)
-  {
-    cudaFree(P->h_x);
-    BFX_CUDA(cudaMalloc(&P->h_x, sizeof(double) * 3 * (size_t)n_x_nodes));
-    P->h_x_n = n_x_nodes;
-  }
-  if (!P->h_values)
-    BFX_CUDA(cudaMalloc(&P->h_values, sizeof(double) * nval));
-  if (n_bc > 0 && (!P->h_bc0 || P->h_bc_n < n_bc))
-  {
-    cudaFree(P->h_bc0);
-    cudaFree(P->h_bc1);
-    BFX_CUDA(cudaMalloc(&P->h_bc0, (size_t)n_bc));
-    BFX_CUDA(cudaMalloc(&P->h_bc1, (size_t)n_bc));
-    P->h_bc_n = n_bc;
-  }
-  if (n_coeff_values > 0 && (!P->h_coeff || P->h_coeff_n < n_coeff_values))
-  {
-    cudaFree(P->h_coeff);
-    BFX_CUDA(cudaMalloc(&P->h_coeff, sizeof(double) * (size_t)n_coeff_values));
-    P->h_coeff_n = n_coeff_values;
-  }
-  BFX_CUDA(cudaMemcpyAsync(P->h_x, x_host, sizeof(double) * 3 * (size_t)n_x_nodes, cudaMemcpyHostToDevice, st));
-  if (bc0_host)
-    BFX_CUDA(cudaMemcpyAsync(P->h_bc0, bc0_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
-  const bool one_marker_array = bc1_host && bc1_host == bc0_host; // same space: rows and columns share the markers
-  if (bc1_host && !one_marker_array)
-    BFX_CUDA(cudaMemcpyAsync(P->h_bc1, bc1_host, (size_t)n_bc, cudaMemcpyHostToDevice, st));
-  bfx_coeffs_t cf;
-  memset(&cf, 0, sizeof(cf));
-  if (coeff_values_host && n_coeff_values > 0)
-  {
-    BFX_CUDA(cudaMemcpyAsync(P->h_coeff, coeff_values_host, sizeof(double) * (size_t)n_coeff_values,
-                             cudaMemcpyHostToDevice, st));
-    cf.n_fused = 1;
-    cf.fused[0].values_dev = P->h_coeff;
-    cf.fused[0].dofmap_dev = P->dofmap0;
-    cf.fused[0].nd = P->nd0;
-    cf.fused[0].bs = coeff_bs;
-  }
-  BFX_CUDA(cudaMemsetAsync(P->h_values, 0, sizeof(double) * nval, st));
-  int e = bfx_assemble_matrix_cells(P, kernel_id, P->h_x, bc0_host ? P->h_bc0 : nullptr,
-                                    bc1_host ? (one_marker_array ? P->h_bc0 : P->h_bc1) : nullptr,
-                                    &cf, constants, n_constants, P->h_values, strategy, BFX_VALUES_OVERWRITE, stream);
+  (void)stream; // the copies and kernels of this entry run on the plan's own streams
+  BFX_REQUIRE(P && !P->hs[0].busy && !P->hs[1].busy, "bfx_assemble_matrix_cells_host: asynchronous calls are in flight");
+  int e = bfx_assemble_matrix_cells_host_begin(P, kernel_id, x_host, n_x_nodes, bc0_host, bc1_host, n_bc,
+                                               coeff_values_host, n_coeff_values, coeff_bs, constants, n_constants,
+                                               values_host, strategy);
   if (e)
     return e;
-  BFX_CUDA(cudaMemcpyAsync(values_host, P->h_values, sizeof(double) * nval, cudaMemcpyDeviceToHost, st));
-  BFX_CUDA(cudaStreamSynchronize(st));
-  return BFX_OK;
+  return bfx_assemble_matrix_cells_host_end(P);
 }
 }

@@ -112,9 +112,18 @@ struct bfx_asm
   char* pos = nullptr;
   int pos_bytes = 1, pos_stride = 0;
   // scratch of the host-buffer entry point
-  double *h_x = nullptr, *h_coeff = nullptr, *h_values = nullptr;
-  int8_t *h_bc0 = nullptr, *h_bc1 = nullptr;
-  int64_t h_x_n = 0, h_coeff_n = 0, h_bc_n = 0;
+  // (two slots: a call may be in flight on each, so that the device-to-host copy of one step overlaps the
+  // host-to-device copy and the kernels of the next: bfx_assemble_matrix_cells_host_begin / _end)
+  struct HostSlot
+  {
+    double *x = nullptr, *coeff = nullptr, *values = nullptr;
+    int8_t *bc0 = nullptr, *bc1 = nullptr;
+    int64_t x_n = 0, coeff_n = 0, bc_n = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr, computed = nullptr; // all work of the call / its kernels only
+    bool busy = false, used = false;
+  } hs[2];
+  int hs_next = 0; // slot the next begin() uses; end() waits for the oldest busy slot
   bfx_chunks* chunks = nullptr;
   bfx_rowgather* rowgather = nullptr;
   // lifting scratch: cells with a Dirichlet column dof (rebuilt by every call)

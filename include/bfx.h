@@ -282,6 +282,19 @@ extern "C"
                                      const double* coeff_values_host, int64_t n_coeff_values, int coeff_bs,
                                      const double* constants_host, int n_constants, double* values_host,
                                      int strategy, bfx_stream_t stream);
+  /* The same entry split in two, so that a caller in a time loop can keep two steps in flight: begin() enqueues
+   * host-to-device copies, zero-fill, assembly and the device-to-host copy of the values on one of the plan's two
+   * internal streams and returns; end() waits for the OLDEST call in flight, after which its values_host is
+   * complete.  With begin(k+1) issued before end(k) the device-to-host copy of step k (2 GB at C2, PCIe bound)
+   * overlaps the uploads and kernels of step k+1 (the kernels of the two calls themselves run one after the other:
+   * they share the plan's per-call scratch).  Host buffers must be pinned and must not be reused before the
+   * matching end(); at most two calls may be in flight (a third begin() returns BFX_ERR_INVALID). */
+  int bfx_assemble_matrix_cells_host_begin(bfx_asm_t* plan, int kernel_id, const double* x_host, int64_t n_x_nodes,
+                                           const int8_t* bc0_host, const int8_t* bc1_host, int64_t n_bc,
+                                           const double* coeff_values_host, int64_t n_coeff_values, int coeff_bs,
+                                           const double* constants_host, int n_constants, double* values_host,
+                                           int strategy);
+  int bfx_assemble_matrix_cells_host_end(bfx_asm_t* plan);
 
   /* ---- Dirichlet conditions ----------------------------------------------------------------- */
   /* DirichletBC::mark_dofs — fem/DirichletBC.h:589-601 */

@@ -506,6 +506,37 @@ def test_host_buffer_entry(bfx, oracle):
     assert P.row_scaled_error(out, ref, pat.offsets) <= TOL
 
 
+def test_host_buffer_entry_two_in_flight(bfx, oracle):
+    """bfx_assemble_matrix_cells_host_begin/_end: two calls in flight on the plan's two slots, results in call
+    order; a third begin and an end without a call in flight are refused."""
+    fem, la, lib = bfx.fem, bfx.la, bfx.lib
+    p = P.tet_p1(6, numbering="first_touch")
+    msh, V = make_space(bfx, p)
+    a, sp, A = assemble_A(bfx, V, lib.K_POISSON_P1_TET_A, constants=[2.0])
+    plan = fem._asm_plan(a, a.integral(fem.IntegralType.cell, 0), fem.IntegralType.cell, A)
+    outs = [np.zeros(A.data.numel()) for _ in range(3)]
+    kappas = [2.0, 3.0, 5.0]
+
+    def begin(k):
+        carr, nc = lib.constants_array([kappas[k]])
+        return lib.lib.bfx_assemble_matrix_cells_host_begin(plan, lib.K_POISSON_P1_TET_A, p.x.ctypes.data, len(p.x), None,
+                                                            None, 0, None, 0, 1, carr, nc, outs[k].ctypes.data,
+                                                            lib.ASM_CHUNKED)
+
+    assert lib.lib.bfx_assemble_matrix_cells_host_end(plan) != 0
+    lib.check(begin(0))
+    lib.check(begin(1))
+    assert begin(2) != 0  # both slots busy
+    lib.check(lib.lib.bfx_assemble_matrix_cells_host_end(plan))  # call 0 complete
+    lib.check(begin(2))
+    lib.check(lib.lib.bfx_assemble_matrix_cells_host_end(plan))
+    lib.check(lib.lib.bfx_assemble_matrix_cells_host_end(plan))
+    assert lib.lib.bfx_assemble_matrix_cells_host_end(plan) != 0
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([1.0]))
+    for k in range(3):
+        assert P.row_scaled_error(outs[k], kappas[k] * ref, pat.offsets) <= TOL
+
+
 @pytest.mark.parametrize("degree", [1, 2])
 def test_matrix_free_action_and_cg(bfx, oracle, degree):
     """SURVEY.md §8f rank 2, the flow of cpp/demo/poisson_matrix_free/main.cpp:150-247 on a tet box: the action
