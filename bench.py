@@ -138,7 +138,13 @@ def build_problem(cfg, n, comm, device):
             cells_h = cells.cpu().numpy()
             dm_h, ndofs = M.p2_tet_dofmap(cells_h, nv)
             dofmap = torch.from_numpy(dm_h).to(device)
-            dof_x = None
+            # dof nodes: vertices, then edge midpoints (Basix edge order)
+            dof_x = torch.empty((ndofs, 3), dtype=torch.float64, device=device)
+            cl = cells.long()
+            dof_x[dofmap[:, :4].reshape(-1).long()] = x[cl.reshape(-1)]
+            for k, (va, vb) in enumerate(M.TET_EDGES):
+                dof_x[dofmap[:, 4 + k].long()] = 0.5 * (x[cl[:, int(va)]] + x[cl[:, int(vb)]])
+            del cl
         im = common.IndexMap(comm, ndofs)
         n_cells_local = cells.shape[0]
         msh = fem.Mesh(comm, x, cells, cell, n_cells_local)

@@ -56,6 +56,7 @@ ERR_UNSUPPORTED = 4
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
 CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
 CHUNKS_SHARED_MATRIX = 4
+CHUNKS_ALT_CB = 8  # 384 (P1) / 96 (P2) cells per chunk
 CHUNKS_SYMMETRIC = 1  # every chunked kernel (ids 0, 2, 6, 8) has a symmetric element matrix
 VALUES_ADD, VALUES_OVERWRITE = 0, 1
 SPMV_FULL, SPMV_DIAG, SPMV_OFFDIAG = 0, 1, 2

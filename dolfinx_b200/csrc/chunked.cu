@@ -40,6 +40,13 @@ constexpr int MAX_LIST = 255;
 constexpr int chunk_cb(int ns) { return ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0)); }
 // threads per chunk: one per cell for small element matrices, several per cell (rows dealt round-robin) else
 constexpr int chunk_threads(int ns) { return 256; }
+// alternative chunk geometry (BFX_CHUNKS_ALT_CB): under the Morton order of a Kuhn box (6 tetrahedra per cube, all six
+// contiguous) 256 or 128 cells cut the chunks through the cubes (42.7 / 21.3 cubes); 384 cells are a 4x4x4 brick of
+// whole cubes and 96 cells a 2x2x4 brick: fewer chunk-boundary destinations per cell (P1: 0.96 instead of 1.42
+// RED pairs per cell, P2: 9.8 instead of 11.1; brute-force counts in DESIGN.md section 4.2)
+constexpr int chunk_cb_alt(int ns) { return ns <= 16 ? 384 : (ns == 55 ? 96 : 0); }
+constexpr int chunk_threads_alt(int ns) { return ns <= 16 ? 384 : 288; }
+constexpr int chunk_min_ctas(int threads) { return threads <= 256 ? 4 : (threads <= 384 ? 3 : 2); }
 // largest element (staged scalars per cell) that gets the bank-coloured staging layout: the colours of a cell
 // travel in registers
 constexpr int COLOUR_MAX_NS = 36; // (measured: P2 Poisson, 55 staged entries, is bound by its chunk-boundary REDs, not by bank conflicts)
@@ -385,6 +392,7 @@ int run_plan_pass_items(int items, bool write, const ChunkBuildArgs& p, int64_t 
   case 3: return run_plan_pass<3>(write, p, nchunks, st);
   case 4: return run_plan_pass<4>(write, p, nchunks, st);
   case 5: return run_plan_pass<5>(write, p, nchunks, st);
+  case 6: return run_plan_pass<6>(write, p, nchunks, st);
   case 7: return run_plan_pass<7>(write, p, nchunks, st);
   case 8: return run_plan_pass<8>(write, p, nchunks, st);
   case 9: return run_plan_pass<9>(write, p, nchunks, st);
@@ -778,7 +786,7 @@ struct ChunkSmem
 };
 
 template <class E, bool SYM, int CB, int THREADS, typename AddrT>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2)) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
+__global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
   constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, NS = staged_per_cell(N, SYM), TPC = THREADS / CB;
   constexpr int DS = SYM ? 2 : 1; // addresses per destination
@@ -1029,11 +1037,10 @@ __global__ void k_pack_marker_bits(int64_t n, const int8_t* __restrict__ markers
   }
 }
 
-template <class E, bool SYM>
-int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
+template <class E, bool SYM, int CB, int THREADS>
+int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
 {
   constexpr int N = E::ND * E::BS, NS = staged_per_cell(N, SYM);
-  constexpr int CB = chunk_cb(NS), THREADS = chunk_threads(NS);
   static_assert(CB > 0, "element too large for the chunked path");
   const bfx_chunks* c = P->chunks;
   if (c->cb != CB || c->n2 != NS)
@@ -1081,6 +1088,19 @@ int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   }
   BFX_CHECK_LAUNCH();
   return BFX_OK;
+}
+
+// the plan fixes the chunk geometry (bfx_asm_build_chunks: default or BFX_CHUNKS_ALT_CB)
+template <class E, bool SYM>
+int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
+{
+  constexpr int NS = staged_per_cell(E::ND * E::BS, SYM);
+  if constexpr (chunk_cb_alt(NS) > 0)
+  {
+    if (P->chunks->cb == chunk_cb_alt(NS))
+      return launch_chunked_cb<E, SYM, chunk_cb_alt(NS), chunk_threads_alt(NS)>(P, a, values_mode, st);
+  }
+  return launch_chunked_cb<E, SYM, chunk_cb(NS), chunk_threads(NS)>(P, a, values_mode, st);
 }
 
 // The symmetric plan needs a symmetric element matrix (all chunked kernels are) AND symmetric bc zeroing:
@@ -1406,7 +1426,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   if (sym && !(csr->bs0 == 1 && csr->bs1 == 1 && P->nd0 == P->nd1 && (!P->dofmap1 || P->dofmap1 == P->dofmap0)))
     return fail(BFX_ERR_UNSUPPORTED, "symmetric chunk plan needs block size 1 and one dofmap for rows and columns");
   const int n2 = sym ? staged_per_cell(P->nd0, true) : P->nd0 * csr->bs0 * P->nd1 * csr->bs1; // staged per cell
-  const int cb = chunk_cb(n2);
+  const int cb = ((flags & BFX_CHUNKS_ALT_CB) && chunk_cb_alt(n2) > 0) ? chunk_cb_alt(n2) : chunk_cb(n2);
   if (cb == 0 || P->ncells == 0)
     return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d staged scalars are not supported", n2);
   const int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
@@ -1601,6 +1621,11 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     {
       BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_chunk_colour<128><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
+    }
+    else if (cb == 384)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_chunk_colour<384><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
     }
     else
       return bail(fail(BFX_ERR_INVALID, "chunk plan: no colouring kernel for %d cells per chunk", cb));

@@ -408,6 +408,8 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
 # 2.1 ms of the cell-parallel kernel for the C2 load vector (both are bound by the L1/LSU pipe, not by the REDs)
 GROUPED_VECTORS = os.environ.get("BFX_GROUPED_VECTORS", "0") != "0"
 CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
+# chunk size: default 256 (P1) / 128 (P2) cells, alternative 384 / 96 (bricks of whole cubes on Kuhn boxes)
+CHUNKS_ALT_CB = os.environ.get("BFX_CHUNKS_ALT_CB", "0") != "0"
 
 
 def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=False):
@@ -429,6 +431,8 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
         if want == _lib.ASM_CHUNKED:
             V0, V1 = form.function_spaces
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
+            if CHUNKS_ALT_CB:
+                flags |= _lib.CHUNKS_ALT_CB
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())

@@ -213,6 +213,8 @@ extern "C"
    * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
   enum
   {
+    BFX_CHUNKS_ALT_CB = 8, /* alternative chunk size: 384 cells (P1 kernels) / 96 cells (P2 Poisson, symmetric) per
+                            * chunk instead of 256 / 128 - whole-cube bricks under the Morton order of a Kuhn box */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
                                      zero-fill and this plan's launch (boundary/interior split): an entry counts as
                                      complete only if EVERY cell of the dofmap that touches it lies in one chunk of this

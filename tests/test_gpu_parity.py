@@ -70,9 +70,10 @@ def test_poisson_p1_matrix(bfx, oracle, n, numbering):
     assert A.squared_norm() == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
 
 
+@pytest.mark.parametrize("alt_cb", [False, True])
 @pytest.mark.parametrize("symmetric", [True, False])
 @pytest.mark.parametrize("case", ["p1_lex", "p1_random", "p2", "tri"])
-def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, monkeypatch):
+def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, monkeypatch):
     """Both scatter-add strategies against the oracle on meshes spanning many chunks: the
     chunk-aggregated kernel (default; complete destinations by plain update, chunk-boundary ones by
     RED) and the plain fp64-RED kernel; then re-assembly without zeroing (values += , the
@@ -80,6 +81,8 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, monkeypatch
     fem, K = bfx.fem, bfx.lib
     # symmetric plan: upper triangle staged, (i,j)/(j,i) entries updated from one sum; general plan otherwise
     monkeypatch.setattr(fem, "CHUNKS_SYMMETRIC", symmetric)
+    # alternative chunk size (BFX_CHUNKS_ALT_CB): 384 cells for the P1 kernels, 96 for symmetric P2
+    monkeypatch.setattr(fem, "CHUNKS_ALT_CB", alt_cb)
     if case.startswith("p1"):
         p = P.tet_p1(13, numbering="lex" if case == "p1_lex" else "random", seed=5)
         kern, okern, consts = K.K_POISSON_P1_TET_A, oracle.K_POISSON_P1_TET_A, [2.0]
@@ -99,6 +102,9 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, monkeypatch
         if strategy == K.ASM_CHUNKED:
             nchunks, ndest, nsrc, nbytes = fem.chunk_stats(a, A)
             assert nchunks > 4 and nsrc >= ref.size // 2 and ndest >= (len(pat.edges) // 2 if symmetric else len(pat.edges))
+            if alt_cb and (case != "p2" or symmetric):
+                cb = 96 if case == "p2" else 384
+                assert nchunks == -(-len(p.dofmap) // cb)
     # default strategy = chunk-aggregated for the P1 kernels
     a, sp, A = assemble_A(bfx, V, kern, constants=consts)
     if kern in K.CHUNKED_KERNELS:
