@@ -394,7 +394,7 @@ def main():
     if strat_used == K.ASM_CHUNKED and world == 1:
         nch, ndest, nsrc, pbytes = fem.chunk_stats(a, A)
         plan_info = {"chunks": nch, "destinations": ndest, "list_entries": nsrc, "plan_bytes": pbytes,
-                     "bank_conflicts_left": fem.chunk_bank_conflicts(a, A)}
+                     "bank_conflicts_left": fem.chunk_bank_conflicts(a, A), "two_stage_writeback": fem.chunk_two_stage(a, A)}
     nnz = A._nnz
     n_rows = A.num_all_rows()
     n_cols = A.index_map(1).size_local + A.index_map(1).num_ghosts

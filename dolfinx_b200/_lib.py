@@ -56,7 +56,13 @@ ERR_UNSUPPORTED = 4
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
 CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
 CHUNKS_SHARED_MATRIX = 4
-CHUNKS_ALT_CB = 8  # 384 (P1) / 96 (P2) cells per chunk
+CHUNKS_TWO_STAGE = 8  # write-back in address order through shared memory (symmetric P1 plans)
+
+
+def CHUNKS_CB(cells):
+    """BFX_CHUNKS_CB(cells): cells per chunk other than the element's default (flags of bfx_asm_build_chunks)."""
+    return ((cells // 32) & 0xFF) << 8
+
 CHUNKS_SYMMETRIC = 1  # every chunked kernel (ids 0, 2, 6, 8) has a symmetric element matrix
 VALUES_ADD, VALUES_OVERWRITE = 0, 1
 SPMV_FULL, SPMV_DIAG, SPMV_OFFDIAG = 0, 1, 2
@@ -114,6 +120,7 @@ _SIGS = {
     "bfx_asm_build_rowgather": ([vp, vp], ci),
     "bfx_asm_build_groups": ([vp, vp, vp], ci),
     "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
+    "bfx_asm_chunk_two_stage": ([vp, C.POINTER(ci)], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),

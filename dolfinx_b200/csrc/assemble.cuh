@@ -63,6 +63,10 @@ struct bfx_chunks
   ChunkHdr* hdr = nullptr;
   uint32_t* winfo = nullptr;  // per group of 32 destinations: (offset of its source lists / 32) << 8 | list length
   void* dest_addr = nullptr;  // scalar index into values per destination
+  // two-stage write-back (BFX_CHUNKS_TWO_STAGE): (address, destination rank | incomplete << 15) of every CSR value the
+  // chunk updates, sorted by address; replaces dest_addr
+  uint32_t* wr_addr = nullptr;
+  uint16_t* wr_src = nullptr;
   int addr_bytes = 4;
   uint16_t* src = nullptr;    // source lists: shared-memory slots of the staged entries, 32-way interleaved
   // bank-conflict-free staging (small element matrices): slot of entry k of cell c = (k * cb/16 + c/16) * 16 +

@@ -40,13 +40,19 @@ constexpr int MAX_LIST = 255;
 constexpr int chunk_cb(int ns) { return ns <= 36 ? 256 : (ns <= 64 ? 128 : (ns <= 100 ? 64 : 0)); }
 // threads per chunk: one per cell for small element matrices, several per cell (rows dealt round-robin) else
 constexpr int chunk_threads(int ns) { return 256; }
-// alternative chunk geometry (BFX_CHUNKS_ALT_CB): under the Morton order of a Kuhn box (6 tetrahedra per cube, all six
-// contiguous) 256 or 128 cells cut the chunks through the cubes (42.7 / 21.3 cubes); 384 cells are a 4x4x4 brick of
-// whole cubes and 96 cells a 2x2x4 brick: fewer chunk-boundary destinations per cell (P1: 0.96 instead of 1.42
-// RED pairs per cell, P2: 9.8 instead of 11.1; brute-force counts in DESIGN.md section 4.2)
-constexpr int chunk_cb_alt(int ns) { return ns <= 16 ? 384 : (ns == 55 ? 96 : 0); }
-constexpr int chunk_threads_alt(int ns) { return ns <= 16 ? 384 : 288; }
-constexpr int chunk_min_ctas(int threads) { return threads <= 256 ? 4 : (threads <= 384 ? 3 : 2); }
+// alternative chunk sizes (bfx_asm_build_chunks flags, BFX_CHUNKS_CB(cells)): under the Morton order of a Kuhn box
+// (6 tetrahedra per cube, all six contiguous) 256 or 128 cells cut the chunks through the cubes (42.7 / 21.3 cubes);
+// 96 / 192 / 384 cells are 2x2x4 / 4x4x2 / 4x4x4 bricks of whole cubes with fewer chunk-boundary destinations per
+// cell (P1 RED pairs per cell: 96: 1.61, 128: 1.80, 192: 1.25, 256: 1.38, 384: 0.96; measured times in DESIGN.md 4.2)
+constexpr bool chunk_cb_supported(int ns, int cb)
+{
+  return ns <= 16 ? (cb == 96 || cb == 128 || cb == 192 || cb == 384) : (ns == 55 ? (cb == 64 || cb == 96) : false);
+}
+constexpr int chunk_threads_for(int ns, int cb) { return ns <= 16 ? cb : (cb == 96 ? 288 : 256); }
+constexpr int chunk_min_ctas(int threads)
+{
+  return threads <= 96 ? 10 : (threads <= 128 ? 8 : (threads <= 192 ? 5 : (threads <= 256 ? 4 : (threads <= 384 ? 3 : 2))));
+}
 // largest element (staged scalars per cell) that gets the bank-coloured staging layout: the colours of a cell
 // travel in registers
 constexpr int COLOUR_MAX_NS = 36; // (measured: P2 Poisson, 55 staged entries, is bound by its chunk-boundary REDs, not by bank conflicts)
@@ -77,6 +83,11 @@ struct ChunkBuildArgs
   int addr_bytes;
   uint16_t* src;
   int* err;
+  // two-stage write-back (BFX_CHUNKS_TWO_STAGE): every (address, destination rank) pair of the chunk - both entries
+  // of a symmetric pair - sorted by address, so that the lanes of the write-back pass hit consecutive CSR values
+  int two, dcap;       // dcap: destinations of a chunk the kernel holds in shared memory
+  uint32_t* wr_addr;   // 2 * n_dest_pad entries, chunk q at 2 * dest_base
+  uint16_t* wr_src;    // destination rank | 0x8000 if the destination is incomplete (RED)
 };
 
 __device__ __forceinline__ uint32_t pos_at(const char* pos, int pos_stride, int pos_bytes, int64_t e, int t)
@@ -296,6 +307,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
     {
       p.o_ndw[q] = (n_dw + 3) & ~3; // 16-byte aligned winfo / 128-destination aligned chunks (TMA)
       p.o_nsrc32[q] = n_src32;
+      if (p.two && (n_dest > p.dcap || 2 * n_dest > NK))
+        atomicMax(p.err, 5); // the host drops the two-stage write-back and goes on
     }
     return;
   }
@@ -335,7 +348,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
         addr = contrib_addr(p, q, sidx[st], blk, other);
       }
       const int64_t at = (dest_base + r) * (p.sym ? 2 : 1);
-      if (p.addr_bytes == 4)
+      if (p.two)
+        ; // the addresses go to the sorted write-back lists below
+      else if (p.addr_bytes == 4)
       {
         static_cast<uint32_t*>(p.dest_addr)[at] = (uint32_t)addr;
         if (p.sym)
@@ -350,6 +365,56 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
       for (int j = 0; j < m; ++j)
         out[j << 5] = j < cnt ? (uint16_t)(sidx[st + j] + sidx[st + j] / p.cb) : (uint16_t)(p.ns * (p.cb + 1));
     }
+    if (p.two)
+    {
+      // ---- 5. write-back lists: (address << 16 | incomplete << 15 | rank) of both entries of every destination,
+      //         sorted by address
+      uint64_t* wk = reinterpret_cast<uint64_t*>(((uintptr_t)(dstart + NK + 2) + 15) & ~(uintptr_t)15); // see plan_smem
+      int* wcnt = reinterpret_cast<int*>(wk + NK);
+      if (tid == 0)
+        *wcnt = 0;
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it)
+      {
+        const int r = tid * ITEMS + it;
+        if (r < n_dest)
+        {
+          const int d = v2[it];
+          int64_t blk, other;
+          const int64_t addr = contrib_addr(p, q, sidx[dstart[d]], blk, other);
+          const uint64_t tag = (uint64_t)(((k2[it] >> 8) & 1u) << 15) | (uint64_t)r;
+          const int at = atomicAdd(wcnt, other != addr ? 2 : 1);
+          wk[at] = ((uint64_t)addr << 16) | tag;
+          if (other != addr)
+            wk[at + 1] = ((uint64_t)other << 16) | tag;
+        }
+      }
+      __syncthreads();
+      const int n_wr = *wcnt;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it)
+      {
+        const int k = tid * ITEMS + it;
+        keys[it] = k < n_wr ? wk[k] : ~0ull;
+      }
+      __syncthreads();
+      Sort1(temp.s1).Sort(keys, 16, 16 + p.addr_bits);
+      const int n_wr_pad = (n_wr + 31) & ~31;
+      const int64_t wr_base = 2 * dest_base;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it)
+      {
+        const int k = tid * ITEMS + it;
+        if (k < n_wr_pad)
+        {
+          p.wr_addr[wr_base + k] = k < n_wr ? (uint32_t)(keys[it] >> 16) : 0u;
+          p.wr_src[wr_base + k] = k < n_wr ? (uint16_t)(keys[it] & 0xffffu) : (uint16_t)0;
+        }
+      }
+      if (tid == 0)
+        p.hdr[q].pad = n_wr;
+    }
   }
 }
 
@@ -363,7 +428,9 @@ size_t plan_smem()
   t = t > sizeof(typename Sort2::TempStorage) ? t : sizeof(typename Sort2::TempStorage);
   t = t > sizeof(typename Scan::TempStorage) ? t : sizeof(typename Scan::TempStorage);
   t = (t + 15) / 16 * 16;
-  return t + PLAN_THREADS * 8 + PLAN_THREADS * 4 * 2 + (size_t)(2 * PLAN_THREADS * ITEMS + 2) * 2 + 16;
+  // + the staging array of the two-stage write-back lists (NK keys of 8 bytes, a counter, alignment slack)
+  return t + PLAN_THREADS * 8 + PLAN_THREADS * 4 * 2 + (size_t)(2 * PLAN_THREADS * ITEMS + 2) * 2 + 16
+         + (size_t)PLAN_THREADS * ITEMS * 8 + 64;
 }
 
 template <int ITEMS>
@@ -388,6 +455,7 @@ int run_plan_pass_items(int items, bool write, const ChunkBuildArgs& p, int64_t 
 {
   switch (items)
   {
+  case 1: return run_plan_pass<1>(write, p, nchunks, st);
   case 2: return run_plan_pass<2>(write, p, nchunks, st);
   case 3: return run_plan_pass<3>(write, p, nchunks, st);
   case 4: return run_plan_pass<4>(write, p, nchunks, st);
@@ -736,6 +804,8 @@ struct ChunkArgs
   const uint32_t *bits0, *bits1;  // bit-packed Dirichlet markers or NULL
   int same_bc;                    // rows and columns share dofmap and markers
   int overwrite;
+  const uint32_t* wr_addr;        // two-stage write-back lists (see ChunkBuildArgs) or NULL
+  const uint16_t* wr_src;
 };
 
 // ---- TMA bulk copy + mbarrier (one chunk's lists are contiguous: two bulk copies per CTA) -----------
@@ -771,28 +841,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // shared-memory budget of the lists of one chunk (chunks over budget read their lists from global)
-template <int NS, int CB, int DSTRIDE>
+// destinations of one chunk the two-stage kernel holds in shared memory (typical P1 chunks: 0.22 NS CB)
+constexpr int two_stage_dcap(int ns, int cb) { return (ns * cb * 5 / 16) / 32 * 32; }
+
+template <int NS, int CB, int DSTRIDE, bool TWO = false>
 struct ChunkSmem
 {
   static constexpr int SRC_GROUPS = src_group_cap(NS * CB);        // 32-entry groups of source entries
-  static constexpr int DEST_BYTES = (NS * CB / 2) * 4 * DSTRIDE;  // destination addresses
+  static constexpr int DCAP = TWO ? two_stage_dcap(NS, CB) : NS * CB / 2;
+  static constexpr int DEST_BYTES = DCAP * 4 * DSTRIDE;           // destination addresses / write-back addresses
   static constexpr int WINFO = NS * CB / 32;                      // groups of 32 destinations
   static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)NS * (CB + 1) + 2) + 127) / 128 * 128;
   static constexpr size_t SRC_OFF = E_BYTES;
   static constexpr size_t DEST_OFF = SRC_OFF + (size_t)SRC_GROUPS * 64;
   static constexpr size_t WINFO_OFF = DEST_OFF + DEST_BYTES;
   static constexpr size_t BAR_OFF = WINFO_OFF + (((size_t)WINFO * 4 + 15) / 16) * 16 + 16;
-  static constexpr size_t TOTAL = BAR_OFF + 16;
+  static constexpr size_t WRSRC_OFF = BAR_OFF + 16;                 // two-stage: ranks of the write-back lists
+  static constexpr size_t SUM_OFF = WRSRC_OFF + (TWO ? (size_t)DCAP * 2 * 2 : 0); // two-stage: one sum per destination
+  static constexpr size_t TOTAL = SUM_OFF + (TWO ? (size_t)DCAP * 8 : 0);
 };
 
-template <class E, bool SYM, int CB, int THREADS, typename AddrT>
+// TWO (two-stage write-back, symmetric plans with 32-bit addresses): phase 2 leaves the sum of every destination in
+// shared memory; a third phase walks the chunk's (address, destination) list in ADDRESS order, so that consecutive
+// lanes update consecutive CSR values - both entries of a symmetric pair included - instead of two scattered ones each
+template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false>
 __global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
   constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, NS = staged_per_cell(N, SYM), TPC = THREADS / CB;
   constexpr int DS = SYM ? 2 : 1; // addresses per destination
   static_assert(THREADS % CB == 0 && CB % 32 == 0, "a warp must work on one row residue");
   static_assert(!SYM || BS == 1, "symmetric staging is implemented for block size 1");
-  using L = ChunkSmem<NS, CB, DS>;
+  static_assert(!TWO || (SYM && sizeof(AddrT) == 4), "two-stage write-back: symmetric plans, 32-bit addresses");
+  using L = ChunkSmem<NS, CB, DS, TWO>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Es = reinterpret_cast<double*>(smem_raw);
   uint16_t* s_src = reinterpret_cast<uint16_t*>(smem_raw + L::SRC_OFF);
@@ -834,10 +914,14 @@ __global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chu
   // ---- prefetch of the chunk's lists: TMA bulk copies land while phase 1 computes
   const ChunkHdr h = ch.hdr[q];
   const int n_dw = (h.n_dest + 31) >> 5;
-  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 32u * DS * (uint32_t)sizeof(AddrT);
+  const uint32_t n_wr_pad = TWO ? ((uint32_t)h.pad + 31u) & ~31u : 0u; // two-stage: (address, rank) pairs of the chunk
+  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u,
+                 dest_bytes = TWO ? n_wr_pad * 4u : (uint32_t)n_dw * 32u * DS * (uint32_t)sizeof(AddrT);
+  // (a two-stage plan is only built when the destinations of every chunk fit: bfx_asm_build_chunks)
   const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
   const uint16_t* g_src = ch.src + (h.src_base32 << 5);
-  const AddrT* g_dest = static_cast<const AddrT*>(ch.dest_addr) + h.dest_base * DS;
+  const AddrT* g_dest = TWO ? reinterpret_cast<const AddrT*>(ch.wr_addr) + h.dest_base * 2
+                            : static_cast<const AddrT*>(ch.dest_addr) + h.dest_base * DS;
   const uint32_t* g_winfo = ch.winfo + (h.dest_base >> 5);
   if (threadIdx.x == 0)
   {
@@ -847,10 +931,13 @@ __global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chu
     if (fits && n_dw > 0)
     {
       const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u; // chunks start on 4-group boundaries
-      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes);
+      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes + (TWO ? n_wr_pad * 2u : 0u));
       bulk_g2s(s_src, g_src, src_bytes, bar);
-      bulk_g2s(s_dest, g_dest, dest_bytes, bar);
+      if (dest_bytes > 0)
+        bulk_g2s(s_dest, g_dest, dest_bytes, bar);
       bulk_g2s(s_winfo, g_winfo, winfo_bytes, bar);
+      if (TWO && n_wr_pad > 0)
+        bulk_g2s(smem_raw + L::WRSRC_OFF, ch.wr_src + h.dest_base * 2, n_wr_pad * 2u, bar);
     }
   }
 
@@ -980,15 +1067,19 @@ __global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chu
     const int m = (int)(info & 0xffu);
     const uint16_t* p = srcp + ((size_t)(info >> 8) << 5) + lane;
     const int t = (dw << 5) + lane;
-    double* dst = a.values + (int64_t)destp[t * DS];
-    double* dst2 = SYM ? a.values + (int64_t)destp[t * DS + (DS - 1)] : dst;
+    double *dst = nullptr, *dst2 = nullptr;
     double old = 0.0, old2 = 0.0;
     const bool plain = t < h.n_complete;
-    if (plain && !ch.overwrite)
+    if constexpr (!TWO)
     {
-      old = *dst; // issued before the list walk: its latency hides behind the shared-memory sums
-      if (SYM)
-        old2 = *dst2;
+      dst = a.values + (int64_t)destp[t * DS];
+      dst2 = SYM ? a.values + (int64_t)destp[t * DS + (DS - 1)] : dst;
+      if (plain && !ch.overwrite)
+      {
+        old = *dst; // issued before the list walk: its latency hides behind the shared-memory sums
+        if (SYM)
+          old2 = *dst2;
+      }
     }
     double s0 = 0.0, s1 = 0.0;
     int j = 0;
@@ -1007,7 +1098,12 @@ __global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chu
       s0 += Es[i0];
     }
     const double sum = s0 + s1;
-    if (t < h.n_dest)
+    if constexpr (TWO)
+    {
+      if (t < h.n_dest)
+        reinterpret_cast<double*>(smem_raw + L::SUM_OFF)[t] = sum;
+    }
+    else if (t < h.n_dest)
     {
       if (plain)
       {
@@ -1021,6 +1117,26 @@ __global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chu
         if (SYM && dst2 != dst)
           red_add(dst2, sum);
       }
+    }
+  }
+  if constexpr (TWO)
+  {
+    // ---- phase 3: write-back in address order
+    __syncthreads();
+    const double* sums = reinterpret_cast<const double*>(smem_raw + L::SUM_OFF);
+    const uint16_t* wsrc = fits ? reinterpret_cast<const uint16_t*>(smem_raw + L::WRSRC_OFF) : ch.wr_src + h.dest_base * 2;
+    const uint32_t* waddr = reinterpret_cast<const uint32_t*>(destp);
+    for (int t = threadIdx.x; t < h.pad; t += THREADS)
+    {
+      const uint32_t sx = wsrc[t];
+      double* dst = a.values + waddr[t];
+      const double v = sums[sx & 0x7fffu];
+      if (sx & 0x8000u)
+        red_add(dst, v);
+      else if (ch.overwrite)
+        *dst = v;
+      else
+        *dst += v;
     }
   }
 }
@@ -1073,6 +1189,22 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
     k_pack_marker_bits<<<grid_for(c->n_dofs1, 256, 8), 256, 0, st>>>(c->n_dofs1, a.bc1, c->bits1);
     ch.bits1 = c->bits1;
   }
+  ch.wr_addr = c->wr_addr;
+  ch.wr_src = c->wr_src;
+  if constexpr (SYM && NS <= 16 && CB == 256)
+  {
+    if (c->wr_addr) // two-stage plan (32-bit addresses)
+    {
+      const size_t smem2 = ChunkSmem<NS, CB, 2, true>::TOTAL;
+      BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, true><<<(unsigned)c->nchunks, THREADS, smem2, st>>>(a, ch);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
+  if (c->wr_addr)
+    return fail(BFX_ERR_INVALID, "two-stage chunk plan without a two-stage kernel");
   const size_t smem = ChunkSmem<NS, CB, SYM ? 2 : 1>::TOTAL;
   if (c->addr_bytes == 4)
   {
@@ -1090,16 +1222,32 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   return BFX_OK;
 }
 
-// the plan fixes the chunk geometry (bfx_asm_build_chunks: default or BFX_CHUNKS_ALT_CB)
+// the plan fixes the chunk size (bfx_asm_build_chunks: the element's default or BFX_CHUNKS_CB(cells))
+template <class E, bool SYM, int CB>
+int launch_chunked_try(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st, int& status)
+{
+  constexpr int NS = staged_per_cell(E::ND * E::BS, SYM);
+  if constexpr (chunk_cb_supported(NS, CB))
+  {
+    if (P->chunks->cb == CB)
+    {
+      status = launch_chunked_cb<E, SYM, CB, chunk_threads_for(NS, CB)>(P, a, values_mode, st);
+      return 1;
+    }
+  }
+  return 0;
+}
+
 template <class E, bool SYM>
 int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
 {
   constexpr int NS = staged_per_cell(E::ND * E::BS, SYM);
-  if constexpr (chunk_cb_alt(NS) > 0)
-  {
-    if (P->chunks->cb == chunk_cb_alt(NS))
-      return launch_chunked_cb<E, SYM, chunk_cb_alt(NS), chunk_threads_alt(NS)>(P, a, values_mode, st);
-  }
+  int status = BFX_OK;
+  if (launch_chunked_try<E, SYM, 64>(P, a, values_mode, st, status) || launch_chunked_try<E, SYM, 96>(P, a, values_mode, st, status)
+      || launch_chunked_try<E, SYM, 128>(P, a, values_mode, st, status)
+      || launch_chunked_try<E, SYM, 192>(P, a, values_mode, st, status)
+      || launch_chunked_try<E, SYM, 384>(P, a, values_mode, st, status))
+    return status;
   return launch_chunked_cb<E, SYM, chunk_cb(NS), chunk_threads(NS)>(P, a, values_mode, st);
 }
 
@@ -1397,6 +1545,8 @@ void free_chunks(bfx_chunks* c)
   cudaFree(c->hdr);
   cudaFree(c->winfo);
   cudaFree(c->dest_addr);
+  cudaFree(c->wr_addr);
+  cudaFree(c->wr_src);
   cudaFree(c->src);
   cudaFree(c->perm);
   cudaFree(c->xdm);
@@ -1426,7 +1576,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   if (sym && !(csr->bs0 == 1 && csr->bs1 == 1 && P->nd0 == P->nd1 && (!P->dofmap1 || P->dofmap1 == P->dofmap0)))
     return fail(BFX_ERR_UNSUPPORTED, "symmetric chunk plan needs block size 1 and one dofmap for rows and columns");
   const int n2 = sym ? staged_per_cell(P->nd0, true) : P->nd0 * csr->bs0 * P->nd1 * csr->bs1; // staged per cell
-  const int cb = ((flags & BFX_CHUNKS_ALT_CB) && chunk_cb_alt(n2) > 0) ? chunk_cb_alt(n2) : chunk_cb(n2);
+  const int cb_req = ((flags >> 8) & 0xff) * 32; // BFX_CHUNKS_CB(cells); 0 = the element's default
+  const int cb = (cb_req && chunk_cb_supported(n2, cb_req)) ? cb_req : chunk_cb(n2); // not instantiated: default
   if (cb == 0 || P->ncells == 0)
     return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d staged scalars are not supported", n2);
   const int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
@@ -1529,6 +1680,9 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   while (addr_bits < 47 && ((1ull << addr_bits) - 1) < nvals)
     ++addr_bits;
   c->addr_bytes = nvals < 0xffffffffull ? 4 : 8;
+  // two-stage write-back: symmetric P1-sized plans of 256-cell chunks with 32-bit addresses whose chunks all keep
+  // their destinations within the kernel's shared-memory budget (checked by pass A)
+  bool two = (flags & BFX_CHUNKS_TWO_STAGE) && sym && n2 <= 16 && cb == 256 && c->addr_bytes == 4;
   int64_t *ndw = nullptr, *nsrc = nullptr;
   if ((e = dev_alloc(&ndw, (size_t)c->nchunks + 1)) || (e = dev_alloc(&nsrc, (size_t)c->nchunks + 1)))
     return bail(e);
@@ -1552,6 +1706,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   p.o_ndw = ndw;
   p.o_nsrc32 = nsrc;
   p.err = csr->err_flag;
+  p.two = two;
+  p.dcap = two_stage_dcap(n2, cb);
   if ((e = run_plan_pass_items(items, false, p, c->nchunks, st)))
     return bail(e);
   {
@@ -1568,6 +1724,12 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     BFX_CUDA(cudaMemcpyAsync(&herr, csr->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     BFX_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp);
+    if (herr == 5) // some chunk has more destinations than the two-stage kernel holds: classic write-back
+    {
+      BFX_CUDA(cudaMemsetAsync(csr->err_flag, 0, sizeof(int), st));
+      two = false;
+      herr = 0;
+    }
     if (herr)
     {
       BFX_CUDA(cudaMemsetAsync(csr->err_flag, 0, sizeof(int), st));
@@ -1583,11 +1745,20 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   if ((e = dev_alloc(&c->hdr, (size_t)c->nchunks)) || (e = dev_alloc(&c->winfo, (size_t)(c->n_dest_pad / 32 + 8)))
       || (e = dev_alloc(&c->src, (size_t)c->n_src32 * 32 + 32)))
     return bail(e);
+  if (two)
+  {
+    if ((e = dev_alloc(&c->wr_addr, (size_t)(2 * c->n_dest_pad + 64))) || (e = dev_alloc(&c->wr_src, (size_t)(2 * c->n_dest_pad + 64))))
+      return bail(e);
+  }
+  else
   {
     void* da = nullptr;
     BFX_CUDA(cudaMalloc(&da, (size_t)(c->n_dest_pad + 32) * c->addr_bytes * (sym ? 2 : 1)));
     c->dest_addr = da;
   }
+  p.two = two;
+  p.wr_addr = c->wr_addr;
+  p.wr_src = c->wr_src;
   p.dest_base32 = ndw;
   p.src_base32 = nsrc;
   p.hdr = c->hdr;
@@ -1612,22 +1783,25 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     const size_t per_warp = ((size_t)nst * 2 + (size_t)max_rg * 2 + (size_t)nst + 15) / 16 * 16;
     const size_t smem = per_warp * 8;
     const unsigned grid = grid_for((c->nchunks + 7) / 8, 1, 8);
-    if (cb == 256)
+    bool launched = false;
+    auto colour_cb = [&](auto cbc)
     {
-      BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_chunk_colour<256><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
-    }
-    else if (cb == 128)
-    {
-      BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_chunk_colour<128><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
-    }
-    else if (cb == 384)
-    {
-      BFX_CUDA(cudaFuncSetAttribute(k_chunk_colour<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_chunk_colour<384><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
-    }
-    else
+      constexpr int CBC = decltype(cbc)::value;
+      if (cb != CBC || launched)
+        return cudaSuccess;
+      launched = true;
+      cudaError_t ce = cudaFuncSetAttribute(k_chunk_colour<CBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (ce != cudaSuccess)
+        return ce;
+      k_chunk_colour<CBC><<<grid, 256, smem, st>>>(c->nchunks, n2, c->hdr, c->src, c->colour, colw, d_conf, d_over);
+      return cudaSuccess;
+    };
+    BFX_CUDA(colour_cb(std::integral_constant<int, 96>()));
+    BFX_CUDA(colour_cb(std::integral_constant<int, 128>()));
+    BFX_CUDA(colour_cb(std::integral_constant<int, 192>()));
+    BFX_CUDA(colour_cb(std::integral_constant<int, 256>()));
+    BFX_CUDA(colour_cb(std::integral_constant<int, 384>()));
+    if (!launched)
       return bail(fail(BFX_ERR_INVALID, "chunk plan: no colouring kernel for %d cells per chunk", cb));
     BFX_CHECK_LAUNCH();
     unsigned long long h_conf = 0;
@@ -1715,9 +1889,17 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
   if (n_src_entries)
     *n_src_entries = c->n_src32 * 32;
   if (plan_bytes)
-    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4 + c->n_dest_pad * c->addr_bytes * (c->sym ? 2 : 1)
+    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4
+                  + (c->wr_addr ? c->n_dest_pad * 12 : c->n_dest_pad * c->addr_bytes * (c->sym ? 2 : 1))
                   + c->n_src32 * 64 + (c->perm ? P->ncells * 4 : 0)
                   + (c->xdm ? P->ncells * 4 * (int64_t)(P->nx + P->nd0 + (c->dm1 ? P->nd1 : 0)) : 0);
+  return BFX_OK;
+}
+
+int bfx_asm_chunk_two_stage(const bfx_asm_t* P, int* two_stage)
+{
+  BFX_REQUIRE(P && P->chunks && two_stage, "bfx_asm_chunk_two_stage: no chunk plan");
+  *two_stage = P->chunks->wr_addr ? 1 : 0;
   return BFX_OK;
 }
 

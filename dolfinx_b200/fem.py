@@ -408,8 +408,10 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
 # 2.1 ms of the cell-parallel kernel for the C2 load vector (both are bound by the L1/LSU pipe, not by the REDs)
 GROUPED_VECTORS = os.environ.get("BFX_GROUPED_VECTORS", "0") != "0"
 CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
-# chunk size: default 256 (P1) / 128 (P2) cells, alternative 384 / 96 (bricks of whole cubes on Kuhn boxes)
-CHUNKS_ALT_CB = os.environ.get("BFX_CHUNKS_ALT_CB", "0") != "0"
+# cells per chunk: 0 = the element's default (256 P1 / 128 P2); 96, 128, 192, 384 (P1) or 64, 96 (symmetric P2)
+CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
+# write-back of the chunk sums in address order (symmetric P1 plans; see BFX_CHUNKS_TWO_STAGE in include/bfx.h)
+CHUNKS_TWO_STAGE = os.environ.get("BFX_CHUNKS_TWO_STAGE", "0") != "0"
 
 
 def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=False):
@@ -431,8 +433,9 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
         if want == _lib.ASM_CHUNKED:
             V0, V1 = form.function_spaces
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
-            if CHUNKS_ALT_CB:
-                flags |= _lib.CHUNKS_ALT_CB
+            flags |= _lib.CHUNKS_CB(CHUNKS_CB)
+            if CHUNKS_TWO_STAGE:
+                flags |= _lib.CHUNKS_TWO_STAGE
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
@@ -467,6 +470,16 @@ def chunk_bank_conflicts(form: Form, A: la.MatrixCSR, ident=0):
     n = C.c_int64()
     _lib.check(_lib.lib.bfx_asm_chunk_bank_conflicts(plan, C.byref(n)))
     return int(n.value)
+
+
+def chunk_two_stage(form: Form, A: la.MatrixCSR, ident=0) -> bool:
+    """True if the chunk plan of the cell integral writes back in address order (BFX_CHUNKS_TWO_STAGE)."""
+    from . import _lib
+
+    plan = _asm_plan(form, form.integral(IntegralType.cell, ident), IntegralType.cell, A)
+    n = C.c_int()
+    _lib.check(_lib.lib.bfx_asm_chunk_two_stage(plan, C.byref(n)))
+    return bool(n.value)
 
 
 def _interior_facet_plan(form: Form, integ: IntegralData, A: la.MatrixCSR):

@@ -213,8 +213,9 @@ extern "C"
    * given order.  BFX_ERR_UNSUPPORTED when the element matrix is too large for shared-memory staging. */
   enum
   {
-    BFX_CHUNKS_ALT_CB = 8, /* alternative chunk size: 384 cells (P1 kernels) / 96 cells (P2 Poisson, symmetric) per
-                            * chunk instead of 256 / 128 - whole-cube bricks under the Morton order of a Kuhn box */
+    BFX_CHUNKS_TWO_STAGE = 8, /* symmetric P1-sized plans: the kernel leaves the per-destination sums in shared memory
+                                 and writes the CSR values back in ADDRESS order (both entries of a symmetric pair),
+                                 so that consecutive lanes update consecutive values; ignored where not applicable */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
                                      zero-fill and this plan's launch (boundary/interior split): an entry counts as
                                      complete only if EVERY cell of the dofmap that touches it lies in one chunk of this
@@ -224,6 +225,10 @@ extern "C"
                                 element matrix only and update the (i,j)/(j,i) CSR entries from one sum; a call whose
                                 rows and columns do not share dofmap and bc markers is refused (BFX_ERR_UNSUPPORTED) */
   };
+/* cells per chunk other than the element's default (256 for the P1 kernels, 128 for symmetric P2): 96, 128, 192 or 384
+ * for the P1 kernels, 64 or 96 for symmetric P2 (other values: the default is used); OR-ed into the flags of
+ * bfx_asm_build_chunks */
+#define BFX_CHUNKS_CB(cells) ((((cells) / 32) & 0xff) << 8)
   int bfx_asm_build_chunks(bfx_asm_t* plan, const double* x_dev, int flags, bfx_stream_t stream);
   /* Plan of the row-gather strategy (BFX_ASM_ROWGATHER): the transposed dofmap (row -> incident (cell, local
    * node) pairs in ascending cell order, cf. fem::transpose_dofmap, fem/DofMap.h:62-64) and the per-call scratch of
@@ -239,6 +244,8 @@ extern "C"
   /* Staged entries whose shared-memory bank still collides with another entry read in the same half-warp step
    * after the plan's bank colouring (-1: linear staging layout in use). */
   int bfx_asm_chunk_bank_conflicts(const bfx_asm_t* plan, int64_t* n_conflicts);
+  /* 1 if the chunk plan was built with the two-stage (address-ordered) write-back, see BFX_CHUNKS_TWO_STAGE */
+  int bfx_asm_chunk_two_stage(const bfx_asm_t* plan, int* two_stage);
 
   /* impl::assemble_cells_matrix<false> — fem/assemble_matrix_impl.h:92-200 (+ bc row/col zeroing :161-196).
    * bc0/bc1: int8 markers of length bs*(owned+ghost) or NULL.  constants: host array. */

@@ -70,7 +70,7 @@ def test_poisson_p1_matrix(bfx, oracle, n, numbering):
     assert A.squared_norm() == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
 
 
-@pytest.mark.parametrize("alt_cb", [False, True])
+@pytest.mark.parametrize("alt_cb", [0, 96, 192, 384, "two_stage"])
 @pytest.mark.parametrize("symmetric", [True, False])
 @pytest.mark.parametrize("case", ["p1_lex", "p1_random", "p2", "tri"])
 def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, monkeypatch):
@@ -81,8 +81,12 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, mon
     fem, K = bfx.fem, bfx.lib
     # symmetric plan: upper triangle staged, (i,j)/(j,i) entries updated from one sum; general plan otherwise
     monkeypatch.setattr(fem, "CHUNKS_SYMMETRIC", symmetric)
-    # alternative chunk size (BFX_CHUNKS_ALT_CB): 384 cells for the P1 kernels, 96 for symmetric P2
-    monkeypatch.setattr(fem, "CHUNKS_ALT_CB", alt_cb)
+    # cells per chunk (BFX_CHUNKS_CB): 96 / 128 / 192 / 384 for the P1 kernels, 64 / 96 for symmetric P2, else the default
+    # two_stage: write-back of the chunk sums in address order (symmetric P1 plans of 256-cell chunks)
+    two_stage = alt_cb == "two_stage"
+    alt_cb = 0 if two_stage else alt_cb
+    monkeypatch.setattr(fem, "CHUNKS_TWO_STAGE", two_stage)
+    monkeypatch.setattr(fem, "CHUNKS_CB", alt_cb)
     if case.startswith("p1"):
         p = P.tet_p1(13, numbering="lex" if case == "p1_lex" else "random", seed=5)
         kern, okern, consts = K.K_POISSON_P1_TET_A, oracle.K_POISSON_P1_TET_A, [2.0]
@@ -102,9 +106,12 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, mon
         if strategy == K.ASM_CHUNKED:
             nchunks, ndest, nsrc, nbytes = fem.chunk_stats(a, A)
             assert nchunks > 4 and nsrc >= ref.size // 2 and ndest >= (len(pat.edges) // 2 if symmetric else len(pat.edges))
-            if alt_cb and (case != "p2" or symmetric):
-                cb = 96 if case == "p2" else 384
-                assert nchunks == -(-len(p.dofmap) // cb)
+            if case == "p2":
+                cb = (alt_cb if alt_cb == 96 else 128) if symmetric else 64
+            else:
+                cb = alt_cb if alt_cb else 256
+            assert nchunks == -(-len(p.dofmap) // cb)
+            assert fem.chunk_two_stage(a, A) == (two_stage and symmetric and case != "p2")
     # default strategy = chunk-aggregated for the P1 kernels
     a, sp, A = assemble_A(bfx, V, kern, constants=consts)
     if kern in K.CHUNKED_KERNELS:

@@ -29,6 +29,23 @@ __global__ void k_red(double* g, uint64_t n, int per_thread, uint64_t window)
   }
 }
 
+// coalescing: the 32 lanes of a warp form 32 / run groups of `run` consecutive doubles, every group at a
+// pseudo-random run-aligned address of the window; op 0 = RED, 1 = plain store
+__global__ void k_runs(double* g, uint64_t n, int per_thread, uint64_t window, int run, int op)
+{
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t base = window >= n ? 0 : (mix(blockIdx.x) % (n - window));
+  const uint64_t grp = tid / run, in = tid % run;
+  for (int k = 0; k < per_thread; ++k)
+  {
+    const uint64_t a = base + (mix(grp * 1315423911ull + k) % (window / run)) * run + in;
+    if (op == 0)
+      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(g + a), "d"(1.0) : "memory");
+    else
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(g + a), "d"(1.0) : "memory");
+  }
+}
+
 __global__ void k_bulk(double* g, uint64_t n, int per_warp, int seg_doubles, uint64_t window)
 {
   extern __shared__ __align__(128) double s[];
@@ -104,6 +121,21 @@ int main()
     printf("red     window %10llu doubles: %.3f ms, %.2f G red/s, %.3f cyc/lane/SM @1.965GHz\n",
            (unsigned long long)window, ms, ops / ms * 1e-6, ms * 1e-3 * 1.965e9 * 148 / ops);
   }
+  for (int op : {0, 1})
+    for (uint64_t window : {n, (uint64_t)1 << 16})
+      for (int run : {1, 2, 4, 8, 16, 32})
+      {
+        const int per_thread = 128;
+        k_runs<<<grid, 256>>>(g, n, 8, window, run, op);
+        cudaEventRecord(e0);
+        k_runs<<<grid, 256>>>(g, n, per_thread, window, run, op);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = (double)grid * 256 * per_thread;
+        printf("%s window %10llu run %2d: %.3f ms, %.2f G lanes/s, %.3f cyc/lane/SM\n", op == 0 ? "red-runs  " : "store-runs",
+               (unsigned long long)window, run, ms, ops / ms * 1e-6, ms * 1e-3 * 1.965e9 * 148 / ops);
+      }
   CK(cudaFuncSetAttribute(k_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   for (uint64_t window : {n, (uint64_t)1 << 16})
     for (int seg : {2, 4, 8, 16, 32, 64, 128, 512})
