@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
           const int d = v2[it];
           int64_t blk, other;
           const int64_t addr = contrib_addr(p, q, sidx[dstart[d]], blk, other);
-          const uint64_t tag = (uint64_t)(((k2[it] >> 8) & 1u) << 15) | (uint64_t)r;
+          const uint64_t inc = (k2[it] >> 8) & 1u;
+          // split lists (two == 2): all plain stores first, then all REDs, each in address order
+          const uint64_t tag = (inc << 15) | (uint64_t)r | (p.two == 2 ? inc << (16 + p.addr_bits) : 0ull);
           const int at = atomicAdd(wcnt, other != addr ? 2 : 1);
           wk[at] = ((uint64_t)addr << 16) | tag;
           if (other != addr)
@@ -399,7 +401,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
         keys[it] = k < n_wr ? wk[k] : ~0ull;
       }
       __syncthreads();
-      Sort1(temp.s1).Sort(keys, 16, 16 + p.addr_bits);
+      Sort1(temp.s1).Sort(keys, 16, 16 + p.addr_bits + (p.two == 2 ? 1 : 0));
+      const uint64_t amask = (1ull << p.addr_bits) - 1ull;
       const int n_wr_pad = (n_wr + 31) & ~31;
       const int64_t wr_base = 2 * dest_base;
 #pragma unroll
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
         const int k = tid * ITEMS + it;
         if (k < n_wr_pad)
         {
-          p.wr_addr[wr_base + k] = k < n_wr ? (uint32_t)(keys[it] >> 16) : 0u;
+          p.wr_addr[wr_base + k] = k < n_wr ? (uint32_t)((keys[it] >> 16) & amask) : 0u;
           p.wr_src[wr_base + k] = k < n_wr ? (uint16_t)(keys[it] & 0xffffu) : (uint16_t)0;
         }
       }
@@ -1756,7 +1759,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     BFX_CUDA(cudaMalloc(&da, (size_t)(c->n_dest_pad + 32) * c->addr_bytes * (sym ? 2 : 1)));
     c->dest_addr = da;
   }
-  p.two = two;
+  p.two = two ? ((flags & BFX_CHUNKS_TWO_STAGE_SPLIT) ? 2 : 1) : 0;
   p.wr_addr = c->wr_addr;
   p.wr_src = c->wr_src;
   p.dest_base32 = ndw;

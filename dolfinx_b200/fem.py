@@ -411,7 +411,7 @@ CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 # cells per chunk: 0 = the element's default (256 P1 / 128 P2); 96, 128, 192, 384 (P1) or 64, 96 (symmetric P2)
 CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
 # write-back of the chunk sums in address order (symmetric P1 plans; see BFX_CHUNKS_TWO_STAGE in include/bfx.h)
-CHUNKS_TWO_STAGE = os.environ.get("BFX_CHUNKS_TWO_STAGE", "0") != "0"
+CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
 
 def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=False):
@@ -435,7 +435,7 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
             flags |= _lib.CHUNKS_CB(CHUNKS_CB)
             if CHUNKS_TWO_STAGE:
-                flags |= _lib.CHUNKS_TWO_STAGE
+                flags |= _lib.CHUNKS_TWO_STAGE | (_lib.CHUNKS_TWO_STAGE_SPLIT if int(CHUNKS_TWO_STAGE) == 2 else 0)
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())

@@ -70,7 +70,7 @@ def test_poisson_p1_matrix(bfx, oracle, n, numbering):
     assert A.squared_norm() == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
 
 
-@pytest.mark.parametrize("alt_cb", [0, 96, 192, 384, "two_stage"])
+@pytest.mark.parametrize("alt_cb", [0, 96, 192, 384, "two_stage", "two_stage_split"])
 @pytest.mark.parametrize("symmetric", [True, False])
 @pytest.mark.parametrize("case", ["p1_lex", "p1_random", "p2", "tri"])
 def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, monkeypatch):
@@ -83,7 +83,7 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, mon
     monkeypatch.setattr(fem, "CHUNKS_SYMMETRIC", symmetric)
     # cells per chunk (BFX_CHUNKS_CB): 96 / 128 / 192 / 384 for the P1 kernels, 64 / 96 for symmetric P2, else the default
     # two_stage: write-back of the chunk sums in address order (symmetric P1 plans of 256-cell chunks)
-    two_stage = alt_cb == "two_stage"
+    two_stage = {"two_stage": 1, "two_stage_split": 2}.get(alt_cb, 0)
     alt_cb = 0 if two_stage else alt_cb
     monkeypatch.setattr(fem, "CHUNKS_TWO_STAGE", two_stage)
     monkeypatch.setattr(fem, "CHUNKS_CB", alt_cb)
@@ -111,7 +111,8 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, mon
             else:
                 cb = alt_cb if alt_cb else 256
             assert nchunks == -(-len(p.dofmap) // cb)
-            assert fem.chunk_two_stage(a, A) == (two_stage and symmetric and case != "p2")
+            if case.startswith("p1"):  # (triangles: more destinations per chunk than the two-stage kernel holds)
+                assert fem.chunk_two_stage(a, A) == bool(two_stage and symmetric)
     # default strategy = chunk-aggregated for the P1 kernels
     a, sp, A = assemble_A(bfx, V, kern, constants=consts)
     if kern in K.CHUNKED_KERNELS:
