@@ -122,6 +122,7 @@ _SIGS = {
     "bfx_asm_build_groups": ([vp, vp, vp], ci),
     "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
     "bfx_asm_chunk_two_stage": ([vp, C.POINTER(ci)], ci),
+    "bfx_csr_transpose_local": ([vp, vp, i32, vp, vp, vp, i64, C.POINTER(i64), vp], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),

@@ -74,6 +74,19 @@ class SparsityPattern:
         self._csr = None  # device structure (bfx_csr_t*) when built natively
         self._col_ghosts = self._col_ghost_owners = None
 
+    @classmethod
+    def from_graph(cls, comm: Comm, maps, bs, edges, offsets, off_diagonal_offsets):
+        """A finalised pattern from its arrays - the reference's ``la::impl::Sparsity`` aggregate, which
+        ``la::transpose`` / ``la::matmul`` hand to the MatrixCSR constructor (la/mattrans.h:153-155, 431-434)."""
+        sp = cls(comm, maps, bs)
+        sp._edges = np.ascontiguousarray(edges, dtype=np.int32)
+        sp._offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        sp._off_diag = np.ascontiguousarray(off_diagonal_offsets, dtype=np.int32)
+        sp._col_ghosts = maps[1].ghosts.copy()
+        sp._col_ghost_owners = maps[1].owners.copy()
+        sp._finalized = True
+        return sp
+
     # -- insertion -------------------------------------------------------------------------------
     def _check_open(self):
         if self._finalized:
@@ -496,6 +509,74 @@ def matrix_ghost_plan(index_maps, bs, indptr, indices):
 
 
 
+def matrix_transpose_plan(m0: IndexMap, m1: IndexMap, bs, indptr, indices, off_diag_offset, rp0, c0, gather_values):
+    """Host side of the distributed la::transpose (la/mattrans.h:200-434), numpy + the neighbourhood exchange.
+
+    ``rp0`` / ``c0``: row pointer and columns of the locally transposed block (impl::local_transpose);
+    ``gather_values(ks)``: the blocks of the entries ``ks`` of A, flattened (a device gather in the product).
+    Returns the maps [row map, column map] of the result, its structure, and where the local and the received blocks go
+    (``local_dst``: position of every entry of the local transpose, ``recv_dst`` / ``recv_blocks``: position and
+    transposed block of every received entry)."""
+    comm = m0.comm
+    bs0, bs1 = bs
+    nbs = bs0 * bs1
+    n_row, n_col = m0.size_local, m1.size_local
+    n0 = int(rp0[-1])
+    # entries in ghost columns, grouped by the owner of the column, rows ascending (:215-262)
+    od = np.asarray(off_diag_offset[:n_row], dtype=np.int64)
+    lens = np.asarray(indptr[1 : n_row + 1], dtype=np.int64) - od
+    tot = int(lens.sum())
+    starts = np.repeat(od - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens)
+    ks = (np.arange(tot, dtype=np.int64) + starts).astype(np.int64)
+    rows_g = np.repeat(np.arange(n_row, dtype=np.int64) + m0.local_range[0], lens)
+    jg = np.asarray(indices)[ks].astype(np.int64) - n_col
+    nbr = np.searchsorted(m1.src, m1.owners)[jg] if tot else np.zeros(0, dtype=np.int64)
+    order = np.argsort(nbr, kind="stable")
+    counts = np.bincount(nbr, minlength=len(m1.src)) if tot else np.zeros(len(m1.src), dtype=np.int64)
+    disp = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    send_rows = rows_g[order]
+    send_cols = m1.ghosts[jg[order]] if tot else np.zeros(0, dtype=np.int64)
+    send_vals = np.asarray(gather_values(ks[order]), dtype=np.float64) if tot else np.zeros(0)
+
+    def split(a, w=1):
+        return [a[disp[i] * w : disp[i + 1] * w] for i in range(len(m1.src))]
+
+    # this rank sends to src[] (owners of its ghost columns) and receives from dest[] (:200-206, :290-300)
+    recv_rows = comm.neighbor_alltoallv(m1.src, m1.dest, split(send_rows), dtype=np.int64)
+    recv_cols = comm.neighbor_alltoallv(m1.src, m1.dest, split(send_cols), dtype=np.int64)
+    recv_vals = comm.neighbor_alltoallv(m1.src, m1.dest, split(send_vals, nbs), dtype=np.float64)
+    rr = np.concatenate(recv_rows) if len(recv_rows) else np.zeros(0, dtype=np.int64)
+    rc = np.concatenate(recv_cols) if len(recv_cols) else np.zeros(0, dtype=np.int64)
+    rv = np.concatenate(recv_vals) if len(recv_vals) else np.zeros(0)
+    # column map of the result: owned = rows of A, ghosts = sorted unique (global row, sender) pairs (:335-364)
+    senders = (np.repeat(np.asarray(m1.dest, dtype=np.int64), [len(a) for a in recv_rows]) if len(rr)
+               else np.zeros(0, dtype=np.int64))
+    pairs = np.unique(np.stack([rr, senders], axis=1), axis=0) if len(rr) else np.zeros((0, 2), dtype=np.int64)
+    at_col_map = IndexMap(comm, n_row, pairs[:, 0], pairs[:, 1].astype(np.int32))
+    at_row_map = IndexMap(comm, n_col)
+    new_col_local = (n_row + np.searchsorted(pairs[:, 0], rr)).astype(np.int32)  # (a global row has one owner)
+    # merge: the local rows first, the received entries appended in arrival order (:314-424)
+    lc = (rc - m1.local_range[0]).astype(np.int64)
+    assert np.all((lc >= 0) & (lc < n_col))
+    off = np.diff(rp0).astype(np.int64)
+    per_row = np.bincount(lc, minlength=n_col).astype(np.int64) if len(lc) else np.zeros(n_col, dtype=np.int64)
+    row_ptr = np.concatenate([[0], np.cumsum(off + per_row)]).astype(np.int64)
+    cols = np.zeros(int(row_ptr[-1]), dtype=np.int32)
+    local_dst = np.arange(n0, dtype=np.int64) + np.repeat(row_ptr[:-1] - np.asarray(rp0[:-1], dtype=np.int64), off)
+    cols[local_dst] = c0
+    recv_dst = np.zeros(0, dtype=np.int64)
+    if len(lc):
+        o2 = np.argsort(lc, kind="stable")  # arrival rank of an entry inside its row: the reference's cursor
+        first = np.concatenate([[0], np.cumsum(per_row)[:-1]])
+        rank_in_row = np.empty(len(lc), dtype=np.int64)
+        rank_in_row[o2] = np.arange(len(lc)) - first[lc[o2]]
+        recv_dst = row_ptr[lc] + off[lc] + rank_in_row
+        cols[recv_dst] = new_col_local
+    blocks = np.ascontiguousarray(rv.reshape(-1, bs0, bs1).transpose(0, 2, 1)).reshape(-1, nbs)
+    return {"maps": [at_row_map, at_col_map], "row_ptr": row_ptr, "cols": cols, "off_diag": off, "local_dst": local_dst,
+            "recv_dst": recv_dst, "recv_blocks": blocks}
+
+
 class MatrixCSR:
     """la::MatrixCSR<double> with device storage (la/MatrixCSR.h:67-624).
 
@@ -729,6 +810,55 @@ class MatrixCSR:
             _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
             y.scatter_reverse(InsertMode.add)
             _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
+
+    def transpose(self) -> "MatrixCSR":
+        """la::transpose (la/mattrans.h:121-437; python/dolfinx/la/__init__.py:207-209).
+
+        The block owned rows x owned columns is transposed on the device (``bfx_csr_transpose_local``, bit-exact
+        with impl::local_transpose).  The entries in ghost columns travel to the column owners as (global row,
+        global column, value) triplets over the neighbourhood of the column map and are appended to the owner's
+        rows in arrival order, like the reference; the result has no ghost rows."""
+        from . import _lib
+
+        torch = _torch()
+        m0, m1 = self._index_maps
+        bs0, bs1 = self._bs
+        nbs = bs0 * bs1
+        n_row, n_col = m0.size_local, m1.size_local
+        comm = m0.comm
+        indptr, indices = self.indptr, self.indices
+        cap = int(indptr[n_row])
+        dev = self.data.device
+        rpT = torch.empty(n_col + 1, dtype=torch.int64, device=dev)
+        cT = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        vT = torch.empty(max(cap, 1) * nbs, dtype=torch.float64, device=dev)
+        nnzT = C.c_int64(0)
+        _lib.check(_lib.lib.bfx_csr_transpose_local(self._csr, self.data.data_ptr(), n_col, rpT.data_ptr(), cT.data_ptr(),
+                                                    vT.data_ptr(), cap, C.byref(nnzT), _lib.current_stream()))
+        n0 = int(nnzT.value)
+        rp0 = rpT.cpu().numpy()
+        c0 = cT[:n0].cpu().numpy()
+        if comm.size == 1 or (len(m1.src) == 0 and len(m1.dest) == 0):
+            # no neighbours in the column map: every column is owned (la/mattrans.h:139-159)
+            at_col_map = IndexMap(comm, n_row)
+            at_row_map = IndexMap(comm, n_col)
+            sp = SparsityPattern.from_graph(comm, [at_row_map, at_col_map], (bs1, bs0), c0, rp0, np.diff(rp0))
+            AT = MatrixCSR(sp)
+            AT._data.copy_(vT[: n0 * nbs])
+            AT._is_zero = False
+            return AT
+        # ---- entries in ghost columns -> column owners; merged structure (host side of la/mattrans.h:200-434)
+        plan = matrix_transpose_plan(m0, m1, self._bs, indptr, indices, self.off_diag_offset, rp0, c0,
+                                     lambda ks: self.data.view(-1, nbs)[torch.from_numpy(ks).to(dev)].reshape(-1).cpu().numpy())
+        sp = SparsityPattern.from_graph(comm, plan["maps"], (bs1, bs0), plan["cols"], plan["row_ptr"], plan["off_diag"])
+        AT = MatrixCSR(sp)
+        out = AT._data.view(-1, nbs)
+        if n0:
+            out[torch.from_numpy(plan["local_dst"]).to(dev)] = vT[: n0 * nbs].view(-1, nbs)
+        if len(plan["recv_dst"]):
+            out[torch.from_numpy(plan["recv_dst"]).to(dev)] = torch.from_numpy(plan["recv_blocks"]).to(dev)
+        AT._is_zero = False
+        return AT
 
     def to_dense(self):
         """MatrixCSR::to_dense (la/MatrixCSR.h:343-370), host numpy."""

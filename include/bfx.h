@@ -150,6 +150,14 @@ extern "C"
   };
   int bfx_spmv(const bfx_csr_t* csr, const double* values_dev, const double* x_dev, double* y_dev, int part,
                bfx_stream_t stream);
+  /* la::impl::local_transpose - la/mattrans.h:47-108: transpose of the block "owned rows x owned columns" (entries
+   * row_ptr[i] .. off_diag_offset[i] of the owned rows).  Row j of the result lists the rows of A with an entry in
+   * column j in ascending order, every bs0 x bs1 block is stored transposed; bit-exact with the reference loop.
+   * row_ptrT (device, n_cols_owned + 1) is always written and the number of entries returned in *nnzT_host; colsT /
+   * valsT (device, room for `capacity` entries / blocks; row_ptr[n_rows_owned] of A is always enough) may be NULL to
+   * query the size only.  Synchronises the stream. */
+  int bfx_csr_transpose_local(const bfx_csr_t* A, const double* values, int32_t n_cols_owned, int64_t* row_ptrT,
+                              int32_t* colsT, double* valsT, int64_t capacity, int64_t* nnzT_host, bfx_stream_t stream);
   /* bs = 1 SpMV kernel of this matrix: 0 = entry-consecutive stream, 1 = row per thread out of staged (cols, values),
    * 2 = row per thread fed by a two-stage TMA pipeline (persistent CTAs); -1 (default) = time the three on the first
    * bfx_spmv call and keep the fastest (which one wins depends on the numbering of the matrix). */

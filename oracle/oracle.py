@@ -644,3 +644,104 @@ def matrix_mult(mats, scs_col, xs, ys):
 def inner_product(maps, bs, xs, ys):
     """la::inner_product (la/Vector.h:434-460): owned entries, MPI_SUM."""
     return float(sum(np.dot(x[: bs * m.size_local], y[: bs * m.size_local]) for m, x, y in zip(maps, xs, ys)))
+
+
+# ---------------------------------------------------------------------------
+# la::transpose (la/mattrans.h) - SURVEY.md section 8f rank 4
+# ---------------------------------------------------------------------------
+def local_transpose(A: OMatrix):
+    """impl::local_transpose (la/mattrans.h:47-108): transpose of the block owned rows x owned columns.
+
+    Returns (colsT int32, row_ptrT int64, valsT); the loops are the reference's (a write cursor per column, rows in
+    ascending order, every bs0 x bs1 block stored transposed)."""
+    bs0, bs1 = A.bs
+    n_rows, n_cols = A.index_maps[0].size_local, A.index_maps[1].size_local
+    row_count = np.zeros(n_cols, dtype=np.int64)
+    for i in range(n_rows):  # :64-67
+        for k in range(int(A.row_ptr[i]), int(A.off_diag_offset[i])):
+            row_count[A.cols[k]] += 1
+    row_ptrT = np.concatenate([[0], np.cumsum(row_count)]).astype(np.int64)  # :70-72
+    colsT = np.zeros(int(row_ptrT[-1]), dtype=np.int32)
+    valsT = np.zeros(int(row_ptrT[-1]) * bs0 * bs1)
+    cursor = row_ptrT[:-1].copy()
+    blocks = A.data.reshape(-1, bs0, bs1)
+    outT = valsT.reshape(-1, bs1, bs0)
+    for i in range(n_rows):  # :78-104
+        for k in range(int(A.row_ptr[i]), int(A.off_diag_offset[i])):
+            col = int(A.cols[k])
+            pos = int(cursor[col])
+            cursor[col] += 1
+            colsT[pos] = i
+            outT[pos] = blocks[k].T
+    return colsT, row_ptrT, valsT
+
+
+def transpose(mats):
+    """la::transpose on every (simulated) rank - la/mattrans.h:121-437.
+
+    The entries in ghost columns travel to the column owners as (global row, global column, value) triplets over
+    the neighbourhood "send to src, receive from dest" of the column map (:200-206, :290-300); the owner appends
+    them to its rows in arrival order (:395-424) behind the locally transposed block; the ghost columns of the
+    result are the sorted unique (global row, sender) pairs received (:335-361).  Row map of the result: the owned
+    columns, no ghosts (:429)."""
+    size = len(mats)
+    sends = []
+    for A in mats:
+        m0, m1 = A.index_maps
+        n_row, n_col = m0.size_local, m1.size_local
+        nbs = A.bs[0] * A.bs[1]
+        ghost_col_owner = np.searchsorted(m1.src, m1.owners)  # rank_to_nbr (:191-197)
+        bufs = [([], [], []) for _ in m1.src]
+        for i in range(n_row):  # :248-262
+            for k in range(int(A.off_diag_offset[i]), int(A.row_ptr[i + 1])):
+                j = int(A.cols[k]) - n_col
+                b = bufs[int(ghost_col_owner[j])]
+                b[0].append(m0.local_range[0] + i)
+                b[1].append(int(m1.ghosts[j]))
+                b[2].append(A.data[k * nbs:(k + 1) * nbs].copy())
+        sends.append(bufs)
+    out_edges = [A.index_maps[1].src for A in mats]
+    in_edges = [A.index_maps[1].dest for A in mats]
+    recv_rows = neighbor_alltoallv(out_edges, in_edges, [[np.array(b[0], dtype=np.int64) for b in s] for s in sends])
+    recv_cols = neighbor_alltoallv(out_edges, in_edges, [[np.array(b[1], dtype=np.int64) for b in s] for s in sends])
+    recv_vals = neighbor_alltoallv(
+        out_edges, in_edges,
+        [[np.concatenate(b[2]) if b[2] else np.zeros(0) for b in s] for s in sends])
+    # column maps of the results: owned = rows of A, ghosts = sorted unique (global row, sender) pairs
+    ghosts_T, owners_T = [], []
+    for r, A in enumerate(mats):
+        pairs = sorted({(int(g), int(A.index_maps[1].dest[p])) for p, arr in enumerate(recv_rows[r]) for g in arr})
+        ghosts_T.append([g for g, _ in pairs])
+        owners_T.append([o for _, o in pairs])
+    col_maps = make_index_maps([A.index_maps[0].size_local for A in mats], ghosts_T, owners_T)
+    row_maps = make_index_maps([A.index_maps[1].size_local for A in mats], [[] for _ in mats], [[] for _ in mats])
+    out = []
+    for r, A in enumerate(mats):
+        bs0, bs1 = A.bs
+        nbs = bs0 * bs1
+        m1 = A.index_maps[1]
+        n_row, n_col = A.index_maps[0].size_local, m1.size_local
+        c0, rp0, v0 = local_transpose(A)
+        count = np.diff(rp0).astype(np.int64)
+        rc = np.concatenate(recv_cols[r]) if recv_cols[r] else np.zeros(0, dtype=np.int64)
+        rr = np.concatenate(recv_rows[r]) if recv_rows[r] else np.zeros(0, dtype=np.int64)
+        rv = np.concatenate(recv_vals[r]) if recv_vals[r] else np.zeros(0)
+        for c in rc:  # :318-325
+            count[int(c) - m1.local_range[0]] += 1
+        row_ptr = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
+        g2l = {g: n_row + i for i, g in enumerate(ghosts_T[r])}
+        cols = np.zeros(int(row_ptr[-1]), dtype=np.int32)
+        vals = np.zeros(int(row_ptr[-1]) * nbs)
+        off = np.diff(rp0).astype(np.int64)  # off_diag_offsets (:386-393)
+        cursor = row_ptr[:-1] + off
+        for i in range(n_col):  # :371-381
+            cols[row_ptr[i]:row_ptr[i] + off[i]] = c0[rp0[i]:rp0[i + 1]]
+            vals[row_ptr[i] * nbs:(row_ptr[i] + off[i]) * nbs] = v0[rp0[i] * nbs:rp0[i + 1] * nbs]
+        for k in range(len(rc)):  # :395-424
+            lc = int(rc[k]) - m1.local_range[0]
+            pos = int(cursor[lc])
+            cursor[lc] += 1
+            cols[pos] = g2l[int(rr[k])]
+            vals[pos * nbs:(pos + 1) * nbs] = rv[k * nbs:(k + 1) * nbs].reshape(bs0, bs1).T.reshape(-1)
+        out.append(OMatrix([row_maps[r], col_maps[r]], (bs1, bs0), vals, cols, row_ptr, row_ptr[:-1] + off))
+    return out

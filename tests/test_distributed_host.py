@@ -168,6 +168,31 @@ def _worker(rank, world, port, nglob, tmpdir):
         assert np.array_equal(plan["val_send_disp"], oA.val_send_disp)
         assert np.array_equal(plan["val_recv_disp"], oA.val_recv_disp)
         assert np.array_equal(plan["unpack_pos"], oA.unpack_pos)
+        # la::transpose (la/mattrans.h): the host side (exchange of the ghost-column entries, merged structure, column
+        # map of the result) against the oracle's simulated ranks; the local transpose (a device kernel in the product)
+        # is taken from the oracle here
+        for tbs in ((1, 1), (2, 3)):
+            nb = tbs[0] * tbs[1]
+            tmats = []
+            for r_, A_ in enumerate(omats):
+                d_ = np.random.default_rng(100 + r_).random(len(A_.cols) * nb)
+                tmats.append(O.OMatrix(A_.index_maps, tbs, d_, A_.cols, A_.row_ptr, A_.off_diag_offset))
+            oT = O.transpose(tmats)[rank]
+            mine = tmats[rank]
+            c0, rp0, v0 = O.local_transpose(mine)
+            tp = la.matrix_transpose_plan(pat.index_map(0), pat.index_map(1), tbs, mine.row_ptr, mine.cols,
+                                          mine.off_diag_offset, rp0, c0,
+                                          lambda ks: mine.data.reshape(-1, nb)[ks].reshape(-1))
+            assert np.array_equal(tp["row_ptr"], oT.row_ptr) and np.array_equal(tp["cols"], oT.cols)
+            assert np.array_equal(tp["row_ptr"][:-1] + tp["off_diag"], oT.off_diag_offset)
+            tr, tc = tp["maps"]
+            assert tr.num_ghosts == 0 and tr.local_range == oT.index_maps[0].local_range
+            assert np.array_equal(tc.ghosts, oT.index_maps[1].ghosts) and np.array_equal(tc.owners, oT.index_maps[1].owners)
+            vals = np.zeros(len(tp["cols"]) * nb).reshape(-1, nb)
+            vals[tp["local_dst"]] = v0.reshape(-1, nb)
+            if len(tp["recv_dst"]):
+                vals[tp["recv_dst"]] = tp["recv_blocks"]
+            assert np.array_equal(vals.reshape(-1), oT.data)
         # collectives used by la::norm / inner_product
         assert comm.allreduce_sum(float(rank + 1)) == sum(range(1, world + 1))
         assert comm.allreduce_max(float(rank)) == world - 1

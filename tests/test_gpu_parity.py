@@ -411,6 +411,46 @@ def test_spmv_all_block_sizes(bfx, oracle, bs):
     assert np.allclose(A.to_dense(), As.toarray())
 
 
+@pytest.mark.parametrize("bs", [(1, 1), (2, 2), (3, 3), (2, 3), (3, 2)])
+def test_transpose(bfx, oracle, bs):
+    """MatrixCSR.transpose (la::transpose, la/mattrans.h) on one rank: structure and values bit-identical to the
+    oracle's restatement of impl::local_transpose, and equal to the scipy transpose - the check of
+    python/test/unit/la/test_transpose.py:21-68 - for a random rectangular matrix with empty rows and columns."""
+    la, common, torch, lib = bfx.la, bfx.common, bfx.torch, bfx.lib
+    n0, n1 = 37, 23
+    im0, im1 = common.IndexMap(common.COMM_SELF, n0), common.IndexMap(common.COMM_SELF, n1)
+    rng = np.random.default_rng(12345)
+    sp = la.SparsityPattern(common.COMM_SELF, [im0, im1], bs)
+    for i in range(n0):
+        if i % 7 == 3:
+            continue  # empty row
+        cols = rng.choice(n1 - 1, size=rng.integers(1, 9), replace=False)  # (column n1 - 1 stays empty)
+        sp.insert(np.array([i]), np.sort(cols))
+    sp.finalize()
+    A = la.MatrixCSR(sp)
+    A.data.copy_(torch.from_numpy(rng.random(A.data.numel())))
+    AT = A.transpose()
+    assert AT.block_size == [bs[1], bs[0]]
+    assert AT.index_map(0).size_local == n1 and AT.index_map(1).size_local == n0
+    oA = oracle.OMatrix([oracle.make_index_maps([n0], [[]], [[]])[0], oracle.make_index_maps([n1], [[]], [[]])[0]], bs,
+                        A.data.cpu().numpy(), A.indices, A.indptr, A.off_diag_offset)
+    c0, rp0, v0 = oracle.local_transpose(oA)
+    assert np.array_equal(AT.indptr, rp0) and np.array_equal(AT.indices, c0)
+    assert np.array_equal(AT.data.cpu().numpy(), v0)
+    assert np.array_equal(AT.to_scipy().toarray(), A.to_scipy().toarray().T)
+    # (A^T)^T == A
+    ATT = AT.transpose()
+    assert np.array_equal(ATT.indptr, A.indptr) and np.array_equal(ATT.indices, A.indices)
+    assert np.array_equal(ATT.data.cpu().numpy(), A.data.cpu().numpy())
+    # mult with the transposed matrix == multT with the original
+    x = la.Vector(im0, bs[0])
+    x.array.copy_(torch.arange(x.array.numel(), dtype=torch.float64))
+    y1, y2 = la.Vector(im1, bs[1]), la.Vector(im1, bs[1])
+    AT.mult(x, y1)
+    A.mult(x, y2, transpose=True)
+    assert np.allclose(y1.array.cpu().numpy(), y2.array.cpu().numpy(), rtol=1e-13, atol=1e-13)
+
+
 @pytest.mark.parametrize("kind", ["p1", "p2", "q1"])
 def test_spmv_assembled(bfx, oracle, kind):
     la, fem, torch = bfx.la, bfx.fem, bfx.torch

@@ -313,3 +313,64 @@ def test_golden_interior_facets_dS(oracle):
     # total of all entries = int_dS (avg 1)(avg 1) = total length of the interior edges
     length = 2 * 11 * 1.0 + 144 * np.sqrt(2.0) / 12.0
     assert np.sum(data) == pytest.approx(length, rel=1e-13)
+
+
+def _random_distributed_matrices(O, size, bs, rng):
+    """A rectangular matrix on `size` simulated ranks with random rows, ghost columns and values."""
+    nr = [5 + r for r in range(size)]
+    nc = [4 + 2 * r for r in range(size)]
+    coff = np.concatenate([[0], np.cumsum(nc)])
+    ghosts, owners = [], []
+    for r in range(size):
+        other = [g for g in range(coff[-1]) if not (coff[r] <= g < coff[r + 1])]
+        gs = sorted(rng.choice(other, size=min(len(other), 3 + r), replace=False).tolist()) if other else []
+        ghosts.append(gs)
+        owners.append([int(np.searchsorted(coff, g, side="right") - 1) for g in gs])
+    m0 = O.make_index_maps(nr, [[] for _ in nr], [[] for _ in nr])
+    m1 = O.make_index_maps(nc, ghosts, owners)
+    mats = []
+    for r in range(size):
+        rp, cols, od = [0], [], []
+        for _ in range(nr[r]):
+            dc = sorted(rng.choice(nc[r], size=rng.integers(0, nc[r] + 1), replace=False).tolist())
+            ng = len(ghosts[r])
+            gc = sorted((nc[r] + rng.choice(ng, size=rng.integers(0, ng + 1), replace=False)).tolist()) if ng else []
+            cols += dc + gc
+            od.append(rp[-1] + len(dc))
+            rp.append(len(cols))
+        data = rng.random(len(cols) * bs[0] * bs[1])
+        mats.append(O.OMatrix([m0[r], m1[r]], bs, data, np.array(cols, dtype=np.int32), np.array(rp, dtype=np.int64),
+                              np.array(od, dtype=np.int64)))
+    return mats
+
+
+def _gather(mats):
+    """mat_gather of python/test/unit/la/conftest.py:20-43 on simulated ranks."""
+    import scipy.sparse as sps
+
+    bs0, bs1 = mats[0].bs
+    vals, cols, ptr = [], [], [np.zeros(1, dtype=np.int64)]
+    for A in mats:
+        nr = A.index_maps[0].size_local
+        n = int(A.row_ptr[nr])
+        vals.append(A.data[: n * bs0 * bs1])
+        cols.append(A.index_maps[1].local_to_global(A.cols[:n]))
+        ptr.append(A.row_ptr[1 : nr + 1] + ptr[-1][-1])
+    shape = (mats[0].index_maps[0].size_global * bs0, mats[0].index_maps[1].size_global * bs1)
+    return sps.bsr_matrix((np.concatenate(vals).reshape(-1, bs0, bs1), np.concatenate(cols), np.concatenate(ptr)), shape=shape)
+
+
+@pytest.mark.parametrize("bs", [(1, 1), (2, 2), (3, 3), (2, 3), (3, 2)])
+@pytest.mark.parametrize("size", [1, 2, 3, 4])
+def test_transpose_vs_scipy(oracle, size, bs):
+    """la::transpose restated (oracle.transpose, la/mattrans.h) against the gathered scipy transpose, the check of
+    python/test/unit/la/test_transpose.py:21-68, on 1-4 simulated ranks."""
+    rng = np.random.default_rng(12345)
+    mats = _random_distributed_matrices(oracle, size, bs, rng)
+    G = _gather(mats).toarray()
+    T = oracle.transpose(mats)
+    GT = _gather(T).toarray()
+    assert GT.shape == G.T.shape and np.array_equal(GT, G.T)
+    for A, AT in zip(mats, T):
+        assert AT.index_maps[0].num_ghosts == 0 and AT.bs == (bs[1], bs[0])
+        assert AT.index_maps[0].size_local == A.index_maps[1].size_local
