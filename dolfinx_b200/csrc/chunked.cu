@@ -23,6 +23,7 @@
 // The same file holds the grouped vector kernel (bfx_asm_build_groups) that reuses the warp tables.
 #include "asm_device.cuh"
 #include "elements.cuh"
+#include <cstdlib>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -867,8 +868,10 @@ struct ChunkSmem
 // TWO (two-stage write-back, symmetric plans with 32-bit addresses): phase 2 leaves the sum of every destination in
 // shared memory; a third phase walks the chunk's (address, destination) list in ADDRESS order, so that consecutive
 // lanes update consecutive CSR values - both entries of a symmetric pair included - instead of two scattered ones each
-template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false>
-__global__ void __launch_bounds__(THREADS, chunk_min_ctas(THREADS)) k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
+// OCC: resident CTAs per SM asked of the register allocator (0 = chunk_min_ctas(THREADS))
+template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0>
+__global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
+    k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
   constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, NS = staged_per_cell(N, SYM), TPC = THREADS / CB;
   constexpr int DS = SYM ? 2 : 1; // addresses per destination
@@ -1209,6 +1212,19 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   if (c->wr_addr)
     return fail(BFX_ERR_INVALID, "two-stage chunk plan without a two-stage kernel");
   const size_t smem = ChunkSmem<NS, CB, SYM ? 2 : 1>::TOTAL;
+  if constexpr (SYM && NS <= 16 && CB == 256)
+  {
+    // experiment knob (read once): BFX_CHUNK_OCC=5 runs the variant compiled for 5 resident CTAs per SM (51 registers)
+    static const int occ = getenv("BFX_CHUNK_OCC") ? atoi(getenv("BFX_CHUNK_OCC")) : 0;
+    if (occ == 5 && c->addr_bytes == 4)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
   if (c->addr_bytes == 4)
   {
     BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t>,
