@@ -123,24 +123,21 @@ class SparsityPattern:
             self._segments.append(("cells", cells, dofmap0, dofmap1))
 
     # -- finalize --------------------------------------------------------------------------------
-    def _ghost_row_lists(self, local_size0, num_rows0):
-        """Per ghost row: columns in insertion order, first occurrences only."""
-        n_ghost = num_rows0 - local_size0
-        lists = [[] for _ in range(n_ghost)]
-        seen = [set() for _ in range(n_ghost)]
+    def _ghost_row_entries(self, local_size0, num_rows0, ncols):
+        """(ghost row index, local column) of every distinct entry inserted into a ghost row, grouped by row, the
+        columns of a row in the order of their first insertion."""
+        rows_all, cols_all = [], []
         for seg in self._segments:
             if seg[0] == "coo":
                 _, rows, cols = seg
                 sel = np.flatnonzero(rows >= local_size0)
-                for r, c in zip(rows[sel] - local_size0, cols[sel]):
-                    c = int(c)
-                    if c not in seen[r]:
-                        seen[r].add(c)
-                        lists[r].append(c)
+                rows_all.append(rows[sel].astype(np.int64) - local_size0)
+                cols_all.append(cols[sel].astype(np.int64))
             else:
                 from . import _lib
 
                 _, cells, dm0, dm1 = seg
+                n_ghost = num_rows0 - local_size0
                 ncells = dm0.shape[0] if cells is None else cells.numel()
                 counts = np.zeros(n_ghost, dtype=np.int64)
                 args = (num_rows0, local_size0, _lib.dptr(dm0), dm0.shape[1], _lib.dptr(dm1), dm1.shape[1],
@@ -148,14 +145,11 @@ class SparsityPattern:
                 _lib.check(_lib.lib.bfx_sparsity_ghost_rows(*args, counts.ctypes.data, None, _lib.current_stream()))
                 packed = np.zeros(int(counts.sum()), dtype=np.int32)
                 _lib.check(_lib.lib.bfx_sparsity_ghost_rows(*args, counts.ctypes.data, packed.ctypes.data, _lib.current_stream()))
-                off = np.concatenate([[0], np.cumsum(counts)])
-                for g in range(n_ghost):
-                    for c in packed[off[g]:off[g + 1]]:
-                        c = int(c)
-                        if c not in seen[g]:
-                            seen[g].add(c)
-                            lists[g].append(c)
-        return lists
+                rows_all.append(np.repeat(np.arange(n_ghost, dtype=np.int64), counts))
+                cols_all.append(packed.astype(np.int64))
+        if not rows_all:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        return first_occurrences_by_row(np.concatenate(rows_all), np.concatenate(cols_all), ncols)
 
     def finalize(self):
         if self._finalized:
@@ -170,45 +164,27 @@ class SparsityPattern:
 
         if self.comm.size > 1:
             # (global row, global col, col owner) triplets of ghost rows -> owners (:291-383)
-            lists = self._ghost_row_lists(local_size0, num_rows0)
+            grow_i, gcol_l = self._ghost_row_entries(local_size0, num_rows0, local_size1 + m1.num_ghosts)
             neighbour_rank = np.searchsorted(m0.src, m0.owners)
-            bufs = [[] for _ in m0.src]
-            for i, cols_i in enumerate(lists):
-                if not cols_i:
-                    continue
-                cl = np.asarray(cols_i, dtype=np.int64)
-                owned = cl < local_size1
-                gcol = np.where(owned, cl + m1.local_range[0], 0)
-                gown = np.full(cl.size, self.comm.rank, dtype=np.int64)
-                if np.any(~owned):
-                    gi = cl[~owned] - local_size1
-                    gcol[~owned] = m1.ghosts[gi]
-                    gown[~owned] = m1.owners[gi]
-                trip = np.stack([np.full(cl.size, m0.ghosts[i], dtype=np.int64), gcol, gown], axis=1).reshape(-1)
-                bufs[neighbour_rank[i]].append(trip)
-            send = [np.concatenate(b) if b else np.zeros(0, dtype=np.int64) for b in bufs]
+            owned = gcol_l < local_size1
+            gi = np.where(owned, 0, gcol_l - local_size1)
+            has_g = m1.num_ghosts > 0
+            gcol = np.where(owned, gcol_l + m1.local_range[0], m1.ghosts[gi] if has_g else 0)
+            gown = np.where(owned, self.comm.rank, m1.owners[gi].astype(np.int64) if has_g else 0)
+            trip = np.stack([m0.ghosts[grow_i] if grow_i.size else np.zeros(0, dtype=np.int64), gcol, gown], axis=1)
+            nb = neighbour_rank[grow_i] if grow_i.size else np.zeros(0, dtype=np.int64)
+            order = np.argsort(nb, kind="stable")  # per owner: ghost rows ascending, columns in insertion order
+            cnt = np.bincount(nb, minlength=len(m0.src)) if grow_i.size else np.zeros(len(m0.src), dtype=np.int64)
+            disp = np.concatenate([[0], np.cumsum(cnt)])
+            trip = trip[order].astype(np.int64)
+            send = [trip[disp[k]:disp[k + 1]].reshape(-1) for k in range(len(m0.src))]
             recv = self.comm.neighbor_alltoallv(m0.src, m0.dest, send, dtype=np.int64)
             data_in = np.concatenate(recv) if recv else np.zeros(0, dtype=np.int64)
             # new ghost columns in arrival order (:389-423)
-            g2l = {int(g): local_size1 + i for i, g in enumerate(col_ghosts)}
-            rr, rc = [], []
-            local_i = local_size1 + len(col_ghosts)
-            for i in range(0, data_in.size, 3):
-                row_local = int(data_in[i]) - m0.local_range[0]
-                col, owner = int(data_in[i + 1]), int(data_in[i + 2])
-                rr.append(row_local)
-                if m1.local_range[0] <= col < m1.local_range[1]:
-                    rc.append(col - m1.local_range[0])
-                else:
-                    j = g2l.get(col)
-                    if j is None:
-                        j = g2l[col] = local_i
-                        col_ghosts.append(col)
-                        col_ghost_owners.append(owner)
-                        local_i += 1
-                    rc.append(j)
-            recv_rows = np.asarray(rr, dtype=np.int32)
-            recv_cols = np.asarray(rc, dtype=np.int32)
+            in_rows, in_cols, in_own = data_in[0::3], data_in[1::3], data_in[2::3]
+            recv_rows = (in_rows - m0.local_range[0]).astype(np.int32)
+            recv_cols, col_ghosts, col_ghost_owners = received_columns_to_local(
+                in_cols, in_own, m1.local_range, col_ghosts, col_ghost_owners)
 
         cell_segs = [s for s in self._segments if s[0] == "cells"]
         coo_rows = [s[1] for s in self._segments if s[0] == "coo"] + [recv_rows]
@@ -461,6 +437,68 @@ def cg(x: Vector, b: Vector, action, kmax: int = 50, rtol: float = 1e-8) -> int:
 # ---------------------------------------------------------------------------------------------
 # MatrixCSR
 # ---------------------------------------------------------------------------------------------
+def received_columns_to_local(in_cols, in_own, local_range, col_ghosts, col_ghost_owners):
+    """Local column index of every received (global column, owner) pair; columns this rank neither owns nor ghosts are
+    appended to the ghost list in ARRIVAL order (la/SparsityPattern.cpp:389-423).
+    Returns (local columns int32, ghosts list, owners list)."""
+    in_cols = np.asarray(in_cols, dtype=np.int64)
+    in_own = np.asarray(in_own, dtype=np.int64)
+    ls1 = local_range[1] - local_range[0]
+    mine = (in_cols >= local_range[0]) & (in_cols < local_range[1])
+    known = np.asarray(col_ghosts, dtype=np.int64)
+    cand = np.flatnonzero(~mine & ~np.isin(in_cols, known))
+    col_ghosts, col_ghost_owners = list(col_ghosts), list(col_ghost_owners)
+    if cand.size:
+        _, first = np.unique(in_cols[cand], return_index=True)
+        newg = cand[np.sort(first)]  # first arrival of every unknown column
+        col_ghosts += in_cols[newg].tolist()
+        col_ghost_owners += in_own[newg].tolist()
+    allg = np.asarray(col_ghosts, dtype=np.int64)
+    out = in_cols - local_range[0]
+    if np.any(~mine):
+        og = np.argsort(allg, kind="stable")
+        out[~mine] = ls1 + og[np.searchsorted(allg[og], in_cols[~mine])]
+    return out.astype(np.int32), col_ghosts, col_ghost_owners
+
+
+def locate_entries(indptr, indices, rows, cols, ncols):
+    """Position in the CSR arrays of every (rows[k], cols[k]) - the ``std::lower_bound`` per entry of
+    la/MatrixCSR.h:829-845, for all entries at once: inside the rows that occur, (row rank, column) is a strictly
+    increasing key, so one ``searchsorted`` over the entries of those rows does it.  None if an entry is missing."""
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    if rows.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    indptr = np.asarray(indptr)
+    urows, inv = np.unique(rows, return_inverse=True)
+    start = indptr[urows].astype(np.int64)
+    lens = indptr[urows + 1].astype(np.int64) - start
+    tot = int(lens.sum())
+    first = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    flat = np.arange(tot, dtype=np.int64) + np.repeat(start - first, lens)  # positions of the entries of those rows
+    rank_of = np.repeat(np.arange(urows.size, dtype=np.int64), lens)
+    keys = rank_of * np.int64(ncols) + np.asarray(indices)[flat].astype(np.int64)
+    want = inv.astype(np.int64) * np.int64(ncols) + cols
+    at = np.searchsorted(keys, want)
+    if tot == 0 or np.any(at >= tot) or np.any(keys[np.minimum(at, tot - 1)] != want):
+        return None
+    return flat[at]
+
+
+def first_occurrences_by_row(rows, cols, ncols):
+    """(rows, cols) pairs in insertion order -> the pairs grouped by row, every row keeping its DISTINCT columns in
+    the order of their first insertion (what the COO cache of la/SparsityPattern.cpp:291-330 hands to the owners).
+    Returns (rows_sorted, cols_sorted)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    if rows.size == 0:
+        return rows, cols
+    _, first = np.unique(rows * np.int64(ncols) + cols, return_index=True)
+    keep = np.sort(first)  # first occurrences, still in insertion order
+    order = np.argsort(rows[keep], kind="stable")
+    return rows[keep][order], cols[keep][order]
+
+
 def matrix_ghost_plan(index_maps, bs, indptr, indices):
     """Ghost-row exchange plan built by the MatrixCSR constructor (la/MatrixCSR.h:705-849), host side.
 
@@ -497,13 +535,9 @@ def matrix_ghost_plan(index_maps, bs, indptr, indices):
         order1 = np.argsort(m1.ghosts, kind="stable")
         pos = np.searchsorted(m1.ghosts[order1], gc[ghost_mask])
         lcol[ghost_mask] = ls1 + order1[pos]
-    unpack = np.empty(lrow.size, dtype=np.int64)
-    for k in range(lrow.size):
-        c0, c1 = indptr[lrow[k]], indptr[lrow[k] + 1]
-        d = c0 + np.searchsorted(indices[c0:c1], lcol[k])
-        if d >= c1 or indices[d] != lcol[k]:
-            raise RuntimeError("MatrixCSR: received ghost-row entry not in sparsity")
-        unpack[k] = d
+    unpack = locate_entries(indptr, indices, lrow, lcol, ls1 + m1.num_ghosts)
+    if unpack is None:
+        raise RuntimeError("MatrixCSR: received ghost-row entry not in sparsity")
     return dict(ghost_row_to_rank=ghost_row_to_rank, val_send_disp=val_send_disp * bs2,
                 val_recv_disp=bs2 * recv_disp // 2, unpack_pos=unpack, src=m0.src.copy(), dest=m0.dest.copy())
 

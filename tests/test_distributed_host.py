@@ -213,3 +213,65 @@ def test_product_host_plans_gloo(tmp_path, world, nglob):
     s.close()
     mp.spawn(_worker, args=(world, port, nglob, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+# ---------------------------------------------------------------------------------------------
+# vectorised host helpers against literal per-entry loops (the loops of the reference)
+# ---------------------------------------------------------------------------------------------
+def test_host_plan_helpers_against_loops():
+    from dolfinx_b200 import la
+
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        # first_occurrences_by_row: insertion-ordered distinct columns per row (SparsityPattern.cpp:291-330)
+        nrows, ncols, n = int(rng.integers(1, 9)), int(rng.integers(1, 12)), int(rng.integers(0, 200))
+        rows, cols = rng.integers(0, nrows, n), rng.integers(0, ncols, n)
+        lists = [[] for _ in range(nrows)]
+        for r, c in zip(rows, cols):
+            if c not in lists[r]:
+                lists[r].append(int(c))
+        r2, c2 = la.first_occurrences_by_row(rows, cols, ncols)
+        assert np.array_equal(r2, np.repeat(np.arange(nrows), [len(x) for x in lists]))
+        assert np.array_equal(c2, np.array([c for x in lists for c in x], dtype=np.int64))
+
+        # received_columns_to_local: new ghost columns in arrival order (SparsityPattern.cpp:389-423)
+        lo = int(rng.integers(0, 50))
+        hi = lo + int(rng.integers(1, 20))
+        known = rng.choice(np.setdiff1d(np.arange(0, 120), np.arange(lo, hi)), size=int(rng.integers(0, 10)), replace=False)
+        owners = rng.integers(0, 4, known.size)
+        m = int(rng.integers(0, 150))
+        in_cols = rng.integers(0, 120, m)
+        in_own = in_cols % 5  # the owner is a function of the column, as in a real exchange
+        g2l = {int(g): (hi - lo) + i for i, g in enumerate(known)}
+        gh, go, out = list(known), list(owners), []
+        for c, o in zip(in_cols, in_own):
+            if lo <= c < hi:
+                out.append(int(c) - lo)
+            else:
+                if int(c) not in g2l:
+                    g2l[int(c)] = (hi - lo) + len(gh)
+                    gh.append(int(c))
+                    go.append(int(o))
+                out.append(g2l[int(c)])
+        o2, gh2, go2 = la.received_columns_to_local(in_cols, in_own, (lo, hi), list(known), list(owners))
+        assert np.array_equal(o2, np.array(out, dtype=np.int32)) and list(gh2) == gh and list(go2) == go
+
+        # locate_entries: lower_bound per entry (MatrixCSR.h:829-845)
+        nr, nc = int(rng.integers(1, 15)), int(rng.integers(1, 20))
+        indptr, indices = [0], []
+        for _ in range(nr):
+            cs = np.sort(rng.choice(nc, size=int(rng.integers(0, nc + 1)), replace=False))
+            indices += cs.tolist()
+            indptr.append(len(indices))
+        indptr, indices = np.array(indptr, dtype=np.int64), np.array(indices, dtype=np.int32)
+        if len(indices):
+            k = rng.integers(0, len(indices), int(rng.integers(0, 60)))
+            qr = np.searchsorted(indptr, k, side="right") - 1
+            got = la.locate_entries(indptr, indices, qr, indices[k], nc)
+            assert np.array_equal(got, k)
+            # an entry that is not in the pattern is reported
+            full = [(r, c) for r in range(nr) for c in range(nc) if c not in indices[indptr[r]:indptr[r + 1]]]
+            if full:
+                r, c = full[int(rng.integers(0, len(full)))]
+                assert la.locate_entries(indptr, indices, np.append(qr, r), np.append(indices[k], c), nc) is None
+        assert la.locate_entries(indptr, indices, [], [], nc).size == 0
