@@ -154,13 +154,22 @@ def build_problem(cfg, n, comm, device):
         nglob = tuple(n * pg[d] for d in range(3))
         part = M.BoxPartition(comm.rank, pg, nglob)
         if elem == "P2":
-            raise SystemExit("multi-GPU bench is defined for P1 / Q1 (BASELINE configs[4])")
-        x, cells, dofmap, local, n_owned, ghosts, owners = M.partition_cells_torch(part, cell, device)
+            # BASELINE configs[2] on N GPUs: the P2 dofs of a Kuhn box are the points of the doubled lattice, partitioned
+            # like vertices (mesh.p2_partition; host numpy, then uploaded)
+            xd_h, dm_h, n_owned, ghosts, owners, dc_h = M.p2_partition(part)
+            x = torch.from_numpy(part.coordinates()).to(device)
+            cells = torch.from_numpy(xd_h).to(device)
+            dofmap = torch.from_numpy(dm_h).to(device)
+            dof_x = torch.from_numpy(dc_h).to(device)
+            ndofs = n_owned + len(ghosts)
+            del xd_h, dm_h, dc_h
+        else:
+            x, cells, dofmap, local, n_owned, ghosts, owners = M.partition_cells_torch(part, cell, device)
+            ndofs = n_owned + len(ghosts)
+            dof_x = torch.empty((ndofs, 3), dtype=torch.float64, device=device)
+            dof_x[local.reshape(-1).long()] = x
+            del local
         im = common.IndexMap(comm, n_owned, ghosts, owners)
-        ndofs = n_owned + len(ghosts)
-        dof_x = torch.empty((ndofs, 3), dtype=torch.float64, device=device)
-        dof_x[local.reshape(-1).long()] = x
-        del local
         msh = fem.Mesh(comm, x, cells, cell, cells.shape[0])
     bs = 3 if elem == "Q1" else 1
     V = fem.FunctionSpace(msh, elem, fem.DofMap(dofmap, bs, im))

@@ -322,6 +322,53 @@ class BoxPartition:
         return lat.astype(np.int32), np.ascontiguousarray(dm.astype(np.int32)), n_owned, ghosts, owners
 
 
+@dataclass
+class DoubledBoxPartition(BoxPartition):
+    """The lattice of P2 dof nodes of a brick partition.
+
+    On a Kuhn box every point of the DOUBLED lattice (2n+1)^3 carries exactly one P2 dof: even coordinates are
+    vertices, one / two / three odd coordinates are the midpoints of the axis edges / the face diagonals / the body
+    diagonal (each unit square and each cube has exactly one diagonal: (2n+1)^3 = V + E).  So the
+    P2 dofs of a brick partition are numbered, owned and ghosted exactly like the vertices of the partition of the
+    doubled lattice ("lower brick owns the shared plane"); this class is that partition: ``nglob`` holds 2 n, and the
+    split of a direction is twice the split of the cube lattice."""
+
+    @staticmethod
+    def _split(n, p, r):
+        start, count = BoxPartition._split(n // 2, p, r)
+        return 2 * start, 2 * count
+
+
+def p2_partition(part: "BoxPartition"):
+    """P2 Lagrange dofs of the brick ``part`` of a tetrahedral (Kuhn) box.
+
+    Returns (x_dofmap int32 (C,4), dofmap int32 (C,10), n_owned, ghosts int64, owners int32, dof_coords (ndofs,3)):
+    local dofs = owned doubled-lattice points lexicographically, then ghosts (see :class:`DoubledBoxPartition`);
+    cell dofs = 4 vertices, then the 6 edges in Basix order (:data:`TET_EDGES`)."""
+    d2 = DoubledBoxPartition(part.rank, part.pgrid, tuple(2 * n for n in part.nglob))
+    assert d2.nloc == tuple(2 * n for n in part.nloc) and d2.origin == tuple(2 * o for o in part.origin)
+    local, n_owned, ghosts, owners = d2.vertex_numbering()
+    lat = box_tets(part.nloc, dtype=np.int64)
+    nx, ny, nz = part.nloc
+    ix, iy, iz = lat % (nx + 1), (lat // (nx + 1)) % (ny + 1), lat // ((nx + 1) * (ny + 1))
+
+    def flat2(x2, y2, z2):
+        return (z2 * (2 * ny + 1) + y2) * (2 * nx + 1) + x2
+
+    cols = [flat2(2 * ix[:, a], 2 * iy[:, a], 2 * iz[:, a]) for a in range(4)]
+    cols += [flat2(ix[:, a] + ix[:, b], iy[:, a] + iy[:, b], iz[:, a] + iz[:, b]) for a, b in TET_EDGES]
+    dm = local.reshape(-1)[np.stack(cols, axis=1)]
+    # coordinates of the dof nodes (owned first, then ghosts), domain [0,1]^3
+    ndofs = n_owned + len(ghosts)
+    z2, y2, x2 = np.meshgrid(np.arange(2 * nz + 1), np.arange(2 * ny + 1), np.arange(2 * nx + 1), indexing="ij")
+    dc = np.empty((ndofs, 3))
+    idx = local.reshape(-1)
+    for d, (c2, o, n) in enumerate(((x2, part.origin[0], part.nglob[0]), (y2, part.origin[1], part.nglob[1]),
+                                    (z2, part.origin[2], part.nglob[2]))):
+        dc[idx, d] = (c2.reshape(-1) + 2 * o) / (2.0 * n)
+    return lat.astype(np.int32), np.ascontiguousarray(dm.astype(np.int32)), n_owned, ghosts, owners, dc
+
+
 def _partition_numbering_torch(part: "BoxPartition", device):
     """Device version of :meth:`BoxPartition.vertex_numbering`: (local int32 (nz+1,ny+1,nx+1), n_owned,
     ghosts int64 numpy, owners int32 numpy)."""

@@ -275,3 +275,64 @@ def test_host_plan_helpers_against_loops():
                 r, c = full[int(rng.integers(0, len(full)))]
                 assert la.locate_entries(indptr, indices, np.append(qr, r), np.append(indices[k], c), nc) is None
         assert la.locate_entries(indptr, indices, [], [], nc).size == 0
+
+
+@pytest.mark.parametrize("nranks,nglob", [(2, (4, 3, 2)), (4, (4, 4, 2)), (8, (4, 4, 4)), (3, (5, 2, 2))])
+def test_oracle_distributed_p2_equals_serial(oracle, nranks, nglob):
+    """BASELINE configs[2] on several ranks: the P2 brick partition (mesh.p2_partition: the dofs of a Kuhn box are the
+    points of the doubled lattice) assembled per simulated rank + scatter_rev equals the serial P2 assembly entry by
+    entry, the dofs matched through their coordinates (cf. cpp/test/matrix.cpp:59-64)."""
+    O = oracle
+    pg = M.pgrid_for(nranks)
+    parts = [M.BoxPartition(r, pg, nglob) for r in range(nranks)]
+    inputs = []
+    for part in parts:
+        xd, dm, n_owned, ghosts, owners, dc = M.p2_partition(part)
+        inputs.append(dict(x=part.coordinates(), x_dofmap=xd, dofmap=dm, n_owned=n_owned, ghosts=ghosts, owners=owners, dc=dc))
+    maps, pats, mats = oracle_world(O, inputs)
+    kappa = np.array([2.0])
+    for i, A in zip(inputs, mats):
+        O.assemble_matrix(O.K_POISSON_P2_TET_A, i["x_dofmap"], i["x"], np.arange(len(i["dofmap"])), i["dofmap"], 1,
+                          i["dofmap"], 1, A.data, A.cols, A.row_ptr, constants=kappa)
+    O.matrix_scatter_rev(mats)
+    N = maps[0].size_global
+    assert N == (2 * nglob[0] + 1) * (2 * nglob[1] + 1) * (2 * nglob[2] + 1)
+    # doubled-lattice key of every global dof, from the owners' coordinates
+    n2 = 2 * np.array(nglob)
+    key_of_global = np.empty(N, dtype=np.int64)
+    for i, m in zip(inputs, maps):
+        k = np.rint(i["dc"][: m.size_local] * n2).astype(np.int64)
+        key_of_global[m.local_range[0]:m.local_range[1]] = (k[:, 2] * (n2[1] + 1) + k[:, 1]) * (n2[0] + 1) + k[:, 0]
+    assert len(np.unique(key_of_global)) == N
+    for i, m in zip(inputs, maps):  # ghost global indices point at dofs with the same coordinates
+        kg = np.rint(i["dc"][m.size_local:] * n2).astype(np.int64)
+        assert np.array_equal(key_of_global[m.ghosts], (kg[:, 2] * (n2[1] + 1) + kg[:, 1]) * (n2[0] + 1) + kg[:, 0])
+    G = sp.lil_matrix((N, N))
+    for A in mats:
+        m0, m1 = A.index_maps
+        for r in range(m0.size_local):
+            gc = m1.local_to_global(A.cols[A.row_ptr[r]:A.row_ptr[r + 1]])
+            G[m0.local_range[0] + r, gc] = A.data[A.row_ptr[r]:A.row_ptr[r + 1]]
+    # serial reference, renumbered to the distributed global numbering through the coordinates
+    ps = P.tet_p2(nglob)
+    ks = np.rint(ps.dof_coords * n2).astype(np.int64)
+    key_s = (ks[:, 2] * (n2[1] + 1) + ks[:, 1]) * (n2[0] + 1) + ks[:, 0]
+    glob_of_key = np.empty(N, dtype=np.int64)
+    glob_of_key[key_of_global] = np.arange(N)
+    to_glob = glob_of_key[key_s]  # serial dof -> distributed global dof
+    pat, ref = P.oracle_assemble_matrix(O, ps, O.K_POISSON_P2_TET_A, constants=kappa)
+    S = sp.csr_matrix((ref, pat.edges, pat.offsets), shape=(N, N)).tocoo()
+    S = sp.csr_matrix((S.data, (to_glob[S.row], to_glob[S.col])), shape=(N, N))
+    Gc = G.tocsr()
+    assert abs(Gc - S).max() <= 1e-12 * abs(S).max()
+    # same structure: the index sets of the owned rows agree with the serial pattern (explicit zeros included)
+    keys_d = []
+    for A in mats:
+        m0, m1 = A.index_maps
+        nl = m0.size_local
+        rows_g = np.repeat(np.arange(nl, dtype=np.int64) + m0.local_range[0], np.diff(A.row_ptr[: nl + 1]))
+        keys_d.append(rows_g * N + m1.local_to_global(A.cols[: A.row_ptr[nl]]))
+    rows_s = np.repeat(np.arange(N, dtype=np.int64), np.diff(pat.offsets))
+    keys_s = to_glob[rows_s] * N + to_glob[pat.edges]
+    assert np.array_equal(np.sort(np.concatenate(keys_d)), np.sort(keys_s))
+    assert O.matrix_squared_norm(mats) == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
