@@ -336,3 +336,83 @@ def test_oracle_distributed_p2_equals_serial(oracle, nranks, nglob):
     keys_s = to_glob[rows_s] * N + to_glob[pat.edges]
     assert np.array_equal(np.sort(np.concatenate(keys_d)), np.sort(keys_s))
     assert O.matrix_squared_norm(mats) == pytest.approx(float(np.sum(ref**2)), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's ring fixtures: cpp/test/vector.cpp:22-55, cpp/test/common/index_map.cpp:22-170
+# ---------------------------------------------------------------------------------------------
+def ring_maps(O, size, size_local=100):
+    """create_index_map of cpp/test/common/index_map.cpp:22-38: (size - 1) * 3 ghosts owned by the next rank."""
+    ghosts = [[((r + 1) % size) * size_local + i for i in range((size - 1) * 3)] for r in range(size)]
+    owners = [[(r + 1) % size] * len(g) for r, g in enumerate(ghosts)]
+    return O.make_index_maps([size_local] * size, ghosts, owners)
+
+
+@pytest.mark.parametrize("size", [1, 2, 3, 5])
+def test_oracle_ring_vector_and_scatter(oracle, size):
+    O = oracle
+    size_local = 100
+    maps = ring_maps(O, size, size_local)
+    # cpp/test/vector.cpp:40-54: closed-form norms (ghosts do not count)
+    ones = [np.ones(m.size_local + m.num_ghosts) for m in maps]
+    assert O.inner_product(maps, 1, ones, ones) == size * size_local
+    vs = [np.full(m.size_local + m.num_ghosts, float(m.rank)) for m in maps]
+    sumn2 = size_local * (size - 1) * size * (2 * size - 1) / 6
+    assert O.inner_product(maps, 1, vs, vs) == sumn2
+    for n in (1, 5, 10):
+        scs = O.make_scatterers(maps, n)
+        # index_map.cpp:40-100: forward scatter of val * rank => every ghost holds val * next rank
+        val = 11.0
+        xs = [np.concatenate([np.full(n * m.size_local, val * m.rank), np.full(n * m.num_ghosts, -1.0)]) for m in maps]
+        O.vector_scatter_fwd(maps, scs, n, xs)
+        for m, x in zip(maps, xs):
+            assert np.all(x[n * m.size_local:] == val * ((m.rank + 1) % size))
+        # index_map.cpp:103-166: reverse scatter (add) of `value` in every ghost => sum = n * value * num_ghosts, twice
+        value = 15.0
+        xs = [np.concatenate([np.zeros(n * m.size_local), np.full(n * m.num_ghosts, value)]) for m in maps]
+        for rep in (1, 2):
+            O.vector_scatter_rev(maps, scs, n, xs, "add")
+            for m, x in zip(maps, xs):
+                # rank r receives from the previous rank's ghosts
+                assert x[: n * m.size_local].sum() == rep * n * value * maps[(m.rank - 1) % size].num_ghosts
+
+
+def _ring_worker(rank, world, port, tmpdir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        from dolfinx_b200 import common
+        from oracle import oracle as O
+
+        omaps = ring_maps(O, world)
+        om = omaps[rank]
+        im = common.IndexMap(common.Comm(), om.size_local, om.ghosts, om.owners)
+        assert im.local_range == om.local_range and im.size_global == world * 100
+        assert np.array_equal(im.src, om.src) and np.array_equal(im.dest, om.dest)
+        assert np.array_equal(im.local_to_global(np.arange(om.size_local + om.num_ghosts)),
+                              om.local_to_global(np.arange(om.size_local + om.num_ghosts)))
+        for n in (1, 5, 10):
+            sc = common.Scatterer(im, n)
+            osc = O.make_scatterers(omaps, n)[rank]
+            for name in ("local_inds", "remote_inds", "sizes_local", "displs_local", "sizes_remote", "displs_remote"):
+                assert np.array_equal(getattr(sc, name), getattr(osc, name)), (name, n)
+            assert len(sc.local_indices()) == n * 3 * (world - 1) and len(sc.remote_indices()) == n * om.num_ghosts
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_product_ring_index_map_and_scatterer_gloo(tmp_path, world):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_ring_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
