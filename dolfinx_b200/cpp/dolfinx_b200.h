@@ -457,6 +457,25 @@ auto norm(const V& x, Norm type = Norm::l2)
   return r;
 }
 
+namespace impl
+{
+/// la::impl::Sparsity (la/matmul.h): a finalised pattern given by its arrays - what la::transpose / la::matmul hand
+/// to the MatrixCSR constructor (la/mattrans.h:153-155, 431-434)
+struct Sparsity
+{
+  std::shared_ptr<const common::IndexMap> row_map, col_map;
+  std::vector<std::int32_t> cols;
+  std::vector<std::int64_t> offsets;
+  std::vector<std::int32_t> off_diag;
+  std::array<int, 2> bs;
+  std::shared_ptr<const common::IndexMap> index_map(int dim) const { return dim == 0 ? row_map : col_map; }
+  int block_size(int dim) const { return bs.at(dim); }
+  std::pair<std::span<const std::int32_t>, std::span<const std::int64_t>> graph() const { return {cols, offsets}; }
+  std::span<const std::int32_t> off_diagonal_offsets() const { return off_diag; }
+  bfx_csr_t* release_csr() const { return nullptr; }
+};
+} // namespace impl
+
 /// la::MatrixCSR<double> (compact block mode) with device storage
 template <typename T = double>
 class MatrixCSR
@@ -466,10 +485,28 @@ class MatrixCSR
 public:
   using value_type = T;
   /// MatrixCSR(const SparsityPattern&) — la/MatrixCSR.h:628-703 (+ single-rank ghost plan: empty)
-  explicit MatrixCSR(const SparsityPattern& p)
-      : _index_maps{p.index_map(0), p.index_map(1)}, _bs{p.block_size(0), p.block_size(1)},
-        _cols(p.graph().first.begin(), p.graph().first.end()), _row_ptr(p.graph().second.begin(), p.graph().second.end())
+  explicit MatrixCSR(const SparsityPattern& p) { init(p); }
+  /// MatrixCSR(const impl::Sparsity&) with its values (host), as la::transpose builds its result (la/mattrans.h:155-157)
+  MatrixCSR(const impl::Sparsity& p, std::span<const T> values)
   {
+    init(p);
+    _data.copy_from(values);
+  }
+  MatrixCSR(const MatrixCSR&) = delete;
+  ~MatrixCSR()
+  {
+    bfx_csr_scatter_destroy(_scatter);
+    bfx_csr_destroy(_csr);
+  }
+
+private:
+  template <class Pattern>
+  void init(const Pattern& p)
+  {
+    _index_maps = {p.index_map(0), p.index_map(1)};
+    _bs = {p.block_size(0), p.block_size(1)};
+    _cols.assign(p.graph().first.begin(), p.graph().first.end());
+    _row_ptr.assign(p.graph().second.begin(), p.graph().second.end());
     std::span<const std::int32_t> nd = p.off_diagonal_offsets();
     _off_diagonal_offset.resize(nd.size());
     for (std::size_t i = 0; i < nd.size(); ++i)
@@ -483,12 +520,8 @@ public:
     }
     _data = DeviceArray<T>(_cols.size() * _bs[0] * _bs[1]);
   }
-  MatrixCSR(const MatrixCSR&) = delete;
-  ~MatrixCSR()
-  {
-    bfx_csr_scatter_destroy(_scatter);
-    bfx_csr_destroy(_csr);
-  }
+
+public:
   /// Install the ghost-row exchange plan computed by the reference constructor (la/MatrixCSR.h:705-849)
   void set_ghost_plan(std::span<const std::int32_t> ghost_row_to_rank, std::span<const std::int64_t> val_send_disp,
                       std::span<const std::int64_t> val_recv_disp, std::span<const std::int64_t> unpack_pos)
@@ -608,6 +641,39 @@ private:
   bfx_csr_t* _csr = nullptr;
   bfx_csr_scatter_t* _scatter = nullptr;
 };
+
+/// la::transpose (la/mattrans.h:121-159): the branch without neighbours in the column map (one rank, or no ghost
+/// columns anywhere near this rank); impl::local_transpose runs on the device, bit-exact (bfx_csr_transpose_local).
+/// With ghost columns the entries travel to the column owners first - host-side integer work the caller keeps
+/// (dolfinx_b200.la.matrix_transpose_plan is the tested restatement of la/mattrans.h:200-434).
+template <typename T>
+MatrixCSR<T> transpose(const MatrixCSR<T>& A)
+{
+  auto m0 = A.index_map(0);
+  auto m1 = A.index_map(1);
+  if (m0->comm().size != 1 and !(m1->src().empty() and m1->dest().empty()))
+    throw std::runtime_error("la::transpose: ghost columns present - exchange them first (la/mattrans.h:200-434)");
+  const std::array<int, 2> bs = A.block_size();
+  const std::int32_t n_row = m0->size_local(), n_col = m1->size_local();
+  const std::int64_t cap = A.row_ptr()[n_row];
+  DeviceArray<std::int64_t> rp(n_col + 1);
+  DeviceArray<std::int32_t> cols(std::max<std::int64_t>(cap, 1));
+  DeviceArray<T> vals(std::max<std::int64_t>(cap, 1) * bs[0] * bs[1]);
+  std::int64_t nnz = 0;
+  check(bfx_csr_transpose_local(A.csr(), A.values().data(), n_col, rp.data(), cols.data(), vals.data(), cap, &nnz, nullptr));
+  impl::Sparsity sp;
+  sp.row_map = std::make_shared<common::IndexMap>(m0->comm(), n_col); // la/mattrans.h:142-143
+  sp.col_map = std::make_shared<common::IndexMap>(m0->comm(), n_row);
+  sp.offsets = rp.to_host();
+  sp.cols = cols.to_host();
+  sp.cols.resize(nnz);
+  sp.off_diag.resize(n_col);
+  for (std::int32_t j = 0; j < n_col; ++j)
+    sp.off_diag[j] = static_cast<std::int32_t>(sp.offsets[j + 1] - sp.offsets[j]); // all columns owned (:148-151)
+  sp.bs = {bs[1], bs[0]};
+  std::vector<T> v = vals.to_host();
+  return MatrixCSR<T>(sp, std::span<const T>(v.data(), nnz * bs[0] * bs[1]));
+}
 } // namespace la
 
 // -------------------------------------------------------------------------------------------------

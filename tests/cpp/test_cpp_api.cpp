@@ -18,6 +18,13 @@ using namespace dolfinx_b200;
     }                                                                                                                  \
   } while (0)
 
+// compile-only: la::transpose of the mirror (its device part is covered by tests/test_gpu_parity.py::test_transpose)
+[[maybe_unused]] static double transpose_compiles(const dolfinx_b200::la::MatrixCSR<double>& A)
+{
+  auto AT = dolfinx_b200::la::transpose(A);
+  return AT.squared_norm();
+}
+
 int main()
 {
   int ndev = 0;
