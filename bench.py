@@ -5,11 +5,12 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
 
 A *step* is one full matrix assembly call sequence on one batch of synthetic input
-(SURVEY.md §8d): ``assemble_matrix`` with Dirichlet markers + ``set_diagonal`` +
-``MatrixCSR.scatter_reverse``; the ``values <- 0`` fill is excluded (values accumulate
-across steps).  ``value`` = global DOFs / step time, inputs resident in HBM.  ``e2e`` is the same
-metric through the host-buffer C-ABI entry (bfx_assemble_matrix_cells_host): geometry and bc
-markers copied host->device and the CSR values copied device->host inside the timed region.
+(SURVEY.md §8d), as a time loop issues it: ``A.set_value(0)`` + ``assemble_matrix`` with Dirichlet
+markers + ``set_diagonal`` + ``MatrixCSR.scatter_reverse`` (overlapped with the interior cells on
+N > 1 GPUs).  ``value`` = global DOFs / step time, inputs resident in HBM.  ``roofline`` times the
+assembly kernel alone.  ``e2e`` is the same metric through the host-buffer C-ABI entry
+(bfx_assemble_matrix_cells_host_begin/_end, two steps in flight): geometry and bc markers copied
+host->device and all CSR values copied device->host inside the timed region.
 SpMV (MatrixCSR::mult) is timed in a second loop and reported under ``spmv``.
 """
 
