@@ -374,3 +374,43 @@ def test_transpose_vs_scipy(oracle, size, bs):
     for A, AT in zip(mats, T):
         assert AT.index_maps[0].num_ghosts == 0 and AT.bs == (bs[1], bs[0])
         assert AT.index_maps[0].size_local == A.index_maps[1].size_local
+
+
+def test_empty_and_ragged_inputs(oracle):
+    """Edge cases of the path on the oracle: an empty cell list assembles nothing, an empty bc list marks nothing,
+    SpMV over a matrix with empty rows, a ragged (subset) cell list equals the sum of its parts."""
+    O = oracle
+    p = P.tet_p1(3, numbering="random", seed=1)
+    pat = P.oracle_pattern(O, p)
+    data = np.zeros(len(pat.edges))
+    none = np.zeros(0, dtype=np.int32)
+    O.assemble_matrix(O.K_POISSON_P1_TET_A, p.x_dofmap, p.x, none, p.dofmap, 1, p.dofmap, 1, data, pat.edges, pat.offsets,
+                      constants=np.array([2.0]))
+    assert not data.any()
+    b = np.zeros(p.ndofs)
+    O.assemble_vector(O.K_LOAD_P1_TET_L, p.x_dofmap, p.x, none, p.dofmap, 1, b, coeffs=np.zeros((0, 4)))
+    assert not b.any()
+    markers = np.zeros(p.ndofs, dtype=np.int8)
+    O.bc_mark(markers, none)
+    assert not markers.any()
+    O.set_diagonal(data, pat.edges, pat.offsets, 1, 1, none, 1.0)
+    assert not data.any()
+    # ragged split of the cell list: A(cells0) + A(cells1) == A(all)
+    cells = np.arange(len(p.dofmap), dtype=np.int32)
+    rng = np.random.default_rng(0)
+    mask = rng.random(len(cells)) < 0.37
+    parts = []
+    for sub in (cells[mask], cells[~mask], cells):
+        d = np.zeros(len(pat.edges))
+        O.assemble_matrix(O.K_POISSON_P1_TET_A, p.x_dofmap, p.x, sub, p.dofmap, 1, p.dofmap, 1, d, pat.edges, pat.offsets,
+                          constants=np.array([2.0]))
+        parts.append(d)
+    assert np.max(np.abs(parts[0] + parts[1] - parts[2])) <= 1e-13 * np.max(np.abs(parts[2]))
+    # SpMV with empty rows: y untouched there
+    row_ptr = np.array([0, 0, 2, 2, 3], dtype=np.int64)
+    cols = np.array([0, 3, 1], dtype=np.int32)
+    vals = np.array([1.0, 2.0, 3.0])
+    x = np.array([1.0, 10.0, 100.0, 1000.0])
+    y = np.full(4, 7.0)
+    O.spmv(vals, row_ptr[:-1], row_ptr[1:], cols, x, y, 1, 1)
+    assert np.array_equal(y, np.array([7.0, 7.0 + 1.0 + 2000.0, 7.0, 7.0 + 30.0]))
