@@ -12,7 +12,7 @@ The oracle cannot assemble 1e8 cells in seconds, so these tests use what the dom
 * symmetry x.(A y) = y.(A x), linearity of MatrixCSR::mult;
 * the aggregated strategy (chunked / row-gather) against the RED-per-contribution kernel;
 * re-assembly without zeroing doubles the matrix (python/test/unit/fem/test_assembler.py:145-165);
-* load vectors: sum_i b_i = int f for f = 1 and f = x0.
+* load vectors: sum_i b_i = int f for f = 1 (elasticity: f = e_0).
 """
 
 import numpy as np
@@ -23,6 +23,7 @@ from tests import problems as P
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
+
 
 def _edges(n):
     return 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) + n**3
