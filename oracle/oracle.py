@@ -745,3 +745,71 @@ def transpose(mats):
             vals[pos * nbs:(pos + 1) * nbs] = rv[k * nbs:(k + 1) * nbs].reshape(bs0, bs1).T.reshape(-1)
         out.append(OMatrix([row_maps[r], col_maps[r]], (bs1, bs0), vals, cols, row_ptr, row_ptr[:-1] + off))
     return out
+
+
+def matmul_local(A: OMatrix, B: OMatrix, new_col_map=None, ghost_row_ptr=None, ghost_cols=None, ghost_vals=None):
+    """impl::matmul (la/matmul.h:395-536), block size 1: C = A B row by row with a dense accumulator.
+
+    Restated with the reference's order of operations, because the STRUCTURE of C depends on the values: a product
+    that is exactly zero does not create an entry (:457, :477), and entries whose sum cancels to exactly zero are
+    removed (:486-497) - so the summation order (entries of row i of A in storage order, for each the entries of the
+    row of B in storage order) is part of the result.  Rows of B behind ghost columns of A come in through
+    ``ghost_row_ptr / ghost_cols / ghost_vals`` (already in the column numbering of C), as fetch_ghost_rows (:60-390)
+    delivers them; on one rank they are empty.  Returns (row_ptr int64, off_diag int32, cols int32, vals)."""
+    if tuple(A.bs) != (1, 1) or tuple(B.bs) != (1, 1):
+        raise RuntimeError("Currently matmul only supports block size=1")  # :549-552
+    mB1 = B.index_maps[1]
+    col_map_C = mB1 if new_col_map is None else new_col_map
+    n_rows_A = A.index_maps[0].size_local
+    n_rows_B = B.index_maps[0].size_local
+    n_owned_cols_B = mB1.size_local
+    n_owned_cols_C = col_map_C.size_local
+    if new_col_map is None:
+        remap = n_owned_cols_B + np.arange(mB1.num_ghosts)
+    else:
+        g2l = {int(g): n_owned_cols_C + i for i, g in enumerate(col_map_C.ghosts)}
+        remap = np.array([g2l[int(g)] for g in mB1.ghosts], dtype=np.int64)
+    num_cols_C = n_owned_cols_C + col_map_C.num_ghosts
+    acc = np.zeros(num_cols_C)
+    in_row = np.zeros(num_cols_C, dtype=bool)
+    row_ptr, off_diag, cols_C, vals_C = [0], [], [], []
+    for i in range(n_rows_A):
+        row_cols = []
+        for ka in range(int(A.row_ptr[i]), int(A.off_diag_offset[i])):  # :449-466
+            j = int(A.cols[ka])
+            a = A.data[ka]
+            for kb in range(int(B.row_ptr[j]), int(B.row_ptr[j + 1])):
+                c = int(B.cols[kb])
+                k = c if c < n_owned_cols_B else int(remap[c - n_owned_cols_B])
+                v = a * B.data[kb]
+                if not in_row[k] and v != 0.0:
+                    in_row[k] = True
+                    row_cols.append(k)
+                acc[k] += v
+        for ka in range(int(A.off_diag_offset[i]), int(A.row_ptr[i + 1])):  # :469-484
+            g = int(A.cols[ka]) - n_rows_B
+            a = A.data[ka]
+            for kb in range(int(ghost_row_ptr[g]), int(ghost_row_ptr[g + 1])):
+                k = int(ghost_cols[kb])
+                v = a * ghost_vals[kb]
+                if not in_row[k] and v != 0.0:
+                    in_row[k] = True
+                    row_cols.append(k)
+                acc[k] += v
+        kept = []
+        for k in row_cols:  # :486-497
+            if acc[k] == 0.0:
+                in_row[k] = False
+            else:
+                kept.append(k)
+        kept.sort()  # :501
+        off_diag.append(int(np.searchsorted(kept, n_owned_cols_C)))  # :505-507
+        for c in kept:  # :510-516
+            cols_C.append(c)
+            vals_C.append(acc[c])
+            acc[c] = 0.0
+            in_row[c] = False
+        # (columns touched only by products that were exactly zero keep acc == 0 and in_row == False)
+        row_ptr.append(len(cols_C))
+    return (np.array(row_ptr, dtype=np.int64), np.array(off_diag, dtype=np.int32), np.array(cols_C, dtype=np.int32),
+            np.array(vals_C, dtype=np.float64))

@@ -414,3 +414,51 @@ def test_empty_and_ragged_inputs(oracle):
     y = np.full(4, 7.0)
     O.spmv(vals, row_ptr[:-1], row_ptr[1:], cols, x, y, 1, 1)
     assert np.array_equal(y, np.array([7.0, 7.0 + 1.0 + 2000.0, 7.0, 7.0 + 30.0]))
+
+
+def _serial_omatrix(O, S):
+    """A scipy CSR matrix (sorted columns, explicit zeros kept) as a one-rank OMatrix."""
+    S = S.tocsr()
+    S.sort_indices()
+    m0 = O.make_index_maps([S.shape[0]], [[]], [[]])[0]
+    m1 = O.make_index_maps([S.shape[1]], [[]], [[]])[0]
+    return O.OMatrix([m0, m1], (1, 1), S.data.astype(np.float64), S.indices.astype(np.int32), S.indptr.astype(np.int64),
+                     S.indptr[1:].astype(np.int64))
+
+
+@pytest.mark.parametrize("shape", [(7, 7, 7), (9, 5, 11), (1, 6, 3)])
+def test_matmul_local_vs_scipy(oracle, shape):
+    """impl::matmul restated (oracle.matmul_local, la/matmul.h:395-536) against scipy, the check of
+    python/test/unit/la/test_matmul.py:21-118: values, sorted columns, and no stored zeros - neither from zero
+    factors nor from exact cancellation."""
+    import scipy.sparse as sps
+
+    rng = np.random.default_rng(12345)
+    n, k, m = shape
+    A = sps.random(n, k, density=0.5, random_state=1, format="csr", dtype=np.float64)
+    B = sps.random(k, m, density=0.5, random_state=2, format="csr", dtype=np.float64)
+    if k >= 2 and n >= 1 and A.nnz and B.nnz:
+        # exact cancellation: A[0, 0] B[0, 0] + A[0, 1] B[1, 0] = 0; and an explicit zero in B
+        A = A.tolil()
+        B = B.tolil()
+        A[0, 0], A[0, 1] = 2.0, -4.0
+        B[0, 0], B[1, 0] = 1.0, 0.5
+        for j in range(2, k):
+            B[j, 0] = 0.0
+        A, B = A.tocsr(), B.tocsr()
+        # the last stored entry of B becomes an explicit zero
+        B = sps.csr_matrix((np.where(np.arange(B.nnz) == B.nnz - 1, 0.0, B.data), B.indices, B.indptr), shape=B.shape)
+    rp, od, cols, vals = oracle.matmul_local(_serial_omatrix(oracle, A), _serial_omatrix(oracle, B))
+    C = sps.csr_matrix((vals, cols, rp), shape=(n, m))
+    ref = (A @ B).toarray()
+    assert np.allclose(C.toarray(), ref, rtol=1e-14, atol=1e-15)
+    assert np.all(vals != 0.0)
+    for i in range(n):
+        assert np.all(np.diff(cols[rp[i]:rp[i + 1]]) > 0)
+    assert np.array_equal(od, np.diff(rp))  # every column is owned on one rank
+    if k >= 2 and A.nnz and B.nnz:
+        assert ref[0, 0] == 0.0 and 0 not in cols[rp[0]:rp[1]]
+    with pytest.raises(RuntimeError):
+        bad = _serial_omatrix(oracle, A)
+        bad.bs = (2, 2)
+        oracle.matmul_local(bad, _serial_omatrix(oracle, B))
