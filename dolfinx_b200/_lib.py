@@ -56,6 +56,7 @@ ERR_UNSUPPORTED = 4
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
 CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
 CHUNKS_SHARED_MATRIX = 4
+CHUNKS_PAD4 = 32  # source lists padded to multiples of 4 entries
 CHUNKS_TWO_STAGE_SPLIT = 16
 CHUNKS_TWO_STAGE = 8  # write-back in address order through shared memory (symmetric P1 plans)
 

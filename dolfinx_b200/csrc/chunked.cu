@@ -86,6 +86,7 @@ struct ChunkBuildArgs
   int* err;
   // two-stage write-back (BFX_CHUNKS_TWO_STAGE): every (address, destination rank) pair of the chunk - both entries
   // of a symmetric pair - sorted by address, so that the lanes of the write-back pass hit consecutive CSR values
+  int pad4;            // BFX_CHUNKS_PAD4: list lengths (per group of 32 destinations) padded to multiples of 4
   int two, dcap;       // dcap: destinations of a chunk the kernel holds in shared memory
   uint32_t* wr_addr;   // 2 * n_dest_pad entries, chunk q at 2 * dest_base
   uint16_t* wr_src;    // destination rank | 0x8000 if the destination is incomplete (RED)
@@ -296,6 +297,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
   __syncthreads();
   const int n_dw = (n_dest + 31) >> 5;
   int my_m = tid < n_dw ? (int)mw[tid] : 0, my_off, n_src32;
+  if (p.pad4 && tid < n_dw && my_m <= 252)
+  {
+    my_m = (my_m + 3) & ~3; // the padding entries point at the zero slot; 252: the length travels in 8 bits
+    mw[tid] = (uint32_t)my_m; // (read by the list writer after the next barrier)
+  }
   if (n_dw > PLAN_THREADS) // cannot happen: NK / 32 <= 1024 for ITEMS <= 32
     *p.err = 4;
   Scan(temp.sc).ExclusiveSum(my_m, my_off, n_src32);
@@ -865,11 +871,73 @@ struct ChunkSmem
   static constexpr size_t TOTAL = SUM_OFF + (TWO ? (size_t)DCAP * 8 : 0);
 };
 
+// Phase 2 of the DIET kernel variant: the same walk as the classic kernel (same summation order, same updates), as a
+// function that the kernel inlines TWICE - once on the shared-memory copies of the chunk's lists, once on the global
+// arrays - so that each copy addresses ONE state space (LDS / 32-bit addresses in the first) instead of generic loads
+// with 64-bit arithmetic, and with the 4-step loop kept rolled: the classic code is unrolled to 16 steps with a cascade
+// of 8 / 4 / 3 / 2 / 1-step remainders, 132 instructions per destination for lists of ~6 entries.
+template <bool SYM, int THREADS, typename AddrT>
+__device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, const AddrT* __restrict__ destp,
+                                           const uint32_t* __restrict__ winfop, const double* __restrict__ Es,
+                                           double* __restrict__ values, int n_dest, int n_complete, int n_dw, int overwrite)
+{
+  constexpr int DS = SYM ? 2 : 1;
+  const int lane = threadIdx.x & 31;
+  for (int dw = threadIdx.x >> 5; dw < n_dw; dw += THREADS / 32)
+  {
+    const uint32_t info = winfop[dw];
+    const int m = (int)(info & 0xffu);
+    const uint16_t* p = srcp + ((info >> 8) << 5) + lane;
+    const int t = (dw << 5) + lane;
+    double* dst = values + (int64_t)destp[t * DS];
+    double* dst2 = SYM ? values + (int64_t)destp[t * DS + (DS - 1)] : dst;
+    const bool plain = t < n_complete;
+    double old = 0.0, old2 = 0.0;
+    if (plain && !overwrite)
+    {
+      old = *dst;
+      if (SYM)
+        old2 = *dst2;
+    }
+    double s0 = 0.0, s1 = 0.0;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 4 <= m; j += 4)
+    {
+      const uint32_t i0 = p[(j + 0) << 5], i1 = p[(j + 1) << 5], i2 = p[(j + 2) << 5], i3 = p[(j + 3) << 5];
+      s0 += Es[i0];
+      s1 += Es[i1];
+      s0 += Es[i2];
+      s1 += Es[i3];
+    }
+#pragma unroll 1
+    for (; j < m; ++j) // (empty when the plan pads the lists to multiples of 4: BFX_CHUNKS_PAD4)
+      s0 += Es[p[j << 5]];
+    const double sum = s0 + s1;
+    if (t < n_dest)
+    {
+      if (plain)
+      {
+        *dst = old + sum;
+        if (SYM && dst2 != dst)
+          *dst2 = old2 + sum;
+      }
+      else
+      {
+        red_add(dst, sum);
+        if (SYM && dst2 != dst)
+          red_add(dst2, sum);
+      }
+    }
+  }
+}
+
 // TWO (two-stage write-back, symmetric plans with 32-bit addresses): phase 2 leaves the sum of every destination in
 // shared memory; a third phase walks the chunk's (address, destination) list in ADDRESS order, so that consecutive
 // lanes update consecutive CSR values - both entries of a symmetric pair included - instead of two scattered ones each
 // OCC: resident CTAs per SM asked of the register allocator (0 = chunk_min_ctas(THREADS))
-template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0>
+// DIET: phase 2 through chunk_walk (round-2 experiment, selected by BFX_CHUNK_DIET=1; not the default)
+template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0, bool DIET = false>
 __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
@@ -1062,6 +1130,15 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   if (fits && n_dw > 0)
     mbar_wait(bar, 0);
 
+  if constexpr (DIET)
+  {
+    static_assert(!TWO, "the diet variant keeps the classic write-back");
+    if (fits)
+      chunk_walk<SYM, THREADS, AddrT>(s_src, s_dest, s_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
+    else
+      chunk_walk<SYM, THREADS, AddrT>(g_src, g_dest, g_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
+    return;
+  }
   // ---- phase 2: one thread per distinct destination
   const int lane = threadIdx.x & 31;
   const uint16_t* srcp = fits ? s_src : g_src;
@@ -1221,6 +1298,19 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
+  if constexpr (SYM && CB == chunk_cb(NS))
+  {
+    // round-2 experiment knob (read once): BFX_CHUNK_DIET=1 runs the variant whose phase 2 is chunk_walk
+    static const int diet = getenv("BFX_CHUNK_DIET") ? atoi(getenv("BFX_CHUNK_DIET")) : 0;
+    if (diet && c->addr_bytes == 4)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
       BFX_CHECK_LAUNCH();
       return BFX_OK;
     }
@@ -1726,6 +1816,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   p.o_nsrc32 = nsrc;
   p.err = csr->err_flag;
   p.two = two;
+  p.pad4 = (flags & BFX_CHUNKS_PAD4) ? 1 : 0;
   p.dcap = two_stage_dcap(n2, cb);
   if ((e = run_plan_pass_items(items, false, p, c->nchunks, st)))
     return bail(e);

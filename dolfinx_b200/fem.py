@@ -411,6 +411,7 @@ CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 # cells per chunk: 0 = the element's default (256 P1 / 128 P2); 96, 128, 192, 384 (P1) or 64, 96 (symmetric P2)
 CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
 # write-back of the chunk sums in address order (symmetric P1 plans; see BFX_CHUNKS_TWO_STAGE in include/bfx.h)
+CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padded to multiples of 4 (round-2 experiment)
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
 
@@ -434,6 +435,8 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
             V0, V1 = form.function_spaces
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
             flags |= _lib.CHUNKS_CB(CHUNKS_CB)
+            if CHUNKS_PAD4:
+                flags |= _lib.CHUNKS_PAD4
             if CHUNKS_TWO_STAGE:
                 flags |= _lib.CHUNKS_TWO_STAGE | (_lib.CHUNKS_TWO_STAGE_SPLIT if int(CHUNKS_TWO_STAGE) == 2 else 0)
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)

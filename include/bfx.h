@@ -224,6 +224,7 @@ extern "C"
     BFX_CHUNKS_TWO_STAGE = 8, /* symmetric P1-sized plans: the kernel leaves the per-destination sums in shared memory
                                  and writes the CSR values back in ADDRESS order (both entries of a symmetric pair),
                                  so that consecutive lanes update consecutive values; ignored where not applicable */
+    BFX_CHUNKS_PAD4 = 32, /* pad the source lists to multiples of 4 entries (no remainder steps in the list walk) */
     BFX_CHUNKS_TWO_STAGE_SPLIT = 16, /* with BFX_CHUNKS_TWO_STAGE: plain stores first, REDs after, each in address order */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
                                      zero-fill and this plan's launch (boundary/interior split): an entry counts as
