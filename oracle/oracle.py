@@ -813,3 +813,61 @@ def matmul_local(A: OMatrix, B: OMatrix, new_col_map=None, ghost_row_ptr=None, g
         row_ptr.append(len(cols_C))
     return (np.array(row_ptr, dtype=np.int64), np.array(off_diag, dtype=np.int32), np.array(cols_C, dtype=np.int32),
             np.array(vals_C, dtype=np.float64))
+
+
+def matmul(matsA, matsB):
+    """la::matmul on every (simulated) rank - la/matmul.h:538-579: C = A B for block size 1.
+
+    fetch_ghost_rows (:79-390): every ghost column of A is a row of B on its owner; the owner sends that row (global
+    columns, owner of every column, values, in its storage order); the column map of C is B's column map extended by
+    the SORTED UNIQUE (global column, owner) pairs of the received entries and of B's own ghosts (:330-356) - unless
+    the column map of A has no neighbours on this rank, then B's column map is kept as it is (:104-113).  The rows
+    of C are then computed by impl::matmul (matmul_local).  The row map of C has no ghosts (:569-570)."""
+    size = len(matsA)
+    fetched, new_ghosts, new_owners = [], [], []
+    for r in range(size):
+        A, B = matsA[r], matsB[r]
+        mA1, mB1 = A.index_maps[1], B.index_maps[1]
+        if size == 1 or (len(mA1.src) == 0 and len(mA1.dest) == 0):
+            fetched.append(None)
+            new_ghosts.append(list(mB1.ghosts))
+            new_owners.append(list(mB1.owners))
+            continue
+        rows = []
+        for g, o in zip(mA1.ghosts, mA1.owners):
+            Bo = matsB[int(o)]
+            mo0, mo1 = Bo.index_maps
+            lr = int(g) - mo0.local_range[0]
+            assert 0 <= lr < mo0.size_local
+            k0, k1 = int(Bo.row_ptr[lr]), int(Bo.row_ptr[lr + 1])
+            lc = Bo.cols[k0:k1]
+            gcols = mo1.local_to_global(lc)
+            cown = np.where(lc < mo1.size_local, int(o), mo1.owners[np.maximum(lc - mo1.size_local, 0)] if mo1.num_ghosts
+                            else int(o))
+            rows.append((gcols, cown.astype(np.int64), Bo.data[k0:k1].copy()))
+        lo, hi = mB1.local_range
+        pairs = {(int(c), int(w)) for gc, ow, _ in rows for c, w in zip(gc, ow) if not (lo <= c < hi)}
+        pairs |= {(int(g), int(o)) for g, o in zip(mB1.ghosts, mB1.owners)}
+        pairs = sorted(pairs)
+        fetched.append(rows)
+        new_ghosts.append([g for g, _ in pairs])
+        new_owners.append([o for _, o in pairs])
+    col_maps = make_index_maps([B.index_maps[1].size_local for B in matsB], new_ghosts, new_owners)
+    row_maps = make_index_maps([A.index_maps[0].size_local for A in matsA], [[] for _ in matsA], [[] for _ in matsA])
+    out = []
+    for r in range(size):
+        A, B = matsA[r], matsB[r]
+        cm = col_maps[r]
+        if fetched[r] is None:
+            rp, od, cols, vals = matmul_local(A, B)
+        else:
+            g2l = {int(g): cm.size_local + i for i, g in enumerate(cm.ghosts)}
+            lo = cm.local_range[0]
+            grp, gcols, gvals = [0], [], []
+            for gc, _, v in fetched[r]:
+                gcols += [int(c) - lo if lo <= c < cm.local_range[1] else g2l[int(c)] for c in gc]
+                gvals += list(v)
+                grp.append(len(gcols))
+            rp, od, cols, vals = matmul_local(A, B, cm, np.array(grp), np.array(gcols, dtype=np.int64), np.array(gvals))
+        out.append(OMatrix([row_maps[r], cm], (1, 1), vals, cols, rp, rp[:-1] + od.astype(np.int64)))
+    return out

@@ -315,10 +315,10 @@ def test_golden_interior_facets_dS(oracle):
     assert np.sum(data) == pytest.approx(length, rel=1e-13)
 
 
-def _random_distributed_matrices(O, size, bs, rng):
+def _random_distributed_matrices(O, size, bs, rng, nr=None, nc=None):
     """A rectangular matrix on `size` simulated ranks with random rows, ghost columns and values."""
-    nr = [5 + r for r in range(size)]
-    nc = [4 + 2 * r for r in range(size)]
+    nr = [5 + r for r in range(size)] if nr is None else nr
+    nc = [4 + 2 * r for r in range(size)] if nc is None else nc
     coff = np.concatenate([[0], np.cumsum(nc)])
     ghosts, owners = [], []
     for r in range(size):
@@ -462,3 +462,26 @@ def test_matmul_local_vs_scipy(oracle, shape):
         bad = _serial_omatrix(oracle, A)
         bad.bs = (2, 2)
         oracle.matmul_local(bad, _serial_omatrix(oracle, B))
+
+
+@pytest.mark.parametrize("size", [1, 2, 3, 4])
+def test_matmul_distributed_vs_scipy(oracle, size):
+    """la::matmul restated on simulated ranks (oracle.matmul: fetch_ghost_rows + impl::matmul, la/matmul.h) against the
+    product of the gathered scipy matrices - the check of python/test/unit/la/test_matmul.py:21-80 (square and
+    rectangular): values, sorted columns, diagonal block first, no ghost rows."""
+    rng = np.random.default_rng(12345)
+    A = _random_distributed_matrices(oracle, size, (1, 1), rng)
+    ncA = [m.index_maps[1].size_local for m in A]
+    B = _random_distributed_matrices(oracle, size, (1, 1), rng, nr=ncA, nc=[3 + r for r in range(size)])
+    C = oracle.matmul(A, B)
+    G = (_gather(A).tocsr() @ _gather(B).tocsr()).toarray()
+    GC = _gather(C).toarray()
+    assert GC.shape == G.shape and np.allclose(GC, G, rtol=1e-13, atol=1e-14)
+    for a, c in zip(A, C):
+        assert c.index_maps[0].num_ghosts == 0 and c.index_maps[0].size_local == a.index_maps[0].size_local
+        nl = c.index_maps[1].size_local
+        for i in range(c.index_maps[0].size_local):
+            row = c.cols[c.row_ptr[i]:c.row_ptr[i + 1]]
+            assert np.all(np.diff(row) > 0)
+            assert np.all(row[: c.off_diag_offset[i] - c.row_ptr[i]] < nl) and np.all(row[c.off_diag_offset[i] - c.row_ptr[i]:] >= nl)
+        assert np.all(c.data != 0.0)
