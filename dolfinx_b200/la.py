@@ -543,6 +543,80 @@ def matrix_ghost_plan(index_maps, bs, indptr, indices):
 
 
 
+def matrix_matmul_plan(m1A: IndexMap, m0B: IndexMap, m1B: IndexMap, indptrB, indicesB, gather_values_B):
+    """Host side of la::matmul: impl::fetch_ghost_rows (la/matmul.h:79-390), numpy + the neighbourhood exchanges.
+
+    Every ghost column of A (map ``m1A``) is a row of B on its owner.  The owners send those rows (global columns, the
+    owner of every column, values - ``gather_values_B(ks)`` returns the values of the entries ``ks`` of B); the column
+    map of C is B's column map extended by the sorted unique (global column, owner) pairs received (:330-356), or B's
+    column map itself when the column map of A has no neighbours on this rank (:104-113).
+    Returns dict(col_map, ghost_row_ptr int64, ghost_cols int32 (local in col_map), ghost_vals, b_ghost_remap int32
+    (B's ghost columns in col_map, la/matmul.h:419-422)); the rows are in the order of A's ghost columns."""
+    comm = m1A.comm
+    if comm.size == 1 or (len(m1A.src) == 0 and len(m1A.dest) == 0):
+        cm = IndexMap(comm, m1B.size_local, m1B.ghosts, m1B.owners)
+        return {"col_map": cm, "ghost_row_ptr": np.zeros(1, dtype=np.int64), "ghost_cols": np.zeros(0, dtype=np.int32),
+                "ghost_vals": np.zeros(0), "b_ghost_remap": (m1B.size_local + np.arange(m1B.num_ghosts)).astype(np.int32)}
+    indptrB = np.asarray(indptrB, dtype=np.int64)
+    # the rows we need, grouped by owner in ghost order; perm[i] = position of ghost i in that order (:150-160)
+    nbr = np.searchsorted(m1A.src, m1A.owners)
+    order = np.argsort(nbr, kind="stable")
+    perm = np.empty(len(order), dtype=np.int64)
+    perm[order] = np.arange(len(order))
+    cnt = np.bincount(nbr, minlength=len(m1A.src))
+    disp = np.concatenate([[0], np.cumsum(cnt)])
+    required = m1A.ghosts[order]
+    asked = comm.neighbor_alltoallv(m1A.src, m1A.dest, [required[disp[i]:disp[i + 1]] for i in range(len(m1A.src))])
+    # the rows asked of this rank: entries, global columns, owners of the columns, row sizes (:180-262)
+    send_cols, send_own, send_vals, send_sizes = [], [], [], []
+    for rows_g in asked:
+        lr = (np.asarray(rows_g, dtype=np.int64) - m0B.local_range[0]).astype(np.int64)
+        assert np.all((lr >= 0) & (lr < m0B.size_local)), "matmul: asked for a row this rank does not own"
+        lens = indptrB[lr + 1] - indptrB[lr]
+        first = np.concatenate([[0], np.cumsum(lens)[:-1]]) if lens.size else np.zeros(0, dtype=np.int64)
+        ks = np.arange(int(lens.sum()), dtype=np.int64) + np.repeat(indptrB[lr] - first, lens)
+        lc = np.asarray(indicesB)[ks].astype(np.int64)
+        send_cols.append(m1B.local_to_global(lc) if lc.size else np.zeros(0, dtype=np.int64))
+        own = np.full(lc.size, comm.rank, dtype=np.int64)
+        gh = lc >= m1B.size_local
+        if np.any(gh):
+            own[gh] = m1B.owners[lc[gh] - m1B.size_local]
+        send_own.append(own)
+        send_vals.append(np.asarray(gather_values_B(ks), dtype=np.float64) if ks.size else np.zeros(0))
+        send_sizes.append(lens.astype(np.int64))
+    rc = comm.neighbor_alltoallv(m1A.dest, m1A.src, send_cols)
+    ro = comm.neighbor_alltoallv(m1A.dest, m1A.src, send_own)
+    rv = comm.neighbor_alltoallv(m1A.dest, m1A.src, send_vals, dtype=np.float64)
+    rs = comm.neighbor_alltoallv(m1A.dest, m1A.src, send_sizes)
+    rc = np.concatenate(rc) if len(rc) else np.zeros(0, dtype=np.int64)
+    ro = np.concatenate(ro) if len(ro) else np.zeros(0, dtype=np.int64)
+    rv = np.concatenate(rv) if len(rv) else np.zeros(0)
+    rs = np.concatenate(rs) if len(rs) else np.zeros(0, dtype=np.int64)
+    # column map of C (:318-356)
+    lo, hi = m1B.local_range
+    far = (rc < lo) | (rc >= hi)
+    pairs = np.stack([np.concatenate([rc[far], m1B.ghosts]), np.concatenate([ro[far], m1B.owners.astype(np.int64)])], axis=1)
+    pairs = np.unique(pairs, axis=0) if len(pairs) else np.zeros((0, 2), dtype=np.int64)
+    cm = IndexMap(comm, m1B.size_local, pairs[:, 0], pairs[:, 1].astype(np.int32))
+
+    def to_local(g):
+        g = np.asarray(g, dtype=np.int64)
+        out = g - lo
+        f = (g < lo) | (g >= hi)
+        if np.any(f):
+            out[f] = m1B.size_local + np.searchsorted(pairs[:, 0], g[f])
+        return out.astype(np.int32)
+
+    cols_l = to_local(rc)
+    # back to the order of A's ghost columns (:364-388)
+    rp_recv = np.concatenate([[0], np.cumsum(rs)]).astype(np.int64)
+    sizes = rs[perm]
+    rp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    src_pos = np.arange(int(sizes.sum()), dtype=np.int64) + np.repeat(rp_recv[perm] - rp[:-1], sizes)
+    return {"col_map": cm, "ghost_row_ptr": rp, "ghost_cols": cols_l[src_pos], "ghost_vals": rv[src_pos],
+            "b_ghost_remap": to_local(m1B.ghosts)}
+
+
 def matrix_transpose_plan(m0: IndexMap, m1: IndexMap, bs, indptr, indices, off_diag_offset, rp0, c0, gather_values):
     """Host side of the distributed la::transpose (la/mattrans.h:200-434), numpy + the neighbourhood exchange.
 

@@ -815,7 +815,7 @@ def matmul_local(A: OMatrix, B: OMatrix, new_col_map=None, ghost_row_ptr=None, g
             np.array(vals_C, dtype=np.float64))
 
 
-def matmul(matsA, matsB):
+def matmul(matsA, matsB, return_ghost_rows=False):
     """la::matmul on every (simulated) rank - la/matmul.h:538-579: C = A B for block size 1.
 
     fetch_ghost_rows (:79-390): every ghost column of A is a row of B on its owner; the owner sends that row (global
@@ -854,12 +854,13 @@ def matmul(matsA, matsB):
         new_owners.append([o for _, o in pairs])
     col_maps = make_index_maps([B.index_maps[1].size_local for B in matsB], new_ghosts, new_owners)
     row_maps = make_index_maps([A.index_maps[0].size_local for A in matsA], [[] for _ in matsA], [[] for _ in matsA])
-    out = []
+    out, ghost_rows = [], []
     for r in range(size):
         A, B = matsA[r], matsB[r]
         cm = col_maps[r]
         if fetched[r] is None:
             rp, od, cols, vals = matmul_local(A, B)
+            ghost_rows.append((np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)))
         else:
             g2l = {int(g): cm.size_local + i for i, g in enumerate(cm.ghosts)}
             lo = cm.local_range[0]
@@ -869,5 +870,6 @@ def matmul(matsA, matsB):
                 gvals += list(v)
                 grp.append(len(gcols))
             rp, od, cols, vals = matmul_local(A, B, cm, np.array(grp), np.array(gcols, dtype=np.int64), np.array(gvals))
+            ghost_rows.append((np.array(grp, dtype=np.int64), np.array(gcols, dtype=np.int64), np.array(gvals)))
         out.append(OMatrix([row_maps[r], cm], (1, 1), vals, cols, rp, rp[:-1] + od.astype(np.int64)))
-    return out
+    return (out, ghost_rows) if return_ghost_rows else out

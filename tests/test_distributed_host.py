@@ -193,6 +193,29 @@ def _worker(rank, world, port, nglob, tmpdir):
             if len(tp["recv_dst"]):
                 vals[tp["recv_dst"]] = tp["recv_blocks"]
             assert np.array_equal(vals.reshape(-1), oT.data)
+        # la::matmul (la/matmul.h): fetch_ghost_rows on the host (rows of B behind the ghost columns of A, the
+        # column map of C) against the oracle's simulated ranks, then impl::matmul on the fetched rows: C = A A
+        mmats = []
+        for r_, A_ in enumerate(omats):
+            d_ = np.random.default_rng(200 + r_).random(len(A_.cols))
+            # square product: rows of B = owned columns of A -> drop the ghost rows of the assembled structure
+            nl = A_.index_maps[0].size_local
+            n = int(A_.row_ptr[nl])
+            rowmap = O.make_index_maps([m.index_maps[0].size_local for m in omats], [[] for _ in omats], [[] for _ in omats])[r_]
+            mmats.append(O.OMatrix([rowmap, A_.index_maps[1]], (1, 1), d_[:n], A_.cols[:n], A_.row_ptr[: nl + 1],
+                                   A_.off_diag_offset[:nl]))
+        oC, oghost = O.matmul(mmats, mmats, return_ghost_rows=True)
+        mine = mmats[rank]
+        rmap = common.IndexMap(comm, mine.index_maps[0].size_local)
+        mp = la.matrix_matmul_plan(pat.index_map(1), rmap, pat.index_map(1), mine.row_ptr, mine.cols,
+                                   lambda ks: mine.data[ks])
+        ocm = oC[rank].index_maps[1]
+        assert np.array_equal(mp["col_map"].ghosts, ocm.ghosts) and np.array_equal(mp["col_map"].owners, ocm.owners)
+        assert np.array_equal(mp["ghost_row_ptr"], oghost[rank][0]) and np.array_equal(mp["ghost_cols"], oghost[rank][1])
+        assert np.array_equal(mp["ghost_vals"], oghost[rank][2])
+        rp_, od_, cols_, vals_ = O.matmul_local(mine, mine, ocm, mp["ghost_row_ptr"], mp["ghost_cols"], mp["ghost_vals"])
+        assert np.array_equal(rp_, oC[rank].row_ptr) and np.array_equal(cols_, oC[rank].cols)
+        assert np.array_equal(vals_, oC[rank].data)
         # collectives used by la::norm / inner_product
         assert comm.allreduce_sum(float(rank + 1)) == sum(range(1, world + 1))
         assert comm.allreduce_max(float(rank)) == world - 1
