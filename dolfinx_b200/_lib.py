@@ -124,6 +124,8 @@ _SIGS = {
     "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
     "bfx_asm_chunk_two_stage": ([vp, C.POINTER(ci)], ci),
     "bfx_csr_transpose_local": ([vp, vp, i32, vp, vp, vp, i64, C.POINTER(i64), vp], ci),
+    "bfx_csr_matmul_begin": ([vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(i64), vp], ci),
+    "bfx_csr_matmul_end": ([vp, vp, vp, vp, vp, vp], ci),
     "bfx_asm_chunk_stats": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], ci),
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),

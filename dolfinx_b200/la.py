@@ -919,6 +919,50 @@ class MatrixCSR:
             y.scatter_reverse(InsertMode.add)
             _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
 
+    def matmul(self, B: "MatrixCSR") -> "MatrixCSR":
+        """la::matmul (la/matmul.h:538-579; python/dolfinx/la/__init__.py:186-205): C = A B, block size 1.
+
+        impl::fetch_ghost_rows is host-side integer work (``matrix_matmul_plan``: the rows of B behind the ghost columns
+        of A, the column map of C); impl::matmul runs on the device, one thread per row, bitwise the reference's rows
+        (``bfx_csr_matmul_begin/_end``, csrc/matmul_row.h)."""
+        from . import _lib
+
+        torch = _torch()
+        if (self.index_map(1).size_local != B.index_map(0).size_local
+                or self.index_map(1).size_global != B.index_map(0).size_global):
+            raise RuntimeError("Invalid matrix sizes for matmul.")
+        if tuple(self._bs) != (1, 1) or tuple(B._bs) != (1, 1):
+            raise RuntimeError("Block size not supported in matmul.")
+        dev = self.data.device
+        comm = self._index_maps[0].comm
+        plan = matrix_matmul_plan(self.index_map(1), B.index_map(0), B.index_map(1), B.indptr, B.indices,
+                                  lambda ks: B.data[torch.from_numpy(ks).to(dev)].cpu().numpy())
+        cm = plan["col_map"]
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
+        remap = up(np.append(plan["b_ghost_remap"], 0), torch.int32)  # (one spare entry: never an empty allocation)
+        grp = up(plan["ghost_row_ptr"], torch.int64)
+        gcols = up(np.append(plan["ghost_cols"], 0), torch.int32)
+        gvals = up(np.append(plan["ghost_vals"], 0.0), torch.float64)
+        h = C.c_void_p()
+        nnz = C.c_int64(0)
+        st = _lib.current_stream()
+        _lib.check(_lib.lib.bfx_csr_matmul_begin(self._csr, self.data.data_ptr(), B._csr, B.data.data_ptr(),
+                                                 B.index_map(1).size_local, remap.data_ptr(), grp.data_ptr(), gcols.data_ptr(),
+                                                 gvals.data_ptr(), cm.size_local, C.byref(h), C.byref(nnz), st))
+        n_rows = self._index_maps[0].size_local
+        rp = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        od = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+        cols = torch.empty(max(int(nnz.value), 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(int(nnz.value), 1), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib.bfx_csr_matmul_end(h, rp.data_ptr(), od.data_ptr(), cols.data_ptr(), vals.data_ptr(), st))
+        n = int(nnz.value)
+        sp = SparsityPattern.from_graph(comm, [IndexMap(comm, n_rows), cm], (1, 1), cols[:n].cpu().numpy(), rp.cpu().numpy(),
+                                        od[:n_rows].cpu().numpy())
+        Cm = MatrixCSR(sp)
+        Cm._data.copy_(vals[:n])
+        Cm._is_zero = False
+        return Cm
+
     def transpose(self) -> "MatrixCSR":
         """la::transpose (la/mattrans.h:121-437; python/dolfinx/la/__init__.py:207-209).
 

@@ -158,6 +158,23 @@ extern "C"
    * query the size only.  Synchronises the stream. */
   int bfx_csr_transpose_local(const bfx_csr_t* A, const double* values, int32_t n_cols_owned, int64_t* row_ptrT,
                               int32_t* colsT, double* valsT, int64_t capacity, int64_t* nnzT_host, bfx_stream_t stream);
+  /* la::matmul, local part - impl::matmul, la/matmul.h:395-536 (block size 1; BFX_ERR_UNSUPPORTED otherwise, the
+   * reference throws "Currently matmul only supports block size=1"): C = A B over the owned rows of A.  Columns of B
+   * below n_owned_cols_b keep their index in C, its ghost columns are renumbered through b_ghost_remap (device, one
+   * entry per ghost column of B); the rows of B behind ghost columns of A come as a CSR of fetched rows (device;
+   * ghost_row_ptr has one entry more than A has ghost columns, columns already in the numbering of C) - the output of
+   * impl::fetch_ghost_rows (:79-390), which stays host-side (dolfinx_b200.la.matrix_matmul_plan).  The rows are
+   * bitwise the reference's: same order of additions, no entry for zero products or exact cancellations, sorted
+   * columns.  begin() computes C into a workspace and returns its number of entries; end() copies row pointer
+   * (n_rows_owned(A) + 1), per-row count of owned columns, columns and values into the caller's device arrays (NULL to
+   * skip) and destroys the handle. */
+  typedef struct bfx_matmul bfx_matmul_t;
+  int bfx_csr_matmul_begin(const bfx_csr_t* A, const double* a_values, const bfx_csr_t* B, const double* b_values,
+                           int32_t n_owned_cols_b, const int32_t* b_ghost_remap, const int64_t* ghost_row_ptr,
+                           const int32_t* ghost_cols, const double* ghost_vals, int32_t n_owned_cols_c,
+                           bfx_matmul_t** out, int64_t* nnz_host, bfx_stream_t stream);
+  int bfx_csr_matmul_end(bfx_matmul_t* handle, int64_t* row_ptr, int32_t* off_diag, int32_t* cols, double* vals,
+                         bfx_stream_t stream);
   /* bs = 1 SpMV kernel of this matrix: 0 = entry-consecutive stream, 1 = row per thread out of staged (cols, values),
    * 2 = row per thread fed by a two-stage TMA pipeline (persistent CTAs); -1 (default) = time the three on the first
    * bfx_spmv call and keep the fastest (which one wins depends on the numbering of the matrix). */
