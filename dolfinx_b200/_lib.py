@@ -56,6 +56,7 @@ ERR_UNSUPPORTED = 4
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
 CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
 CHUNKS_SHARED_MATRIX = 4
+CHUNK_KERNEL_DEFAULT, CHUNK_KERNEL_OCC5, CHUNK_KERNEL_DIET = 0, 1, 2
 CHUNKS_PAD4 = 32  # source lists padded to multiples of 4 entries
 CHUNKS_TWO_STAGE_SPLIT = 16
 CHUNKS_TWO_STAGE = 8  # write-back in address order through shared memory (symmetric P1 plans)
@@ -123,6 +124,7 @@ _SIGS = {
     "bfx_asm_build_groups": ([vp, vp, vp], ci),
     "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
     "bfx_asm_chunk_two_stage": ([vp, C.POINTER(ci)], ci),
+    "bfx_asm_chunk_set_kernel": ([vp, ci], ci),
     "bfx_csr_transpose_local": ([vp, vp, i32, vp, vp, vp, i64, C.POINTER(i64), vp], ci),
     "bfx_csr_matmul_begin": ([vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(i64), vp], ci),
     "bfx_csr_matmul_end": ([vp, vp, vp, vp, vp, vp], ci),

@@ -59,6 +59,7 @@ struct bfx_chunks
 {
   int cb = 0, n2 = 0; // cells per chunk, staged scalars per cell
   bool sym = false;   // symmetric form: destinations are (row i col j, row j col i) pairs
+  int kernel_variant = 0; // BFX_CHUNK_KERNEL_*: which instantiation of the assembly kernel runs (bfx_asm_chunk_set_kernel)
   int64_t nchunks = 0, n_dest_pad = 0, n_src32 = 0;
   ChunkHdr* hdr = nullptr;
   uint32_t* winfo = nullptr;  // per group of 32 destinations: (offset of its source lists / 32) << 8 | list length

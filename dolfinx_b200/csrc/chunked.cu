@@ -23,7 +23,6 @@
 // The same file holds the grouped vector kernel (bfx_asm_build_groups) that reuses the warp tables.
 #include "asm_device.cuh"
 #include "elements.cuh"
-#include <cstdlib>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -936,7 +935,7 @@ __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, co
 // shared memory; a third phase walks the chunk's (address, destination) list in ADDRESS order, so that consecutive
 // lanes update consecutive CSR values - both entries of a symmetric pair included - instead of two scattered ones each
 // OCC: resident CTAs per SM asked of the register allocator (0 = chunk_min_ctas(THREADS))
-// DIET: phase 2 through chunk_walk (round-2 experiment, selected by BFX_CHUNK_DIET=1; not the default)
+// DIET: phase 2 through chunk_walk (round-2 experiment, selected by bfx_asm_chunk_set_kernel; not the default)
 template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0, bool DIET = false>
 __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
@@ -1291,9 +1290,8 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   const size_t smem = ChunkSmem<NS, CB, SYM ? 2 : 1>::TOTAL;
   if constexpr (SYM && NS <= 16 && CB == 256)
   {
-    // experiment knob (read once): BFX_CHUNK_OCC=5 runs the variant compiled for 5 resident CTAs per SM (51 registers)
-    static const int occ = getenv("BFX_CHUNK_OCC") ? atoi(getenv("BFX_CHUNK_OCC")) : 0;
-    if (occ == 5 && c->addr_bytes == 4)
+    // BFX_CHUNK_KERNEL_OCC5: the variant compiled for 5 resident CTAs per SM (48 registers)
+    if (c->kernel_variant == BFX_CHUNK_KERNEL_OCC5 && c->addr_bytes == 4)
     {
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1304,9 +1302,8 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   }
   if constexpr (SYM && CB == chunk_cb(NS))
   {
-    // round-2 experiment knob (read once): BFX_CHUNK_DIET=1 runs the variant whose phase 2 is chunk_walk
-    static const int diet = getenv("BFX_CHUNK_DIET") ? atoi(getenv("BFX_CHUNK_DIET")) : 0;
-    if (diet && c->addr_bytes == 4)
+    // BFX_CHUNK_KERNEL_DIET: the variant whose phase 2 is chunk_walk
+    if (c->kernel_variant == BFX_CHUNK_KERNEL_DIET && c->addr_bytes == 4)
     {
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2003,6 +2000,15 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
                   + (c->wr_addr ? c->n_dest_pad * 12 : c->n_dest_pad * c->addr_bytes * (c->sym ? 2 : 1))
                   + c->n_src32 * 64 + (c->perm ? P->ncells * 4 : 0)
                   + (c->xdm ? P->ncells * 4 * (int64_t)(P->nx + P->nd0 + (c->dm1 ? P->nd1 : 0)) : 0);
+  return BFX_OK;
+}
+
+int bfx_asm_chunk_set_kernel(bfx_asm_t* P, int variant)
+{
+  BFX_REQUIRE(P && P->chunks, "bfx_asm_chunk_set_kernel: no chunk plan");
+  BFX_REQUIRE(variant == BFX_CHUNK_KERNEL_DEFAULT || variant == BFX_CHUNK_KERNEL_OCC5 || variant == BFX_CHUNK_KERNEL_DIET,
+              "bfx_asm_chunk_set_kernel: unknown variant %d", variant);
+  P->chunks->kernel_variant = variant;
   return BFX_OK;
 }
 

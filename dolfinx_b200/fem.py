@@ -411,6 +411,8 @@ CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 # cells per chunk: 0 = the element's default (256 P1 / 128 P2); 96, 128, 192, 384 (P1) or 64, 96 (symmetric P2)
 CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
 # write-back of the chunk sums in address order (symmetric P1 plans; see BFX_CHUNKS_TWO_STAGE in include/bfx.h)
+# kernel variant of the chunk plans: 0 default, 1 = 5 CTAs per SM (BFX_CHUNK_OCC=5), 2 = "diet" list walk (BFX_CHUNK_DIET=1)
+CHUNK_KERNEL = (2 if os.environ.get("BFX_CHUNK_DIET", "0") != "0" else 1 if os.environ.get("BFX_CHUNK_OCC", "0") == "5" else 0)
 CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padded to multiples of 4 (round-2 experiment)
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
@@ -442,6 +444,8 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
+            if st == _lib.OK and CHUNK_KERNEL:
+                _lib.check(_lib.lib.bfx_asm_chunk_set_kernel(plan, CHUNK_KERNEL))
         else:
             st = _lib.lib.bfx_asm_build_rowgather(plan, _lib.current_stream())
         if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):

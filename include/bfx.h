@@ -271,6 +271,16 @@ extern "C"
   /* Staged entries whose shared-memory bank still collides with another entry read in the same half-warp step
    * after the plan's bank colouring (-1: linear staging layout in use). */
   int bfx_asm_chunk_bank_conflicts(const bfx_asm_t* plan, int64_t* n_conflicts);
+  /* Kernel variant of a chunk plan (symmetric plans with the element's default chunk size; ignored elsewhere):
+   * DEFAULT; OCC5 = compiled for 5 resident CTAs per SM (P1-sized elements; measured slower on B200); DIET = list walk
+   * specialised per state space with rolled loops (round-2 experiment).  All give the same values. */
+  enum
+  {
+    BFX_CHUNK_KERNEL_DEFAULT = 0,
+    BFX_CHUNK_KERNEL_OCC5 = 1,
+    BFX_CHUNK_KERNEL_DIET = 2
+  };
+  int bfx_asm_chunk_set_kernel(bfx_asm_t* plan, int variant);
   /* 1 if the chunk plan was built with the two-stage (address-ordered) write-back, see BFX_CHUNKS_TWO_STAGE */
   int bfx_asm_chunk_two_stage(const bfx_asm_t* plan, int* two_stage);
 
