@@ -74,6 +74,7 @@ struct bfx_chunks
   // colour[c][k]; the colours make the 16 lanes of every list step hit 16 different 8-byte banks
   uint8_t* colour = nullptr;  // ns (padded to a multiple of 4) bytes per cell slot, or NULL (padded linear layout)
   int64_t n_bank_conflicts = 0; // list reads the colouring could not make conflict free (diagnostic)
+  bool bank_ordered = false;    // BFX_CHUNKS_BANK_ORDER: the lists of the linear layout are ordered bank-aware
   int32_t* perm = nullptr;    // locality ordering of the plan's cell list (or NULL)
   // geometry dofmap / dofmaps in chunk order (one row per cell slot), so that phase 1 streams them
   // instead of chasing perm -> cells -> dofmap; NULL = the plan's own arrays are already in order
@@ -85,6 +86,8 @@ struct bfx_chunks
   int32_t *wv_ids = nullptr, *wd_ids = nullptr;
   uint8_t *wv_cnt = nullptr, *wd_cnt = nullptr;
   uint8_t *wv_loc = nullptr, *wd_loc = nullptr; // 4 * ceil(width / 4) bytes per slot
+  int lean_dbg = 0;
+  bool tables_complete = false; // every group of 32 cells has its node (and dof) table: no direct-gather groups
   // Vector plans (bfx_asm_build_groups): for every group of 32 cell slots, the (cell, local dof) pairs that
   // land on each distinct dof of the group: goff[g][l] .. goff[g][l+1] index glist[g][], entries = i * 32 + lane
   uint8_t *glist = nullptr, *goff = nullptr;

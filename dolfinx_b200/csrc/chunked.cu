@@ -22,6 +22,7 @@
 // free.  DESIGN.md section 4.2 has the measured effect of every step.
 // The same file holds the grouped vector kernel (bfx_asm_build_groups) that reuses the warp tables.
 #include "asm_device.cuh"
+#include <algorithm>
 #include "elements.cuh"
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
@@ -712,6 +713,89 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Bank-aware ORDER of the source lists (padded linear staging layout, no colours): the 16 lanes of a half warp read
+// one list entry each per step; the order of a destination's entries is free (it only fixes the summation order), so
+// a greedy pass lets every lane take, at every step, a remaining entry whose 8-byte bank is still unused in that step
+// (padding entries of shorter lists float to the steps where nothing fits).  One warp per chunk; lists longer than
+// 32 entries keep their order.  What cannot be avoided is counted.
+__global__ void __launch_bounds__(256)
+    k_chunk_bank_order(int64_t nchunks, const ChunkHdr* __restrict__ hdr, const uint32_t* __restrict__ winfo,
+                       uint16_t* __restrict__ src, int zero_slot, unsigned long long* __restrict__ n_conflicts)
+{
+  const int lane = threadIdx.x & 31;
+  const int half_base = lane & 16, turn_of_me = lane & 15;
+  unsigned long long bad = 0;
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nchunks; q += ((int64_t)gridDim.x * blockDim.x) >> 5)
+  {
+    const ChunkHdr h = hdr[q];
+    const int n_dw = (h.n_dest + 31) >> 5;
+    const uint32_t* wi = winfo + (h.dest_base >> 5);
+    for (int dw = 0; dw < n_dw; ++dw)
+    {
+      const uint32_t info = wi[dw];
+      const int m = (int)(info & 0xffu);
+      if (m < 2 || m > 32)
+        continue;
+      uint16_t* list = src + ((h.src_base32 + (info >> 8)) << 5) + lane;
+      uint16_t ent[32], outl[32];
+      uint32_t rem = 0; // real entries not yet scheduled
+      for (int j = 0; j < m; ++j)
+      {
+        ent[j] = list[j << 5];
+        if (ent[j] != zero_slot)
+          rem |= 1u << j;
+      }
+      int pads = m - __popc(rem);
+      for (int j = 0; j < m; ++j)
+      {
+        uint32_t used = 0;
+        for (int t0 = 0; t0 < 16; ++t0)
+        {
+          const int t = (t0 + j) & 15; // rotate the picking order so that no lane is always last
+          uint32_t mine = used;
+          if (turn_of_me == t)
+          {
+            int pick = -1;
+            uint32_t r = rem;
+            while (r)
+            {
+              const int k = __ffs(r) - 1;
+              r &= r - 1;
+              if (!((used >> (ent[k] & 15)) & 1u))
+              {
+                pick = k;
+                break;
+              }
+            }
+            if (pick < 0 && pads > 0)
+            {
+              --pads;
+              outl[j] = (uint16_t)zero_slot;
+            }
+            else
+            {
+              if (pick < 0)
+              {
+                pick = __ffs(rem) - 1; // (rem != 0: real entries + pads == remaining steps)
+                ++bad;
+              }
+              rem &= ~(1u << pick);
+              outl[j] = ent[pick];
+              mine = used | (1u << (ent[pick] & 15));
+            }
+          }
+          used = __shfl_sync(0xffffffffu, mine, half_base | t);
+        }
+      }
+      for (int j = 0; j < m; ++j)
+        list[j << 5] = outl[j];
+    }
+  }
+  bad = warp_sum(bad);
+  if (lane == 0 && bad)
+    atomicAdd(n_conflicts, bad);
+}
+
 // distinct ids of every group of 32 consecutive slots + per-slot positions in that list (see bfx_chunks)
 template <int WMAX>
 __global__ void __launch_bounds__(128)
@@ -780,6 +864,16 @@ __global__ void __launch_bounds__(128)
     }
     __syncwarp();
   }
+}
+
+__global__ void k_count_zero_bytes(int64_t n, const uint8_t* __restrict__ v, unsigned long long* __restrict__ out)
+{
+  unsigned long long z = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    z += v[t] == 0;
+  z = warp_sum(z);
+  if ((threadIdx.x & 31) == 0 && z)
+    atomicAdd(out, z);
 }
 
 __global__ void k_permute_rows(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ cells,
@@ -875,7 +969,7 @@ struct ChunkSmem
 // arrays - so that each copy addresses ONE state space (LDS / 32-bit addresses in the first) instead of generic loads
 // with 64-bit arithmetic, and with the 4-step loop kept rolled: the classic code is unrolled to 16 steps with a cascade
 // of 8 / 4 / 3 / 2 / 1-step remainders, 132 instructions per destination for lists of ~6 entries.
-template <bool SYM, int THREADS, typename AddrT>
+template <bool SYM, int THREADS, typename AddrT, int DBG = 0>
 __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, const AddrT* __restrict__ destp,
                                            const uint32_t* __restrict__ winfop, const double* __restrict__ Es,
                                            double* __restrict__ values, int n_dest, int n_complete, int n_dw, int overwrite)
@@ -913,7 +1007,7 @@ __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, co
     for (; j < m; ++j) // (empty when the plan pads the lists to multiples of 4: BFX_CHUNKS_PAD4)
       s0 += Es[p[j << 5]];
     const double sum = s0 + s1;
-    if (t < n_dest)
+    if (t < n_dest && (DBG != 3 || sum == 1.2345e300))
     {
       if (plain)
       {
@@ -936,7 +1030,8 @@ __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, co
 // lanes update consecutive CSR values - both entries of a symmetric pair included - instead of two scattered ones each
 // OCC: resident CTAs per SM asked of the register allocator (0 = chunk_min_ctas(THREADS))
 // DIET: phase 2 through chunk_walk (round-2 experiment, selected by bfx_asm_chunk_set_kernel; not the default)
-template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0, bool DIET = false>
+// DBG (profiling only, results are wrong): 1 = phase 1 only, 2 = phase 2 only, 3 = phase 2 without the global updates
+template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0, bool DIET = false, int DBG = 0>
 __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
@@ -964,8 +1059,8 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   const int64_t gw = (q * CB + (c & ~31)) >> 5; // group of 32 consecutive cell slots this warp works on
   const bool use_bits = ch.bits0 || ch.bits1;
   const bool dof_tab = BS == 1 && use_bits && ch.wd_cnt && (ch.same_bc || !ch.bits1);
-  const int dcnt = dof_tab ? ch.wd_cnt[gw] : 0;
-  const int vcnt = ch.wv_cnt ? ch.wv_cnt[gw] : 0;
+  const int dcnt = (dof_tab && (DBG < 2 || DBG == 4)) ? ch.wd_cnt[gw] : 0;
+  const int vcnt = (ch.wv_cnt && (DBG < 2 || DBG == 4)) ? ch.wv_cnt[gw] : 0;
   const int64_t dof_id = dof_tab ? ch.wd_ids[gw * 32 + lane1] : 0;
   const int32_t vtx_id = ch.wv_cnt ? ch.wv_ids[gw * 32 + lane1] : 0;
   constexpr int COLW = (NS + 3) / 4;
@@ -1001,7 +1096,7 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     // one thread arms the barrier and starts the copies; nobody else touches the header before phase 2
     mbar_init(bar, 1);
     Es[ch.colour ? NS * CB : NS * (CB + 1)] = 0.0; // the slot padded list entries point at
-    if (fits && n_dw > 0)
+    if (fits && n_dw > 0 && DBG != 4)
     {
       const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u; // chunks start on 4-group boundaries
       mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes + (TWO ? n_wr_pad * 2u : 0u));
@@ -1015,7 +1110,7 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   }
 
   // ---- phase 1: element matrices of the chunk -> shared memory (entry-major)
-  const bool active = slot < a.n;
+  const bool active = slot < a.n && (DBG < 2 || DBG == 4);
   int64_t e = slot;
   int32_t cell = (int32_t)slot;
   if (active && (E::WSIZE > 0 || !ch.xdm))
@@ -1126,16 +1221,25 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     }
   }
   __syncthreads();
-  if (fits && n_dw > 0)
+  if (fits && n_dw > 0 && DBG != 4)
     mbar_wait(bar, 0);
+  if constexpr (DBG == 1 || DBG == 4)
+  {
+    double chk = 0.0; // keeps the staged values alive
+    for (int k = 0; k < NS; ++k)
+      chk += Es[k * CB + ((threadIdx.x * 7 + k) % CB)];
+    if (chk == 1.2345e300)
+      a.values[0] = chk;
+    return;
+  }
 
   if constexpr (DIET)
   {
     static_assert(!TWO, "the diet variant keeps the classic write-back");
     if (fits)
-      chunk_walk<SYM, THREADS, AddrT>(s_src, s_dest, s_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
+      chunk_walk<SYM, THREADS, AddrT, DBG>(s_src, s_dest, s_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
     else
-      chunk_walk<SYM, THREADS, AddrT>(g_src, g_dest, g_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
+      chunk_walk<SYM, THREADS, AddrT, DBG>(g_src, g_dest, g_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
     return;
   }
   // ---- phase 2: one thread per distinct destination
@@ -1223,6 +1327,312 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// LEAN kernel (round 2): the same algorithm as k_matrix_chunked for symmetric plans of P1-sized scalar elements
+// (<= 4 nodes, <= 4 dofs per cell) with the padded linear staging layout, 32-bit addresses and complete warp
+// tables, rewritten for instruction count - phase 1 of the classic kernel alone runs 1.87 ms at C2 at 80 % issue
+// utilisation (profiles/r02_phase_split.txt): 450 instructions per cell of which 104 are fp64.  Here: 32-bit slot
+// arithmetic, one table word per cell, unconditional shuffles (no WARPSYNC / collective bookkeeping), Dirichlet
+// handling behind one warp vote, staging through immediate offsets.
+// ---------------------------------------------------------------------------------------------
+struct LeanArgs
+{
+  const ChunkHdr* hdr;
+  const uint32_t* winfo;
+  const uint32_t* dest; // two addresses per destination
+  const uint16_t* src;
+  const int32_t *wv_ids, *wd_ids; // one entry per cell slot: the node / dof this LANE fetches for its group of 32 cells
+  const uint32_t *wv_loc, *wd_loc; // per cell slot: 4 x uint8 positions of its nodes / dofs in the group's table
+  const uint32_t* bits;           // bit-packed Dirichlet markers or NULL
+  const double* x;
+  double* values;
+  double constants[4];
+  uint32_t n; // cells of the plan
+  int overwrite;
+};
+
+template <class E, int CB, int DBG = 0>
+__global__ void __launch_bounds__(CB, chunk_min_ctas(CB)) k_matrix_lean(const LeanArgs p)
+{
+  constexpr int NX = E::NX, ND = E::ND, NS = ND * (ND + 1) / 2, LD = CB + 1;
+  static_assert(E::BS == 1 && NX <= 4 && ND <= 4 && E::WSIZE == 0, "lean kernel: P1-sized scalar elements without coefficients");
+  using L = ChunkSmem<NS, CB, 2, false>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Es = reinterpret_cast<double*>(smem_raw);
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(smem_raw + L::SRC_OFF);
+  uint32_t* s_dest = reinterpret_cast<uint32_t*>(smem_raw + L::DEST_OFF);
+  uint32_t* s_winfo = reinterpret_cast<uint32_t*>(smem_raw + L::WINFO_OFF);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t slot = blockIdx.x * (uint32_t)CB + tid;
+  // ---- first-level loads (coalesced, one word each)
+  const int32_t vtx = __ldg(p.wv_ids + slot);
+  const uint32_t locv = __ldg(p.wv_loc + slot);
+  uint32_t dof = 0, locd = 0;
+  if (p.bits)
+  {
+    dof = (uint32_t)__ldg(p.wd_ids + slot);
+    locd = __ldg(p.wd_loc + slot);
+  }
+  const ChunkHdr h = p.hdr[blockIdx.x];
+  const int n_dw = (h.n_dest + 31) >> 5;
+  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 256u;
+  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
+  const uint16_t* g_src = p.src + (h.src_base32 << 5);
+  const uint32_t* g_dest = p.dest + h.dest_base * 2;
+  const uint32_t* g_winfo = p.winfo + (h.dest_base >> 5);
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    Es[NS * LD] = 0.0; // the slot padded list entries point at
+    if (fits && n_dw > 0)
+    {
+      const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u;
+      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes);
+      bulk_g2s(s_src, g_src, src_bytes, bar);
+      bulk_g2s(s_dest, g_dest, dest_bytes, bar);
+      bulk_g2s(s_winfo, g_winfo, winfo_bytes, bar);
+    }
+  }
+  // ---- second level: this lane's node (and marker word)
+  const double* pp = p.x + 3 * (int64_t)vtx;
+  const double px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+  uint32_t bit = 0;
+  if (p.bits)
+    bit = (__ldg(p.bits + (dof >> 5)) >> (dof & 31u)) & 1u;
+  // ---- coordinates of this cell's nodes (the shuffle uses the low 5 bits of the lane operand)
+  double xc[NX][3];
+#pragma unroll
+  for (int v = 0; v < NX; ++v)
+  {
+    const int l = (int)(locv >> (8 * v));
+    xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+    xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+    xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+  }
+  uint32_t m = 0;
+  if (__any_sync(0xffffffffu, bit)) // some cell of this warp touches a Dirichlet dof
+  {
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      m |= __shfl_sync(0xffffffffu, bit, (int)(locd >> (8 * i))) << i;
+  }
+  if (slot < p.n && DBG != 2 && DBG != 3)
+  {
+    typename E::Geo g;
+    E::prepare(g, xc, nullptr, p.constants, 0);
+    double* e = Es + tid;
+    if (m == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double row[ND];
+        E::row(g, i, row);
+#pragma unroll
+        for (int j = i; j < ND; ++j)
+          e[(i * ND - i * (i - 1) / 2 + (j - i)) * LD] = row[j];
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double row[ND];
+        E::row(g, i, row);
+#pragma unroll
+        for (int j = i; j < ND; ++j)
+          e[(i * ND - i * (i - 1) / 2 + (j - i)) * LD] = ((m >> i) | (m >> j)) & 1u ? 0.0 : row[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (fits && n_dw > 0)
+    mbar_wait(bar, 0);
+  if constexpr (DBG == 1)
+  {
+    double chk = 0.0; // keeps the staged values alive
+    for (int k = 0; k < NS; ++k)
+      chk += Es[k * LD + ((tid * 7 + k) % CB)];
+    if (chk == 1.2345e300)
+      p.values[0] = chk;
+    return;
+  }
+  if (fits)
+    chunk_walk<true, CB, uint32_t, DBG>(s_src, s_dest, s_winfo, Es, p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
+  else
+    chunk_walk<true, CB, uint32_t, DBG>(g_src, g_dest, g_winfo, Es, p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LEAN2: the lean kernel as PERSISTENT CTAs with a two-stage pipeline.  The CTA walks chunks q, q + grid, ...; the
+// lists of chunk q + grid (source lists, destination addresses, group table: three TMA bulk copies) land in the
+// other shared-memory stage and the table words of its cells are fetched into registers while chunk q is computed,
+// so that of the three DRAM round trips of a short-lived CTA (tables, lists, coordinates) only the coordinate
+// gather stays exposed.  One __syncthreads per chunk; the staging area is handed back through an mbarrier that every
+// thread arrives on after its list walk and waits for just before it stages the next chunk.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NS, int CB>
+struct Lean2Smem
+{
+  static constexpr int SRC_GROUPS = (NS * CB / 32) * 19 / 10; // 32-entry groups of list entries per stage
+  static constexpr int DCAP = (NS * CB * 13 / 40) / 32 * 32;   // destinations per stage
+  static constexpr int WINFO = DCAP / 32;
+  static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)NS * (CB + 1) + 2) + 127) / 128 * 128;
+  static constexpr size_t SRC_BYTES = (size_t)SRC_GROUPS * 64, DEST_BYTES = (size_t)DCAP * 8;
+  static constexpr size_t WINFO_BYTES = ((size_t)WINFO * 4 + 15) / 16 * 16;
+  static constexpr size_t STAGE = SRC_BYTES + DEST_BYTES + WINFO_BYTES;
+  static constexpr size_t STAGE_OFF = E_BYTES;
+  static constexpr size_t HDR_OFF = STAGE_OFF + 2 * STAGE; // 2 x ChunkHdr
+  static constexpr size_t BAR_OFF = HDR_OFF + 2 * sizeof(ChunkHdr);
+  static constexpr size_t TOTAL = BAR_OFF + 32;
+};
+
+template <class E, int CB>
+__global__ void __launch_bounds__(CB, chunk_min_ctas(CB)) k_matrix_lean2(const LeanArgs p, const uint32_t nchunks)
+{
+  constexpr int NX = E::NX, ND = E::ND, NS = ND * (ND + 1) / 2, LD = CB + 1;
+  static_assert(E::BS == 1 && NX <= 4 && ND <= 4 && E::WSIZE == 0, "lean kernel: P1-sized scalar elements without coefficients");
+  using L = Lean2Smem<NS, CB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Es = reinterpret_cast<double*>(smem_raw);
+  ChunkHdr* s_hdr = reinterpret_cast<ChunkHdr*>(smem_raw + L::HDR_OFF);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF); // [2]
+  uint64_t* bar_free = bar_full + 2;
+
+  const uint32_t tid = threadIdx.x;
+  // one thread: header of chunk q -> shared memory, TMA of its lists into stage st
+  auto fetch_lists = [&](uint32_t q, int st)
+  {
+    const ChunkHdr h = p.hdr[q];
+    s_hdr[st] = h;
+    const int n_dw = (h.n_dest + 31) >> 5;
+    const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 256u;
+    const bool fits = h.n_src32 <= L::SRC_GROUPS && n_dw <= L::WINFO;
+    if (fits && n_dw > 0)
+    {
+      unsigned char* base = smem_raw + L::STAGE_OFF + (size_t)st * L::STAGE;
+      const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u;
+      mbar_expect_tx(bar_full + st, src_bytes + dest_bytes + winfo_bytes);
+      bulk_g2s(base, p.src + (h.src_base32 << 5), src_bytes, bar_full + st);
+      bulk_g2s(base + L::SRC_BYTES, p.dest + h.dest_base * 2, dest_bytes, bar_full + st);
+      bulk_g2s(base + L::SRC_BYTES + L::DEST_BYTES, p.winfo + (h.dest_base >> 5), winfo_bytes, bar_full + st);
+    }
+  };
+  uint32_t q = blockIdx.x;
+  if (tid == 0)
+  {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_full + 1, 1);
+    mbar_init(bar_free, CB);
+    Es[NS * LD] = 0.0; // the slot padded list entries point at
+    fetch_lists(q, 0);
+  }
+  // table words of the first chunk
+  uint32_t slot = q * (uint32_t)CB + tid;
+  int32_t vtx = __ldg(p.wv_ids + slot);
+  uint32_t locv = __ldg(p.wv_loc + slot);
+  uint32_t dof = 0, locd = 0;
+  if (p.bits)
+  {
+    dof = (uint32_t)__ldg(p.wd_ids + slot);
+    locd = __ldg(p.wd_loc + slot);
+  }
+  __syncthreads(); // barriers initialised before anybody waits on them
+
+  for (uint32_t it = 0; q < nchunks; ++it, q += gridDim.x)
+  {
+    const int st = (int)(it & 1u);
+    // ---- this chunk: second-level loads (the lane's node, its marker word)
+    const double* pp = p.x + 3 * (int64_t)vtx;
+    const double px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+    uint32_t bit = 0;
+    if (p.bits)
+      bit = (__ldg(p.bits + (dof >> 5)) >> (dof & 31u)) & 1u;
+    const uint32_t locv_c = locv, locd_c = locd;
+    const bool active = slot < p.n;
+    // ---- next chunk: table words into registers, lists into the other stage
+    const uint32_t qn = q + gridDim.x;
+    if (qn < nchunks)
+    {
+      slot = qn * (uint32_t)CB + tid;
+      vtx = __ldg(p.wv_ids + slot);
+      locv = __ldg(p.wv_loc + slot);
+      if (p.bits)
+      {
+        dof = (uint32_t)__ldg(p.wd_ids + slot);
+        locd = __ldg(p.wd_loc + slot);
+      }
+      if (tid == 0)
+      {
+        if (it > 0)
+          mbar_wait(bar_free, (it - 1) & 1u); // everybody has left the walk that read this stage
+        fetch_lists(qn, st ^ 1);
+      }
+    }
+    // ---- coordinates of this cell's nodes
+    double xc[NX][3];
+#pragma unroll
+    for (int v = 0; v < NX; ++v)
+    {
+      const int l = (int)(locv_c >> (8 * v));
+      xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+      xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+      xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+    }
+    uint32_t m = 0;
+    if (__any_sync(0xffffffffu, bit))
+    {
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        m |= __shfl_sync(0xffffffffu, bit, (int)(locd_c >> (8 * i))) << i;
+    }
+    typename E::Geo g;
+    if (active)
+      E::prepare(g, xc, nullptr, p.constants, 0);
+    if (it > 0)
+      mbar_wait(bar_free, (it - 1) & 1u); // the previous walk no longer reads the staging area
+    if (active)
+    {
+      double* e = Es + tid;
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double row[ND];
+        E::row(g, i, row);
+#pragma unroll
+        for (int j = i; j < ND; ++j)
+          e[(i * ND - i * (i - 1) / 2 + (j - i)) * LD] = (m && (((m >> i) | (m >> j)) & 1u)) ? 0.0 : row[j];
+      }
+    }
+    __syncthreads();
+    const ChunkHdr h = s_hdr[st];
+    const int n_dw = (h.n_dest + 31) >> 5;
+    const bool fits = h.n_src32 <= L::SRC_GROUPS && n_dw <= L::WINFO;
+    if (fits)
+    {
+      if (n_dw > 0)
+        mbar_wait(bar_full + st, (it >> 1) & 1u);
+      const unsigned char* base = smem_raw + L::STAGE_OFF + (size_t)st * L::STAGE;
+      chunk_walk<true, CB, uint32_t>(reinterpret_cast<const uint16_t*>(base),
+                                     reinterpret_cast<const uint32_t*>(base + L::SRC_BYTES),
+                                     reinterpret_cast<const uint32_t*>(base + L::SRC_BYTES + L::DEST_BYTES), Es, p.values,
+                                     h.n_dest, h.n_complete, n_dw, p.overwrite);
+    }
+    else
+      chunk_walk<true, CB, uint32_t>(p.src + (h.src_base32 << 5), p.dest + h.dest_base * 2, p.winfo + (h.dest_base >> 5), Es,
+                                     p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
+    mbar_arrive(bar_free);
+  }
+}
+
 // int8 markers -> one bit per dof (32 dofs per word, one warp ballot per word)
 __global__ void k_pack_marker_bits(int64_t n, const int8_t* __restrict__ markers, uint32_t* __restrict__ bits)
 {
@@ -1296,6 +1706,81 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
+  if constexpr (SYM && E::NX <= 4 && E::ND <= 4 && E::BS == 1 && E::WSIZE == 0 && THREADS == CB)
+  {
+    // BFX_CHUNK_KERNEL_LEAN: the instruction-lean kernel (linear staging, complete warp tables, 32-bit addresses)
+    if (c->kernel_variant == BFX_CHUNK_KERNEL_LEAN && c->addr_bytes == 4 && !c->colour && c->tables_complete
+        && P->ncells < 0xffffffffLL - CB && (!a.bc0 || c->wd_ids))
+    {
+      LeanArgs lp;
+      lp.hdr = c->hdr, lp.winfo = c->winfo, lp.dest = static_cast<const uint32_t*>(c->dest_addr), lp.src = c->src;
+      lp.wv_ids = c->wv_ids, lp.wv_loc = reinterpret_cast<const uint32_t*>(c->wv_loc);
+      lp.wd_ids = c->wd_ids, lp.wd_loc = reinterpret_cast<const uint32_t*>(c->wd_loc);
+      lp.bits = ch.bits0;
+      lp.x = a.x;
+      lp.values = a.values;
+      for (int k = 0; k < 4; ++k)
+        lp.constants[k] = a.constants[k];
+      lp.n = (uint32_t)a.n;
+      lp.overwrite = ch.overwrite;
+      const int dbg = c->lean_dbg;
+      if (dbg == 10) // persistent two-stage pipeline
+      {
+        using L2 = Lean2Smem<NS, CB>;
+        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean2<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2::TOTAL));
+        int per_sm = 0;
+        BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matrix_lean2<E, CB>, CB, L2::TOTAL));
+        const int64_t grid = std::min<int64_t>(c->nchunks, (int64_t)sm_count() * std::max(per_sm, 1));
+        k_matrix_lean2<E, CB><<<(unsigned)grid, CB, L2::TOTAL, st>>>(lp, (uint32_t)c->nchunks);
+      }
+      else if (dbg == 0)
+      {
+        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_matrix_lean<E, CB><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+      }
+      else if constexpr (CB == 256 && E::NX == 4)
+      {
+        auto go = [&](auto d)
+        {
+          constexpr int D = decltype(d)::value;
+          cudaFuncSetAttribute(k_matrix_lean<E, CB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k_matrix_lean<E, CB, D><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+        };
+        if (dbg == 1)
+          go(std::integral_constant<int, 1>());
+        else if (dbg == 2)
+          go(std::integral_constant<int, 2>());
+        else
+          go(std::integral_constant<int, 3>());
+      }
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
+  if constexpr (SYM && NS <= 16 && CB == 256)
+  {
+    // profiling-only variants (10 + DBG): see k_matrix_chunked
+    if (c->kernel_variant >= 11 && c->kernel_variant <= 14 && c->addr_bytes == 4)
+    {
+      auto go = [&](auto dbg)
+      {
+        constexpr int D = decltype(dbg)::value;
+        cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true, D>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true, D><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+      };
+      if (c->kernel_variant == 11)
+        go(std::integral_constant<int, 1>());
+      else if (c->kernel_variant == 12)
+        go(std::integral_constant<int, 2>());
+      else if (c->kernel_variant == 13)
+        go(std::integral_constant<int, 3>());
+      else
+        go(std::integral_constant<int, 4>());
       BFX_CHECK_LAUNCH();
       return BFX_OK;
     }
@@ -1744,6 +2229,23 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
       k_warp_tables<8><<<grid, 128, 0, st>>>(nslots_pad, P->ncells, P->nd0, drows, c->wd_ids, c->wd_cnt, c->wd_loc);
     }
     BFX_CHECK_LAUNCH();
+    // groups that hold cells but have no table (more than 32 distinct ids): the lean kernel needs none
+    {
+      unsigned long long* d_bad = nullptr;
+      unsigned long long h_bad = 0;
+      if ((e = dev_alloc(&d_bad, 1)))
+        return bail(e);
+      BFX_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
+      const int64_t nw_active = (P->ncells + 31) / 32;
+      if (c->wv_cnt)
+        k_count_zero_bytes<<<grid_for(nw_active, 256, 8), 256, 0, st>>>(nw_active, c->wv_cnt, d_bad);
+      if (c->wd_cnt)
+        k_count_zero_bytes<<<grid_for(nw_active, 256, 8), 256, 0, st>>>(nw_active, c->wd_cnt, d_bad);
+      BFX_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, st));
+      BFX_CUDA(cudaStreamSynchronize(st));
+      cudaFree(d_bad);
+      c->tables_complete = c->wv_cnt && h_bad == 0;
+    }
   }
 
   // ---- scratch of the bit-packed Dirichlet markers (sized by the largest dof the cells reference)
@@ -1875,6 +2377,21 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   p.src = c->src;
   if ((e = run_plan_pass_items(items, true, p, c->nchunks, st)))
     return bail(e);
+  if ((flags & BFX_CHUNKS_LINEAR_STAGING) && (flags & BFX_CHUNKS_BANK_ORDER))
+  {
+    unsigned long long* d_conf = nullptr;
+    if ((e = dev_alloc(&d_conf, 1)))
+      return bail(e);
+    BFX_CUDA(cudaMemsetAsync(d_conf, 0, sizeof(unsigned long long), st));
+    k_chunk_bank_order<<<grid_for(c->nchunks, 8, 16), 256, 0, st>>>(c->nchunks, c->hdr, c->winfo, c->src, n2 * (cb + 1), d_conf);
+    BFX_CHECK_LAUNCH();
+    unsigned long long h_conf = 0;
+    BFX_CUDA(cudaMemcpyAsync(&h_conf, d_conf, sizeof(h_conf), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_conf);
+    c->n_bank_conflicts = (int64_t)h_conf;
+    c->bank_ordered = true;
+  }
   // ---- bank-conflict-free staging layout (element matrices of at most 16 staged entries)
   if (n2 <= COLOUR_MAX_NS && !(flags & BFX_CHUNKS_LINEAR_STAGING))
   {
@@ -2006,9 +2523,12 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
 int bfx_asm_chunk_set_kernel(bfx_asm_t* P, int variant)
 {
   BFX_REQUIRE(P && P->chunks, "bfx_asm_chunk_set_kernel: no chunk plan");
-  BFX_REQUIRE(variant == BFX_CHUNK_KERNEL_DEFAULT || variant == BFX_CHUNK_KERNEL_OCC5 || variant == BFX_CHUNK_KERNEL_DIET,
+  BFX_REQUIRE(variant == BFX_CHUNK_KERNEL_DEFAULT || variant == BFX_CHUNK_KERNEL_OCC5 || variant == BFX_CHUNK_KERNEL_DIET
+                  || variant == BFX_CHUNK_KERNEL_LEAN || (variant >= 11 && variant <= 14),
               "bfx_asm_chunk_set_kernel: unknown variant %d", variant);
   P->chunks->kernel_variant = variant;
+  if (const char* d = getenv("BFX_LEAN_DBG")) // profiling only (wrong results): 1 phase 1, 2 phase 2, 3 phase 2 without updates
+    P->chunks->lean_dbg = atoi(d);
   return BFX_OK;
 }
 
@@ -2022,7 +2542,7 @@ int bfx_asm_chunk_two_stage(const bfx_asm_t* P, int* two_stage)
 int bfx_asm_chunk_bank_conflicts(const bfx_asm_t* P, int64_t* n_conflicts)
 {
   BFX_REQUIRE(P && P->chunks && n_conflicts, "bfx_asm_chunk_bank_conflicts: no chunk plan");
-  *n_conflicts = P->chunks->colour ? P->chunks->n_bank_conflicts : -1;
+  *n_conflicts = (P->chunks->colour || P->chunks->bank_ordered) ? P->chunks->n_bank_conflicts : -1;
   return BFX_OK;
 }
 }

@@ -412,7 +412,8 @@ CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
 # write-back of the chunk sums in address order (symmetric P1 plans; see BFX_CHUNKS_TWO_STAGE in include/bfx.h)
 # kernel variant of the chunk plans: 0 default, 1 = 5 CTAs per SM (BFX_CHUNK_OCC=5), 2 = "diet" list walk (BFX_CHUNK_DIET=1)
-CHUNK_KERNEL = (2 if os.environ.get("BFX_CHUNK_DIET", "0") != "0" else 1 if os.environ.get("BFX_CHUNK_OCC", "0") == "5" else 0)
+CHUNK_KERNEL = int(os.environ["BFX_CHUNK_DBG"]) if "BFX_CHUNK_DBG" in os.environ else (2 if os.environ.get("BFX_CHUNK_DIET", "0") != "0" else 1 if os.environ.get("BFX_CHUNK_OCC", "0") == "5" else 0)
+CHUNK_LEAN = os.environ.get("BFX_CHUNK_LEAN", "0") != "0"  # round 2: lean kernel on the linear staging layout
 CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padded to multiples of 4 (round-2 experiment)
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
@@ -439,13 +440,17 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
             flags |= _lib.CHUNKS_CB(CHUNKS_CB)
             if CHUNKS_PAD4:
                 flags |= _lib.CHUNKS_PAD4
+            if CHUNK_LEAN:
+                flags |= _lib.CHUNKS_LINEAR_STAGING
+                if os.environ.get("BFX_CHUNKS_BANK_ORDER", "1") != "0":
+                    flags |= _lib.CHUNKS_BANK_ORDER
             if CHUNKS_TWO_STAGE:
                 flags |= _lib.CHUNKS_TWO_STAGE | (_lib.CHUNKS_TWO_STAGE_SPLIT if int(CHUNKS_TWO_STAGE) == 2 else 0)
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
-            if st == _lib.OK and CHUNK_KERNEL:
-                _lib.check(_lib.lib.bfx_asm_chunk_set_kernel(plan, CHUNK_KERNEL))
+            if st == _lib.OK and (CHUNK_KERNEL or CHUNK_LEAN):
+                _lib.check(_lib.lib.bfx_asm_chunk_set_kernel(plan, 3 if CHUNK_LEAN else CHUNK_KERNEL))
         else:
             st = _lib.lib.bfx_asm_build_rowgather(plan, _lib.current_stream())
         if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):

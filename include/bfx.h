@@ -241,6 +241,9 @@ extern "C"
     BFX_CHUNKS_TWO_STAGE = 8, /* symmetric P1-sized plans: the kernel leaves the per-destination sums in shared memory
                                  and writes the CSR values back in ADDRESS order (both entries of a symmetric pair),
                                  so that consecutive lanes update consecutive values; ignored where not applicable */
+    BFX_CHUNKS_BANK_ORDER = 64, /* with BFX_CHUNKS_LINEAR_STAGING: order every source list so that the 16 lanes of a half
+                                   warp read 16 different shared-memory banks per step where possible (no per-cell
+                                   colour bytes, no extra instructions in the kernel) */
     BFX_CHUNKS_PAD4 = 32, /* pad the source lists to multiples of 4 entries (no remainder steps in the list walk) */
     BFX_CHUNKS_TWO_STAGE_SPLIT = 16, /* with BFX_CHUNKS_TWO_STAGE: plain stores first, REDs after, each in address order */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
@@ -278,7 +281,9 @@ extern "C"
   {
     BFX_CHUNK_KERNEL_DEFAULT = 0,
     BFX_CHUNK_KERNEL_OCC5 = 1,
-    BFX_CHUNK_KERNEL_DIET = 2
+    BFX_CHUNK_KERNEL_DIET = 2,
+    BFX_CHUNK_KERNEL_LEAN = 3 /* instruction-lean kernel for symmetric P1-sized plans built with BFX_CHUNKS_LINEAR_STAGING
+                                 (falls back to DEFAULT where its preconditions do not hold) */
   };
   int bfx_asm_chunk_set_kernel(bfx_asm_t* plan, int variant);
   /* 1 if the chunk plan was built with the two-stage (address-ordered) write-back, see BFX_CHUNKS_TWO_STAGE */
