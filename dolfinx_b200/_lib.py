@@ -55,10 +55,12 @@ ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
 CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
+LEAN_KERNELS = frozenset({0, 6})  # symmetric P1-sized kernels without coefficients: k_matrix_lean
 CHUNKS_SHARED_MATRIX = 4
 CHUNKS_LINEAR_STAGING = 2  # padded linear staging layout (no bank colouring); needed by CHUNK_KERNEL_LEAN
-CHUNK_KERNEL_DEFAULT, CHUNK_KERNEL_OCC5, CHUNK_KERNEL_DIET = 0, 1, 2
+CHUNK_KERNEL_DEFAULT, CHUNK_KERNEL_OCC5, CHUNK_KERNEL_DIET, CHUNK_KERNEL_LEAN = 0, 1, 2, 3
 CHUNKS_BANK_ORDER = 64  # bank-aware order of the source lists (linear staging layout)
+CHUNKS_LEN_SORT = 128  # destinations ordered by list length only (lean kernel)
 CHUNKS_PAD4 = 32  # source lists padded to multiples of 4 entries
 CHUNKS_TWO_STAGE_SPLIT = 16
 CHUNKS_TWO_STAGE = 8  # write-back in address order through shared memory (symmetric P1 plans)

@@ -74,6 +74,7 @@ struct bfx_chunks
   // colour[c][k]; the colours make the 16 lanes of every list step hit 16 different 8-byte banks
   uint8_t* colour = nullptr;  // ns (padded to a multiple of 4) bytes per cell slot, or NULL (padded linear layout)
   int64_t n_bank_conflicts = 0; // list reads the colouring could not make conflict free (diagnostic)
+  bool len_sorted = false;      // BFX_CHUNKS_LEN_SORT: winfo holds (info, completeness mask) pairs
   bool bank_ordered = false;    // BFX_CHUNKS_BANK_ORDER: the lists of the linear layout are ordered bank-aware
   int32_t* perm = nullptr;    // locality ordering of the plan's cell list (or NULL)
   // geometry dofmap / dofmaps in chunk order (one row per cell slot), so that phase 1 streams them

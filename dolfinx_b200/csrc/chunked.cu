@@ -86,6 +86,7 @@ struct ChunkBuildArgs
   int* err;
   // two-stage write-back (BFX_CHUNKS_TWO_STAGE): every (address, destination rank) pair of the chunk - both entries
   // of a symmetric pair - sorted by address, so that the lanes of the write-back pass hit consecutive CSR values
+  int len_sort;        // BFX_CHUNKS_LEN_SORT: destinations ordered by list length only; completeness travels as a bit mask
   int pad4;            // BFX_CHUNKS_PAD4: list lengths (per group of 32 destinations) padded to multiples of 4
   int two, dcap;       // dcap: destinations of a chunk the kernel holds in shared memory
   uint32_t* wr_addr;   // 2 * n_dest_pad entries, chunk q at 2 * dest_base
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
   uint64_t* lastkey = reinterpret_cast<uint64_t*>(raw + ((sizeof(Temp) + 15) / 16) * 16);
   uint32_t* mw = reinterpret_cast<uint32_t*>(lastkey + PLAN_THREADS);
   uint32_t* woff = mw + PLAN_THREADS;
-  uint16_t* sidx = reinterpret_cast<uint16_t*>(woff + PLAN_THREADS);
+  uint32_t* cmask = woff + PLAN_THREADS;
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(cmask + PLAN_THREADS);
   uint16_t* dstart = sidx + NK;
 
   const int64_t q = blockIdx.x;
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
   // ---- 2. distinct destinations: heads of equal-address runs
   lastkey[tid] = keys[ITEMS - 1];
   mw[tid] = 0;
+  cmask[tid] = 0;
   __syncthreads();
   int nheads = 0, nvalid = 0;
   bool head[ITEMS];
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
       contrib_addr(p, q, sidx[st], blk, other);
       const bool complete = p.total[blk] == cnt;
       ncomp += complete;
-      k2[it] = ((complete ? 0u : 1u) << 8) | (uint32_t)(MAX_LIST - cnt);
+      k2[it] = ((complete && !p.len_sort ? 0u : 1u) << 8) | (uint32_t)(MAX_LIST - cnt);
       v2[it] = (uint16_t)d;
     }
   }
@@ -334,8 +337,33 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
       h.pad = 0;
       p.hdr[q] = h;
     }
-    if (tid < n_dw)
+    if (tid < n_dw && !p.len_sort)
       p.winfo[(dest_base >> 5) + tid] = (woff[tid] << 8) | mw[tid];
+    if (p.len_sort)
+    {
+      // completeness of every destination as one bit per lane of its group
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it)
+      {
+        const int r = tid * ITEMS + it;
+        if (r < n_dest)
+        {
+          const int d = v2[it];
+          const int st = dstart[d];
+          const int cnt = min((int)dstart[d + 1] - st, MAX_LIST);
+          int64_t blk, other;
+          contrib_addr(p, q, sidx[st], blk, other);
+          if (p.total[blk] == cnt)
+            atomicOr(&cmask[r >> 5], 1u << (r & 31));
+        }
+      }
+      __syncthreads();
+      if (tid < n_dw)
+      {
+        p.winfo[2 * ((dest_base >> 5) + tid)] = (woff[tid] << 8) | mw[tid];
+        p.winfo[2 * ((dest_base >> 5) + tid) + 1] = cmask[tid];
+      }
+    }
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it)
     {
@@ -390,7 +418,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_chunk_plan(const ChunkBuildArg
           const int d = v2[it];
           int64_t blk, other;
           const int64_t addr = contrib_addr(p, q, sidx[dstart[d]], blk, other);
-          const uint64_t inc = (k2[it] >> 8) & 1u;
+          const uint64_t inc = p.total[blk] == min((int)dstart[d + 1] - (int)dstart[d], MAX_LIST) ? 0u : 1u;
           // split lists (two == 2): all plain stores first, then all REDs, each in address order
           const uint64_t tag = (inc << 15) | (uint64_t)r | (p.two == 2 ? inc << (16 + p.addr_bits) : 0ull);
           const int at = atomicAdd(wcnt, other != addr ? 2 : 1);
@@ -439,7 +467,7 @@ size_t plan_smem()
   t = t > sizeof(typename Scan::TempStorage) ? t : sizeof(typename Scan::TempStorage);
   t = (t + 15) / 16 * 16;
   // + the staging array of the two-stage write-back lists (NK keys of 8 bytes, a counter, alignment slack)
-  return t + PLAN_THREADS * 8 + PLAN_THREADS * 4 * 2 + (size_t)(2 * PLAN_THREADS * ITEMS + 2) * 2 + 16
+  return t + PLAN_THREADS * 8 + PLAN_THREADS * 4 * 3 + (size_t)(2 * PLAN_THREADS * ITEMS + 2) * 2 + 16
          + (size_t)PLAN_THREADS * ITEMS * 8 + 64;
 }
 
@@ -720,31 +748,39 @@ __global__ void __launch_bounds__(256)
 // 32 entries keep their order.  What cannot be avoided is counted.
 __global__ void __launch_bounds__(256)
     k_chunk_bank_order(int64_t nchunks, const ChunkHdr* __restrict__ hdr, const uint32_t* __restrict__ winfo,
-                       uint16_t* __restrict__ src, int zero_slot, unsigned long long* __restrict__ n_conflicts)
+                       uint16_t* __restrict__ src, int zero_slot, int wstride, unsigned long long* __restrict__ n_conflicts)
 {
-  const int lane = threadIdx.x & 31;
-  const int half_base = lane & 16, turn_of_me = lane & 15;
+  __shared__ int s_freq[8][2][16]; // per warp and half warp: remaining entries per bank
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int half = lane >> 4, half_base = lane & 16, turn_of_me = lane & 15;
+  int* freq = s_freq[wib][half];
   unsigned long long bad = 0;
   for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nchunks; q += ((int64_t)gridDim.x * blockDim.x) >> 5)
   {
     const ChunkHdr h = hdr[q];
     const int n_dw = (h.n_dest + 31) >> 5;
-    const uint32_t* wi = winfo + (h.dest_base >> 5);
+    const uint32_t* wi = winfo + (h.dest_base >> 5) * wstride;
     for (int dw = 0; dw < n_dw; ++dw)
     {
-      const uint32_t info = wi[dw];
+      const uint32_t info = wi[dw * wstride];
       const int m = (int)(info & 0xffu);
       if (m < 2 || m > 32)
         continue;
       uint16_t* list = src + ((h.src_base32 + (info >> 8)) << 5) + lane;
       uint16_t ent[32], outl[32];
       uint32_t rem = 0; // real entries not yet scheduled
+      freq[turn_of_me] = 0;
+      __syncwarp();
       for (int j = 0; j < m; ++j)
       {
         ent[j] = list[j << 5];
         if (ent[j] != zero_slot)
+        {
           rem |= 1u << j;
+          atomicAdd(&freq[ent[j] & 15], 1);
+        }
       }
+      __syncwarp();
       int pads = m - __popc(rem);
       for (int j = 0; j < m; ++j)
       {
@@ -755,16 +791,18 @@ __global__ void __launch_bounds__(256)
           uint32_t mine = used;
           if (turn_of_me == t)
           {
-            int pick = -1;
+            // among the remaining entries on a free bank, the one whose bank is the most crowded in this half warp
+            int pick = -1, best = -1;
             uint32_t r = rem;
             while (r)
             {
               const int k = __ffs(r) - 1;
               r &= r - 1;
-              if (!((used >> (ent[k] & 15)) & 1u))
+              const int b = ent[k] & 15;
+              if (!((used >> b) & 1u) && freq[b] > best)
               {
+                best = freq[b];
                 pick = k;
-                break;
               }
             }
             if (pick < 0 && pads > 0)
@@ -782,13 +820,16 @@ __global__ void __launch_bounds__(256)
               rem &= ~(1u << pick);
               outl[j] = ent[pick];
               mine = used | (1u << (ent[pick] & 15));
+              --freq[ent[pick] & 15];
             }
           }
+          __syncwarp();
           used = __shfl_sync(0xffffffffu, mine, half_base | t);
         }
       }
       for (int j = 0; j < m; ++j)
         list[j << 5] = outl[j];
+      __syncwarp();
     }
   }
   bad = warp_sum(bad);
@@ -946,6 +987,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // shared-memory budget of the lists of one chunk (chunks over budget read their lists from global)
 // destinations of one chunk the two-stage kernel holds in shared memory (typical P1 chunks: 0.22 NS CB)
 constexpr int two_stage_dcap(int ns, int cb) { return (ns * cb * 5 / 16) / 32 * 32; }
+// the same for the lean kernel's two-stage variant (tighter: three 384-cell CTAs per SM)
+constexpr int lean_two_dcap(int ns, int cb) { return (ns * cb * 3 / 10) / 32 * 32; }
+
+// shared memory of the lean kernel with address-ordered write-back
+template <int NS, int CB>
+struct LeanTwoSmem
+{
+  static constexpr int SRC_GROUPS = (NS * CB / 32) * 3 / 2;
+  static constexpr int DCAP = lean_two_dcap(NS, CB);
+  static constexpr int WINFO = DCAP / 32 * 2;
+  static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)NS * (CB + 1) + 2) + 127) / 128 * 128;
+  static constexpr size_t SRC_OFF = E_BYTES;
+  static constexpr size_t WADDR_OFF = SRC_OFF + (size_t)SRC_GROUPS * 64;
+  static constexpr size_t WSRC_OFF = WADDR_OFF + (size_t)DCAP * 2 * 4;
+  static constexpr size_t WINFO_OFF = WSRC_OFF + (size_t)DCAP * 2 * 2;
+  static constexpr size_t SUM_OFF = WINFO_OFF + (((size_t)WINFO * 4 + 15) / 16) * 16;
+  static constexpr size_t BAR_OFF = SUM_OFF + (size_t)DCAP * 8;
+  static constexpr size_t TOTAL = BAR_OFF + 16;
+};
 
 template <int NS, int CB, int DSTRIDE, bool TWO = false>
 struct ChunkSmem
@@ -969,7 +1029,36 @@ struct ChunkSmem
 // arrays - so that each copy addresses ONE state space (LDS / 32-bit addresses in the first) instead of generic loads
 // with 64-bit arithmetic, and with the 4-step loop kept rolled: the classic code is unrolled to 16 steps with a cascade
 // of 8 / 4 / 3 / 2 / 1-step remainders, 132 instructions per destination for lists of ~6 entries.
-template <bool SYM, int THREADS, typename AddrT, int DBG = 0>
+// walk of the two-stage variant: the sum of destination t is left in sums[t] (no addresses needed)
+template <int THREADS, int WS>
+__device__ __forceinline__ void chunk_walk_sums(const uint16_t* __restrict__ srcp, const uint32_t* __restrict__ winfop,
+                                                const double* __restrict__ Es, double* __restrict__ sums, int n_dw)
+{
+  const int lane = threadIdx.x & 31;
+  for (int dw = threadIdx.x >> 5; dw < n_dw; dw += THREADS / 32)
+  {
+    const uint32_t info = winfop[WS * dw];
+    const int m = (int)(info & 0xffu);
+    const uint16_t* p = srcp + ((info >> 8) << 5) + lane;
+    double s0 = 0.0, s1 = 0.0;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 4 <= m; j += 4)
+    {
+      const uint32_t i0 = p[(j + 0) << 5], i1 = p[(j + 1) << 5], i2 = p[(j + 2) << 5], i3 = p[(j + 3) << 5];
+      s0 += Es[i0];
+      s1 += Es[i1];
+      s0 += Es[i2];
+      s1 += Es[i3];
+    }
+#pragma unroll 1
+    for (; j < m; ++j)
+      s0 += Es[p[j << 5]];
+    sums[(dw << 5) + lane] = s0 + s1;
+  }
+}
+
+template <bool SYM, int THREADS, typename AddrT, int DBG = 0, bool MASKED = false>
 __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, const AddrT* __restrict__ destp,
                                            const uint32_t* __restrict__ winfop, const double* __restrict__ Es,
                                            double* __restrict__ values, int n_dest, int n_complete, int n_dw, int overwrite)
@@ -978,13 +1067,13 @@ __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, co
   const int lane = threadIdx.x & 31;
   for (int dw = threadIdx.x >> 5; dw < n_dw; dw += THREADS / 32)
   {
-    const uint32_t info = winfop[dw];
+    const uint32_t info = MASKED ? winfop[2 * dw] : winfop[dw];
     const int m = (int)(info & 0xffu);
     const uint16_t* p = srcp + ((info >> 8) << 5) + lane;
     const int t = (dw << 5) + lane;
     double* dst = values + (int64_t)destp[t * DS];
     double* dst2 = SYM ? values + (int64_t)destp[t * DS + (DS - 1)] : dst;
-    const bool plain = t < n_complete;
+    const bool plain = MASKED ? ((winfop[2 * dw + 1] >> lane) & 1u) != 0u : t < n_complete;
     double old = 0.0, old2 = 0.0;
     if (plain && !overwrite)
     {
@@ -1351,8 +1440,8 @@ struct LeanArgs
   int overwrite;
 };
 
-template <class E, int CB, int DBG = 0>
-__global__ void __launch_bounds__(CB, chunk_min_ctas(CB)) k_matrix_lean(const LeanArgs p)
+template <class E, int CB, int DBG = 0, int OCC = 0, bool MASKED = false>
+__global__ void __launch_bounds__(CB, OCC ? OCC : chunk_min_ctas(CB)) k_matrix_lean(const LeanArgs p)
 {
   constexpr int NX = E::NX, ND = E::ND, NS = ND * (ND + 1) / 2, LD = CB + 1;
   static_assert(E::BS == 1 && NX <= 4 && ND <= 4 && E::WSIZE == 0, "lean kernel: P1-sized scalar elements without coefficients");
@@ -1378,17 +1467,18 @@ __global__ void __launch_bounds__(CB, chunk_min_ctas(CB)) k_matrix_lean(const Le
   const ChunkHdr h = p.hdr[blockIdx.x];
   const int n_dw = (h.n_dest + 31) >> 5;
   const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 256u;
-  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
+  constexpr int WS = MASKED ? 2 : 1; // words per group: (list offset, length) [, completeness mask]
+  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && WS * n_dw <= L::WINFO;
   const uint16_t* g_src = p.src + (h.src_base32 << 5);
   const uint32_t* g_dest = p.dest + h.dest_base * 2;
-  const uint32_t* g_winfo = p.winfo + (h.dest_base >> 5);
+  const uint32_t* g_winfo = p.winfo + (h.dest_base >> 5) * WS;
   if (tid == 0)
   {
     mbar_init(bar, 1);
     Es[NS * LD] = 0.0; // the slot padded list entries point at
     if (fits && n_dw > 0)
     {
-      const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u;
+      const uint32_t winfo_bytes = ((uint32_t)(n_dw * WS) * 4u + 15u) & ~15u;
       mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes);
       bulk_g2s(s_src, g_src, src_bytes, bar);
       bulk_g2s(s_dest, g_dest, dest_bytes, bar);
@@ -1461,9 +1551,143 @@ __global__ void __launch_bounds__(CB, chunk_min_ctas(CB)) k_matrix_lean(const Le
     return;
   }
   if (fits)
-    chunk_walk<true, CB, uint32_t, DBG>(s_src, s_dest, s_winfo, Es, p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
+    chunk_walk<true, CB, uint32_t, DBG, MASKED>(s_src, s_dest, s_winfo, Es, p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
   else
-    chunk_walk<true, CB, uint32_t, DBG>(g_src, g_dest, g_winfo, Es, p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
+    chunk_walk<true, CB, uint32_t, DBG, MASKED>(g_src, g_dest, g_winfo, Es, p.values, h.n_dest, h.n_complete, n_dw, p.overwrite);
+}
+
+// Phase 1 of the lean kernels as a function: table words, the lane's node, shuffles, element matrix -> Es
+template <class E, int CB>
+__device__ __forceinline__ void lean_stage(const LeanArgs& p, double* __restrict__ Es, uint32_t tid, uint32_t slot)
+{
+  constexpr int NX = E::NX, ND = E::ND, LD = CB + 1;
+  const int32_t vtx = __ldg(p.wv_ids + slot);
+  const uint32_t locv = __ldg(p.wv_loc + slot);
+  uint32_t bit = 0, locd = 0;
+  if (p.bits)
+  {
+    const uint32_t dof = (uint32_t)__ldg(p.wd_ids + slot);
+    locd = __ldg(p.wd_loc + slot);
+    bit = (__ldg(p.bits + (dof >> 5)) >> (dof & 31u)) & 1u;
+  }
+  const double* pp = p.x + 3 * (int64_t)vtx;
+  const double px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+  double xc[NX][3];
+#pragma unroll
+  for (int v = 0; v < NX; ++v)
+  {
+    const int l = (int)(locv >> (8 * v));
+    xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+    xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+    xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+  }
+  uint32_t m = 0;
+  if (__any_sync(0xffffffffu, bit))
+  {
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      m |= __shfl_sync(0xffffffffu, bit, (int)(locd >> (8 * i))) << i;
+  }
+  if (slot < p.n)
+  {
+    typename E::Geo g;
+    E::prepare(g, xc, nullptr, p.constants, 0);
+    double* e = Es + tid;
+    if (m == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double row[ND];
+        E::row(g, i, row);
+#pragma unroll
+        for (int j = i; j < ND; ++j)
+          e[(i * ND - i * (i - 1) / 2 + (j - i)) * LD] = row[j];
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double row[ND];
+        E::row(g, i, row);
+#pragma unroll
+        for (int j = i; j < ND; ++j)
+          e[(i * ND - i * (i - 1) / 2 + (j - i)) * LD] = ((m >> i) | (m >> j)) & 1u ? 0.0 : row[j];
+      }
+    }
+  }
+}
+
+// Lean kernel with ADDRESS-ORDERED write-back (plans built with BFX_CHUNKS_TWO_STAGE): the list walk leaves one sum per
+// destination in shared memory, then the chunk's (address, destination) list - both entries of every symmetric pair,
+// sorted by address at plan time, plain stores first, REDs after - is walked by consecutive lanes, so that a warp
+// updates runs of consecutive CSR values (l1tex wavefronts of the scattered updates: 2.9 per cell, r02 ncu capture).
+template <class E, int CB, int WS>
+__global__ void __launch_bounds__(CB, chunk_min_ctas(CB)) k_matrix_lean_two(const LeanArgs p, const uint32_t* __restrict__ wr_addr,
+                                                                             const uint16_t* __restrict__ wr_src)
+{
+  constexpr int ND = E::ND, NS = ND * (ND + 1) / 2, LD = CB + 1;
+  using L = LeanTwoSmem<NS, CB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Es = reinterpret_cast<double*>(smem_raw);
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(smem_raw + L::SRC_OFF);
+  uint32_t* s_waddr = reinterpret_cast<uint32_t*>(smem_raw + L::WADDR_OFF);
+  uint16_t* s_wsrc = reinterpret_cast<uint16_t*>(smem_raw + L::WSRC_OFF);
+  uint32_t* s_winfo = reinterpret_cast<uint32_t*>(smem_raw + L::WINFO_OFF);
+  double* s_sum = reinterpret_cast<double*>(smem_raw + L::SUM_OFF);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+
+  const uint32_t tid = threadIdx.x;
+  const ChunkHdr h = p.hdr[blockIdx.x];
+  const int n_dw = (h.n_dest + 31) >> 5;
+  const uint32_t n_wr = (uint32_t)h.pad, n_wr_pad = (n_wr + 31u) & ~31u;
+  const bool fits = h.n_src32 <= L::SRC_GROUPS && WS * n_dw <= L::WINFO; // (n_dest <= DCAP: checked when the plan was built)
+  const uint16_t* g_src = p.src + (h.src_base32 << 5);
+  const uint32_t* g_winfo = p.winfo + (h.dest_base >> 5) * WS;
+  const uint32_t* g_waddr = wr_addr + h.dest_base * 2;
+  const uint16_t* g_wsrc = wr_src + h.dest_base * 2;
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    Es[NS * LD] = 0.0;
+    if (fits && n_dw > 0)
+    {
+      const uint32_t winfo_bytes = ((uint32_t)(n_dw * WS) * 4u + 15u) & ~15u;
+      mbar_expect_tx(bar, (uint32_t)h.n_src32 * 64u + winfo_bytes + n_wr_pad * 6u);
+      bulk_g2s(s_src, g_src, (uint32_t)h.n_src32 * 64u, bar);
+      bulk_g2s(s_winfo, g_winfo, winfo_bytes, bar);
+      if (n_wr_pad)
+      {
+        bulk_g2s(s_waddr, g_waddr, n_wr_pad * 4u, bar);
+        bulk_g2s(s_wsrc, g_wsrc, n_wr_pad * 2u, bar);
+      }
+    }
+  }
+  lean_stage<E, CB>(p, Es, tid, blockIdx.x * (uint32_t)CB + tid);
+  __syncthreads();
+  if (fits && n_dw > 0)
+    mbar_wait(bar, 0);
+  if (fits)
+    chunk_walk_sums<CB, WS>(s_src, s_winfo, Es, s_sum, n_dw);
+  else
+    chunk_walk_sums<CB, WS>(g_src, g_winfo, Es, s_sum, n_dw);
+  __syncthreads();
+  const uint32_t* wa = fits ? s_waddr : g_waddr;
+  const uint16_t* ws = fits ? s_wsrc : g_wsrc;
+  for (uint32_t t = tid; t < n_wr; t += CB)
+  {
+    const uint32_t sx = ws[t];
+    double* dst = p.values + wa[t];
+    const double v = s_sum[sx & 0x7fffu];
+    if (sx & 0x8000u)
+      red_add(dst, v);
+    else if (p.overwrite)
+      *dst = v;
+    else
+      *dst += v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1683,6 +1907,88 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   }
   ch.wr_addr = c->wr_addr;
   ch.wr_src = c->wr_src;
+  if constexpr (SYM && E::NX <= 4 && E::ND <= 4 && E::BS == 1 && E::WSIZE == 0 && THREADS == CB)
+  {
+    // BFX_CHUNK_KERNEL_LEAN: the instruction-lean kernel (linear staging, complete warp tables, 32-bit addresses)
+    if (c->kernel_variant == BFX_CHUNK_KERNEL_LEAN && c->addr_bytes == 4 && !c->colour && c->tables_complete
+        && P->ncells < 0xffffffffLL - CB && (!a.bc0 || c->wd_ids))
+    {
+      const bool lean_two = c->wr_addr != nullptr;
+      const size_t smem = ChunkSmem<NS, CB, 2>::TOTAL;
+      LeanArgs lp;
+      lp.hdr = c->hdr, lp.winfo = c->winfo, lp.dest = static_cast<const uint32_t*>(c->dest_addr), lp.src = c->src;
+      lp.wv_ids = c->wv_ids, lp.wv_loc = reinterpret_cast<const uint32_t*>(c->wv_loc);
+      lp.wd_ids = c->wd_ids, lp.wd_loc = reinterpret_cast<const uint32_t*>(c->wd_loc);
+      lp.bits = ch.bits0;
+      lp.x = a.x;
+      lp.values = a.values;
+      for (int k = 0; k < 4; ++k)
+        lp.constants[k] = a.constants[k];
+      lp.n = (uint32_t)a.n;
+      lp.overwrite = ch.overwrite;
+      const int dbg = c->lean_dbg;
+      if (lean_two)
+      {
+        using LT = LeanTwoSmem<NS, CB>;
+        if (c->len_sorted)
+        {
+          BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean_two<E, CB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT::TOTAL));
+          k_matrix_lean_two<E, CB, 2><<<(unsigned)c->nchunks, CB, LT::TOTAL, st>>>(lp, c->wr_addr, c->wr_src);
+        }
+        else
+        {
+          BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean_two<E, CB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT::TOTAL));
+          k_matrix_lean_two<E, CB, 1><<<(unsigned)c->nchunks, CB, LT::TOTAL, st>>>(lp, c->wr_addr, c->wr_src);
+        }
+      }
+      else if (dbg == 10) // persistent two-stage pipeline
+      {
+        using L2 = Lean2Smem<NS, CB>;
+        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean2<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2::TOTAL));
+        int per_sm = 0;
+        BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matrix_lean2<E, CB>, CB, L2::TOTAL));
+        const int64_t grid = std::min<int64_t>(c->nchunks, (int64_t)sm_count() * std::max(per_sm, 1));
+        k_matrix_lean2<E, CB><<<(unsigned)grid, CB, L2::TOTAL, st>>>(lp, (uint32_t)c->nchunks);
+      }
+      else if (dbg == 20 && CB == 256) // 5 resident CTAs per SM
+      {
+        if constexpr (CB == 256)
+        {
+          BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB, 0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_matrix_lean<E, CB, 0, 5><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+        }
+      }
+      else if (c->len_sorted)
+      {
+        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_matrix_lean<E, CB, 0, 0, true><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+      }
+      else if (dbg == 0)
+      {
+        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_matrix_lean<E, CB><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+      }
+      else if constexpr (CB == 256 && E::NX == 4)
+      {
+        auto go = [&](auto d)
+        {
+          constexpr int D = decltype(d)::value;
+          cudaFuncSetAttribute(k_matrix_lean<E, CB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k_matrix_lean<E, CB, D><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+        };
+        if (dbg == 1)
+          go(std::integral_constant<int, 1>());
+        else if (dbg == 2)
+          go(std::integral_constant<int, 2>());
+        else
+          go(std::integral_constant<int, 3>());
+      }
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
+  if (c->len_sorted)
+    return fail(BFX_ERR_UNSUPPORTED, "chunk plan ordered by list length (BFX_CHUNKS_LEN_SORT) needs the lean kernel");
   if constexpr (SYM && NS <= 16 && CB == 256)
   {
     if (c->wr_addr) // two-stage plan (32-bit addresses)
@@ -1706,57 +2012,6 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 5><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
-      BFX_CHECK_LAUNCH();
-      return BFX_OK;
-    }
-  }
-  if constexpr (SYM && E::NX <= 4 && E::ND <= 4 && E::BS == 1 && E::WSIZE == 0 && THREADS == CB)
-  {
-    // BFX_CHUNK_KERNEL_LEAN: the instruction-lean kernel (linear staging, complete warp tables, 32-bit addresses)
-    if (c->kernel_variant == BFX_CHUNK_KERNEL_LEAN && c->addr_bytes == 4 && !c->colour && c->tables_complete
-        && P->ncells < 0xffffffffLL - CB && (!a.bc0 || c->wd_ids))
-    {
-      LeanArgs lp;
-      lp.hdr = c->hdr, lp.winfo = c->winfo, lp.dest = static_cast<const uint32_t*>(c->dest_addr), lp.src = c->src;
-      lp.wv_ids = c->wv_ids, lp.wv_loc = reinterpret_cast<const uint32_t*>(c->wv_loc);
-      lp.wd_ids = c->wd_ids, lp.wd_loc = reinterpret_cast<const uint32_t*>(c->wd_loc);
-      lp.bits = ch.bits0;
-      lp.x = a.x;
-      lp.values = a.values;
-      for (int k = 0; k < 4; ++k)
-        lp.constants[k] = a.constants[k];
-      lp.n = (uint32_t)a.n;
-      lp.overwrite = ch.overwrite;
-      const int dbg = c->lean_dbg;
-      if (dbg == 10) // persistent two-stage pipeline
-      {
-        using L2 = Lean2Smem<NS, CB>;
-        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean2<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2::TOTAL));
-        int per_sm = 0;
-        BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_matrix_lean2<E, CB>, CB, L2::TOTAL));
-        const int64_t grid = std::min<int64_t>(c->nchunks, (int64_t)sm_count() * std::max(per_sm, 1));
-        k_matrix_lean2<E, CB><<<(unsigned)grid, CB, L2::TOTAL, st>>>(lp, (uint32_t)c->nchunks);
-      }
-      else if (dbg == 0)
-      {
-        BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_matrix_lean<E, CB><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
-      }
-      else if constexpr (CB == 256 && E::NX == 4)
-      {
-        auto go = [&](auto d)
-        {
-          constexpr int D = decltype(d)::value;
-          cudaFuncSetAttribute(k_matrix_lean<E, CB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          k_matrix_lean<E, CB, D><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
-        };
-        if (dbg == 1)
-          go(std::integral_constant<int, 1>());
-        else if (dbg == 2)
-          go(std::integral_constant<int, 2>());
-        else
-          go(std::integral_constant<int, 3>());
-      }
       BFX_CHECK_LAUNCH();
       return BFX_OK;
     }
@@ -2248,6 +2503,11 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     }
   }
 
+  // the lean kernel's plan options need complete warp tables, symmetric pairs and 32-bit value indices: without
+  // them the plan is built for the classic kernel (bank-coloured staging, destinations sorted by completeness)
+  if (!(c->tables_complete && sym && (uint64_t)csr->nnz * csr->bs0 * csr->bs1 < 0xffffffffull && P->nx <= 4 && P->nd0 <= 4
+        && c->wd_ids))
+    flags &= ~(BFX_CHUNKS_LINEAR_STAGING | BFX_CHUNKS_BANK_ORDER | BFX_CHUNKS_LEN_SORT);
   // ---- scratch of the bit-packed Dirichlet markers (sized by the largest dof the cells reference)
   {
     int32_t* d_max = nullptr;
@@ -2290,7 +2550,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   c->addr_bytes = nvals < 0xffffffffull ? 4 : 8;
   // two-stage write-back: symmetric P1-sized plans of 256-cell chunks with 32-bit addresses whose chunks all keep
   // their destinations within the kernel's shared-memory budget (checked by pass A)
-  bool two = (flags & BFX_CHUNKS_TWO_STAGE) && sym && n2 <= 16 && cb == 256 && c->addr_bytes == 4;
+  const bool lean_plan = (flags & BFX_CHUNKS_LINEAR_STAGING) != 0;
+  bool two = (flags & BFX_CHUNKS_TWO_STAGE) && sym && n2 <= 16 && (cb == 256 || lean_plan) && c->addr_bytes == 4;
   int64_t *ndw = nullptr, *nsrc = nullptr;
   if ((e = dev_alloc(&ndw, (size_t)c->nchunks + 1)) || (e = dev_alloc(&nsrc, (size_t)c->nchunks + 1)))
     return bail(e);
@@ -2316,7 +2577,9 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   p.err = csr->err_flag;
   p.two = two;
   p.pad4 = (flags & BFX_CHUNKS_PAD4) ? 1 : 0;
-  p.dcap = two_stage_dcap(n2, cb);
+  p.len_sort = ((flags & BFX_CHUNKS_LEN_SORT) && lean_plan && sym) ? 1 : 0;
+  c->len_sorted = p.len_sort != 0;
+  p.dcap = lean_plan ? lean_two_dcap(n2, cb) : two_stage_dcap(n2, cb);
   if ((e = run_plan_pass_items(items, false, p, c->nchunks, st)))
     return bail(e);
   {
@@ -2351,7 +2614,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     c->n_dest_pad = tot[0] * 32;
     c->n_src32 = tot[1];
   }
-  if ((e = dev_alloc(&c->hdr, (size_t)c->nchunks)) || (e = dev_alloc(&c->winfo, (size_t)(c->n_dest_pad / 32 + 8)))
+  if ((e = dev_alloc(&c->hdr, (size_t)c->nchunks)) || (e = dev_alloc(&c->winfo, (size_t)(c->n_dest_pad / 32 + 8) * (c->len_sorted ? 2 : 1)))
       || (e = dev_alloc(&c->src, (size_t)c->n_src32 * 32 + 32)))
     return bail(e);
   if (two)
@@ -2383,7 +2646,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     if ((e = dev_alloc(&d_conf, 1)))
       return bail(e);
     BFX_CUDA(cudaMemsetAsync(d_conf, 0, sizeof(unsigned long long), st));
-    k_chunk_bank_order<<<grid_for(c->nchunks, 8, 16), 256, 0, st>>>(c->nchunks, c->hdr, c->winfo, c->src, n2 * (cb + 1), d_conf);
+    k_chunk_bank_order<<<grid_for(c->nchunks, 8, 16), 256, 0, st>>>(c->nchunks, c->hdr, c->winfo, c->src, n2 * (cb + 1),
+                                                                       c->len_sorted ? 2 : 1, d_conf);
     BFX_CHECK_LAUNCH();
     unsigned long long h_conf = 0;
     BFX_CUDA(cudaMemcpyAsync(&h_conf, d_conf, sizeof(h_conf), cudaMemcpyDeviceToHost, st));

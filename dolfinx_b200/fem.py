@@ -413,7 +413,10 @@ CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
 # write-back of the chunk sums in address order (symmetric P1 plans; see BFX_CHUNKS_TWO_STAGE in include/bfx.h)
 # kernel variant of the chunk plans: 0 default, 1 = 5 CTAs per SM (BFX_CHUNK_OCC=5), 2 = "diet" list walk (BFX_CHUNK_DIET=1)
 CHUNK_KERNEL = int(os.environ["BFX_CHUNK_DBG"]) if "BFX_CHUNK_DBG" in os.environ else (2 if os.environ.get("BFX_CHUNK_DIET", "0") != "0" else 1 if os.environ.get("BFX_CHUNK_OCC", "0") == "5" else 0)
-CHUNK_LEAN = os.environ.get("BFX_CHUNK_LEAN", "0") != "0"  # round 2: lean kernel on the linear staging layout
+# lean kernel for the symmetric P1-sized kernels (default): padded linear staging with bank-aware list order,
+# destinations sorted by list length, 384-cell chunks (4 x 4 x 4 cubes of a Kuhn box under the Morton order):
+# C2 launch 2.71 ms against 3.30 ms of the bank-coloured classic kernel (profiles/r02_p1_variants.txt)
+CHUNK_LEAN = os.environ.get("BFX_CHUNK_LEAN", "1") != "0"
 CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padded to multiples of 4 (round-2 experiment)
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
@@ -437,20 +440,23 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
         if want == _lib.ASM_CHUNKED:
             V0, V1 = form.function_spaces
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
-            flags |= _lib.CHUNKS_CB(CHUNKS_CB)
+            lean = CHUNK_LEAN and integ.kernel in _lib.LEAN_KERNELS and (flags & _lib.CHUNKS_SYMMETRIC) and not CHUNKS_TWO_STAGE
+            flags |= _lib.CHUNKS_CB(CHUNKS_CB if CHUNKS_CB else (384 if lean else 0))
             if CHUNKS_PAD4:
                 flags |= _lib.CHUNKS_PAD4
-            if CHUNK_LEAN:
+            if lean:
                 flags |= _lib.CHUNKS_LINEAR_STAGING
                 if os.environ.get("BFX_CHUNKS_BANK_ORDER", "1") != "0":
                     flags |= _lib.CHUNKS_BANK_ORDER
+                if os.environ.get("BFX_CHUNKS_LEN_SORT", "1") != "0":
+                    flags |= _lib.CHUNKS_LEN_SORT
             if CHUNKS_TWO_STAGE:
                 flags |= _lib.CHUNKS_TWO_STAGE | (_lib.CHUNKS_TWO_STAGE_SPLIT if int(CHUNKS_TWO_STAGE) == 2 else 0)
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
-            if st == _lib.OK and (CHUNK_KERNEL or CHUNK_LEAN):
-                _lib.check(_lib.lib.bfx_asm_chunk_set_kernel(plan, 3 if CHUNK_LEAN else CHUNK_KERNEL))
+            if st == _lib.OK and (CHUNK_KERNEL or lean):
+                _lib.check(_lib.lib.bfx_asm_chunk_set_kernel(plan, CHUNK_KERNEL if CHUNK_KERNEL else _lib.CHUNK_KERNEL_LEAN))
         else:
             st = _lib.lib.bfx_asm_build_rowgather(plan, _lib.current_stream())
         if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):

@@ -244,6 +244,9 @@ extern "C"
     BFX_CHUNKS_BANK_ORDER = 64, /* with BFX_CHUNKS_LINEAR_STAGING: order every source list so that the 16 lanes of a half
                                    warp read 16 different shared-memory banks per step where possible (no per-cell
                                    colour bytes, no extra instructions in the kernel) */
+    BFX_CHUNKS_LEN_SORT = 128, /* with BFX_CHUNKS_LINEAR_STAGING on symmetric plans: destinations ordered by list length
+                                  only (less padding of the 32-way interleaved lists); whether a destination is complete
+                                  travels as one bit per lane in the group table; lean kernel only */
     BFX_CHUNKS_PAD4 = 32, /* pad the source lists to multiples of 4 entries (no remainder steps in the list walk) */
     BFX_CHUNKS_TWO_STAGE_SPLIT = 16, /* with BFX_CHUNKS_TWO_STAGE: plain stores first, REDs after, each in address order */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its

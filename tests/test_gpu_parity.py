@@ -109,7 +109,8 @@ def test_chunked_and_atomic_strategies(bfx, oracle, case, symmetric, alt_cb, mon
             if case == "p2":
                 cb = (alt_cb if alt_cb == 96 else 128) if symmetric else 64
             else:
-                cb = alt_cb if alt_cb else 256
+                # symmetric P1-sized plans default to the lean kernel's 384-cell chunks (fem.CHUNK_LEAN)
+                cb = alt_cb if alt_cb else (384 if (symmetric and fem.CHUNK_LEAN and not two_stage) else 256)
             assert nchunks == -(-len(p.dofmap) // cb)
             if case.startswith("p1"):  # (triangles: more destinations per chunk than the two-stage kernel holds)
                 assert fem.chunk_two_stage(a, A) == bool(two_stage and symmetric)
