@@ -107,6 +107,18 @@ struct bfx_rowgather
   double* rec = nullptr;     // per-call cell records (K, |det J|)
   int32_t* na_cells = nullptr;           // per-call list of cells that are not parallelepipeds
   unsigned long long* na_count = nullptr;
+  // block-gather plan (round 2, k_q1_blockgather): tiles of BG_ROWS consecutive block rows; per tile the distinct
+  // incident cells, per CSR block the list of its (cell slot, i, j) contributions, blocks ranked by list length
+  int32_t* bg_cells = nullptr;  // [tile][BG_CCAP]: distinct cells (entity indices) of the tile, ascending
+  void* bg_tiles = nullptr;     // [tile] BGTile header: first block, counts, blocks per contribution level
+  uint16_t* bg_perm = nullptr;  // [tile][BG_NBCAP]: rank -> block in tile | row in tile << 10
+  uint16_t* bg_ent = nullptr;   // [tile][8 BG_INCCAP]: contributions (slot << 6 | i << 3 | j), level-major
+  uint8_t* bg_zcb = nullptr;    // [tile][BG_NBCAP]: per-call Dirichlet mask of every block's column node
+  uint8_t *bg_mask0 = nullptr, *bg_mask1 = nullptr; // per-call Dirichlet masks per node (bit k = component k)
+  int64_t bg_n_nodes = 0;
+  int64_t bg_ntiles = 0;
+  int bg_max_cells = 0, bg_max_blocks = 0, bg_max_inc = 0; // over all tiles (sizes the kernel's shared memory)
+  bool bg_ok = false;
 };
 
 struct bfx_asm

@@ -20,6 +20,7 @@
 // shared between rows): 2x the flops of the cell-parallel kernel, bought back many times by the
 // missing atomics.
 #include "asm_device.cuh"
+#include <algorithm>
 #include "elements.cuh"
 #include <cub/device/device_scan.cuh>
 
@@ -175,6 +176,49 @@ __device__ __forceinline__ void q1_affine_D(int i, int j, const double (&K)[3][3
 #pragma unroll
     for (int b = 0; b < 3; ++b)
       D[p][b] = adet * (K[0][p] * M1[0][b] + K[1][p] * M1[1][b] + K[2][p] * M1[2][b]);
+}
+
+// The same tensor ADDED to A, written for instruction count (block-gather kernel): with s_i[c] = +-1 the sign of
+// d(phi_i)/d(xi_c) and M_m = 1/3 | 1/6 (nodes i, j agree | differ in direction m),
+//   That_ij[c][d] = s_i[c] s_j[d] W[c][d],  W[c][c] = M_{c+1} M_{c+2},  W[c][d] = M_{3-c-d} / 4  (c != d),
+// so D = |det| sum_c K[c][:]^T (sum_d W'[c][d] K[d][:]) with the signs folded into W' by sign-bit flips; 1/3 and 1/6
+// differ in one exponent bit, so M_m costs one integer instruction.  9 + 27 + 27 fp64 operations.
+__device__ __forceinline__ void q1_affine_D_add(int i, int j, const double (&K)[3][3], double adet, double (&A)[3][3])
+{
+  const int e = i ^ j;
+  double M[3];
+  M[0] = __hiloint2double(0x3FD55555 - ((e << 20) & 0x100000), 0x55555555); // 1/3 or 1/6
+  M[1] = __hiloint2double(0x3FD55555 - ((e << 19) & 0x100000), 0x55555555);
+  M[2] = __hiloint2double(0x3FD55555 - ((e << 18) & 0x100000), 0x55555555);
+  const double a0 = adet * M[0], a1 = adet * M[1], aq = 0.25 * adet;
+  double W[3][3];
+  W[0][0] = a1 * M[2];
+  W[1][1] = a0 * M[2];
+  W[2][2] = a0 * M[1];
+  W[0][1] = W[1][0] = aq * M[2];
+  W[0][2] = W[2][0] = 0.25 * a1;
+  W[1][2] = W[2][1] = 0.25 * a0;
+  // signs: s_i[c] s_j[d] = -1 iff bit c of i differs from bit d of j (s = +1 for a set bit)
+  const int si[3] = {(i << 31) & (int)0x80000000, (i << 30) & (int)0x80000000, (i << 29) & (int)0x80000000};
+  const int sj[3] = {(j << 31) & (int)0x80000000, (j << 30) & (int)0x80000000, (j << 29) & (int)0x80000000};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      W[c][d] = __hiloint2double(__double2hiint(W[c][d]) ^ si[c] ^ sj[d], __double2loint(W[c][d]));
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+  {
+    double V[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      V[b] = W[c][0] * K[0][b] + W[c][1] * K[1][b] + W[c][2] * K[2][b];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        A[p][b] = fma(K[c][p], V[b], A[p][b]);
+  }
 }
 
 template <typename PosT>
@@ -341,6 +385,473 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_q1_rowgather(const RGArgs g)
     rs = re;
   }
 }
+
+// =====================================================================================================
+// Block-gather kernel (round 2).  ncu of k_q1_rowgather (profiles/r01_prof_q1_192_rowgather.csv): 17 345 instructions
+// per cell, 160 of 300 shared-memory wavefronts per cell in the 72-byte read-modify-writes of the accumulators, every
+// D_ij recomputed by a lane that shares its row with 7 others behind __syncwarp.  Here ONE THREAD OWNS ONE CSR BLOCK:
+// its 9 accumulators live in registers, it walks the precomputed list of the block's (cell, i, j) contributions (1, 2,
+// 4 or 8 on a structured mesh), reads the cell record (K, |det J|) from the tile's shared-memory copy and applies
+// mu (tr D I + D^T) + lambda D once.  Blocks are ranked by list length at plan time, so the lanes of a warp run the
+// same number of steps.  The finished blocks are written into a shared-memory image of the tile's contiguous value
+// range, which leaves the SM as ONE TMA bulk store (cp.async.bulk.global.shared::cta) - no store instructions, no
+// atomics, every value written once, bitwise reproducible.
+// =====================================================================================================
+constexpr int BG_ROWS = 16;     // block rows per tile
+constexpr int BG_THREADS = 128;
+constexpr int BG_NBCAP = 512;   // blocks per tile the plan accepts (rank and block index travel in 10 bits)
+constexpr int BG_CCAP = 128;    // distinct cells per tile
+constexpr int BG_KMAX = 16;     // contributions per block
+constexpr int BG_INCCAP = 256;  // (row, cell) incidences per tile
+
+// per-tile header of the block-gather plan (64 bytes)
+struct BGTile
+{
+  int64_t b0;             // first block of the tile (row_ptr[r0])
+  int32_t nb, ninc, nuc;  // blocks, (row, cell) incidences, distinct cells
+  int32_t pad;
+  uint16_t nlev[BG_KMAX]; // blocks with more than k contributions
+  int32_t pad2[2];
+};
+static_assert(sizeof(BGTile) == 64, "tile header layout");
+
+struct BGPlanArgs
+{
+  int32_t n_rows;
+  const int64_t* row_ptr;
+  const int64_t* tptr;
+  const uint32_t* tent;
+  const char* pos;
+  int pos_bytes, pos_stride;
+  int32_t* cells;  // [tile][BG_CCAP]
+  uint16_t* perm;  // [tile][BG_NBCAP]
+  uint16_t* ent;   // [tile][8 BG_INCCAP], level-major
+  BGTile* tiles;
+  int* err;     // 1: tile over a capacity
+  int* maxima;  // [0] cells per tile, [1] blocks per tile, [2] (row, cell) incidences per tile
+};
+
+__global__ void __launch_bounds__(BG_THREADS) k_bg_plan(const BGPlanArgs g)
+{
+  __shared__ uint32_t s_cand[BG_INCCAP];
+  __shared__ int32_t s_ucell[BG_CCAP];
+  __shared__ uint8_t s_first[BG_INCCAP];
+  __shared__ uint8_t s_cnt[BG_NBCAP], s_row[BG_NBCAP];
+  __shared__ uint16_t s_ent[BG_NBCAP][BG_KMAX];
+  __shared__ uint16_t s_rank[BG_NBCAP];
+  __shared__ int s_hist[BG_KMAX + 2], s_start[BG_KMAX + 2], s_wsum[BG_THREADS / 32], s_nuc, s_bad;
+  const int tid = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int32_t r0 = (int32_t)(tile * BG_ROWS), r1 = min(r0 + BG_ROWS, g.n_rows);
+  const int64_t b0 = g.row_ptr[r0];
+  const int nb = (int)(g.row_ptr[r1] - b0);
+  const int64_t t0 = g.tptr[r0];
+  const int ninc = (int)(g.tptr[r1] - t0);
+  if (tid == 0)
+  {
+    s_nuc = 0;
+    s_bad = 0;
+  }
+  if (nb > BG_NBCAP || ninc > BG_INCCAP)
+  {
+    if (tid == 0)
+      *g.err = 1;
+    return;
+  }
+  for (int k = tid; k < BG_NBCAP; k += BG_THREADS)
+    s_cnt[k] = 0;
+  for (int k = tid; k < BG_KMAX + 2; k += BG_THREADS)
+    s_hist[k] = 0;
+  for (int k = tid; k < ninc; k += BG_THREADS)
+    s_cand[k] = g.tent[t0 + k] >> 3;
+  __syncthreads();
+  // ---- distinct cells of the tile in ascending entity order
+  for (int k = tid; k < ninc; k += BG_THREADS)
+  {
+    bool first = true;
+    for (int m = 0; m < k && first; ++m)
+      first = s_cand[m] != s_cand[k];
+    s_first[k] = first;
+    if (first)
+      atomicAdd(&s_nuc, 1);
+  }
+  __syncthreads();
+  const int nuc = s_nuc;
+  if (nuc > BG_CCAP)
+  {
+    if (tid == 0)
+      *g.err = 1;
+    return;
+  }
+  for (int k = tid; k < ninc; k += BG_THREADS)
+    if (s_first[k])
+    {
+      int at = 0;
+      for (int m = 0; m < ninc; ++m)
+        at += s_first[m] && s_cand[m] < s_cand[k];
+      s_ucell[at] = (int32_t)s_cand[k];
+    }
+  __syncthreads();
+  // ---- contributions of every block: one thread per row, cells in ascending entity order (fixed summation order)
+  if (tid < r1 - r0)
+  {
+    const int32_t r = r0 + tid;
+    const int rowb = (int)(g.row_ptr[r] - b0);
+    for (int64_t t = g.tptr[r]; t < g.tptr[r + 1]; ++t)
+    {
+      const uint32_t en = g.tent[t];
+      const int64_t e = en >> 3;
+      const int i = (int)(en & 7u);
+      int lo = 0, hi = nuc - 1;
+      while (lo < hi)
+      {
+        const int mid = (lo + hi) >> 1;
+        if (s_ucell[mid] < (int32_t)e)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      const char* prow = g.pos + e * g.pos_stride;
+      for (int j = 0; j < 8; ++j)
+      {
+        const int p = g.pos_bytes == 1 ? (int)reinterpret_cast<const uint8_t*>(prow)[i * 8 + j]
+                                       : (int)reinterpret_cast<const uint16_t*>(prow)[i * 8 + j];
+        const int bidx = rowb + p;
+        const int k = s_cnt[bidx];
+        if (k >= BG_KMAX)
+        {
+          s_bad = 1;
+          continue;
+        }
+        s_ent[bidx][k] = (uint16_t)((lo << 6) | (i << 3) | j);
+        s_cnt[bidx] = (uint8_t)(k + 1);
+      }
+    }
+    for (int b = rowb; b < (int)(g.row_ptr[r + 1] - b0); ++b)
+      s_row[b] = (uint8_t)tid;
+  }
+  __syncthreads();
+  if (s_bad)
+  {
+    if (tid == 0)
+      *g.err = 1;
+    return;
+  }
+  // ---- rank the blocks by list length (descending), stable in the block index
+  for (int b = tid; b < nb; b += BG_THREADS)
+    atomicAdd(&s_hist[s_cnt[b]], 1);
+  __syncthreads();
+  if (tid == 0)
+  {
+    int run = 0;
+    for (int c = BG_KMAX; c >= 0; --c)
+    {
+      s_start[c] = run;
+      run += s_hist[c];
+    }
+  }
+  __syncthreads();
+  {
+    // blocks tid*4 .. tid*4+3; for every length c a block-wide exclusive scan of the flags (cnt == c)
+    const int lane = tid & 31, wib = tid >> 5;
+    for (int c = BG_KMAX; c >= 0; --c)
+    {
+      if (s_hist[c] == 0)
+        continue; // (block-uniform)
+      int mine = 0;
+      for (int u = 0; u < BG_NBCAP / BG_THREADS; ++u)
+      {
+        const int b = tid * (BG_NBCAP / BG_THREADS) + u;
+        mine += b < nb && s_cnt[b] == c;
+      }
+      int incl = mine;
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+          incl += v;
+      }
+      if (lane == 31)
+        s_wsum[wib] = incl;
+      __syncthreads();
+      int base = s_start[c] + incl - mine;
+      for (int w = 0; w < wib; ++w)
+        base += s_wsum[w];
+      for (int u = 0; u < BG_NBCAP / BG_THREADS; ++u)
+      {
+        const int b = tid * (BG_NBCAP / BG_THREADS) + u;
+        if (b < nb && s_cnt[b] == c)
+          s_rank[b] = (uint16_t)base++;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- output (fixed strides per tile: every address of the kernel's prologue follows from the tile index)
+  if (tid == 0)
+  {
+    BGTile h;
+    h.b0 = b0;
+    h.nb = nb, h.ninc = ninc, h.nuc = nuc, h.pad = 0, h.pad2[0] = h.pad2[1] = 0;
+    for (int k = 0; k < BG_KMAX; ++k)
+    {
+      int nk = 0; // blocks with more than k contributions
+      for (int c = k + 1; c <= BG_KMAX; ++c)
+        nk += s_hist[c];
+      h.nlev[k] = (uint16_t)nk;
+    }
+    g.tiles[tile] = h;
+    atomicMax(g.maxima, nuc);
+    atomicMax(g.maxima + 1, nb);
+    atomicMax(g.maxima + 2, ninc);
+  }
+  for (int k = tid; k < nuc; k += BG_THREADS)
+    g.cells[tile * BG_CCAP + k] = s_ucell[k];
+  for (int b = tid; b < nb; b += BG_THREADS)
+  {
+    const int rk = s_rank[b], cnt = s_cnt[b];
+    g.perm[tile * BG_NBCAP + rk] = (uint16_t)(b | ((int)s_row[b] << 10));
+    int off = 0;
+    for (int k = 0; k < cnt; ++k)
+    {
+      g.ent[tile * (8 * BG_INCCAP) + off + rk] = s_ent[b][k];
+      int nk = 0;
+      for (int c = k + 1; c <= BG_KMAX; ++c)
+        nk += s_hist[c];
+      off += nk;
+    }
+  }
+}
+
+// int8 markers of a block-size-3 space -> one byte per node (bit k = component k)
+__global__ void k_bg_node_masks(int64_t n_nodes, const int8_t* __restrict__ bc, uint8_t* __restrict__ mask)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = (uint8_t)((bc[3 * i] ? 1 : 0) | (bc[3 * i + 1] ? 2 : 0) | (bc[3 * i + 2] ? 4 : 0));
+}
+
+struct BGArgs
+{
+  int64_t ntiles;
+  const BGTile* tiles;
+  const int32_t* cells;
+  const uint16_t *perm, *ent;
+  const double* rec;
+  const uint8_t* mask0; // per node: bit k set = component k of the ROW carries a Dirichlet condition (or NULL)
+  const uint8_t* zcb;   // per (tile, block in tile): the same for the block's COLUMN (or NULL)
+  double mu, lmbda;
+  double* values;
+  int dbg; // profiling only: 1 = no contribution loop, 2 = no store
+  int overwrite;
+  int img_cap, cell_cap, inc_cap, nb_cap; // shared-memory layout: image doubles; per stage: cells, incidences, blocks
+};
+
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+
+// per (tile, block): Dirichlet mask of the block's column node (one pass over cols per call, coalesced)
+__global__ void k_bg_block_masks(int64_t ntiles, const BGTile* __restrict__ tiles, const int32_t* __restrict__ cols,
+                                 const uint8_t* __restrict__ mask1, int32_t n_nodes, uint8_t* __restrict__ zcb)
+{
+  const int64_t total = ntiles * BG_NBCAP;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t tile = t / BG_NBCAP;
+    const int b = (int)(t - tile * BG_NBCAP);
+    const BGTile& h = tiles[tile];
+    if (b < h.nb)
+    {
+      const int32_t c = cols[h.b0 + b];
+      zcb[t] = c < n_nodes ? mask1[c] : (uint8_t)0; // (columns beyond the rows' map: ghost columns no cell touches)
+    }
+  }
+}
+
+// Persistent CTAs, two shared-memory stages: while tile T is computed, the lists of the CTA's next tile N arrive by
+// cp.async (their addresses follow from the tile index: fixed strides), the header of the tile after that is on its
+// way, and the cell records of N (second level: they need N's cell ids) are requested after T's contribution loop.
+// One TMA bulk store per tile; two block-wide barriers per tile.
+__global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g)
+{
+  extern __shared__ __align__(16) unsigned char bg_raw[];
+  double* img_base = reinterpret_cast<double*>(bg_raw);
+  BGTile* s_hdr = reinterpret_cast<BGTile*>(bg_raw + sizeof(double) * g.img_cap); // ring of 3
+  unsigned char* stage0 = reinterpret_cast<unsigned char*>(s_hdr + 3);
+  const size_t rec_bytes = (size_t)g.cell_cap * RG_STRIDE * 8, ent_bytes = (size_t)g.inc_cap * 16,
+               perm_bytes = ((size_t)g.nb_cap * 2 + 15) & ~(size_t)15, zc_bytes = ((size_t)g.nb_cap + 15) & ~(size_t)15;
+  const size_t stage_bytes = rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16;
+  const int tid = threadIdx.x;
+  const int64_t G = gridDim.x;
+
+  auto fetch_hdr = [&](int64_t tile, int slot)
+  {
+    if (tid < 4)
+      cp_async16(reinterpret_cast<unsigned char*>(s_hdr + slot) + 16 * tid, reinterpret_cast<const unsigned char*>(g.tiles + tile) + 16 * tid);
+  };
+  // lists of a tile whose header is in shared memory -> stage st; returns this thread's cell id (second-level key)
+  auto fetch_lists = [&](int64_t tile, const BGTile& h, int st) -> int32_t
+  {
+    unsigned char* base = stage0 + (size_t)st * stage_bytes;
+    const uint4* e4 = reinterpret_cast<const uint4*>(g.ent + tile * (8 * BG_INCCAP));
+    for (int k = tid; k < h.ninc; k += BG_THREADS)
+      cp_async16(base + rec_bytes + 16 * (size_t)k, e4 + k);
+    const uint4* p4 = reinterpret_cast<const uint4*>(g.perm + tile * BG_NBCAP);
+    for (int k = tid; k < (h.nb + 7) / 8; k += BG_THREADS)
+      cp_async16(base + rec_bytes + ent_bytes + 16 * (size_t)k, p4 + k);
+    if (g.zcb)
+    {
+      const uint4* z4 = reinterpret_cast<const uint4*>(g.zcb + tile * BG_NBCAP);
+      for (int k = tid; k < (h.nb + 15) / 16; k += BG_THREADS)
+        cp_async16(base + rec_bytes + ent_bytes + perm_bytes + 16 * (size_t)k, z4 + k);
+    }
+    if (g.mask0 && tid == 0)
+      cp_async16(base + rec_bytes + ent_bytes + perm_bytes + zc_bytes, g.mask0 + tile * BG_ROWS);
+    return tid < h.nuc ? __ldg(g.cells + tile * BG_CCAP + tid) : -1;
+  };
+  auto fetch_records = [&](int32_t cid, int st)
+  {
+    if (cid >= 0)
+    {
+      const double2* rp = reinterpret_cast<const double2*>(g.rec) + (int64_t)cid * 5;
+      double2* sp = reinterpret_cast<double2*>(stage0 + (size_t)st * stage_bytes) + tid * 5;
+#pragma unroll
+      for (int w = 0; w < 5; ++w)
+        cp_async16(sp + w, rp + w);
+    }
+  };
+
+  int64_t T = blockIdx.x;
+  if (T >= g.ntiles)
+    return;
+  // ---- prologue: headers of the first two tiles, lists and records of the first
+  fetch_hdr(T, 0);
+  if (T + G < g.ntiles)
+    fetch_hdr(T + G, 1);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  {
+    const int32_t cid = fetch_lists(T, s_hdr[0], 0);
+    fetch_records(cid, 0);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  for (int it = 0; T < g.ntiles; ++it, T += G)
+  {
+    const int st = it & 1;
+    const BGTile& h = s_hdr[it % 3];
+    const int64_t N = T + G, NN = T + 2 * G;
+    // ---- next tile: lists (first level); the tile after it: header
+    int32_t cid_n = -1;
+    if (N < g.ntiles)
+      cid_n = fetch_lists(N, s_hdr[(it + 1) % 3], st ^ 1);
+    if (NN < g.ntiles)
+      fetch_hdr(NN, (it + 2) % 3);
+
+    const unsigned char* base = stage0 + (size_t)st * stage_bytes;
+    const double* s_rec = reinterpret_cast<const double*>(base);
+    const uint16_t* s_ent = reinterpret_cast<const uint16_t*>(base + rec_bytes);
+    const uint16_t* s_perm = reinterpret_cast<const uint16_t*>(base + rec_bytes + ent_bytes);
+    const uint8_t* s_zc = base + rec_bytes + ent_bytes + perm_bytes;
+    const uint8_t* s_zr = s_zc + zc_bytes;
+    const int nb = h.nb;
+    const int64_t b0 = h.b0;
+    // smem element i of the image sits at the same offset modulo 16 bytes as global element b0 * 9 + i
+    const int head = (int)((b0 * 9) & 1);
+    double* img = img_base + head;
+    const bool skip = nb == 0 || (!g.overwrite && h.ninc == 0); // (add mode: no cell of the plan touches the tile)
+    if (!skip)
+    {
+      for (int t = tid; t < nb; t += BG_THREADS)
+      {
+        const uint32_t pmt = s_perm[t];
+        const int bidx = (int)(pmt & 1023u), rowid = (int)(pmt >> 10);
+        double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        int off = 0;
+#pragma unroll 1
+        for (int k = 0; k < BG_KMAX; ++k)
+        {
+          const int nk = h.nlev[k];
+          if (t >= nk || g.dbg == 1)
+            break;
+          const uint32_t en = s_ent[off + t];
+          off += nk;
+          const double2* sp = reinterpret_cast<const double2*>(s_rec + (en >> 6) * RG_STRIDE);
+          const double2 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3], q4 = sp[4];
+          if (q4.y >= 0.0)
+          {
+            const double K[3][3] = {{q0.x, q0.y, q1.x}, {q1.y, q2.x, q2.y}, {q3.x, q3.y, q4.x}};
+            q1_affine_D_add((int)((en >> 3) & 7u), (int)(en & 7u), K, q4.y, A);
+          }
+        }
+        const unsigned zr = g.mask0 ? s_zr[rowid] : 0u, zc = g.zcb ? s_zc[bidx] : 0u;
+        const double tr = A[0][0] + A[1][1] + A[2][2];
+        double* o = img + bidx * 9;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int l = 0; l < 3; ++l)
+          {
+            const double v = g.mu * ((k == l ? tr : 0.0) + A[l][k]) + g.lmbda * A[k][l];
+            o[3 * k + l] = (((zr >> k) | (zc >> l)) & 1u) ? 0.0 : v;
+          }
+      }
+    }
+    // ---- next tile: cell records (second level; the ids were requested before the contribution loop)
+    fetch_records(cid_n, st ^ 1);
+    double* out = g.values + b0 * 9;
+    const int total = nb * 9;
+    if (g.overwrite)
+    {
+      // generic-proxy writes of the image -> visible to the async proxy, then one bulk store of the aligned part
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0 && !skip)
+      {
+        if (head)
+          out[0] = img[0];
+        const int nbulk = g.dbg == 2 ? 0 : (total - head) & ~1;
+        if (nbulk > 0)
+        {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + head),
+                       "r"((uint32_t)__cvta_generic_to_shared(img + head)), "r"((uint32_t)nbulk * 8u)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (total - head - nbulk)
+          out[total - 1] = img[total - 1];
+      }
+    }
+    else
+    {
+      __syncthreads();
+      if (!skip)
+        for (int t0i = tid; t0i < total; t0i += 8 * BG_THREADS)
+        {
+          double old[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+          {
+            const int t = t0i + u * BG_THREADS;
+            old[u] = t < total ? out[t] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+          {
+            const int t = t0i + u * BG_THREADS;
+            if (t < total)
+              out[t] = old[u] + img[t];
+          }
+        }
+    }
+    // ---- the next tile's data has landed, the image may be overwritten
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (tid == 0)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+  }
+}
 } // namespace
 
 namespace bfx
@@ -354,6 +865,13 @@ void free_rowgather(bfx_rowgather* g)
   cudaFree(g->rec);
   cudaFree(g->na_cells);
   cudaFree(g->na_count);
+  cudaFree(g->bg_cells);
+  cudaFree(g->bg_tiles);
+  cudaFree(g->bg_perm);
+  cudaFree(g->bg_ent);
+  cudaFree(g->bg_zcb);
+  cudaFree(g->bg_mask0);
+  cudaFree(g->bg_mask1);
   delete g;
 }
 
@@ -370,6 +888,59 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
   if (P->ncells > 0)
     k_rg_records<<<grid_for(P->ncells, 128, 0), 128, 0, st>>>(P->ncells, P->cells, P->x_dofmap, a.x, G->rec, G->na_cells,
                                                                G->na_count);
+  if (G->bg_ok && !getenv("BFX_ROWGATHER_V1")) // block-gather kernel (default); the round-1 kernel stays for A/B runs
+  {
+    BGArgs b;
+    b.ntiles = G->bg_ntiles;
+    b.tiles = static_cast<const BGTile*>(G->bg_tiles);
+    b.cells = G->bg_cells, b.perm = G->bg_perm, b.ent = G->bg_ent;
+    b.rec = G->rec;
+    b.mask0 = nullptr;
+    b.zcb = nullptr;
+    if (a.bc0)
+    {
+      k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc0, G->bg_mask0);
+      b.mask0 = G->bg_mask0;
+    }
+    if (a.bc1)
+    {
+      const uint8_t* m1 = G->bg_mask0;
+      if (a.bc1 != a.bc0)
+      {
+        k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc1, G->bg_mask1);
+        m1 = G->bg_mask1;
+      }
+      k_bg_block_masks<<<grid_for(G->bg_ntiles * BG_NBCAP, 256, 16), 256, 0, st>>>(G->bg_ntiles, static_cast<const BGTile*>(G->bg_tiles), csr->cols, m1,
+                                                                                (int32_t)G->bg_n_nodes, G->bg_zcb);
+      b.zcb = G->bg_zcb;
+    }
+    b.mu = a.constants[0], b.lmbda = a.constants[1];
+    b.values = a.values;
+    b.overwrite = values_mode == BFX_VALUES_OVERWRITE;
+    b.dbg = getenv("BFX_BG_DBG") ? atoi(getenv("BFX_BG_DBG")) : 0;
+    b.img_cap = (G->bg_max_blocks * 9 + 3) & ~1;
+    b.cell_cap = G->bg_max_cells;
+    b.inc_cap = G->bg_max_inc;
+    b.nb_cap = G->bg_max_blocks;
+    const size_t stage = (size_t)b.cell_cap * RG_STRIDE * 8 + (size_t)b.inc_cap * 16 + (((size_t)b.nb_cap * 2 + 15) & ~(size_t)15)
+                         + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16;
+    const size_t smem = sizeof(double) * (size_t)b.img_cap + 3 * sizeof(BGTile) + 2 * stage;
+    if (G->bg_ntiles > 0)
+    {
+      BFX_CUDA(cudaFuncSetAttribute(k_q1_blockgather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_q1_blockgather, BG_THREADS, smem));
+      const int64_t grid = std::min<int64_t>(G->bg_ntiles, (int64_t)sm_count() * std::max(per_sm, 1));
+      k_q1_blockgather<<<(unsigned)grid, BG_THREADS, smem, st>>>(b);
+    }
+    BFX_CHECK_LAUNCH();
+    AsmArgs nb = a;
+    nb.cells = G->na_cells;
+    nb.n = P->ncells;
+    nb.n_dev = G->na_count;
+    nb.pos = nullptr;
+    return launch_q1_red(P, nb, st);
+  }
   RGArgs g;
   g.n_rows = csr->n_rows_all;
   g.row_ptr = csr->row_ptr;
@@ -476,6 +1047,46 @@ int bfx_asm_build_rowgather(bfx_asm_t* P, bfx_stream_t stream)
     BFX_CHECK_LAUNCH();
     BFX_CUDA(cudaStreamSynchronize(st));
     cudaFree(cursor);
+  }
+  // ---- block-gather plan (tiles of BG_ROWS rows); a tile over a capacity keeps the round-1 kernel
+  if (n > 0 && n_rows > 0)
+  {
+    const int64_t ntiles = ((int64_t)n_rows + BG_ROWS - 1) / BG_ROWS;
+    int *d_err = nullptr, *d_max = nullptr;
+    if ((e = dev_alloc(&G->bg_cells, (size_t)ntiles * BG_CCAP)) || (e = dev_alloc(reinterpret_cast<BGTile**>(&G->bg_tiles), (size_t)ntiles))
+        || (e = dev_alloc(&G->bg_perm, (size_t)ntiles * BG_NBCAP)) || (e = dev_alloc(&G->bg_ent, (size_t)ntiles * 8 * BG_INCCAP))
+        || (e = dev_alloc(&G->bg_zcb, (size_t)ntiles * BG_NBCAP)) || (e = dev_alloc(&d_err, 1)) || (e = dev_alloc(&d_max, 3)))
+      return bail(e);
+    BFX_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    BFX_CUDA(cudaMemsetAsync(d_max, 0, 3 * sizeof(int), st));
+    BGPlanArgs b;
+    b.n_rows = n_rows;
+    b.row_ptr = csr->row_ptr;
+    b.tptr = G->tptr;
+    b.tent = G->tent;
+    b.pos = P->pos;
+    b.pos_bytes = P->pos_bytes;
+    b.pos_stride = P->pos_stride;
+    b.cells = G->bg_cells, b.perm = G->bg_perm, b.ent = G->bg_ent, b.tiles = static_cast<BGTile*>(G->bg_tiles);
+    b.err = d_err;
+    b.maxima = d_max;
+    k_bg_plan<<<(unsigned)ntiles, BG_THREADS, 0, st>>>(b);
+    BFX_CHECK_LAUNCH();
+    int h_err = 0, h_max[3] = {0, 0, 0};
+    BFX_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+    BFX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_err);
+    cudaFree(d_max);
+    // per-call scratch of the Dirichlet node masks (rows and columns share the node numbering: one dofmap)
+    G->bg_n_nodes = n_rows;
+    if ((e = dev_alloc(&G->bg_mask0, (size_t)n_rows + 2 * BG_ROWS)) || (e = dev_alloc(&G->bg_mask1, (size_t)n_rows + 2 * BG_ROWS)))
+      return bail(e);
+    G->bg_ntiles = ntiles;
+    G->bg_max_cells = h_max[0];
+    G->bg_max_blocks = h_max[1];
+    G->bg_max_inc = h_max[2];
+    G->bg_ok = h_err == 0;
   }
   P->rowgather = G;
   return BFX_OK;
