@@ -51,6 +51,8 @@ ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
 # linear-form kernels with the grouped (one RED per distinct dof of 32 cells) variant
 GROUPED_VECTOR_KERNELS = frozenset({1, 3, 7, 15})
+CHUNKED_VECTOR_KERNELS = frozenset({1, 3, 7, 9, 11, 15, 16})
+CHUNKED_VECTOR_DEFAULT = frozenset({9, 16})  # where it measures faster than the RED kernel (P2 tetrahedra)  # linear-form kernels with a chunk-aggregated variant
 ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)
@@ -126,6 +128,7 @@ _SIGS = {
     "bfx_asm_build_chunks": ([vp, vp, ci, vp], ci),
     "bfx_asm_build_rowgather": ([vp, vp], ci),
     "bfx_asm_build_groups": ([vp, vp, vp], ci),
+    "bfx_asm_build_chunks_vector": ([vp, vp, ci, vp], ci),
     "bfx_asm_chunk_bank_conflicts": ([vp, C.POINTER(i64)], ci),
     "bfx_asm_chunk_two_stage": ([vp, C.POINTER(ci)], ci),
     "bfx_asm_chunk_set_kernel": ([vp, ci], ci),

@@ -74,6 +74,7 @@ struct bfx_chunks
   // colour[c][k]; the colours make the 16 lanes of every list step hit 16 different 8-byte banks
   uint8_t* colour = nullptr;  // ns (padded to a multiple of 4) bytes per cell slot, or NULL (padded linear layout)
   int64_t n_bank_conflicts = 0; // list reads the colouring could not make conflict free (diagnostic)
+  bool vector_plan = false;     // chunk plan of a linear form (bfx_asm_build_chunks_vector)
   bool len_sorted = false;      // BFX_CHUNKS_LEN_SORT: winfo holds (info, completeness mask) pairs
   bool bank_ordered = false;    // BFX_CHUNKS_BANK_ORDER: the lists of the linear layout are ordered bank-aware
   int32_t* perm = nullptr;    // locality ordering of the plan's cell list (or NULL)
@@ -159,6 +160,7 @@ int chunked_supported(int kernel_id);
 int launch_chunked(const bfx_asm* P, int kernel_id, const AsmArgs& a, int values_mode, cudaStream_t st);
 void free_chunks(bfx_chunks* c);
 int grouped_vector_supported(int kernel_id);
+int chunked_vector_cells(int kernel_id);
 int launch_vector_grouped(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st);
 // rowgather.cu
 int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st);

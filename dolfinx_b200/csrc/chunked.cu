@@ -907,6 +907,12 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+__global__ void k_iota64(int64_t n, int64_t* __restrict__ out)
+{
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = t;
+}
+
 __global__ void k_count_zero_bytes(int64_t n, const uint8_t* __restrict__ v, unsigned long long* __restrict__ out)
 {
   unsigned long long z = 0;
@@ -950,6 +956,7 @@ struct ChunkArgs
   int overwrite;
   const uint32_t* wr_addr;        // two-stage write-back lists (see ChunkBuildArgs) or NULL
   const uint16_t* wr_src;
+  int tables_complete;            // every group of 32 cells has its node (and dof) table: no per-group count loads
 };
 
 // ---- TMA bulk copy + mbarrier (one chunk's lists are contiguous: two bulk copies per CTA) -----------
@@ -1907,6 +1914,7 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   }
   ch.wr_addr = c->wr_addr;
   ch.wr_src = c->wr_src;
+  ch.tables_complete = 0;
   if constexpr (SYM && E::NX <= 4 && E::ND <= 4 && E::BS == 1 && E::WSIZE == 0 && THREADS == CB)
   {
     // BFX_CHUNK_KERNEL_LEAN: the instruction-lean kernel (linear staging, complete warp tables, 32-bit addresses)
@@ -2308,6 +2316,172 @@ __global__ void __launch_bounds__(256) k_vector_grouped(const AsmArgs a, const C
   }
 }
 
+// Chunk-aggregated VECTOR assembly (fem::impl::assemble_cells, fem/assemble_vector_impl.h:72-116): the matrix
+// machinery on a vector - element vectors staged in shared memory per chunk of CB cells, one sum per distinct
+// (dof, component) of the chunk through the plan's source lists, a plain load/add/store for the dofs whose cells all
+// lie in the chunk and ONE RED per chunk-boundary dof (the cell-parallel kernel issues one RED per (cell, local dof)).
+// The plan is the chunk plan of an identity "matrix" (row = dof, one column): bfx_asm_build_chunks_vector.
+template <class E, int CB, typename AddrT>
+__global__ void __launch_bounds__(CB, (E::ND * E::BS > 16) ? 1 : chunk_min_ctas(CB)) k_vector_chunked(const AsmArgs a, const ChunkArgs ch)
+{
+  constexpr int NX = E::NX, ND = E::ND, N = ND * E::BS, LD = CB + 1;
+  using L = ChunkSmem<N, CB, 1>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Es = reinterpret_cast<double*>(smem_raw);
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(smem_raw + L::SRC_OFF);
+  AddrT* s_dest = reinterpret_cast<AddrT*>(smem_raw + L::DEST_OFF);
+  uint32_t* s_winfo = reinterpret_cast<uint32_t*>(smem_raw + L::WINFO_OFF);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t q = blockIdx.x;
+  const int64_t slot = q * CB + tid;
+  const int64_t gw = slot >> 5;
+  // ---- first-level loads
+  const int vcnt = (ch.tables_complete && NX <= 4) ? 32 : (ch.wv_cnt ? ch.wv_cnt[gw] : 0);
+  const int32_t vtx = vcnt ? __ldg(ch.wv_ids + slot) : 0;
+  const uint32_t locv = (vcnt && NX <= 4) ? __ldg(reinterpret_cast<const uint32_t*>(ch.wv_loc) + slot) : 0u;
+  // coefficient on the plan's own dofmap (P1-sized scalar elements): through the dof table, like the coordinates
+  constexpr bool DOF_TAB = E::WSIZE > 0 && E::WND == ND && E::WBS == 1 && E::BS == 1 && ND <= 4;
+  int dcnt = 0;
+  int32_t dof = 0;
+  uint32_t locd = 0;
+  if constexpr (DOF_TAB)
+  {
+    if (ch.wd_cnt && !a.coef.packed && a.coef.f[0].dm == a.dofmap0)
+    {
+      dcnt = ch.tables_complete ? 32 : ch.wd_cnt[gw];
+      if (dcnt)
+      {
+        dof = __ldg(ch.wd_ids + slot);
+        locd = __ldg(reinterpret_cast<const uint32_t*>(ch.wd_loc) + slot);
+      }
+    }
+  }
+  const ChunkHdr h = ch.hdr[q];
+  const int n_dw = (h.n_dest + 31) >> 5;
+  const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 32u * (uint32_t)sizeof(AddrT);
+  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
+  const uint16_t* g_src = ch.src + (h.src_base32 << 5);
+  const AddrT* g_dest = static_cast<const AddrT*>(ch.dest_addr) + h.dest_base;
+  const uint32_t* g_winfo = ch.winfo + (h.dest_base >> 5);
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    Es[N * LD] = 0.0;
+    if (fits && n_dw > 0)
+    {
+      const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u;
+      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes);
+      bulk_g2s(s_src, g_src, src_bytes, bar);
+      bulk_g2s(s_dest, g_dest, dest_bytes, bar);
+      bulk_g2s(s_winfo, g_winfo, winfo_bytes, bar);
+    }
+  }
+  const bool active = slot < a.n;
+  int64_t e = slot;
+  int32_t cell = (int32_t)slot;
+  const bool need_cell = !(vcnt && NX <= 4) || (E::WSIZE > 0 && !dcnt); // direct gathers index the caller's arrays
+  if (active && need_cell && (ch.perm || a.cells))
+  {
+    e = ch.perm ? ch.perm[slot] : slot;
+    cell = a.cells ? a.cells[e] : (int32_t)e;
+  }
+  // ---- coordinates
+  double xc[NX][3];
+  if (vcnt && NX <= 4) // warp-uniform
+  {
+    const double* pp = a.x + 3 * (int64_t)vtx;
+    const double px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+#pragma unroll
+    for (int v = 0; v < NX; ++v)
+    {
+      const int l = (int)(locv >> (8 * (v & 3)));
+      xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+      xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+      xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+    }
+  }
+  else if (active)
+  {
+    int32_t xd[NX];
+    load_ints<NX>(ch.xdm ? ch.xdm + slot * NX : a.x_dofmap + (int64_t)cell * NX, xd);
+    gather_coords<NX>(a.x, xd, xc);
+  }
+  // ---- coefficient
+  double w[E::WSIZE > 0 ? E::WSIZE : 1];
+  if constexpr (E::WSIZE > 0)
+  {
+    bool done = false;
+    if constexpr (DOF_TAB)
+    {
+      if (dcnt) // warp-uniform
+      {
+        const double fv = __ldg(a.coef.f[0].v + dof);
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+          w[i] = __shfl_sync(0xffffffffu, fv, (int)(locd >> (8 * i)));
+        done = true;
+      }
+    }
+    if (!done && active)
+      load_w<E>(a, e, cell, w);
+  }
+  if (active)
+  {
+    typename E::Geo g;
+    E::prepare(g, xc, w, a.constants, 0);
+    double out[N];
+    E::vec(g, out);
+    double* es = Es + tid;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      es[k * LD] = out[k];
+  }
+  __syncthreads();
+  if (fits && n_dw > 0)
+    mbar_wait(bar, 0);
+  if (fits)
+    chunk_walk<false, CB, AddrT>(s_src, s_dest, s_winfo, Es, a.b, h.n_dest, h.n_complete, n_dw, 0);
+  else
+    chunk_walk<false, CB, AddrT>(g_src, g_dest, g_winfo, Es, a.b, h.n_dest, h.n_complete, n_dw, 0);
+  (void)lane;
+}
+
+template <class E>
+int launch_vector_chunked_e(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
+{
+  constexpr int N = E::ND * E::BS;
+  constexpr int CB = N <= 10 ? 384 : 256;
+  const bfx_chunks* c = P->chunks;
+  if (a.n == 0)
+    return BFX_OK;
+  if (!c->vector_plan || c->cb != CB || c->n2 != N || c->colour || c->sym)
+    return fail(BFX_ERR_INVALID, "vector chunk plan (cb=%d, staged=%d) does not match the kernel (cb=%d, staged=%d)", c->cb,
+                c->n2, CB, N);
+  ChunkArgs ch;
+  memset(&ch, 0, sizeof(ch));
+  ch.hdr = c->hdr, ch.winfo = c->winfo, ch.dest_addr = c->dest_addr, ch.src = c->src;
+  ch.perm = c->perm;
+  ch.xdm = c->xdm, ch.dm0 = c->dm0;
+  ch.wv_ids = c->wv_ids, ch.wv_cnt = c->wv_cnt, ch.wv_loc = c->wv_loc;
+  ch.wd_ids = c->wd_ids, ch.wd_cnt = c->wd_cnt, ch.wd_loc = c->wd_loc;
+  ch.tables_complete = c->tables_complete && (P->nd0 > 4 || c->wd_ids);
+  const size_t smem = ChunkSmem<N, CB, 1>::TOTAL;
+  if (c->addr_bytes == 4)
+  {
+    BFX_CUDA(cudaFuncSetAttribute(k_vector_chunked<E, CB, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_vector_chunked<E, CB, uint32_t><<<(unsigned)c->nchunks, CB, smem, st>>>(a, ch);
+  }
+  else
+  {
+    BFX_CUDA(cudaFuncSetAttribute(k_vector_chunked<E, CB, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_vector_chunked<E, CB, uint64_t><<<(unsigned)c->nchunks, CB, smem, st>>>(a, ch);
+  }
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
 template <class E>
 int launch_vector_grouped_e(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
 {
@@ -2368,8 +2542,38 @@ int grouped_vector_supported(int kernel_id)
   }
 }
 
+int chunked_vector_cells(int kernel_id)
+{
+  // cells per chunk of the chunk-aggregated vector kernel of a linear-form kernel, 0 = none
+  switch (kernel_id)
+  {
+  case BFX_K_SOURCE_P1_TRI_L:
+  case BFX_K_LOAD_COEFF_P1_TRI_L:
+  case BFX_K_LOAD_P1_TET_L:
+  case BFX_K_LOAD_P2_TET_L:
+  case BFX_K_ACTION_POISSON_P1_TET_L:
+  case BFX_K_ACTION_POISSON_P2_TET_L: return 384;
+  case BFX_K_LOAD_Q1_HEX_L: return 256;
+  default: return 0;
+  }
+}
+
 int launch_vector_grouped(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st)
 {
+  if (P->chunks && P->chunks->vector_plan)
+  {
+    switch (kernel_id)
+    {
+    case BFX_K_SOURCE_P1_TRI_L: return launch_vector_chunked_e<el::SourceP1Tri>(P, a, st);
+    case BFX_K_LOAD_COEFF_P1_TRI_L: return launch_vector_chunked_e<el::LoadCoeffP1Tri>(P, a, st);
+    case BFX_K_LOAD_P1_TET_L: return launch_vector_chunked_e<el::LoadP1Tet>(P, a, st);
+    case BFX_K_LOAD_P2_TET_L: return launch_vector_chunked_e<el::LoadP2Tet>(P, a, st);
+    case BFX_K_LOAD_Q1_HEX_L: return launch_vector_chunked_e<el::LoadQ1Hex>(P, a, st);
+    case BFX_K_ACTION_POISSON_P1_TET_L: return launch_vector_chunked_e<el::ActionOf<el::PoissonP1Tet>>(P, a, st);
+    case BFX_K_ACTION_POISSON_P2_TET_L: return launch_vector_chunked_e<el::ActionOf<el::PoissonP2Tet>>(P, a, st);
+    default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d has no chunk-aggregated vector variant", kernel_id);
+    }
+  }
   if (!P->chunks || !P->chunks->glist)
     return fail(BFX_ERR_INVALID, "grouped vector assembly needs bfx_asm_build_groups() on the plan first");
   switch (kernel_id)
@@ -2423,7 +2627,7 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     return fail(BFX_ERR_UNSUPPORTED, "symmetric chunk plan needs block size 1 and one dofmap for rows and columns");
   const int n2 = sym ? staged_per_cell(P->nd0, true) : P->nd0 * csr->bs0 * P->nd1 * csr->bs1; // staged per cell
   const int cb_req = ((flags >> 8) & 0xff) * 32; // BFX_CHUNKS_CB(cells); 0 = the element's default
-  const int cb = (cb_req && chunk_cb_supported(n2, cb_req)) ? cb_req : chunk_cb(n2); // not instantiated: default
+  const int cb = (cb_req && (chunk_cb_supported(n2, cb_req) || (flags & BFX_CHUNKS_VECTOR))) ? cb_req : chunk_cb(n2); // not instantiated: default
   if (cb == 0 || P->ncells == 0)
     return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d staged scalars are not supported", n2);
   const int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
@@ -2505,9 +2709,12 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
 
   // the lean kernel's plan options need complete warp tables, symmetric pairs and 32-bit value indices: without
   // them the plan is built for the classic kernel (bank-coloured staging, destinations sorted by completeness)
-  if (!(c->tables_complete && sym && (uint64_t)csr->nnz * csr->bs0 * csr->bs1 < 0xffffffffull && P->nx <= 4 && P->nd0 <= 4
-        && c->wd_ids))
+  if (flags & BFX_CHUNKS_VECTOR)
+    flags &= ~BFX_CHUNKS_LEN_SORT; // (the vector kernel runs on the padded linear layout with any tables)
+  else if (!(c->tables_complete && sym && (uint64_t)csr->nnz * csr->bs0 * csr->bs1 < 0xffffffffull && P->nx <= 4 && P->nd0 <= 4
+             && c->wd_ids))
     flags &= ~(BFX_CHUNKS_LINEAR_STAGING | BFX_CHUNKS_BANK_ORDER | BFX_CHUNKS_LEN_SORT);
+  c->vector_plan = (flags & BFX_CHUNKS_VECTOR) != 0;
   // ---- scratch of the bit-packed Dirichlet markers (sized by the largest dof the cells reference)
   {
     int32_t* d_max = nullptr;
@@ -2716,6 +2923,52 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   cudaFree(nsrc);
   P->chunks = c;
   return BFX_OK;
+}
+
+int bfx_asm_build_chunks_vector(bfx_asm_t* P, const double* x_dev, int kernel_id, bfx_stream_t stream)
+{
+  BFX_REQUIRE(P && !P->csr, "bfx_asm_build_chunks_vector: needs the plan of a linear form");
+  const int cb = chunked_vector_cells(kernel_id);
+  bfx_kernel_info_t info;
+  if (cb == 0 || bfx_kernel_info(kernel_id, &info) != BFX_OK)
+    return fail(BFX_ERR_UNSUPPORTED, "kernel id %d has no chunk-aggregated vector variant", kernel_id);
+  if (P->ncells == 0)
+    return fail(BFX_ERR_UNSUPPORTED, "chunk plan of an empty cell list");
+  cudaStream_t st = S(stream);
+  // the chunk plan of an identity "matrix": row = dof, one column, position 0 - the value index of (cell, i, a) is
+  // bs * dofmap(cell, i) + a, which is exactly where assemble_cells adds be[bs * i + a]
+  const int64_t n = (int64_t)P->n_rows_all;
+  bfx_csr fake;
+  fake.n_rows_all = fake.n_rows_owned = P->n_rows_all;
+  fake.bs0 = info.bs;
+  fake.bs1 = 1;
+  fake.nnz = fake.nnz_owned = n;
+  char* zeros = nullptr;
+  int e = BFX_OK;
+  if ((e = dev_alloc(&fake.row_ptr, (size_t)n + 1)) || (e = dev_alloc(&fake.err_flag, 1)) || (e = dev_alloc(&zeros, 64)))
+  {
+    cudaFree(fake.row_ptr);
+    cudaFree(fake.err_flag);
+    return e;
+  }
+  k_iota64<<<grid_for(n + 1, 256, 16), 256, 0, st>>>(n + 1, fake.row_ptr);
+  BFX_CUDA(cudaMemsetAsync(fake.err_flag, 0, sizeof(int), st));
+  BFX_CUDA(cudaMemsetAsync(zeros, 0, 64, st));
+  const int nd1_saved = P->nd1;
+  P->csr = &fake;
+  P->pos = zeros;
+  P->pos_stride = 0;
+  P->pos_bytes = 1;
+  P->nd1 = 1;
+  e = bfx_asm_build_chunks(P, x_dev, BFX_CHUNKS_VECTOR | BFX_CHUNKS_LINEAR_STAGING | BFX_CHUNKS_BANK_ORDER | BFX_CHUNKS_CB(cb), stream);
+  P->csr = nullptr;
+  P->pos = nullptr;
+  P->nd1 = nd1_saved;
+  cudaStreamSynchronize(st);
+  cudaFree(fake.row_ptr);
+  cudaFree(fake.err_flag);
+  cudaFree(zeros);
+  return e;
 }
 
 int bfx_asm_build_groups(bfx_asm_t* P, const double* x_dev, bfx_stream_t stream)

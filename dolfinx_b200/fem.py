@@ -407,6 +407,11 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
 # grouped vector assembly (one RED per distinct dof of 32 cells) is opt-in: on B200 it measures 2.6 ms against
 # 2.1 ms of the cell-parallel kernel for the C2 load vector (both are bound by the L1/LSU pipe, not by the REDs)
 GROUPED_VECTORS = os.environ.get("BFX_GROUPED_VECTORS", "0") != "0"
+# chunk-aggregated vector assembly (round 2): one RED per chunk-boundary dof instead of one per (cell, local dof)
+# measured at C2 / C3 / C4 (profiles/r02_vector_variants.txt): it wins for the P2 kernels (0.53 against 0.62 ms) and loses for
+# the P1 / Q1 load vectors (2.44 against 2.08 ms, 3.65 against 2.65 ms), so only the P2 kernels take it by default
+CHUNKED_VECTORS = os.environ.get("BFX_CHUNKED_VECTORS", "1") != "0"
+CHUNKED_VECTORS_ALL = os.environ.get("BFX_CHUNKED_VECTORS", "1") == "all"
 CHUNKS_SYMMETRIC = os.environ.get("BFX_CHUNKS_SYMMETRIC", "1") != "0"
 # cells per chunk: 0 = the element's default (256 P1 / 128 P2); 96, 128, 192, 384 (P1) or 64, 96 (symmetric P2)
 CHUNKS_CB = int(os.environ.get("BFX_CHUNKS_CB", "0"))
@@ -701,7 +706,18 @@ def assemble_vector(b, L: Form, constants=None, coeffs=None):
         cf = _coeffs_for(L, integ, None if coeffs is None else coeffs[(itype, ident)])
         if itype == IntegralType.cell:
             strat = _lib.ASM_ATOMIC
-            if integ.kernel in _lib.GROUPED_VECTOR_KERNELS and GROUPED_VECTORS:
+            if (integ.kernel in (_lib.CHUNKED_VECTOR_KERNELS if CHUNKED_VECTORS_ALL else _lib.CHUNKED_VECTOR_DEFAULT)
+                    and CHUNKED_VECTORS and not GROUPED_VECTORS):
+                # element vectors summed per chunk of 256 / 384 cells on the SM (plan built once, on first use)
+                key = ("vchunks", plan.value)
+                if key not in L._plans:
+                    st = _lib.lib.bfx_asm_build_chunks_vector(plan, L.mesh.x.data_ptr(), integ.kernel, _lib.current_stream())
+                    if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):
+                        _lib.check(st)
+                    L._plans[key] = st == _lib.OK
+                if L._plans[key]:
+                    strat = _lib.ASM_CHUNKED
+            elif integ.kernel in _lib.GROUPED_VECTOR_KERNELS and GROUPED_VECTORS:
                 # one RED per distinct dof of a group of 32 cells (plan built once, on first use)
                 key = ("groups", plan.value)
                 if key not in L._plans:
@@ -720,6 +736,11 @@ def assemble_vector(b, L: Form, constants=None, coeffs=None):
         else:
             raise NotImplementedError(f"integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
     return b
+
+
+import itertools as _itertools
+
+_LIFT_SERIAL = _itertools.count()
 
 
 def apply_lifting(b, a, bcs, x0=None, alpha: float = 1.0, constants=None, coeffs=None):
@@ -753,7 +774,26 @@ def apply_lifting(b, a, bcs, x0=None, alpha: float = 1.0, constants=None, coeffs
         for (itype, ident), integ in aj._integrals.items():
             if itype != IntegralType.cell:
                 raise NotImplementedError("lifting of facet integrals")
-            plan = _asm_plan(aj, integ, itype, None)
+            # has_bc (fem/assemble_matrix_impl.h:27-34) once per (integral, bcs): the dof sets of a DirichletBC are
+            # fixed at construction, so the cells with a marked column dof form a fixed boundary layer; the lifting
+            # plan holds only those (the reference tests every cell of the domain on every call)
+            lkey = ("liftcells", id(integ), tuple(id(bc) for bc in bcs[j]))
+            if lkey not in aj._plans or any(r() is not bc for r, bc in zip(aj._plans[lkey][1], bcs[j])):
+                import weakref
+
+                ent, n = _entities_dev(aj, integ, itype)
+                dm1 = V1.dofmap.dev if ent is None else V1.dofmap.dev[ent.long()]
+                bsz = V1.dofmap.index_map_bs
+                node_marked = markers.view(-1, bsz).any(dim=1) if bsz > 1 else markers.bool()
+                hit = node_marked[dm1[:n].long()].any(dim=1)
+                ids = torch.arange(n, dtype=torch.int32, device=dm1.device) if ent is None else ent[:n]
+                aj._plans[lkey] = (ids[hit].contiguous(), [weakref.ref(bc) for bc in bcs[j]], next(_LIFT_SERIAL))
+            lcells, _, serial = aj._plans[lkey]
+            if lcells.numel() == 0:
+                continue
+            # (packed coefficient arrays are indexed by the position in the integral's own entity list: whole list then)
+            plan = (_asm_plan(aj, integ, itype, None, subset=(("lift", serial), lcells)) if coeffs is None
+                    else _asm_plan(aj, integ, itype, None))
             cf = _coeffs_for(aj, integ, None if coeffs is None else coeffs[j][(itype, ident)])
             _lib.check(_lib.lib.bfx_lift_bc_cells(
                 plan, integ.kernel, aj.mesh.x.data_ptr(), C.byref(cf), carr, nc, arr.data_ptr(), values.data_ptr(),

@@ -247,6 +247,7 @@ extern "C"
     BFX_CHUNKS_LEN_SORT = 128, /* with BFX_CHUNKS_LINEAR_STAGING on symmetric plans: destinations ordered by list length
                                   only (less padding of the 32-way interleaved lists); whether a destination is complete
                                   travels as one bit per lane in the group table; lean kernel only */
+    BFX_CHUNKS_VECTOR = 65536, /* internal: the plan of a linear form (set by bfx_asm_build_chunks_vector) */
     BFX_CHUNKS_PAD4 = 32, /* pad the source lists to multiples of 4 entries (no remainder steps in the list walk) */
     BFX_CHUNKS_TWO_STAGE_SPLIT = 16, /* with BFX_CHUNKS_TWO_STAGE: plain stores first, REDs after, each in address order */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
@@ -272,6 +273,12 @@ extern "C"
    * distinct nodes / dofs of every group of 32 cells and the list of (cell, local dof) pairs per distinct dof:
    * one warp assembles 32 cells and issues one RED per distinct dof instead of one per (cell, local dof). */
   int bfx_asm_build_groups(bfx_asm_t* plan, const double* x_dev, bfx_stream_t stream);
+  /* Chunk plan of a LINEAR form for kernel_id (bfx_assemble_vector_cells with BFX_ASM_CHUNKED): element vectors staged
+   * in shared memory per chunk of 256 / 384 Morton-ordered cells, one sum per distinct (dof, component) of the chunk, a
+   * plain update for dofs whose cells all lie in the chunk and one RED per chunk-boundary dof
+   * (fem/assemble_vector_impl.h:72-116 issues one += per (cell, local dof)).  Replaces a bfx_asm_build_groups plan.
+   * BFX_ERR_UNSUPPORTED for kernels without the variant (facet kernels). */
+  int bfx_asm_build_chunks_vector(bfx_asm_t* plan, const double* x_dev, int kernel_id, bfx_stream_t stream);
   int bfx_asm_chunk_stats(const bfx_asm_t* plan, int64_t* nchunks, int64_t* n_dest, int64_t* n_src_entries,
                           int64_t* plan_bytes);
   /* Staged entries whose shared-memory bank still collides with another entry read in the same half-warp step
