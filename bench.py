@@ -221,46 +221,151 @@ def alg_bytes_spmv(pb, nnz, n_rows, n_cols):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm (oracle port on the host cores)
+# CPU arm: the reference's algorithm (oracle port) on the host cores, decomposed like MPI ranks
 # ---------------------------------------------------------------------------------------------
-def cpu_assembly_rate(cfg, n_sample, repeats, threads):
-    """DOFs/s of the oracle port: `threads` workers, each assembling its own n_sample^3 box
-    (MPI-rank-like decomposition without the halo), `repeats` times."""
-    from oracle import oracle as O
-    from tests import problems as P
+def _mesh_fixture():
+    """The numpy box / brick-partition generators (dolfinx_b200/mesh.py), loaded as a stand-alone file: the CPU arm
+    imports neither the dolfinx_b200 package nor its native library."""
+    import importlib.util
 
-    O.build(fast=True)
-    if cfg == "p1":
-        p = P.tet_p1(n_sample, numbering="first_touch", shuffle_geometry=False)
-        kid, consts = O.K_POISSON_P1_TET_A, np.array([2.0])
-    elif cfg == "p2":
-        p = P.tet_p2(n_sample)
-        kid, consts = O.K_POISSON_P2_TET_A, np.array([2.0])
-    else:
-        p = P.hex_q1(n_sample)
-        kid, consts = O.K_ELASTICITY_Q1_HEX_A, np.array([1.0e9 / 2.6, 1.0e9 * 0.3 / (1.3 * 0.4)])
-    pat = P.oracle_pattern(O, p)
-    cells = np.arange(len(p.dofmap), dtype=np.int32)
-    bdofs = np.flatnonzero((p.dof_coords[:, 0] < 1e-12) | (p.dof_coords[:, 0] > 1 - 1e-12)).astype(np.int32)
-    markers = np.zeros(p.ndofs * p.bs, dtype=np.int8)
-    O.bc_mark(markers, O.unroll_dofs(bdofs, p.bs))
-    datas = [np.zeros(len(pat.edges) * p.bs * p.bs) for _ in range(threads)]
+    spec = importlib.util.spec_from_file_location("bfx_mesh_fixture", os.path.join(ROOT, "dolfinx_b200", "mesh.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["bfx_mesh_fixture"] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
-    def work(t):
-        for _ in range(repeats):
-            O.assemble_matrix(kid, p.x_dofmap, p.x, cells, p.dofmap, p.bs, p.dofmap, p.bs, datas[t], pat.edges,
-                              pat.offsets, bc0=markers, bc1=markers, constants=consts, fast=True)
-            O.set_diagonal(datas[t], pat.edges, pat.offsets, p.bs, p.bs, O.unroll_dofs(bdofs, p.bs), 1.0)
 
-    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-    t0 = time.perf_counter()
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
-    dt = time.perf_counter() - t0
-    dofs = p.ndofs * p.bs * threads * repeats
-    return dofs / dt, dt, p.ndofs * p.bs, len(cells)
+def _grid3(n):
+    """n = px * py * pz with the factors as equal as possible (brick grid of the simulated ranks)."""
+    best = (n, 1, 1)
+    for px in range(1, n + 1):
+        if n % px:
+            continue
+        for py in range(1, n // px + 1):
+            if (n // px) % py:
+                continue
+            pz = n // px // py
+            cand = tuple(sorted((px, py, pz), reverse=True))
+            if max(cand) - min(cand) < max(best) - min(best):
+                best = cand
+    return best
+
+
+class CpuWorld:
+    """ONE global box of n^3 cubes, split into `ranks` bricks (the product's own partition rule: lower brick owns the
+    shared planes, GhostMode::none).  Every simulated rank is one host thread: it assembles its owned cells into its own
+    MatrixCSR (rows of shared vertices are ghost rows on the non-owners), sets the Dirichlet diagonal, and the restated
+    MatrixCSR::scatter_rev (la/MatrixCSR.h:399-468) then adds the ghost rows to their owners - what `mpirun -np ranks`
+    of the reference does, with the MPI exchange replaced by memory copies (which favours the CPU)."""
+
+    def __init__(self, cfg, n, ranks):
+        from oracle import oracle as O
+
+        O.build(fast=True)
+        M = _mesh_fixture()
+        self.O, self.cfg, self.n, self.ranks = O, cfg, n, ranks
+        pg = _grid3(ranks)
+        nglob = (n, n, n)
+        self.pgrid = pg
+        self.bs = 3 if cfg == "q1" else 1
+        ins = []
+        for r in range(ranks):
+            part = M.BoxPartition(r, pg, nglob)
+            x = part.coordinates()
+            if cfg == "p2":
+                xd, dm, n_owned, ghosts, owners, dc = M.p2_partition(part)
+            else:
+                xd, dm, n_owned, ghosts, owners = part.tets() if cfg == "p1" else part.hexes()
+                local = part.vertex_numbering()[0].reshape(-1)
+                dc = np.empty((n_owned + len(ghosts), 3))
+                dc[local] = x
+            ins.append(dict(x=x, x_dofmap=xd, dofmap=dm, n_owned=n_owned, ghosts=ghosts, owners=owners, dc=dc))
+        self.ins = ins
+        maps = O.make_index_maps([i["n_owned"] for i in ins], [i["ghosts"] for i in ins], [i["owners"] for i in ins])
+        rows, cols = [], []
+        for i in ins:
+            r_, c_ = O.sparsity_insert_cells(np.arange(len(i["dofmap"])), i["dofmap"], i["dofmap"])
+            rows.append(r_)
+            cols.append(c_)
+        pats = O.sparsity_finalize(maps, maps, (self.bs, self.bs), rows, cols)
+        del rows, cols
+        self.mats = O.make_matrices(pats)
+        self.maps = maps
+        self.kid = {"p1": O.K_POISSON_P1_TET_A, "p2": O.K_POISSON_P2_TET_A, "q1": O.K_ELASTICITY_Q1_HEX_A}[cfg]
+        self.consts = np.array([2.0]) if cfg != "q1" else np.array([1.0e9 / 2.6, 1.0e9 * 0.3 / (1.3 * 0.4)])
+        self.markers, self.bc_rows, self.cells = [], [], []
+        for i in ins:
+            dc = i["dc"]
+            mask = ((dc[:, 0] < 1e-12) | (dc[:, 1] > 1 - 1e-12)) if cfg == "q1" else ((dc[:, 0] < 1e-12) | (dc[:, 0] > 1 - 1e-12))
+            bd = np.flatnonzero(mask).astype(np.int32)
+            mk = np.zeros(len(dc) * self.bs, dtype=np.int8)
+            O.bc_mark(mk, O.unroll_dofs(bd, self.bs))
+            self.markers.append(mk)
+            self.bc_rows.append(O.unroll_dofs(bd[bd < i["n_owned"]], self.bs))  # set_diagonal: owned rows only
+            self.cells.append(np.arange(len(i["dofmap"]), dtype=np.int32))
+        # vectorised form of the ghost-row exchange plan the oracle built (pack order: ghost-row order per neighbour)
+        bs2 = self.bs * self.bs
+        self.pack_idx, self.unpack_idx, self.ghost_begin = [], [], []
+        for A in self.mats:
+            m0 = A.index_maps[0]
+            per = [[] for _ in m0.src]
+            for i, g in enumerate(A.ghost_row_to_rank):
+                r0, r1 = A.row_ptr[m0.size_local + i] * bs2, A.row_ptr[m0.size_local + i + 1] * bs2
+                per[g].append(np.arange(r0, r1, dtype=np.int64))
+            self.pack_idx.append([np.concatenate(b) if b else np.zeros(0, dtype=np.int64) for b in per])
+            self.unpack_idx.append((A.unpack_pos[:, None] * bs2 + np.arange(bs2)[None, :]).reshape(-1))
+            self.ghost_begin.append(int(A.row_ptr[m0.size_local]) * bs2)
+        self.dofs_global = maps[0].size_global * self.bs
+        self.n_cells = sum(len(i["dofmap"]) for i in ins)
+
+    def scatter_rev(self):
+        send = [[A.data[ix] for ix in self.pack_idx[r]] for r, A in enumerate(self.mats)]
+        for r, A in enumerate(self.mats):
+            m0 = A.index_maps[0]
+            parts = [send[s][list(self.mats[s].index_maps[0].src).index(r)] for s in m0.dest]
+            if parts:
+                np.add.at(A.data, self.unpack_idx[r], np.concatenate(parts))
+            A.data[self.ghost_begin[r]:] = 0.0
+
+    def step(self, repeats=1):
+        O = self.O
+
+        def work(r):
+            i, A = self.ins[r], self.mats[r]
+            for _ in range(repeats):
+                A.data[:] = 0.0
+                O.assemble_matrix(self.kid, i["x_dofmap"], i["x"], self.cells[r], i["dofmap"], self.bs, i["dofmap"], self.bs,
+                                  A.data, A.cols, A.row_ptr, bc0=self.markers[r], bc1=self.markers[r], constants=self.consts,
+                                  fast=True)
+                O.set_diagonal(A.data, A.cols, A.row_ptr, self.bs, self.bs, self.bc_rows[r], 1.0)
+
+        t0 = time.perf_counter()
+        for _ in range(1):
+            ths = [threading.Thread(target=work, args=(r,)) for r in range(self.ranks)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        self.scatter_rev()
+        return time.perf_counter() - t0
+
+    def describe(self):
+        pg = self.pgrid
+        return (f"{self.ranks} host threads = {self.ranks} simulated MPI ranks ({pg[0]}x{pg[1]}x{pg[2]} bricks) of ONE "
+                f"{self.n}^3 box ({self.n_cells} cells, {self.dofs_global} DOFs): oracle assemble_matrix(bcs) + set_diagonal "
+                f"per rank, then the restated scatter_rev; liboracle_fast.so")
+
+
+def cpu_assembly_rate(cfg, n, ranks, min_seconds):
+    """(DOF/s, seconds per step, description) of the CPU arm: steps are repeated until min_seconds have passed."""
+    w = CpuWorld(cfg, n, ranks)
+    w.step()  # warm-up (page faults, thread start)
+    times = []
+    t_all = time.perf_counter()
+    while time.perf_counter() - t_all < min_seconds or len(times) < 2:
+        times.append(w.step())
+    dt = float(np.median(times))
+    return w.dofs_global / dt, dt, w.describe() + f"; median of {len(times)} steps", w
 
 
 def host_cores():
@@ -270,31 +375,36 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+CPU_SAMPLE_N = {"p1": 64, "p2": 32, "q1": 48}      # cpu_baseline leg of the GPU arm (about 10 s of CPU work + setup)
+CPU_REFERENCE_N = {"p1": 96, "p2": 48, "q1": 64}   # --impl reference: the largest box whose Python-side setup stays short
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    n_sample = {"p1": 48, "p2": 20, "q1": 24}[args.config]
-    # size each step so that the whole run stays within a few minutes
-    rate, dt, dofs, ncells = cpu_assembly_rate(args.config, n_sample, 1, cores)
-    target_s = 4.0
-    repeats = max(1, int(target_s / max(dt, 1e-3)))
+    n = args.n_cpu or CPU_REFERENCE_N[args.config]
+    t0 = time.perf_counter()
+    w = CpuWorld(args.config, n, cores)
+    t_setup = time.perf_counter() - t0
     for _ in range(args.warmup):
-        cpu_assembly_rate(args.config, n_sample, 1, cores)
-    times, rates = [], []
-    for _ in range(args.steps):
-        r, dts, _, _ = cpu_assembly_rate(args.config, n_sample, repeats, cores)
-        times.append(dts)
-        rates.append(r)
-    value = float(np.mean(rates))
-    sample = (f"{cores} threads x {repeats} x oracle assemble_matrix+set_diagonal on a {n_sample}^3 box "
-              f"({ncells} cells, {dofs} DOFs each), liboracle_fast.so")
+        w.step()
+    times = [w.step() for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    value = w.dofs_global / dt
+    sample = w.describe() + f"; setup {t_setup:.0f} s (untimed)"
+    cfgd = workload_config(args, 1)
+    names = {"p1": "Poisson P1 tets", "p2": "Poisson P2 tets", "q1": "Linear elasticity Q1 hexes (bs=3)"}
+    cfgd["workload"] = (f"{names[args.config]} on a {n}x{n}x{n} box (CPU arm: the largest box whose pure-Python pattern setup "
+                        f"stays within minutes; the GPU arm runs {cfgd['cells_per_gpu']}^3 per GPU): assemble_matrix(bcs) + "
+                        "set_diagonal + scatter_reverse into MatrixCSR")
+    cfgd["cells_per_edge_cpu"] = n
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": cfgd,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -357,6 +467,7 @@ def main():
     ap.add_argument("--spmv-reps", type=int, default=100)
     ap.add_argument("--spmv-variant", type=int, default=-1, help="bs=1 SpMV kernel (0 stream, 1 rows, 2 TMA rows); -1 = timed selection")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--n-cpu", type=int, default=0, help="cells per edge of the CPU arm's box (0 = default per config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lean", action="store_true",
                     help="N > 1 at shard sizes near the HBM limit (C5: --n 500): never build the plan of the whole "
@@ -602,15 +713,12 @@ def main():
                "slots_max_rel_diff": err2}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         cores = host_cores()
-        n_sample = {"p1": 48, "p2": 20, "q1": 24}[args.config]
-        r1, dt1, dofs, ncells = cpu_assembly_rate(args.config, n_sample, 1, cores)
-        reps = max(1, int(8.0 / max(dt1, 1e-3)))
-        rate, dtc, _, _ = cpu_assembly_rate(args.config, n_sample, reps, cores)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} threads x {reps} x oracle assemble_matrix+set_diagonal on a {n_sample}^3 box "
-                         f"({ncells} cells, {dofs} DOFs each; {dtc:.1f} s), liboracle_fast.so"}
+        ncpu = args.n_cpu or CPU_SAMPLE_N[args.config]
+        rate, dtc, desc, _w = cpu_assembly_rate(args.config, ncpu, cores, 8.0)
+        del _w
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc + f" ({dtc * 1e3:.1f} ms per step)"}
 
     if rank == 0:
         ach = b_asm / (ms_kernel * 1e-3) / 1e9
