@@ -11,6 +11,7 @@ The data-path exchanges (C1-C4, C6) run on the device through libbfx.so.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -277,31 +278,53 @@ class Scatterer:
     def num_p2p_requests(self):
         return len(self.dest) + len(self.src)
 
-    def device_plan(self):
-        if self._plan is None:
-            from . import _lib
+    def new_device_plan(self):
+        """A fresh bfx_scatter_t (device index arrays, staging buffers, communication stream, events) from the host
+        arrays of this plan.  Every la::Vector owns one, like the buffers and the request of the reference's Vector
+        (la/Vector.h:131-138), so that exchanges of two vectors on the same IndexMap may be in flight together."""
+        from . import _lib
 
-            h = C.c_void_p()
-            li = np.ascontiguousarray(self.local_inds)
-            ri = np.ascontiguousarray(self.remote_inds)
-            _lib.check(
-                _lib.lib.bfx_scatter_create(
-                    C.byref(h), self.map.comm.nccl, li.ctypes.data, li.size, ri.ctypes.data, ri.size,
-                    self.sizes_local.ctypes.data, self.displs_local.ctypes.data,
-                    np.ascontiguousarray(self.dest).ctypes.data, len(self.dest), self.sizes_remote.ctypes.data,
-                    self.displs_remote.ctypes.data, np.ascontiguousarray(self.src).ctypes.data, len(self.src),
-                )
+        h = C.c_void_p()
+        li = np.ascontiguousarray(self.local_inds)
+        ri = np.ascontiguousarray(self.remote_inds)
+        _lib.check(
+            _lib.lib.bfx_scatter_create(
+                C.byref(h), self.map.comm.nccl, li.ctypes.data, li.size, ri.ctypes.data, ri.size,
+                self.sizes_local.ctypes.data, self.displs_local.ctypes.data,
+                np.ascontiguousarray(self.dest).ctypes.data, len(self.dest), self.sizes_remote.ctypes.data,
+                self.displs_remote.ctypes.data, np.ascontiguousarray(self.src).ctypes.data, len(self.src),
             )
-            self._plan = h
+        )
+        return h
+
+    def device_plan(self):
+        """The plan's own device instance (callers that drive bfx_scatter_* themselves; one exchange at a time)."""
+        if self._plan is None:
+            self._plan = self.new_device_plan()
+            release_with(self, "bfx_scatter_destroy", self._plan)
         return self._plan
 
 
-_scatterer_cache: dict = {}
+def _release(name, handle):
+    from . import _lib
+
+    getattr(_lib.lib, name)(handle)
+
+
+def release_with(owner, destroy_name: str, handle):
+    """Destroy a libbfx handle when ``owner`` is collected (not at interpreter exit: the process teardown frees the
+    device and the library may already be unloaded)."""
+    fin = weakref.finalize(owner, _release, destroy_name, handle)
+    fin.atexit = False
+    return fin
+
+
+_scatterer_cache = weakref.WeakValueDictionary()
 
 
 def cached_scatterer(index_map: IndexMap, bs: int) -> Scatterer:
-    """la::Vector builds a new Scatterer per instance (la/Vector.h:131-138); on the GPU the plan
-    is built once per (IndexMap, bs) and shared."""
+    """The HOST plan of common::Scatterer is built once per (IndexMap, bs) and shared by the vectors on that map (its
+    constructor is a neighbourhood exchange, common/Scatterer.h:142-159); device buffers are per Vector."""
     key = (id(index_map), bs)
     sc = _scatterer_cache.get(key)
     if sc is None or sc.map is not index_map:

@@ -978,7 +978,7 @@ int bfx_csr_device_ptrs(const bfx_csr_t* A, const int64_t** row_ptr, const int32
 
 int bfx_csr_set_spmv_variant(bfx_csr_t* A, int variant)
 {
-  BFX_REQUIRE(A && variant >= -1 && variant <= 2, "bfx_csr_set_spmv_variant: variant must be -1 (select by timing) .. 2");
+  BFX_REQUIRE(A && variant >= -2 && variant <= 2, "bfx_csr_set_spmv_variant: variant must be -2 (select by timing), -1 (by row length) .. 2");
   A->spmv_variant = variant;
   return BFX_OK;
 }
@@ -1054,9 +1054,17 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
       else
         k_spmv_stream<8><<<(n + 31) / 32, SPMV_THREADS, 0, st>>>(n, A->row_ptr, re, A->cols, values, x, yy);
     };
+    if (A->spmv_variant == -1)
+    {
+      // default: chosen by the average row length alone, so that every rank and every run take the same kernel (the
+      // kernels sum a row in different orders: a timed choice would make y differ in the last bits from run to run).
+      // Short rows (P1: 15 entries) -> row per thread behind the TMA pipeline, long rows (P2: 29) -> entry stream;
+      // measured at C2 / C3: 0.70 against 0.83 / 1.12 ms, 1.83 against 2.47 / 2.98 ms (profiles/r02_spmv_variants.txt)
+      const_cast<bfx_csr*>(A)->spmv_variant = avg <= 20.0 ? 2 : 0;
+    }
     if (A->spmv_variant < 0)
     {
-      // plan-time autotuning (once per matrix): time both kernels into a scratch y, keep the faster
+      // opt-in autotuning (bfx_csr_set_spmv_variant(-2)): time the kernels into a scratch y, keep the fastest
       double* scratch = nullptr;
       cudaEvent_t e0, e1;
       if (cudaMalloc(&scratch, sizeof(double) * (size_t)n) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess
@@ -1114,6 +1122,8 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
           k_spmv_blocked<3, 3><<<grid_for((int64_t)n_launch * 32, 256, 32), 256, 0, st>>>(n_launch, rb, re, A->cols,
                                                                                            values, x, yy, nullptr);
       };
+      if (A->spmv_variant == -1)
+        const_cast<bfx_csr*>(A)->spmv_variant = 1; // deterministic default: the TMA-fed kernel (3.50 against 4.10 ms at C4)
       if (A->spmv_variant < 0)
       {
         double* scratch = nullptr;

@@ -15,7 +15,7 @@ struct bfx_csr
   int32_t* offdiag_rows = nullptr;  // owned rows with at least one ghost column
   int32_t n_offdiag_rows = 0;
   int* err_flag = nullptr;          // device flag: "Entry not in sparsity"
-  int spmv_variant = -1;            // bs=1 SpMV kernel chosen by the first bfx_spmv call (autotuned)
+  int spmv_variant = -1;            // SpMV kernel: -1 = by average row length on the first bfx_spmv call, -2 = by timing
 };
 
 namespace bfx

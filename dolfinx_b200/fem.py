@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import enum
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -117,6 +118,7 @@ class FunctionSpace:
 
     def __init__(self, mesh: Mesh, element: str, dofmap: DofMap):
         self.mesh, self.element, self.dofmap = mesh, element, dofmap
+        self._markers = {}  # bc marker arrays by bc combination (_bc_markers)
 
     def contains(self, V) -> bool:
         """fem/FunctionSpace.h:153 — no sub-spaces on this path: identity."""
@@ -175,7 +177,11 @@ class Form:
         self.coefficients = list(coefficients)
         self.constants = list(constants)
         self.mesh = mesh if mesh is not None else self.function_spaces[0].mesh
+        # cache of derived device data: entity lists, bfx_asm_t plans (keyed on the integral and on the serial number
+        # of the matrix whose sparsity their position tables index), aggregated-strategy flags.  The plans die with
+        # the form, or with their matrix, whichever goes first (_release_plans / _drop_matrix_plans).
         self._plans = {}
+        weakref.finalize(self, _release_plans, self._plans).atexit = False
 
     def integral_ids(self, itype):
         return sorted(i for (t, i) in self._integrals if t == itype)
@@ -189,6 +195,45 @@ class Form:
         for c in self.coefficients:
             n.append(n[-1] + c.function_space.space_dimension)
         return n
+
+
+def _is_plan_entry(key):
+    return isinstance(key, tuple) and key and key[0] in ("plan", "dS")
+
+
+def _destroy_plan_entry(plans, key):
+    """bfx_asm_destroy of one cached plan; the flags keyed on its address go with it (addresses are reused)."""
+    from . import _lib
+
+    h = plans.pop(key)[0]
+    for k in [k for k in plans if isinstance(k, tuple) and k[0] in ("aggplan", "vchunks", "groups") and k[1] == h.value]:
+        del plans[k]
+    _lib.lib.bfx_asm_destroy(h)
+
+
+def _release_plans(plans):
+    for key in [k for k in plans if _is_plan_entry(k)]:
+        _destroy_plan_entry(plans, key)
+    plans.clear()
+
+
+def _drop_matrix_plans(plans, serial):
+    """The matrix with this serial number is gone: its plans (CSR positions of a sparsity that no longer exists) too."""
+    for key in [k for k in plans if _is_plan_entry(k) and k[2] == serial]:
+        _destroy_plan_entry(plans, key)
+    plans.pop(("matrix", serial), None)
+
+
+def _matrix_key(form: Form, A):
+    """Cache key component for the matrix a plan belongs to (None for vectors / functionals); the first plan of a
+    (form, matrix) pair registers the clean-up that runs when the matrix is collected."""
+    if A is None:
+        return None
+    reg = ("matrix", A._serial)
+    if reg not in form._plans:
+        form._plans[reg] = True
+        weakref.finalize(A, _drop_matrix_plans, form._plans, A._serial).atexit = False
+    return A._serial
 
 
 def pack_constants(form: Form) -> np.ndarray:
@@ -355,15 +400,25 @@ def set_bc(b, bcs, x0=None, alpha: float = 1.0):
 # assembly
 # ---------------------------------------------------------------------------------------------
 def _bc_markers(V: FunctionSpace, bcs):
-    """dof markers of length bs*(owned+ghost) (fem/assembler.h:558-577); None when no bc applies."""
+    """dof markers of length bs*(owned+ghost) (fem/assembler.h:558-577); None when no bc applies.
+
+    The dof set of a DirichletBC is fixed at construction, so the marker array of a (space, bcs) combination is built
+    once and kept on the space (a time loop re-assembles with the same bcs every step)."""
     torch = _torch()
-    mk = None
-    for bc in bcs:
-        if V.contains(bc.function_space):
-            if mk is None:
-                im = V.dofmap.index_map
-                mk = torch.zeros(V.dofmap.index_map_bs * (im.size_local + im.num_ghosts), dtype=torch.int8, device=la._device())
-            bc.mark_dofs(mk)
+    mine = [bc for bc in bcs if V.contains(bc.function_space)]
+    if not mine:
+        return None
+    key = tuple(id(bc) for bc in mine)
+    hit = V._markers.get(key)
+    if hit is not None and all(r() is bc for r, bc in zip(hit[1], mine)):
+        return hit[0]
+    im = V.dofmap.index_map
+    mk = torch.zeros(V.dofmap.index_map_bs * (im.size_local + im.num_ghosts), dtype=torch.int8, device=la._device())
+    for bc in mine:
+        bc.mark_dofs(mk)
+    if len(V._markers) >= 8:
+        V._markers.clear()
+    V._markers[key] = (mk, [weakref.ref(bc) for bc in mine])
     return mk
 
 
@@ -374,7 +429,7 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
     (used to overlap boundary-cell assembly with the ghost-row exchange)."""
     from . import _lib
 
-    key = ("plan", id(integ), id(A) if A is not None else None, subset[0] if subset else None)
+    key = ("plan", id(integ), _matrix_key(form, A), subset[0] if subset else None)
     if key in form._plans:
         return form._plans[key][0]
     mesh = form.mesh
@@ -512,7 +567,7 @@ def _interior_facet_plan(form: Form, integ: IntegralData, A: la.MatrixCSR):
     from . import _lib
 
     torch = _torch()
-    key = ("dS", id(integ), id(A))
+    key = ("dS", id(integ), _matrix_key(form, A))
     if key not in form._plans:
         ent = integ.entities
         f = torch.as_tensor(np.ascontiguousarray(np.asarray(ent).reshape(-1, 2, 2), dtype=np.int64)
@@ -595,7 +650,7 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
                 strat = _matrix_strategy(a, integ, plan, strategy)
                 mode = _lib.VALUES_OVERWRITE if A._is_zero else _lib.VALUES_ADD
                 # a kernel that writes every value once absorbs a pending A.set_value(0)
-                vals = A._take_zero_fill() if (A._is_zero and strat == _lib.ASM_ROWGATHER) else A.data
+                vals = A._take_zero_fill() if (A._is_zero and strat == _lib.ASM_ROWGATHER) else A._values()
                 _lib.check(_lib.lib.bfx_assemble_matrix_cells(
                     plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
                     None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, vals.data_ptr(), strat, mode,
@@ -604,13 +659,13 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
                 ent, n = _entities_dev(a, integ, itype)
                 _lib.check(_lib.lib.bfx_assemble_matrix_facets(
                     plan, integ.kernel, a.mesh.x.data_ptr(), ent.data_ptr(), n, None if bc0 is None else bc0.data_ptr(),
-                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(),
+                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A._values().data_ptr(),
                     _lib.current_stream()))
             elif itype == IntegralType.interior_facet:
                 plan, ent, n = _interior_facet_plan(a, integ, A)
                 _lib.check(_lib.lib.bfx_assemble_matrix_facets(
                     plan, integ.kernel, a.mesh.x.data_ptr(), ent.data_ptr(), n, None if bc0 is None else bc0.data_ptr(),
-                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A.data.data_ptr(),
+                    None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, A._values().data_ptr(),
                     _lib.current_stream()))
             else:
                 raise NotImplementedError(f"integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
@@ -642,7 +697,7 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
         raise NotImplementedError("overlapped assembly handles cell integrals")
 
     was_zero = A._is_zero
-    vals = A.data  # (a pending set_value(0) is written here)
+    vals = A._values()  # (a pending set_value(0) is written here)
 
     def run(tag_index):
         for (itype, ident), integ in items:
@@ -779,8 +834,10 @@ def apply_lifting(b, a, bcs, x0=None, alpha: float = 1.0, constants=None, coeffs
             # plan holds only those (the reference tests every cell of the domain on every call)
             lkey = ("liftcells", id(integ), tuple(id(bc) for bc in bcs[j]))
             if lkey not in aj._plans or any(r() is not bc for r, bc in zip(aj._plans[lkey][1], bcs[j])):
-                import weakref
-
+                if lkey in aj._plans:  # ids reused by other bc objects: the old cell list and its plan are stale
+                    stale = ("plan", id(integ), None, ("lift", aj._plans[lkey][2]))
+                    if stale in aj._plans:
+                        _destroy_plan_entry(aj._plans, stale)
                 ent, n = _entities_dev(aj, integ, itype)
                 dm1 = V1.dofmap.dev if ent is None else V1.dofmap.dev[ent.long()]
                 bsz = V1.dofmap.index_map_bs
@@ -810,7 +867,7 @@ def set_diagonal(A: la.MatrixCSR, V: FunctionSpace, bcs, diagonal: float = 1.0):
             if n_owned == 0:
                 continue
             try:
-                _lib.check(_lib.lib.bfx_csr_set_diagonal(A._csr, A.data.data_ptr(), bc.dofs_dev.data_ptr(), n_owned,
+                _lib.check(_lib.lib.bfx_csr_set_diagonal(A._csr, A._values().data_ptr(), bc.dofs_dev.data_ptr(), n_owned,
                                                          float(diagonal), _lib.current_stream()))
             except _lib.BfxError as e:
                 raise _translate(e) from e

@@ -11,10 +11,11 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import itertools
 
 import numpy as np
 
-from .common import Comm, IndexMap, Scatterer, cached_scatterer
+from .common import Comm, IndexMap, Scatterer, cached_scatterer, release_with
 
 
 class InsertMode(enum.IntEnum):
@@ -207,6 +208,7 @@ class SparsityPattern:
                 )
             )
             self._csr = h
+            release_with(self, "bfx_csr_destroy", h)  # matrices on this pattern keep the pattern alive
         elif len(cell_segs) > 1:
             raise NotImplementedError("at most one device cell list per SparsityPattern")
         else:
@@ -307,6 +309,13 @@ class Vector:
         self.array = torch.zeros(n, dtype=torch.float64, device=_device()) if array is None else array
         assert self.array.numel() == n
         self._scatterer = cached_scatterer(index_map, self.bs)
+        self._dev_plan = None  # this vector's own device buffers / stream / events, created by the first exchange
+
+    def _plan(self):
+        if self._dev_plan is None:
+            self._dev_plan = self._scatterer.new_device_plan()
+            release_with(self, "bfx_scatter_destroy", self._dev_plan)
+        return self._dev_plan
 
     @property
     def block_size(self):
@@ -326,13 +335,13 @@ class Vector:
         from . import _lib
 
         if self.index_map.comm.size > 1:
-            _lib.check(_lib.lib.bfx_scatter_fwd_begin(self._scatterer.device_plan(), self.array.data_ptr(), _lib.current_stream()))
+            _lib.check(_lib.lib.bfx_scatter_fwd_begin(self._plan(), self.array.data_ptr(), _lib.current_stream()))
 
     def scatter_fwd_end(self):
         from . import _lib
 
         if self.index_map.comm.size > 1:
-            _lib.check(_lib.lib.bfx_scatter_fwd_end(self._scatterer.device_plan(), self.array.data_ptr(), self._n_owned(), _lib.current_stream()))
+            _lib.check(_lib.lib.bfx_scatter_fwd_end(self._plan(), self.array.data_ptr(), self._n_owned(), _lib.current_stream()))
 
     def scatter_forward(self):
         """Vector::scatter_fwd — owner values to ghosts."""
@@ -343,14 +352,14 @@ class Vector:
         from . import _lib
 
         if self.index_map.comm.size > 1:
-            _lib.check(_lib.lib.bfx_scatter_rev_begin(self._scatterer.device_plan(), self.array.data_ptr(), self._n_owned(), _lib.current_stream()))
+            _lib.check(_lib.lib.bfx_scatter_rev_begin(self._plan(), self.array.data_ptr(), self._n_owned(), _lib.current_stream()))
 
     def scatter_rev_end(self, mode: InsertMode = InsertMode.add):
         from . import _lib
 
         if self.index_map.comm.size > 1:
             op = 1 if mode == InsertMode.add else 0
-            _lib.check(_lib.lib.bfx_scatter_rev_end(self._scatterer.device_plan(), self.array.data_ptr(), op, _lib.current_stream()))
+            _lib.check(_lib.lib.bfx_scatter_rev_end(self._plan(), self.array.data_ptr(), op, _lib.current_stream()))
 
     def scatter_reverse(self, mode: InsertMode = InsertMode.add):
         """Vector::scatter_rev(op) — ghost values to owners (add or insert)."""
@@ -685,6 +694,9 @@ def matrix_transpose_plan(m0: IndexMap, m1: IndexMap, bs, indptr, indices, off_d
             "recv_dst": recv_dst, "recv_blocks": blocks}
 
 
+_MATRIX_SERIAL = itertools.count(1)
+
+
 class MatrixCSR:
     """la::MatrixCSR<double> with device storage (la/MatrixCSR.h:67-624).
 
@@ -731,6 +743,7 @@ class MatrixCSR:
             _lib.check(_lib.lib.bfx_csr_create(C.byref(h), n_all, m0.size_local, ptr_e.ctypes.data,
                                                np.ascontiguousarray(cols_e).ctypes.data, od_e.ctypes.data, 1, 1))
             self._csr = h
+            release_with(self, "bfx_csr_destroy", h)
         elif pattern._csr is None:
             edges, offsets = pattern.graph
             off_diag = (pattern.off_diagonal_offsets.astype(np.int64) + offsets[:-1])  # :695-703
@@ -739,6 +752,7 @@ class MatrixCSR:
                                                np.ascontiguousarray(edges).ctypes.data, off_diag.ctypes.data,
                                                self._bs[0], self._bs[1]))
             self._csr = h
+            release_with(self, "bfx_csr_destroy", h)
         else:
             self._csr = pattern._csr
         self._nnz = int(_lib.lib.bfx_csr_nnz(self._csr))
@@ -746,7 +760,8 @@ class MatrixCSR:
         self._is_zero = True
         self._zero_pending = False  # set_value(0) not yet written to memory (see set_value)
         self._scatter_plan = None
-        self._asm_plans = {}
+        # never reused, unlike id(): forms key their cached assembly plans (positions in THIS sparsity) on it
+        self._serial = next(_MATRIX_SERIAL)
         self._build_ghost_plan()
 
     # -- ghost-row plan (la/MatrixCSR.h:705-849) -------------------------------------------------
@@ -771,6 +786,7 @@ class MatrixCSR:
                 )
             )
             self._scatter_plan = h
+            release_with(self, "bfx_csr_scatter_destroy", h)
         return self._scatter_plan
 
     # -- accessors -------------------------------------------------------------------------------
@@ -806,13 +822,19 @@ class MatrixCSR:
         return self._index_maps[0].size_local + self._index_maps[0].num_ghosts
 
     # -- value manipulation ------------------------------------------------------------------------
-    @property
-    def data(self):
-        """The value array (python/dolfinx/la/__init__.py ``MatrixCSR.data``)."""
+    def _values(self):
+        """The value array for the library's own kernels (a pending zero-fill is written first)."""
         if self._zero_pending:
             self._data.zero_()
             self._zero_pending = False
         return self._data
+
+    @property
+    def data(self):
+        """The value array (python/dolfinx/la/__init__.py ``MatrixCSR.data``).  The caller may write through it, so
+        the matrix no longer counts as known-zero: the next assembly accumulates (fem/assembler.h:497-498)."""
+        self._is_zero = False
+        return self._values()
 
     def set_value(self, x: float):
         """MatrixCSR::set(value) (la/MatrixCSR.h:239-241).
@@ -850,7 +872,7 @@ class MatrixCSR:
             raise RuntimeError("Unsupported block size in MatrixCSR insertion")
         assert x.size == rows.size * cols.size * d0 * d1
         try:
-            _lib.check(_lib.lib.bfx_csr_insert(self._csr, self.data.data_ptr(), kind, d0, d1, x.ctypes.data,
+            _lib.check(_lib.lib.bfx_csr_insert(self._csr, self._values().data_ptr(), kind, d0, d1, x.ctypes.data,
                                                rows.ctypes.data, rows.size, cols.ctypes.data, cols.size, op,
                                                _lib.current_stream()))
         except _lib.BfxError as e:
@@ -872,14 +894,14 @@ class MatrixCSR:
 
         p = self._device_scatter_plan()
         if p is not None:
-            _lib.check(_lib.lib.bfx_csr_scatter_rev_begin(p, self.data.data_ptr(), _lib.current_stream()))
+            _lib.check(_lib.lib.bfx_csr_scatter_rev_begin(p, self._values().data_ptr(), _lib.current_stream()))
 
     def scatter_rev_end(self):
         from . import _lib
 
         p = self._device_scatter_plan()
         if p is not None:
-            _lib.check(_lib.lib.bfx_csr_scatter_rev_end(p, self.data.data_ptr(), _lib.current_stream()))
+            _lib.check(_lib.lib.bfx_csr_scatter_rev_end(p, self._values().data_ptr(), _lib.current_stream()))
 
     def scatter_reverse(self):
         """MatrixCSR::scatter_rev (la/MatrixCSR.h:384-468)."""
@@ -891,7 +913,7 @@ class MatrixCSR:
         from . import _lib
 
         out = C.c_double(0.0)
-        _lib.check(_lib.lib.bfx_csr_squared_norm(self._csr, self.data.data_ptr(), C.byref(out), _lib.current_stream()))
+        _lib.check(_lib.lib.bfx_csr_squared_norm(self._csr, self._values().data_ptr(), C.byref(out), _lib.current_stream()))
         return self._index_maps[0].comm.allreduce_sum(out.value)
 
     def mult(self, x: Vector, y: Vector, transpose: bool = False):
@@ -906,18 +928,18 @@ class MatrixCSR:
         multi = self._index_maps[0].comm.size > 1
         if not transpose:
             if not multi:
-                _lib.check(L.bfx_spmv(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_FULL, st))
+                _lib.check(L.bfx_spmv(self._csr, self._values().data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_FULL, st))
                 return
             x.scatter_fwd_begin()
-            _lib.check(L.bfx_spmv(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
+            _lib.check(L.bfx_spmv(self._csr, self._values().data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
             x.scatter_fwd_end()
-            _lib.check(L.bfx_spmv(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
+            _lib.check(L.bfx_spmv(self._csr, self._values().data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
         else:
             ncl = self._bs[1] * self._index_maps[1].size_local
             y.array[ncl:].zero_()
-            _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
+            _lib.check(L.bfx_spmvT(self._csr, self._values().data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_OFFDIAG, st))
             y.scatter_reverse(InsertMode.add)
-            _lib.check(L.bfx_spmvT(self._csr, self.data.data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
+            _lib.check(L.bfx_spmvT(self._csr, self._values().data_ptr(), x.array.data_ptr(), y.array.data_ptr(), _lib.SPMV_DIAG, st))
 
     def matmul(self, B: "MatrixCSR") -> "MatrixCSR":
         """la::matmul (la/matmul.h:538-579; python/dolfinx/la/__init__.py:186-205): C = A B, block size 1.
@@ -933,10 +955,10 @@ class MatrixCSR:
             raise RuntimeError("Invalid matrix sizes for matmul.")
         if tuple(self._bs) != (1, 1) or tuple(B._bs) != (1, 1):
             raise RuntimeError("Block size not supported in matmul.")
-        dev = self.data.device
+        dev = self._values().device
         comm = self._index_maps[0].comm
         plan = matrix_matmul_plan(self.index_map(1), B.index_map(0), B.index_map(1), B.indptr, B.indices,
-                                  lambda ks: B.data[torch.from_numpy(ks).to(dev)].cpu().numpy())
+                                  lambda ks: B._values()[torch.from_numpy(ks).to(dev)].cpu().numpy())
         cm = plan["col_map"]
         up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
         remap = up(np.append(plan["b_ghost_remap"], 0), torch.int32)  # (one spare entry: never an empty allocation)
@@ -946,7 +968,7 @@ class MatrixCSR:
         h = C.c_void_p()
         nnz = C.c_int64(0)
         st = _lib.current_stream()
-        _lib.check(_lib.lib.bfx_csr_matmul_begin(self._csr, self.data.data_ptr(), B._csr, B.data.data_ptr(),
+        _lib.check(_lib.lib.bfx_csr_matmul_begin(self._csr, self._values().data_ptr(), B._csr, B.data.data_ptr(),
                                                  B.index_map(1).size_local, remap.data_ptr(), grp.data_ptr(), gcols.data_ptr(),
                                                  gvals.data_ptr(), cm.size_local, C.byref(h), C.byref(nnz), st))
         n_rows = self._index_maps[0].size_local
@@ -980,12 +1002,12 @@ class MatrixCSR:
         comm = m0.comm
         indptr, indices = self.indptr, self.indices
         cap = int(indptr[n_row])
-        dev = self.data.device
+        dev = self._values().device
         rpT = torch.empty(n_col + 1, dtype=torch.int64, device=dev)
         cT = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
         vT = torch.empty(max(cap, 1) * nbs, dtype=torch.float64, device=dev)
         nnzT = C.c_int64(0)
-        _lib.check(_lib.lib.bfx_csr_transpose_local(self._csr, self.data.data_ptr(), n_col, rpT.data_ptr(), cT.data_ptr(),
+        _lib.check(_lib.lib.bfx_csr_transpose_local(self._csr, self._values().data_ptr(), n_col, rpT.data_ptr(), cT.data_ptr(),
                                                     vT.data_ptr(), cap, C.byref(nnzT), _lib.current_stream()))
         n0 = int(nnzT.value)
         rp0 = rpT.cpu().numpy()
@@ -1001,7 +1023,7 @@ class MatrixCSR:
             return AT
         # ---- entries in ghost columns -> column owners; merged structure (host side of la/mattrans.h:200-434)
         plan = matrix_transpose_plan(m0, m1, self._bs, indptr, indices, self.off_diag_offset, rp0, c0,
-                                     lambda ks: self.data.view(-1, nbs)[torch.from_numpy(ks).to(dev)].reshape(-1).cpu().numpy())
+                                     lambda ks: self._values().view(-1, nbs)[torch.from_numpy(ks).to(dev)].reshape(-1).cpu().numpy())
         sp = SparsityPattern.from_graph(comm, plan["maps"], (bs1, bs0), plan["cols"], plan["row_ptr"], plan["off_diag"])
         AT = MatrixCSR(sp)
         out = AT._data.view(-1, nbs)
@@ -1018,7 +1040,7 @@ class MatrixCSR:
         nrows = self.num_all_rows()
         ncols = self._index_maps[1].size_local + self._index_maps[1].num_ghosts
         A = np.zeros((nrows * bs0, ncols * bs1))
-        data = self.data.cpu().numpy().reshape(-1, bs0, bs1)
+        data = self._values().cpu().numpy().reshape(-1, bs0, bs1)
         indptr, indices = self.indptr, self.indices
         for r in range(nrows):
             for j in range(indptr[r], indptr[r + 1]):
@@ -1034,7 +1056,7 @@ class MatrixCSR:
         ncols = self._index_maps[1].size_local + self._index_maps[1].num_ghosts
         nrows = self.num_all_rows() if ghosted else self.num_owned_rows()
         nnzlocal = self.indptr[nrows]
-        data = self.data.cpu().numpy()
+        data = self._values().cpu().numpy()
         indptr, indices = self.indptr[: nrows + 1], self.indices[:nnzlocal]
         if bs0 == 1 and bs1 == 1:
             return sp.csr_matrix((data[:nnzlocal], indices, indptr), shape=(nrows, ncols))

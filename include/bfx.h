@@ -176,8 +176,10 @@ extern "C"
   int bfx_csr_matmul_end(bfx_matmul_t* handle, int64_t* row_ptr, int32_t* off_diag, int32_t* cols, double* vals,
                          bfx_stream_t stream);
   /* bs = 1 SpMV kernel of this matrix: 0 = entry-consecutive stream, 1 = row per thread out of staged (cols, values),
-   * 2 = row per thread fed by a two-stage TMA pipeline (persistent CTAs); -1 (default) = time the three on the first
-   * bfx_spmv call and keep the fastest (which one wins depends on the numbering of the matrix). */
+   * 2 = row per thread fed by a two-stage TMA pipeline (persistent CTAs); -1 (default) = chosen by the average row
+   * length on the first bfx_spmv call (the same kernel on every rank and in every run: results are reproducible);
+   * -2 = time the three on the first bfx_spmv call and keep the fastest (which one wins depends on the numbering of
+   * the matrix; not reproducible from run to run in the last bits). */
   int bfx_csr_set_spmv_variant(bfx_csr_t* csr, int variant);
   /* MatrixCSR::multT local kernels — la/MatrixCSR.h:950-1016 → impl::spmvT la/matrix_csr_impl.h:319-343 */
   int bfx_spmvT(const bfx_csr_t* csr, const double* values_dev, const double* x_dev, double* y_dev, int part,

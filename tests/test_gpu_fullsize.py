@@ -18,7 +18,8 @@ The oracle cannot assemble 1e8 cells in seconds, so these tests use what the dom
 import numpy as np
 import pytest
 
-from tests import problems as P
+from tests import problems as P  # noqa: F401
+from tests import sampled_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -51,62 +52,6 @@ def env():
     ns = NS()
     ns.K, ns.common, ns.fem, ns.la, ns.torch, ns.bench = _lib, common, fem, la, torch, bench
     return ns
-
-
-def _oracle_rows(env, oracle, pb, A, kid, consts, markers_host, rows):
-    """Rows `rows` (block indices) of the matrix by the CPU oracle on the sub-mesh of their incident cells."""
-    torch, fem = env.torch, env.fem
-    V, msh = pb["V"], pb["mesh"]
-    dm = V.dofmap.dev
-    rows_dev = torch.from_numpy(rows).to(dm.device)
-    sel = torch.zeros(dm.shape[0], dtype=torch.bool, device=dm.device)
-    lut = torch.zeros(pb["ndofs_local"], dtype=torch.bool, device=dm.device)
-    lut[rows_dev.long()] = True
-    for i in range(dm.shape[1]):
-        sel |= lut[dm[:, i].long()]
-    cells = torch.nonzero(sel).reshape(-1)
-    dm_s = dm[cells].cpu().numpy()
-    xd_s = msh.x_dofmap[cells].cpu().numpy()
-    ud, inv = np.unique(dm_s, return_inverse=True)
-    ux, invx = np.unique(xd_s, return_inverse=True)
-    x_l = msh.x[torch.from_numpy(ux).to(dm.device).long()].cpu().numpy()
-    bs = pb["bs"]
-    p = P.Problem(x_l, invx.reshape(xd_s.shape).astype(np.int32), inv.reshape(dm_s.shape).astype(np.int32), len(ud), bs,
-                  msh.cell_type)
-    bc_l = None
-    if markers_host is not None:
-        bc_l = np.ascontiguousarray(markers_host.reshape(-1, bs)[ud].reshape(-1))
-    pat, ref = P.oracle_assemble_matrix(oracle, p, kid, constants=consts, bc=bc_l)
-    if bc_l is not None:
-        loc = np.searchsorted(ud, rows).astype(np.int32)
-        unrolled = oracle.unroll_dofs(loc, bs)
-        unrolled = unrolled[bc_l[unrolled] != 0]
-        oracle.set_diagonal(ref, pat.edges, pat.offsets, bs, bs, unrolled.astype(np.int32), 1.0)
-    return ud, pat, ref, int(cells.numel())
-
-
-def _compare_rows(env, A, rows, ud, pat, ref, bs):
-    torch = env.torch
-    indptr = A.indptr
-    indices = A.indices
-    bs2 = bs * bs
-    worst = 0.0
-    data = A.data
-    for r in rows:
-        l = int(np.searchsorted(ud, r))
-        o0, o1 = int(pat.offsets[l]), int(pat.offsets[l + 1])
-        g0, g1 = int(indptr[r]), int(indptr[r + 1])
-        assert np.array_equal(ud[pat.edges[o0:o1]], indices[g0:g1]), f"columns of row {r} differ"
-        ref_r = ref[o0 * bs2:o1 * bs2]
-        got = data[g0 * bs2:g1 * bs2].cpu().numpy()
-        # blocked rows: scale every scalar row of the block row separately
-        rr = ref_r.reshape(o1 - o0, bs, bs)
-        gg = got.reshape(o1 - o0, bs, bs)
-        for i in range(bs):
-            scale = np.abs(rr[:, i, :]).max()
-            scale = scale if scale > 0 else 1.0
-            worst = max(worst, float(np.abs(gg[:, i, :] - rr[:, i, :]).max() / scale))
-    return worst
 
 
 @pytest.mark.parametrize("cfg", ["p1", "p2", "q1"])
@@ -192,9 +137,9 @@ def test_full_size_config(env, oracle, cfg):
         kid, consts = oracle.K_POISSON_P2_TET_A, np.array([2.0])
     else:
         kid, consts = oracle.K_ELASTICITY_Q1_HEX_A, np.array([1.0e9 / 2.6, 1.0e9 * 0.3 / (1.3 * 0.4)])
-    ud, pat, ref, ncells_sub = _oracle_rows(env, oracle, pb, A, kid, consts, mk, rows)
+    ud, pat, ref, ncells_sub = sampled_rows.oracle_rows(torch, oracle, pb, kid, consts, mk, rows)
     assert ncells_sub > len(rows)
-    err = _compare_rows(env, A, rows, ud, pat, ref, bs)
+    err = sampled_rows.compare_rows(A, rows, ud, pat, ref, bs)
     assert err <= TOL, f"sampled rows vs oracle: {err}"
 
     # ---- load vector: sum b = int f --------------------------------------------------------------------------------
