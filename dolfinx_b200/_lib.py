@@ -60,7 +60,7 @@ CHUNKED_KERNELS = frozenset({0, 2, 6, 8})
 LEAN_KERNELS = frozenset({0, 6})  # symmetric P1-sized kernels without coefficients: k_matrix_lean
 CHUNKS_SHARED_MATRIX = 4
 CHUNKS_LINEAR_STAGING = 2  # padded linear staging layout (no bank colouring); needed by CHUNK_KERNEL_LEAN
-CHUNK_KERNEL_DEFAULT, CHUNK_KERNEL_OCC5, CHUNK_KERNEL_DIET, CHUNK_KERNEL_LEAN = 0, 1, 2, 3
+CHUNK_KERNEL_DEFAULT, CHUNK_KERNEL_OCC5, CHUNK_KERNEL_DIET, CHUNK_KERNEL_LEAN, CHUNK_KERNEL_WIDE = 0, 1, 2, 3, 4
 CHUNKS_BANK_ORDER = 64  # bank-aware order of the source lists (linear staging layout)
 CHUNKS_LEN_SORT = 128  # destinations ordered by list length only (lean kernel)
 CHUNKS_PAD4 = 32  # source lists padded to multiples of 4 entries

@@ -970,6 +970,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// L2 prefetch of a contiguous global range (16-byte granules): the data is read later by ordinary loads
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -993,7 +998,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 
 // shared-memory budget of the lists of one chunk (chunks over budget read their lists from global)
 // destinations of one chunk the two-stage kernel holds in shared memory (typical P1 chunks: 0.22 NS CB)
-constexpr int two_stage_dcap(int ns, int cb) { return (ns * cb * 5 / 16) / 32 * 32; }
+constexpr int two_stage_dcap(int ns, int cb) { return ns > 36 ? (ns * cb / 2) / 32 * 32 : (ns * cb * 5 / 16) / 32 * 32; }
+// two-stage kernels of large elements (P2: 55 staged entries per cell) read the address-ordered write-back lists from
+// global memory in phase 3 (coalesced, each entry once) instead of staging them: shared memory keeps two CTAs per SM
+constexpr bool two_stage_lists_global(int ns) { return ns > 36; }
 // the same for the lean kernel's two-stage variant (tighter: three 384-cell CTAs per SM)
 constexpr int lean_two_dcap(int ns, int cb) { return (ns * cb * 3 / 10) / 32 * 32; }
 
@@ -1019,7 +1027,11 @@ struct ChunkSmem
 {
   static constexpr int SRC_GROUPS = src_group_cap(NS * CB);        // 32-entry groups of source entries
   static constexpr int DCAP = TWO ? two_stage_dcap(NS, CB) : NS * CB / 2;
-  static constexpr int DEST_BYTES = DCAP * 4 * DSTRIDE;           // destination addresses / write-back addresses
+  static constexpr bool WRG = TWO && two_stage_lists_global(NS);
+  // (round 2, measured and dropped: destination addresses of the large elements read from global memory by the list
+  // walk, L2-prefetched at CTA start - 28 KB less shared memory per P2 chunk.  128 cells: still two CTAs per SM, 4.24
+  // against 3.87 ms; 96 cells with three CTAs per SM: 3.84 ms, no better than the staged lists - profiles/r02_p2_variants.txt)
+  static constexpr int DEST_BYTES = WRG ? 0 : DCAP * 4 * DSTRIDE; // destination addresses / write-back addresses
   static constexpr int WINFO = NS * CB / 32;                      // groups of 32 destinations
   static constexpr size_t E_BYTES = (sizeof(double) * ((size_t)NS * (CB + 1) + 2) + 127) / 128 * 128;
   static constexpr size_t SRC_OFF = E_BYTES;
@@ -1027,7 +1039,7 @@ struct ChunkSmem
   static constexpr size_t WINFO_OFF = DEST_OFF + DEST_BYTES;
   static constexpr size_t BAR_OFF = WINFO_OFF + (((size_t)WINFO * 4 + 15) / 16) * 16 + 16;
   static constexpr size_t WRSRC_OFF = BAR_OFF + 16;                 // two-stage: ranks of the write-back lists
-  static constexpr size_t SUM_OFF = WRSRC_OFF + (TWO ? (size_t)DCAP * 2 * 2 : 0); // two-stage: one sum per destination
+  static constexpr size_t SUM_OFF = WRSRC_OFF + ((TWO && !WRG) ? (size_t)DCAP * 2 * 2 : 0); // two-stage: one sum per destination
   static constexpr size_t TOTAL = SUM_OFF + (TWO ? (size_t)DCAP * 8 : 0);
 };
 
@@ -1128,7 +1140,7 @@ __device__ __forceinline__ void chunk_walk(const uint16_t* __restrict__ srcp, co
 // DIET: phase 2 through chunk_walk (round-2 experiment, selected by bfx_asm_chunk_set_kernel; not the default)
 // DBG (profiling only, results are wrong): 1 = phase 1 only, 2 = phase 2 only, 3 = phase 2 without the global updates
 template <class E, bool SYM, int CB, int THREADS, typename AddrT, bool TWO = false, int OCC = 0, bool DIET = false, int DBG = 0>
-__global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
+__global__ void __launch_bounds__(THREADS, OCC ? OCC : (staged_per_cell(E::ND * E::BS, SYM) > 36 ? 2 : chunk_min_ctas(THREADS)))
     k_matrix_chunked(const AsmArgs a, const ChunkArgs ch)
 {
   constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS, NS = staged_per_cell(N, SYM), TPC = THREADS / CB;
@@ -1175,14 +1187,26 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   for (int k = 0; k < LOCWV; ++k)
     locv[k] = ch.wv_cnt ? __ldg(reinterpret_cast<const uint32_t*>(ch.wv_loc) + slot * LOCWV + k) : 0u;
 
+  // no dof table (more than 32 distinct dofs per 32 cells: P2): the cell's own dofmap row is a first-level load too, so
+  // that the marker words travel together with the coordinates instead of after the geometry
+  constexpr bool EARLY_D0 = BS == 1 && ND > 4;
+  const bool early_bits = EARLY_D0 && use_bits && !dof_tab && ch.bits0 && (ch.same_bc || !ch.bits1) && slot < a.n
+                          && (DBG < 2 || DBG == 4) && ch.dm0;
+  constexpr int NDE = EARLY_D0 ? ND : 1;
+  int32_t d0e[NDE];
+  if (early_bits)
+    load_ints<NDE>(ch.dm0 + slot * ND, d0e);
+
   // ---- prefetch of the chunk's lists: TMA bulk copies land while phase 1 computes
   const ChunkHdr h = ch.hdr[q];
   const int n_dw = (h.n_dest + 31) >> 5;
   const uint32_t n_wr_pad = TWO ? ((uint32_t)h.pad + 31u) & ~31u : 0u; // two-stage: (address, rank) pairs of the chunk
+  constexpr bool WRG = L::WRG; // two-stage write-back lists read from global memory in phase 3
   const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u,
-                 dest_bytes = TWO ? n_wr_pad * 4u : (uint32_t)n_dw * 32u * DS * (uint32_t)sizeof(AddrT);
+                 dest_bytes = WRG ? 0u : (TWO ? n_wr_pad * 4u : (uint32_t)n_dw * 32u * DS * (uint32_t)sizeof(AddrT));
   // (a two-stage plan is only built when the destinations of every chunk fit: bfx_asm_build_chunks)
-  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO;
+  const bool fits = h.n_src32 <= L::SRC_GROUPS && dest_bytes <= (uint32_t)L::DEST_BYTES && n_dw <= L::WINFO
+                    && (!WRG || n_dw * 32 <= L::DCAP);
   const uint16_t* g_src = ch.src + (h.src_base32 << 5);
   const AddrT* g_dest = TWO ? reinterpret_cast<const AddrT*>(ch.wr_addr) + h.dest_base * 2
                             : static_cast<const AddrT*>(ch.dest_addr) + h.dest_base * DS;
@@ -1195,13 +1219,18 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     if (fits && n_dw > 0 && DBG != 4)
     {
       const uint32_t winfo_bytes = ((uint32_t)n_dw * 4u + 15u) & ~15u; // chunks start on 4-group boundaries
-      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes + (TWO ? n_wr_pad * 2u : 0u));
+      mbar_expect_tx(bar, src_bytes + dest_bytes + winfo_bytes + ((TWO && !WRG) ? n_wr_pad * 2u : 0u));
       bulk_g2s(s_src, g_src, src_bytes, bar);
       if (dest_bytes > 0)
         bulk_g2s(s_dest, g_dest, dest_bytes, bar);
       bulk_g2s(s_winfo, g_winfo, winfo_bytes, bar);
-      if (TWO && n_wr_pad > 0)
+      if (TWO && !WRG && n_wr_pad > 0)
         bulk_g2s(smem_raw + L::WRSRC_OFF, ch.wr_src + h.dest_base * 2, n_wr_pad * 2u, bar);
+      if (WRG && n_wr_pad > 0) // phase 3 reads these with ordinary loads: have them in L2 by then
+      {
+        bulk_prefetch_l2(ch.wr_addr + h.dest_base * 2, n_wr_pad * 4u);
+        bulk_prefetch_l2(ch.wr_src + h.dest_base * 2, n_wr_pad * 2u);
+      }
     }
   }
 
@@ -1223,6 +1252,13 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   {
     const double* pp = a.x + 3 * (int64_t)vtx_id;
     px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+  }
+  uint32_t bwe[NDE];
+  if (early_bits)
+  {
+#pragma unroll
+    for (int i = 0; i < NDE; ++i)
+      bwe[i] = __ldg(ch.bits0 + (d0e[i] >> 5));
   }
   // -- coordinates
   double xc[NX][3];
@@ -1260,6 +1296,14 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
 #pragma unroll
       for (int i = 0; i < ND; ++i)
         m0 |= __shfl_sync(0xffffffffu, b, (locd[i >> 2] >> (8 * (i & 3))) & 31u) << i;
+      if (ch.same_bc)
+        m1 = m0;
+    }
+    else if (early_bits)
+    {
+#pragma unroll
+      for (int i = 0; i < NDE; ++i)
+        m0 |= ((bwe[i] >> (d0e[i] & 31)) & 1u) << i;
       if (ch.same_bc)
         m1 = m0;
     }
@@ -1329,9 +1373,16 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     return;
   }
 
-  if constexpr (DIET)
+  if constexpr (DIET && TWO)
   {
-    static_assert(!TWO, "the diet variant keeps the classic write-back");
+    double* sums = reinterpret_cast<double*>(smem_raw + L::SUM_OFF);
+    if (fits)
+      chunk_walk_sums<THREADS, 1>(s_src, s_winfo, Es, sums, n_dw);
+    else
+      chunk_walk_sums<THREADS, 1>(g_src, g_winfo, Es, sums, n_dw);
+  }
+  else if constexpr (DIET)
+  {
     if (fits)
       chunk_walk<SYM, THREADS, AddrT, DBG>(s_src, s_dest, s_winfo, Es, a.values, h.n_dest, h.n_complete, n_dw, ch.overwrite);
     else
@@ -1341,9 +1392,9 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
   // ---- phase 2: one thread per distinct destination
   const int lane = threadIdx.x & 31;
   const uint16_t* srcp = fits ? s_src : g_src;
-  const AddrT* destp = fits ? s_dest : g_dest;
+  const AddrT* destp = (fits && !WRG) ? s_dest : g_dest;
   const uint32_t* winfop = fits ? s_winfo : g_winfo;
-  for (int dw = threadIdx.x >> 5; dw < n_dw; dw += THREADS / 32)
+  for (int dw = threadIdx.x >> 5; dw < ((DIET && TWO) ? 0 : n_dw); dw += THREADS / 32)
   {
     const uint32_t info = winfop[dw];
     const int m = (int)(info & 0xffu);
@@ -1406,8 +1457,9 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : chunk_min_ctas(THREADS))
     // ---- phase 3: write-back in address order
     __syncthreads();
     const double* sums = reinterpret_cast<const double*>(smem_raw + L::SUM_OFF);
-    const uint16_t* wsrc = fits ? reinterpret_cast<const uint16_t*>(smem_raw + L::WRSRC_OFF) : ch.wr_src + h.dest_base * 2;
+    const uint16_t* wsrc = (fits && !WRG) ? reinterpret_cast<const uint16_t*>(smem_raw + L::WRSRC_OFF) : ch.wr_src + h.dest_base * 2;
     const uint32_t* waddr = reinterpret_cast<const uint32_t*>(destp);
+#pragma unroll 8
     for (int t = threadIdx.x; t < h.pad; t += THREADS)
     {
       const uint32_t sx = wsrc[t];
@@ -2009,6 +2061,18 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       return BFX_OK;
     }
   }
+  if constexpr (SYM && two_stage_lists_global(NS) && CB == chunk_cb(NS))
+  {
+    if (c->wr_addr) // two-stage plan of a large element: DIET list walk, write-back lists streamed from global memory
+    {
+      const size_t smem2 = ChunkSmem<NS, CB, 2, true>::TOTAL;
+      BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, true, 0, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, true, 0, true><<<(unsigned)c->nchunks, THREADS, smem2, st>>>(a, ch);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
   if (c->wr_addr)
     return fail(BFX_ERR_INVALID, "two-stage chunk plan without a two-stage kernel");
   const size_t smem = ChunkSmem<NS, CB, SYM ? 2 : 1>::TOTAL;
@@ -2024,7 +2088,7 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       return BFX_OK;
     }
   }
-  if constexpr (SYM && NS <= 16 && CB == 256)
+  if constexpr (SYM && CB == chunk_cb(NS) && THREADS == chunk_threads(NS))
   {
     // profiling-only variants (10 + DBG): see k_matrix_chunked
     if (c->kernel_variant >= 11 && c->kernel_variant <= 14 && c->addr_bytes == 4)
@@ -2048,10 +2112,12 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       return BFX_OK;
     }
   }
-  if constexpr (SYM && CB == chunk_cb(NS))
+  if constexpr (SYM && (CB == chunk_cb(NS) || two_stage_lists_global(NS)))
   {
-    // BFX_CHUNK_KERNEL_DIET: the variant whose phase 2 is chunk_walk
-    if (c->kernel_variant == BFX_CHUNK_KERNEL_DIET && c->addr_bytes == 4)
+    // BFX_CHUNK_KERNEL_DIET: the variant whose phase 2 is chunk_walk (the default of the large elements)
+    if ((c->kernel_variant == BFX_CHUNK_KERNEL_DIET || c->kernel_variant == BFX_CHUNK_KERNEL_WIDE
+         || (two_stage_lists_global(NS) && c->kernel_variant == BFX_CHUNK_KERNEL_DEFAULT))
+        && c->addr_bytes == 4)
     {
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2102,6 +2168,12 @@ int launch_chunked_es(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       || launch_chunked_try<E, SYM, 192>(P, a, values_mode, st, status)
       || launch_chunked_try<E, SYM, 384>(P, a, values_mode, st, status))
     return status;
+  if constexpr (SYM && NS > 36)
+  {
+    // BFX_CHUNK_KERNEL_WIDE: four threads per cell (twice the warps per SM at the same shared memory) + chunk_walk
+    if (P->chunks->kernel_variant == BFX_CHUNK_KERNEL_WIDE)
+      return launch_chunked_cb<E, SYM, chunk_cb(NS), 4 * chunk_cb(NS)>(P, a, values_mode, st);
+  }
   return launch_chunked_cb<E, SYM, chunk_cb(NS), chunk_threads(NS)>(P, a, values_mode, st);
 }
 
@@ -2758,7 +2830,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
   // two-stage write-back: symmetric P1-sized plans of 256-cell chunks with 32-bit addresses whose chunks all keep
   // their destinations within the kernel's shared-memory budget (checked by pass A)
   const bool lean_plan = (flags & BFX_CHUNKS_LINEAR_STAGING) != 0;
-  bool two = (flags & BFX_CHUNKS_TWO_STAGE) && sym && n2 <= 16 && (cb == 256 || lean_plan) && c->addr_bytes == 4;
+  bool two = (flags & BFX_CHUNKS_TWO_STAGE) && sym && c->addr_bytes == 4
+             && ((n2 <= 16 && (cb == 256 || lean_plan)) || (two_stage_lists_global(n2) && cb == chunk_cb(n2)));
   int64_t *ndw = nullptr, *nsrc = nullptr;
   if ((e = dev_alloc(&ndw, (size_t)c->nchunks + 1)) || (e = dev_alloc(&nsrc, (size_t)c->nchunks + 1)))
     return bail(e);
@@ -3041,7 +3114,7 @@ int bfx_asm_chunk_set_kernel(bfx_asm_t* P, int variant)
 {
   BFX_REQUIRE(P && P->chunks, "bfx_asm_chunk_set_kernel: no chunk plan");
   BFX_REQUIRE(variant == BFX_CHUNK_KERNEL_DEFAULT || variant == BFX_CHUNK_KERNEL_OCC5 || variant == BFX_CHUNK_KERNEL_DIET
-                  || variant == BFX_CHUNK_KERNEL_LEAN || (variant >= 11 && variant <= 14),
+                  || variant == BFX_CHUNK_KERNEL_LEAN || variant == BFX_CHUNK_KERNEL_WIDE || (variant >= 11 && variant <= 14),
               "bfx_asm_chunk_set_kernel: unknown variant %d", variant);
   P->chunks->kernel_variant = variant;
   if (const char* d = getenv("BFX_LEAN_DBG")) // profiling only (wrong results): 1 phase 1, 2 phase 2, 3 phase 2 without updates

@@ -294,8 +294,10 @@ extern "C"
     BFX_CHUNK_KERNEL_DEFAULT = 0,
     BFX_CHUNK_KERNEL_OCC5 = 1,
     BFX_CHUNK_KERNEL_DIET = 2,
-    BFX_CHUNK_KERNEL_LEAN = 3 /* instruction-lean kernel for symmetric P1-sized plans built with BFX_CHUNKS_LINEAR_STAGING
-                                 (falls back to DEFAULT where its preconditions do not hold) */
+    BFX_CHUNK_KERNEL_LEAN = 3, /* instruction-lean kernel for symmetric P1-sized plans built with BFX_CHUNKS_LINEAR_STAGING
+                                  (falls back to DEFAULT where its preconditions do not hold) */
+    BFX_CHUNK_KERNEL_WIDE = 4  /* elements with more than 36 staged entries per cell (P2): four threads per cell and the
+                                  DIET list walk - twice the resident warps per SM at the same shared memory */
   };
   int bfx_asm_chunk_set_kernel(bfx_asm_t* plan, int variant);
   /* 1 if the chunk plan was built with the two-stage (address-ordered) write-back, see BFX_CHUNKS_TWO_STAGE */
