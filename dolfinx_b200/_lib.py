@@ -46,6 +46,11 @@ K_ACTION_POISSON_P1_TET_L = 15
 K_ACTION_POISSON_P2_TET_L = 16
 K_L2NORM2_P1_TET_M = 17
 K_AVG_MASS_P1_TRI_DS = 18
+K_AVG_LOAD_P1_TRI_DS_L = 19
+K_ONE_TRI_DS_M = 20
+K_AVG2_COEFF_P1_TRI_DS_M = 21
+K_COEFF2_P1_TRI_FACET_M = 22
+K_LOAD_PROD_P1_TET_L = 23
 
 ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
@@ -139,6 +144,7 @@ _SIGS = {
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),
     "bfx_assemble_scalar_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, C.POINTER(f64), vp], ci),
+    "bfx_assemble_scalar_facets": ([vp, ci, vp, vp, i64, C.POINTER(Coeffs), C.POINTER(f64), ci, C.POINTER(f64), vp], ci),
     "bfx_lift_bc_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp, vp, vp, f64, vp], ci),
     "bfx_assemble_matrix_facets": ([vp, ci, vp, vp, i64, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),
     "bfx_assemble_vector_facets": ([vp, ci, vp, vp, i64, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, vp], ci),
@@ -230,7 +236,8 @@ def kernel_info(kernel_id: int) -> KernelInfo:
 
 
 def make_coeffs(packed=None, cstride=0, fused=None, offset=0):
-    """Build a bfx_coeffs_t. ``fused`` = (values tensor, dofmap tensor, nd, bs)."""
+    """Build a bfx_coeffs_t.  ``fused`` = (values tensor, dofmap tensor, nd, bs), or a list of such tuples for a kernel
+    that gathers several coefficients (in the order of the kernel's w)."""
     c = Coeffs()
     if packed is not None:
         c.packed_dev = dptr(packed)
@@ -238,13 +245,15 @@ def make_coeffs(packed=None, cstride=0, fused=None, offset=0):
         c.n_fused = 1
         c.fused[0].offset = offset
     elif fused is not None:
-        v, dm, nd, bs = fused
-        c.n_fused = 1
-        c.fused[0].values_dev = dptr(v)
-        c.fused[0].dofmap_dev = dptr(dm)
-        c.fused[0].nd = nd
-        c.fused[0].bs = bs
-        c.fused[0].offset = offset
+        items = [fused] if isinstance(fused, tuple) else list(fused)
+        assert 1 <= len(items) <= 4
+        c.n_fused = len(items)
+        for k, (v, dm, nd, bs) in enumerate(items):
+            c.fused[k].values_dev = dptr(v)
+            c.fused[k].dofmap_dev = dptr(dm)
+            c.fused[k].nd = nd
+            c.fused[k].bs = bs
+            c.fused[k].offset = offset
     return c
 
 

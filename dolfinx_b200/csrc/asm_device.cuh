@@ -65,8 +65,19 @@ __device__ __forceinline__ void gather_coords(const double* __restrict__ x, cons
   }
 }
 
-// Coefficients: packed reference layout, or the fused gather of ONE coefficient whose layout the
-// element fixes at compile time (pack_impl, fem/pack.h:77-103)
+// Coefficients: packed reference layout, or the fused gather of the element's coefficients (NCOEF of them, one unless
+// the element says otherwise, each WND nodes x WBS components: pack_impl, fem/pack.h:77-103), w = [coef 0 | coef 1 ..]
+template <class E, class = void>
+struct ncoef_of
+{
+  static constexpr int value = 1;
+};
+template <class E>
+struct ncoef_of<E, decltype((void)E::NCOEF)>
+{
+  static constexpr int value = E::NCOEF;
+};
+
 template <class E>
 __device__ __forceinline__ void load_w(const AsmArgs& a, int64_t e, int32_t cell, double* w)
 {
@@ -80,15 +91,21 @@ __device__ __forceinline__ void load_w(const AsmArgs& a, int64_t e, int32_t cell
     }
     else
     {
-      const int32_t* dm = a.coef.f[0].dm + (int64_t)cell * E::WND;
-      const double* v = a.coef.f[0].v;
+      constexpr int NC = ncoef_of<E>::value;
+      static_assert(NC <= 4 && NC * E::WND * E::WBS == E::WSIZE, "fused gather: NCOEF coefficients of WND x WBS scalars");
 #pragma unroll
-      for (int i = 0; i < E::WND; ++i)
+      for (int c = 0; c < NC; ++c)
       {
-        const int64_t d = __ldg(dm + i);
+        const int32_t* dm = a.coef.f[c].dm + (int64_t)cell * E::WND;
+        const double* v = a.coef.f[c].v;
 #pragma unroll
-        for (int k = 0; k < E::WBS; ++k)
-          w[E::WBS * i + k] = __ldg(v + E::WBS * d + k);
+        for (int i = 0; i < E::WND; ++i)
+        {
+          const int64_t d = __ldg(dm + i);
+#pragma unroll
+          for (int k = 0; k < E::WBS; ++k)
+            w[(c * E::WND + i) * E::WBS + k] = __ldg(v + E::WBS * d + k);
+        }
       }
     }
   }

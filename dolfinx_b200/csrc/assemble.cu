@@ -164,7 +164,15 @@ __global__ void __launch_bounds__(256) k_scalar_cells(const AsmArgs a, double* _
   double acc = 0.0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
   {
-    const int32_t cell = a.cells ? a.cells[e] : (int32_t)e;
+    int32_t cell;
+    int lf = 0;
+    if (a.entities)
+    {
+      cell = a.entities[2 * e];
+      lf = a.entities[2 * e + 1];
+    }
+    else
+      cell = a.cells ? a.cells[e] : (int32_t)e;
     int32_t xd[NX];
     load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
     double xc[NX][3];
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(256) k_scalar_cells(const AsmArgs a, double* _
     double w[E::WSIZE > 0 ? E::WSIZE : 1];
     load_w<E>(a, e, cell, w);
     typename E::Geo g;
-    E::prepare(g, xc, w, a.constants, 0);
+    E::prepare(g, xc, w, a.constants, lf);
     acc += E::scalar(g);
   }
   __shared__ double part[8];
@@ -889,6 +897,8 @@ int dispatch_vector(int kernel_id, const AsmArgs& a, cudaStream_t st)
   case BFX_K_FACET_LOAD_P1_TET_L: return launch_vector<el::FacetLoadP1Tet>(a, st);
   case BFX_K_ACTION_POISSON_P1_TET_L: return launch_vector<el::ActionOf<el::PoissonP1Tet>>(a, st);
   case BFX_K_ACTION_POISSON_P2_TET_L: return launch_vector<el::ActionOf<el::PoissonP2Tet>>(a, st);
+  case BFX_K_AVG_LOAD_P1_TRI_DS_L: return launch_vector<el::AvgLoadP1TriDS>(a, st);
+  case BFX_K_LOAD_PROD_P1_TET_L: return launch_vector<el::LoadProdP1Tet>(a, st);
   default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a linear-form kernel", kernel_id);
   }
 }
@@ -899,7 +909,10 @@ const bfx_kernel_info_t KINFO[BFX_K_COUNT] = {
     {3, 3, 1, 2, 0, 0, 1},  {3, 3, 1, 1, 0, 1, 1},  {4, 4, 1, 2, 0, 1, 0},  {4, 4, 1, 1, 4, 0, 0},
     {4, 10, 1, 2, 0, 1, 0}, {4, 10, 1, 1, 10, 0, 0}, {8, 8, 3, 2, 0, 2, 0}, {8, 8, 3, 1, 24, 0, 0},
     {4, 4, 1, 1, 4, 0, 1},  {4, 4, 1, 2, 0, 0, 1},  {0, 0, 0, -1, 0, 0, 0}, {4, 4, 1, 1, 4, 1, 0},
-    {4, 10, 1, 1, 10, 1, 0}, {4, 4, 1, 0, 4, 0, 0}, {6, 6, 1, 2, 0, 0, 1}};
+    {4, 10, 1, 1, 10, 1, 0}, {4, 4, 1, 0, 4, 0, 0}, {6, 6, 1, 2, 0, 0, 1}, {6, 6, 1, 1, 0, 0, 1},
+    {6, 6, 1, 0, 0, 0, 1},  {6, 6, 1, 0, 6, 0, 1},  {3, 3, 1, 0, 3, 0, 1},  {4, 4, 1, 1, 8, 0, 0}};
+// coefficients gathered by the fused path of a kernel (all of the same layout): 1 unless listed
+int kernel_ncoef(int kernel_id) { return kernel_id == BFX_K_LOAD_PROD_P1_TET_L ? 2 : 1; }
 
 int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, const bfx_coeffs_t* coeffs,
                 const double* constants, int n_constants, AsmArgs& a, bool need_csr = true)
@@ -939,13 +952,17 @@ int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, cons
     }
     else
     {
-      BFX_REQUIRE(coeffs->n_fused == 1 && coeffs->fused[0].values_dev && coeffs->fused[0].dofmap_dev,
-                  "fused coefficient gather supports exactly one coefficient");
-      BFX_REQUIRE(coeffs->fused[0].nd * coeffs->fused[0].bs == ki.w_size,
-                  "coefficient layout nd*bs=%d does not match kernel w size %d", coeffs->fused[0].nd * coeffs->fused[0].bs,
-                  ki.w_size);
-      a.coef.f[0].v = coeffs->fused[0].values_dev;
-      a.coef.f[0].dm = coeffs->fused[0].dofmap_dev;
+      const int nc = kernel_ncoef(kernel_id);
+      BFX_REQUIRE(coeffs->n_fused == nc, "kernel id %d gathers %d coefficient(s), %d given", kernel_id, nc, coeffs->n_fused);
+      for (int k = 0; k < nc; ++k)
+      {
+        BFX_REQUIRE(coeffs->fused[k].values_dev && coeffs->fused[k].dofmap_dev, "fused coefficient %d: null array", k);
+        BFX_REQUIRE(coeffs->fused[k].nd * coeffs->fused[k].bs * nc == ki.w_size,
+                    "coefficient layout nd*bs=%d does not match kernel w size %d / %d", coeffs->fused[k].nd * coeffs->fused[k].bs,
+                    ki.w_size, nc);
+        a.coef.f[k].v = coeffs->fused[k].values_dev;
+        a.coef.f[k].dm = coeffs->fused[k].dofmap_dev;
+      }
     }
   }
   if (P->csr)
@@ -997,7 +1014,8 @@ int bfx_asm_create(bfx_asm_t** out, const bfx_csr_t* csr, const int32_t* x_dofma
                    int nd0, const int32_t* dofmap1, int nd1, int64_t ncells_all, const int32_t* cells, int64_t ncells,
                    int32_t n_rows_all, int borrow, bfx_stream_t stream)
 {
-  BFX_REQUIRE(out && x_dofmap && dofmap0 && nx > 0 && nd0 > 0 && ncells_all >= 0 && ncells >= 0,
+  // (a mesh without cells - an empty rank, an interior-facet domain without facets - has empty arrays: NULL is fine then)
+  BFX_REQUIRE(out && nx > 0 && nd0 > 0 && ncells_all >= 0 && ncells >= 0 && ((x_dofmap && dofmap0) || ncells_all == 0),
               "bfx_asm_create: bad arguments");
   cudaStream_t st = S(stream);
   bfx_asm* P = new bfx_asm();
@@ -1220,27 +1238,23 @@ int bfx_assemble_vector_cells(const bfx_asm_t* P, int kernel_id, const double* x
   return dispatch_vector(kernel_id, a, S(stream));
 }
 
-int bfx_assemble_scalar_cells(const bfx_asm_t* P, int kernel_id, const double* x, const bfx_coeffs_t* coeffs,
-                              const double* constants, int n_constants, double* result_host, bfx_stream_t stream)
+namespace
 {
-  AsmArgs a;
-  int e = fill_common(P, kernel_id, 0, x, coeffs, constants, n_constants, a);
-  if (e)
-    return e;
-  BFX_REQUIRE(result_host, "bfx_assemble_scalar_cells: null result");
-  cudaStream_t st = S(stream);
-  a.cells = P->cells;
-  a.n = P->ncells;
+// sum of a functional kernel over the cells / entities of `a`, brought to the host
+int run_scalar(int kernel_id, const AsmArgs& a, double* result_host, cudaStream_t st)
+{
   double* d_res = nullptr;
   BFX_CUDA(cudaMalloc(&d_res, sizeof(double)));
   BFX_CUDA(cudaMemsetAsync(d_res, 0, sizeof(double), st));
   if (a.n > 0)
   {
+    const unsigned grid = grid_for(a.n, 256, 8);
     switch (kernel_id)
     {
-    case BFX_K_L2NORM2_P1_TET_M:
-      k_scalar_cells<el::L2Norm2P1Tet><<<grid_for(a.n, 256, 8), 256, 0, st>>>(a, d_res);
-      break;
+    case BFX_K_L2NORM2_P1_TET_M: k_scalar_cells<el::L2Norm2P1Tet><<<grid, 256, 0, st>>>(a, d_res); break;
+    case BFX_K_ONE_TRI_DS_M: k_scalar_cells<el::OneTriDS><<<grid, 256, 0, st>>>(a, d_res); break;
+    case BFX_K_AVG2_COEFF_P1_TRI_DS_M: k_scalar_cells<el::Avg2CoeffP1TriDS><<<grid, 256, 0, st>>>(a, d_res); break;
+    case BFX_K_COEFF2_P1_TRI_FACET_M: k_scalar_cells<el::Coeff2P1TriFacet><<<grid, 256, 0, st>>>(a, d_res); break;
     default: cudaFree(d_res); return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a functional kernel", kernel_id);
     }
   }
@@ -1249,6 +1263,36 @@ int bfx_assemble_scalar_cells(const bfx_asm_t* P, int kernel_id, const double* x
   cudaFree(d_res);
   BFX_CHECK_LAUNCH();
   return BFX_OK;
+}
+} // namespace
+
+int bfx_assemble_scalar_cells(const bfx_asm_t* P, int kernel_id, const double* x, const bfx_coeffs_t* coeffs,
+                              const double* constants, int n_constants, double* result_host, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 0, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(result_host, "bfx_assemble_scalar_cells: null result");
+  BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
+  a.cells = P->cells;
+  a.n = P->ncells;
+  return run_scalar(kernel_id, a, result_host, S(stream));
+}
+
+int bfx_assemble_scalar_facets(const bfx_asm_t* P, int kernel_id, const double* x, const int32_t* entities,
+                               int64_t n_entities, const bfx_coeffs_t* coeffs, const double* constants, int n_constants,
+                               double* result_host, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 0, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(result_host && (entities || n_entities == 0), "bfx_assemble_scalar_facets: null argument");
+  BFX_REQUIRE(KINFO[kernel_id].facet, "kernel id %d is not a facet kernel", kernel_id);
+  a.entities = entities;
+  a.n = n_entities;
+  return run_scalar(kernel_id, a, result_host, S(stream));
 }
 
 int bfx_assemble_vector_facets(const bfx_asm_t* P, int kernel_id, const double* x, const int32_t* entities,

@@ -14,7 +14,7 @@ struct CoefArgs
     const double* v;   // coefficient dof vector
     const int32_t* dm; // its dofmap (ncells_all x WND)
     int off;           // offset of this coefficient inside w (packed layout)
-  } f[1];
+  } f[4];              // fused gather: the element's NCOEF coefficients in the order of w
 };
 
 struct AsmArgs

@@ -2691,7 +2691,10 @@ extern "C"
 {
 int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_stream_t stream)
 {
-  BFX_REQUIRE(P && P->csr && P->pos, "bfx_asm_build_chunks: plan has no matrix / position map");
+  BFX_REQUIRE(P && P->csr, "bfx_asm_build_chunks: plan has no matrix");
+  if (P->ncells == 0) // an empty integration domain (fem/assemble_matrix_impl.h:127): nothing to aggregate
+    return fail(BFX_ERR_UNSUPPORTED, "chunk plan of an empty cell list");
+  BFX_REQUIRE(P->pos, "bfx_asm_build_chunks: plan has no position map");
   cudaStream_t st = S(stream);
   const bfx_csr* csr = P->csr;
   const bool sym = (flags & BFX_CHUNKS_SYMMETRIC) != 0;

@@ -985,7 +985,9 @@ int bfx_csr_set_spmv_variant(bfx_csr_t* A, int variant)
 
 int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* y, int part, bfx_stream_t stream)
 {
-  BFX_REQUIRE(A && values && x && y, "bfx_spmv: null argument");
+  BFX_REQUIRE(A && ((values && x && y) || A->nnz == 0 || A->n_rows_owned == 0), "bfx_spmv: null argument");
+  if (A->nnz == 0)
+    return BFX_OK; // y += 0 (an empty rank: la/MatrixCSR.h:877-946 loops over no rows)
   const int32_t n = A->n_rows_owned;
   if (n == 0)
     return BFX_OK;
@@ -1175,7 +1177,9 @@ int bfx_spmv(const bfx_csr_t* A, const double* values, const double* x, double* 
 
 int bfx_spmvT(const bfx_csr_t* A, const double* values, const double* x, double* y, int part, bfx_stream_t stream)
 {
-  BFX_REQUIRE(A && values && x && y, "bfx_spmvT: null argument");
+  BFX_REQUIRE(A && ((values && x && y) || A->nnz == 0 || A->n_rows_owned == 0), "bfx_spmvT: null argument");
+  if (A->nnz == 0)
+    return BFX_OK;
   const int32_t n = A->n_rows_owned;
   if (n == 0)
     return BFX_OK;
@@ -1239,7 +1243,7 @@ int bfx_csr_insert(const bfx_csr_t* A, double* values, int kind, int dbs0, int d
 int bfx_csr_set_diagonal(const bfx_csr_t* A, double* values, const int32_t* rows, int64_t n, double diag,
                          bfx_stream_t stream)
 {
-  BFX_REQUIRE(A && values, "bfx_csr_set_diagonal: null argument");
+  BFX_REQUIRE(A && (values || A->nnz == 0), "bfx_csr_set_diagonal: null argument");
   if (n == 0)
     return BFX_OK;
   cudaStream_t st = S(stream);
@@ -1251,7 +1255,12 @@ int bfx_csr_set_diagonal(const bfx_csr_t* A, double* values, const int32_t* rows
 
 int bfx_csr_squared_norm(const bfx_csr_t* A, const double* values, double* result_host, bfx_stream_t stream)
 {
-  BFX_REQUIRE(A && values && result_host, "bfx_csr_squared_norm: null argument");
+  BFX_REQUIRE(A && (values || A->nnz == 0) && result_host, "bfx_csr_squared_norm: null argument");
+  if (A->nnz == 0)
+  {
+    *result_host = 0.0;
+    return BFX_OK;
+  }
   return reduce<0>(A->nnz_owned * A->bs0 * A->bs1, values, values, result_host, S(stream));
 }
 

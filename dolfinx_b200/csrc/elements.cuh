@@ -235,6 +235,140 @@ struct AvgMassP1TriDS
   }
 };
 
+// Shared edge of the two cells of an interior facet (macro cell [cell0 | cell1]): local vertices of the edge in each
+// cell, cell1's pair ordered like cell0's, and the edge length
+struct TriDSBase
+{
+  static constexpr int NX = 6, BS = 1;
+  static BFX_DI double edge(const double (&xc)[6][3], int lf, int (&v)[2][2])
+  {
+    const int lfs[2] = {lf & 7, lf >> 3};
+    double len = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+    {
+      double c3[3][3];
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          c3[n][m] = xc[3 * s + n][m];
+      TriBase::facet(c3, lfs[s], v[s][0], v[s][1], len);
+    }
+    // (dynamic row index: select, so that xc stays in registers)
+    double p[3] = {0, 0, 0}, q[3] = {0, 0, 0};
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+      {
+        p[m] = n == v[0][0] ? xc[n][m] : p[m];
+        q[m] = n == v[1][0] ? xc[3 + n][m] : q[m];
+      }
+    if (fabs(p[0] - q[0]) + fabs(p[1] - q[1]) + fabs(p[2] - q[2]) > 1e-12 * (1.0 + len))
+    {
+      const int t = v[1][0];
+      v[1][0] = v[1][1];
+      v[1][1] = t;
+    }
+    return len;
+  }
+};
+
+// conj(avg(v))*dS, P1 triangles (python/test/unit/fem/test_assembler.py:1003): element vector [cell0 | cell1];
+// int_edge phi = len / 2 on the two edge vertices of each cell, avg halves it
+struct AvgLoadP1TriDS : TriDSBase
+{
+  static constexpr int ND = 6, WSIZE = 0, WND = 0, WBS = 1, CSIZE = 0, RANK = 1;
+  static constexpr bool FACET = true;
+  struct Geo
+  {
+    int v[2][2];
+    double len;
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[6][3], const double*, const double*, int lf)
+  {
+    g.len = edge(xc, lf, g.v);
+  }
+  static BFX_DI void vec(const Geo& g, double (&out)[6])
+  {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+    {
+      const int s = i / 3, vi = i - 3 * s;
+      out[i] = (vi == g.v[s][0] || vi == g.v[s][1]) ? 0.25 * g.len : 0.0;
+    }
+  }
+};
+
+// functional 1*dS: the length of the interior facet (python/test/unit/fem/test_assemble_domains.py:203-210)
+struct OneTriDS : TriDSBase
+{
+  static constexpr int ND = 6, WSIZE = 0, WND = 0, WBS = 1, CSIZE = 0, RANK = 0;
+  static constexpr bool FACET = true;
+  struct Geo
+  {
+    double v;
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[6][3], const double*, const double*, int lf)
+  {
+    int v[2][2];
+    g.v = edge(xc, lf, v);
+  }
+  static BFX_DI double scalar(const Geo& g) { return g.v; }
+};
+
+// functional inner(avg(f), avg(f))*dS, f in P1 (test_assemble_domains.py:225): w = [f on cell0 (3), f on cell1 (3)];
+// with h = avg(f) linear along the edge: len (ha^2 + ha hb + hb^2) / 3
+struct Avg2CoeffP1TriDS : TriDSBase
+{
+  static constexpr int ND = 6, WSIZE = 6, WND = 6, WBS = 1, CSIZE = 0, RANK = 0;
+  static constexpr bool FACET = true;
+  struct Geo
+  {
+    double v;
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[6][3], const double* w, const double*, int lf)
+  {
+    int v[2][2];
+    const double len = edge(xc, lf, v);
+    double h[2] = {0, 0};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+        h[a] += 0.5 * ((n == v[0][a] ? w[n] : 0.0) + (n == v[1][a] ? w[3 + n] : 0.0));
+    g.v = len * (h[0] * h[0] + h[0] * h[1] + h[1] * h[1]) * (1.0 / 3.0);
+  }
+  static BFX_DI double scalar(const Geo& g) { return g.v; }
+};
+
+// functional inner(f, f)*ds on an exterior facet, f in P1 (test_assemble_domains.py:224)
+struct Coeff2P1TriFacet : TriBase
+{
+  static constexpr int WSIZE = 3, WND = 3, WBS = 1, CSIZE = 0, RANK = 0;
+  static constexpr bool FACET = true;
+  struct Geo
+  {
+    double v;
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[3][3], const double* w, const double*, int lf)
+  {
+    int a, b;
+    double len;
+    facet(xc, lf, a, b, len);
+    double fa = 0, fb = 0;
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+    {
+      fa = n == a ? w[n] : fa;
+      fb = n == b ? w[n] : fb;
+    }
+    g.v = len * (fa * fa + fa * fb + fb * fb) * (1.0 / 3.0);
+  }
+  static BFX_DI double scalar(const Geo& g) { return g.v; }
+};
+
 // ---- tetrahedra -------------------------------------------------------------------------------
 struct TetBase
 {
@@ -342,6 +476,43 @@ BFX_DI constexpr int tet_eb(int k) { return (k == 0 || k == 1 || k == 3) ? 3 : (
 //   A_vv' = S_vv' (v == v' ? 1/10 : -1/30)
 //   A_v,e(a,b) = (1/30) [ S_vb (v == a ? 3 : -1) + S_va (v == b ? 3 : -1) ]
 //   A_e(a,b),e(c,d) = (2/15) [ (1+d_ac) S_bd + (1+d_ad) S_bc + (1+d_bc) S_ad + (1+d_bd) S_ac ]
+// inner(f*g, v)*dx with f, g in P1: TWO coefficients in one integral, w = [f (4), g (4)].
+// int lambda_i lambda_j lambda_k = |det| m(i,j,k) / 720 with m = 6 (i=j=k), 2 (two equal), 1 (all different)
+struct LoadProdP1Tet : TetBase
+{
+  static constexpr int ND = 4, BS = 1, WSIZE = 8, WND = 4, WBS = 1, NCOEF = 2, CSIZE = 0, RANK = 1;
+  static constexpr bool FACET = false;
+  struct Geo
+  {
+    double b[4];
+  };
+  static BFX_DI void prepare(Geo& g, const double (&xc)[4][3], const double* w, const double*, int)
+  {
+    double n[4][3];
+    const double det = fabs(normals(xc, n));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          const double m = (i == j && j == k) ? 6.0 : ((i == j || j == k || i == k) ? 2.0 : 1.0);
+          acc = fma(m * w[j], w[4 + k], acc);
+        }
+      g.b[i] = det * acc * (1.0 / 720.0);
+    }
+  }
+  static BFX_DI void vec(const Geo& g, double (&out)[4])
+  {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      out[i] = g.b[i];
+  }
+};
+
 struct PoissonP2Tet : TetBase
 {
   static constexpr int ND = 10, BS = 1, WSIZE = 0, WND = 0, WBS = 1, CSIZE = 1, RANK = 2;

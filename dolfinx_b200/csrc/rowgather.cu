@@ -987,7 +987,10 @@ extern "C"
 {
 int bfx_asm_build_rowgather(bfx_asm_t* P, bfx_stream_t stream)
 {
-  BFX_REQUIRE(P && P->csr && P->pos, "bfx_asm_build_rowgather: plan has no matrix / position map");
+  BFX_REQUIRE(P && P->csr, "bfx_asm_build_rowgather: plan has no matrix");
+  if (P->ncells == 0)
+    return fail(BFX_ERR_UNSUPPORTED, "row-gather plan of an empty cell list");
+  BFX_REQUIRE(P->pos, "bfx_asm_build_rowgather: plan has no position map");
   const bfx_csr* csr = P->csr;
   if (!(P->nd0 == 8 && P->nd1 == 8 && P->nx == 8 && csr->bs0 == 3 && csr->bs1 == 3))
     return fail(BFX_ERR_UNSUPPORTED, "row-gather assembly is implemented for Q1 hexahedra with block size 3");

@@ -285,7 +285,10 @@ int bfx_scatter_destroy(bfx_scatter_t* s)
 
 int bfx_scatter_fwd_begin(bfx_scatter_t* s, const double* x, bfx_stream_t stream)
 {
-  BFX_REQUIRE(s && x, "bfx_scatter_fwd_begin: null argument");
+  BFX_REQUIRE(s, "bfx_scatter_fwd_begin: null plan");
+  if (s->dest.empty() && s->src.empty())
+    return BFX_OK; // Scatterer.h:256-257: nothing to exchange (x may be an empty array)
+  BFX_REQUIRE(x, "bfx_scatter_fwd_begin: null array");
   if (s->dest.empty() && s->src.empty())
     return BFX_OK; // Scatterer.h:256-257
   cudaStream_t st = S(stream);
@@ -307,7 +310,10 @@ int bfx_scatter_fwd_begin(bfx_scatter_t* s, const double* x, bfx_stream_t stream
 
 int bfx_scatter_fwd_end(bfx_scatter_t* s, double* x, int64_t n_owned, bfx_stream_t stream)
 {
-  BFX_REQUIRE(s && x, "bfx_scatter_fwd_end: null argument");
+  BFX_REQUIRE(s, "bfx_scatter_fwd_end: null plan");
+  if (s->dest.empty() && s->src.empty())
+    return BFX_OK; // Scatterer.h:256-257: nothing to exchange (x may be an empty array)
+  BFX_REQUIRE(x, "bfx_scatter_fwd_end: null array");
   if (s->dest.empty() && s->src.empty())
     return BFX_OK;
   cudaStream_t st = S(stream);
@@ -322,7 +328,10 @@ int bfx_scatter_fwd_end(bfx_scatter_t* s, double* x, int64_t n_owned, bfx_stream
 
 int bfx_scatter_rev_begin(bfx_scatter_t* s, const double* x, int64_t n_owned, bfx_stream_t stream)
 {
-  BFX_REQUIRE(s && x, "bfx_scatter_rev_begin: null argument");
+  BFX_REQUIRE(s, "bfx_scatter_rev_begin: null plan");
+  if (s->dest.empty() && s->src.empty())
+    return BFX_OK; // Scatterer.h:256-257: nothing to exchange (x may be an empty array)
+  BFX_REQUIRE(x, "bfx_scatter_rev_begin: null array");
   if (s->dest.empty() && s->src.empty())
     return BFX_OK;
   cudaStream_t st = S(stream);
@@ -344,7 +353,10 @@ int bfx_scatter_rev_begin(bfx_scatter_t* s, const double* x, int64_t n_owned, bf
 
 int bfx_scatter_rev_end(bfx_scatter_t* s, double* x, int op, bfx_stream_t stream)
 {
-  BFX_REQUIRE(s && x, "bfx_scatter_rev_end: null argument");
+  BFX_REQUIRE(s, "bfx_scatter_rev_end: null plan");
+  if (s->dest.empty() && s->src.empty())
+    return BFX_OK; // Scatterer.h:256-257: nothing to exchange (x may be an empty array)
+  BFX_REQUIRE(x, "bfx_scatter_rev_end: null array");
   if (s->dest.empty() && s->src.empty())
     return BFX_OK;
   cudaStream_t st = S(stream);

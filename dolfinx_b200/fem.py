@@ -270,6 +270,19 @@ def pack_coefficients(form: Form):
     cstride = offsets[-1]
     out = {}
     for (itype, ident), integ in form._integrals.items():
+        if itype == IntegralType.interior_facet:
+            # (nf, 2, cstride): the two restrictions of every coefficient, cell0 then cell1 (fem/pack.h:196-226)
+            f = _interior_facets_dev(form, integ)
+            c = torch.zeros((f.shape[0], 2, cstride), dtype=torch.float64, device=la._device())
+            for k in integ.coeffs:
+                u = form.coefficients[k]
+                dm = u.function_space.dofmap
+                for side in range(2):
+                    d = dm.dev[f[:, side, 0]].long()  # (nf, nd)
+                    vals = u.x.array.view(-1, dm.bs)[d].reshape(f.shape[0], -1)
+                    c[:, side, offsets[k]:offsets[k] + vals.shape[1]] = vals
+            out[(itype, ident)] = (c.reshape(f.shape[0], 2 * cstride), 2 * cstride)
+            continue
         ent, n = _entities_dev(form, integ, itype)
         c = torch.zeros((n, cstride), dtype=torch.float64, device=la._device())
         for k in integ.coeffs:
@@ -560,30 +573,60 @@ def chunk_two_stage(form: Form, A: la.MatrixCSR, ident=0) -> bool:
     return bool(n.value)
 
 
-def _interior_facet_plan(form: Form, integ: IntegralData, A: la.MatrixCSR):
-    """Plan of an interior-facet integral (fem/assemble_matrix_impl.h:442-667): every facet becomes a MACRO cell
-    whose geometry nodes and dofs are the joint arrays [cell0 | cell1]; the kernel receives the two local facet
-    indices packed as lf0 + 8 lf1.  Returns (plan, entities (facet, packed local facets) on device, n)."""
+def _interior_facets_dev(form: Form, integ: IntegralData):
+    """(nf, 2, 2) int64 device tensor [[cell0, local0], [cell1, local1]] of an interior-facet integral."""
+    torch = _torch()
+    key = ("dSf", id(integ))
+    if key not in form._plans:
+        ent = integ.entities
+        form._plans[key] = torch.as_tensor(
+            np.ascontiguousarray(np.asarray(ent).reshape(-1, 2, 2), dtype=np.int64) if not torch.is_tensor(ent)
+            else ent.reshape(-1, 2, 2).long().cpu(), device=la._device())
+    return form._plans[key]
+
+
+def _joint_dofmap(form: Form, integ: IntegralData, dm: DofMap):
+    """[dofs(cell0) | dofs(cell1)] per interior facet (fem/assemble_matrix_impl.h:581-587), cached per dofmap."""
+    torch = _torch()
+    key = ("dSdm", id(integ), id(dm))
+    if key not in form._plans:
+        f = _interior_facets_dev(form, integ)
+        form._plans[key] = (torch.cat([dm.dev[f[:, 0, 0]], dm.dev[f[:, 1, 0]]], dim=1).contiguous(), dm)
+    return form._plans[key][0]
+
+
+def _interior_facet_plan(form: Form, integ: IntegralData, A: la.MatrixCSR = None):
+    """Plan of an interior-facet integral (fem/assemble_matrix_impl.h:442-667, fem/assemble_vector_impl.h:249-339,
+    fem/assemble_scalar_impl.h:122-168): every facet becomes a MACRO cell whose geometry nodes and dofs are the joint
+    arrays [cell0 | cell1]; the kernel receives the two local facet indices packed as lf0 + 8 lf1.  Bilinear forms
+    need the matrix (CSR positions); linear forms and functionals pass None.
+    Returns (plan, entities (facet, packed local facets) on device, n)."""
     from . import _lib
 
     torch = _torch()
     key = ("dS", id(integ), _matrix_key(form, A))
     if key not in form._plans:
-        ent = integ.entities
-        f = torch.as_tensor(np.ascontiguousarray(np.asarray(ent).reshape(-1, 2, 2), dtype=np.int64)
-                            if not torch.is_tensor(ent) else ent.reshape(-1, 2, 2).long().cpu(), device=la._device())
+        f = _interior_facets_dev(form, integ)
         n = int(f.shape[0])
         mesh = form.mesh
-        dm0, dm1 = form.function_spaces[0].dofmap, form.function_spaces[1].dofmap
         xdm = torch.cat([mesh.x_dofmap[f[:, 0, 0]], mesh.x_dofmap[f[:, 1, 0]]], dim=1).contiguous()
-        j0 = torch.cat([dm0.dev[f[:, 0, 0]], dm0.dev[f[:, 1, 0]]], dim=1).contiguous()
-        j1 = j0 if dm1 is dm0 else torch.cat([dm1.dev[f[:, 0, 0]], dm1.dev[f[:, 1, 0]]], dim=1).contiguous()
+        if form.rank >= 1:
+            dm0 = form.function_spaces[0].dofmap
+        else:  # a functional has no test space: the plan carries the dofmap of its first coefficient, or the geometry's
+            dm0 = form.coefficients[0].function_space.dofmap if form.coefficients else None
+        dm1 = form.function_spaces[1].dofmap if form.rank == 2 else None
+        j0 = _joint_dofmap(form, integ, dm0) if dm0 is not None else xdm
+        j1 = None if dm1 is None else (j0 if dm1 is dm0 else _joint_dofmap(form, integ, dm1))
         entities = torch.stack([torch.arange(n, device=f.device), f[:, 0, 1] + 8 * f[:, 1, 1]], dim=1).to(torch.int32).contiguous()
-        im0 = dm0.index_map
+        if dm0 is not None:
+            n_rows = dm0.index_map.size_local + dm0.index_map.num_ghosts
+        else:
+            n_rows = int(mesh.x.shape[0])
         h = C.c_void_p()
         _lib.check(_lib.lib.bfx_asm_create(
-            C.byref(h), A._csr, xdm.data_ptr(), xdm.shape[1], j0.data_ptr(), j0.shape[1], j1.data_ptr(), j1.shape[1],
-            n, None, 0, im0.size_local + im0.num_ghosts, 1, _lib.current_stream()))
+            C.byref(h), A._csr if A is not None else None, xdm.data_ptr(), xdm.shape[1], j0.data_ptr(), j0.shape[1],
+            None if j1 is None else j1.data_ptr(), 0 if j1 is None else j1.shape[1], n, None, 0, n_rows, 1,
+            _lib.current_stream()))
         form._plans[key] = (h, entities, n, (xdm, j0, j1))  # the joint arrays are borrowed by the plan: keep them
     return form._plans[key][:3]
 
@@ -604,7 +647,10 @@ def _boundary_interior_cells(form: Form, integ: IntegralData):
     return form._plans[key]
 
 
-def _coeffs_for(form: Form, integ: IntegralData, packed):
+def _coeffs_for(form: Form, integ: IntegralData, packed, itype=None):
+    """bfx_coeffs_t of an integral: the caller's packed array (reference layout), or the fused gather of the integral's
+    active coefficients straight from their dof vectors (all of them, in the order of the kernel's w; on interior
+    facets through the joint dofmaps [cell0 | cell1])."""
     from . import _lib
 
     if packed is not None:
@@ -612,11 +658,17 @@ def _coeffs_for(form: Form, integ: IntegralData, packed):
         off = form.coefficient_offsets()[integ.coeffs[0]] if integ.coeffs else 0
         return _lib.make_coeffs(packed=c, cstride=cstride, offset=off)
     if integ.coeffs:
-        if len(integ.coeffs) != 1:
-            raise NotImplementedError("fused coefficient gather supports one active coefficient; pass pack_coefficients(form)")
-        u = form.coefficients[integ.coeffs[0]]
-        dm = u.function_space.dofmap
-        return _lib.make_coeffs(fused=(u.x.array, dm.dev, dm.shape[1], dm.bs))
+        if len(integ.coeffs) > 4:
+            raise NotImplementedError("fused coefficient gather supports up to four active coefficients; pass pack_coefficients(form)")
+        fused = []
+        for k in integ.coeffs:
+            u = form.coefficients[k]
+            dm = u.function_space.dofmap
+            if itype == IntegralType.interior_facet:
+                fused.append((u.x.array, _joint_dofmap(form, integ, dm), 2 * dm.shape[1], dm.bs))
+            else:
+                fused.append((u.x.array, dm.dev, dm.shape[1], dm.bs))
+        return _lib.make_coeffs(fused=fused)
     return _lib.make_coeffs()
 
 
@@ -645,7 +697,7 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
     try:
         for (itype, ident), integ in a._integrals.items():
             plan = None if itype == IntegralType.interior_facet else _asm_plan(a, integ, itype, A)
-            cf = _coeffs_for(a, integ, None if coeffs is None else coeffs[(itype, ident)])
+            cf = _coeffs_for(a, integ, None if coeffs is None else coeffs[(itype, ident)], itype)
             if itype == IntegralType.cell:
                 strat = _matrix_strategy(a, integ, plan, strategy)
                 mode = _lib.VALUES_OVERWRITE if A._is_zero else _lib.VALUES_ADD
@@ -736,13 +788,26 @@ def assemble_scalar(M: Form, constants=None, coeffs=None) -> float:
     carr, nc = _lib.constants_array(consts)
     total = 0.0
     for (itype, ident), integ in M._integrals.items():
-        if itype != IntegralType.cell:
-            raise NotImplementedError(f"assemble_scalar: integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
-        plan = _asm_plan(M, integ, itype, None)
-        cf = _coeffs_for(M, integ, None if coeffs is None else coeffs[(itype, ident)])
+        packed = None if coeffs is None else coeffs[(itype, ident)]
+        cf = _coeffs_for(M, integ, packed, itype)
         out = C.c_double(0.0)
-        _lib.check(_lib.lib.bfx_assemble_scalar_cells(plan, integ.kernel, M.mesh.x.data_ptr(), C.byref(cf), carr, nc,
-                                                      C.byref(out), _lib.current_stream()))
+        if itype == IntegralType.cell:
+            plan = _asm_plan(M, integ, itype, None)
+            _lib.check(_lib.lib.bfx_assemble_scalar_cells(plan, integ.kernel, M.mesh.x.data_ptr(), C.byref(cf), carr, nc,
+                                                          C.byref(out), _lib.current_stream()))
+        elif itype == IntegralType.exterior_facet:
+            # fem/assemble_scalar_impl.h:78-113
+            plan = _asm_plan(M, integ, itype, None)
+            ent, n = _entities_dev(M, integ, itype)
+            _lib.check(_lib.lib.bfx_assemble_scalar_facets(plan, integ.kernel, M.mesh.x.data_ptr(), ent.data_ptr(), n,
+                                                           C.byref(cf), carr, nc, C.byref(out), _lib.current_stream()))
+        elif itype == IntegralType.interior_facet:
+            # fem/assemble_scalar_impl.h:122-168
+            plan, ent, n = _interior_facet_plan(M, integ, None)
+            _lib.check(_lib.lib.bfx_assemble_scalar_facets(plan, integ.kernel, M.mesh.x.data_ptr(), ent.data_ptr(), n,
+                                                           C.byref(cf), carr, nc, C.byref(out), _lib.current_stream()))
+        else:
+            raise NotImplementedError(f"assemble_scalar: integral type {itype!r} is outside the hot path (SURVEY.md §8f)")
         total += out.value
     return total
 
@@ -757,8 +822,14 @@ def assemble_vector(b, L: Form, constants=None, coeffs=None):
     consts = pack_constants(L) if constants is None else np.asarray(constants, dtype=np.float64)
     carr, nc = _lib.constants_array(consts)
     for (itype, ident), integ in L._integrals.items():
+        cf = _coeffs_for(L, integ, None if coeffs is None else coeffs[(itype, ident)], itype)
+        if itype == IntegralType.interior_facet:
+            # fem/assemble_vector_impl.h:249-339: element vector [cell0 | cell1] through the joint dofmap
+            plan, ent, n = _interior_facet_plan(L, integ, None)
+            _lib.check(_lib.lib.bfx_assemble_vector_facets(plan, integ.kernel, L.mesh.x.data_ptr(), ent.data_ptr(), n,
+                                                           C.byref(cf), carr, nc, arr.data_ptr(), _lib.current_stream()))
+            continue
         plan = _asm_plan(L, integ, itype, None)
-        cf = _coeffs_for(L, integ, None if coeffs is None else coeffs[(itype, ident)])
         if itype == IntegralType.cell:
             strat = _lib.ASM_ATOMIC
             if (integ.kernel in (_lib.CHUNKED_VECTOR_KERNELS if CHUNKED_VECTORS_ALL else _lib.CHUNKED_VECTOR_DEFAULT)

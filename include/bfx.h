@@ -88,7 +88,14 @@ extern "C"
                                            cells: the plan is built on joint arrays [cell0 | cell1] of geometry nodes and
                                            dofs per facet (fem/assemble_matrix_impl.h:442-667), and the entity list of
                                            bfx_assemble_matrix_facets holds (facet, local_facet0 + 8 * local_facet1) */
-    BFX_K_COUNT = 19
+    BFX_K_AVG_LOAD_P1_TRI_DS_L = 19,    /* conj(avg(v))*dS, P1 triangles (test_assembler.py:1003): macro-cell vector */
+    BFX_K_ONE_TRI_DS_M = 20,            /* functional 1*dS (test_assemble_domains.py:203-210) */
+    BFX_K_AVG2_COEFF_P1_TRI_DS_M = 21,  /* functional inner(avg(f), avg(f))*dS, f P1 (test_assemble_domains.py:225);
+                                           w = [f on cell0 | f on cell1] (fem/pack.h:196-226) */
+    BFX_K_COEFF2_P1_TRI_FACET_M = 22,   /* functional inner(f, f)*ds on exterior facets, f P1 (test_assemble_domains.py:224) */
+    BFX_K_LOAD_PROD_P1_TET_L = 23,      /* inner(f*g, v)*dx, f and g P1: TWO coefficients in one integral,
+                                           w = [f | g] at the form's coefficient offsets (fem/Form.h:593-604) */
+    BFX_K_COUNT = 24
   };
 
   /* Static description of a kernel id: geometry nodes per cell, dofs per cell of test/trial space,
@@ -330,6 +337,12 @@ extern "C"
                                  const int32_t* entities_dev, int64_t n_entities, const int8_t* bc0_dev,
                                  const int8_t* bc1_dev, const bfx_coeffs_t* coeffs, const double* constants_host,
                                  int n_constants, double* values_dev, bfx_stream_t stream);
+  /* impl::assemble_exterior_facets / assemble_interior_facets of a functional - fem/assemble_scalar_impl.h:78-168.
+   * entities as above ((cell, local_facet), or (facet, lf0 + 8 lf1) on a macro-cell plan); the sum over the entities
+   * is written to *result_host (the caller reduces over ranks). */
+  int bfx_assemble_scalar_facets(const bfx_asm_t* plan, int kernel_id, const double* x_dev, const int32_t* entities_dev,
+                                 int64_t n_entities, const bfx_coeffs_t* coeffs, const double* constants_host,
+                                 int n_constants, double* result_host, bfx_stream_t stream);
   int bfx_assemble_vector_facets(const bfx_asm_t* plan, int kernel_id, const double* x_dev,
                                  const int32_t* entities_dev, int64_t n_entities, const bfx_coeffs_t* coeffs,
                                  const double* constants_host, int n_constants, double* b_dev, bfx_stream_t stream);

@@ -330,6 +330,87 @@ static void k_avg_mass_p1_tri_dS(double* A, const double* w, const double* c, co
           A[6 * (3 * s + v[s][a]) + 3 * t + v[t][b]] += 0.25 * len * (a == b ? 2.0 : 1.0) / 6.0;
 }
 
+/* Vertices of the shared edge in the two cells of an interior facet, cell1's pair ordered like cell0's (matched
+ * through the coordinates); returns the edge length. */
+static double tri_dS_vertices(const double* xc, const int* e, int v[2][2])
+{
+  double len = 0.0;
+  for (int s = 0; s < 2; ++s)
+  {
+    double l;
+    tri_facet(xc + 9 * s, e[s], &v[s][0], &v[s][1], &l);
+    len = l;
+  }
+  const double* p0 = xc + 3 * v[0][0];
+  const double* q0 = xc + 9 + 3 * v[1][0];
+  if (fabs(p0[0] - q0[0]) + fabs(p0[1] - q0[1]) + fabs(p0[2] - q0[2]) > 1e-12 * (1.0 + len))
+  {
+    int t = v[1][0];
+    v[1][0] = v[1][1];
+    v[1][1] = t;
+  }
+  return len;
+}
+
+/* L = conj(avg(v)) dS, P1 triangles (python/test/unit/fem/test_assembler.py:1003): macro element vector of 6 entries
+ * [cell0 | cell1]; int_edge phi_a = len / 2 for the two edge vertices of each cell, avg halves it. */
+static void k_avg_load_p1_tri_dS_L(double* b, const double* w, const double* c, const double* xc, const int* e,
+                                   const uint8_t* q, void* d)
+{
+  (void)w; (void)c; (void)q; (void)d;
+  int v[2][2];
+  const double len = tri_dS_vertices(xc, e, v);
+  for (int s = 0; s < 2; ++s)
+    for (int a = 0; a < 2; ++a)
+      b[3 * s + v[s][a]] += 0.5 * (0.5 * len);
+}
+
+/* M = 1 dS: the length of the interior facet (python/test/unit/fem/test_assemble_domains.py:203-210) */
+static void k_one_tri_dS_M(double* A, const double* w, const double* c, const double* xc, const int* e,
+                           const uint8_t* q, void* d)
+{
+  (void)w; (void)c; (void)q; (void)d;
+  int a, b;
+  double len;
+  tri_facet(xc, e[0], &a, &b, &len);
+  A[0] += len;
+}
+
+/* two-point Gauss rule on [0, 1] */
+static const double GAUSS2[2] = {0.21132486540518713, 0.7886751345948129};
+
+/* M = inner(avg(f), avg(f)) dS, f in P1 (python/test/unit/fem/test_assemble_domains.py:225): w = [f on cell0 (3),
+ * f on cell1 (3)] (the reference packs the two restrictions one after the other, fem/pack.h:196-226) */
+static void k_avg2_coeff_p1_tri_dS_M(double* A, const double* w, const double* c, const double* xc, const int* e,
+                                     const uint8_t* q, void* d)
+{
+  (void)c; (void)q; (void)d;
+  int v[2][2];
+  const double len = tri_dS_vertices(xc, e, v);
+  for (int g = 0; g < 2; ++g)
+  {
+    const double t = GAUSS2[g];
+    const double h = 0.5 * ((1.0 - t) * w[v[0][0]] + t * w[v[0][1]]) + 0.5 * ((1.0 - t) * w[3 + v[1][0]] + t * w[3 + v[1][1]]);
+    A[0] += 0.5 * len * h * h;
+  }
+}
+
+/* M = inner(f, f) ds on an exterior facet, f in P1 (python/test/unit/fem/test_assemble_domains.py:224) */
+static void k_coeff2_p1_tri_ds_M(double* A, const double* w, const double* c, const double* xc, const int* e,
+                                 const uint8_t* q, void* d)
+{
+  (void)c; (void)q; (void)d;
+  int a, b;
+  double len;
+  tri_facet(xc, e[0], &a, &b, &len);
+  for (int g = 0; g < 2; ++g)
+  {
+    const double t = GAUSS2[g];
+    const double h = (1.0 - t) * w[a] + t * w[b];
+    A[0] += 0.5 * len * h * h;
+  }
+}
+
 /* --- tetrahedra ---------------------------------------------------------- */
 
 /* J = [x1-x0, x2-x0, x3-x0] (columns), as FFCx builds it (test_custom_jit_kernels.py:173-182) */
@@ -414,6 +495,30 @@ static void k_load_p1_tet_L(double* b, const double* w, const double* c, const d
       f += w[j] * phi[j];
     for (int i = 0; i < 4; ++i)
       b[i] += pts[p][3] * det * f * phi[i];
+  }
+}
+
+/* L = f g v dx, P1 tets, f and g in P1: TWO coefficients in one integral, w = [f (4), g (4)] at the form's
+ * coefficient offsets (fem/Form.h:593-604, fem/pack.h:265-330) */
+static void k_load_prod_p1_tet_L(double* b, const double* w, const double* c, const double* xc, const int* e,
+                                 const uint8_t* q, void* d)
+{
+  (void)c; (void)e; (void)q; (void)d;
+  double K[3][3];
+  double det = fabs(tet_geometry(xc, K));
+  double pts[64][4];
+  int np = tet_rule(3, pts);
+  for (int p = 0; p < np; ++p)
+  {
+    double phi[4] = {1 - pts[p][0] - pts[p][1] - pts[p][2], pts[p][0], pts[p][1], pts[p][2]};
+    double f = 0, g = 0;
+    for (int j = 0; j < 4; ++j)
+    {
+      f += w[j] * phi[j];
+      g += w[4 + j] * phi[j];
+    }
+    for (int i = 0; i < 4; ++i)
+      b[i] += pts[p][3] * det * f * g * phi[i];
   }
 }
 
@@ -705,6 +810,11 @@ enum
   K_ACTION_POISSON_P2_TET_L = 16,
   K_L2NORM2_P1_TET_M = 17,
   K_AVG_MASS_P1_TRI_DS = 18,
+  K_AVG_LOAD_P1_TRI_DS_L = 19,
+  K_ONE_TRI_DS_M = 20,
+  K_AVG2_COEFF_P1_TRI_DS_M = 21,
+  K_COEFF2_P1_TRI_FACET_M = 22,
+  K_LOAD_PROD_P1_TET_L = 23,
   K_COUNT
 };
 
@@ -731,6 +841,11 @@ static orc_kernel_t kernel_table(int id)
   case K_ACTION_POISSON_P2_TET_L: return k_action_poisson_p2_tet_L;
   case K_L2NORM2_P1_TET_M: return k_l2norm2_p1_tet_M;
   case K_AVG_MASS_P1_TRI_DS: return k_avg_mass_p1_tri_dS;
+  case K_AVG_LOAD_P1_TRI_DS_L: return k_avg_load_p1_tri_dS_L;
+  case K_ONE_TRI_DS_M: return k_one_tri_dS_M;
+  case K_AVG2_COEFF_P1_TRI_DS_M: return k_avg2_coeff_p1_tri_dS_M;
+  case K_COEFF2_P1_TRI_FACET_M: return k_coeff2_p1_tri_ds_M;
+  case K_LOAD_PROD_P1_TET_L: return k_load_prod_p1_tet_L;
   default: return 0;
   }
 }
@@ -745,6 +860,19 @@ int orc_tabulate(int kernel_id, double* A, int nA, const double* w, const double
   memset(A, 0, sizeof(double) * nA);
   uint8_t perm = 0;
   k(A, w, c, xc, &local_entity, &perm, 0);
+  return 0;
+}
+
+/* The same for an interior-facet (macro cell) kernel: two local facet indices */
+int orc_tabulate2(int kernel_id, double* A, int nA, const double* w, const double* c, const double* xc, int lf0, int lf1)
+{
+  orc_kernel_t k = kernel_table(kernel_id);
+  if (!k)
+    return -2;
+  memset(A, 0, sizeof(double) * nA);
+  const int lf[2] = {lf0, lf1};
+  uint8_t perm[2] = {0, 0};
+  k(A, w, c, xc, lf, perm, 0);
   return 0;
 }
 
@@ -975,6 +1103,88 @@ int orc_assemble_matrix_interior_facets(int kernel_id, const int32_t* x_dofmap, 
   free(j0);
   free(j1);
   return err;
+}
+
+/* impl::assemble_interior_facets of a linear form (fem/assemble_vector_impl.h:249-339): be = [cell0 | cell1], added
+ * through the dofmaps of the two cells; coeffs is (nf, 2, cstride) (the two restrictions of every coefficient). */
+int orc_assemble_vector_interior_facets(int kernel_id, const int32_t* x_dofmap, int nx, const double* x,
+                                        const int32_t* facets, int64_t nf, const int32_t* dmap, int nd, int bs,
+                                        const double* coeffs, int cstride, const double* constants, double* b)
+{
+  orc_kernel_t kernel = kernel_table(kernel_id);
+  if (!kernel)
+    return -2;
+  double* be = (double*)malloc(sizeof(double) * 2 * bs * nd);
+  double* cdofs = (double*)malloc(sizeof(double) * 3 * 2 * nx);
+  for (int64_t f = 0; f < nf; ++f)
+  {
+    const int32_t c[2] = {facets[4 * f], facets[4 * f + 2]};
+    const int lf[2] = {facets[4 * f + 1], facets[4 * f + 3]};
+    for (int s = 0; s < 2; ++s)
+      for (int i = 0; i < nx; ++i)
+        memcpy(cdofs + 3 * (s * nx + i), x + 3 * (size_t)x_dofmap[(size_t)c[s] * nx + i], 3 * sizeof(double));
+    memset(be, 0, sizeof(double) * 2 * bs * nd);
+    uint8_t perm[2] = {0, 0};
+    kernel(be, coeffs ? coeffs + (size_t)f * 2 * cstride : 0, constants, cdofs, lf, perm, 0);
+    for (int s = 0; s < 2; ++s)
+    {
+      const int32_t* dofs = dmap + (size_t)c[s] * nd;
+      for (int i = 0; i < nd; ++i)
+        for (int k = 0; k < bs; ++k)
+          b[(size_t)bs * dofs[i] + k] += be[bs * (s * nd + i) + k];
+    }
+  }
+  free(be);
+  free(cdofs);
+  return 0;
+}
+
+/* impl::assemble_exterior_facets of a functional (fem/assemble_scalar_impl.h:78-113): entities = (cell, local facet) */
+int orc_assemble_scalar_facets(int kernel_id, const int32_t* x_dofmap, int nx, const double* x, const int32_t* entities,
+                               int64_t n, const double* coeffs, int cstride, const double* constants, double* value)
+{
+  orc_kernel_t kernel = kernel_table(kernel_id);
+  if (!kernel)
+    return -2;
+  double* cdofs = (double*)malloc(sizeof(double) * 3 * nx);
+  double v = 0.0;
+  for (int64_t index = 0; index < n; ++index)
+  {
+    const int32_t* x_dofs = x_dofmap + (size_t)entities[2 * index] * nx;
+    int local_entity = entities[2 * index + 1];
+    for (int i = 0; i < nx; ++i)
+      memcpy(cdofs + 3 * i, x + 3 * (size_t)x_dofs[i], 3 * sizeof(double));
+    uint8_t perm = 0;
+    kernel(&v, coeffs ? coeffs + (size_t)index * cstride : 0, constants, cdofs, &local_entity, &perm, 0);
+  }
+  free(cdofs);
+  *value = v;
+  return 0;
+}
+
+/* impl::assemble_interior_facets of a functional (fem/assemble_scalar_impl.h:122-168) */
+int orc_assemble_scalar_interior_facets(int kernel_id, const int32_t* x_dofmap, int nx, const double* x,
+                                        const int32_t* facets, int64_t nf, const double* coeffs, int cstride,
+                                        const double* constants, double* value)
+{
+  orc_kernel_t kernel = kernel_table(kernel_id);
+  if (!kernel)
+    return -2;
+  double* cdofs = (double*)malloc(sizeof(double) * 3 * 2 * nx);
+  double v = 0.0;
+  for (int64_t f = 0; f < nf; ++f)
+  {
+    const int32_t c[2] = {facets[4 * f], facets[4 * f + 2]};
+    const int lf[2] = {facets[4 * f + 1], facets[4 * f + 3]};
+    for (int s = 0; s < 2; ++s)
+      for (int i = 0; i < nx; ++i)
+        memcpy(cdofs + 3 * (s * nx + i), x + 3 * (size_t)x_dofmap[(size_t)c[s] * nx + i], 3 * sizeof(double));
+    uint8_t perm[2] = {0, 0};
+    kernel(&v, coeffs ? coeffs + (size_t)f * 2 * cstride : 0, constants, cdofs, lf, perm, 0);
+  }
+  free(cdofs);
+  *value = v;
+  return 0;
 }
 
 /* impl::assemble_cells of a functional (fem/assemble_scalar_impl.h:32-60): value += kernel(...) over the cells */

@@ -44,6 +44,11 @@ K_ACTION_POISSON_P1_TET_L = 15
 K_ACTION_POISSON_P2_TET_L = 16
 K_L2NORM2_P1_TET_M = 17
 K_AVG_MASS_P1_TRI_DS = 18
+K_AVG_LOAD_P1_TRI_DS_L = 19
+K_ONE_TRI_DS_M = 20
+K_AVG2_COEFF_P1_TRI_DS_M = 21
+K_COEFF2_P1_TRI_FACET_M = 22
+K_LOAD_PROD_P1_TET_L = 23
 
 
 def build(fast: bool = False) -> str:
@@ -88,6 +93,12 @@ def _i8(a):
 def tabulate(kernel_id, nA, xc, w=None, c=None, local_entity=0):
     A = np.zeros(nA)
     w, c, xc = _f64(w), _f64(c), _f64(xc)
+    if isinstance(local_entity, (tuple, list)):  # interior facet: the local facet index in each of the two cells
+        err = lib().orc_tabulate2(
+            C.c_int(kernel_id), _p(A, C.c_double), C.c_int(nA), _p(w, C.c_double), _p(c, C.c_double), _p(xc, C.c_double),
+            C.c_int(local_entity[0]), C.c_int(local_entity[1]))
+        assert err == 0
+        return A
     err = lib().orc_tabulate(
         C.c_int(kernel_id), _p(A, C.c_double), C.c_int(nA), _p(w, C.c_double), _p(c, C.c_double), _p(xc, C.c_double),
         C.c_int(local_entity),
@@ -203,6 +214,50 @@ def assemble_matrix_interior_facets(kernel_id, x_dofmap, x, facets, dmap0, bs0, 
         _p(constants, C.c_double), _p(data, C.c_double), _p(cols, C.c_int32), _p(row_ptr, C.c_int64))
     if err:
         raise RuntimeError("Entry not in sparsity")
+
+
+def assemble_vector_interior_facets(kernel_id, x_dofmap, x, facets, dmap, bs, b, coeffs=None, constants=None):
+    """impl::assemble_interior_facets of a linear form (fem/assemble_vector_impl.h:249-339); coeffs (nf, 2*cstride)."""
+    x_dofmap, dmap = _i32(x_dofmap), _i32(dmap)
+    facets = _i32(np.asarray(facets).reshape(-1, 4))
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    cstride = 0 if coeffs is None else coeffs.shape[1] // 2
+    err = lib().orc_assemble_vector_interior_facets(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(facets, C.c_int32), C.c_int64(len(facets)), _p(dmap, C.c_int32), C.c_int(dmap.shape[1]), C.c_int(bs),
+        _p(coeffs, C.c_double), C.c_int(cstride), _p(constants, C.c_double), _p(b, C.c_double))
+    assert err == 0
+    return b
+
+
+def assemble_scalar_facets(kernel_id, x_dofmap, x, entities, coeffs=None, constants=None):
+    """fem::assemble_scalar over exterior facets (fem/assemble_scalar_impl.h:78-113); entities (n, 2)."""
+    x_dofmap = _i32(x_dofmap)
+    entities = _i32(np.asarray(entities).reshape(-1, 2))
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    cstride = 0 if coeffs is None else coeffs.shape[1]
+    out = C.c_double(0.0)
+    err = lib().orc_assemble_scalar_facets(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(entities, C.c_int32), C.c_int64(len(entities)), _p(coeffs, C.c_double), C.c_int(cstride),
+        _p(constants, C.c_double), C.byref(out))
+    assert err == 0
+    return out.value
+
+
+def assemble_scalar_interior_facets(kernel_id, x_dofmap, x, facets, coeffs=None, constants=None):
+    """fem::assemble_scalar over interior facets (fem/assemble_scalar_impl.h:122-168); coeffs (nf, 2*cstride)."""
+    x_dofmap = _i32(x_dofmap)
+    facets = _i32(np.asarray(facets).reshape(-1, 4))
+    coeffs, constants, x = _f64(coeffs), _f64(constants), _f64(x)
+    cstride = 0 if coeffs is None else coeffs.shape[1] // 2
+    out = C.c_double(0.0)
+    err = lib().orc_assemble_scalar_interior_facets(
+        C.c_int(kernel_id), _p(x_dofmap, C.c_int32), C.c_int(x_dofmap.shape[1]), _p(x, C.c_double),
+        _p(facets, C.c_int32), C.c_int64(len(facets)), _p(coeffs, C.c_double), C.c_int(cstride),
+        _p(constants, C.c_double), C.byref(out))
+    assert err == 0
+    return out.value
 
 
 def assemble_scalar(kernel_id, x_dofmap, x, cells, coeffs=None, constants=None):

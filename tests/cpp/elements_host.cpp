@@ -41,6 +41,17 @@ int run_vector(const double* xc_flat, const double* w, const double* c, int lf, 
     b[i] = out[i];
   return N;
 }
+
+template <class E>
+int run_scalar(const double* xc_flat, const double* w, const double* c, int lf, double* v)
+{
+  double xc[E::NX][3];
+  std::memcpy(xc, xc_flat, sizeof(xc));
+  typename E::Geo g;
+  E::prepare(g, xc, w, c, lf);
+  v[0] = E::scalar(g);
+  return 1;
+}
 } // namespace
 
 /// Element tensor of kernel `id` for one cell: returns the number of scalars written to out, or -1
@@ -64,6 +75,12 @@ extern "C" int elements_host_tabulate(int id, const double* xc, const double* w,
   case BFX_K_FACET_LOAD_P1_TET_L: return run_vector<el::FacetLoadP1Tet>(xc, w, c, lf, out);
   case BFX_K_ACTION_POISSON_P1_TET_L: return run_vector<el::ActionOf<el::PoissonP1Tet>>(xc, w, c, lf, out);
   case BFX_K_ACTION_POISSON_P2_TET_L: return run_vector<el::ActionOf<el::PoissonP2Tet>>(xc, w, c, lf, out);
+  case BFX_K_AVG_LOAD_P1_TRI_DS_L: return run_vector<el::AvgLoadP1TriDS>(xc, w, c, lf, out);
+  case BFX_K_LOAD_PROD_P1_TET_L: return run_vector<el::LoadProdP1Tet>(xc, w, c, lf, out);
+  case BFX_K_ONE_TRI_DS_M: return run_scalar<el::OneTriDS>(xc, w, c, lf, out);
+  case BFX_K_AVG2_COEFF_P1_TRI_DS_M: return run_scalar<el::Avg2CoeffP1TriDS>(xc, w, c, lf, out);
+  case BFX_K_COEFF2_P1_TRI_FACET_M: return run_scalar<el::Coeff2P1TriFacet>(xc, w, c, lf, out);
+  case BFX_K_L2NORM2_P1_TET_M: return run_scalar<el::L2Norm2P1Tet>(xc, w, c, lf, out);
   default: return -1;
   }
 }

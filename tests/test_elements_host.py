@@ -5,7 +5,7 @@ affine cells, entry by entry, for every local facet.  This puts the source the G
 GPU tests then only have to show that the same source gives the same numbers on the device.
 
 Not covered here (device-only code paths, covered by tests/test_gpu_parity.py): the Q1 elasticity matrix kernels
-(assemble.cu / rowgather.cu), the interior-facet macro-cell kernel (two entity indices), the functional kernel."""
+(assemble.cu / rowgather.cu)."""
 
 import ctypes as C
 import os
@@ -22,7 +22,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNELS = [_lib.K_LAPLACE_P1_TRI_A, _lib.K_SOURCE_P1_TRI_L, _lib.K_MASS_COEFF_P1_TRI_A, _lib.K_LOAD_COEFF_P1_TRI_L,
            _lib.K_FACET_MASS_P1_TRI_A, _lib.K_FACET_CONST_P1_TRI_L, _lib.K_POISSON_P1_TET_A, _lib.K_LOAD_P1_TET_L,
            _lib.K_POISSON_P2_TET_A, _lib.K_LOAD_P2_TET_L, _lib.K_LOAD_Q1_HEX_L, _lib.K_FACET_LOAD_P1_TET_L,
-           _lib.K_FACET_MASS_P1_TET_A, _lib.K_ACTION_POISSON_P1_TET_L, _lib.K_ACTION_POISSON_P2_TET_L]
+           _lib.K_FACET_MASS_P1_TET_A, _lib.K_ACTION_POISSON_P1_TET_L, _lib.K_ACTION_POISSON_P2_TET_L,
+           _lib.K_L2NORM2_P1_TET_M, _lib.K_COEFF2_P1_TRI_FACET_M, _lib.K_LOAD_PROD_P1_TET_L]
+# interior-facet kernels: macro cells [cell0 | cell1], two local facet indices
+DS_KERNELS = [_lib.K_AVG_MASS_P1_TRI_DS, _lib.K_AVG_LOAD_P1_TRI_DS_L, _lib.K_ONE_TRI_DS_M, _lib.K_AVG2_COEFF_P1_TRI_DS_M]
 
 
 @pytest.fixture(scope="module")
@@ -62,7 +65,7 @@ def _cell(nx, rng):
 def test_device_element_source_equals_oracle_quadrature(oracle, hostlib, kid):
     ki = _lib.kernel_info(kid)
     n = ki.nd * ki.bs
-    nA = n * n if ki.rank == 2 else n
+    nA = n * n if ki.rank == 2 else (n if ki.rank == 1 else 1)
     nfacets = {3: 3, 4: 4, 8: 6}[ki.nx] if ki.facet else 1
     rng = np.random.default_rng(1000 + kid)
     for trial in range(5):
@@ -80,6 +83,43 @@ def test_device_element_source_equals_oracle_quadrature(oracle, hostlib, kid):
             if ki.rank == 2 and ki.w_size == 0:
                 A = out.reshape(n, n)
                 assert np.max(np.abs(A - A.T)) <= 1e-14 * scale  # all bilinear benchmark forms are symmetric
+
+
+def _macro_cell(rng, lf0, lf1, order1):
+    """Two triangles sharing an edge: cell0 a random affine triangle whose local facet lf0 is the shared edge, cell1 the
+    edge vertices (in the order `order1`) and a point on the other side placed at local index lf1."""
+    c0 = _cell(3, rng)
+    e = [v for v in range(3) if v != lf0]
+    a, b = c0[e[0]], c0[e[1]]
+    apex = a + b - c0[lf0] + 0.3 * (b - a) * rng.standard_normal()  # reflected through the edge midpoint, sheared
+    c1 = np.zeros((3, 3))
+    others = [v for v in range(3) if v != lf1]
+    ends = (a, b) if order1 == 0 else (b, a)
+    c1[others[0]], c1[others[1]], c1[lf1] = ends[0], ends[1], apex
+    return np.ascontiguousarray(np.vstack([c0, c1]))
+
+
+@pytest.mark.parametrize("kid", DS_KERNELS)
+def test_interior_facet_element_source_equals_oracle(oracle, hostlib, kid):
+    ki = _lib.kernel_info(kid)
+    assert ki.nx == 6 and ki.facet
+    n = ki.nd * ki.bs
+    nA = n * n if ki.rank == 2 else (n if ki.rank == 1 else 1)
+    rng = np.random.default_rng(2000 + kid)
+    for lf0 in range(3):
+        for lf1 in range(3):
+            for order1 in range(2):
+                xc = _macro_cell(rng, lf0, lf1, order1)
+                w = rng.standard_normal(max(ki.w_size, 1))
+                c = np.ones(1)
+                out = np.zeros(nA)
+                got = hostlib.elements_host_tabulate(C.c_int(kid), xc.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                                                     c.ctypes.data_as(C.c_void_p), C.c_int(lf0 + 8 * lf1),
+                                                     out.ctypes.data_as(C.c_void_p))
+                assert got == nA
+                ref = oracle.tabulate(kid, nA, xc, w, c, (lf0, lf1))
+                scale = max(np.max(np.abs(ref)), 1e-300)
+                assert np.max(np.abs(out - ref)) <= 1e-12 * scale, (kid, lf0, lf1, order1)
 
 
 def test_kernel_id_tables_agree(oracle):

@@ -808,3 +808,152 @@ def test_block_mode_expanded(bfx, oracle):
     A.mult(x, y)
     B.mult(xe, ye)
     assert np.allclose(y.array.cpu().numpy(), dense @ xh, rtol=1e-14) and np.allclose(ye.array.cpu().numpy(), dense @ xh, rtol=1e-14)
+
+
+def test_facet_functionals_and_interior_facet_vector(bfx, oracle):
+    """Row f3 of SURVEY.md §8: interior-facet linear forms (fem/assemble_vector_impl.h:249-339) and the facet branches of
+    assemble_scalar (fem/assemble_scalar_impl.h:78-168) on the CUDA path: the reference's expectations
+    (test_assemble_domains.py:203-240) and the oracle, fused and packed coefficients, additivity of a form with
+    cell + exterior + interior integrals."""
+    fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
+    from dolfinx_b200 import mesh as M
+
+    N = 10
+    p = P.tri_p1(N, N)
+    msh, V = make_space(bfx, p)
+    facets = M.interior_facets(p.x_dofmap, M.TRI_FACETS)
+    ext = M.exterior_facets(p.x_dofmap, M.TRI_FACETS)
+    length = 2 * (N - 1) + N * np.sqrt(2.0)
+    one = fem.Form([], {fem.IntegralType.interior_facet: [(0, K.K_ONE_TRI_DS_M, facets, [])]}, mesh=msh)
+    assert fem.assemble_scalar(one) == pytest.approx(length, rel=1e-13)
+
+    f = fem.Function(V)
+    fv = p.dof_coords[:, 0] + 2 * p.dof_coords[:, 1] ** 2
+    f.x.array.copy_(torch.from_numpy(fv).to(f.x.array.device))
+    j3 = fem.Form([], {fem.IntegralType.interior_facet: [(0, K.K_AVG2_COEFF_P1_TRI_DS_M, facets, [0])]}, coefficients=[f], mesh=msh)
+    w3 = np.concatenate([fv[p.dofmap[facets[:, 0, 0]]], fv[p.dofmap[facets[:, 1, 0]]]], axis=1)
+    ref3 = oracle.assemble_scalar_interior_facets(oracle.K_AVG2_COEFF_P1_TRI_DS_M, p.x_dofmap, p.x, facets, coeffs=w3)
+    got3 = fem.assemble_scalar(j3)
+    assert got3 == pytest.approx(ref3, rel=1e-12)
+    assert fem.assemble_scalar(j3, coeffs=fem.pack_coefficients(j3)) == pytest.approx(ref3, rel=1e-12)  # packed layout
+    j2 = fem.Form([], {fem.IntegralType.exterior_facet: [(0, K.K_COEFF2_P1_TRI_FACET_M, ext, [0])]}, coefficients=[f], mesh=msh)
+    ref2 = oracle.assemble_scalar_facets(oracle.K_COEFF2_P1_TRI_FACET_M, p.x_dofmap, p.x, ext, coeffs=fv[p.dofmap[ext[:, 0]]])
+    got2 = fem.assemble_scalar(j2)
+    assert got2 == pytest.approx(ref2, rel=1e-12)
+    # additivity (test_assemble_domains.py:213-240): one form with both facet integrals
+    j23 = fem.Form([], {fem.IntegralType.exterior_facet: [(0, K.K_COEFF2_P1_TRI_FACET_M, ext, [0])],
+                        fem.IntegralType.interior_facet: [(0, K.K_AVG2_COEFF_P1_TRI_DS_M, facets, [0])]},
+                   coefficients=[f], mesh=msh)
+    assert fem.assemble_scalar(j23) == pytest.approx(got2 + got3, rel=1e-13)
+    # f = 2 / 3: the reference's constants
+    f.x.array.fill_(3.0)
+    assert fem.assemble_scalar(j3) == pytest.approx(9.0 * length, rel=1e-13)
+    f.x.array.fill_(2.0)
+    assert fem.assemble_scalar(j2) == pytest.approx(16.0, rel=1e-13)
+
+    # linear form conj(avg(v))*dS (test_assembler.py:1003)
+    L = fem.Form([V], {fem.IntegralType.interior_facet: [(0, K.K_AVG_LOAD_P1_TRI_DS_L, facets, [])]})
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    ref = np.zeros(p.ndofs)
+    oracle.assemble_vector_interior_facets(oracle.K_AVG_LOAD_P1_TRI_DS_L, p.x_dofmap, p.x, facets, p.dofmap, 1, ref)
+    got = b.array.cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= TOL * np.max(np.abs(ref))
+    assert got.sum() == pytest.approx(length, rel=1e-13)
+    fem.assemble_vector(b, L)  # accumulates (fem/assembler.h:230-257)
+    assert np.max(np.abs(b.array.cpu().numpy() - 2 * ref)) <= 2 * TOL * np.max(np.abs(ref))
+
+
+def test_two_fused_coefficients(bfx, oracle):
+    """An integral with TWO active coefficients (L = f g v dx): the fused gather takes both from their dof vectors, the
+    packed path reads the reference layout [f | g] at the form's coefficient offsets; both equal the oracle."""
+    fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
+    p = P.tet_p1(5, numbering="random")
+    msh, V = make_space(bfx, p)
+    dc = p.dof_coords
+    fv, gv = 1 + dc[:, 0] + np.sin(3 * dc[:, 1]), 2 - dc[:, 1] + dc[:, 2] ** 2
+    f, g = fem.Function(V), fem.Function(V)
+    f.x.array.copy_(torch.from_numpy(fv).to(f.x.array.device))
+    g.x.array.copy_(torch.from_numpy(gv).to(g.x.array.device))
+    L = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_LOAD_PROD_P1_TET_L, None, [0, 1])]}, coefficients=[f, g])
+    cells = np.arange(len(p.dofmap), dtype=np.int32)
+    ref = np.zeros(p.ndofs)
+    oracle.assemble_vector(oracle.K_LOAD_PROD_P1_TET_L, p.x_dofmap, p.x, cells, p.dofmap, 1, ref,
+                           coeffs=np.concatenate([fv[p.dofmap], gv[p.dofmap]], axis=1))
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b, L)
+    assert np.max(np.abs(b.array.cpu().numpy() - ref)) <= TOL * np.max(np.abs(ref))
+    b2 = la.Vector(V.dofmap.index_map, 1)
+    fem.assemble_vector(b2, L, coeffs=fem.pack_coefficients(L))
+    assert np.max(np.abs(b2.array.cpu().numpy() - ref)) <= TOL * np.max(np.abs(ref))
+    # wrong number of coefficients for the kernel: refused by the library, not silently mis-read
+    L1 = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_LOAD_PROD_P1_TET_L, None, [0])]}, coefficients=[f, g])
+    with pytest.raises(K.BfxError):
+        fem.assemble_vector(la.Vector(V.dofmap.index_map, 1), L1)
+
+
+def test_empty_inputs_on_gpu(bfx, oracle):
+    """Edge cases through the C-ABI (reference behaviour: an empty cell loop assembles nothing,
+    fem/assemble_matrix_impl.h:127; an empty bc list marks nothing, fem/assembler.h:558-577; set_diagonal over no
+    owned bc rows returns, :644-686): zero cells, zero facets, empty bc lists, zero-length entity lists of every
+    integral type, a vector of length zero."""
+    fem, la, K, torch, common = bfx.fem, bfx.la, bfx.lib, bfx.torch, bfx.common
+    from dolfinx_b200 import mesh as M
+
+    p = P.tet_p1(3)
+    msh, V = make_space(bfx, p)
+    none = np.zeros(0, dtype=np.int32)
+    a_all = fem.Form([V, V], {fem.IntegralType.cell: [(0, K.K_POISSON_P1_TET_A, None, [])]}, constants=[fem.Constant(2.0)])
+    sp = fem.create_sparsity_pattern(a_all)
+    sp.finalize()
+    # (1) a cell integral over NO cells on the full pattern: A stays zero, every strategy
+    for strat in (None, K.ASM_ATOMIC):
+        a0 = fem.Form([V, V], {fem.IntegralType.cell: [(0, K.K_POISSON_P1_TET_A, none, [])]}, constants=[fem.Constant(2.0)])
+        A = la.MatrixCSR(sp)
+        fem.assemble_matrix(A, a0, strategy=strat)
+        A.scatter_reverse()
+        assert A.squared_norm() == 0.0
+    # (2) empty bc list and a bc without dofs: same matrix as no bc at all
+    A1, A2, A3 = la.MatrixCSR(sp), la.MatrixCSR(sp), la.MatrixCSR(sp)
+    fem.assemble_matrix(A1, a_all)
+    fem.assemble_matrix(A2, a_all, bcs=[])
+    bc_empty = fem.DirichletBC(fem.Constant(0.0), none, V)
+    fem.assemble_matrix(A3, a_all, bcs=[bc_empty])
+    fem.set_diagonal(A3, V, [bc_empty], 1.0)
+    assert torch.equal(A1.data, A2.data) and torch.equal(A1.data, A3.data)
+    b = la.Vector(V.dofmap.index_map, 1)
+    fem.apply_lifting(b, [a_all], [[bc_empty]])
+    fem.apply_lifting(b, [a_all], [[]])
+    fem.set_bc(b, [bc_empty])
+    assert float(b.array.abs().max()) == 0.0
+    # (3) linear form and functional over no cells / no facets
+    f = fem.Function(V)
+    f.x.array.fill_(1.0)
+    L0 = fem.Form([V], {fem.IntegralType.cell: [(0, K.K_LOAD_P1_TET_L, none, [0])],
+                        fem.IntegralType.exterior_facet: [(0, K.K_FACET_LOAD_P1_TET_L, np.zeros((0, 2), dtype=np.int32), [0])]},
+                  coefficients=[f])
+    fem.assemble_vector(b, L0)
+    assert float(b.array.abs().max()) == 0.0
+    M0 = fem.Form([], {fem.IntegralType.cell: [(0, K.K_L2NORM2_P1_TET_M, none, [0])]}, coefficients=[f], mesh=msh)
+    assert fem.assemble_scalar(M0) == 0.0
+    pt = P.tri_p1(3, 3)
+    msht, Vt = make_space(bfx, pt)
+    nofacets = np.zeros((0, 2, 2), dtype=np.int32)
+    one = fem.Form([], {fem.IntegralType.interior_facet: [(0, K.K_ONE_TRI_DS_M, nofacets, [])]}, mesh=msht)
+    assert fem.assemble_scalar(one) == 0.0
+    Ls = fem.Form([Vt], {fem.IntegralType.interior_facet: [(0, K.K_AVG_LOAD_P1_TRI_DS_L, nofacets, [])]})
+    bt = la.Vector(Vt.dofmap.index_map, 1)
+    fem.assemble_vector(bt, Ls)
+    assert float(bt.array.abs().max()) == 0.0
+    # (4) zero-length vectors and an empty matrix (a rank that owns nothing): reductions, mult, scatter are no-ops
+    im0 = common.IndexMap(common.COMM_SELF, 0)
+    z = la.Vector(im0, 1)
+    assert la.norm(z) == 0.0 and la.inner_product(z, z) == 0.0
+    z.scatter_forward()
+    z.scatter_reverse()
+    sp0 = la.SparsityPattern(common.COMM_SELF, [im0, im0], [1, 1])
+    sp0.finalize()
+    A0 = la.MatrixCSR(sp0)
+    assert A0.squared_norm() == 0.0 and A0.data.numel() == 0
+    A0.mult(z, z)
+    A0.scatter_reverse()

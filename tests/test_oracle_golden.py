@@ -485,3 +485,56 @@ def test_matmul_distributed_vs_scipy(oracle, size):
             assert np.all(np.diff(row) > 0)
             assert np.all(row[: c.off_diag_offset[i] - c.row_ptr[i]] < nl) and np.all(row[c.off_diag_offset[i] - c.row_ptr[i]:] >= nl)
         assert np.all(c.data != 0.0)
+
+
+def test_facet_functionals_and_interior_facet_vector_golden(oracle):
+    """Facet branches of fem::assemble_scalar / assemble_vector pinned on the reference's own expectations:
+    assemble_scalar(1*dS) on the N x N unit square = 2 (N - 1) + N sqrt(2) (python/test/unit/fem/
+    test_assemble_domains.py:203-210); inner(f2, f2)*ds = 4 * 4 and inner(avg(f3), avg(f3))*dS = 9 * that length for
+    f2 = 2, f3 = 3 (test_additivity, :213-240); conj(avg(v))*dS (test_assembler.py:1003) sums to the same length,
+    and every entry equals the hat-function integrals over the interior edges at the vertex (brute force)."""
+    from dolfinx_b200 import mesh as M
+
+    N = 10
+    p = P.tri_p1(N, N)
+    facets = M.interior_facets(p.x_dofmap, M.TRI_FACETS)
+    ext = M.exterior_facets(p.x_dofmap, M.TRI_FACETS)
+    length = 2 * (N - 1) + N * np.sqrt(2.0)
+    val = oracle.assemble_scalar_interior_facets(oracle.K_ONE_TRI_DS_M, p.x_dofmap, p.x, facets)
+    assert val == pytest.approx(length, rel=1e-13)
+    f3 = np.full(p.ndofs, 3.0)
+    w3 = np.concatenate([f3[p.dofmap[facets[:, 0, 0]]], f3[p.dofmap[facets[:, 1, 0]]]], axis=1)
+    j3 = oracle.assemble_scalar_interior_facets(oracle.K_AVG2_COEFF_P1_TRI_DS_M, p.x_dofmap, p.x, facets, coeffs=w3)
+    assert j3 == pytest.approx(9.0 * length, rel=1e-13)
+    f2 = np.full(p.ndofs, 2.0)
+    j2 = oracle.assemble_scalar_facets(oracle.K_COEFF2_P1_TRI_FACET_M, p.x_dofmap, p.x, ext, coeffs=f2[p.dofmap[ext[:, 0]]])
+    assert j2 == pytest.approx(16.0, rel=1e-13)
+    # a non-constant coefficient: f = x + 2 y, int_{boundary} f^2 ds by hand = sum over the four sides
+    f = p.dof_coords[:, 0] + 2 * p.dof_coords[:, 1]
+    jf = oracle.assemble_scalar_facets(oracle.K_COEFF2_P1_TRI_FACET_M, p.x_dofmap, p.x, ext, coeffs=f[p.dofmap[ext[:, 0]]])
+    # y=0: int x^2 = 1/3; y=1: int (x+2)^2 = 19/3; x=0: int 4y^2 = 4/3; x=1: int (1+2y)^2 = 13/3
+    assert jf == pytest.approx((1 + 19 + 4 + 13) / 3.0, rel=1e-13)
+    b = np.zeros(p.ndofs)
+    oracle.assemble_vector_interior_facets(oracle.K_AVG_LOAD_P1_TRI_DS_L, p.x_dofmap, p.x, facets, p.dofmap, 1, b)
+    assert b.sum() == pytest.approx(length, rel=1e-13)
+    brute = np.zeros(p.ndofs)
+    for (c0, l0), (c1, l1) in facets:
+        vs = [v for k, v in enumerate(p.x_dofmap[c0]) if k != l0]
+        ln = np.linalg.norm(p.x[vs[0]] - p.x[vs[1]])
+        for v in vs:  # continuous P1: avg(v) = v on the edge, int phi = len / 2
+            brute[p.dofmap[c0][list(p.x_dofmap[c0]).index(v)]] += 0.5 * ln
+    assert np.max(np.abs(b - brute)) <= 1e-13
+
+
+def test_two_coefficient_kernel_golden(oracle):
+    """L = f g v dx with two P1 coefficients in ONE integral: sum_i b_i = int f g, exact for the quadrature used
+    (f = 1 + x, g = 2 - y + z on the unit cube: int = 3/2 * ... computed by hand = 3.0)."""
+    p = P.tet_p1(4)
+    dc = p.dof_coords
+    f, g = 1 + dc[:, 0], 2 - dc[:, 1] + dc[:, 2]
+    cells = np.arange(len(p.dofmap), dtype=np.int32)
+    w = np.concatenate([f[p.dofmap], g[p.dofmap]], axis=1)
+    b = np.zeros(p.ndofs)
+    oracle.assemble_vector(oracle.K_LOAD_PROD_P1_TET_L, p.x_dofmap, p.x, cells, p.dofmap, 1, b, coeffs=w)
+    # int (1 + x)(2 - y + z) over the unit cube = (3/2) * 2 = 3 (y and z terms cancel)
+    assert b.sum() == pytest.approx(3.0, rel=1e-13)
