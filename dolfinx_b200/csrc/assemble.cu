@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(64 * Q1_CELLS, 3) k_elasticity_q1(const AsmArg
           p = find_col(a.cols, rb, a.row_ptr[r + 1], c);
         if (p < 0)
           *a.err = 1;
-        s_p[cl][t] = p < 0 ? -1 : p * 9;
+        const bool outside = a.row_hi > 0 && (r < a.row_lo || r >= a.row_hi); // (row-range call: another call's rows)
+        s_p[cl][t] = (p < 0 || outside) ? -1 : p * 9;
         bool zr[3] = {false, false, false}, zc[3] = {false, false, false};
         if (a.bc0)
         {
@@ -657,8 +658,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 2) k_elasticity_q1_sym(const AsmAr
       }
       if (pij < 0 || pji < 0)
         *a.err = 1;
-      S.p[cl][i * 8 + j] = pij < 0 ? -1 : pij * 9;
-      S.p[cl][j * 8 + i] = pji < 0 ? -1 : pji * 9;
+      // (row-range call: blocks in rows of another call's range are dropped)
+      const bool out_i = a.row_hi > 0 && (ri < a.row_lo || ri >= a.row_hi);
+      const bool out_j = a.row_hi > 0 && (rj < a.row_lo || rj >= a.row_hi);
+      S.p[cl][i * 8 + j] = (pij < 0 || out_i) ? -1 : pij * 9;
+      S.p[cl][j * 8 + i] = (pji < 0 || out_j) ? -1 : pji * 9;
 #pragma unroll
       for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -1160,6 +1164,37 @@ int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x
     return launch_rowgather_q1(P, a, values_mode, S(stream));
   }
   return dispatch_matrix<0>(P, kernel_id, a, S(stream));
+}
+
+int bfx_assemble_matrix_rows(const bfx_asm_t* P, int kernel_id, const double* x, const int8_t* bc0, const int8_t* bc1,
+                             const bfx_coeffs_t* coeffs, const double* constants, int n_constants, double* values,
+                             int32_t row_begin, int32_t row_end, int reuse_records, bfx_stream_t stream)
+{
+  AsmArgs a;
+  int e = fill_common(P, kernel_id, 2, x, coeffs, constants, n_constants, a);
+  if (e)
+    return e;
+  BFX_REQUIRE(values, "bfx_assemble_matrix_rows: null values");
+  if (kernel_id != BFX_K_ELASTICITY_Q1_HEX_A || !P->rowgather)
+    return fail(BFX_ERR_UNSUPPORTED, "bfx_assemble_matrix_rows: kernel id %d / plan has no row-gather variant", kernel_id);
+  const int tr = rowgather_tile_rows(P);
+  BFX_REQUIRE(tr > 0 && row_begin >= 0 && row_begin <= row_end && row_end <= P->csr->n_rows_all
+                  && row_begin % tr == 0 && (row_end % tr == 0 || row_end == P->csr->n_rows_all),
+              "bfx_assemble_matrix_rows: row range [%d, %d) must be cut at multiples of %d rows", row_begin, row_end, tr);
+  a.cells = P->cells;
+  a.n = P->ncells;
+  a.bc0 = bc0;
+  a.bc1 = bc1;
+  a.values = values;
+  a.pos = P->pos;
+  return launch_rowgather_q1(P, a, BFX_VALUES_OVERWRITE, S(stream), row_begin, row_end, reuse_records != 0);
+}
+
+int bfx_asm_rowgather_tile_rows(const bfx_asm_t* P, int* rows)
+{
+  BFX_REQUIRE(P && rows, "bfx_asm_rowgather_tile_rows: null argument");
+  *rows = rowgather_tile_rows(P);
+  return BFX_OK;
 }
 
 int bfx_assemble_matrix_facets(const bfx_asm_t* P, int kernel_id, const double* x, const int32_t* entities,

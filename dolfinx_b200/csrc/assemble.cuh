@@ -39,6 +39,9 @@ struct AsmArgs
   const double* x0;
   double alpha;
   int* err;
+  // RED kernels called for a row range of the matrix (bfx_assemble_matrix_rows): contributions to rows outside
+  // [row_lo, row_hi) are dropped; row_hi == 0: no filter
+  int32_t row_lo, row_hi;
 };
 } // namespace bfx
 
@@ -163,7 +166,9 @@ int grouped_vector_supported(int kernel_id);
 int chunked_vector_cells(int kernel_id);
 int launch_vector_grouped(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st);
 // rowgather.cu
-int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st);
+int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st, int32_t row_begin = 0,
+                        int32_t row_end = -1, bool reuse_records = false);
+int rowgather_tile_rows(const bfx_asm* P);
 void free_rowgather(bfx_rowgather* g);
 // assemble.cu: the cell-parallel fp64-RED Q1 elasticity kernel (used for non-affine cells by the row-gather path)
 int launch_q1_red(const bfx_asm* P, const AsmArgs& a, cudaStream_t st);

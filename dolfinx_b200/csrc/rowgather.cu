@@ -631,7 +631,9 @@ __global__ void k_bg_node_masks(int64_t n_nodes, const int8_t* __restrict__ bc, 
 
 struct BGArgs
 {
-  int64_t ntiles;
+  int64_t ntiles;     // all tiles of the plan
+  int64_t tile_begin; // this launch: tiles [tile_begin, tile_end)
+  int64_t tile_end;
   const BGTile* tiles;
   const int32_t* cells;
   const uint16_t *perm, *ent;
@@ -721,12 +723,12 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
     }
   };
 
-  int64_t T = blockIdx.x;
-  if (T >= g.ntiles)
+  int64_t T = g.tile_begin + blockIdx.x;
+  if (T >= g.tile_end)
     return;
   // ---- prologue: headers of the first two tiles, lists and records of the first
   fetch_hdr(T, 0);
-  if (T + G < g.ntiles)
+  if (T + G < g.tile_end)
     fetch_hdr(T + G, 1);
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -737,16 +739,16 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  for (int it = 0; T < g.ntiles; ++it, T += G)
+  for (int it = 0; T < g.tile_end; ++it, T += G)
   {
     const int st = it & 1;
     const BGTile& h = s_hdr[it % 3];
     const int64_t N = T + G, NN = T + 2 * G;
     // ---- next tile: lists (first level); the tile after it: header
     int32_t cid_n = -1;
-    if (N < g.ntiles)
+    if (N < g.tile_end)
       cid_n = fetch_lists(N, s_hdr[(it + 1) % 3], st ^ 1);
-    if (NN < g.ntiles)
+    if (NN < g.tile_end)
       fetch_hdr(NN, (it + 2) % 3);
 
     const unsigned char* base = stage0 + (size_t)st * stage_bytes;
@@ -875,7 +877,14 @@ void free_rowgather(bfx_rowgather* g)
   delete g;
 }
 
-int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st)
+int rowgather_tile_rows(const bfx_asm* P) { return (P && P->rowgather && P->rowgather->bg_ok) ? BG_ROWS : 0; }
+
+// row_begin / row_end (block rows, multiples of BG_ROWS; row_end < 0: all rows): the rows this call writes.  Every row
+// is formed completely from the plan's cells, so calls on disjoint row ranges add up to the one-launch result: ghost
+// rows first, their exchange behind the owned rows (fem.assemble_matrix_overlapped).  reuse_records: the cell records
+// and the list of non-affine cells of the previous call on the same geometry are still valid.
+int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaStream_t st, int32_t row_begin,
+                        int32_t row_end, bool reuse_records)
 {
   const bfx_rowgather* G = P->rowgather;
   if (!G)
@@ -883,15 +892,24 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
   if (a.dofmap1 != a.dofmap0)
     return fail(BFX_ERR_UNSUPPORTED, "row-gather assembly needs identical test and trial dofmaps");
   const bfx_csr* csr = P->csr;
+  const bool ranged = row_end >= 0 && !(row_begin == 0 && row_end >= csr->n_rows_all);
+  const bool use_bg = G->bg_ok && !getenv("BFX_ROWGATHER_V1");
+  if (ranged && !use_bg)
+    return fail(BFX_ERR_UNSUPPORTED, "row-range assembly needs the block-gather plan");
   // pre-pass: cell records + list of cells that are not parallelepipeds
-  BFX_CUDA(cudaMemsetAsync(G->na_count, 0, sizeof(unsigned long long), st));
-  if (P->ncells > 0)
-    k_rg_records<<<grid_for(P->ncells, 128, 0), 128, 0, st>>>(P->ncells, P->cells, P->x_dofmap, a.x, G->rec, G->na_cells,
-                                                               G->na_count);
-  if (G->bg_ok && !getenv("BFX_ROWGATHER_V1")) // block-gather kernel (default); the round-1 kernel stays for A/B runs
+  if (!reuse_records)
+  {
+    BFX_CUDA(cudaMemsetAsync(G->na_count, 0, sizeof(unsigned long long), st));
+    if (P->ncells > 0)
+      k_rg_records<<<grid_for(P->ncells, 128, 0), 128, 0, st>>>(P->ncells, P->cells, P->x_dofmap, a.x, G->rec, G->na_cells,
+                                                                 G->na_count);
+  }
+  if (use_bg) // block-gather kernel (default); the round-1 kernel stays for A/B runs
   {
     BGArgs b;
     b.ntiles = G->bg_ntiles;
+    b.tile_begin = ranged ? row_begin / BG_ROWS : 0;
+    b.tile_end = ranged ? std::min<int64_t>(((int64_t)row_end + BG_ROWS - 1) / BG_ROWS, G->bg_ntiles) : G->bg_ntiles;
     b.tiles = static_cast<const BGTile*>(G->bg_tiles);
     b.cells = G->bg_cells, b.perm = G->bg_perm, b.ent = G->bg_ent;
     b.rec = G->rec;
@@ -925,12 +943,12 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
     const size_t stage = (size_t)b.cell_cap * RG_STRIDE * 8 + (size_t)b.inc_cap * 16 + (((size_t)b.nb_cap * 2 + 15) & ~(size_t)15)
                          + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16;
     const size_t smem = sizeof(double) * (size_t)b.img_cap + 3 * sizeof(BGTile) + 2 * stage;
-    if (G->bg_ntiles > 0)
+    if (b.tile_end > b.tile_begin)
     {
       BFX_CUDA(cudaFuncSetAttribute(k_q1_blockgather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
       BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_q1_blockgather, BG_THREADS, smem));
-      const int64_t grid = std::min<int64_t>(G->bg_ntiles, (int64_t)sm_count() * std::max(per_sm, 1));
+      const int64_t grid = std::min<int64_t>(b.tile_end - b.tile_begin, (int64_t)sm_count() * std::max(per_sm, 1));
       k_q1_blockgather<<<(unsigned)grid, BG_THREADS, smem, st>>>(b);
     }
     BFX_CHECK_LAUNCH();
@@ -939,6 +957,11 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
     nb.n = P->ncells;
     nb.n_dev = G->na_count;
     nb.pos = nullptr;
+    if (ranged) // the non-affine cells add to this call's rows only
+    {
+      nb.row_lo = (int32_t)(b.tile_begin * BG_ROWS);
+      nb.row_hi = (int32_t)std::min<int64_t>(b.tile_end * BG_ROWS, csr->n_rows_all);
+    }
     return launch_q1_red(P, nb, st);
   }
   RGArgs g;

@@ -749,6 +749,36 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
         raise NotImplementedError("overlapped assembly handles cell integrals")
 
     was_zero = A._is_zero
+    if was_zero and len(items) == 1 and items[0][1].kernel in _lib.ROWGATHER_KERNELS and strategy in (None, _lib.ASM_ROWGATHER):
+        # Row-gather kernels form every CSR row completely from the cells of this rank, so the overlap splits the ROWS:
+        # ghost rows (the tail of the row range) first, their exchange behind the owned rows; every value is written
+        # once, which also absorbs the pending zero-fill.
+        (itype, ident), integ = items[0]
+        plan = _asm_plan(a, integ, itype, A)
+        if _matrix_strategy(a, integ, plan, strategy) == _lib.ASM_ROWGATHER:
+            tr = C.c_int(0)
+            _lib.check(_lib.lib.bfx_asm_rowgather_tile_rows(plan, C.byref(tr)))
+            n_owned, n_all = A.num_owned_rows(), A.num_all_rows()
+            if tr.value > 0:
+                split = (n_owned // tr.value) * tr.value
+                vals = A._take_zero_fill()
+                cf = _coeffs_for(a, integ, None, itype)
+
+                def rows(r0, r1, reuse):
+                    _lib.check(_lib.lib.bfx_assemble_matrix_rows(
+                        plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
+                        None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, vals.data_ptr(), r0, r1, reuse,
+                        _lib.current_stream()))
+
+                try:
+                    rows(split, n_all, 0)
+                    A.scatter_rev_begin()
+                    rows(0, split, 1)
+                    A.scatter_rev_end()
+                except _lib.BfxError as e:
+                    raise _translate(e) from e
+                A._is_zero = False
+                return A
     vals = A._values()  # (a pending set_value(0) is written here)
 
     def run(tag_index):

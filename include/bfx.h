@@ -337,6 +337,17 @@ extern "C"
                                  const int32_t* entities_dev, int64_t n_entities, const int8_t* bc0_dev,
                                  const int8_t* bc1_dev, const bfx_coeffs_t* coeffs, const double* constants_host,
                                  int n_constants, double* values_dev, bfx_stream_t stream);
+  /* Row-range form of the row-gather strategy (plans with bfx_asm_build_rowgather): writes the CSR block rows
+   * [row_begin, row_end) - each one complete from all cells of the plan, BFX_VALUES_OVERWRITE - and nothing else.
+   * Calls on disjoint ranges add up to one bfx_assemble_matrix_cells call; a distributed caller assembles its ghost
+   * rows first, starts MatrixCSR::scatter_rev (la/MatrixCSR.h:399-468) and assembles the owned rows meanwhile.
+   * The range must be cut at multiples of bfx_asm_rowgather_tile_rows().  reuse_records != 0: the per-cell geometry
+   * records of the previous call with the same x_dev are reused. */
+  int bfx_assemble_matrix_rows(const bfx_asm_t* plan, int kernel_id, const double* x_dev, const int8_t* bc0_dev,
+                               const int8_t* bc1_dev, const bfx_coeffs_t* coeffs, const double* constants_host,
+                               int n_constants, double* values_dev, int32_t row_begin, int32_t row_end,
+                               int reuse_records, bfx_stream_t stream);
+  int bfx_asm_rowgather_tile_rows(const bfx_asm_t* plan, int* rows);
   /* impl::assemble_exterior_facets / assemble_interior_facets of a functional - fem/assemble_scalar_impl.h:78-168.
    * entities as above ((cell, local_facet), or (facet, lf0 + 8 lf1) on a macro-cell plan); the sum over the entities
    * is written to *result_host (the caller reduces over ranks). */

@@ -957,3 +957,48 @@ def test_empty_inputs_on_gpu(bfx, oracle):
     assert A0.squared_norm() == 0.0 and A0.data.numel() == 0
     A0.mult(z, z)
     A0.scatter_reverse()
+
+
+@pytest.mark.parametrize("perturb", [0.0, 0.3])
+def test_q1_rowgather_row_ranges(bfx, oracle, perturb):
+    """bfx_assemble_matrix_rows: the row-gather kernel on two disjoint row ranges (tail first, as the distributed
+    overlap does with its ghost rows) reproduces the one-call result bit for bit on affine cells, and to 1e-12 with
+    the non-affine remainder (REDs); rows outside a call's range are not touched; badly cut ranges are refused."""
+    import ctypes as C
+
+    fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
+    n = 6
+    p = P.hex_q1(n, numbering="random", seed=3, perturb=perturb)
+    if perturb:
+        keep = p.x[:, 2] < 0.5
+        p.x[keep] = P.hex_q1(n, numbering="random", seed=3).x[keep]
+    msh, V = make_space(bfx, p)
+    bdofs = np.flatnonzero(p.dof_coords[:, 0] < 1e-12).astype(np.int32)
+    bc = fem.DirichletBC(fem.Constant(np.zeros(3)), bdofs, V)
+    a, sp, A = assemble_A(bfx, V, K.K_ELASTICITY_Q1_HEX_A, constants=[[1.0, 1.5]], bcs=[bc], strategy=K.ASM_ROWGATHER)
+    whole = A.data.clone()
+    integ = a.integral(fem.IntegralType.cell, 0)
+    plan = fem._asm_plan(a, integ, fem.IntegralType.cell, A)
+    tr = C.c_int(0)
+    K.check(K.lib.bfx_asm_rowgather_tile_rows(plan, C.byref(tr)))
+    assert tr.value > 0
+    n_all = A.num_all_rows()
+    split = (n_all * 2 // 3 // tr.value) * tr.value
+    mk = fem._bc_markers(V, [bc])
+    carr, nc = K.constants_array(fem.pack_constants(a))
+    cf = K.make_coeffs()
+    vals = torch.full_like(whole, 7.0)  # (sentinel: rows outside the range must keep it)
+
+    def rows(r0, r1, reuse):
+        return K.lib.bfx_assemble_matrix_rows(plan, integ.kernel, msh.x.data_ptr(), mk.data_ptr(), mk.data_ptr(), C.byref(cf),
+                                              carr, nc, vals.data_ptr(), r0, r1, reuse, K.current_stream())
+
+    K.check(rows(split, n_all, 0))
+    cut = int(A.indptr[split]) * 9
+    assert bool((vals[:cut] == 7.0).all()), "rows before the range were written"
+    K.check(rows(0, split, 1))
+    if perturb:
+        assert float((vals - whole).abs().max()) <= TOL * float(whole.abs().max())
+    else:
+        assert torch.equal(vals, whole)
+    assert rows(1, n_all, 0) != K.OK  # not cut at a tile boundary

@@ -1,3 +1,3 @@
-mkdir -p gpurun_out/r2_31
-python -m pytest tests -m gpu -x -q -k "facet_functionals or two_fused or empty_inputs or interior_facets or exterior_facets or packed" > gpurun_out/r2_31/pytest_new.log 2>&1
-tail -40 gpurun_out/r2_31/pytest_new.log
+mkdir -p gpurun_out/r2_32
+python -m pytest tests -m gpu -x -q -k "q1 or Q1" > gpurun_out/r2_32/pytest_q1.log 2>&1
+tail -15 gpurun_out/r2_32/pytest_q1.log
