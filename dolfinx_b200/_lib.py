@@ -159,6 +159,7 @@ _SIGS = {
     "bfx_dot": ([i64, vp, vp, C.POINTER(f64), vp], ci),
     "bfx_norm": ([i64, vp, ci, C.POINTER(f64), vp], ci),
     "bfx_axpy": ([i64, f64, vp, vp, vp], ci),
+    "bfx_fill": ([i64, f64, vp, vp], ci),
     "bfx_comm_unique_id": ([C.c_char_p], ci),
     "bfx_comm_create": ([pvp, C.c_char_p, ci, ci], ci),
     "bfx_comm_destroy": ([vp], ci),

@@ -13,10 +13,13 @@
 //                         fem/assembler.h:230-257, 336-493, 513-630, 644-686
 //
 // Storage lives in HBM (DeviceArray); every arithmetic method forwards to a CUDA kernel through
-// the C-ABI.  There is no MPI in this build environment: a rank is a process with one GPU and a
-// bfx_comm_t (NCCL).  The single-rank path is complete; for several ranks the exchange plans
-// (Scatterer members, MatrixCSR ghost-row plan) are passed in as the arrays the reference's
-// constructors compute (INTEGRATION.md shows the MPI binding a maintainer would add).
+// the C-ABI.  There is no MPI in this build environment: a rank is a process (or thread) with one GPU
+// and a bfx_comm_t (NCCL) for the data path.  The HOST side of several ranks - IndexMap src/dest and
+// offsets, the Scatterer plan (common/Scatterer.h:65-198), SparsityPattern::finalize with its ghost-row
+// exchange (la/SparsityPattern.cpp:264-491) and the MatrixCSR ghost-row plan (la/MatrixCSR.h:705-849)
+// - is implemented here on two exchange callbacks of common::Comm (neighbor_alltoallv, allgatherv: what
+// MPI_Neighbor_alltoallv / MPI_Allgatherv do in the reference), so that MPI, a torch.distributed bridge
+// or the in-process mailboxes of tests/cpp/test_cpp_multirank.cpp can be plugged.
 #pragma once
 
 #include "../../include/bfx.h"
@@ -24,6 +27,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -31,6 +35,7 @@
 #include <span>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <variant>
 #include <vector>
@@ -105,6 +110,13 @@ struct Comm
 {
   int rank = 0, size = 1;
   bfx_comm_t* nccl = nullptr;
+  /// Host-side exchanges of the plan constructors (integer data; needed when size > 1):
+  /// neighbor_alltoallv(dest, src, send): send[i] goes to rank dest[i]; returns the buffer received from every rank
+  /// src[j], in the order of src (MPI_Neighbor_alltoallv on the graph src -> me -> dest).
+  using Buffers = std::vector<std::vector<std::int64_t>>;
+  std::function<Buffers(std::span<const int>, std::span<const int>, const Buffers&)> neighbor_alltoallv;
+  /// allgatherv(mine): the arrays of all ranks, by rank (MPI_Allgatherv)
+  std::function<Buffers(std::span<const std::int64_t>)> allgatherv;
 };
 
 class IndexMap
@@ -127,6 +139,38 @@ public:
   {
     if (ghosts.size() != owners.size() or !std::ranges::is_sorted(_src) or !std::ranges::is_sorted(_dest))
       throw std::runtime_error("IndexMap: inconsistent ghost data");
+  }
+  /// IndexMap(comm, local_size, ghosts, owners) on several ranks (common/IndexMap.cpp:888-932): collective.
+  /// Offset by exclusive scan, global size by reduction, src = sorted unique ghost owners, dest = the ranks that
+  /// list this rank among their src (build_src_dest).
+  IndexMap(Comm comm, std::int32_t local_size, std::span<const std::int64_t> ghosts, std::span<const int> owners)
+      : _comm(comm), _ghosts(ghosts.begin(), ghosts.end()), _owners(owners.begin(), owners.end())
+  {
+    if (ghosts.size() != owners.size())
+      throw std::runtime_error("IndexMap: inconsistent ghost data");
+    _src.assign(owners.begin(), owners.end());
+    std::ranges::sort(_src);
+    _src.erase(std::unique(_src.begin(), _src.end()), _src.end());
+    std::int64_t offset = 0, total = local_size;
+    if (comm.size > 1)
+    {
+      if (!comm.allgatherv)
+        throw std::runtime_error("IndexMap on several ranks needs Comm::allgatherv");
+      std::vector<std::int64_t> mine{local_size};
+      mine.insert(mine.end(), _src.begin(), _src.end());
+      const Comm::Buffers all = comm.allgatherv(mine);
+      total = 0;
+      for (int r = 0; r < comm.size; ++r)
+      {
+        if (r < comm.rank)
+          offset += all[r][0];
+        total += all[r][0];
+        if (std::find(all[r].begin() + 1, all[r].end(), (std::int64_t)comm.rank) != all[r].end())
+          _dest.push_back(r);
+      }
+    }
+    _local_range = {offset, offset + local_size};
+    _size_global = total;
   }
   std::array<std::int64_t, 2> local_range() const noexcept { return _local_range; }
   std::int32_t num_ghosts() const noexcept { return static_cast<std::int32_t>(_ghosts.size()); }
@@ -158,12 +202,55 @@ class Scatterer
 {
 public:
   /// One rank: all plan arrays empty, every begin/end a no-op (common/Scatterer.h:71-72)
-  Scatterer(const IndexMap& map, int bs) : _src(map.src().begin(), map.src().end()), _dest(map.dest().begin(), map.dest().end())
+  /// Several ranks: the plan of common/Scatterer.h:84-197 (collective: one neighbourhood exchange of ghost indices)
+  Scatterer(const IndexMap& map, int bs)
+      : _src(map.src().begin(), map.src().end()), _dest(map.dest().begin(), map.dest().end()), _nccl(map.comm().nccl)
   {
-    if (map.comm().size != 1)
-      throw std::runtime_error("Scatterer(map, bs): several ranks need the plan arrays (see other constructor)");
-    (void)bs;
-    create(map.comm().nccl);
+    if (map.comm().size == 1)
+      return;
+    if (!map.comm().neighbor_alltoallv)
+      throw std::runtime_error("Scatterer on several ranks needs Comm::neighbor_alltoallv");
+    // ghost positions sorted by owner, stable (:98-101); sizes / displacements per owning rank (:122-130)
+    const std::span<const int> owners = map.owners();
+    std::vector<std::int32_t> perm(owners.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](std::int32_t a, std::int32_t b) { return owners[a] < owners[b]; });
+    _displs_remote.assign(_src.size() + 1, 0);
+    _sizes_remote.assign(_src.size(), 0);
+    Comm::Buffers send(_src.size());
+    for (std::int32_t k : perm)
+    {
+      const std::size_t i = std::ranges::lower_bound(_src, owners[k]) - _src.begin();
+      send[i].push_back(map.ghosts()[k]);
+    }
+    for (std::size_t i = 0; i < _src.size(); ++i)
+    {
+      _sizes_remote[i] = (int)send[i].size();
+      _displs_remote[i + 1] = _displs_remote[i] + _sizes_remote[i];
+    }
+    // ghost global indices to their owners (:142-159)
+    const Comm::Buffers recv = map.comm().neighbor_alltoallv(_src, _dest, send);
+    _displs_local.assign(_dest.size() + 1, 0);
+    _sizes_local.assign(_dest.size(), 0);
+    const std::array<std::int64_t, 2> range = map.local_range();
+    for (std::size_t j = 0; j < _dest.size(); ++j)
+    {
+      _sizes_local[j] = (int)recv[j].size();
+      _displs_local[j + 1] = _displs_local[j] + _sizes_local[j];
+      for (std::int64_t g : recv[j])
+      {
+        if (g < range[0] or g >= range[1])
+          throw std::runtime_error("Scatterer: received index outside the owned range");
+        for (int c = 0; c < bs; ++c) // expanded by the block size (:171-197)
+          _local_inds.push_back((std::int32_t)((g - range[0]) * bs + c));
+      }
+    }
+    for (std::int32_t k : perm)
+      for (int c = 0; c < bs; ++c)
+        _remote_inds.push_back(k * bs + c);
+    for (auto* v : {&_sizes_local, &_displs_local, &_sizes_remote, &_displs_remote})
+      for (int& e : *v)
+        e *= bs;
   }
   /// Several ranks: the arrays computed by the reference constructor (common/Scatterer.h:84-197)
   Scatterer(const IndexMap& map, std::vector<std::int32_t> local_inds, std::vector<std::int32_t> remote_inds,
@@ -172,16 +259,25 @@ public:
       : _src(map.src().begin(), map.src().end()), _dest(map.dest().begin(), map.dest().end()),
         _remote_inds(std::move(remote_inds)), _sizes_remote(std::move(sizes_remote)),
         _displs_remote(std::move(displs_remote)), _local_inds(std::move(local_inds)),
-        _sizes_local(std::move(sizes_local)), _displs_local(std::move(displs_local))
+        _sizes_local(std::move(sizes_local)), _displs_local(std::move(displs_local)), _nccl(map.comm().nccl)
   {
-    create(map.comm().nccl);
   }
   Scatterer(const Scatterer&) = delete;
   ~Scatterer() { bfx_scatter_destroy(_plan); }
   const std::vector<std::int32_t>& local_indices() const noexcept { return _local_inds; }
   const std::vector<std::int32_t>& remote_indices() const noexcept { return _remote_inds; }
+  const std::vector<int>& sizes_local() const noexcept { return _sizes_local; }
+  const std::vector<int>& displs_local() const noexcept { return _displs_local; }
+  const std::vector<int>& sizes_remote() const noexcept { return _sizes_remote; }
+  const std::vector<int>& displs_remote() const noexcept { return _displs_remote; }
   std::size_t num_p2p_requests() const noexcept { return _dest.size() + _src.size(); }
-  bfx_scatter_t* plan() const { return _plan; }
+  /// the device side of the plan (index arrays, staging buffers, stream, events), created by the first exchange
+  bfx_scatter_t* plan() const
+  {
+    if (!_plan)
+      const_cast<Scatterer*>(this)->create(_nccl);
+    return _plan;
+  }
 
 private:
   void create(bfx_comm_t* nccl)
@@ -200,6 +296,7 @@ private:
   std::vector<int> _sizes_remote, _displs_remote;
   std::vector<std::int32_t> _local_inds;
   std::vector<int> _sizes_local, _displs_local;
+  bfx_comm_t* _nccl = nullptr;
   bfx_scatter_t* _plan = nullptr;
 };
 } // namespace common
@@ -215,7 +312,7 @@ enum class Norm
   frobenius
 };
 
-/// la::SparsityPattern (single-rank finalize; la/SparsityPattern.cpp:194-240, 264-491)
+/// la::SparsityPattern (la/SparsityPattern.cpp:194-240, 264-491)
 class SparsityPattern
 {
 public:
@@ -251,24 +348,96 @@ public:
     closed();
     _dm0 = dofmap0_dev, _dm1 = dofmap1_dev, _nd0 = nd0, _nd1 = nd1, _ncells = ncells;
   }
+  /// SparsityPattern::finalize (la/SparsityPattern.cpp:264-491).  On several ranks (collective): the entries inserted
+  /// into ghost rows travel to the row owners as (global row, global column, column owner) triplets (:291-383),
+  /// columns the owner did not know are appended to its column map in arrival order (:389-423), then every row is
+  /// de-duplicated and sorted (:438-478) and the column IndexMap is rebuilt (:488-490).
   void finalize()
   {
-    if (_csr)
+    if (_finalized)
       throw std::runtime_error("Sparsity pattern has already been finalised.");
-    if (_comm.size != 1)
-      throw std::runtime_error("SparsityPattern::finalize: several ranks go through the ghost-row exchange "
-                               "(dolfinx_b200.la.SparsityPattern / INTEGRATION.md)");
-    const std::int32_t n0 = _index_maps[0]->size_local() + _index_maps[0]->num_ghosts();
-    const std::int32_t l1 = _index_maps[1]->size_local();
+    const common::IndexMap& m0 = *_index_maps[0];
+    const common::IndexMap& m1 = *_index_maps[1];
+    const std::int32_t local_size0 = m0.size_local(), n0 = local_size0 + m0.num_ghosts();
+    const std::int32_t l1 = m1.size_local();
+    std::vector<std::int64_t> col_ghosts(m1.ghosts().begin(), m1.ghosts().end());
+    std::vector<int> col_owners(m1.owners().begin(), m1.owners().end());
+    if (_comm.size > 1)
+    {
+      if (_dm0)
+        throw std::runtime_error("SparsityPattern::finalize on several ranks: insert the cells on the host "
+                                 "(the device cell list is the single-rank fast path of this mirror)");
+      if (!_comm.neighbor_alltoallv)
+        throw std::runtime_error("SparsityPattern::finalize on several ranks needs Comm::neighbor_alltoallv");
+      // distinct entries of every ghost row, columns in the order of their first insertion (the COO cache order)
+      std::vector<std::vector<std::int32_t>> grow(m0.num_ghosts());
+      for (std::size_t k = 0; k < _cache_rows.size(); ++k)
+      {
+        const std::int32_t r = _cache_rows[k];
+        if (r >= local_size0 and r < n0)
+        {
+          auto& v = grow[r - local_size0];
+          if (std::find(v.begin(), v.end(), _cache_cols[k]) == v.end())
+            v.push_back(_cache_cols[k]);
+        }
+      }
+      const std::span<const int> src = m0.src(), dest = m0.dest();
+      common::Comm::Buffers send(src.size());
+      const std::array<std::int64_t, 2> range1 = m1.local_range();
+      for (std::int32_t g = 0; g < m0.num_ghosts(); ++g) // per owner: ghost rows ascending
+      {
+        auto& out = send[std::ranges::lower_bound(src, m0.owners()[g]) - src.begin()];
+        for (std::int32_t c : grow[g])
+        {
+          const bool owned = c < l1;
+          out.push_back(m0.ghosts()[g]);
+          out.push_back(owned ? range1[0] + c : m1.ghosts()[c - l1]);
+          out.push_back(owned ? _comm.rank : m1.owners()[c - l1]);
+        }
+      }
+      const common::Comm::Buffers recv = _comm.neighbor_alltoallv(src, dest, send);
+      // received columns -> local indices; unknown ones join the ghost list in arrival order
+      std::unordered_map<std::int64_t, std::int32_t> ghost_local;
+      for (std::size_t i = 0; i < col_ghosts.size(); ++i)
+        ghost_local.emplace(col_ghosts[i], l1 + (std::int32_t)i);
+      const std::int64_t row0 = m0.local_range()[0];
+      for (const auto& buf : recv)
+        for (std::size_t k = 0; k + 2 < buf.size(); k += 3)
+        {
+          const std::int64_t gr = buf[k], gc = buf[k + 1];
+          std::int32_t lc;
+          if (gc >= range1[0] and gc < range1[1])
+            lc = (std::int32_t)(gc - range1[0]);
+          else
+          {
+            auto [it, fresh] = ghost_local.try_emplace(gc, l1 + (std::int32_t)col_ghosts.size());
+            if (fresh)
+            {
+              col_ghosts.push_back(gc);
+              col_owners.push_back((int)buf[k + 2]);
+            }
+            lc = it->second;
+          }
+          _cache_rows.push_back((std::int32_t)(gr - row0));
+          _cache_cols.push_back(lc);
+        }
+    }
     if (_dm0)
     {
-      check(bfx_sparsity_build(&_csr, n0, _index_maps[0]->size_local(), l1, _dm0, _nd0, _dm1, _nd1, nullptr, _ncells,
-                               _cache_rows.data(), _cache_cols.data(), (std::int64_t)_cache_rows.size(), _bs[0], _bs[1],
-                               nullptr));
+      check(bfx_sparsity_build(&_csr, n0, local_size0, l1, _dm0, _nd0, _dm1, _nd1, nullptr, _ncells, _cache_rows.data(),
+                               _cache_cols.data(), (std::int64_t)_cache_rows.size(), _bs[0], _bs[1], nullptr));
+      const std::int64_t nnz = bfx_csr_nnz(_csr);
+      _offsets.resize(n0 + 1);
+      _edges.resize(nnz);
+      std::vector<std::int64_t> od(n0);
+      check(bfx_csr_get_structure(_csr, _offsets.data(), _edges.data(), od.data()));
+      _off_diagonal_offsets.resize(n0);
+      for (std::int32_t i = 0; i < n0; ++i)
+        _off_diagonal_offsets[i] = (std::int32_t)(od[i] - _offsets[i]);
     }
     else
     {
-      // bucket by row, de-duplicate, sort (SparsityPattern.cpp:438-478)
+      // bucket by row, de-duplicate, sort (SparsityPattern.cpp:438-478); the device copy is made on first use
       std::vector<std::vector<std::int32_t>> rows(n0);
       for (std::size_t k = 0; k < _cache_rows.size(); ++k)
       {
@@ -276,29 +445,22 @@ public:
           throw std::runtime_error("SparsityPattern: row out of range");
         rows[_cache_rows[k]].push_back(_cache_cols[k]);
       }
-      std::vector<std::int64_t> offsets(1, 0), off_diag;
-      std::vector<std::int32_t> edges;
+      _offsets.assign(1, 0);
+      _off_diagonal_offsets.clear();
       for (auto& r : rows)
       {
         std::ranges::sort(r);
         r.erase(std::unique(r.begin(), r.end()), r.end());
-        off_diag.push_back(offsets.back() + std::distance(r.begin(), std::ranges::lower_bound(r, l1)));
-        edges.insert(edges.end(), r.begin(), r.end());
-        offsets.push_back(offsets.back() + (std::int64_t)r.size());
+        _off_diagonal_offsets.push_back((std::int32_t)std::distance(r.begin(), std::ranges::lower_bound(r, l1)));
+        _edges.insert(_edges.end(), r.begin(), r.end());
+        _offsets.push_back(_offsets.back() + (std::int64_t)r.size());
       }
-      check(bfx_csr_create(&_csr, n0, _index_maps[0]->size_local(), offsets.data(), edges.data(), off_diag.data(), _bs[0],
-                           _bs[1]));
     }
     std::vector<std::int32_t>().swap(_cache_rows);
     std::vector<std::int32_t>().swap(_cache_cols);
-    const std::int64_t nnz = bfx_csr_nnz(_csr);
-    _offsets.resize(n0 + 1);
-    _edges.resize(nnz);
-    std::vector<std::int64_t> od(n0);
-    check(bfx_csr_get_structure(_csr, _offsets.data(), _edges.data(), od.data()));
-    _off_diagonal_offsets.resize(n0);
-    for (std::int32_t i = 0; i < n0; ++i)
-      _off_diagonal_offsets[i] = (std::int32_t)(od[i] - _offsets[i]);
+    if (_comm.size > 1) // the column map with the ghosts found (collective, like the reference's IndexMap constructor)
+      _index_maps[1] = std::make_shared<const common::IndexMap>(_comm, l1, col_ghosts, col_owners);
+    _finalized = true;
   }
   std::shared_ptr<const common::IndexMap> index_map(int dim) const { return _index_maps.at(dim); }
   int block_size(int dim) const { return _bs[dim]; }
@@ -317,13 +479,23 @@ public:
     final();
     return _off_diagonal_offsets;
   }
-  /// device structure shared with MatrixCSR (ownership passes to the first matrix built from it)
+  /// device structure shared with MatrixCSR (ownership passes to the first matrix built from it); patterns built on
+  /// the host upload theirs here, on first use
   bfx_csr_t* release_csr() const
   {
     final();
-    bfx_csr_t* c = _csr_released ? nullptr : _csr;
+    if (_csr_released)
+      return nullptr;
+    if (!_csr)
+    {
+      const std::int32_t n0 = _index_maps[0]->size_local() + _index_maps[0]->num_ghosts();
+      std::vector<std::int64_t> od(n0);
+      for (std::int32_t i = 0; i < n0; ++i)
+        od[i] = _offsets[i] + _off_diagonal_offsets[i];
+      check(bfx_csr_create(&_csr, n0, _index_maps[0]->size_local(), _offsets.data(), _edges.data(), od.data(), _bs[0], _bs[1]));
+    }
     _csr_released = true;
-    return c;
+    return _csr;
   }
   ~SparsityPattern()
   {
@@ -334,12 +506,12 @@ public:
 private:
   void closed() const
   {
-    if (_csr)
+    if (_finalized)
       throw std::runtime_error("Cannot insert into sparsity pattern. It has already been finalized");
   }
   void final() const
   {
-    if (!_csr)
+    if (!_finalized)
       throw std::runtime_error("Sparsity pattern has not been finalised.");
   }
   common::Comm _comm;
@@ -351,8 +523,9 @@ private:
   std::int64_t _ncells = 0;
   std::vector<std::int32_t> _edges, _off_diagonal_offsets;
   std::vector<std::int64_t> _offsets;
-  bfx_csr_t* _csr = nullptr;
+  mutable bfx_csr_t* _csr = nullptr;
   mutable bool _csr_released = false;
+  bool _finalized = false;
 };
 
 /// la::Vector<double> with device storage
@@ -372,11 +545,7 @@ public:
       : _map(map), _bs(bs), _x((std::size_t)bs * (map->size_local() + map->num_ghosts())), _scatterer(std::move(sc))
   {
   }
-  void set(T v)
-  {
-    std::vector<T> h(_x.size(), v);
-    _x.copy_from(h);
-  }
+  void set(T v) { check(bfx_fill((std::int64_t)_x.size(), v, _x.data(), nullptr)); }
   void scatter_fwd_begin() { check(bfx_scatter_fwd_begin(_scatterer->plan(), _x.data(), nullptr)); }
   void scatter_fwd_end()
   {
@@ -477,6 +646,84 @@ struct Sparsity
 } // namespace impl
 
 /// la::MatrixCSR<double> (compact block mode) with device storage
+namespace impl
+{
+/// The ghost-row exchange plan the MatrixCSR constructor builds (la/MatrixCSR.h:705-849), members as in the reference:
+/// ghost_row_to_rank (index into src), val_send_disp / val_recv_disp (already x bs0*bs1), unpack_pos (block positions
+/// of the received entries in the owner's CSR).
+struct GhostRowPlan
+{
+  std::vector<std::int32_t> ghost_row_to_rank;
+  std::vector<std::int64_t> val_send_disp, val_recv_disp, unpack_pos;
+};
+
+/// Collective over the neighbourhood of the row map (one exchange of (global row, global column) pairs)
+inline GhostRowPlan matrix_ghost_plan(const common::IndexMap& m0, const common::IndexMap& m1, std::array<int, 2> bs,
+                                      std::span<const std::int64_t> row_ptr, std::span<const std::int32_t> cols)
+{
+  const common::Comm& comm = m0.comm();
+  if (!comm.neighbor_alltoallv)
+    throw std::runtime_error("MatrixCSR on several ranks needs Comm::neighbor_alltoallv");
+  const std::int64_t bs2 = (std::int64_t)bs[0] * bs[1];
+  const std::int32_t ls0 = m0.size_local(), ls1 = m1.size_local();
+  const std::span<const int> src = m0.src(), dest = m0.dest();
+  GhostRowPlan p;
+  // owner (as index into src) of every ghost row; entries per owner (:725-742)
+  std::vector<std::int64_t> per_proc(src.size(), 0);
+  for (std::int32_t i = 0; i < m0.num_ghosts(); ++i)
+  {
+    const std::int32_t r = (std::int32_t)(std::ranges::lower_bound(src, m0.owners()[i]) - src.begin());
+    p.ghost_row_to_rank.push_back(r);
+    per_proc[r] += row_ptr[ls0 + i + 1] - row_ptr[ls0 + i];
+  }
+  p.val_send_disp.assign(src.size() + 1, 0);
+  std::partial_sum(per_proc.begin(), per_proc.end(), p.val_send_disp.begin() + 1);
+  // (global row, global column) of every ghost-row entry, per owner in ghost-row order (:750-775)
+  common::Comm::Buffers send(src.size());
+  for (std::int32_t i = 0; i < m0.num_ghosts(); ++i)
+  {
+    auto& out = send[p.ghost_row_to_rank[i]];
+    for (std::int64_t j = row_ptr[ls0 + i]; j < row_ptr[ls0 + i + 1]; ++j)
+    {
+      out.push_back(m0.ghosts()[i]);
+      const std::int32_t c = cols[j];
+      out.push_back(c < ls1 ? m1.local_range()[0] + c : m1.ghosts()[c - ls1]);
+    }
+  }
+  const common::Comm::Buffers recv = comm.neighbor_alltoallv(src, dest, send); // :777-800
+  // positions in the owner's CSR (:813-846)
+  std::unordered_map<std::int64_t, std::int32_t> ghost_local;
+  for (std::int32_t i = 0; i < m1.num_ghosts(); ++i)
+    ghost_local.emplace(m1.ghosts()[i], ls1 + i);
+  p.val_recv_disp.assign(1, 0);
+  for (const auto& buf : recv)
+  {
+    for (std::size_t k = 0; k + 1 < buf.size(); k += 2)
+    {
+      const std::int64_t lrow = buf[k] - m0.local_range()[0];
+      if (lrow < 0 or lrow >= ls0)
+        throw std::runtime_error("MatrixCSR: received a ghost row this rank does not own");
+      std::int32_t lcol;
+      if (buf[k + 1] >= m1.local_range()[0] and buf[k + 1] < m1.local_range()[1])
+        lcol = (std::int32_t)(buf[k + 1] - m1.local_range()[0]);
+      else if (auto it = ghost_local.find(buf[k + 1]); it != ghost_local.end())
+        lcol = it->second;
+      else
+        throw std::runtime_error("MatrixCSR: received ghost-row entry not in sparsity");
+      const auto b = cols.begin() + row_ptr[lrow], e = cols.begin() + row_ptr[lrow + 1];
+      const auto it = std::lower_bound(b, e, lcol);
+      if (it == e or *it != lcol)
+        throw std::runtime_error("MatrixCSR: received ghost-row entry not in sparsity");
+      p.unpack_pos.push_back(std::distance(cols.begin(), it));
+    }
+    p.val_recv_disp.push_back(p.val_recv_disp.back() + bs2 * (std::int64_t)(buf.size() / 2));
+  }
+  for (auto& d : p.val_send_disp)
+    d *= bs2;
+  return p;
+}
+} // namespace impl
+
 template <typename T = double>
 class MatrixCSR
 {
@@ -519,6 +766,11 @@ private:
                            _off_diagonal_offset.data(), _bs[0], _bs[1]));
     }
     _data = DeviceArray<T>(_cols.size() * _bs[0] * _bs[1]);
+    if (_index_maps[0]->comm().size > 1) // the constructor builds the ghost-row plan (collective, la/MatrixCSR.h:705-849)
+    {
+      const impl::GhostRowPlan g = impl::matrix_ghost_plan(*_index_maps[0], *_index_maps[1], _bs, _row_ptr, _cols);
+      set_ghost_plan(g.ghost_row_to_rank, g.val_send_disp, g.val_recv_disp, g.unpack_pos);
+    }
   }
 
 public:
@@ -532,16 +784,23 @@ public:
                                  (std::int32_t)ghost_row_to_rank.size(), val_send_disp.data(), src.data(), (int)src.size(),
                                  val_recv_disp.data(), dest.data(), (int)dest.size(), unpack_pos.data()));
   }
+  /// MatrixCSR::set(value) (la/MatrixCSR.h:239-241); a zeroed matrix lets the next assembly overwrite instead of add
   void set(T x)
   {
-    if (x == T(0))
-      _data.fill_zero();
-    else
-    {
-      std::vector<T> h(_data.size(), x);
-      _data.copy_from(h);
-    }
+    check(bfx_fill((std::int64_t)_data.size(), x, _data.data(), nullptr));
+    _known_zero = x == T(0);
   }
+  /// true until something is added / set after set(0) (or construction): the assembler's BFX_VALUES_OVERWRITE switch
+  bool known_zero() const { return _known_zero; }
+  void touched() { _known_zero = false; }
+  /// The insertion functor the reference passes to fem::assemble_matrix (la/MatrixCSR.h:134-175 mat_add_values):
+  /// here a handle on the matrix, consumed by the fem::assemble_matrix overload below (the element tensors never
+  /// visit the host, so there is nothing to call back per cell)
+  struct MatAdd
+  {
+    MatrixCSR* A;
+  };
+  MatAdd mat_add_values() { return MatAdd{this}; }
   /// MatrixCSR::set / add<BS0,BS1> — la/MatrixCSR.h:265-335
   template <int BS0 = 1, int BS1 = 1>
   void set(std::span<const T> x, std::span<const std::int32_t> rows, std::span<const std::int32_t> cols)
@@ -574,7 +833,14 @@ public:
   {
     double r = 0;
     check(bfx_csr_squared_norm(_csr, _data.data(), &r, nullptr));
-    return r; // + all-reduce over ranks (la/MatrixCSR.h:483-484) when comm.size > 1
+    if (const common::Comm& c = _index_maps[0]->comm(); c.size > 1) // la/MatrixCSR.h:483-484
+    {
+      DeviceArray<double> d(1);
+      d.copy_from(std::span<const double>(&r, 1));
+      check(bfx_comm_allreduce(c.nccl, d.data(), 1, 0, nullptr));
+      r = d.to_host()[0];
+    }
+    return r;
   }
   /// y += A x — la/MatrixCSR.h:877-946 (split around the ghost update of x)
   void mult(Vector<T>& x, Vector<T>& y) const
@@ -609,7 +875,12 @@ public:
     return A;
   }
   std::shared_ptr<const common::IndexMap> index_map(int dim) const { return _index_maps.at(dim); }
-  DeviceArray<T>& values() { return _data; }
+  /// mutable access: the caller may write, so the matrix no longer counts as known-zero
+  DeviceArray<T>& values()
+  {
+    _known_zero = false;
+    return _data;
+  }
   const DeviceArray<T>& values() const { return _data; }
   const std::vector<std::int64_t>& row_ptr() const { return _row_ptr; }
   const std::vector<std::int32_t>& cols() const { return _cols; }
@@ -632,6 +903,7 @@ private:
       throw std::runtime_error("Unsupported block size in MatrixCSR insertion");
     check(bfx_csr_insert(_csr, _data.data(), kind, BS0, BS1, x.data(), rows.data(), (int)rows.size(), cols.data(),
                          (int)cols.size(), op, nullptr));
+    _known_zero = false;
   }
   std::array<std::shared_ptr<const common::IndexMap>, 2> _index_maps;
   std::array<int, 2> _bs;
@@ -640,6 +912,7 @@ private:
   std::vector<std::int64_t> _row_ptr, _off_diagonal_offset;
   bfx_csr_t* _csr = nullptr;
   bfx_csr_scatter_t* _scatter = nullptr;
+  bool _known_zero = true; // fresh values are zero (DeviceArray)
 };
 
 /// la::transpose (la/mattrans.h:121-159): the branch without neighbours in the column map (one rank, or no ghost
@@ -977,10 +1250,12 @@ void assemble_matrix(la::MatrixCSR<T>& A, const Form<T>& a,
   {
     bfx_asm_t* plan = a.plan(key, A.csr());
     bfx_coeffs_t cf = impl::coeffs_for(a, id);
+    // a matrix known to be zero (fresh, or after set(0)) is overwritten by the aggregated kernels instead of added to
+    const int mode = A.known_zero() ? BFX_VALUES_OVERWRITE : BFX_VALUES_ADD;
     if (key.first == IntegralType::cell)
       check(bfx_assemble_matrix_cells(plan, id.kernel, a.mesh()->x.data(), mk0 ? mk0->data() : nullptr,
                                       mk1 ? mk1->data() : nullptr, &cf, c.data(), (int)c.size(), A.values().data(),
-                                      a.matrix_strategy(key, A.csr()), BFX_VALUES_ADD, nullptr));
+                                      a.matrix_strategy(key, A.csr()), mode, nullptr));
     else if (key.first == IntegralType::exterior_facet)
     {
       DeviceArray<std::int32_t> ent{std::span<const std::int32_t>(id.entities)};
@@ -991,7 +1266,16 @@ void assemble_matrix(la::MatrixCSR<T>& A, const Form<T>& a,
     }
     else
       throw std::runtime_error("integral type outside the hot path");
+    A.touched();
   }
+}
+
+/// fem::assemble_matrix(mat_add, a, bcs) with the matrix's own insertion functor (fem/assembler.h:589-602)
+template <typename T>
+void assemble_matrix(typename la::MatrixCSR<T>::MatAdd mat_add, const Form<T>& a,
+                     const std::vector<std::reference_wrapper<const DirichletBC<T>>>& bcs = {})
+{
+  assemble_matrix(*mat_add.A, a, bcs);
 }
 
 /// fem::assemble_vector(b, L) — fem/assembler.h:230-257

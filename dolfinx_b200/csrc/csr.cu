@@ -115,6 +115,12 @@ int reduce(int64_t n, const double* x, const double* y, double* result_host, cud
   return BFX_OK;
 }
 
+__global__ void k_fill(int64_t n, double v, double* __restrict__ x)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+
 __global__ void k_axpy(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y)
 {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -1285,6 +1291,21 @@ int bfx_axpy(int64_t n, double alpha, const double* x, double* y, bfx_stream_t s
   if (n <= 0)
     return BFX_OK;
   k_axpy<<<grid_for(n, 256, 16), 256, 0, S(stream)>>>(n, alpha, x, y);
+  BFX_CHECK_LAUNCH();
+  return BFX_OK;
+}
+
+int bfx_fill(int64_t n, double value, double* x, bfx_stream_t stream)
+{
+  if (n <= 0)
+    return BFX_OK;
+  BFX_REQUIRE(x, "bfx_fill: null array");
+  if (value == 0.0)
+  {
+    BFX_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, S(stream)));
+    return BFX_OK;
+  }
+  k_fill<<<grid_for(n, 256, 16), 256, 0, S(stream)>>>(n, value, x);
   BFX_CHECK_LAUNCH();
   return BFX_OK;
 }

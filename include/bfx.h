@@ -398,6 +398,8 @@ extern "C"
   int bfx_norm(int64_t n, const double* x_dev, int type /*0 l1, 1 l2^2, 2 linf*/, double* result_host,
                bfx_stream_t stream);
   int bfx_axpy(int64_t n, double alpha, const double* x_dev, double* y_dev, bfx_stream_t stream);
+  /* x[i] = value - la::Vector::set / MatrixCSR::set(value) (la/Vector.h:205-208, la/MatrixCSR.h:239-241) */
+  int bfx_fill(int64_t n, double value, double* x_dev, bfx_stream_t stream);
 
   /* ---- communicator (NCCL over NVLink; replaces MPI on the data path) ------------------------ */
   int bfx_comm_unique_id(char id_out[128]);

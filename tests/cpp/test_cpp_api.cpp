@@ -111,6 +111,23 @@ int main()
     REQUIRE(threw);
   }
 
+  // re-assembly: adds onto the matrix (fem/assembler.h:497-498); after set(0) the aggregated kernel overwrites instead and
+  // reproduces the first assembly; the reference's call shape with the insertion functor does the same
+  {
+    const double n1 = A.squared_norm();
+    fem::assemble_matrix(A, a);
+    REQUIRE(std::abs(A.squared_norm() - 4 * n1) <= 1e-12 * n1);
+    A.set(0.0);
+    REQUIRE(A.known_zero() and A.squared_norm() == 0.0);
+    fem::assemble_matrix<double>(A.mat_add_values(), a);
+    REQUIRE(!A.known_zero() and std::abs(A.squared_norm() - n1) <= 1e-13 * n1);
+    A.set(2.5); // MatrixCSR::set(value), filled on the device
+    REQUIRE(std::abs(A.squared_norm() - 6.25 * (double)sp.num_nonzeros()) <= 1e-9);
+    la::Vector<double> v(imap, 1);
+    v.set(-3.0);
+    REQUIRE(std::abs(la::norm(v, la::Norm::l1) - 3.0 * ndofs) < 1e-9 and std::abs(la::norm(v, la::Norm::linf) - 3.0) == 0.0);
+  }
+
   // (2) Dirichlet problem: u = g on x0 in {0,1}, g = 1 + 3 x1
   std::vector<std::int32_t> bdofs;
   for (int d = 0; d < ndofs; ++d)
