@@ -93,6 +93,8 @@ struct bfx_chunks
   uint8_t *wv_loc = nullptr, *wd_loc = nullptr; // 4 * ceil(width / 4) bytes per slot
   int lean_dbg = 0;
   bool tables_complete = false; // every group of 32 cells has its node (and dof) table: no direct-gather groups
+  bool slim = false;            // reduced to what the lean kernel reads (perm, xdm, dm0, dm1, wv_cnt, wd_cnt freed)
+  int nx = 0, nd0 = 0;          // geometry nodes / dofs per cell of the plan (table word counts)
   // Vector plans (bfx_asm_build_groups): for every group of 32 cell slots, the (cell, local dof) pairs that
   // land on each distinct dof of the group: goff[g][l] .. goff[g][l+1] index glist[g][], entries = i * 32 + lane
   uint8_t *glist = nullptr, *goff = nullptr;

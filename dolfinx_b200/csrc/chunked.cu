@@ -2047,6 +2047,8 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       return BFX_OK;
     }
   }
+  if (c->slim)
+    return fail(BFX_ERR_INVALID, "chunk plan reduced for the lean kernel: this call (element, addresses or markers) needs the full plan");
   if (c->len_sorted)
     return fail(BFX_ERR_UNSUPPORTED, "chunk plan ordered by list length (BFX_CHUNKS_LEN_SORT) needs the lean kernel");
   if constexpr (SYM && NS <= 16 && CB == 256)
@@ -3106,10 +3108,18 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
   if (n_src_entries)
     *n_src_entries = c->n_src32 * 32;
   if (plan_bytes)
-    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4
+  {
+    // device bytes the plan holds now: headers, list headers, destination addresses, source lists, the locality
+    // permutation and chunk-ordered dofmaps (while kept), the warp tables (ids + positions per cell slot)
+    const int64_t slots = c->nchunks * c->cb;
+    const int64_t lv = 4 * ((P->nx + 3) / 4), ld = 4 * ((P->nd0 + 3) / 4);
+    *plan_bytes = c->nchunks * (int64_t)sizeof(ChunkHdr) + c->n_dest_pad / 32 * 4 * (c->len_sorted ? 2 : 1)
                   + (c->wr_addr ? c->n_dest_pad * 12 : c->n_dest_pad * c->addr_bytes * (c->sym ? 2 : 1))
                   + c->n_src32 * 64 + (c->perm ? P->ncells * 4 : 0)
-                  + (c->xdm ? P->ncells * 4 * (int64_t)(P->nx + P->nd0 + (c->dm1 ? P->nd1 : 0)) : 0);
+                  + (c->xdm ? P->ncells * 4 * (int64_t)P->nx : 0) + (c->dm0 ? P->ncells * 4 * (int64_t)P->nd0 : 0)
+                  + (c->dm1 ? P->ncells * 4 * (int64_t)P->nd1 : 0) + (c->wv_ids ? slots * (4 + lv) : 0)
+                  + (c->wd_ids ? slots * (4 + ld) : 0) + (c->colour ? slots * 4 * ((c->n2 + 3) / 4) : 0);
+  }
   return BFX_OK;
 }
 
@@ -3119,7 +3129,24 @@ int bfx_asm_chunk_set_kernel(bfx_asm_t* P, int variant)
   BFX_REQUIRE(variant == BFX_CHUNK_KERNEL_DEFAULT || variant == BFX_CHUNK_KERNEL_OCC5 || variant == BFX_CHUNK_KERNEL_DIET
                   || variant == BFX_CHUNK_KERNEL_LEAN || variant == BFX_CHUNK_KERNEL_WIDE || (variant >= 11 && variant <= 14),
               "bfx_asm_chunk_set_kernel: unknown variant %d", variant);
-  P->chunks->kernel_variant = variant;
+  bfx_chunks* c = P->chunks;
+  if (c->slim && variant != BFX_CHUNK_KERNEL_LEAN)
+    return fail(BFX_ERR_INVALID, "bfx_asm_chunk_set_kernel: the plan was reduced to what the lean kernel reads");
+  c->kernel_variant = variant;
+  // A plan that will run the lean kernel only keeps what that kernel reads: the Morton permutation and the chunk-ordered
+  // copies of the geometry dofmap / dofmaps (36 bytes per P1 cell) served the plan construction and the kernels that
+  // gather directly; with complete warp tables nothing at run time touches them.
+  if (variant == BFX_CHUNK_KERNEL_LEAN && c->sym && c->addr_bytes == 4 && !c->colour && c->tables_complete && c->wv_ids
+      && c->wd_ids && P->nx <= 4 && P->nd0 <= 4 && !c->vector_plan && !getenv("BFX_CHUNKS_KEEP_ALL"))
+  {
+    cudaFree(c->perm), c->perm = nullptr;
+    cudaFree(c->xdm), c->xdm = nullptr;
+    cudaFree(c->dm0), c->dm0 = nullptr;
+    cudaFree(c->dm1), c->dm1 = nullptr;
+    cudaFree(c->wv_cnt), c->wv_cnt = nullptr;
+    cudaFree(c->wd_cnt), c->wd_cnt = nullptr;
+    c->slim = true;
+  }
   if (const char* d = getenv("BFX_LEAN_DBG")) // profiling only (wrong results): 1 phase 1, 2 phase 2, 3 phase 2 without updates
     P->chunks->lean_dbg = atoi(d);
   return BFX_OK;

@@ -236,8 +236,10 @@ int bfx_scatter_create(bfx_scatter_t** out, bfx_comm_t* comm, const int32_t* loc
                        const int32_t* displs_remote, const int32_t* src, int n_src)
 {
   BFX_REQUIRE(out && n_local >= 0 && n_remote >= 0 && n_dest >= 0 && n_src >= 0, "bfx_scatter_create: bad arguments");
+  // (a rank may have neighbours on one side only - the owner of a shared plane ghosts nothing: the arrays of the empty
+  // side may be NULL)
   if (n_dest + n_src > 0)
-    BFX_REQUIRE(comm && sizes_local && displs_local && sizes_remote && displs_remote,
+    BFX_REQUIRE(comm && (n_dest == 0 || (sizes_local && displs_local && dest)) && (n_src == 0 || (sizes_remote && displs_remote && src)),
                 "bfx_scatter_create: neighbours given without a communicator / sizes");
   bfx_scatter* s = new bfx_scatter();
   s->comm = comm;
