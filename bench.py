@@ -586,7 +586,7 @@ def run_leg(ctx, args, cfg, n, headline, lean=False, steps=None):
     strat = {"auto": None, "atomic": K.ASM_ATOMIC, "chunked": K.ASM_CHUNKED, "rowgather": K.ASM_ROWGATHER}[args.strategy]
     t0 = time.perf_counter()
     integ0 = a.integral(fem.IntegralType.cell, 0)
-    if lean:
+    if lean and not (cfg == "p1" and strat in (None, K.ASM_CHUNKED) and fem.CHUNK_LEAN):
         # builds the boundary-cell and interior-cell plans only; the kernel-only leg times the interior launch
         fem.assemble_matrix_overlapped(A, a, bcs=[bc], strategy=strat)
         cells_int = fem._boundary_interior_cells(a, integ0)[1]
@@ -594,6 +594,7 @@ def run_leg(ctx, args, cfg, n, headline, lean=False, steps=None):
         strat_used = fem._matrix_strategy(a, integ0, kplan, strat, shared=True)
         kernel_cells = int(cells_int.numel())
     else:
+        # (lean P1 plans: the distributed step runs the one plan of all cells in two parts - nothing else to build)
         fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)  # builds the assembly plan (and its chunk lists)
         kplan = fem._asm_plan(a, integ0, fem.IntegralType.cell, A)
         # the strategy the product path actually runs on the whole cell list (what the kernel-only and e2e legs time)
@@ -719,6 +720,28 @@ def run_leg(ctx, args, cfg, n, headline, lean=False, steps=None):
     ms_spmv, ms_vec, ms_lift, ms_kernel = (float(v) for v in tt)
     del x, y, b
 
+    # ---- phases of one distributed step (CUDA events on the launching stream, mean of 5 steps, this rank) -------
+    timeline = None
+    if world > 1 and args.timeline:
+        acc = {}
+        for _ in range(5):
+            barrier()
+            tl = []
+            A.set_value(0.0)
+            fem.assemble_matrix_overlapped(A, a, bcs=[bc], strategy=strat, timeline=tl)
+            ev_d = torch.cuda.Event(enable_timing=True)
+            fem.set_diagonal(A, V, [bc], 1.0)
+            ev_d.record()
+            tl.append(("set_diagonal", ev_d))
+            torch.cuda.synchronize()
+            for (n0, e0_), (n1, e1_) in zip(tl[:-1], tl[1:]):
+                acc.setdefault(n1, []).append(e0_.elapsed_time(e1_))
+        timeline = {k: float(np.mean(v)) for k, v in acc.items()}
+        tl_all = [None] * world
+        dist.all_gather_object(tl_all, timeline)
+        timeline = {"per_rank_ms": tl_all, "note": "gaps between events on the launching stream; the exchange itself runs "
+                    "on the communication stream and shows up as waiting time in 'wait + unpack'"}
+
     # ---- end-to-end through the host-buffer C-ABI entry (headline leg) ---------------------------------
     e2e = None
     if headline and not args.no_e2e and not lean:
@@ -750,6 +773,7 @@ def run_leg(ctx, args, cfg, n, headline, lean=False, steps=None):
             "sizes": {"dofs_global": pb["ndofs_global"] * pb["bs"], "cells_per_gpu": pb["n_cells"], "nnz_per_gpu": nnz},
             "setup_s": {"mesh": t_mesh, "sparsity+matrix": t_pattern, "assembly_plan+first_call": t_plan},
             "chunk_plan": plan_info,
+            "timeline": timeline,
             "hbm": {"peak_allocated_gb": torch.cuda.max_memory_allocated() / 1e9,
                     "free_gb_at_end": torch.cuda.mem_get_info()[0] / 1e9, "total_gb": torch.cuda.mem_get_info()[1] / 1e9},
         }
@@ -837,6 +861,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--n-cpu", type=int, default=0, help="cells per edge of the CPU arm's box (0 = default per config)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: per-phase CUDA-event times of the distributed step")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity legs (oracle on sampled rows / norms)")
     ap.add_argument("--legs", default="auto",
                     help="other BASELINE configs measured in the same run and reported under 'configs': comma list of "
@@ -916,7 +941,7 @@ def main():
             "gpu_launches": per_step * args.steps, "clocks": head["clocks"],
             "spmv": head["spmv"], "vector_assembly_ms": head["vector_assembly_ms"],
             "apply_lifting_ms": head["apply_lifting_ms"], "sizes": head["sizes"], "setup_s": head["setup_s"],
-            "chunk_plan": head["chunk_plan"], "hbm": head["hbm"],
+            "chunk_plan": head["chunk_plan"], "timeline": head.get("timeline"), "hbm": head["hbm"],
             "configs": legs,
         }
         emit(line)

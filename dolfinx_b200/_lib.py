@@ -144,6 +144,8 @@ _SIGS = {
     "bfx_assemble_matrix_cells": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_vector_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, vp], ci),
     "bfx_assemble_scalar_cells": ([vp, ci, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, C.POINTER(f64), vp], ci),
+    "bfx_asm_chunk_partition": ([vp, i32, C.POINTER(i64)], ci),
+    "bfx_assemble_matrix_cells_part": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, ci, ci, vp], ci),
     "bfx_assemble_matrix_rows": ([vp, ci, vp, vp, vp, C.POINTER(Coeffs), C.POINTER(f64), ci, vp, i32, i32, ci, vp], ci),
     "bfx_asm_rowgather_tile_rows": ([vp, C.POINTER(ci)], ci),
     "bfx_assemble_scalar_facets": ([vp, ci, vp, vp, i64, C.POINTER(Coeffs), C.POINTER(f64), ci, C.POINTER(f64), vp], ci),

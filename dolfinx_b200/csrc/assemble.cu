@@ -1166,6 +1166,18 @@ int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x
   return dispatch_matrix<0>(P, kernel_id, a, S(stream));
 }
 
+int bfx_assemble_matrix_cells_part(bfx_asm_t* P, int kernel_id, const double* x, const int8_t* bc0, const int8_t* bc1,
+                                   const bfx_coeffs_t* coeffs, const double* constants, int n_constants, double* values,
+                                   int values_mode, int part, bfx_stream_t stream)
+{
+  BFX_REQUIRE(P && P->chunks && part >= 0 && part <= 2, "bfx_assemble_matrix_cells_part: needs a partitioned chunk plan");
+  P->chunks->launch_part = part;
+  const int e = bfx_assemble_matrix_cells(P, kernel_id, x, bc0, bc1, coeffs, constants, n_constants, values, BFX_ASM_CHUNKED,
+                                          values_mode, stream);
+  P->chunks->launch_part = 0;
+  return e;
+}
+
 int bfx_assemble_matrix_rows(const bfx_asm_t* P, int kernel_id, const double* x, const int8_t* bc0, const int8_t* bc1,
                              const bfx_coeffs_t* coeffs, const double* constants, int n_constants, double* values,
                              int32_t row_begin, int32_t row_end, int reuse_records, bfx_stream_t stream)

@@ -93,6 +93,13 @@ struct bfx_chunks
   uint8_t *wv_loc = nullptr, *wd_loc = nullptr; // 4 * ceil(width / 4) bytes per slot
   int lean_dbg = 0;
   bool tables_complete = false; // every group of 32 cells has its node (and dof) table: no direct-gather groups
+  // split of the chunks for the distributed overlap (bfx_asm_chunk_partition): part 1 = chunks with a cell that touches a
+  // row >= part_rows (ghost rows), listed in part_list; part 2 = the others (part_flag[q] == 0)
+  uint32_t* part_list = nullptr;
+  uint8_t* part_flag = nullptr;
+  int64_t n_part1 = 0;
+  int32_t part_rows = -1;
+  int launch_part = 0; // which part the next launch runs (0 = all chunks); set by bfx_assemble_matrix_cells_part
   bool slim = false;            // reduced to what the lean kernel reads (perm, xdm, dm0, dm1, wv_cnt, wd_cnt freed)
   int nx = 0, nd0 = 0;          // geometry nodes / dofs per cell of the plan (table word counts)
   // Vector plans (bfx_asm_build_groups): for every group of 32 cell slots, the (cell, local dof) pairs that

@@ -1483,6 +1483,32 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : (staged_per_cell(E::ND * 
 // arithmetic, one table word per cell, unconditional shuffles (no WARPSYNC / collective bookkeeping), Dirichlet
 // handling behind one warp vote, staging through immediate offsets.
 // ---------------------------------------------------------------------------------------------
+// one warp per chunk: does any dof of the chunk's tables lie at or beyond n_owned (a ghost row)?
+__global__ void k_chunk_partition(int64_t nchunks, int cb, const int32_t* __restrict__ wd_ids, int64_t ncells,
+                                  int32_t n_owned, uint8_t* __restrict__ flag, uint32_t* __restrict__ list,
+                                  unsigned long long* __restrict__ count)
+{
+  const int lane = threadIdx.x & 31;
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nchunks; q += ((int64_t)gridDim.x * blockDim.x) >> 5)
+  {
+    bool hit = false;
+    for (int k = lane; k < cb; k += 32)
+    {
+      const int64_t slot = q * cb + k;
+      // (table words of the groups past the last cell are padding)
+      if ((slot & ~(int64_t)31) < ncells)
+        hit |= wd_ids[slot] >= n_owned;
+    }
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0)
+    {
+      flag[q] = hit ? 1 : 0;
+      if (hit)
+        list[atomicAdd(count, 1ull)] = (uint32_t)q;
+    }
+  }
+}
+
 struct LeanArgs
 {
   const ChunkHdr* hdr;
@@ -1497,6 +1523,10 @@ struct LeanArgs
   double constants[4];
   uint32_t n; // cells of the plan
   int overwrite;
+  // launch over part of the chunks: chunk_list[blockIdx.x] names the chunk (grid = list length), or every chunk with
+  // skip[chunk] != 0 returns at once (grid = all chunks); both NULL = all chunks
+  const uint32_t* chunk_list;
+  const uint8_t* skip;
 };
 
 template <class E, int CB, int DBG = 0, int OCC = 0, bool MASKED = false>
@@ -1513,7 +1543,12 @@ __global__ void __launch_bounds__(CB, OCC ? OCC : chunk_min_ctas(CB)) k_matrix_l
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t slot = blockIdx.x * (uint32_t)CB + tid;
+  uint32_t q = blockIdx.x;
+  if (p.chunk_list)
+    q = __ldg(p.chunk_list + blockIdx.x);
+  // (the skip flag travels with the first-level loads and is tested after them: no extra load level per CTA)
+  const uint8_t skipped = p.skip ? __ldg(p.skip + q) : (uint8_t)0;
+  const uint32_t slot = q * (uint32_t)CB + tid;
   // ---- first-level loads (coalesced, one word each)
   const int32_t vtx = __ldg(p.wv_ids + slot);
   const uint32_t locv = __ldg(p.wv_loc + slot);
@@ -1523,7 +1558,9 @@ __global__ void __launch_bounds__(CB, OCC ? OCC : chunk_min_ctas(CB)) k_matrix_l
     dof = (uint32_t)__ldg(p.wd_ids + slot);
     locd = __ldg(p.wd_loc + slot);
   }
-  const ChunkHdr h = p.hdr[blockIdx.x];
+  const ChunkHdr h = p.hdr[q];
+  if (skipped)
+    return;
   const int n_dw = (h.n_dest + 31) >> 5;
   const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 256u;
   constexpr int WS = MASKED ? 2 : 1; // words per group: (list offset, length) [, completeness mask]
@@ -1986,7 +2023,19 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
         lp.constants[k] = a.constants[k];
       lp.n = (uint32_t)a.n;
       lp.overwrite = ch.overwrite;
+      lp.chunk_list = nullptr, lp.skip = nullptr;
+      unsigned lean_grid = (unsigned)c->nchunks;
+      if (c->launch_part == 1)
+        lp.chunk_list = c->part_list, lean_grid = (unsigned)c->n_part1;
+      else if (c->launch_part == 2)
+        lp.skip = c->part_flag;
+      if (c->launch_part != 0 && !c->part_flag)
+        return fail(BFX_ERR_INVALID, "chunk plan has no partition (bfx_asm_chunk_partition)");
+      if (lean_grid == 0)
+        return BFX_OK;
       const int dbg = c->lean_dbg;
+      if (c->launch_part != 0 && (c->wr_addr != nullptr || dbg != 0))
+        return fail(BFX_ERR_UNSUPPORTED, "partial launches are implemented for the default lean kernel");
       if (lean_two)
       {
         using LT = LeanTwoSmem<NS, CB>;
@@ -2021,12 +2070,12 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       else if (c->len_sorted)
       {
         BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_matrix_lean<E, CB, 0, 0, true><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+        k_matrix_lean<E, CB, 0, 0, true><<<lean_grid, CB, smem, st>>>(lp);
       }
       else if (dbg == 0)
       {
         BFX_CUDA(cudaFuncSetAttribute(k_matrix_lean<E, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_matrix_lean<E, CB><<<(unsigned)c->nchunks, CB, smem, st>>>(lp);
+        k_matrix_lean<E, CB><<<lean_grid, CB, smem, st>>>(lp);
       }
       else if constexpr (CB == 256 && E::NX == 4)
       {
@@ -2047,6 +2096,8 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       return BFX_OK;
     }
   }
+  if (c->launch_part != 0)
+    return fail(BFX_ERR_UNSUPPORTED, "partial launches are implemented for the lean kernel");
   if (c->slim)
     return fail(BFX_ERR_INVALID, "chunk plan reduced for the lean kernel: this call (element, addresses or markers) needs the full plan");
   if (c->len_sorted)
@@ -2664,6 +2715,8 @@ void free_chunks(bfx_chunks* c)
 {
   if (!c)
     return;
+  cudaFree(c->part_list);
+  cudaFree(c->part_flag);
   cudaFree(c->glist);
   cudaFree(c->goff);
   cudaFree(c->hdr);
@@ -3120,6 +3173,37 @@ int bfx_asm_chunk_stats(const bfx_asm_t* P, int64_t* nchunks, int64_t* n_dest, i
                   + (c->dm1 ? P->ncells * 4 * (int64_t)P->nd1 : 0) + (c->wv_ids ? slots * (4 + lv) : 0)
                   + (c->wd_ids ? slots * (4 + ld) : 0) + (c->colour ? slots * 4 * ((c->n2 + 3) / 4) : 0);
   }
+  return BFX_OK;
+}
+
+int bfx_asm_chunk_partition(bfx_asm_t* P, int32_t n_owned_rows, int64_t* n_first)
+{
+  BFX_REQUIRE(P && P->chunks && n_first, "bfx_asm_chunk_partition: no chunk plan");
+  bfx_chunks* c = P->chunks;
+  if (!(c->tables_complete && c->wd_ids && P->nd0 <= 4 && !c->vector_plan))
+    return fail(BFX_ERR_UNSUPPORTED, "chunk partition needs complete dof tables (lean plans)");
+  if (c->part_flag && c->part_rows == n_owned_rows)
+  {
+    *n_first = c->n_part1;
+    return BFX_OK;
+  }
+  cudaFree(c->part_list), c->part_list = nullptr;
+  cudaFree(c->part_flag), c->part_flag = nullptr;
+  int e;
+  unsigned long long* d_count = nullptr;
+  if ((e = dev_alloc(&c->part_list, (size_t)c->nchunks + 1)) || (e = dev_alloc(&c->part_flag, (size_t)c->nchunks + 1))
+      || (e = dev_alloc(&d_count, 1)))
+    return e;
+  BFX_CUDA(cudaMemset(d_count, 0, sizeof(unsigned long long)));
+  k_chunk_partition<<<grid_for(c->nchunks * 32, 256, 16), 256>>>(c->nchunks, c->cb, c->wd_ids, P->ncells, n_owned_rows,
+                                                                c->part_flag, c->part_list, d_count);
+  BFX_CHECK_LAUNCH();
+  unsigned long long h = 0;
+  BFX_CUDA(cudaMemcpy(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d_count);
+  c->n_part1 = (int64_t)h;
+  c->part_rows = n_owned_rows;
+  *n_first = c->n_part1;
   return BFX_OK;
 }
 

@@ -490,6 +490,8 @@ CHUNK_KERNEL = int(os.environ["BFX_CHUNK_DBG"]) if "BFX_CHUNK_DBG" in os.environ
 # destinations sorted by list length, 384-cell chunks (4 x 4 x 4 cubes of a Kuhn box under the Morton order):
 # C2 launch 2.71 ms against 3.30 ms of the bank-coloured classic kernel (profiles/r02_p1_variants.txt)
 CHUNK_LEAN = os.environ.get("BFX_CHUNK_LEAN", "1") != "0"
+# distributed overlap of the lean plans: boundary chunks on a high-priority side stream beside the interior launch
+OVERLAP_SIDE_STREAM = os.environ.get("BFX_OVERLAP_SIDE_STREAM", "0") != "0"  # measured at N = 2: no gain (3.32 against 3.22 ms per step)
 CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padded to multiples of 4 (round-2 experiment)
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
@@ -727,13 +729,20 @@ def assemble_matrix(A: la.MatrixCSR, a: Form, bcs=(), constants=None, coeffs=Non
     return A
 
 
-def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None, strategy=None):
+def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None, strategy=None, timeline=None):
     """``assemble_matrix`` + ``A.scatter_reverse()`` with the ghost-row exchange hidden behind the
     interior cells: boundary cells are assembled first, the NCCL exchange of the ghost rows starts on
     the communication stream, interior cells are assembled meanwhile, then the received values are
     added (north_star: "overlapped with interior-cell assembly").  Same result as the two separate
     reference calls (fem/assembler.h:589-602 then la/MatrixCSR.h:384-468) up to summation order."""
     from . import _lib
+
+    def mark(name):
+        # (profiling: ``timeline`` collects (phase, CUDA event) pairs recorded on the caller's stream)
+        if timeline is not None:
+            ev = _torch().cuda.Event(enable_timing=True)
+            ev.record()
+            timeline.append((name, ev))
 
     if a.mesh.comm.size == 1:
         assemble_matrix(A, a, bcs, constants=constants, strategy=strategy)
@@ -771,15 +780,80 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
                         _lib.current_stream()))
 
                 try:
+                    mark("start")
                     rows(split, n_all, 0)
+                    mark("ghost rows")
                     A.scatter_rev_begin()
+                    mark("pack + send (enqueue)")
                     rows(0, split, 1)
+                    mark("owned rows")
                     A.scatter_rev_end()
+                    mark("wait + unpack")
                 except _lib.BfxError as e:
                     raise _translate(e) from e
                 A._is_zero = False
                 return A
+    if len(items) == 1 and items[0][1].kernel in _lib.LEAN_KERNELS and strategy in (None, _lib.ASM_CHUNKED) and CHUNK_LEAN:
+        # Lean chunk plans: ONE plan of all cells, launched in two parts - the chunks with a cell on a ghost row first,
+        # the others behind the exchange.  The chunks keep the whole-cube geometry and the completeness of the
+        # one-launch plan (a plan over the interior cell SUBSET is cut through the cubes: 2.90 against 2.72 ms at C2).
+        (itype, ident), integ = items[0]
+        plan = _asm_plan(a, integ, itype, A)
+        if _matrix_strategy(a, integ, plan, strategy) == _lib.ASM_CHUNKED:
+            n1 = C.c_int64(0)
+            st = _lib.lib.bfx_asm_chunk_partition(plan, A.num_owned_rows(), C.byref(n1))
+            if st == _lib.OK:
+                mark("start")
+                vals = A._values()
+                mark("zero fill")
+                mode = _lib.VALUES_OVERWRITE if was_zero else _lib.VALUES_ADD
+                cf = _coeffs_for(a, integ, None, itype)
+
+                def part(k):
+                    _lib.check(_lib.lib.bfx_assemble_matrix_cells_part(
+                        plan, integ.kernel, a.mesh.x.data_ptr(), None if bc0 is None else bc0.data_ptr(),
+                        None if bc1 is None else bc1.data_ptr(), C.byref(cf), carr, nc, vals.data_ptr(), mode, k,
+                        _lib.current_stream()))
+
+                try:
+                    torch = _torch()
+                    if n1.value > 0 and OVERLAP_SIDE_STREAM:
+                        # the few boundary chunks run on a high-priority side stream NEXT TO the interior launch (they
+                        # write disjoint complete entries and RED the shared ones): their tail does not idle the GPU, and
+                        # the pack + send follow them on that stream
+                        key = ("side", 0)
+                        if key not in a._plans:
+                            a._plans[key] = torch.cuda.Stream(priority=-1)
+                        side, main = a._plans[key], torch.cuda.current_stream()
+                        side.wait_stream(main)  # the zero fill
+                        with torch.cuda.stream(side):
+                            part(1)
+                            A.scatter_rev_begin()
+                        mark("boundary chunks + pack + send (side stream, enqueue)")
+                        part(2)
+                        mark("interior chunks")
+                        A.scatter_rev_end()
+                        mark("wait + unpack")
+                        A._is_zero = False
+                        return A
+                    if n1.value > 0:
+                        part(1)
+                    mark("boundary chunks")
+                    A.scatter_rev_begin()
+                    mark("pack + send (enqueue)")
+                    part(2 if n1.value > 0 else 0)  # (no chunk on a ghost row: the plain launch of all chunks)
+                    mark("interior chunks")
+                    A.scatter_rev_end()
+                    mark("wait + unpack")
+                except _lib.BfxError as e:
+                    raise _translate(e) from e
+                A._is_zero = False
+                return A
+            if st != _lib.ERR_UNSUPPORTED:
+                _lib.check(st)
+    mark("start")
     vals = A._values()  # (a pending set_value(0) is written here)
+    mark("zero fill")
 
     def run(tag_index):
         for (itype, ident), integ in items:
@@ -799,9 +873,13 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
 
     try:
         run(0)
+        mark("boundary cells")
         A.scatter_rev_begin()
+        mark("pack + send (enqueue)")
         run(1)
+        mark("interior cells")
         A.scatter_rev_end()
+        mark("wait + unpack")
     except _lib.BfxError as e:
         raise _translate(e) from e
     A._is_zero = False

@@ -1002,3 +1002,53 @@ def test_q1_rowgather_row_ranges(bfx, oracle, perturb):
     else:
         assert torch.equal(vals, whole)
     assert rows(1, n_all, 0) != K.OK  # not cut at a tile boundary
+
+
+def test_chunk_plan_partition(bfx, oracle):
+    """bfx_asm_chunk_partition / bfx_assemble_matrix_cells_part: the chunks of ONE lean plan split at a row threshold
+    (the distributed overlap's ghost rows) - part 1 then part 2 give the one-launch matrix (overwrite mode on zeros
+    and add mode), part 1 alone writes nothing into chunks without a row beyond the threshold, and a threshold beyond
+    the last row leaves part 1 empty."""
+    import ctypes as C
+
+    fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
+    p = P.tet_p1(16, numbering="first_touch")  # (2^k cubes per edge: whole-cube chunks, complete warp tables)
+    msh, V = make_space(bfx, p)
+    bdofs = np.flatnonzero(p.dof_coords[:, 0] < 1e-12).astype(np.int32)
+    bc = fem.DirichletBC(fem.Constant(0.0), bdofs, V)
+    a, sp, A = assemble_A(bfx, V, K.K_POISSON_P1_TET_A, constants=[2.0], bcs=[bc])
+    whole = A.data.clone()
+    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([2.0]),
+                                        bc=(np.isin(np.arange(p.ndofs), bdofs)).astype(np.int8))
+    check_matrix(A, pat, ref)
+    integ = a.integral(fem.IntegralType.cell, 0)
+    plan = fem._asm_plan(a, integ, fem.IntegralType.cell, A)
+    mk = fem._bc_markers(V, [bc])
+    carr, nc = K.constants_array(fem.pack_constants(a))
+    cf = K.make_coeffs()
+    n1 = C.c_int64(-1)
+    thr = (2 * p.ndofs) // 3
+    K.check(K.lib.bfx_asm_chunk_partition(plan, thr, C.byref(n1)))
+    nch = fem.chunk_stats(a, A)[0]
+    assert 0 < n1.value < nch
+
+    def part(vals, k, mode):
+        K.check(K.lib.bfx_assemble_matrix_cells_part(plan, integ.kernel, msh.x.data_ptr(), mk.data_ptr(), mk.data_ptr(),
+                                                     C.byref(cf), carr, nc, vals.data_ptr(), mode, k, K.current_stream()))
+
+    vals = torch.zeros_like(whole)
+    part(vals, 1, K.VALUES_OVERWRITE)
+    first = vals.clone()
+    assert 0 < int((first != 0).sum()) < int((whole != 0).sum())
+    part(vals, 2, K.VALUES_OVERWRITE)
+    assert float((vals - whole).abs().max()) <= TOL * float(whole.abs().max())
+    part(vals, 1, K.VALUES_ADD)
+    part(vals, 2, K.VALUES_ADD)
+    assert float((vals - 2 * whole).abs().max()) <= 2 * TOL * float(whole.abs().max())
+    K.check(K.lib.bfx_asm_chunk_partition(plan, p.ndofs, C.byref(n1)))
+    assert n1.value == 0
+    vals.zero_()
+    part(vals, 1, K.VALUES_OVERWRITE)
+    assert float(vals.abs().max()) == 0.0
+    part(vals, 2, K.VALUES_OVERWRITE)
+    assert float((vals - whole).abs().max()) <= TOL * float(whole.abs().max())
