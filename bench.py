@@ -44,7 +44,7 @@ CONFIGS = {
 def measured_traffic(config, strategy, n):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f).get(f"{config}:{strategy}:{n}")
         return None if t is None else t["bytes"]
     except (OSError, ValueError, KeyError):
@@ -930,9 +930,9 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc + f" ({dtc * 1e3:.1f} ms per step)"}
 
     if rank == 0:
-        # kernels of libbfx launched inside the timed step loop: the assembly kernel (two launches on N > 1 GPUs:
+        # kernels of libbfx launched inside the timed step loop: marker bit-packing + the assembly kernel (two launches on N > 1 GPUs:
         # boundary cells, interior cells) + set_diagonal, and on N > 1 the pack / unpack kernels of scatter_rev
-        per_step = 2 if world == 1 else 5
+        per_step = 3 if world == 1 else 6
         line = {
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
