@@ -1,4 +1,8 @@
-mkdir -p gpurun_out/r2_41
-ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 400 --csv --log-file gpurun_out/r2_41/launches_p1.csv python bench.py --steps 3 --warmup 3 --legs none --no-cpu --no-e2e --no-parity > gpurun_out/r2_41/ncu_bench.log 2>&1
-tail -2 gpurun_out/r2_41/ncu_bench.log | cut -c1-300
-wc -l gpurun_out/r2_41/launches_p1.csv
+mkdir -p gpurun_out/r2_42
+python -m pytest tests -m gpu -x -q -k "q1 or Q1 or elasticity" > gpurun_out/r2_42/pytest_q1.log 2>&1; tail -3 gpurun_out/r2_42/pytest_q1.log
+python bench.py --config q1 --steps 10 --warmup 3 --no-cpu --no-e2e --legs none > gpurun_out/r2_42/q1.json 2> gpurun_out/r2_42/q1.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_42/q1.json').read().strip().splitlines()[-1])
+print('q1 kernel %.3f frac %.3f step %.3f parity %s'%(d['roofline']['kernel_ms'],d['roofline']['frac'],d['ms_per_step'],d['parity']['ok']))
+PY
