@@ -867,6 +867,7 @@ def main():
                     help="other BASELINE configs measured in the same run and reported under 'configs': comma list of "
                          "p2,q1,c5 | none | auto (default run of the headline config: p2,q1; and c5 = P1 500^3 per GPU "
                          "on 8 GPUs)")
+    ap.add_argument("--c5-n", type=int, default=500, help="cells per edge and GPU of the c5 leg")
     ap.add_argument("--lean", action="store_true",
                     help="N > 1 at shard sizes near the HBM limit (C5: --n 500): never build the plan of the whole "
                          "cell list beside the boundary / interior plans of the overlapped assembly; implies --no-e2e")
@@ -911,15 +912,26 @@ def main():
     else:
         names = [s for s in args.legs.split(",") if s and s != "none"]
     for name in names:
-        if name == "c5":
-            if world == 1:
-                continue
-            leg = run_leg(ctx, args, "p1", 500, headline=False, lean=True, steps=min(args.steps, 10))
-        else:
-            leg = run_leg(ctx, args, name, CONFIGS[name][2], headline=False, steps=min(args.steps, 10))
+        # (a leg that fails - e.g. a shard that does not fit - must not take the headline line with it; the failure is
+        # agreed on by all ranks so that nobody waits in a collective of a leg the others left)
+        leg, err = None, None
+        try:
+            if name == "c5":
+                if world == 1:
+                    continue
+                leg = run_leg(ctx, args, "p1", args.c5_n, headline=False, lean=True, steps=min(args.steps, 10))
+            else:
+                leg = run_leg(ctx, args, name, CONFIGS[name][2], headline=False, steps=min(args.steps, 10))
+        except Exception as e:  # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"[:300]
         release()
+        failed = torch.tensor([1.0 if err else 0.0], device=ctx.device)
+        if world > 1:
+            dist.all_reduce(failed, op=dist.ReduceOp.MAX)
         if rank == 0:
-            legs[name] = leg
+            legs[name] = leg if float(failed.item()) == 0.0 else {"error": err or "failed on another rank"}
+        if float(failed.item()) != 0.0 and world > 1:
+            break  # ranks may be out of step inside the failed leg's collectives: no further legs
 
     cpu = None
     if rank == 0 and not args.no_cpu:

@@ -57,7 +57,9 @@ ROWGATHER_KERNELS = frozenset({10})
 # linear-form kernels with the grouped (one RED per distinct dof of 32 cells) variant
 GROUPED_VECTOR_KERNELS = frozenset({1, 3, 7, 15})
 CHUNKED_VECTOR_KERNELS = frozenset({1, 3, 7, 9, 11, 15, 16})
-CHUNKED_VECTOR_DEFAULT = frozenset({9, 16})  # where it measures faster than the RED kernel (P2 tetrahedra)  # linear-form kernels with a chunk-aggregated variant
+# where the chunk plan measures faster than the RED kernel: P2 tetrahedra (chunk-aggregated kernel) and the P1-sized
+# kernels (table kernel k_vector_tables on the plan's warp tables: 1.95 against 2.08 ms at C2)
+CHUNKED_VECTOR_DEFAULT = frozenset({1, 3, 7, 9, 15, 16})
 ERR_UNSUPPORTED = 4
 # bilinear kernels whose DEFAULT strategy is the chunk-aggregated variant (csrc/chunked.cu): the P1 kernels,
 # and P2 Poisson (with the symmetric plan: 55 staged entries per cell, 128 cells per chunk)

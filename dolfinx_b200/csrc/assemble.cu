@@ -1281,7 +1281,13 @@ int bfx_assemble_vector_cells(const bfx_asm_t* P, int kernel_id, const double* x
   a.n = P->ncells;
   a.b = b;
   if (strategy == BFX_ASM_CHUNKED)
-    return launch_vector_grouped(P, kernel_id, a, S(stream));
+  {
+    // (a plan reduced to its warp tables refuses calls the table kernel cannot serve - packed coefficients, a
+    // coefficient on another dofmap: those take the RED kernel, like the matrix path does)
+    const int st = launch_vector_grouped(P, kernel_id, a, S(stream));
+    if (st != BFX_ERR_UNSUPPORTED)
+      return st;
+  }
   return dispatch_vector(kernel_id, a, S(stream));
 }
 

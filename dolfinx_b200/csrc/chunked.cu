@@ -2573,6 +2573,61 @@ __global__ void __launch_bounds__(CB, (E::ND * E::BS > 16) ? 1 : chunk_min_ctas(
   (void)lane;
 }
 
+// Table kernel (round 2): P1-sized scalar elements.  One thread per cell, no shared memory, no barrier: the node this
+// lane fetches for its group of 32 cells and the coefficient value of the dof it fetches travel to the cells by warp
+// shuffles (one coordinate gather per LANE instead of four per cell: 824 M -> ~250 M load sectors at C2), the element
+// vector leaves by one RED per (cell, dof).  Grid-stride over the groups at full occupancy: the three dependent load
+// levels are hidden by the other warps instead of by a CTA's phases.
+template <class E>
+__global__ void __launch_bounds__(256) k_vector_tables(const AsmArgs a, const ChunkArgs ch, const int64_t nslots_pad)
+{
+  constexpr int NX = E::NX, ND = E::ND;
+  static_assert(NX <= 4 && ND <= 4 && E::BS == 1, "table kernel: P1-sized scalar elements");
+  constexpr bool HAS_W = E::WSIZE > 0;
+  for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; (slot & ~(int64_t)31) < nslots_pad;
+       slot += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t vtx = __ldg(ch.wv_ids + slot);
+    const uint32_t locv = __ldg(reinterpret_cast<const uint32_t*>(ch.wv_loc) + slot);
+    const int32_t dof = __ldg(ch.wd_ids + slot);
+    const uint32_t locd = __ldg(reinterpret_cast<const uint32_t*>(ch.wd_loc) + slot);
+    const double* pp = a.x + 3 * (int64_t)vtx;
+    const double px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+    double fv = 0.0;
+    if constexpr (HAS_W)
+      fv = __ldg(a.coef.f[0].v + dof);
+    double xc[NX][3];
+#pragma unroll
+    for (int v = 0; v < NX; ++v)
+    {
+      const int l = (int)(locv >> (8 * v));
+      xc[v][0] = __shfl_sync(0xffffffffu, px, l);
+      xc[v][1] = __shfl_sync(0xffffffffu, py, l);
+      xc[v][2] = __shfl_sync(0xffffffffu, pz, l);
+    }
+    double w[HAS_W ? E::WSIZE : 1];
+    int32_t d[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+    {
+      const int l = (int)(locd >> (8 * i));
+      if constexpr (HAS_W)
+        w[i] = __shfl_sync(0xffffffffu, fv, l);
+      d[i] = __shfl_sync(0xffffffffu, dof, l);
+    }
+    if (slot < a.n)
+    {
+      typename E::Geo g;
+      E::prepare(g, xc, w, a.constants, 0);
+      double out[ND];
+      E::vec(g, out);
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        red_add(a.b + d[i], out[i]);
+    }
+  }
+}
+
 template <class E>
 int launch_vector_chunked_e(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
 {
@@ -2592,6 +2647,21 @@ int launch_vector_chunked_e(const bfx_asm* P, const AsmArgs& a, cudaStream_t st)
   ch.wv_ids = c->wv_ids, ch.wv_cnt = c->wv_cnt, ch.wv_loc = c->wv_loc;
   ch.wd_ids = c->wd_ids, ch.wd_cnt = c->wd_cnt, ch.wd_loc = c->wd_loc;
   ch.tables_complete = c->tables_complete && (P->nd0 > 4 || c->wd_ids);
+  if constexpr (E::NX <= 4 && E::ND <= 4 && E::BS == 1 && (E::WSIZE == 0 || (E::WND == E::ND && E::WBS == 1 && E::WSIZE == E::ND)))
+  {
+    // table kernel: complete tables, the coefficient (if any) lives on the plan's own dofmap and is gathered, not packed
+    const bool coef_ok = E::WSIZE == 0 || (!a.coef.packed && a.coef.f[0].dm == a.dofmap0);
+    if (ch.tables_complete && c->wv_ids && c->wd_ids && coef_ok && !getenv("BFX_VECTOR_NO_TABLES"))
+    {
+      const int64_t nslots_pad = c->nchunks * (int64_t)c->cb;
+      const unsigned grid = (unsigned)std::min<int64_t>((nslots_pad + 255) / 256, (int64_t)sm_count() * 8);
+      k_vector_tables<E><<<grid, 256, 0, st>>>(a, ch, nslots_pad);
+      BFX_CHECK_LAUNCH();
+      return BFX_OK;
+    }
+  }
+  if (c->slim)
+    return fail(BFX_ERR_UNSUPPORTED, "vector chunk plan reduced to its warp tables: this call (packed or foreign coefficient) needs the RED kernel");
   const size_t smem = ChunkSmem<N, CB, 1>::TOTAL;
   if (c->addr_bytes == 4)
   {
@@ -3099,6 +3169,28 @@ int bfx_asm_build_chunks_vector(bfx_asm_t* P, const double* x_dev, int kernel_id
   cudaFree(fake.row_ptr);
   cudaFree(fake.err_flag);
   cudaFree(zeros);
+  if (e == BFX_OK && info.nx <= 4 && info.nd <= 4 && info.bs == 1 && !getenv("BFX_VECTOR_NO_TABLES"))
+  {
+    // P1-sized kernels run the TABLE kernel (k_vector_tables): it needs the warp tables only.  Without complete tables
+    // (meshes the Morton order does not cut into whole groups) the chunk-aggregated kernel is slower than the RED
+    // kernel for these elements: tell the caller to keep that one.
+    bfx_chunks* c = P->chunks;
+    if (!(c->tables_complete && c->wv_ids && c->wd_ids))
+    {
+      free_chunks(P->chunks);
+      P->chunks = nullptr;
+      return fail(BFX_ERR_UNSUPPORTED, "vector chunk plan: incomplete warp tables for a P1-sized kernel");
+    }
+    cudaFree(c->src), c->src = nullptr;
+    cudaFree(c->dest_addr), c->dest_addr = nullptr;
+    cudaFree(c->winfo), c->winfo = nullptr;
+    cudaFree(c->perm), c->perm = nullptr;
+    cudaFree(c->xdm), c->xdm = nullptr;
+    cudaFree(c->dm0), c->dm0 = nullptr;
+    cudaFree(c->wv_cnt), c->wv_cnt = nullptr;
+    cudaFree(c->wd_cnt), c->wd_cnt = nullptr;
+    c->slim = true;
+  }
   return e;
 }
 
