@@ -586,15 +586,19 @@ def run_leg(ctx, args, cfg, n, headline, lean=False, steps=None):
     strat = {"auto": None, "atomic": K.ASM_ATOMIC, "chunked": K.ASM_CHUNKED, "rowgather": K.ASM_ROWGATHER}[args.strategy]
     t0 = time.perf_counter()
     integ0 = a.integral(fem.IntegralType.cell, 0)
-    if lean and not (cfg == "p1" and strat in (None, K.ASM_CHUNKED) and fem.CHUNK_LEAN):
-        # builds the boundary-cell and interior-cell plans only; the kernel-only leg times the interior launch
+    subset_plans = False
+    if lean:
+        # near the HBM limit: build only what the distributed step needs.  Lean P1 plans run ONE plan of all cells in two
+        # parts; everything else runs plans over the boundary / interior cell subsets, and the kernel-only leg then
+        # times the interior launch instead of building a third plan
         fem.assemble_matrix_overlapped(A, a, bcs=[bc], strategy=strat)
+        subset_plans = any(isinstance(k, tuple) and k[0] == "plan" and k[3] == "int" for k in a._plans)
+    if subset_plans:
         cells_int = fem._boundary_interior_cells(a, integ0)[1]
         kplan = fem._asm_plan(a, integ0, fem.IntegralType.cell, A, subset=("int", cells_int))
         strat_used = fem._matrix_strategy(a, integ0, kplan, strat, shared=True)
         kernel_cells = int(cells_int.numel())
     else:
-        # (lean P1 plans: the distributed step runs the one plan of all cells in two parts - nothing else to build)
         fem.assemble_matrix(A, a, bcs=[bc], strategy=strat)  # builds the assembly plan (and its chunk lists)
         kplan = fem._asm_plan(a, integ0, fem.IntegralType.cell, A)
         # the strategy the product path actually runs on the whole cell list (what the kernel-only and e2e legs time)
@@ -923,7 +927,10 @@ def main():
             else:
                 leg = run_leg(ctx, args, name, CONFIGS[name][2], headline=False, steps=min(args.steps, 10))
         except Exception as e:  # noqa: BLE001
-            err = f"{type(e).__name__}: {e}"[:300]
+            import traceback
+
+            where = " <- ".join(f"{f.name}:{f.lineno}" for f in traceback.extract_tb(e.__traceback__)[-4:])
+            err = (f"{type(e).__name__}: {e}"[:300]) + " @ " + where
         release()
         failed = torch.tensor([1.0 if err else 0.0], device=ctx.device)
         if world > 1:

@@ -24,6 +24,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
 
 OK = 0
+ERR_CUDA = 1
 ERR_NOT_IN_SPARSITY = 3
 ERR_NO_DEVICE = 6
 
@@ -71,6 +72,8 @@ CHUNK_KERNEL_DEFAULT, CHUNK_KERNEL_OCC5, CHUNK_KERNEL_DIET, CHUNK_KERNEL_LEAN, C
 CHUNKS_BANK_ORDER = 64  # bank-aware order of the source lists (linear staging layout)
 CHUNKS_LEN_SORT = 128  # destinations ordered by list length only (lean kernel)
 CHUNKS_PAD4 = 32  # source lists padded to multiples of 4 entries
+CHUNKS_LEAN_ONLY = 262144  # fail early (ERR_UNSUPPORTED) instead of building a non-lean plan
+CHUNKS_CB_SOFT = 131072  # the chunk size is the lean kernel's preference: default size if the lean options do not apply
 CHUNKS_TWO_STAGE_SPLIT = 16
 CHUNKS_TWO_STAGE = 8  # write-back in address order through shared memory (symmetric P1 plans)
 

@@ -2254,21 +2254,39 @@ int morton_perm(const bfx_asm* P, const double* x_dev, int32_t** perm_out, cudaS
   int e;
   if ((e = dev_alloc(&bb, 6)) || (e = dev_alloc(&k0, (size_t)n)) || (e = dev_alloc(&k1, (size_t)n))
       || (e = dev_alloc(&i0, (size_t)n)) || (e = dev_alloc(perm_out, (size_t)n)))
+  {
+    cudaFree(bb), cudaFree(k0), cudaFree(k1), cudaFree(i0), cudaFree(*perm_out);
+    *perm_out = nullptr;
     return e;
+  }
   const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
   BFX_CUDA(cudaMemcpyAsync(bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
   k_centroid_bbox<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb);
   k_morton_keys<<<grid_for(n, 256, 8), 256, 0, st>>>(n, P->cells, P->x_dofmap, P->nx, x_dev, bb, k0, i0);
   BFX_CHECK_LAUNCH();
-  BFX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, *perm_out, n, 0, 63, st));
-  BFX_CUDA(cudaMalloc(&tmp, tmp_bytes));
-  BFX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, i0, *perm_out, n, 0, 63, st));
-  BFX_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp);
-  cudaFree(bb);
-  cudaFree(k0);
-  cudaFree(k1);
-  cudaFree(i0);
+  auto release = [&]()
+  {
+    cudaFree(tmp);
+    cudaFree(bb);
+    cudaFree(k0);
+    cudaFree(k1);
+    cudaFree(i0);
+  };
+  cudaError_t ce = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, *perm_out, n, 0, 63, st);
+  if (ce == cudaSuccess)
+    ce = cudaMalloc(&tmp, tmp_bytes);
+  if (ce == cudaSuccess)
+    ce = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, i0, *perm_out, n, 0, 63, st);
+  if (ce == cudaSuccess)
+    ce = cudaStreamSynchronize(st);
+  release();
+  if (ce != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    cudaFree(*perm_out);
+    *perm_out = nullptr;
+    return fail(BFX_ERR_CUDA, "Morton ordering of the cell list failed: %s", cudaGetErrorString(ce));
+  }
   return BFX_OK;
 }
 
@@ -2827,10 +2845,10 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     return fail(BFX_ERR_UNSUPPORTED, "symmetric chunk plan needs block size 1 and one dofmap for rows and columns");
   const int n2 = sym ? staged_per_cell(P->nd0, true) : P->nd0 * csr->bs0 * P->nd1 * csr->bs1; // staged per cell
   const int cb_req = ((flags >> 8) & 0xff) * 32; // BFX_CHUNKS_CB(cells); 0 = the element's default
-  const int cb = (cb_req && (chunk_cb_supported(n2, cb_req) || (flags & BFX_CHUNKS_VECTOR))) ? cb_req : chunk_cb(n2); // not instantiated: default
+  int cb = (cb_req && (chunk_cb_supported(n2, cb_req) || (flags & BFX_CHUNKS_VECTOR))) ? cb_req : chunk_cb(n2); // not instantiated: default
   if (cb == 0 || P->ncells == 0)
     return fail(BFX_ERR_UNSUPPORTED, "chunk plan: element matrices of %d staged scalars are not supported", n2);
-  const int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
+  int items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
   free_chunks(P->chunks);
   P->chunks = nullptr;
   bfx_chunks* c = new bfx_chunks();
@@ -2868,7 +2886,8 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
 
   // ---- warp tables of geometry nodes and dofs (groups of 32 consecutive cell slots)
   {
-    const int64_t nslots_pad = c->nchunks * cb, nw = nslots_pad / 32;
+    // (padded to a common multiple of the chunk sizes: the plan may fall back to the element's default chunk size below)
+    const int64_t nslots_pad = (P->ncells + 767) / 768 * 768, nw = nslots_pad / 32;
     const int32_t* xrows = c->xdm ? c->xdm : P->x_dofmap;
     const int32_t* drows = c->dm0 ? c->dm0 : P->dofmap0;
     const int lv = 4 * ((P->nx + 3) / 4), ld = 4 * ((P->nd0 + 3) / 4);
@@ -2913,7 +2932,21 @@ int bfx_asm_build_chunks(bfx_asm_t* P, const double* x_dev, int flags, bfx_strea
     flags &= ~BFX_CHUNKS_LEN_SORT; // (the vector kernel runs on the padded linear layout with any tables)
   else if (!(c->tables_complete && sym && (uint64_t)csr->nnz * csr->bs0 * csr->bs1 < 0xffffffffull && P->nx <= 4 && P->nd0 <= 4
              && c->wd_ids))
+  {
+    if (flags & BFX_CHUNKS_LEAN_ONLY)
+      return bail(fail(BFX_ERR_UNSUPPORTED, "chunk plan: the lean options do not apply to this mesh (incomplete warp tables)"));
+    // ... and with the element's default chunk size when the caller asked for the lean kernel's 384 cells: whole-cube
+    // bricks only pay on meshes the Morton order cuts cleanly, which is what complete tables indicate (classic kernel
+    // at C2: 3.28 ms with 256 cells, 3.63 ms with 384)
+    if ((flags & BFX_CHUNKS_CB_SOFT) && cb != chunk_cb(n2) && chunk_cb(n2) > 0 && 768 % chunk_cb(n2) == 0)
+    {
+      cb = chunk_cb(n2);
+      items = (n2 * cb + PLAN_THREADS - 1) / PLAN_THREADS;
+      c->cb = cb;
+      c->nchunks = (P->ncells + cb - 1) / cb;
+    }
     flags &= ~(BFX_CHUNKS_LINEAR_STAGING | BFX_CHUNKS_BANK_ORDER | BFX_CHUNKS_LEN_SORT);
+  }
   c->vector_plan = (flags & BFX_CHUNKS_VECTOR) != 0;
   // ---- scratch of the bit-packed Dirichlet markers (sized by the largest dof the cells reference)
   {

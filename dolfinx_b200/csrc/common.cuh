@@ -17,6 +17,8 @@ int fail(int status, const char* fmt, ...);
   {                                                                                                                  \
     cudaError_t _e = (call);                                                                                         \
     if (_e != cudaSuccess)                                                                                           \
+      (void)cudaGetLastError(); /* (a failed allocation must not surface again at the next launch check) */          \
+    if (_e != cudaSuccess)                                                                                           \
       return ::bfx::fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? BFX_ERR_NO_DEVICE           \
                                                                                        : BFX_ERR_CUDA,               \
                          "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);                \

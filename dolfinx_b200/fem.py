@@ -222,6 +222,7 @@ def _drop_matrix_plans(plans, serial):
     for key in [k for k in plans if _is_plan_entry(k) and k[2] == serial]:
         _destroy_plan_entry(plans, key)
     plans.pop(("matrix", serial), None)
+    plans.pop(("lean_attempt", serial), None)
 
 
 def _matrix_key(form: Form, A):
@@ -496,7 +497,7 @@ CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padd
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
 
 
-def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=False):
+def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=False, lean_only=False):
     """Assembly strategy of a cell integral: the caller's choice, else the aggregated kernel of the
     element where it has one (chunk-aggregated for the P1 kernels, row-gather for Q1 elasticity; the
     plan's lists are built once, on first use), else fp64 REDs."""
@@ -511,12 +512,16 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
     if want == _lib.ASM_ATOMIC:
         return want
     key = ("aggplan", plan.value, want)
+    if lean_only and key not in form._plans:
+        key = ("aggplan", plan.value, want, "lean_only")  # (a refusal here must not be remembered as "no chunk plan")
     if key not in form._plans:
         if want == _lib.ASM_CHUNKED:
             V0, V1 = form.function_spaces
             flags = _lib.CHUNKS_SYMMETRIC if (CHUNKS_SYMMETRIC and V0 is V1 and V0.dofmap.bs == 1) else 0
             lean = CHUNK_LEAN and integ.kernel in _lib.LEAN_KERNELS and (flags & _lib.CHUNKS_SYMMETRIC) and not CHUNKS_TWO_STAGE
             flags |= _lib.CHUNKS_CB(CHUNKS_CB if CHUNKS_CB else (384 if lean else 0))
+            if lean and not CHUNKS_CB:
+                flags |= _lib.CHUNKS_CB_SOFT
             if CHUNKS_PAD4:
                 flags |= _lib.CHUNKS_PAD4
             if lean:
@@ -529,6 +534,8 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
                 flags |= _lib.CHUNKS_TWO_STAGE | (_lib.CHUNKS_TWO_STAGE_SPLIT if int(CHUNKS_TWO_STAGE) == 2 else 0)
             if shared:  # a cell subset: other launches add to the same matrix (assemble_matrix_overlapped)
                 flags |= _lib.CHUNKS_SHARED_MATRIX
+            if lean_only:
+                flags |= _lib.CHUNKS_LEAN_ONLY
             st = _lib.lib.bfx_asm_build_chunks(plan, form.mesh.x.data_ptr(), flags, _lib.current_stream())
             if st == _lib.OK and (CHUNK_KERNEL or lean):
                 _lib.check(_lib.lib.bfx_asm_chunk_set_kernel(plan, CHUNK_KERNEL if CHUNK_KERNEL else _lib.CHUNK_KERNEL_LEAN))
@@ -537,8 +544,12 @@ def _matrix_strategy(form: Form, integ: IntegralData, plan, strategy, shared=Fal
         if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):
             _lib.check(st)
         form._plans[key] = st == _lib.OK
+        if lean_only and st == _lib.OK:
+            form._plans[("aggplan", plan.value, want)] = True
     if form._plans[key]:
         return want
+    if lean_only:
+        return None
     if strategy is not None:
         raise NotImplementedError("the requested assembly strategy is not available for this kernel / mesh")
     return _lib.ASM_ATOMIC
@@ -793,13 +804,27 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
                     raise _translate(e) from e
                 A._is_zero = False
                 return A
-    if len(items) == 1 and items[0][1].kernel in _lib.LEAN_KERNELS and strategy in (None, _lib.ASM_CHUNKED) and CHUNK_LEAN:
+    def room_for_lean_attempt():
+        # The attempt builds the plan of ALL cells up to its warp tables (~250 bytes per cell at the peak: position map,
+        # Morton keys, chunk-ordered dofmaps, tables) before it knows whether the mesh takes the lean options; on a shard
+        # near the HBM limit (C5: 750 M cells per GPU) that is not affordable beside the subset plans of the other scheme.
+        key = ("lean_attempt", A._serial)  # (decided once per (form, matrix))
+        if key not in a._plans:
+            torch = _torch()
+            ncells = _entities_dev(a, items[0][1], IntegralType.cell)[1]
+            if ncells >= (1 << 26):
+                torch.cuda.empty_cache()  # blocks cached by torch are invisible to the cudaMalloc of the plan builder
+            a._plans[key] = torch.cuda.mem_get_info()[0] >= 250 * ncells
+        return a._plans[key]
+
+    if (len(items) == 1 and items[0][1].kernel in _lib.LEAN_KERNELS and strategy in (None, _lib.ASM_CHUNKED) and CHUNK_LEAN
+            and room_for_lean_attempt()):
         # Lean chunk plans: ONE plan of all cells, launched in two parts - the chunks with a cell on a ghost row first,
         # the others behind the exchange.  The chunks keep the whole-cube geometry and the completeness of the
         # one-launch plan (a plan over the interior cell SUBSET is cut through the cubes: 2.90 against 2.72 ms at C2).
         (itype, ident), integ = items[0]
         plan = _asm_plan(a, integ, itype, A)
-        if _matrix_strategy(a, integ, plan, strategy) == _lib.ASM_CHUNKED:
+        if _matrix_strategy(a, integ, plan, strategy, lean_only=True) == _lib.ASM_CHUNKED:
             n1 = C.c_int64(0)
             st = _lib.lib.bfx_asm_chunk_partition(plan, A.num_owned_rows(), C.byref(n1))
             if st == _lib.OK:
@@ -851,6 +876,11 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
                 return A
             if st != _lib.ERR_UNSUPPORTED:
                 _lib.check(st)
+        # no lean plan for this mesh (incomplete warp tables; the builder stopped before the lists): the plan of all
+        # cells is not needed by the subset scheme below - on a shard near the memory limit it must not stay beside
+        # the two subset plans
+        if ("aggplan", plan.value, _lib.ASM_CHUNKED) not in a._plans:
+            _destroy_plan_entry(a._plans, ("plan", id(integ), _matrix_key(a, A), None))
     mark("start")
     vals = A._values()  # (a pending set_value(0) is written here)
     mark("zero fill")
@@ -945,7 +975,16 @@ def assemble_vector(b, L: Form, constants=None, coeffs=None):
                 # element vectors summed per chunk of 256 / 384 cells on the SM (plan built once, on first use)
                 key = ("vchunks", plan.value)
                 if key not in L._plans:
-                    st = _lib.lib.bfx_asm_build_chunks_vector(plan, L.mesh.x.data_ptr(), integ.kernel, _lib.current_stream())
+                    # the plan is an optional accelerator: on a shard near the memory limit (its construction peaks at
+                    # ~150 bytes per cell: Morton keys, chunk-ordered dofmaps, lists) the RED kernel stays
+                    free = _torch().cuda.mem_get_info()[0]
+                    ncells = _entities_dev(L, integ, itype)[1]
+                    if free < 200 * ncells:
+                        st = _lib.ERR_UNSUPPORTED
+                    else:
+                        st = _lib.lib.bfx_asm_build_chunks_vector(plan, L.mesh.x.data_ptr(), integ.kernel, _lib.current_stream())
+                    if st == _lib.ERR_CUDA and b"out of memory" in _lib.lib.bfx_last_error():
+                        st = _lib.ERR_UNSUPPORTED
                     if st not in (_lib.OK, _lib.ERR_UNSUPPORTED):
                         _lib.check(st)
                     L._plans[key] = st == _lib.OK
@@ -1018,12 +1057,18 @@ def apply_lifting(b, a, bcs, x0=None, alpha: float = 1.0, constants=None, coeffs
                     if stale in aj._plans:
                         _destroy_plan_entry(aj._plans, stale)
                 ent, n = _entities_dev(aj, integ, itype)
-                dm1 = V1.dofmap.dev if ent is None else V1.dofmap.dev[ent.long()]
                 bsz = V1.dofmap.index_map_bs
                 node_marked = markers.view(-1, bsz).any(dim=1) if bsz > 1 else markers.bool()
-                hit = node_marked[dm1[:n].long()].any(dim=1)
-                ids = torch.arange(n, dtype=torch.int32, device=dm1.device) if ent is None else ent[:n]
-                aj._plans[lkey] = (ids[hit].contiguous(), [weakref.ref(bc) for bc in bcs[j]], next(_LIFT_SERIAL))
+                picked = []
+                for s0 in range(0, n, 1 << 24):  # (slices: the int64 index temporaries of a 750 M-cell shard are 24 GB)
+                    s1 = min(n, s0 + (1 << 24))
+                    rows = V1.dofmap.dev[s0:s1] if ent is None else V1.dofmap.dev[ent[s0:s1].long()]
+                    hit = node_marked[rows.long()].any(dim=1)
+                    ids = (torch.arange(s0, s1, dtype=torch.int32, device=rows.device) if ent is None else ent[s0:s1])
+                    picked.append(ids[hit])
+                    del rows, hit, ids
+                lc = torch.cat(picked).contiguous() if picked else torch.zeros(0, dtype=torch.int32, device=markers.device)
+                aj._plans[lkey] = (lc, [weakref.ref(bc) for bc in bcs[j]], next(_LIFT_SERIAL))
             lcells, _, serial = aj._plans[lkey]
             if lcells.numel() == 0:
                 continue

@@ -257,6 +257,12 @@ extern "C"
                                   only (less padding of the 32-way interleaved lists); whether a destination is complete
                                   travels as one bit per lane in the group table; lean kernel only */
     BFX_CHUNKS_VECTOR = 65536, /* internal: the plan of a linear form (set by bfx_asm_build_chunks_vector) */
+    BFX_CHUNKS_CB_SOFT = 131072, /* BFX_CHUNKS_CB(cells) is the lean kernel's preference, not a demand: a plan that cannot
+                                   take the lean options (incomplete warp tables ...) is built with the element's default
+                                   chunk size instead */
+    BFX_CHUNKS_LEAN_ONLY = 262144, /* build the plan only if it can take the lean kernel's options; otherwise return
+                                      BFX_ERR_UNSUPPORTED right after the warp tables, before any list is built (a caller
+                                      with another scheme for that case does not pay the memory of a plan it will drop) */
     BFX_CHUNKS_PAD4 = 32, /* pad the source lists to multiples of 4 entries (no remainder steps in the list walk) */
     BFX_CHUNKS_TWO_STAGE_SPLIT = 16, /* with BFX_CHUNKS_TWO_STAGE: plain stores first, REDs after, each in address order */
     BFX_CHUNKS_SHARED_MATRIX = 4, /* the plan's cell list is a SUBSET of the cells that add to the matrix between its
