@@ -53,6 +53,8 @@ K_AVG2_COEFF_P1_TRI_DS_M = 21
 K_COEFF2_P1_TRI_FACET_M = 22
 K_LOAD_PROD_P1_TET_L = 23
 
+USER_KERNEL_BASE = 1000  # ids of kernels registered by the caller (bfx_register_kernel, include/bfx_plugin.cuh)
+
 ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
 # linear-form kernels with the grouped (one RED per distinct dof of 32 cells) variant
@@ -120,6 +122,7 @@ _SIGS = {
     "bfx_host_alloc": ([pvp, C.c_size_t], ci),
     "bfx_host_free": ([vp], ci),
     "bfx_kernel_info": ([ci, C.POINTER(KernelInfo)], ci),
+    "bfx_register_kernel": ([ci, C.POINTER(KernelInfo), vp], ci),
     "bfx_csr_create": ([pvp, i32, i32, vp, vp, vp, ci, ci], ci),
     "bfx_csr_destroy": ([vp], ci),
     "bfx_csr_nnz": ([vp], i64),
@@ -237,6 +240,21 @@ def host_first_touch(flat: np.ndarray, ndofs: int) -> np.ndarray:
         out = np.empty(ndofs, dtype=np.int64)
         check(lib.bfx_host_first_touch_i64(flat.ctypes.data, flat.size, ndofs, out.ctypes.data))
     return out
+
+
+_plugins = []  # (CDLL, launcher) pairs kept alive for the lifetime of the process
+
+
+def register_plugin_kernel(kernel_id: int, library_path: str, symbol: str) -> KernelInfo:
+    """Register a caller-built kernel (include/bfx_plugin.cuh: ``BFX_PLUGIN_KERNEL(E, symbol)``) under ``kernel_id``
+    (>= USER_KERNEL_BASE): the device-side replacement of plugging a tabulate_tensor pointer into a fem::Form."""
+    plug = C.CDLL(library_path)
+    info = KernelInfo()
+    getattr(plug, symbol + "_info")(C.byref(info))
+    fn = getattr(plug, symbol)
+    check(lib.bfx_register_kernel(kernel_id, C.byref(info), C.cast(fn, C.c_void_p)))
+    _plugins.append((plug, fn))
+    return info
 
 
 def kernel_info(kernel_id: int) -> KernelInfo:

@@ -6,198 +6,14 @@
 #include "assemble.cuh"
 #include "elements.cuh"
 #include "asm_device.cuh"
+#include "cell_kernels.cuh"
+#include <map>
 #include <vector>
 
 using namespace bfx;
 
 namespace
 {
-// ---------------------------------------------------------------------------------------------
-// generic thread-per-cell matrix kernel.  MODE 0: assemble with bc row/col zeroing into CSR
-// (fp64 RED); MODE 1: lifting (b -= alpha Ae (g - x0) on marked columns).
-// ---------------------------------------------------------------------------------------------
-template <class E, typename PosT, int MODE>
-__global__ void __launch_bounds__(128) k_matrix_cells(const AsmArgs a)
-{
-  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
-  {
-    int32_t cell;
-    int lf = 0;
-    if (a.entities)
-    {
-      cell = a.entities[2 * e];
-      lf = a.entities[2 * e + 1];
-    }
-    else
-      cell = a.cells ? a.cells[e] : (int32_t)e;
-
-    int32_t d0[ND], d1[ND];
-    load_ints<ND>(a.dofmap0 + (int64_t)cell * ND, d0);
-    load_ints<ND>(a.dofmap1 + (int64_t)cell * ND, d1);
-
-    uint32_t m0 = 0, m1 = 0; // bc marker bit per scalar row / column of Ae
-    if (a.bc1)
-    {
-#pragma unroll
-      for (int j = 0; j < N; ++j)
-        m1 |= (a.bc1[(int64_t)BS * d1[j / BS] + j % BS] ? 1u : 0u) << j;
-    }
-    if (MODE == 1 && m1 == 0)
-      continue; // has_bc (assemble_matrix_impl.h:27-34,139-143)
-    if (MODE == 0 && a.bc0)
-    {
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        m0 |= (a.bc0[(int64_t)BS * d0[i / BS] + i % BS] ? 1u : 0u) << i;
-    }
-
-    int32_t xd[NX];
-    load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
-    double xc[NX][3];
-    gather_coords<NX>(a.x, xd, xc);
-    double w[E::WSIZE > 0 ? E::WSIZE : 1];
-    load_w<E>(a, e, cell, w);
-    typename E::Geo g;
-    E::prepare(g, xc, w, a.constants, lf);
-
-    if constexpr (MODE == 0)
-    {
-      PosRegs<PosT, ND * ND> pos;
-      if (a.pos)
-        pos.load(a.pos, e);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-      {
-        if ((m0 >> i) & 1u)
-          continue;
-        double row[N];
-        E::row(g, i, row);
-        const int32_t r = d0[i / BS];
-        const int64_t rb = a.row_ptr[r];
-        const int64_t re = a.pos ? 0 : a.row_ptr[r + 1];
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-        {
-          if ((m1 >> j) & 1u)
-            continue;
-          int64_t p;
-          if (a.pos)
-            p = rb + pos.get((i / BS) * ND + j / BS);
-          else
-          {
-            p = find_col(a.cols, rb, re, d1[j / BS]);
-            if (p < 0)
-            {
-              *a.err = 1;
-              continue;
-            }
-          }
-          red_add(a.values + p * (BS * BS) + (i % BS) * BS + (j % BS), row[j]);
-        }
-      }
-    }
-    else
-    {
-      double dv[N]; // alpha * (g - x0) on marked columns (assemble_vector_impl.h:377-402)
-#pragma unroll
-      for (int j = 0; j < N; ++j)
-      {
-        const int64_t jj = (int64_t)BS * d1[j / BS] + j % BS;
-        dv[j] = ((m1 >> j) & 1u) ? a.alpha * (a.bc_values1[jj] - (a.x0 ? a.x0[jj] : 0.0)) : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-      {
-        double row[N];
-        E::row(g, i, row);
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-          acc = fma(row[j], dv[j], acc);
-        if (acc != 0.0)
-          red_add(a.b + (int64_t)BS * d0[i / BS] + i % BS, -acc);
-      }
-    }
-  }
-}
-
-// generic thread-per-cell vector kernel
-template <class E>
-__global__ void __launch_bounds__(128) k_vector_cells(const AsmArgs a)
-{
-  constexpr int NX = E::NX, ND = E::ND, BS = E::BS, N = ND * BS;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
-  {
-    int32_t cell;
-    int lf = 0;
-    if (a.entities)
-    {
-      cell = a.entities[2 * e];
-      lf = a.entities[2 * e + 1];
-    }
-    else
-      cell = a.cells ? a.cells[e] : (int32_t)e;
-    int32_t d0[ND], xd[NX];
-    load_ints<ND>(a.dofmap0 + (int64_t)cell * ND, d0);
-    load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
-    double xc[NX][3];
-    gather_coords<NX>(a.x, xd, xc);
-    double w[E::WSIZE > 0 ? E::WSIZE : 1];
-    load_w<E>(a, e, cell, w);
-    typename E::Geo g;
-    E::prepare(g, xc, w, a.constants, lf);
-    double out[N];
-    E::vec(g, out);
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      if (!E::FACET || out[i] != 0.0)
-        red_add(a.b + (int64_t)BS * d0[i / BS] + i % BS, out[i]);
-  }
-}
-
-// functional (rank 0): per-thread cell values, block reduction, one fp64 atomic per block
-template <class E>
-__global__ void __launch_bounds__(256) k_scalar_cells(const AsmArgs a, double* __restrict__ result)
-{
-  constexpr int NX = E::NX;
-  double acc = 0.0;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x)
-  {
-    int32_t cell;
-    int lf = 0;
-    if (a.entities)
-    {
-      cell = a.entities[2 * e];
-      lf = a.entities[2 * e + 1];
-    }
-    else
-      cell = a.cells ? a.cells[e] : (int32_t)e;
-    int32_t xd[NX];
-    load_ints<NX>(a.x_dofmap + (int64_t)cell * NX, xd);
-    double xc[NX][3];
-    gather_coords<NX>(a.x, xd, xc);
-    double w[E::WSIZE > 0 ? E::WSIZE : 1];
-    load_w<E>(a, e, cell, w);
-    typename E::Geo g;
-    E::prepare(g, xc, w, a.constants, lf);
-    acc += E::scalar(g);
-  }
-  __shared__ double part[8];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0)
-    part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 8)
-  {
-    double v = part[threadIdx.x];
-    for (int o = 4; o > 0; o >>= 1)
-      v += __shfl_xor_sync(0xffu, v, o);
-    if (threadIdx.x == 0)
-      atomicAdd(result, v);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Q1 hexahedron linear elasticity (bs = 3): 64 threads per cell, one per (i, j) node pair.
 // Phase 1: 8 threads per cell evaluate K = J^{-1}, |det J| and the 8 physical gradients at the
@@ -871,6 +687,8 @@ int launch_vector(const AsmArgs& a, cudaStream_t st)
   return BFX_OK;
 }
 
+int launch_user(const bfx_asm* P, int kernel_id, const AsmArgs& a, int mode, double* scalar_dev, cudaStream_t st);
+
 template <int MODE>
 int dispatch_matrix(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStream_t st)
 {
@@ -884,7 +702,10 @@ int dispatch_matrix(const bfx_asm* P, int kernel_id, const AsmArgs& a, cudaStrea
   case BFX_K_FACET_MASS_P1_TET_A: return launch_matrix<el::FacetMassP1Tet, MODE>(P, a, st);
   case BFX_K_AVG_MASS_P1_TRI_DS: return launch_matrix<el::AvgMassP1TriDS, MODE>(P, a, st);
   case BFX_K_ELASTICITY_Q1_HEX_A: return launch_q1<MODE>(P, a, st);
-  default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a bilinear-form kernel", kernel_id);
+  default:
+    if (kernel_id >= BFX_K_USER_BASE)
+      return launch_user(P, kernel_id, a, MODE, nullptr, st);
+    return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a bilinear-form kernel", kernel_id);
   }
 }
 
@@ -903,7 +724,10 @@ int dispatch_vector(int kernel_id, const AsmArgs& a, cudaStream_t st)
   case BFX_K_ACTION_POISSON_P2_TET_L: return launch_vector<el::ActionOf<el::PoissonP2Tet>>(a, st);
   case BFX_K_AVG_LOAD_P1_TRI_DS_L: return launch_vector<el::AvgLoadP1TriDS>(a, st);
   case BFX_K_LOAD_PROD_P1_TET_L: return launch_vector<el::LoadProdP1Tet>(a, st);
-  default: return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a linear-form kernel", kernel_id);
+  default:
+    if (kernel_id >= BFX_K_USER_BASE)
+      return launch_user(nullptr, kernel_id, a, 2, nullptr, st);
+    return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a linear-form kernel", kernel_id);
   }
 }
 
@@ -918,12 +742,41 @@ const bfx_kernel_info_t KINFO[BFX_K_COUNT] = {
 // coefficients gathered by the fused path of a kernel (all of the same layout): 1 unless listed
 int kernel_ncoef(int kernel_id) { return kernel_id == BFX_K_LOAD_PROD_P1_TET_L ? 2 : 1; }
 
+// kernels registered by the caller (bfx_register_kernel, include/bfx_plugin.cuh)
+struct UserKernel
+{
+  bfx_kernel_info_t info;
+  bfx_user_launch_t launch;
+};
+std::map<int, UserKernel>& user_kernels()
+{
+  static std::map<int, UserKernel> m;
+  return m;
+}
+const bfx_kernel_info_t* kinfo(int kernel_id)
+{
+  if (kernel_id >= 0 && kernel_id < BFX_K_COUNT)
+    return KINFO[kernel_id].rank >= 0 ? &KINFO[kernel_id] : nullptr;
+  auto it = user_kernels().find(kernel_id);
+  return it == user_kernels().end() ? nullptr : &it->second.info;
+}
+int launch_user(const bfx_asm* P, int kernel_id, const AsmArgs& a, int mode, double* scalar_dev, cudaStream_t st)
+{
+  auto it = user_kernels().find(kernel_id);
+  if (it == user_kernels().end())
+    return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is neither built in nor registered", kernel_id);
+  const int e = it->second.launch(&a, P ? P->pos_bytes : 1, mode, scalar_dev, st);
+  if (e != BFX_OK)
+    return fail(e, "registered kernel %d: launch failed (mode %d)", kernel_id, mode);
+  return BFX_OK;
+}
+
 int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, const bfx_coeffs_t* coeffs,
                 const double* constants, int n_constants, AsmArgs& a, bool need_csr = true)
 {
   BFX_REQUIRE(P && x, "assemble: null plan or geometry");
-  BFX_REQUIRE(kernel_id >= 0 && kernel_id < BFX_K_COUNT, "assemble: bad kernel id %d", kernel_id);
-  const bfx_kernel_info_t& ki = KINFO[kernel_id];
+  BFX_REQUIRE(kinfo(kernel_id), "assemble: bad kernel id %d", kernel_id);
+  const bfx_kernel_info_t& ki = *kinfo(kernel_id);
   BFX_REQUIRE(ki.rank == rank, "kernel id %d has rank %d, expected %d", kernel_id, ki.rank, rank);
   BFX_REQUIRE(ki.nx == P->nx && ki.nd == P->nd0, "kernel id %d expects nx=%d nd=%d, plan has nx=%d nd=%d", kernel_id,
               ki.nx, ki.nd, P->nx, P->nd0);
@@ -956,8 +809,9 @@ int fill_common(const bfx_asm* P, int kernel_id, int rank, const double* x, cons
     }
     else
     {
-      const int nc = kernel_ncoef(kernel_id);
-      BFX_REQUIRE(coeffs->n_fused == nc, "kernel id %d gathers %d coefficient(s), %d given", kernel_id, nc, coeffs->n_fused);
+      // (registered kernels: as many coefficients of one layout as fill w)
+      const int nc = kernel_id >= BFX_K_USER_BASE ? (coeffs->n_fused > 0 ? coeffs->n_fused : 1) : kernel_ncoef(kernel_id);
+      BFX_REQUIRE(coeffs->n_fused == nc && nc <= 4, "kernel id %d gathers %d coefficient(s), %d given", kernel_id, nc, coeffs->n_fused);
       for (int k = 0; k < nc; ++k)
       {
         BFX_REQUIRE(coeffs->fused[k].values_dev && coeffs->fused[k].dofmap_dev, "fused coefficient %d: null array", k);
@@ -1009,8 +863,18 @@ extern "C"
 {
 int bfx_kernel_info(int kernel_id, bfx_kernel_info_t* info)
 {
-  BFX_REQUIRE(kernel_id >= 0 && kernel_id < BFX_K_COUNT && info, "bfx_kernel_info: bad kernel id %d", kernel_id);
-  *info = KINFO[kernel_id];
+  BFX_REQUIRE(info && (kinfo(kernel_id) || (kernel_id >= 0 && kernel_id < BFX_K_COUNT)), "bfx_kernel_info: bad kernel id %d", kernel_id);
+  *info = kinfo(kernel_id) ? *kinfo(kernel_id) : KINFO[kernel_id];
+  return BFX_OK;
+}
+
+int bfx_register_kernel(int kernel_id, const bfx_kernel_info_t* info, bfx_user_launch_t launch)
+{
+  BFX_REQUIRE(kernel_id >= BFX_K_USER_BASE && info && launch, "bfx_register_kernel: ids start at BFX_K_USER_BASE (%d)", BFX_K_USER_BASE);
+  BFX_REQUIRE(info->nx > 0 && info->nd > 0 && info->bs > 0 && info->rank >= 0 && info->rank <= 2 && info->w_size >= 0
+                  && info->c_size >= 0 && info->c_size <= 8,
+              "bfx_register_kernel: inconsistent kernel description");
+  user_kernels()[kernel_id] = UserKernel{*info, launch};
   return BFX_OK;
 }
 
@@ -1139,7 +1003,7 @@ int bfx_assemble_matrix_cells(const bfx_asm_t* P, int kernel_id, const double* x
   if (e)
     return e;
   BFX_REQUIRE(values, "bfx_assemble_matrix_cells: null values");
-  BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
+  BFX_REQUIRE(!kinfo(kernel_id)->facet, "kernel id %d is a facet kernel", kernel_id);
   if (strategy != BFX_ASM_ATOMIC && strategy != BFX_ASM_CHUNKED && strategy != BFX_ASM_ROWGATHER)
     return fail(BFX_ERR_UNSUPPORTED, "assembly strategy %d not available", strategy);
   a.cells = P->cells;
@@ -1218,7 +1082,7 @@ int bfx_assemble_matrix_facets(const bfx_asm_t* P, int kernel_id, const double* 
   if (e)
     return e;
   BFX_REQUIRE(values && (entities || n_entities == 0), "bfx_assemble_matrix_facets: null argument");
-  BFX_REQUIRE(KINFO[kernel_id].facet, "kernel id %d is not a facet kernel", kernel_id);
+  BFX_REQUIRE(kinfo(kernel_id)->facet, "kernel id %d is not a facet kernel", kernel_id);
   a.entities = entities;
   a.n = n_entities;
   a.bc0 = bc0;
@@ -1258,7 +1122,7 @@ int bfx_lift_bc_cells(const bfx_asm_t* P, int kernel_id, const double* x, const 
     cudaStream_t st = S(stream);
     BFX_CUDA(cudaMemsetAsync(Pm->lift_count, 0, sizeof(unsigned long long), st));
     k_cells_with_bc<<<grid_for(P->ncells, 256, 16), 256, 0, st>>>(P->ncells, P->cells, a.dofmap1, P->nd1,
-                                                                  KINFO[kernel_id].bs, bc_markers1, Pm->lift_cells,
+                                                                  kinfo(kernel_id)->bs, bc_markers1, Pm->lift_cells,
                                                                   Pm->lift_count);
     a.cells = Pm->lift_cells;
     a.n_dev = Pm->lift_count;
@@ -1274,7 +1138,7 @@ int bfx_assemble_vector_cells(const bfx_asm_t* P, int kernel_id, const double* x
   if (e)
     return e;
   BFX_REQUIRE(b, "bfx_assemble_vector_cells: null b");
-  BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
+  BFX_REQUIRE(!kinfo(kernel_id)->facet, "kernel id %d is a facet kernel", kernel_id);
   if (strategy != BFX_ASM_ATOMIC && strategy != BFX_ASM_CHUNKED)
     return fail(BFX_ERR_UNSUPPORTED, "assembly strategy %d not available", strategy);
   a.cells = P->cells;
@@ -1308,7 +1172,19 @@ int run_scalar(int kernel_id, const AsmArgs& a, double* result_host, cudaStream_
     case BFX_K_ONE_TRI_DS_M: k_scalar_cells<el::OneTriDS><<<grid, 256, 0, st>>>(a, d_res); break;
     case BFX_K_AVG2_COEFF_P1_TRI_DS_M: k_scalar_cells<el::Avg2CoeffP1TriDS><<<grid, 256, 0, st>>>(a, d_res); break;
     case BFX_K_COEFF2_P1_TRI_FACET_M: k_scalar_cells<el::Coeff2P1TriFacet><<<grid, 256, 0, st>>>(a, d_res); break;
-    default: cudaFree(d_res); return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a functional kernel", kernel_id);
+    default:
+      if (kernel_id >= BFX_K_USER_BASE)
+      {
+        const int eu = launch_user(nullptr, kernel_id, a, 3, d_res, st);
+        if (eu)
+        {
+          cudaFree(d_res);
+          return eu;
+        }
+        break;
+      }
+      cudaFree(d_res);
+      return fail(BFX_ERR_UNSUPPORTED, "kernel id %d is not a functional kernel", kernel_id);
     }
   }
   BFX_CUDA(cudaMemcpyAsync(result_host, d_res, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1327,7 +1203,7 @@ int bfx_assemble_scalar_cells(const bfx_asm_t* P, int kernel_id, const double* x
   if (e)
     return e;
   BFX_REQUIRE(result_host, "bfx_assemble_scalar_cells: null result");
-  BFX_REQUIRE(!KINFO[kernel_id].facet, "kernel id %d is a facet kernel", kernel_id);
+  BFX_REQUIRE(!kinfo(kernel_id)->facet, "kernel id %d is a facet kernel", kernel_id);
   a.cells = P->cells;
   a.n = P->ncells;
   return run_scalar(kernel_id, a, result_host, S(stream));
@@ -1342,7 +1218,7 @@ int bfx_assemble_scalar_facets(const bfx_asm_t* P, int kernel_id, const double* 
   if (e)
     return e;
   BFX_REQUIRE(result_host && (entities || n_entities == 0), "bfx_assemble_scalar_facets: null argument");
-  BFX_REQUIRE(KINFO[kernel_id].facet, "kernel id %d is not a facet kernel", kernel_id);
+  BFX_REQUIRE(kinfo(kernel_id)->facet, "kernel id %d is not a facet kernel", kernel_id);
   a.entities = entities;
   a.n = n_entities;
   return run_scalar(kernel_id, a, result_host, S(stream));
@@ -1357,7 +1233,7 @@ int bfx_assemble_vector_facets(const bfx_asm_t* P, int kernel_id, const double* 
   if (e)
     return e;
   BFX_REQUIRE(b && (entities || n_entities == 0), "bfx_assemble_vector_facets: null argument");
-  BFX_REQUIRE(KINFO[kernel_id].facet, "kernel id %d is not a facet kernel", kernel_id);
+  BFX_REQUIRE(kinfo(kernel_id)->facet, "kernel id %d is not a facet kernel", kernel_id);
   a.entities = entities;
   a.n = n_entities;
   a.b = b;

@@ -447,9 +447,14 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
     if key in form._plans:
         return form._plans[key][0]
     mesh = form.mesh
-    # a functional (rank 0) has no test space: its plan carries the dofmap of its (first) coefficient
-    V0 = form.function_spaces[0] if form.rank > 0 else form.coefficients[0].function_space
-    dm0 = V0.dofmap
+    # a functional (rank 0) has no test space: its plan carries the dofmap of its (first) coefficient, or - without
+    # coefficients (M = 1 dx) - the geometry dofmap in that role
+    if form.rank > 0:
+        dm0 = form.function_spaces[0].dofmap
+    elif form.coefficients:
+        dm0 = form.coefficients[0].function_space.dofmap
+    else:
+        dm0 = None
     dm1 = form.function_spaces[1].dofmap if form.rank == 2 else None
     if subset is not None:
         ent, n = subset[1], int(subset[1].numel())
@@ -457,13 +462,17 @@ def _asm_plan(form: Form, integ: IntegralData, itype, A: la.MatrixCSR = None, su
         ent, n = _entities_dev(form, integ, itype)
     else:
         ent, n = None, 0  # facet integrals pass their entities at call time
-    im0 = dm0.index_map
+    if dm0 is not None:
+        d0_ptr, nd0 = dm0.dev.data_ptr(), dm0.shape[1]
+        n_rows = dm0.index_map.size_local + dm0.index_map.num_ghosts
+    else:
+        d0_ptr, nd0, n_rows = mesh.x_dofmap.data_ptr(), mesh.nx, int(mesh.x.shape[0])
     h = C.c_void_p()
     _lib.check(
         _lib.lib.bfx_asm_create(
-            C.byref(h), A._csr if A is not None else None, mesh.x_dofmap.data_ptr(), mesh.nx, dm0.dev.data_ptr(),
-            dm0.shape[1], dm1.dev.data_ptr() if dm1 is not None else None, dm1.shape[1] if dm1 is not None else 0,
-            mesh.num_cells, None if ent is None else ent.data_ptr(), n, im0.size_local + im0.num_ghosts, 1,
+            C.byref(h), A._csr if A is not None else None, mesh.x_dofmap.data_ptr(), mesh.nx, d0_ptr,
+            nd0, dm1.dev.data_ptr() if dm1 is not None else None, dm1.shape[1] if dm1 is not None else 0,
+            mesh.num_cells, None if ent is None else ent.data_ptr(), n, n_rows, 1,
             _lib.current_stream(),
         )
     )

@@ -106,6 +106,17 @@ extern "C"
   } bfx_kernel_info_t;
   int bfx_kernel_info(int kernel_id, bfx_kernel_info_t* info);
 
+  /* Kernel plug point for forms the library does not ship (include/bfx_plugin.cuh): the caller compiles the library's
+   * generic kernels for its own element struct and registers the launcher under an id >= BFX_K_USER_BASE.
+   * launch(args, pos_bytes, mode, scalar_dev, stream): args = the library's kernel argument block, mode 0 matrix,
+   * 1 lifting, 2 vector, 3 functional.  Registered ids run the cell-parallel fp64-RED strategy. */
+  enum
+  {
+    BFX_K_USER_BASE = 1000
+  };
+  typedef int (*bfx_user_launch_t)(const void* args, int pos_bytes, int mode, double* scalar_dev, void* stream);
+  int bfx_register_kernel(int kernel_id, const bfx_kernel_info_t* info, bfx_user_launch_t launch);
+
   /* ---- la::MatrixCSR structure ------------------------------------------------------------ */
   /* MatrixCSR(const SparsityPattern&) — la/MatrixCSR.h:628-703: copies graph, off_diag = row_ptr + nnz_diag.
    * row_ptr: int64[n_rows_all+1], cols: int32[nnz] (sorted per row), off_diag: int64[n_rows_all]. */

@@ -522,6 +522,49 @@ static void k_load_prod_p1_tet_L(double* b, const double* w, const double* c, co
   }
 }
 
+/* Forms the product does NOT ship: the checker side of the kernel plug point test (tests/cpp/user_kernel_plugin.cu
+ * registers the device versions through bfx_register_kernel).  a = inner(u, v) dx, L = c0 v dx, M = 1 dx on P1 tets. */
+static void k_mass_p1_tet_A(double* A, const double* w, const double* c, const double* xc, const int* e,
+                            const uint8_t* q, void* d)
+{
+  (void)w; (void)c; (void)e; (void)q; (void)d;
+  double K[3][3];
+  double det = fabs(tet_geometry(xc, K));
+  double pts[64][4];
+  int np = tet_rule(3, pts);
+  for (int p = 0; p < np; ++p)
+  {
+    double phi[4] = {1 - pts[p][0] - pts[p][1] - pts[p][2], pts[p][0], pts[p][1], pts[p][2]};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        A[4 * i + j] += pts[p][3] * det * phi[i] * phi[j];
+  }
+}
+
+static void k_source_const_p1_tet_L(double* b, const double* w, const double* c, const double* xc, const int* e,
+                                    const uint8_t* q, void* d)
+{
+  (void)w; (void)e; (void)q; (void)d;
+  double K[3][3];
+  double det = fabs(tet_geometry(xc, K));
+  double pts[64][4];
+  int np = tet_rule(2, pts);
+  for (int p = 0; p < np; ++p)
+  {
+    double phi[4] = {1 - pts[p][0] - pts[p][1] - pts[p][2], pts[p][0], pts[p][1], pts[p][2]};
+    for (int i = 0; i < 4; ++i)
+      b[i] += pts[p][3] * det * c[0] * phi[i];
+  }
+}
+
+static void k_volume_tet_M(double* A, const double* w, const double* c, const double* xc, const int* e, const uint8_t* q,
+                           void* d)
+{
+  (void)w; (void)c; (void)e; (void)q; (void)d;
+  double K[3][3];
+  A[0] += fabs(tet_geometry(xc, K)) / 6.0;
+}
+
 /* P2 basis on the reference tetrahedron: 4 vertex functions then 6 edge functions in Basix edge order */
 static const int TET_E[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
 
@@ -815,6 +858,9 @@ enum
   K_AVG2_COEFF_P1_TRI_DS_M = 21,
   K_COEFF2_P1_TRI_FACET_M = 22,
   K_LOAD_PROD_P1_TET_L = 23,
+  K_MASS_P1_TET_A = 24,         /* oracle-only: the plug point test's forms */
+  K_SOURCE_CONST_P1_TET_L = 25,
+  K_VOLUME_TET_M = 26,
   K_COUNT
 };
 
@@ -846,6 +892,9 @@ static orc_kernel_t kernel_table(int id)
   case K_AVG2_COEFF_P1_TRI_DS_M: return k_avg2_coeff_p1_tri_dS_M;
   case K_COEFF2_P1_TRI_FACET_M: return k_coeff2_p1_tri_ds_M;
   case K_LOAD_PROD_P1_TET_L: return k_load_prod_p1_tet_L;
+  case K_MASS_P1_TET_A: return k_mass_p1_tet_A;
+  case K_SOURCE_CONST_P1_TET_L: return k_source_const_p1_tet_L;
+  case K_VOLUME_TET_M: return k_volume_tet_M;
   default: return 0;
   }
 }

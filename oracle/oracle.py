@@ -49,6 +49,9 @@ K_ONE_TRI_DS_M = 20
 K_AVG2_COEFF_P1_TRI_DS_M = 21
 K_COEFF2_P1_TRI_FACET_M = 22
 K_LOAD_PROD_P1_TET_L = 23
+ORACLE_MASS_P1_TET_A = 24  # oracle-only forms of the kernel plug point test
+ORACLE_SOURCE_CONST_P1_TET_L = 25
+ORACLE_VOLUME_TET_M = 26
 
 
 def build(fast: bool = False) -> str:
