@@ -55,7 +55,7 @@ K_LOAD_PROD_P1_TET_L = 23
 
 USER_KERNEL_BASE = 1000  # ids of kernels registered by the caller (bfx_register_kernel, include/bfx_plugin.cuh)
 
-ASM_ATOMIC, ASM_GATHER, ASM_CHUNKED, ASM_ROWGATHER = 0, 1, 2, 3
+ASM_ATOMIC, ASM_CHUNKED, ASM_ROWGATHER = 0, 2, 3
 ROWGATHER_KERNELS = frozenset({10})
 # linear-form kernels with the grouped (one RED per distinct dof of 32 cells) variant
 GROUPED_VECTOR_KERNELS = frozenset({1, 3, 7, 15})

@@ -225,7 +225,7 @@ extern "C"
   enum
   {
     BFX_ASM_ATOMIC = 0, /* cell-parallel, fp64 RED atomics into CSR through the cell->nnz map */
-    BFX_ASM_GATHER = 1, /* reserved (row-parallel gather); returns BFX_ERR_UNSUPPORTED */
+    /* 1 was reserved for a row-parallel gather in round 1; BFX_ASM_ROWGATHER took that role */
     BFX_ASM_CHUNKED = 2, /* chunk-aggregated: element matrices staged in shared memory, one update per distinct
                             CSR entry and chunk; needs bfx_asm_build_chunks() */
     BFX_ASM_ROWGATHER = 3 /* row-parallel gather with per-(row, cell) recomputation, every CSR value written once by
