@@ -93,10 +93,8 @@ struct bfx_chunks
   uint8_t *wv_loc = nullptr, *wd_loc = nullptr; // 4 * ceil(width / 4) bytes per slot
   int lean_dbg = 0;
   bool tables_complete = false; // every group of 32 cells has its node (and dof) table: no direct-gather groups
-  // split of the chunks for the distributed overlap (bfx_asm_chunk_partition): part 1 = chunks with a cell that touches a
-  // row >= part_rows (ghost rows), listed in part_list; part 2 = the others (part_flag[q] == 0)
-  uint32_t* part_list = nullptr;
-  uint8_t* part_flag = nullptr;
+  // split of the chunks for the distributed overlap (bfx_asm_chunk_partition): the chunks with a cell that touches a row
+  // >= part_rows (ghost rows) are MOVED to the front - part 1 = chunks [0, n_part1), part 2 = the others
   int64_t n_part1 = 0;
   int32_t part_rows = -1;
   int launch_part = 0; // which part the next launch runs (0 = all chunks); set by bfx_assemble_matrix_cells_part

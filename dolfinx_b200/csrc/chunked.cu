@@ -1485,8 +1485,7 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : (staged_per_cell(E::ND * 
 // ---------------------------------------------------------------------------------------------
 // one warp per chunk: does any dof of the chunk's tables lie at or beyond n_owned (a ghost row)?
 __global__ void k_chunk_partition(int64_t nchunks, int cb, const int32_t* __restrict__ wd_ids, int64_t ncells,
-                                  int32_t n_owned, uint8_t* __restrict__ flag, uint32_t* __restrict__ list,
-                                  unsigned long long* __restrict__ count)
+                                  int32_t n_owned, int32_t* __restrict__ flag)
 {
   const int lane = threadIdx.x & 31;
   for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nchunks; q += ((int64_t)gridDim.x * blockDim.x) >> 5)
@@ -1501,11 +1500,33 @@ __global__ void k_chunk_partition(int64_t nchunks, int cb, const int32_t* __rest
     }
     hit = __any_sync(0xffffffffu, hit);
     if (lane == 0)
-    {
       flag[q] = hit ? 1 : 0;
-      if (hit)
-        list[atomicAdd(count, 1ull)] = (uint32_t)q;
-    }
+  }
+}
+
+// new position of every chunk: flagged chunks first, both classes in their old (Morton) order
+__global__ void k_chunk_new_index(int64_t nchunks, const int32_t* __restrict__ flag, const int32_t* __restrict__ before,
+                                  int32_t n_first, int32_t* __restrict__ to)
+{
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nchunks; q += (int64_t)gridDim.x * blockDim.x)
+    to[q] = flag[q] ? before[q] : n_first + (int32_t)(q - before[q]);
+}
+
+// per-chunk records moved to their new positions: the header and the cb table words of every table
+__global__ void k_chunk_move(int64_t nchunks, int cb, const int32_t* __restrict__ to, const ChunkHdr* __restrict__ hdr,
+                             ChunkHdr* __restrict__ hdr_new, const uint32_t* __restrict__ t0, uint32_t* __restrict__ n0,
+                             const uint32_t* __restrict__ t1, uint32_t* __restrict__ n1, const uint32_t* __restrict__ t2,
+                             uint32_t* __restrict__ n2, const uint32_t* __restrict__ t3, uint32_t* __restrict__ n3)
+{
+  const int64_t total = nchunks * cb;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x)
+  {
+    const int64_t q = s / cb;
+    const int k = (int)(s - q * cb);
+    const int64_t d = (int64_t)to[q] * cb + k;
+    n0[d] = t0[s], n1[d] = t1[s], n2[d] = t2[s], n3[d] = t3[s];
+    if (k == 0)
+      hdr_new[to[q]] = hdr[q];
   }
 }
 
@@ -1523,10 +1544,9 @@ struct LeanArgs
   double constants[4];
   uint32_t n; // cells of the plan
   int overwrite;
-  // launch over part of the chunks: chunk_list[blockIdx.x] names the chunk (grid = list length), or every chunk with
-  // skip[chunk] != 0 returns at once (grid = all chunks); both NULL = all chunks
-  const uint32_t* chunk_list;
-  const uint8_t* skip;
+  // launch over part of the chunks: the grid covers the chunks [chunk_begin, chunk_begin + gridDim.x)
+  // (bfx_asm_chunk_partition puts the chunks on ghost rows first)
+  uint32_t chunk_begin;
 };
 
 template <class E, int CB, int DBG = 0, int OCC = 0, bool MASKED = false>
@@ -1543,11 +1563,7 @@ __global__ void __launch_bounds__(CB, OCC ? OCC : chunk_min_ctas(CB)) k_matrix_l
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
 
   const uint32_t tid = threadIdx.x;
-  uint32_t q = blockIdx.x;
-  if (p.chunk_list)
-    q = __ldg(p.chunk_list + blockIdx.x);
-  // (the skip flag travels with the first-level loads and is tested after them: no extra load level per CTA)
-  const uint8_t skipped = p.skip ? __ldg(p.skip + q) : (uint8_t)0;
+  const uint32_t q = blockIdx.x + p.chunk_begin;
   const uint32_t slot = q * (uint32_t)CB + tid;
   // ---- first-level loads (coalesced, one word each)
   const int32_t vtx = __ldg(p.wv_ids + slot);
@@ -1559,8 +1575,6 @@ __global__ void __launch_bounds__(CB, OCC ? OCC : chunk_min_ctas(CB)) k_matrix_l
     locd = __ldg(p.wd_loc + slot);
   }
   const ChunkHdr h = p.hdr[q];
-  if (skipped)
-    return;
   const int n_dw = (h.n_dest + 31) >> 5;
   const uint32_t src_bytes = (uint32_t)h.n_src32 * 64u, dest_bytes = (uint32_t)n_dw * 256u;
   constexpr int WS = MASKED ? 2 : 1; // words per group: (list offset, length) [, completeness mask]
@@ -2023,14 +2037,14 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
         lp.constants[k] = a.constants[k];
       lp.n = (uint32_t)a.n;
       lp.overwrite = ch.overwrite;
-      lp.chunk_list = nullptr, lp.skip = nullptr;
+      lp.chunk_begin = 0;
       unsigned lean_grid = (unsigned)c->nchunks;
-      if (c->launch_part == 1)
-        lp.chunk_list = c->part_list, lean_grid = (unsigned)c->n_part1;
-      else if (c->launch_part == 2)
-        lp.skip = c->part_flag;
-      if (c->launch_part != 0 && !c->part_flag)
+      if (c->launch_part != 0 && c->part_rows < 0)
         return fail(BFX_ERR_INVALID, "chunk plan has no partition (bfx_asm_chunk_partition)");
+      if (c->launch_part == 1)
+        lean_grid = (unsigned)c->n_part1;
+      else if (c->launch_part == 2)
+        lp.chunk_begin = (uint32_t)c->n_part1, lean_grid = (unsigned)(c->nchunks - c->n_part1);
       if (lean_grid == 0)
         return BFX_OK;
       const int dbg = c->lean_dbg;
@@ -2803,8 +2817,6 @@ void free_chunks(bfx_chunks* c)
 {
   if (!c)
     return;
-  cudaFree(c->part_list);
-  cudaFree(c->part_flag);
   cudaFree(c->glist);
   cudaFree(c->goff);
   cudaFree(c->hdr);
@@ -3305,28 +3317,85 @@ int bfx_asm_chunk_partition(bfx_asm_t* P, int32_t n_owned_rows, int64_t* n_first
 {
   BFX_REQUIRE(P && P->chunks && n_first, "bfx_asm_chunk_partition: no chunk plan");
   bfx_chunks* c = P->chunks;
-  if (!(c->tables_complete && c->wd_ids && P->nd0 <= 4 && !c->vector_plan))
-    return fail(BFX_ERR_UNSUPPORTED, "chunk partition needs complete dof tables (lean plans)");
-  if (c->part_flag && c->part_rows == n_owned_rows)
+  if (!(c->tables_complete && c->wv_ids && c->wd_ids && P->nx <= 4 && P->nd0 <= 4 && !c->vector_plan && c->slim))
+    return fail(BFX_ERR_UNSUPPORTED, "chunk partition needs a plan reduced to the lean kernel's arrays");
+  if (c->part_rows == n_owned_rows)
   {
     *n_first = c->n_part1;
     return BFX_OK;
   }
-  cudaFree(c->part_list), c->part_list = nullptr;
-  cudaFree(c->part_flag), c->part_flag = nullptr;
+  // flags, their exclusive scan, the new index of every chunk
+  const int64_t nch = c->nchunks;
+  int32_t *flag = nullptr, *before = nullptr, *to = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  ChunkHdr* hdr_new = nullptr;
+  uint32_t* tn[4] = {nullptr, nullptr, nullptr, nullptr};
+  const int64_t nslots_alloc = (P->ncells + 767) / 768 * 768; // (as allocated by bfx_asm_build_chunks)
+  auto release = [&]()
+  {
+    cudaFree(flag), cudaFree(before), cudaFree(to), cudaFree(tmp);
+  };
   int e;
-  unsigned long long* d_count = nullptr;
-  if ((e = dev_alloc(&c->part_list, (size_t)c->nchunks + 1)) || (e = dev_alloc(&c->part_flag, (size_t)c->nchunks + 1))
-      || (e = dev_alloc(&d_count, 1)))
+  if ((e = dev_alloc(&flag, (size_t)nch + 1)) || (e = dev_alloc(&before, (size_t)nch + 1)) || (e = dev_alloc(&to, (size_t)nch))
+      || (e = dev_alloc(&hdr_new, (size_t)nch)))
+  {
+    release();
+    cudaFree(hdr_new);
     return e;
-  BFX_CUDA(cudaMemset(d_count, 0, sizeof(unsigned long long)));
-  k_chunk_partition<<<grid_for(c->nchunks * 32, 256, 16), 256>>>(c->nchunks, c->cb, c->wd_ids, P->ncells, n_owned_rows,
-                                                                c->part_flag, c->part_list, d_count);
-  BFX_CHECK_LAUNCH();
-  unsigned long long h = 0;
-  BFX_CUDA(cudaMemcpy(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost));
-  cudaFree(d_count);
-  c->n_part1 = (int64_t)h;
+  }
+  for (int k = 0; k < 4; ++k)
+    if ((e = dev_alloc(&tn[k], (size_t)nslots_alloc)))
+    {
+      release();
+      cudaFree(hdr_new);
+      for (auto* t : tn)
+        cudaFree(t);
+      return e;
+    }
+  BFX_CUDA(cudaMemset(flag, 0, sizeof(int32_t) * ((size_t)nch + 1)));
+  k_chunk_partition<<<grid_for(nch * 32, 256, 16), 256>>>(nch, c->cb, c->wd_ids, P->ncells, n_owned_rows, flag);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, before, nch + 1);
+  cudaError_t ce = cudaMalloc(&tmp, tmp_bytes);
+  if (ce == cudaSuccess)
+    ce = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, before, nch + 1);
+  int32_t h_first = 0;
+  if (ce == cudaSuccess)
+    ce = cudaMemcpy(&h_first, before + nch, sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    release();
+    cudaFree(hdr_new);
+    for (auto* t : tn)
+      cudaFree(t);
+    return fail(BFX_ERR_CUDA, "bfx_asm_chunk_partition: %s", cudaGetErrorString(ce));
+  }
+  k_chunk_new_index<<<grid_for(nch, 256, 8), 256>>>(nch, flag, before, h_first, to);
+  // tables keep their padding beyond the last chunk
+  uint32_t* told[4] = {reinterpret_cast<uint32_t*>(c->wv_ids), reinterpret_cast<uint32_t*>(c->wv_loc),
+                       reinterpret_cast<uint32_t*>(c->wd_ids), reinterpret_cast<uint32_t*>(c->wd_loc)};
+  for (int k = 0; k < 4; ++k)
+    cudaMemcpy(tn[k], told[k], sizeof(uint32_t) * (size_t)nslots_alloc, cudaMemcpyDeviceToDevice);
+  k_chunk_move<<<grid_for(nch * c->cb, 256, 16), 256>>>(nch, c->cb, to, c->hdr, hdr_new, told[0], tn[0], told[1], tn[1],
+                                                       told[2], tn[2], told[3], tn[3]);
+  ce = cudaDeviceSynchronize();
+  release();
+  if (ce != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    cudaFree(hdr_new);
+    for (auto* t : tn)
+      cudaFree(t);
+    return fail(BFX_ERR_CUDA, "bfx_asm_chunk_partition: %s", cudaGetErrorString(ce));
+  }
+  cudaFree(c->hdr);
+  for (auto* t : told)
+    cudaFree(t);
+  c->hdr = hdr_new;
+  c->wv_ids = reinterpret_cast<int32_t*>(tn[0]), c->wv_loc = reinterpret_cast<uint8_t*>(tn[1]);
+  c->wd_ids = reinterpret_cast<int32_t*>(tn[2]), c->wd_loc = reinterpret_cast<uint8_t*>(tn[3]);
+  c->n_part1 = h_first;
   c->part_rows = n_owned_rows;
   *n_first = c->n_part1;
   return BFX_OK;

@@ -354,9 +354,9 @@ extern "C"
                                  const int32_t* entities_dev, int64_t n_entities, const int8_t* bc0_dev,
                                  const int8_t* bc1_dev, const bfx_coeffs_t* coeffs, const double* constants_host,
                                  int n_constants, double* values_dev, bfx_stream_t stream);
-  /* Chunk plans for the distributed overlap: bfx_asm_chunk_partition marks the chunks that hold a cell touching a row
-   * >= n_owned_rows (a ghost row); *n_first = their number.  bfx_assemble_matrix_cells_part then runs part 1 (those
-   * chunks), part 2 (all the others) or 0 (all) of the SAME plan - the chunk geometry (whole-cube bricks under the
+  /* Chunk plans for the distributed overlap: bfx_asm_chunk_partition moves the chunks that hold a cell touching a row
+   * >= n_owned_rows (a ghost row) to the front of the plan; *n_first = their number.  bfx_assemble_matrix_cells_part then
+   * runs part 1 (those chunks), part 2 (all the others) or 0 (all) of the SAME plan - the chunk geometry (whole-cube bricks under the
    * Morton order) and the completeness of every destination stay those of the one-launch plan, which a plan over a
    * cell subset loses.  A caller assembles part 1, starts MatrixCSR::scatter_rev and assembles part 2 meanwhile. */
   int bfx_asm_chunk_partition(bfx_asm_t* plan, int32_t n_owned_rows, int64_t* n_first);
