@@ -111,7 +111,9 @@ int bfx_csr_matmul_begin(const bfx_csr_t* A, const double* a_values, const bfx_c
       || (e = dev_alloc(&h->off_diag, n1)))
     return bail(e);
   k_matmul_bound<<<grid_for((int64_t)n1, 256, 16), 256, 0, st>>>(m, h->n_rows, h->cnt);
-  cudaError_t ce = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->cnt, h->wofs, (int)n1, st);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess)
+    ce = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->cnt, h->wofs, (int)n1, st);
   if (ce == cudaSuccess)
     ce = cudaMalloc(&tmp, tmp_bytes);
   if (ce == cudaSuccess)
@@ -125,7 +127,9 @@ int bfx_csr_matmul_begin(const bfx_csr_t* A, const double* a_values, const bfx_c
   if ((e = dev_alloc(&h->wcols, (size_t)total + 1)) || (e = dev_alloc(&h->wvals, (size_t)total + 1)))
     return bail(e);
   k_matmul_rows<<<grid_for((int64_t)n1, 128, 32), 128, 0, st>>>(m, h->n_rows, h->wofs, h->wcols, h->wvals, h->cnt, h->off_diag);
-  ce = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, h->cnt, h->row_ptr, (int)n1, st);
+  ce = cudaGetLastError();
+  if (ce == cudaSuccess)
+    ce = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, h->cnt, h->row_ptr, (int)n1, st);
   if (ce == cudaSuccess)
     ce = cudaMemcpyAsync(&h->nnz, h->row_ptr + h->n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess)
