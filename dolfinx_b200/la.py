@@ -326,7 +326,9 @@ class Vector:
         return self._scatterer
 
     def set(self, v: float):
-        self.array.fill_(v)
+        from . import _lib
+
+        _lib.check(_lib.lib.bfx_fill(self.array.numel(), float(v), self.array.data_ptr(), _lib.current_stream()))
 
     def _n_owned(self):
         return self.bs * self.index_map.size_local
@@ -825,7 +827,10 @@ class MatrixCSR:
     def _values(self):
         """The value array for the library's own kernels (a pending zero-fill is written first)."""
         if self._zero_pending:
-            self._data.zero_()
+            from . import _lib
+
+            # (the library's own fill: cudaMemsetAsync on the caller's stream, no framework kernel in the step)
+            _lib.check(_lib.lib.bfx_fill(self._data.numel(), 0.0, self._data.data_ptr(), _lib.current_stream()))
             self._zero_pending = False
         return self._data
 
@@ -845,8 +850,10 @@ class MatrixCSR:
         if x == 0.0:
             self._zero_pending = True
         else:
+            from . import _lib
+
             self._zero_pending = False
-            self._data.fill_(x)
+            _lib.check(_lib.lib.bfx_fill(self._data.numel(), float(x), self._data.data_ptr(), _lib.current_stream()))
         self._is_zero = x == 0.0
 
     def _take_zero_fill(self):
