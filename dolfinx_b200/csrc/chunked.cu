@@ -1493,10 +1493,9 @@ __global__ void k_chunk_partition(int64_t nchunks, int cb, const int32_t* __rest
     bool hit = false;
     for (int k = lane; k < cb; k += 32)
     {
-      const int64_t slot = q * cb + k;
-      // (table words of the groups past the last cell are padding)
-      if ((slot & ~(int64_t)31) < ncells)
-        hit |= wd_ids[slot] >= n_owned;
+      // (table words of padding slots repeat a dof of their group, or dof 0 in a group without cells: never a ghost
+      // unless everything is)
+      hit |= wd_ids[q * cb + k] >= n_owned;
     }
     hit = __any_sync(0xffffffffu, hit);
     if (lane == 0)
@@ -1516,7 +1515,8 @@ __global__ void k_chunk_new_index(int64_t nchunks, const int32_t* __restrict__ f
 __global__ void k_chunk_move(int64_t nchunks, int cb, const int32_t* __restrict__ to, const ChunkHdr* __restrict__ hdr,
                              ChunkHdr* __restrict__ hdr_new, const uint32_t* __restrict__ t0, uint32_t* __restrict__ n0,
                              const uint32_t* __restrict__ t1, uint32_t* __restrict__ n1, const uint32_t* __restrict__ t2,
-                             uint32_t* __restrict__ n2, const uint32_t* __restrict__ t3, uint32_t* __restrict__ n3)
+                             uint32_t* __restrict__ n2, const uint32_t* __restrict__ t3, uint32_t* __restrict__ n3,
+                             int64_t ncells, int already_counted)
 {
   const int64_t total = nchunks * cb;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x)
@@ -1526,7 +1526,12 @@ __global__ void k_chunk_move(int64_t nchunks, int cb, const int32_t* __restrict_
     const int64_t d = (int64_t)to[q] * cb + k;
     n0[d] = t0[s], n1[d] = t1[s], n2[d] = t2[s], n3[d] = t3[s];
     if (k == 0)
-      hdr_new[to[q]] = hdr[q];
+    {
+      ChunkHdr h = hdr[q];
+      if (!already_counted) // first partition of this plan: chunk q holds the cells [q cb, min((q + 1) cb, ncells))
+        h.pad = (int32_t)max((int64_t)0, min((int64_t)cb, ncells - q * cb));
+      hdr_new[to[q]] = h;
+    }
   }
 }
 
@@ -1547,6 +1552,7 @@ struct LeanArgs
   // launch over part of the chunks: the grid covers the chunks [chunk_begin, chunk_begin + gridDim.x)
   // (bfx_asm_chunk_partition puts the chunks on ghost rows first)
   uint32_t chunk_begin;
+  int valid_in_hdr; // cells of chunk q = hdr[q].pad (reordered plans) instead of min(CB, n - q CB)
 };
 
 template <class E, int CB, int DBG = 0, int OCC = 0, bool MASKED = false>
@@ -1618,7 +1624,10 @@ __global__ void __launch_bounds__(CB, OCC ? OCC : chunk_min_ctas(CB)) k_matrix_l
     for (int i = 0; i < ND; ++i)
       m |= __shfl_sync(0xffffffffu, bit, (int)(locd >> (8 * i))) << i;
   }
-  if (slot < p.n && DBG != 2 && DBG != 3)
+  // (a partitioned plan has its chunks reordered: the one partly filled chunk is no longer the last, its count of
+  // cells travels in the header)
+  const bool has_cell = p.valid_in_hdr ? tid < (uint32_t)h.pad : slot < p.n;
+  if (has_cell && DBG != 2 && DBG != 3)
   {
     typename E::Geo g;
     E::prepare(g, xc, nullptr, p.constants, 0);
@@ -2038,6 +2047,7 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       lp.n = (uint32_t)a.n;
       lp.overwrite = ch.overwrite;
       lp.chunk_begin = 0;
+      lp.valid_in_hdr = c->part_rows >= 0 ? 1 : 0;
       unsigned lean_grid = (unsigned)c->nchunks;
       if (c->launch_part != 0 && c->part_rows < 0)
         return fail(BFX_ERR_INVALID, "chunk plan has no partition (bfx_asm_chunk_partition)");
@@ -3378,7 +3388,7 @@ int bfx_asm_chunk_partition(bfx_asm_t* P, int32_t n_owned_rows, int64_t* n_first
   for (int k = 0; k < 4; ++k)
     cudaMemcpy(tn[k], told[k], sizeof(uint32_t) * (size_t)nslots_alloc, cudaMemcpyDeviceToDevice);
   k_chunk_move<<<grid_for(nch * c->cb, 256, 16), 256>>>(nch, c->cb, to, c->hdr, hdr_new, told[0], tn[0], told[1], tn[1],
-                                                       told[2], tn[2], told[3], tn[3]);
+                                                       told[2], tn[2], told[3], tn[3], P->ncells, c->part_rows >= 0 ? 1 : 0);
   ce = cudaDeviceSynchronize();
   release();
   if (ce != cudaSuccess)

@@ -639,7 +639,13 @@ struct BGArgs
   const uint16_t *perm, *ent;
   const double* rec;
   const uint8_t* mask0; // per node: bit k set = component k of the ROW carries a Dirichlet condition (or NULL)
-  const uint8_t* zcb;   // per (tile, block in tile): the same for the block's COLUMN (or NULL)
+  const uint8_t* zcb;   // per (tile, block in tile): the same for the block's COLUMN, precomputed per call (or NULL)
+  // round 2: the column mask of a block looked up by the thread that owns the block - its column index and the node's
+  // mask byte are requested before the contribution loop and used after it - instead of a per-call pass over all
+  // blocks (k_bg_block_masks: 0.67 ms of a 6.44 ms launch at C4)
+  const int32_t* cols;  // CSR column (node) of every block
+  const uint8_t* mask1; // per node: bit k set = component k of the COLUMN carries a Dirichlet condition (or NULL)
+  int32_t n_mask_nodes;
   double mu, lmbda;
   double* values;
   int dbg; // profiling only: 1 = no contribution loop, 2 = no store
@@ -682,7 +688,8 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
   unsigned char* stage0 = reinterpret_cast<unsigned char*>(s_hdr + 3);
   const size_t rec_bytes = (size_t)g.cell_cap * RG_STRIDE * 8, ent_bytes = (size_t)g.inc_cap * 16,
                perm_bytes = ((size_t)g.nb_cap * 2 + 15) & ~(size_t)15, zc_bytes = ((size_t)g.nb_cap + 15) & ~(size_t)15;
-  const size_t stage_bytes = rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16;
+  const size_t col_bytes = ((size_t)g.nb_cap * 4 + 15) & ~(size_t)15; // column node of every block of the tile
+  const size_t stage_bytes = rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16 + col_bytes;
   const int tid = threadIdx.x;
   const int64_t G = gridDim.x;
 
@@ -709,6 +716,17 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
     }
     if (g.mask0 && tid == 0)
       cp_async16(base + rec_bytes + ent_bytes + perm_bytes + zc_bytes, g.mask0 + tile * BG_ROWS);
+    // (tried: a per-tile "no marked column node in [cmin, cmax]" test through a per-call prefix count, to skip the
+    // lookups away from the boundary layer - its two loads sit on the critical path between tiles: 6.52 against 6.21 ms)
+    if (g.mask1) // the tile's blocks are consecutive CSR blocks: their columns are one contiguous run (4-byte copies:
+    {            // the run starts at an arbitrary block)
+      const int32_t* cg = g.cols + h.b0;
+      unsigned char* cs = base + rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16;
+      for (int k = tid; k < h.nb; k += BG_THREADS)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(cs + 4 * (size_t)k)),
+                     "l"(cg + k)
+                     : "memory");
+    }
     return tid < h.nuc ? __ldg(g.cells + tile * BG_CCAP + tid) : -1;
   };
   auto fetch_records = [&](int32_t cid, int st)
@@ -757,6 +775,8 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
     const uint16_t* s_perm = reinterpret_cast<const uint16_t*>(base + rec_bytes + ent_bytes);
     const uint8_t* s_zc = base + rec_bytes + ent_bytes + perm_bytes;
     const uint8_t* s_zr = s_zc + zc_bytes;
+    const int32_t* s_col = reinterpret_cast<const int32_t*>(s_zr + 16);
+    const bool col_masks = g.mask1 != nullptr;
     const int nb = h.nb;
     const int64_t b0 = h.b0;
     // smem element i of the image sits at the same offset modulo 16 bytes as global element b0 * 9 + i
@@ -769,6 +789,12 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
       {
         const uint32_t pmt = s_perm[t];
         const int bidx = (int)(pmt & 1023u), rowid = (int)(pmt >> 10);
+        unsigned zc_direct = 0u;
+        if (col_masks)
+        {
+          const int32_t cnode = s_col[bidx];
+          zc_direct = cnode < g.n_mask_nodes ? (unsigned)__ldg(g.mask1 + cnode) : 0u; // (ghost columns no cell touches)
+        }
         double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
         int off = 0;
 #pragma unroll 1
@@ -787,7 +813,7 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
             q1_affine_D_add((int)((en >> 3) & 7u), (int)(en & 7u), K, q4.y, A);
           }
         }
-        const unsigned zr = g.mask0 ? s_zr[rowid] : 0u, zc = g.zcb ? s_zc[bidx] : 0u;
+        const unsigned zr = g.mask0 ? s_zr[rowid] : 0u, zc = g.mask1 ? zc_direct : (g.zcb ? s_zc[bidx] : 0u);
         const double tr = A[0][0] + A[1][1] + A[2][2];
         double* o = img + bidx * 9;
 #pragma unroll
@@ -920,6 +946,9 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
       k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc0, G->bg_mask0);
       b.mask0 = G->bg_mask0;
     }
+    b.cols = csr->cols;
+    b.mask1 = nullptr;
+    b.n_mask_nodes = (int32_t)G->bg_n_nodes;
     if (a.bc1)
     {
       const uint8_t* m1 = G->bg_mask0;
@@ -928,9 +957,16 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
         k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc1, G->bg_mask1);
         m1 = G->bg_mask1;
       }
-      k_bg_block_masks<<<grid_for(G->bg_ntiles * BG_NBCAP, 256, 16), 256, 0, st>>>(G->bg_ntiles, static_cast<const BGTile*>(G->bg_tiles), csr->cols, m1,
-                                                                                (int32_t)G->bg_n_nodes, G->bg_zcb);
-      b.zcb = G->bg_zcb;
+      if (getenv("BFX_BG_BLOCK_MASKS")) // round-1 scheme, kept for A/B runs: one pass over all blocks per call
+      {
+        k_bg_block_masks<<<grid_for(G->bg_ntiles * BG_NBCAP, 256, 16), 256, 0, st>>>(G->bg_ntiles, static_cast<const BGTile*>(G->bg_tiles), csr->cols, m1,
+                                                                                  (int32_t)G->bg_n_nodes, G->bg_zcb);
+        b.zcb = G->bg_zcb;
+      }
+      else
+      {
+        b.mask1 = m1;
+      }
     }
     b.mu = a.constants[0], b.lmbda = a.constants[1];
     b.values = a.values;
@@ -941,7 +977,7 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
     b.inc_cap = G->bg_max_inc;
     b.nb_cap = G->bg_max_blocks;
     const size_t stage = (size_t)b.cell_cap * RG_STRIDE * 8 + (size_t)b.inc_cap * 16 + (((size_t)b.nb_cap * 2 + 15) & ~(size_t)15)
-                         + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16;
+                         + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16 + (((size_t)b.nb_cap * 4 + 15) & ~(size_t)15);
     const size_t smem = sizeof(double) * (size_t)b.img_cap + 3 * sizeof(BGTile) + 2 * stage;
     if (b.tile_end > b.tile_begin)
     {
