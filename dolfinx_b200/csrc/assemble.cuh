@@ -96,6 +96,8 @@ struct bfx_chunks
   // split of the chunks for the distributed overlap (bfx_asm_chunk_partition): the chunks with a cell that touches a row
   // >= part_rows (ghost rows) are MOVED to the front - part 1 = chunks [0, n_part1), part 2 = the others
   int64_t n_part1 = 0;
+  uint32_t* part_list = nullptr; // plans of the classic kernels keep their chunk order: the chunks of part 1, ascending
+  uint8_t* part_flag = nullptr;  // ... and 1 for every chunk of part 1
   int32_t part_rows = -1;
   int launch_part = 0; // which part the next launch runs (0 = all chunks); set by bfx_assemble_matrix_cells_part
   bool slim = false;            // reduced to what the lean kernel reads (perm, xdm, dm0, dm1, wv_cnt, wd_cnt freed)

@@ -957,6 +957,10 @@ struct ChunkArgs
   const uint32_t* wr_addr;        // two-stage write-back lists (see ChunkBuildArgs) or NULL
   const uint16_t* wr_src;
   int tables_complete;            // every group of 32 cells has its node (and dof) table: no per-group count loads
+  // launch over part of the chunks (bfx_assemble_matrix_cells_part on a plan that is not a lean one): chunk_list names
+  // the chunk of every CTA (grid = list length), or CTAs of chunks with skip[chunk] != 0 return at once
+  const uint32_t* chunk_list;
+  const uint8_t* skip;
 };
 
 // ---- TMA bulk copy + mbarrier (one chunk's lists are contiguous: two bulk copies per CTA) -----------
@@ -1157,7 +1161,11 @@ __global__ void __launch_bounds__(THREADS, OCC ? OCC : (staged_per_cell(E::ND * 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
 
   const int c = threadIdx.x % CB, sub = threadIdx.x / CB;
-  const int64_t q = blockIdx.x;
+  int64_t q = blockIdx.x;
+  if (ch.chunk_list)
+    q = ch.chunk_list[blockIdx.x];
+  else if (ch.skip && ch.skip[q])
+    return;
   const int64_t slot = q * CB + c;
 
   // ---- first-level loads of phase 1, all issued before anything waits (header, group tables, positions):
@@ -1500,6 +1508,28 @@ __global__ void k_chunk_partition(int64_t nchunks, int cb, const int32_t* __rest
     hit = __any_sync(0xffffffffu, hit);
     if (lane == 0)
       flag[q] = hit ? 1 : 0;
+  }
+}
+
+// the same from the chunk-ordered dofmap (plans without dof tables: more than 4 dofs per cell): flag + list
+__global__ void k_chunk_partition_dofmap(int64_t nchunks, int cb, const int32_t* __restrict__ dm0, int nd0, int64_t ncells,
+                                         int32_t n_owned, uint8_t* __restrict__ flag, uint32_t* __restrict__ list,
+                                         unsigned long long* __restrict__ count)
+{
+  const int lane = threadIdx.x & 31;
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nchunks; q += ((int64_t)gridDim.x * blockDim.x) >> 5)
+  {
+    bool hit = false;
+    const int64_t s0 = q * cb, s1 = min(s0 + cb, ncells);
+    for (int64_t k = s0 * nd0 + lane; k < s1 * nd0; k += 32)
+      hit |= dm0[k] >= n_owned;
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0)
+    {
+      flag[q] = hit ? 1 : 0;
+      if (hit)
+        list[atomicAdd(count, 1ull)] = (uint32_t)q;
+    }
   }
 }
 
@@ -2027,6 +2057,19 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   ch.wr_addr = c->wr_addr;
   ch.wr_src = c->wr_src;
   ch.tables_complete = 0;
+  ch.chunk_list = nullptr, ch.skip = nullptr;
+  unsigned classic_grid = (unsigned)c->nchunks;
+  if (c->launch_part != 0 && !c->slim)
+  {
+    if (!c->part_flag)
+      return fail(BFX_ERR_INVALID, "chunk plan has no partition (bfx_asm_chunk_partition)");
+    if (c->launch_part == 1)
+      ch.chunk_list = c->part_list, classic_grid = (unsigned)c->n_part1;
+    else
+      ch.skip = c->part_flag;
+    if (classic_grid == 0)
+      return BFX_OK;
+  }
   if constexpr (SYM && E::NX <= 4 && E::ND <= 4 && E::BS == 1 && E::WSIZE == 0 && THREADS == CB)
   {
     // BFX_CHUNK_KERNEL_LEAN: the instruction-lean kernel (linear staging, complete warp tables, 32-bit addresses)
@@ -2120,8 +2163,8 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
       return BFX_OK;
     }
   }
-  if (c->launch_part != 0)
-    return fail(BFX_ERR_UNSUPPORTED, "partial launches are implemented for the lean kernel");
+  if (c->launch_part != 0 && (c->wr_addr || c->kernel_variant == BFX_CHUNK_KERNEL_OCC5 || (c->kernel_variant >= 11 && c->kernel_variant <= 14)))
+    return fail(BFX_ERR_UNSUPPORTED, "partial launches are implemented for the default / DIET / lean kernels");
   if (c->slim)
     return fail(BFX_ERR_INVALID, "chunk plan reduced for the lean kernel: this call (element, addresses or markers) needs the full plan");
   if (c->len_sorted)
@@ -2198,7 +2241,7 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
     {
       BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+      k_matrix_chunked<E, SYM, CB, THREADS, uint32_t, false, 0, true><<<classic_grid, THREADS, smem, st>>>(a, ch);
       BFX_CHECK_LAUNCH();
       return BFX_OK;
     }
@@ -2207,13 +2250,13 @@ int launch_chunked_cb(const bfx_asm* P, const AsmArgs& a, int values_mode, cudaS
   {
     BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint32_t>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_matrix_chunked<E, SYM, CB, THREADS, uint32_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+    k_matrix_chunked<E, SYM, CB, THREADS, uint32_t><<<classic_grid, THREADS, smem, st>>>(a, ch);
   }
   else
   {
     BFX_CUDA(cudaFuncSetAttribute(k_matrix_chunked<E, SYM, CB, THREADS, uint64_t>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_matrix_chunked<E, SYM, CB, THREADS, uint64_t><<<(unsigned)c->nchunks, THREADS, smem, st>>>(a, ch);
+    k_matrix_chunked<E, SYM, CB, THREADS, uint64_t><<<classic_grid, THREADS, smem, st>>>(a, ch);
   }
   BFX_CHECK_LAUNCH();
   return BFX_OK;
@@ -2827,6 +2870,8 @@ void free_chunks(bfx_chunks* c)
 {
   if (!c)
     return;
+  cudaFree(c->part_list);
+  cudaFree(c->part_flag);
   cudaFree(c->glist);
   cudaFree(c->goff);
   cudaFree(c->hdr);
@@ -3327,13 +3372,59 @@ int bfx_asm_chunk_partition(bfx_asm_t* P, int32_t n_owned_rows, int64_t* n_first
 {
   BFX_REQUIRE(P && P->chunks && n_first, "bfx_asm_chunk_partition: no chunk plan");
   bfx_chunks* c = P->chunks;
-  if (!(c->tables_complete && c->wv_ids && c->wd_ids && P->nx <= 4 && P->nd0 <= 4 && !c->vector_plan && c->slim))
-    return fail(BFX_ERR_UNSUPPORTED, "chunk partition needs a plan reduced to the lean kernel's arrays");
   if (c->part_rows == n_owned_rows)
   {
     *n_first = c->n_part1;
     return BFX_OK;
   }
+  if (!c->slim)
+  {
+    // plans of the classic kernels (P2 ...): the chunks stay where they are; part 1 runs through a chunk list, part 2
+    // skips the flagged chunks (one more load per CTA: nothing against a 4 ms launch of 128-cell chunks)
+    if (c->vector_plan || c->wr_addr || !c->dm0)
+      return fail(BFX_ERR_UNSUPPORTED, "chunk partition: needs the chunk-ordered dofmap of a matrix plan");
+    cudaFree(c->part_list), c->part_list = nullptr;
+    cudaFree(c->part_flag), c->part_flag = nullptr;
+    unsigned long long* d_count = nullptr;
+    int e0;
+    if ((e0 = dev_alloc(&c->part_list, (size_t)c->nchunks + 1)) || (e0 = dev_alloc(&c->part_flag, (size_t)c->nchunks + 1))
+        || (e0 = dev_alloc(&d_count, 1)))
+      return e0;
+    BFX_CUDA(cudaMemset(d_count, 0, sizeof(unsigned long long)));
+    k_chunk_partition_dofmap<<<grid_for(c->nchunks * 32, 256, 16), 256>>>(c->nchunks, c->cb, c->dm0, P->nd0, P->ncells,
+                                                                       n_owned_rows, c->part_flag, c->part_list, d_count);
+    BFX_CHECK_LAUNCH();
+    unsigned long long hc = 0;
+    BFX_CUDA(cudaMemcpy(&hc, d_count, sizeof(hc), cudaMemcpyDeviceToHost));
+    cudaFree(d_count);
+    // (the list order decides nothing - every chunk of part 1 is launched - but a sorted list keeps the launch order,
+    // and with it the order of the REDs, close to that of the whole plan)
+    if (hc > 1)
+    {
+      void* tmp = nullptr;
+      size_t bytes = 0;
+      uint32_t* sorted = nullptr;
+      if (dev_alloc(&sorted, (size_t)hc) == BFX_OK
+          && cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->part_list, sorted, (int)hc) == cudaSuccess
+          && cudaMalloc(&tmp, bytes) == cudaSuccess
+          && cub::DeviceRadixSort::SortKeys(tmp, bytes, c->part_list, sorted, (int)hc) == cudaSuccess
+          && cudaDeviceSynchronize() == cudaSuccess)
+      {
+        cudaFree(c->part_list);
+        c->part_list = sorted;
+        sorted = nullptr;
+      }
+      (void)cudaGetLastError();
+      cudaFree(tmp);
+      cudaFree(sorted);
+    }
+    c->n_part1 = (int64_t)hc;
+    c->part_rows = n_owned_rows;
+    *n_first = c->n_part1;
+    return BFX_OK;
+  }
+  if (!(c->tables_complete && c->wv_ids && c->wd_ids && P->nx <= 4 && P->nd0 <= 4 && !c->vector_plan))
+    return fail(BFX_ERR_UNSUPPORTED, "chunk partition needs a plan reduced to the lean kernel's arrays");
   // flags, their exclusive scan, the new index of every chunk
   const int64_t nch = c->nchunks;
   int32_t *flag = nullptr, *before = nullptr, *to = nullptr;

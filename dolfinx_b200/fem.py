@@ -501,6 +501,8 @@ CHUNK_KERNEL = int(os.environ["BFX_CHUNK_DBG"]) if "BFX_CHUNK_DBG" in os.environ
 # C2 launch 2.71 ms against 3.30 ms of the bank-coloured classic kernel (profiles/r02_p1_variants.txt)
 CHUNK_LEAN = os.environ.get("BFX_CHUNK_LEAN", "1") != "0"
 # distributed overlap of the lean plans: boundary chunks on a high-priority side stream beside the interior launch
+# distributed overlap of the chunk-aggregated kernels: one plan of all cells in two launches (0: plans over cell subsets)
+OVERLAP_ONE_PLAN = os.environ.get("BFX_OVERLAP_ONE_PLAN", "1") != "0"
 OVERLAP_SIDE_STREAM = os.environ.get("BFX_OVERLAP_SIDE_STREAM", "0") != "0"  # measured at N = 2: no gain (3.32 against 3.22 ms per step)
 CHUNKS_PAD4 = os.environ.get("BFX_CHUNKS_PAD4", "0") != "0"  # source lists padded to multiples of 4 (round-2 experiment)
 CHUNKS_TWO_STAGE = int(os.environ.get("BFX_CHUNKS_TWO_STAGE", "0"))  # 1: one address-ordered list, 2: stores, then REDs
@@ -826,14 +828,16 @@ def assemble_matrix_overlapped(A: la.MatrixCSR, a: Form, bcs=(), constants=None,
             a._plans[key] = torch.cuda.mem_get_info()[0] >= 250 * ncells
         return a._plans[key]
 
-    if (len(items) == 1 and items[0][1].kernel in _lib.LEAN_KERNELS and strategy in (None, _lib.ASM_CHUNKED) and CHUNK_LEAN
-            and room_for_lean_attempt()):
+    if (len(items) == 1 and items[0][1].kernel in _lib.CHUNKED_KERNELS and strategy in (None, _lib.ASM_CHUNKED) and CHUNK_LEAN
+            and OVERLAP_ONE_PLAN and room_for_lean_attempt()):
         # Lean chunk plans: ONE plan of all cells, launched in two parts - the chunks with a cell on a ghost row first,
         # the others behind the exchange.  The chunks keep the whole-cube geometry and the completeness of the
         # one-launch plan (a plan over the interior cell SUBSET is cut through the cubes: 2.90 against 2.72 ms at C2).
         (itype, ident), integ = items[0]
         plan = _asm_plan(a, integ, itype, A)
-        if _matrix_strategy(a, integ, plan, strategy, lean_only=True) == _lib.ASM_CHUNKED:
+        # (P1-sized kernels: only if the mesh takes the lean plan - otherwise the builder stops early and the subset
+        # scheme below runs; P2: the plan of the classic kernel, launched through a chunk list / skip flags)
+        if _matrix_strategy(a, integ, plan, strategy, lean_only=integ.kernel in _lib.LEAN_KERNELS) == _lib.ASM_CHUNKED:
             n1 = C.c_int64(0)
             st = _lib.lib.bfx_asm_chunk_partition(plan, A.num_owned_rows(), C.byref(n1))
             if st == _lib.OK:

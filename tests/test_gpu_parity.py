@@ -1005,21 +1005,28 @@ def test_q1_rowgather_row_ranges(bfx, oracle, perturb):
     assert rows(1, n_all, 0) != K.OK  # not cut at a tile boundary
 
 
-def test_chunk_plan_partition(bfx, oracle):
-    """bfx_asm_chunk_partition / bfx_assemble_matrix_cells_part: the chunks of ONE lean plan split at a row threshold
+@pytest.mark.parametrize("case", ["p1", "p2"])
+def test_chunk_plan_partition(bfx, oracle, case):
+    """bfx_asm_chunk_partition / bfx_assemble_matrix_cells_part: the chunks of ONE plan (p1: the lean plan, whose flagged
+    chunks move to the front; p2: the classic plan, chunk list + skip flags) split at a row threshold
     (the distributed overlap's ghost rows) - part 1 then part 2 give the one-launch matrix (overwrite mode on zeros
     and add mode), part 1 alone writes nothing into chunks without a row beyond the threshold, and a threshold beyond
     the last row leaves part 1 empty."""
     import ctypes as C
 
     fem, la, K, torch = bfx.fem, bfx.la, bfx.lib, bfx.torch
-    p = P.tet_p1(16, numbering="first_touch")  # (2^k cubes per edge: whole-cube chunks, complete warp tables)
+    if case == "p1":
+        p = P.tet_p1(16, numbering="first_touch")  # (2^k cubes per edge: whole-cube chunks, complete warp tables)
+        kid, okid = K.K_POISSON_P1_TET_A, oracle.K_POISSON_P1_TET_A
+    else:
+        p = P.tet_p2(7)
+        kid, okid = K.K_POISSON_P2_TET_A, oracle.K_POISSON_P2_TET_A
     msh, V = make_space(bfx, p)
     bdofs = np.flatnonzero(p.dof_coords[:, 0] < 1e-12).astype(np.int32)
     bc = fem.DirichletBC(fem.Constant(0.0), bdofs, V)
-    a, sp, A = assemble_A(bfx, V, K.K_POISSON_P1_TET_A, constants=[2.0], bcs=[bc])
+    a, sp, A = assemble_A(bfx, V, kid, constants=[2.0], bcs=[bc])
     whole = A.data.clone()
-    pat, ref = P.oracle_assemble_matrix(oracle, p, oracle.K_POISSON_P1_TET_A, constants=np.array([2.0]),
+    pat, ref = P.oracle_assemble_matrix(oracle, p, okid, constants=np.array([2.0]),
                                         bc=(np.isin(np.arange(p.ndofs), bdofs)).astype(np.int8))
     check_matrix(A, pat, ref)
     integ = a.integral(fem.IntegralType.cell, 0)
