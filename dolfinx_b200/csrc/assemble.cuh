@@ -129,6 +129,7 @@ struct bfx_rowgather
   uint8_t* bg_zcb = nullptr;    // [tile][BG_NBCAP]: per-call Dirichlet mask of every block's column node
   uint8_t *bg_mask0 = nullptr, *bg_mask1 = nullptr; // per-call Dirichlet masks per node (bit k = component k)
   int64_t bg_n_nodes = 0;
+  uint32_t* bg_cmask = nullptr; // per-call column masks per plan cell (3 bits per local node)
   int64_t bg_ntiles = 0;
   int bg_max_cells = 0, bg_max_blocks = 0, bg_max_inc = 0; // over all tiles (sizes the kernel's shared memory)
   bool bg_ok = false;

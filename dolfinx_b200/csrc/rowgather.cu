@@ -107,41 +107,73 @@ __global__ void k_rg_sort(int32_t n_rows, const int64_t* __restrict__ tptr, uint
 }
 
 // ---- pre-pass: cell records ----------------------------------------------------------------------------
+// One thread per cell; the 80-byte records of a warp's 32 consecutive cells leave as five fully coalesced 512-byte
+// stores through a shared-memory transpose (the per-thread version wrote 16-byte pieces at an 80-byte stride).
+// cmask != NULL: the column Dirichlet masks of the cell's 8 nodes too (3 bits per local node, from the per-node mask
+// bytes) - a block's contributions all name its column node as (cell, j), so the block-gather kernel reads the block's
+// column mask from the record of its first contribution (no pass over cols, no scattered byte loads).
 __global__ void __launch_bounds__(128)
     k_rg_records(int64_t n, const int32_t* __restrict__ cells, const int32_t* __restrict__ x_dofmap,
                  const double* __restrict__ x, double* __restrict__ rec, int32_t* __restrict__ na_cells,
-                 unsigned long long* __restrict__ na_count)
+                 unsigned long long* __restrict__ na_count, const int32_t* __restrict__ dofmap,
+                 const uint8_t* __restrict__ node_mask, uint32_t* __restrict__ cmask)
 {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+  __shared__ double2 s_out[4][32 * 5];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t n_pad = (n + 31) & ~(int64_t)31; // (whole warps stay in the loop: the stores are cooperative)
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_pad; e += (int64_t)gridDim.x * blockDim.x)
   {
-    const int32_t cell = cells ? cells[e] : (int32_t)e;
-    int32_t xd[8];
-    load_ints<8>(x_dofmap + (int64_t)cell * 8, xd);
-    double xc[8][3];
-    gather_coords<8>(x, xd, xc);
-    // parallelepiped test (same criterion as the cell-parallel kernel)
-    double dev2 = 0.0, h2 = 0.0;
-#pragma unroll
-    for (int m = 0; m < 3; ++m)
+    if (e < n)
     {
-      const double e1 = xc[1][m] - xc[0][m], e2 = xc[2][m] - xc[0][m], e3 = xc[4][m] - xc[0][m];
-      const double d3 = xc[3][m] - xc[0][m] - e1 - e2, d5 = xc[5][m] - xc[0][m] - e1 - e3;
-      const double d6 = xc[6][m] - xc[0][m] - e2 - e3, d7 = xc[7][m] - xc[0][m] - e1 - e2 - e3;
-      dev2 += d3 * d3 + d5 * d5 + d6 * d6 + d7 * d7;
-      h2 += e1 * e1 + e2 * e2 + e3 * e3;
+      const int32_t cell = cells ? cells[e] : (int32_t)e;
+      int32_t xd[8];
+      load_ints<8>(x_dofmap + (int64_t)cell * 8, xd);
+      uint32_t cm = 0;
+      if (cmask)
+      {
+        int32_t d[8];
+        load_ints<8>(dofmap + (int64_t)cell * 8, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          cm |= (uint32_t)__ldg(node_mask + d[j]) << (3 * j);
+      }
+      double xc[8][3];
+      gather_coords<8>(x, xd, xc);
+      // parallelepiped test (same criterion as the cell-parallel kernel)
+      double dev2 = 0.0, h2 = 0.0;
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+      {
+        const double e1 = xc[1][m] - xc[0][m], e2 = xc[2][m] - xc[0][m], e3 = xc[4][m] - xc[0][m];
+        const double d3 = xc[3][m] - xc[0][m] - e1 - e2, d5 = xc[5][m] - xc[0][m] - e1 - e3;
+        const double d6 = xc[6][m] - xc[0][m] - e2 - e3, d7 = xc[7][m] - xc[0][m] - e1 - e2 - e3;
+        dev2 += d3 * d3 + d5 * d5 + d6 * d6 + d7 * d7;
+        h2 += e1 * e1 + e2 * e2 + e3 * e3;
+      }
+      const bool affine = dev2 <= 1e-26 * h2;
+      const double X[3] = {0.5, 0.5, 0.5};
+      double K[3][3];
+      const double det = el::HexQ1::jacobian_inverse(xc, X, K);
+      double2* out = s_out[wib] + lane * 5;
+      out[0] = make_double2(K[0][0], K[0][1]);
+      out[1] = make_double2(K[0][2], K[1][0]);
+      out[2] = make_double2(K[1][1], K[1][2]);
+      out[3] = make_double2(K[2][0], K[2][1]);
+      out[4] = make_double2(K[2][2], affine ? fabs(det) : -1.0);
+      if (cmask)
+        cmask[e] = cm;
+      if (!affine)
+        na_cells[atomicAdd(na_count, 1ULL)] = cell;
     }
-    const bool affine = dev2 <= 1e-26 * h2;
-    const double X[3] = {0.5, 0.5, 0.5};
-    double K[3][3];
-    const double det = el::HexQ1::jacobian_inverse(xc, X, K);
-    double2* out = reinterpret_cast<double2*>(rec + e * RG_STRIDE);
-    out[0] = make_double2(K[0][0], K[0][1]);
-    out[1] = make_double2(K[0][2], K[1][0]);
-    out[2] = make_double2(K[1][1], K[1][2]);
-    out[3] = make_double2(K[2][0], K[2][1]);
-    out[4] = make_double2(K[2][2], affine ? fabs(det) : -1.0);
-    if (!affine)
-      na_cells[atomicAdd(na_count, 1ULL)] = cell;
+    __syncwarp();
+    const int64_t e0 = e - lane;
+    const int cnt = (int)min((int64_t)32, n - e0) * 5;
+    double2* gout = reinterpret_cast<double2*>(rec + e0 * RG_STRIDE);
+#pragma unroll
+    for (int w = 0; w < 5; ++w)
+      if (w * 32 + lane < cnt)
+        gout[w * 32 + lane] = s_out[wib][w * 32 + lane];
+    __syncwarp();
   }
 }
 
@@ -646,6 +678,9 @@ struct BGArgs
   const int32_t* cols;  // CSR column (node) of every block
   const uint8_t* mask1; // per node: bit k set = component k of the COLUMN carries a Dirichlet condition (or NULL)
   int32_t n_mask_nodes;
+  // default since: the same masks per plan cell (written by k_rg_records), staged with the cell records; a block reads its
+  // column mask through the (cell slot, j) of its first contribution (or NULL)
+  const uint32_t* cmask;
   double mu, lmbda;
   double* values;
   int dbg; // profiling only: 1 = no contribution loop, 2 = no store
@@ -680,15 +715,21 @@ __global__ void k_bg_block_masks(int64_t ntiles, const BGTile* __restrict__ tile
 // cp.async (their addresses follow from the tile index: fixed strides), the header of the tile after that is on its
 // way, and the cell records of N (second level: they need N's cell ids) are requested after T's contribution loop.
 // One TMA bulk store per tile; two block-wide barriers per tile.
-__global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g)
+// CM: where the column Dirichlet masks come from - 0: none / per-block bytes of a per-call pass (g.zcb), 1: column index
+// -> node mask in the kernel (g.cols, g.mask1), 2: per-cell masks staged with the records (g.cmask; default)
+// NT: threads per CTA; PIPE: the record of contribution k + 1 is read from shared memory before the arithmetic of k
+template <int CM, int NT, int PIPE>
+__global__ void __launch_bounds__(NT, 4) k_q1_blockgather(const BGArgs g)
 {
+  const bool use_cmask = CM == 2, use_mask1 = CM == 1;
   extern __shared__ __align__(16) unsigned char bg_raw[];
   double* img_base = reinterpret_cast<double*>(bg_raw);
   BGTile* s_hdr = reinterpret_cast<BGTile*>(bg_raw + sizeof(double) * g.img_cap); // ring of 3
   unsigned char* stage0 = reinterpret_cast<unsigned char*>(s_hdr + 3);
   const size_t rec_bytes = (size_t)g.cell_cap * RG_STRIDE * 8, ent_bytes = (size_t)g.inc_cap * 16,
                perm_bytes = ((size_t)g.nb_cap * 2 + 15) & ~(size_t)15, zc_bytes = ((size_t)g.nb_cap + 15) & ~(size_t)15;
-  const size_t col_bytes = ((size_t)g.nb_cap * 4 + 15) & ~(size_t)15; // column node of every block of the tile
+  // column node of every block of the tile (mask1 scheme) or column masks of every cell of the tile (cmask scheme)
+  const size_t col_bytes = ((size_t)(use_cmask ? g.cell_cap : (use_mask1 ? g.nb_cap : 0)) * 4 + 15) & ~(size_t)15;
   const size_t stage_bytes = rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16 + col_bytes;
   const int tid = threadIdx.x;
   const int64_t G = gridDim.x;
@@ -703,26 +744,26 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
   {
     unsigned char* base = stage0 + (size_t)st * stage_bytes;
     const uint4* e4 = reinterpret_cast<const uint4*>(g.ent + tile * (8 * BG_INCCAP));
-    for (int k = tid; k < h.ninc; k += BG_THREADS)
+    for (int k = tid; k < h.ninc; k += NT)
       cp_async16(base + rec_bytes + 16 * (size_t)k, e4 + k);
     const uint4* p4 = reinterpret_cast<const uint4*>(g.perm + tile * BG_NBCAP);
-    for (int k = tid; k < (h.nb + 7) / 8; k += BG_THREADS)
+    for (int k = tid; k < (h.nb + 7) / 8; k += NT)
       cp_async16(base + rec_bytes + ent_bytes + 16 * (size_t)k, p4 + k);
-    if (g.zcb)
+    if (CM == 0 && g.zcb)
     {
       const uint4* z4 = reinterpret_cast<const uint4*>(g.zcb + tile * BG_NBCAP);
-      for (int k = tid; k < (h.nb + 15) / 16; k += BG_THREADS)
+      for (int k = tid; k < (h.nb + 15) / 16; k += NT)
         cp_async16(base + rec_bytes + ent_bytes + perm_bytes + 16 * (size_t)k, z4 + k);
     }
     if (g.mask0 && tid == 0)
       cp_async16(base + rec_bytes + ent_bytes + perm_bytes + zc_bytes, g.mask0 + tile * BG_ROWS);
     // (tried: a per-tile "no marked column node in [cmin, cmax]" test through a per-call prefix count, to skip the
     // lookups away from the boundary layer - its two loads sit on the critical path between tiles: 6.52 against 6.21 ms)
-    if (g.mask1) // the tile's blocks are consecutive CSR blocks: their columns are one contiguous run (4-byte copies:
+    if (use_mask1) // the tile's blocks are consecutive CSR blocks: their columns are one contiguous run (4-byte copies:
     {            // the run starts at an arbitrary block)
       const int32_t* cg = g.cols + h.b0;
       unsigned char* cs = base + rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16;
-      for (int k = tid; k < h.nb; k += BG_THREADS)
+      for (int k = tid; k < h.nb; k += NT)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(cs + 4 * (size_t)k)),
                      "l"(cg + k)
                      : "memory");
@@ -738,6 +779,13 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
 #pragma unroll
       for (int w = 0; w < 5; ++w)
         cp_async16(sp + w, rp + w);
+      if (use_cmask)
+      {
+        unsigned char* cs = stage0 + (size_t)st * stage_bytes + rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(cs + 4 * (size_t)tid)),
+                     "l"(g.cmask + cid)
+                     : "memory");
+      }
     }
   };
 
@@ -776,7 +824,9 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
     const uint8_t* s_zc = base + rec_bytes + ent_bytes + perm_bytes;
     const uint8_t* s_zr = s_zc + zc_bytes;
     const int32_t* s_col = reinterpret_cast<const int32_t*>(s_zr + 16);
-    const bool col_masks = g.mask1 != nullptr;
+    const bool col_masks = use_mask1;
+    const uint32_t* s_cm = reinterpret_cast<const uint32_t*>(s_zr + 16);
+    const int nlev0 = h.nlev[0];
     const int nb = h.nb;
     const int64_t b0 = h.b0;
     // smem element i of the image sits at the same offset modulo 16 bytes as global element b0 * 9 + i
@@ -785,7 +835,7 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
     const bool skip = nb == 0 || (!g.overwrite && h.ninc == 0); // (add mode: no cell of the plan touches the tile)
     if (!skip)
     {
-      for (int t = tid; t < nb; t += BG_THREADS)
+      for (int t = tid; t < nb; t += NT)
       {
         const uint32_t pmt = s_perm[t];
         const int bidx = (int)(pmt & 1023u), rowid = (int)(pmt >> 10);
@@ -795,8 +845,52 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
           const int32_t cnode = s_col[bidx];
           zc_direct = cnode < g.n_mask_nodes ? (unsigned)__ldg(g.mask1 + cnode) : 0u; // (ghost columns no cell touches)
         }
+        if (use_cmask && t < nlev0) // (a block without contributions is zero anyway)
+        {
+          const uint32_t e0 = s_ent[t];
+          zc_direct = (s_cm[e0 >> 6] >> (3u * (e0 & 7u))) & 7u;
+        }
         double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
         int off = 0;
+        if (PIPE)
+        {
+          bool have = t < nlev0 && g.dbg != 1;
+          uint32_t en = 0;
+          double2 q0, q1, q2, q3, q4;
+          q0 = q1 = q2 = q3 = q4 = make_double2(0.0, 0.0);
+          if (have)
+          {
+            en = s_ent[t];
+            off = nlev0;
+            const double2* sp = reinterpret_cast<const double2*>(s_rec + (en >> 6) * RG_STRIDE);
+            q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3], q4 = sp[4];
+          }
+#pragma unroll 1
+          for (int k = 1; have; ++k)
+          {
+            const int nk = k < BG_KMAX ? (int)h.nlev[k] : 0;
+            const bool have_n = t < nk;
+            uint32_t en_n = 0;
+            double2 n0 = q0, n1 = q1, n2 = q2, n3 = q3, n4 = q4;
+            if (have_n)
+            {
+              en_n = s_ent[off + t];
+              off += nk;
+              const double2* sp = reinterpret_cast<const double2*>(s_rec + (en_n >> 6) * RG_STRIDE);
+              n0 = sp[0], n1 = sp[1], n2 = sp[2], n3 = sp[3], n4 = sp[4];
+            }
+            if (q4.y >= 0.0)
+            {
+              const double K[3][3] = {{q0.x, q0.y, q1.x}, {q1.y, q2.x, q2.y}, {q3.x, q3.y, q4.x}};
+              q1_affine_D_add((int)((en >> 3) & 7u), (int)(en & 7u), K, q4.y, A);
+            }
+            q0 = n0, q1 = n1, q2 = n2, q3 = n3, q4 = n4;
+            en = en_n;
+            have = have_n;
+          }
+        }
+        else
+        {
 #pragma unroll 1
         for (int k = 0; k < BG_KMAX; ++k)
         {
@@ -813,7 +907,8 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
             q1_affine_D_add((int)((en >> 3) & 7u), (int)(en & 7u), K, q4.y, A);
           }
         }
-        const unsigned zr = g.mask0 ? s_zr[rowid] : 0u, zc = g.mask1 ? zc_direct : (g.zcb ? s_zc[bidx] : 0u);
+        }
+        const unsigned zr = g.mask0 ? s_zr[rowid] : 0u, zc = (use_mask1 || use_cmask) ? zc_direct : (g.zcb ? s_zc[bidx] : 0u);
         const double tr = A[0][0] + A[1][1] + A[2][2];
         double* o = img + bidx * 9;
 #pragma unroll
@@ -855,19 +950,19 @@ __global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g
     {
       __syncthreads();
       if (!skip)
-        for (int t0i = tid; t0i < total; t0i += 8 * BG_THREADS)
+        for (int t0i = tid; t0i < total; t0i += 8 * NT)
         {
           double old[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u)
           {
-            const int t = t0i + u * BG_THREADS;
+            const int t = t0i + u * NT;
             old[u] = t < total ? out[t] : 0.0;
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
           {
-            const int t = t0i + u * BG_THREADS;
+            const int t = t0i + u * NT;
             if (t < total)
               out[t] = old[u] + img[t];
           }
@@ -900,6 +995,7 @@ void free_rowgather(bfx_rowgather* g)
   cudaFree(g->bg_zcb);
   cudaFree(g->bg_mask0);
   cudaFree(g->bg_mask1);
+  cudaFree(g->bg_cmask);
   delete g;
 }
 
@@ -922,13 +1018,34 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
   const bool use_bg = G->bg_ok && !getenv("BFX_ROWGATHER_V1");
   if (ranged && !use_bg)
     return fail(BFX_ERR_UNSUPPORTED, "row-range assembly needs the block-gather plan");
-  // pre-pass: cell records + list of cells that are not parallelepipeds
+  // per-call Dirichlet masks per node (rows and columns share the node numbering: one dofmap)
+  const uint8_t *m0 = nullptr, *m1 = nullptr;
+  if (use_bg && a.bc0)
+  {
+    k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc0, G->bg_mask0);
+    m0 = G->bg_mask0;
+  }
+  if (use_bg && a.bc1)
+  {
+    m1 = G->bg_mask0;
+    if (a.bc1 != a.bc0)
+    {
+      k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc1, G->bg_mask1);
+      m1 = G->bg_mask1;
+    }
+  }
+  // where the kernel takes a block's column mask from: 2 = per-cell masks written by the records pre-pass (default),
+  // 1 = column index -> node mask in the kernel, 0 = one pass over all blocks per call (both kept for A/B runs)
+  const int col_scheme = !m1 ? -1 : (getenv("BFX_BG_BLOCK_MASKS") ? 0 : (getenv("BFX_BG_COL_LOOKUP") ? 1 : 2));
+  // pre-pass: cell records (+ column masks per cell) + list of cells that are not parallelepipeds.  reuse_records: the
+  // records AND the cell masks of the previous call are still valid (same geometry, same column markers)
   if (!reuse_records)
   {
     BFX_CUDA(cudaMemsetAsync(G->na_count, 0, sizeof(unsigned long long), st));
     if (P->ncells > 0)
       k_rg_records<<<grid_for(P->ncells, 128, 0), 128, 0, st>>>(P->ncells, P->cells, P->x_dofmap, a.x, G->rec, G->na_cells,
-                                                                 G->na_count);
+                                                                 G->na_count, a.dofmap1, m1,
+                                                                 col_scheme == 2 ? G->bg_cmask : nullptr);
   }
   if (use_bg) // block-gather kernel (default); the round-1 kernel stays for A/B runs
   {
@@ -939,35 +1056,22 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
     b.tiles = static_cast<const BGTile*>(G->bg_tiles);
     b.cells = G->bg_cells, b.perm = G->bg_perm, b.ent = G->bg_ent;
     b.rec = G->rec;
-    b.mask0 = nullptr;
+    b.mask0 = m0;
     b.zcb = nullptr;
-    if (a.bc0)
-    {
-      k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc0, G->bg_mask0);
-      b.mask0 = G->bg_mask0;
-    }
     b.cols = csr->cols;
     b.mask1 = nullptr;
+    b.cmask = nullptr;
     b.n_mask_nodes = (int32_t)G->bg_n_nodes;
-    if (a.bc1)
+    if (col_scheme == 0)
     {
-      const uint8_t* m1 = G->bg_mask0;
-      if (a.bc1 != a.bc0)
-      {
-        k_bg_node_masks<<<grid_for(G->bg_n_nodes, 256, 8), 256, 0, st>>>(G->bg_n_nodes, a.bc1, G->bg_mask1);
-        m1 = G->bg_mask1;
-      }
-      if (getenv("BFX_BG_BLOCK_MASKS")) // round-1 scheme, kept for A/B runs: one pass over all blocks per call
-      {
-        k_bg_block_masks<<<grid_for(G->bg_ntiles * BG_NBCAP, 256, 16), 256, 0, st>>>(G->bg_ntiles, static_cast<const BGTile*>(G->bg_tiles), csr->cols, m1,
-                                                                                  (int32_t)G->bg_n_nodes, G->bg_zcb);
-        b.zcb = G->bg_zcb;
-      }
-      else
-      {
-        b.mask1 = m1;
-      }
+      k_bg_block_masks<<<grid_for(G->bg_ntiles * BG_NBCAP, 256, 16), 256, 0, st>>>(G->bg_ntiles, static_cast<const BGTile*>(G->bg_tiles), csr->cols, m1,
+                                                                                (int32_t)G->bg_n_nodes, G->bg_zcb);
+      b.zcb = G->bg_zcb;
     }
+    else if (col_scheme == 1)
+      b.mask1 = m1;
+    else if (col_scheme == 2)
+      b.cmask = G->bg_cmask;
     b.mu = a.constants[0], b.lmbda = a.constants[1];
     b.values = a.values;
     b.overwrite = values_mode == BFX_VALUES_OVERWRITE;
@@ -977,15 +1081,27 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
     b.inc_cap = G->bg_max_inc;
     b.nb_cap = G->bg_max_blocks;
     const size_t stage = (size_t)b.cell_cap * RG_STRIDE * 8 + (size_t)b.inc_cap * 16 + (((size_t)b.nb_cap * 2 + 15) & ~(size_t)15)
-                         + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16 + (((size_t)b.nb_cap * 4 + 15) & ~(size_t)15);
+                         + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16
+                         + (((size_t)(b.cmask ? b.cell_cap : (b.mask1 ? b.nb_cap : 0)) * 4 + 15) & ~(size_t)15);
     const size_t smem = sizeof(double) * (size_t)b.img_cap + 3 * sizeof(BGTile) + 2 * stage;
     if (b.tile_end > b.tile_begin)
     {
-      BFX_CUDA(cudaFuncSetAttribute(k_q1_blockgather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // profiling switches (default: 128 threads, no software pipelining): BFX_BG_THREADS=192|256, BFX_BG_PIPE=1
+      const int nt = getenv("BFX_BG_THREADS") ? atoi(getenv("BFX_BG_THREADS")) : BG_THREADS;
+      const bool pipe = getenv("BFX_BG_PIPE") != nullptr;
+      void (*kern)(const BGArgs) = b.cmask ? k_q1_blockgather<2, 128, 0> : (b.mask1 ? k_q1_blockgather<1, 128, 0> : k_q1_blockgather<0, 128, 0>);
+      int threads = BG_THREADS;
+      if (b.cmask && nt == 192)
+        kern = pipe ? k_q1_blockgather<2, 192, 1> : k_q1_blockgather<2, 192, 0>, threads = 192;
+      else if (b.cmask && nt == 256)
+        kern = pipe ? k_q1_blockgather<2, 256, 1> : k_q1_blockgather<2, 256, 0>, threads = 256;
+      else if (b.cmask && pipe)
+        kern = k_q1_blockgather<2, 128, 1>;
+      BFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
-      BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_q1_blockgather, BG_THREADS, smem));
+      BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
       const int64_t grid = std::min<int64_t>(b.tile_end - b.tile_begin, (int64_t)sm_count() * std::max(per_sm, 1));
-      k_q1_blockgather<<<(unsigned)grid, BG_THREADS, smem, st>>>(b);
+      kern<<<(unsigned)grid, threads, smem, st>>>(b);
     }
     BFX_CHECK_LAUNCH();
     AsmArgs nb = a;
@@ -1142,7 +1258,8 @@ int bfx_asm_build_rowgather(bfx_asm_t* P, bfx_stream_t stream)
     cudaFree(d_max);
     // per-call scratch of the Dirichlet node masks (rows and columns share the node numbering: one dofmap)
     G->bg_n_nodes = n_rows;
-    if ((e = dev_alloc(&G->bg_mask0, (size_t)n_rows + 2 * BG_ROWS)) || (e = dev_alloc(&G->bg_mask1, (size_t)n_rows + 2 * BG_ROWS)))
+    if ((e = dev_alloc(&G->bg_mask0, (size_t)n_rows + 2 * BG_ROWS)) || (e = dev_alloc(&G->bg_mask1, (size_t)n_rows + 2 * BG_ROWS))
+        || (e = dev_alloc(&G->bg_cmask, (size_t)n + 1)))
       return bail(e);
     G->bg_ntiles = ntiles;
     G->bg_max_cells = h_max[0];
