@@ -131,7 +131,7 @@ struct bfx_rowgather
   int64_t bg_n_nodes = 0;
   uint32_t* bg_cmask = nullptr; // per-call column masks per plan cell (3 bits per local node)
   int64_t bg_ntiles = 0;
-  int bg_max_cells = 0, bg_max_blocks = 0, bg_max_inc = 0; // over all tiles (sizes the kernel's shared memory)
+  int bg_max_cells = 0, bg_max_blocks = 0, bg_max_steps = 0, bg_max_q = 0; // over all tiles (sizes the kernel's shared memory)
   bool bg_ok = false;
 };
 

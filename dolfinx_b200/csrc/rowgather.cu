@@ -435,15 +435,21 @@ constexpr int BG_NBCAP = 512;   // blocks per tile the plan accepts (rank and bl
 constexpr int BG_CCAP = 128;    // distinct cells per tile
 constexpr int BG_KMAX = 16;     // contributions per block
 constexpr int BG_INCCAP = 256;  // (row, cell) incidences per tile
+constexpr int BG_SCAP = 16;     // contribution steps per thread (step lists: [tile][BG_SCAP][BG_THREADS])
+constexpr int BG_QCAP = 8;      // blocks per thread (block lists: [tile][BG_QCAP][BG_THREADS])
+// step-list entry (16 bits): j | i << 3 | cell slot << 6 | BG_LAST (the block's last contribution: finish and write
+// it) | BG_EMPTY (a block no cell of the plan touches: write zeros); BG_IDLE = no further step for this thread
+constexpr uint32_t BG_LAST = 0x2000u, BG_EMPTY = 0x4000u, BG_IDLE = 0xFFFFu;
 
 // per-tile header of the block-gather plan (64 bytes)
 struct BGTile
 {
   int64_t b0;             // first block of the tile (row_ptr[r0])
   int32_t nb, ninc, nuc;  // blocks, (row, cell) incidences, distinct cells
-  int32_t pad;
+  int32_t nsteps;         // longest step list of a thread
   uint16_t nlev[BG_KMAX]; // blocks with more than k contributions
-  int32_t pad2[2];
+  int32_t nq;             // longest block list of a thread
+  int32_t pad2;
 };
 static_assert(sizeof(BGTile) == 64, "tile header layout");
 
@@ -456,11 +462,11 @@ struct BGPlanArgs
   const char* pos;
   int pos_bytes, pos_stride;
   int32_t* cells;  // [tile][BG_CCAP]
-  uint16_t* perm;  // [tile][BG_NBCAP]
-  uint16_t* ent;   // [tile][8 BG_INCCAP], level-major
+  uint16_t* perm;  // [tile][BG_QCAP][BG_THREADS]: q-th block of thread t (block index in tile | row in tile << 10)
+  uint16_t* ent;   // [tile][BG_SCAP][BG_THREADS]: s-th contribution step of thread t
   BGTile* tiles;
   int* err;     // 1: tile over a capacity
-  int* maxima;  // [0] cells per tile, [1] blocks per tile, [2] (row, cell) incidences per tile
+  int* maxima;  // [0] cells per tile, [1] blocks per tile, [2] steps per thread, [3] blocks per thread
 };
 
 __global__ void __launch_bounds__(BG_THREADS) k_bg_plan(const BGPlanArgs g)
@@ -472,6 +478,10 @@ __global__ void __launch_bounds__(BG_THREADS) k_bg_plan(const BGPlanArgs g)
   __shared__ uint16_t s_ent[BG_NBCAP][BG_KMAX];
   __shared__ uint16_t s_rank[BG_NBCAP];
   __shared__ int s_hist[BG_KMAX + 2], s_start[BG_KMAX + 2], s_wsum[BG_THREADS / 32], s_nuc, s_bad;
+  __shared__ uint16_t s_byrank[BG_NBCAP];
+  __shared__ uint8_t s_owner[BG_NBCAP], s_q[BG_NBCAP], s_s0[BG_NBCAP];
+  __shared__ int s_sum[BG_THREADS], s_nblk[BG_THREADS], s_S, s_Q;
+  __shared__ uint16_t s_steps[BG_SCAP * BG_THREADS], s_blocks[BG_QCAP * BG_THREADS];
   const int tid = threadIdx.x;
   const int64_t tile = blockIdx.x;
   const int32_t r0 = (int32_t)(tile * BG_ROWS), r1 = min(r0 + BG_ROWS, g.n_rows);
@@ -618,12 +628,79 @@ __global__ void __launch_bounds__(BG_THREADS) k_bg_plan(const BGPlanArgs g)
       __syncthreads();
     }
   }
+  // ---- blocks -> threads: every thread of the kernel owns whole blocks (accumulators in registers) and should run the
+  // same number of contribution steps - on a structured mesh a tile has 16 x 8 x 8 = 1024 steps in blocks of 8, 4, 2
+  // and 1, i.e. exactly 8 per thread.  Longest-processing-time rule over the ranked blocks: the next block goes to the
+  // thread with the fewest steps so far (ties: lowest thread, which keeps similar lists in one warp); one warp decides.
+  for (int b = tid; b < nb; b += BG_THREADS)
+    s_byrank[s_rank[b]] = (uint16_t)b;
+  s_sum[tid] = 0;
+  s_nblk[tid] = 0;
+  if (tid == 0)
+  {
+    s_S = 0;
+    s_Q = 0;
+  }
+  for (int k = tid; k < BG_SCAP * BG_THREADS; k += BG_THREADS)
+    s_steps[k] = (uint16_t)BG_IDLE;
+  for (int k = tid; k < BG_QCAP * BG_THREADS; k += BG_THREADS)
+    s_blocks[k] = 0;
+  __syncthreads();
+  if (tid < 32)
+  {
+    for (int r = 0; r < nb; ++r)
+    {
+      const int b = s_byrank[r];
+      const int c = max((int)s_cnt[b], 1); // (a block without contributions still takes one step: it is written)
+      int best = 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < BG_THREADS / 32; ++u)
+      {
+        const int t = tid + 32 * u;
+        best = min(best, s_sum[t] * BG_THREADS + t);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1)
+        best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (tid == 0)
+      {
+        const int t = best % BG_THREADS;
+        s_owner[b] = (uint8_t)t;
+        s_s0[b] = (uint8_t)min(s_sum[t], 255);
+        s_q[b] = (uint8_t)min(s_nblk[t], 255);
+        s_sum[t] += c;
+        s_nblk[t] += 1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  atomicMax(&s_S, s_sum[tid]);
+  atomicMax(&s_Q, s_nblk[tid]);
+  __syncthreads();
+  const int S = s_S, Q = s_Q;
+  if (S > BG_SCAP || Q > BG_QCAP)
+  {
+    if (tid == 0)
+      *g.err = 1;
+    return;
+  }
+  for (int b = tid; b < nb; b += BG_THREADS)
+  {
+    const int t = s_owner[b], cnt = s_cnt[b], s0 = s_s0[b];
+    s_blocks[(int)s_q[b] * BG_THREADS + t] = (uint16_t)(b | ((int)s_row[b] << 10));
+    for (int k = 0; k < cnt; ++k) // cells in ascending entity order: the summation order of a block is fixed
+      s_steps[(s0 + k) * BG_THREADS + t] = (uint16_t)(s_ent[b][k] | (k == cnt - 1 ? BG_LAST : 0u));
+    if (cnt == 0)
+      s_steps[s0 * BG_THREADS + t] = (uint16_t)(BG_LAST | BG_EMPTY);
+  }
+  __syncthreads();
   // ---- output (fixed strides per tile: every address of the kernel's prologue follows from the tile index)
   if (tid == 0)
   {
     BGTile h;
     h.b0 = b0;
-    h.nb = nb, h.ninc = ninc, h.nuc = nuc, h.pad = 0, h.pad2[0] = h.pad2[1] = 0;
+    h.nb = nb, h.ninc = ninc, h.nuc = nuc, h.nsteps = S, h.nq = Q, h.pad2 = 0;
     for (int k = 0; k < BG_KMAX; ++k)
     {
       int nk = 0; // blocks with more than k contributions
@@ -634,24 +711,15 @@ __global__ void __launch_bounds__(BG_THREADS) k_bg_plan(const BGPlanArgs g)
     g.tiles[tile] = h;
     atomicMax(g.maxima, nuc);
     atomicMax(g.maxima + 1, nb);
-    atomicMax(g.maxima + 2, ninc);
+    atomicMax(g.maxima + 2, S);
+    atomicMax(g.maxima + 3, Q);
   }
   for (int k = tid; k < nuc; k += BG_THREADS)
     g.cells[tile * BG_CCAP + k] = s_ucell[k];
-  for (int b = tid; b < nb; b += BG_THREADS)
-  {
-    const int rk = s_rank[b], cnt = s_cnt[b];
-    g.perm[tile * BG_NBCAP + rk] = (uint16_t)(b | ((int)s_row[b] << 10));
-    int off = 0;
-    for (int k = 0; k < cnt; ++k)
-    {
-      g.ent[tile * (8 * BG_INCCAP) + off + rk] = s_ent[b][k];
-      int nk = 0;
-      for (int c = k + 1; c <= BG_KMAX; ++c)
-        nk += s_hist[c];
-      off += nk;
-    }
-  }
+  for (int k = tid; k < S * BG_THREADS; k += BG_THREADS)
+    g.ent[tile * (BG_SCAP * BG_THREADS) + k] = s_steps[k];
+  for (int k = tid; k < Q * BG_THREADS; k += BG_THREADS)
+    g.perm[tile * (BG_QCAP * BG_THREADS) + k] = s_blocks[k];
 }
 
 // int8 markers of a block-size-3 space -> one byte per node (bit k = component k)
@@ -685,7 +753,8 @@ struct BGArgs
   double* values;
   int dbg; // profiling only: 1 = no contribution loop, 2 = no store
   int overwrite;
-  int img_cap, cell_cap, inc_cap, nb_cap; // shared-memory layout: image doubles; per stage: cells, incidences, blocks
+  int img_cap, cell_cap, step_cap, q_cap, nb_cap; // shared-memory layout: image doubles; per stage: cells, steps and
+                                                  // blocks per thread, blocks
 };
 
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc)
@@ -717,17 +786,21 @@ __global__ void k_bg_block_masks(int64_t ntiles, const BGTile* __restrict__ tile
 // One TMA bulk store per tile; two block-wide barriers per tile.
 // CM: where the column Dirichlet masks come from - 0: none / per-block bytes of a per-call pass (g.zcb), 1: column index
 // -> node mask in the kernel (g.cols, g.mask1), 2: per-cell masks staged with the records (g.cmask; default)
-// NT: threads per CTA; PIPE: the record of contribution k + 1 is read from shared memory before the arithmetic of k
-template <int CM, int NT, int PIPE>
-__global__ void __launch_bounds__(NT, 4) k_q1_blockgather(const BGArgs g)
+// Every thread walks its own list of contribution steps (k_bg_plan balances them: 8 per thread on a structured mesh);
+// a step flagged BG_LAST finishes its block: mu (tr D I + D^T) + lambda D, Dirichlet masks, 9 values into the image.
+// (The first version ranked the blocks by list length and gave thread t the blocks t, t + 128, ...: warp 0 ran 13
+// steps per tile and warps 2, 3 seven - 2.2 warps per issue slot parked at the tile barrier, r02_prof_q1_..._v3.csv.)
+template <int CM>
+__global__ void __launch_bounds__(BG_THREADS, 4) k_q1_blockgather(const BGArgs g)
 {
+  constexpr int NT = BG_THREADS;
   const bool use_cmask = CM == 2, use_mask1 = CM == 1;
   extern __shared__ __align__(16) unsigned char bg_raw[];
   double* img_base = reinterpret_cast<double*>(bg_raw);
   BGTile* s_hdr = reinterpret_cast<BGTile*>(bg_raw + sizeof(double) * g.img_cap); // ring of 3
   unsigned char* stage0 = reinterpret_cast<unsigned char*>(s_hdr + 3);
-  const size_t rec_bytes = (size_t)g.cell_cap * RG_STRIDE * 8, ent_bytes = (size_t)g.inc_cap * 16,
-               perm_bytes = ((size_t)g.nb_cap * 2 + 15) & ~(size_t)15, zc_bytes = ((size_t)g.nb_cap + 15) & ~(size_t)15;
+  const size_t rec_bytes = (size_t)g.cell_cap * RG_STRIDE * 8, ent_bytes = (size_t)g.step_cap * NT * 2,
+               perm_bytes = (size_t)g.q_cap * NT * 2, zc_bytes = ((size_t)g.nb_cap + 15) & ~(size_t)15;
   // column node of every block of the tile (mask1 scheme) or column masks of every cell of the tile (cmask scheme)
   const size_t col_bytes = ((size_t)(use_cmask ? g.cell_cap : (use_mask1 ? g.nb_cap : 0)) * 4 + 15) & ~(size_t)15;
   const size_t stage_bytes = rec_bytes + ent_bytes + perm_bytes + zc_bytes + 16 + col_bytes;
@@ -743,11 +816,11 @@ __global__ void __launch_bounds__(NT, 4) k_q1_blockgather(const BGArgs g)
   auto fetch_lists = [&](int64_t tile, const BGTile& h, int st) -> int32_t
   {
     unsigned char* base = stage0 + (size_t)st * stage_bytes;
-    const uint4* e4 = reinterpret_cast<const uint4*>(g.ent + tile * (8 * BG_INCCAP));
-    for (int k = tid; k < h.ninc; k += NT)
+    const uint4* e4 = reinterpret_cast<const uint4*>(g.ent + tile * (BG_SCAP * NT));
+    for (int k = tid; k < h.nsteps * (NT / 8); k += NT)
       cp_async16(base + rec_bytes + 16 * (size_t)k, e4 + k);
-    const uint4* p4 = reinterpret_cast<const uint4*>(g.perm + tile * BG_NBCAP);
-    for (int k = tid; k < (h.nb + 7) / 8; k += NT)
+    const uint4* p4 = reinterpret_cast<const uint4*>(g.perm + tile * (BG_QCAP * NT));
+    for (int k = tid; k < h.nq * (NT / 8); k += NT)
       cp_async16(base + rec_bytes + ent_bytes + 16 * (size_t)k, p4 + k);
     if (CM == 0 && g.zcb)
     {
@@ -824,9 +897,7 @@ __global__ void __launch_bounds__(NT, 4) k_q1_blockgather(const BGArgs g)
     const uint8_t* s_zc = base + rec_bytes + ent_bytes + perm_bytes;
     const uint8_t* s_zr = s_zc + zc_bytes;
     const int32_t* s_col = reinterpret_cast<const int32_t*>(s_zr + 16);
-    const bool col_masks = use_mask1;
     const uint32_t* s_cm = reinterpret_cast<const uint32_t*>(s_zr + 16);
-    const int nlev0 = h.nlev[0];
     const int nb = h.nb;
     const int64_t b0 = h.b0;
     // smem element i of the image sits at the same offset modulo 16 bytes as global element b0 * 9 + i
@@ -835,90 +906,58 @@ __global__ void __launch_bounds__(NT, 4) k_q1_blockgather(const BGArgs g)
     const bool skip = nb == 0 || (!g.overwrite && h.ninc == 0); // (add mode: no cell of the plan touches the tile)
     if (!skip)
     {
-      for (int t = tid; t < nb; t += NT)
+      const int nsteps = h.nsteps;
+      double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      int q = 0;
+#pragma unroll 1
+      for (int sidx = 0; sidx < nsteps; ++sidx)
       {
-        const uint32_t pmt = s_perm[t];
-        const int bidx = (int)(pmt & 1023u), rowid = (int)(pmt >> 10);
-        unsigned zc_direct = 0u;
-        if (col_masks)
+        const uint32_t en = s_ent[sidx * NT + tid];
+        if (en == BG_IDLE)
+          break;
+        const int slot = (int)((en >> 6) & 127u), jn = (int)(en & 7u);
+        if (!(en & BG_EMPTY) && g.dbg != 1)
         {
-          const int32_t cnode = s_col[bidx];
-          zc_direct = cnode < g.n_mask_nodes ? (unsigned)__ldg(g.mask1 + cnode) : 0u; // (ghost columns no cell touches)
-        }
-        if (use_cmask && t < nlev0) // (a block without contributions is zero anyway)
-        {
-          const uint32_t e0 = s_ent[t];
-          zc_direct = (s_cm[e0 >> 6] >> (3u * (e0 & 7u))) & 7u;
-        }
-        double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        int off = 0;
-        if (PIPE)
-        {
-          bool have = t < nlev0 && g.dbg != 1;
-          uint32_t en = 0;
-          double2 q0, q1, q2, q3, q4;
-          q0 = q1 = q2 = q3 = q4 = make_double2(0.0, 0.0);
-          if (have)
-          {
-            en = s_ent[t];
-            off = nlev0;
-            const double2* sp = reinterpret_cast<const double2*>(s_rec + (en >> 6) * RG_STRIDE);
-            q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3], q4 = sp[4];
-          }
-#pragma unroll 1
-          for (int k = 1; have; ++k)
-          {
-            const int nk = k < BG_KMAX ? (int)h.nlev[k] : 0;
-            const bool have_n = t < nk;
-            uint32_t en_n = 0;
-            double2 n0 = q0, n1 = q1, n2 = q2, n3 = q3, n4 = q4;
-            if (have_n)
-            {
-              en_n = s_ent[off + t];
-              off += nk;
-              const double2* sp = reinterpret_cast<const double2*>(s_rec + (en_n >> 6) * RG_STRIDE);
-              n0 = sp[0], n1 = sp[1], n2 = sp[2], n3 = sp[3], n4 = sp[4];
-            }
-            if (q4.y >= 0.0)
-            {
-              const double K[3][3] = {{q0.x, q0.y, q1.x}, {q1.y, q2.x, q2.y}, {q3.x, q3.y, q4.x}};
-              q1_affine_D_add((int)((en >> 3) & 7u), (int)(en & 7u), K, q4.y, A);
-            }
-            q0 = n0, q1 = n1, q2 = n2, q3 = n3, q4 = n4;
-            en = en_n;
-            have = have_n;
-          }
-        }
-        else
-        {
-#pragma unroll 1
-        for (int k = 0; k < BG_KMAX; ++k)
-        {
-          const int nk = h.nlev[k];
-          if (t >= nk || g.dbg == 1)
-            break;
-          const uint32_t en = s_ent[off + t];
-          off += nk;
-          const double2* sp = reinterpret_cast<const double2*>(s_rec + (en >> 6) * RG_STRIDE);
+          const double2* sp = reinterpret_cast<const double2*>(s_rec + slot * RG_STRIDE);
           const double2 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3], q4 = sp[4];
           if (q4.y >= 0.0)
           {
             const double K[3][3] = {{q0.x, q0.y, q1.x}, {q1.y, q2.x, q2.y}, {q3.x, q3.y, q4.x}};
-            q1_affine_D_add((int)((en >> 3) & 7u), (int)(en & 7u), K, q4.y, A);
+            q1_affine_D_add((int)((en >> 3) & 7u), jn, K, q4.y, A);
           }
         }
-        }
-        const unsigned zr = g.mask0 ? s_zr[rowid] : 0u, zc = (use_mask1 || use_cmask) ? zc_direct : (g.zcb ? s_zc[bidx] : 0u);
-        const double tr = A[0][0] + A[1][1] + A[2][2];
-        double* o = img + bidx * 9;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-          for (int l = 0; l < 3; ++l)
+        if (en & BG_LAST)
+        {
+          const uint32_t pmt = s_perm[q * NT + tid];
+          ++q;
+          const int bidx = (int)(pmt & 1023u), rowid = (int)(pmt >> 10);
+          unsigned zc = 0u;
+          if (use_cmask) // every contribution of a block names its column node as (cell, j): this one will do
+            zc = (en & BG_EMPTY) ? 0u : ((s_cm[slot] >> (3 * jn)) & 7u);
+          else if (use_mask1)
           {
-            const double v = g.mu * ((k == l ? tr : 0.0) + A[l][k]) + g.lmbda * A[k][l];
-            o[3 * k + l] = (((zr >> k) | (zc >> l)) & 1u) ? 0.0 : v;
+            const int32_t cnode = s_col[bidx];
+            zc = cnode < g.n_mask_nodes ? (unsigned)__ldg(g.mask1 + cnode) : 0u; // (ghost columns no cell touches)
           }
+          else if (g.zcb)
+            zc = s_zc[bidx];
+          const unsigned zr = g.mask0 ? s_zr[rowid] : 0u;
+          const double tr = A[0][0] + A[1][1] + A[2][2];
+          double* o = img + bidx * 9;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+            {
+              const double v = g.mu * ((k == l ? tr : 0.0) + A[l][k]) + g.lmbda * A[k][l];
+              o[3 * k + l] = (((zr >> k) | (zc >> l)) & 1u) ? 0.0 : v;
+            }
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+              A[k][l] = 0.0;
+        }
       }
     }
     // ---- next tile: cell records (second level; the ids were requested before the contribution loop)
@@ -1036,7 +1075,7 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
   }
   // where the kernel takes a block's column mask from: 2 = per-cell masks written by the records pre-pass (default),
   // 1 = column index -> node mask in the kernel, 0 = one pass over all blocks per call (both kept for A/B runs)
-  const int col_scheme = !m1 ? -1 : (getenv("BFX_BG_BLOCK_MASKS") ? 0 : (getenv("BFX_BG_COL_LOOKUP") ? 1 : 2));
+  const int col_scheme = !m1 ? -1 : ((getenv("BFX_BG_BLOCK_MASKS") && G->bg_zcb) ? 0 : (getenv("BFX_BG_COL_LOOKUP") ? 1 : 2));
   // pre-pass: cell records (+ column masks per cell) + list of cells that are not parallelepipeds.  reuse_records: the
   // records AND the cell masks of the previous call are still valid (same geometry, same column markers)
   if (!reuse_records)
@@ -1078,25 +1117,17 @@ int launch_rowgather_q1(const bfx_asm* P, const AsmArgs& a, int values_mode, cud
     b.dbg = getenv("BFX_BG_DBG") ? atoi(getenv("BFX_BG_DBG")) : 0;
     b.img_cap = (G->bg_max_blocks * 9 + 3) & ~1;
     b.cell_cap = G->bg_max_cells;
-    b.inc_cap = G->bg_max_inc;
+    b.step_cap = G->bg_max_steps;
+    b.q_cap = G->bg_max_q;
     b.nb_cap = G->bg_max_blocks;
-    const size_t stage = (size_t)b.cell_cap * RG_STRIDE * 8 + (size_t)b.inc_cap * 16 + (((size_t)b.nb_cap * 2 + 15) & ~(size_t)15)
+    const size_t stage = (size_t)b.cell_cap * RG_STRIDE * 8 + (size_t)b.step_cap * BG_THREADS * 2 + (size_t)b.q_cap * BG_THREADS * 2
                          + (((size_t)b.nb_cap + 15) & ~(size_t)15) + 16
                          + (((size_t)(b.cmask ? b.cell_cap : (b.mask1 ? b.nb_cap : 0)) * 4 + 15) & ~(size_t)15);
     const size_t smem = sizeof(double) * (size_t)b.img_cap + 3 * sizeof(BGTile) + 2 * stage;
     if (b.tile_end > b.tile_begin)
     {
-      // profiling switches (default: 128 threads, no software pipelining): BFX_BG_THREADS=192|256, BFX_BG_PIPE=1
-      const int nt = getenv("BFX_BG_THREADS") ? atoi(getenv("BFX_BG_THREADS")) : BG_THREADS;
-      const bool pipe = getenv("BFX_BG_PIPE") != nullptr;
-      void (*kern)(const BGArgs) = b.cmask ? k_q1_blockgather<2, 128, 0> : (b.mask1 ? k_q1_blockgather<1, 128, 0> : k_q1_blockgather<0, 128, 0>);
-      int threads = BG_THREADS;
-      if (b.cmask && nt == 192)
-        kern = pipe ? k_q1_blockgather<2, 192, 1> : k_q1_blockgather<2, 192, 0>, threads = 192;
-      else if (b.cmask && nt == 256)
-        kern = pipe ? k_q1_blockgather<2, 256, 1> : k_q1_blockgather<2, 256, 0>, threads = 256;
-      else if (b.cmask && pipe)
-        kern = k_q1_blockgather<2, 128, 1>;
+      void (*kern)(const BGArgs) = b.cmask ? k_q1_blockgather<2> : (b.mask1 ? k_q1_blockgather<1> : k_q1_blockgather<0>);
+      const int threads = BG_THREADS;
       BFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
       BFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -1232,11 +1263,13 @@ int bfx_asm_build_rowgather(bfx_asm_t* P, bfx_stream_t stream)
     const int64_t ntiles = ((int64_t)n_rows + BG_ROWS - 1) / BG_ROWS;
     int *d_err = nullptr, *d_max = nullptr;
     if ((e = dev_alloc(&G->bg_cells, (size_t)ntiles * BG_CCAP)) || (e = dev_alloc(reinterpret_cast<BGTile**>(&G->bg_tiles), (size_t)ntiles))
-        || (e = dev_alloc(&G->bg_perm, (size_t)ntiles * BG_NBCAP)) || (e = dev_alloc(&G->bg_ent, (size_t)ntiles * 8 * BG_INCCAP))
-        || (e = dev_alloc(&G->bg_zcb, (size_t)ntiles * BG_NBCAP)) || (e = dev_alloc(&d_err, 1)) || (e = dev_alloc(&d_max, 3)))
+        || (e = dev_alloc(&G->bg_perm, (size_t)ntiles * BG_QCAP * BG_THREADS))
+        || (e = dev_alloc(&G->bg_ent, (size_t)ntiles * BG_SCAP * BG_THREADS)) || (e = dev_alloc(&d_err, 1)) || (e = dev_alloc(&d_max, 4)))
+      return bail(e);
+    if (getenv("BFX_BG_BLOCK_MASKS") && (e = dev_alloc(&G->bg_zcb, (size_t)ntiles * BG_NBCAP))) // (A/B scheme only)
       return bail(e);
     BFX_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-    BFX_CUDA(cudaMemsetAsync(d_max, 0, 3 * sizeof(int), st));
+    BFX_CUDA(cudaMemsetAsync(d_max, 0, 4 * sizeof(int), st));
     BGPlanArgs b;
     b.n_rows = n_rows;
     b.row_ptr = csr->row_ptr;
@@ -1250,7 +1283,7 @@ int bfx_asm_build_rowgather(bfx_asm_t* P, bfx_stream_t stream)
     b.maxima = d_max;
     k_bg_plan<<<(unsigned)ntiles, BG_THREADS, 0, st>>>(b);
     BFX_CHECK_LAUNCH();
-    int h_err = 0, h_max[3] = {0, 0, 0};
+    int h_err = 0, h_max[4] = {0, 0, 0, 0};
     BFX_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     BFX_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
     BFX_CUDA(cudaStreamSynchronize(st));
@@ -1264,7 +1297,8 @@ int bfx_asm_build_rowgather(bfx_asm_t* P, bfx_stream_t stream)
     G->bg_ntiles = ntiles;
     G->bg_max_cells = h_max[0];
     G->bg_max_blocks = h_max[1];
-    G->bg_max_inc = h_max[2];
+    G->bg_max_steps = h_max[2];
+    G->bg_max_q = h_max[3];
     G->bg_ok = h_err == 0;
   }
   P->rowgather = G;
