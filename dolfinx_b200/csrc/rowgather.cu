@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_q1_rowgather(const RGArgs g)
 // D_ij recomputed by a lane that shares its row with 7 others behind __syncwarp.  Here ONE THREAD OWNS ONE CSR BLOCK:
 // its 9 accumulators live in registers, it walks the precomputed list of the block's (cell, i, j) contributions (1, 2,
 // 4 or 8 on a structured mesh), reads the cell record (K, |det J|) from the tile's shared-memory copy and applies
-// mu (tr D I + D^T) + lambda D once.  Blocks are ranked by list length at plan time, so the lanes of a warp run the
-// same number of steps.  The finished blocks are written into a shared-memory image of the tile's contiguous value
+// mu (tr D I + D^T) + lambda D once.  Whole blocks are dealt to the threads at plan time so that every thread of a tile
+// runs the same number of contribution steps (k_bg_plan, longest-processing-time rule).  The finished blocks are written into a shared-memory image of the tile's contiguous value
 // range, which leaves the SM as ONE TMA bulk store (cp.async.bulk.global.shared::cta) - no store instructions, no
 // atomics, every value written once, bitwise reproducible.
 // =====================================================================================================
