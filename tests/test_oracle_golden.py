@@ -268,6 +268,37 @@ def test_restatement_vs_reference_matrix_csr_impl(oracle, bs):
                           x.ctypes.data_as(C.c_void_p), xr.ctypes.data_as(C.c_void_p), 1, xc.ctypes.data_as(C.c_void_p), 1, 1) == -1
 
 
+GOLDEN_NPZ = os.path.join(os.path.dirname(__file__), "golden", "ref_csr_vectors.npz")
+
+
+@pytest.mark.parametrize("bs", [(1, 1), (2, 2), (3, 3), (2, 3)])
+def test_oracle_vs_committed_reference_vectors(oracle, bs):
+    """The oracle against outputs of the REFERENCE's la/matrix_csr_impl.h (insert_csr :67-109, insert_blocked_csr
+    :112-156, insert_nonblocked_csr :159-201, spmv / spmvT :204-281) recorded by tests/golden/make_ref_csr_vectors.py
+    from the library compiled in place (oracle/_ref).  Runs wherever the repo is, also without /root/reference."""
+    O = oracle
+    g = np.load(GOLDEN_NPZ)
+    tag = f"bs{bs[0]}{bs[1]}"
+    row_ptr, cols = g["row_ptr"], g["cols"]
+    for name in ("csr", "blocked"):
+        rp, cl = (row_ptr, cols) if name == "csr" else (g[f"{tag}_scalar_row_ptr"], g[f"{tag}_scalar_cols"])
+        data = g[f"{tag}_{name}_data0"].copy()
+        for k in range(int(g[f"{tag}_{name}_nops"])):
+            O.insert_csr(name, data, cl, rp, g[f"{tag}_{name}_op{k}_x"], g[f"{tag}_{name}_op{k}_rows"],
+                         g[f"{tag}_{name}_op{k}_cols"], bs[0], bs[1], "add" if int(g[f"{tag}_{name}_op{k}_add"]) else "set")
+        assert np.array_equal(data, g[f"{tag}_{name}_data1"]), name
+    data = g[f"{tag}_nonblocked_data0"].copy()
+    O.insert_csr("nonblocked", data, cols, row_ptr, g[f"{tag}_nonblocked_x"], g[f"{tag}_nonblocked_rows"],
+                 g[f"{tag}_nonblocked_cols"], bs[0], bs[1], "add")
+    assert np.array_equal(data, g[f"{tag}_nonblocked_data1"])
+    y = g[f"{tag}_spmv_y0"].copy()
+    O.spmv(g[f"{tag}_spmv_vals"], row_ptr[:-1], row_ptr[1:], cols, g[f"{tag}_spmv_x"], y, bs[0], bs[1])
+    assert np.array_equal(y, g[f"{tag}_spmv_y1"])
+    yt = g[f"{tag}_spmvT_y0"].copy()
+    O.spmv(g[f"{tag}_spmv_vals"], row_ptr[:-1], row_ptr[1:], cols, g[f"{tag}_spmvT_x"], yt, bs[0], bs[1], transpose=True)
+    assert np.array_equal(yt, g[f"{tag}_spmvT_y1"])
+
+
 @pytest.mark.parametrize("degree", [1, 2])
 def test_action_and_functional_kernels(oracle, degree):
     """The matrix-free kernels of SURVEY.md §8f (cpp/demo/poisson_matrix_free/poisson.py): action(a, ui) equals the
